@@ -1,0 +1,307 @@
+"""Python host side above the C ABI: `Context` (thin RAII wrapper of sppm_ctx) and the
+reference-facing drivers `RayTracer` / `SPPMRayTracer` (Raytracer.h:82-419, 421-477).
+
+Everything that computes goes through libsppm_b200.so; a missing library or device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .scene import Camera, Scene
+
+
+class SppmError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def photon_range(onetime: int, rank: int, world: int):
+    """Contiguous photon-index range [begin, begin+count) of `rank` out of `world`
+    (photons of one round are split across GPUs; ids stay global)."""
+    base, rem = divmod(int(onetime), int(world))
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+class Context:
+    """One sppm_ctx = one CUDA device.  Methods map 1:1 onto include/sppm_b200.h."""
+
+    def __init__(self, device: int = 0, params: abi.SppmParams | None = None):
+        self.lib = abi.load_library()
+        h = C.c_void_p()
+        rc = self.lib.sppm_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise SppmError(f"sppm_ctx_create({device}) failed [{rc}]: {self.lib.sppm_last_error(None).decode()}")
+        self.h = h
+        self.params = abi.default_params()
+        if params is not None:
+            self.set_params(params)
+        self._scene_keep = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sppm_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise SppmError(f"{what} failed [{rc}]: {self.lib.sppm_last_error(self.h).decode()}")
+
+    # -- configuration
+    def set_params(self, p: abi.SppmParams):
+        self._ck(self.lib.sppm_set_params(self.h, C.byref(p)), "sppm_set_params")
+        self.params = p
+
+    def upload_scene(self, scene: Scene | abi.SppmSceneDesc):
+        desc = scene.flatten() if isinstance(scene, Scene) else scene
+        self._scene_keep = (scene, desc)
+        self._ck(self.lib.sppm_scene_upload(self.h, C.byref(desc)), "sppm_scene_upload")
+
+    # -- render path
+    def eye_pass(self, cam: Camera | abi.SppmCameraDesc, pass_id: int = 0) -> int:
+        d = cam.desc() if isinstance(cam, Camera) else cam
+        n = C.c_int64()
+        self._ck(self.lib.sppm_eye_pass(self.h, C.byref(d), pass_id, C.byref(n)), "sppm_eye_pass")
+        return n.value
+
+    def build_index(self):
+        self._ck(self.lib.sppm_build_index(self.h), "sppm_build_index")
+
+    def photon_pass(self, begin: int, count: int, pass_id: int):
+        self._ck(self.lib.sppm_photon_pass(self.h, begin, count, pass_id), "sppm_photon_pass")
+
+    def allreduce(self):
+        self._ck(self.lib.sppm_allreduce(self.h), "sppm_allreduce")
+
+    def update(self):
+        self._ck(self.lib.sppm_update(self.h), "sppm_update")
+
+    def resolve(self, cnt: int, onetime: int, w: int, h: int, out: np.ndarray | None = None) -> np.ndarray:
+        film = out if out is not None else np.empty((h, w, 3), dtype=np.float64)
+        assert film.flags.c_contiguous and film.dtype == np.float64 and film.shape == (h, w, 3)
+        self._ck(self.lib.sppm_resolve(self.h, cnt, onetime, film.ctypes.data), "sppm_resolve")
+        return film
+
+    def tonemap(self, film: np.ndarray, div: float) -> np.ndarray:
+        film = _f64(film)
+        h, w = film.shape[:2]
+        out = np.empty((h, w, 3), dtype=np.uint8)
+        self._ck(self.lib.sppm_tonemap(self.h, film.ctypes.data, w, h, float(div), out.ctypes.data), "sppm_tonemap")
+        return out
+
+    def synchronize(self):
+        self._ck(self.lib.sppm_device_synchronize(self.h), "sppm_device_synchronize")
+
+    def timer_record(self, slot: int):
+        self._ck(self.lib.sppm_timer_record(self.h, slot), "sppm_timer_record")
+
+    def timer_elapsed_ms(self) -> float:
+        ms = C.c_double()
+        self._ck(self.lib.sppm_timer_elapsed_ms(self.h, C.byref(ms)), "sppm_timer_elapsed_ms")
+        return ms.value
+
+    # -- multi-GPU
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.sppm_comm_unique_id(buf)
+        if rc != 0:
+            raise SppmError("sppm_comm_unique_id failed: libnccl.so.2 not loadable")
+        return buf.raw
+
+    def comm_init_rank(self, rank: int, nranks: int, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        self._ck(self.lib.sppm_comm_init_rank(self.h, rank, nranks, buf), "sppm_comm_init_rank")
+
+    def accum_device_ptrs(self):
+        a, b, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._ck(self.lib.sppm_accum_device_ptrs(self.h, C.byref(a), C.byref(b), C.byref(n)), "sppm_accum_device_ptrs")
+        return a.value, b.value, n.value
+
+    # -- hooks
+    def intersect_batch(self, rays6, ids=None, pass_id=0, node=0) -> np.ndarray:
+        rays6 = _f64(rays6, (-1, 6))
+        n = rays6.shape[0]
+        out = np.zeros(n, dtype=hit_dtype)
+        idp = None
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.uint64)
+            idp = ids.ctypes.data
+        self._ck(self.lib.sppm_intersect_batch(self.h, rays6.ctypes.data, n, idp, pass_id, node, out.ctypes.data),
+                 "sppm_intersect_batch")
+        return out
+
+    def bezier_patch_batch(self, rays6, patch_idx, seeds_uv=None) -> np.ndarray:
+        rays6 = _f64(rays6, (-1, 6))
+        n = rays6.shape[0]
+        patch_idx = np.ascontiguousarray(patch_idx, dtype=np.int32)
+        out = np.empty((n, 3), dtype=np.float64)
+        sp = None
+        if seeds_uv is not None:
+            seeds_uv = _f64(seeds_uv, (n, self.params.newton_restarts, 2))
+            sp = seeds_uv.ctypes.data
+        self._ck(self.lib.sppm_bezier_patch_batch(self.h, rays6.ctypes.data, patch_idx.ctypes.data, n, sp, out.ctypes.data),
+                 "sppm_bezier_patch_batch")
+        return out
+
+    def bezier_patch_bench(self, n: int, reps: int, seed: int = 1) -> float:
+        ms = C.c_double()
+        self._ck(self.lib.sppm_bezier_patch_bench(self.h, n, reps, seed, C.byref(ms)), "sppm_bezier_patch_bench")
+        return ms.value
+
+    def import_hitpoints(self, pos3, n3, wgt3, r2, pix, w, h):
+        pos3, n3, wgt3 = _f64(pos3, (-1, 3)), _f64(n3, (-1, 3)), _f64(wgt3, (-1, 3))
+        r2 = _f64(r2, (-1,))
+        pix = np.ascontiguousarray(pix, dtype=np.int32).reshape(-1, 2)
+        n = pos3.shape[0]
+        self._ck(self.lib.sppm_import_hitpoints(self.h, n, _ptr(pos3), _ptr(n3), _ptr(wgt3), _ptr(r2), _ptr(pix), w, h),
+                 "sppm_import_hitpoints")
+
+    def export_hitpoints(self):
+        n = C.c_int64()
+        self._ck(self.lib.sppm_export_hitpoints(self.h, 0, None, None, None, None, None, None, C.byref(n)), "sppm_export_hitpoints")
+        n = n.value
+        pos3, n3, wgt3 = (np.empty((n, 3)) for _ in range(3))
+        r2 = np.empty(n)
+        pix = np.empty((n, 2), dtype=np.int32)
+        node = np.empty(n, dtype=np.uint32)
+        m = C.c_int64()
+        self._ck(self.lib.sppm_export_hitpoints(self.h, n, _ptr(pos3), _ptr(n3), _ptr(wgt3), _ptr(r2), _ptr(pix), _ptr(node),
+                                                C.byref(m)), "sppm_export_hitpoints")
+        return dict(pos=pos3, n=n3, wgt=wgt3, r2=r2, pix=pix, node=node)
+
+    def gather_deposits(self, x3, n3, flux3):
+        x3, n3, flux3 = _f64(x3, (-1, 3)), _f64(n3, (-1, 3)), _f64(flux3, (-1, 3))
+        self._ck(self.lib.sppm_gather_deposits(self.h, x3.shape[0], _ptr(x3), _ptr(n3), _ptr(flux3)), "sppm_gather_deposits")
+
+    def export_stats(self, n: int):
+        newN, N = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+        r2, tao = np.zeros(n), np.zeros((n, 3))
+        self._ck(self.lib.sppm_export_stats(self.h, n, _ptr(newN), _ptr(N), _ptr(r2), _ptr(tao)), "sppm_export_stats")
+        return dict(newN=newN, N=N, r2=r2, tao=tao)
+
+    def keep_deposits(self, keep_all: bool):
+        self._ck(self.lib.sppm_keep_deposits(self.h, 1 if keep_all else 0), "sppm_keep_deposits")
+
+    def export_deposits(self):
+        m = C.c_int64()
+        self._ck(self.lib.sppm_export_deposits(self.h, 0, None, None, None, None, None, C.byref(m)), "sppm_export_deposits")
+        m = m.value
+        x3, n3, f3 = (np.empty((m, 3)) for _ in range(3))
+        pid = np.empty(m, dtype=np.uint64)
+        bounce = np.empty(m, dtype=np.int32)
+        mm = C.c_int64()
+        self._ck(self.lib.sppm_export_deposits(self.h, m, _ptr(x3), _ptr(n3), _ptr(f3), _ptr(pid), _ptr(bounce), C.byref(mm)),
+                 "sppm_export_deposits")
+        return dict(x=x3, n=n3, flux=f3, photon=pid, bounce=bounce)
+
+    def counters(self) -> dict:
+        c = abi.SppmCounters()
+        self._ck(self.lib.sppm_get_counters(self.h, C.byref(c)), "sppm_get_counters")
+        return c.as_dict()
+
+    def reset_counters(self):
+        self._ck(self.lib.sppm_reset_counters(self.h), "sppm_reset_counters")
+
+
+hit_dtype = np.dtype([("t", "f8"), ("pos", "f8", 3), ("n", "f8", 3), ("color", "f8", 3), ("u", "f8"), ("v", "f8"),
+                      ("obj", "i4"), ("patch", "i4"), ("inside", "i4"), ("pad", "i4")])
+assert hit_dtype.itemsize == C.sizeof(abi.SppmHit)
+
+
+class RayTracer:
+    """Raytracer.h:82-419.  `rt.camera = cam; rt.scene = scene; rt.render()` as in the
+    reference (Raytracer.h:439-445); the film lands in `camera.pic`.
+
+    cnt / onetime default to the reference's literals (Raytracer.h:218, 384).  With
+    world > 1 every rank traces its share of each round's photons and the per-round
+    accumulators are summed over ranks (NCCL) before HitPoint::update."""
+
+    def __init__(self, ctx: Context | None = None, device: int = 0, rank: int = 0, world: int = 1):
+        self.ctx = ctx if ctx is not None else Context(device)
+        self.camera: Camera | None = None
+        self.scene: Scene | None = None
+        self.cnt = 10000
+        self.onetime = 100
+        self.pass_base = 0
+        self.rank, self.world = rank, world
+        self.n_hitpoints = 0
+        self._scene_uploaded = None
+
+    def GetHitPoint(self):  # Raytracer.h:102-116
+        if self._scene_uploaded is not self.scene:
+            self.ctx.upload_scene(self.scene)
+            self._scene_uploaded = self.scene
+        self.n_hitpoints = self.ctx.eye_pass(self.camera, self.pass_base)
+        return self.n_hitpoints
+
+    def PhotonMap(self, cnt: int):  # Raytracer.h:210-295
+        begin, count = photon_range(self.onetime, self.rank, self.world)
+        for i in range(cnt):
+            self.ctx.photon_pass(begin, count, self.pass_base * cnt + i)
+            if self.world > 1:
+                self.ctx.allreduce()
+            self.ctx.update()
+        self.ctx.resolve(cnt, self.onetime, self.camera.w, self.camera.h, out=self.camera.pic)
+
+    def render(self):  # Raytracer.h:366-387
+        self.GetHitPoint()
+        self.ctx.build_index()
+        self.PhotonMap(self.cnt)
+
+
+class SPPMRayTracer:
+    """Raytracer.h:421-477: outer loop over jittered replicas, film accumulation, tone map.
+    The reference loops 100000 times; `sppmtime` bounds it here.  One device runs the
+    `replicas` RayTracers of an iteration back to back (the reference's 4 OpenMP threads)."""
+
+    def __init__(self, ctx: Context | None = None, device: int = 0):
+        self.ctx = ctx if ctx is not None else Context(device)
+        self.sppmtime = 1
+        self.replicas = 4
+        self.cnt = 10000
+        self.onetime = 100
+        self.jitter = 0.00015
+        self.image = None
+
+    def render(self, scene: Scene, camera: Camera):
+        from .rng import unit_rand_vec, P_JITTER
+        seed = self.ctx.params.seed
+        for i in range(self.sppmtime):
+            for j in range(self.replicas):
+                c = camera.copy()
+                if self.jitter:
+                    c.MoveTo(camera.pos + self.jitter * unit_rand_vec(seed, i, j, P_JITTER))
+                c.lookAt(camera.look, 1.)
+                rt = RayTracer(self.ctx)
+                rt._scene_uploaded = scene if (i or j) else None
+                rt.camera, rt.scene, rt.cnt, rt.onetime = c, scene, self.cnt, self.onetime
+                rt.pass_base = i * self.replicas + j
+                rt.render()
+                camera.pic += c.pic  # Raytracer.h:449-458
+            self.image = self.ctx.tonemap(camera.pic, (i + 1) * float(self.replicas))  # Raytracer.h:460-470
+        return self.image

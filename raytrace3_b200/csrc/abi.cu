@@ -1,0 +1,813 @@
+// abi.cu — the extern "C" boundary of libsppm_b200.so (include/sppm_b200.h) and the
+// host-side orchestration of one render pass.  No CPU compute path exists here: every
+// entry point that produces results launches the sm_100a kernels of trace.cu / gather.cu.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "ctx.h"
+
+using namespace sppm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int fail(sppm_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+int cuda_fail(sppm_ctx* c, cudaError_t e, const char* where) {
+  return fail(c, SPPM_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CU(c, x)                                        \
+  do {                                                  \
+    cudaError_t e__ = (x);                              \
+    if (e__ != cudaSuccess) return cuda_fail(c, e__, #x); \
+  } while (0)
+
+struct Bind {  // make the context's device current for the duration of a call
+  int prev = -1;
+  explicit Bind(const sppm_ctx* c) {
+    cudaGetDevice(&prev);
+    if (prev != c->device) cudaSetDevice(c->device);
+    else prev = -1;
+  }
+  ~Bind() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+constexpr uint64_t PHOTON_BATCH = 1ull << 21;  // photons traced per kernel launch (all lights)
+
+unsigned long long* scalars(sppm_ctx* c) { return (unsigned long long*)c->dev_scalars.p; }
+
+// pending per-phase timings are folded into the host counters at the next sync point
+struct Pending {
+  bool trace = false, sg = false;
+};
+thread_local Pending g_unused;
+
+void fold_timings(sppm_ctx* c, bool trace, bool sg) {
+  float ms = 0;
+  if (trace && cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]) == cudaSuccess) c->host_counters.ms_trace += ms;
+  if (sg) {
+    if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->host_counters.ms_sort += ms;
+    if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->host_counters.ms_gather += ms;
+  }
+}
+
+__global__ void tonemap_kernel(const double* film, int w, int h, double div, uint8_t* bgr) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)w * h * 3) return;
+  const int k = (int)(t % 3);
+  const long long p = t / 3;
+  const int j = (int)(p % w), i1 = (int)(p / w);
+  const double x = film[t] / div;
+  const int v = (int)(pow(1 - exp(-x), 1 / 2.2) * 255 + .5);  // toInt (Raytracer.h:24-26)
+  bgr[((size_t)(h - 1 - i1) * w + j) * 3 + k] = (uint8_t)v;    // row flip (Raytracer.h:467)
+}
+
+__global__ void synth_pairs_kernel(DevScene s, long long n, uint64_t seed, double* rays6, int32_t* patch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int gp = (int)(i % s.n_patch);
+  const double* b = s.patchBox + (size_t)gp * 6;
+  double u0, u1, u2, u3;
+  draw2(seed, 1, (uint64_t)i, 0, 6, 0, 0, u0, u1);
+  draw2(seed, 1, (uint64_t)i, 0, 6, 1, 0, u2, u3);
+  const d3 tgt = mk(b[0] + (b[3] - b[0]) * u0, b[1] + (b[4] - b[1]) * u1, b[2] + (b[5] - b[2]) * u2);
+  const d3 dirv = unit_rand_vec(seed, 2, (uint64_t)i, 6);
+  const d3 org = tgt + dirv * (40.0 + 40.0 * u3);
+  const d3 dir = get_unit(tgt - org);
+  rays6[6 * i + 0] = org.x; rays6[6 * i + 1] = org.y; rays6[6 * i + 2] = org.z;
+  rays6[6 * i + 3] = dir.x; rays6[6 * i + 4] = dir.y; rays6[6 * i + 5] = dir.z;
+  patch[i] = gp;
+}
+
+// ---- NCCL through dlopen (torch ships libnccl.so.2; nothing is linked) -------------------
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.h || api.ok) return api;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    api.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.h) break;
+  }
+  if (!api.h) return api;
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
+  api.AllReduce = (decltype(api.AllReduce))dlsym(api.h, "ncclAllReduce");
+  api.GroupStart = (decltype(api.GroupStart))dlsym(api.h, "ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.h, "ncclGroupEnd");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.GroupStart && api.GroupEnd && api.CommDestroy;
+  return api;
+}
+
+void free_scene(sppm_ctx* c) {
+  for (auto& b : c->scene_bufs) dev_free(b);
+  c->scene_bufs.clear();
+  c->scene_ok = false;
+}
+template <class T>
+cudaError_t upload(sppm_ctx* c, const std::vector<T>& v, const T** out) {
+  DevBuf b;
+  cudaError_t e = dev_reserve(b, std::max<size_t>(v.size() * sizeof(T), 16));
+  if (e) return e;
+  c->scene_bufs.push_back(b);
+  if (!v.empty()) e = cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+  *out = (const T*)b.p;
+  return e;
+}
+
+int ensure_deposit_capacity(sppm_ctx* c, int64_t cap) {
+  if (cap <= c->dep_cap) return SPPM_OK;
+  CU(c, dev_reserve(c->dep_raw, (size_t)cap * sizeof(Deposit)));
+  CU(c, dev_reserve(c->dep_key, (size_t)cap * 4));
+  c->dep_cap = cap;
+  return SPPM_OK;
+}
+
+// canonical export order = ascending okey
+std::vector<int64_t> canonical_order(const std::vector<uint64_t>& okey) {
+  std::vector<int64_t> ord(okey.size());
+  std::iota(ord.begin(), ord.end(), 0);
+  std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return okey[a] < okey[b]; });
+  return ord;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sppm_abi_version(void) { return SPPM_ABI_VERSION; }
+
+const char* sppm_last_error(const sppm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sppm_default_params(SppmParams* p) {
+  if (!p) return SPPM_ERR_INVALID;
+  p->init_r2 = 2.0;
+  p->alpha = 0.7;
+  p->max_dep = 13;
+  p->newton_iters = 10;
+  p->newton_restarts = 50;
+  p->update_mode = SPPM_UPDATE_REFERENCE;
+  p->newton_mode = SPPM_NEWTON_EXACT;
+  p->reserved = 0;
+  p->seed = 0x5EED5EEDull;
+  return SPPM_OK;
+}
+
+int sppm_ctx_create(int device, sppm_ctx** out) {
+  if (!out) return fail(nullptr, SPPM_ERR_INVALID, "out is null");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return fail(nullptr, SPPM_ERR_NO_DEVICE,
+                std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, SPPM_ERR_INVALID, "device index out of range");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device))) return cuda_fail(nullptr, e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(nullptr, SPPM_ERR_NO_DEVICE,
+                std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                    "; libsppm_b200 carries sm_100a code only");
+  sppm_ctx* c = new sppm_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  sppm_default_params(&c->prm);
+  if ((e = cudaSetDevice(device))) {
+    delete c;
+    return cuda_fail(nullptr, e, "cudaSetDevice");
+  }
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 8 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  ok = ok && dev_reserve(c->dev_scalars, 64) == cudaSuccess && dev_reserve(c->counters, sizeof(DevCounters)) == cudaSuccess;
+  if (ok) {
+    cudaMemset(c->dev_scalars.p, 0, 64);
+    cudaMemset(c->counters.p, 0, sizeof(DevCounters));
+  }
+  if (!ok) {
+    e = cudaGetLastError();
+    sppm_ctx_destroy(c);
+    return cuda_fail(nullptr, e, "context allocation");
+  }
+  *out = c;
+  return SPPM_OK;
+}
+
+void sppm_ctx_destroy(sppm_ctx* c) {
+  if (!c) return;
+  Bind b(c);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->nccl_comm && nccl().ok) nccl().CommDestroy((ncclComm_t)c->nccl_comm);
+  free_scene(c);
+  DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->dep_raw,
+                    &c->dep_sorted, &c->dep_key, &c->dep_key2, &c->dep_idx, &c->dep_idx2, &c->dep_start, &c->cub_tmp,
+                    &c->dev_scalars, &c->counters, &c->film, &c->scratch};
+  for (DevBuf* d : bufs) dev_free(*d);
+  for (int i = 0; i < 8; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int sppm_set_params(sppm_ctx* c, const SppmParams* p) {
+  if (!c || !p) return SPPM_ERR_INVALID;
+  if (p->max_dep < 0 || p->max_dep > 13) return fail(c, SPPM_ERR_INVALID, "max_dep must be in [0,13]");
+  if (p->newton_restarts < 1 || p->newton_restarts > 4095) return fail(c, SPPM_ERR_INVALID, "newton_restarts out of range");
+  if (p->newton_iters < 1) return fail(c, SPPM_ERR_INVALID, "newton_iters must be >= 1");
+  if (!(p->init_r2 > 0)) return fail(c, SPPM_ERR_INVALID, "init_r2 must be > 0");
+  c->prm = *p;
+  return SPPM_OK;
+}
+
+int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
+  if (!c || !s) return SPPM_ERR_INVALID;
+  if (s->n_objects < 0 || s->n_objects > MAX_OBJECTS) return fail(c, SPPM_ERR_INVALID, "n_objects out of range (max 64)");
+  if (s->n_patches < 0 || s->n_patches >= (1 << 16)) return fail(c, SPPM_ERR_INVALID, "n_patches out of range");
+  Bind b(c);
+  CU(c, cudaStreamSynchronize(c->stream));
+  free_scene(c);
+  // per-patch AABBs (Bezier.h:165-175) and per-object AABBs (Bezier.h:219-222), addpoint semantics
+  std::vector<double> patchP((size_t)s->n_patches * 48), patchBox((size_t)s->n_patches * 6);
+  for (int p = 0; p < s->n_patches; p++) {
+    double* bx = &patchBox[(size_t)p * 6];
+    for (int k = 0; k < 3; k++) {
+      bx[k] = SPPM_MAX_NUM;
+      bx[3 + k] = SPPM_MIN_NUM;
+    }
+    for (int q = 0; q < 16; q++)
+      for (int k = 0; k < 3; k++) {
+        const double v = s->patches[((size_t)p * 16 + q) * 3 + k];
+        patchP[((size_t)p * 16 + q) * 3 + k] = v;
+        if (bx[k] > v) bx[k] = v;
+        if (bx[3 + k] < v) bx[3 + k] = v;
+      }
+  }
+  std::vector<DevObject> objs(s->n_objects);
+  for (int i = 0; i < s->n_objects; i++) {
+    const SppmObject& o = s->objects[i];
+    DevObject d;
+    memset(&d, 0, sizeof(d));
+    d.kind = o.kind;
+    d.tex_id = o.tex_id;
+    d.first_patch = o.first_patch;
+    d.n_patch = o.n_patch;
+    if (o.kind < 0 || o.kind > 2) return fail(c, SPPM_ERR_INVALID, "bad object kind");
+    if (o.tex_id >= s->n_textures) return fail(c, SPPM_ERR_INVALID, "tex_id out of range");
+    if (o.kind == SPPM_OBJ_BEZIER && (o.first_patch < 0 || o.n_patch < 0 || o.first_patch + o.n_patch > s->n_patches))
+      return fail(c, SPPM_ERR_INVALID, "bezier patch range out of bounds");
+    const d3 df = ld3(o.mat.diff), rl = ld3(o.mat.refl), rr = ld3(o.mat.refr);
+    d.isDiff = !is_zero3(df);
+    d.isRefl = !is_zero3(rl);
+    d.isRefr = !is_zero3(rr);
+    d.diffr = (df.x + df.y + df.z) / 3;  // Vec3.h:116-119
+    d.reflr = (rl.x + rl.y + rl.z) / 3;
+    d.refrr = (rr.x + rr.y + rr.z) / 3;
+    d.allr = d.diffr + d.reflr + d.refrr;
+    for (int k = 0; k < 3; k++) {
+      d.diff[k] = o.mat.diff[k];
+      d.refl[k] = o.mat.refl[k];
+      d.refr[k] = o.mat.refr[k];
+      d.color[k] = o.color[k];
+      d.p0[k] = o.p0[k];
+      d.norm[k] = o.norm[k];
+      d.texU[k] = o.texU[k];
+      d.texV[k] = o.texV[k];
+    }
+    d.refrn = o.mat.refrn;
+    d.radius = o.radius;
+    const d3 w = cross3(ld3(o.texU), ld3(o.texV));
+    d.texW[0] = w.x; d.texW[1] = w.y; d.texW[2] = w.z;
+    d.texUmod = module(ld3(o.texU));
+    d.texVmod = module(ld3(o.texV));
+    int ndir = 0;  // Obj.h:89-96
+    for (int k = 0; k < 3; k++)
+      if (o.norm[k] != 0) ndir = k;
+    d.vdex = (ndir + 2) % 3;
+    d.udex = (ndir + 1) % 3;
+    for (int k = 0; k < 3; k++) {
+      d.box[k] = SPPM_MAX_NUM;
+      d.box[3 + k] = SPPM_MIN_NUM;
+    }
+    if (o.kind == SPPM_OBJ_BEZIER)
+      for (int p = o.first_patch; p < o.first_patch + o.n_patch; p++)
+        for (int k = 0; k < 3; k++) {
+          d.box[k] = std::min(d.box[k], patchBox[(size_t)p * 6 + k]);
+          d.box[3 + k] = std::max(d.box[3 + k], patchBox[(size_t)p * 6 + 3 + k]);
+        }
+    objs[i] = d;
+  }
+  std::vector<SppmLight> lights(s->lights, s->lights + s->n_lights);
+  std::vector<DevTexture> tex(s->n_textures);
+  for (int t = 0; t < s->n_textures; t++) {
+    const SppmTexture& ht = s->textures[t];
+    if (ht.rows <= 0 || ht.cols <= 0 || !ht.bgr8) return fail(c, SPPM_ERR_INVALID, "empty texture (Q18: the reference would read out of range)");
+    DevBuf tb;
+    const size_t bytes = (size_t)ht.rows * ht.cols * 3;
+    CU(c, dev_reserve(tb, bytes));
+    c->scene_bufs.push_back(tb);
+    CU(c, cudaMemcpyAsync(tb.p, ht.bgr8, bytes, cudaMemcpyHostToDevice, c->stream));
+    tex[t].rows = ht.rows;
+    tex[t].cols = ht.cols;
+    tex[t].bgr = (const uint8_t*)tb.p;
+  }
+  DevScene ds;
+  ds.n_obj = s->n_objects;
+  ds.n_patch = s->n_patches;
+  ds.n_light = s->n_lights;
+  ds.n_tex = s->n_textures;
+  CU(c, upload(c, objs, &ds.obj));
+  CU(c, upload(c, patchP, &ds.patchP));
+  CU(c, upload(c, patchBox, &ds.patchBox));
+  CU(c, upload(c, lights, &ds.lights));
+  CU(c, upload(c, tex, &ds.tex));
+  CU(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
+  c->scene = ds;
+  CU(c, trace_configure(c));
+  c->scene_ok = true;
+  return SPPM_OK;
+}
+
+int sppm_eye_pass(sppm_ctx* c, const SppmCameraDesc* cam, uint64_t pass_id, int64_t* n_hitpoints) {
+  if (!c || !cam) return SPPM_ERR_INVALID;
+  if (!c->scene_ok) return fail(c, SPPM_ERR_INVALID, "sppm_scene_upload must be called first");
+  if (cam->w <= 0 || cam->h <= 0) return fail(c, SPPM_ERR_INVALID, "bad film size");
+  Bind b(c);
+  const int64_t npix = (int64_t)cam->w * cam->h;
+  c->hp_cap = npix * 4 + 1024;
+  CU(c, dev_reserve(c->hp_raw, (size_t)c->hp_cap * sizeof(HpRaw)));
+  c->film_w = cam->w;
+  c->film_h = cam->h;
+  c->index_ok = false;
+  CU(c, cudaMemsetAsync(scalars(c), 0, 8, c->stream));
+  CU(c, cudaEventRecord(c->ev[4], c->stream));
+  CU(c, launch_eye_pass(c, *cam, pass_id));
+  CU(c, cudaEventRecord(c->ev[5], c->stream));
+  unsigned long long n = 0;
+  CU(c, cudaMemcpyAsync(&n, scalars(c), 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+  c->host_counters.ms_eye = ms;
+  if ((int64_t)n > c->hp_cap) return fail(c, SPPM_ERR_CAPACITY, "hit-point buffer overflow (more than 4 hit points per pixel)");
+  c->n_hp = (int64_t)n;
+  if (n_hitpoints) *n_hitpoints = c->n_hp;
+  return SPPM_OK;
+}
+
+int sppm_build_index(sppm_ctx* c) {
+  if (!c) return SPPM_ERR_INVALID;
+  Bind b(c);
+  CU(c, cudaEventRecord(c->ev[4], c->stream));
+  CU(c, build_index(c));
+  CU(c, cudaEventRecord(c->ev[5], c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+  c->host_counters.ms_build = ms;
+  return SPPM_OK;
+}
+
+int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, uint64_t pass_id) {
+  if (!c) return SPPM_ERR_INVALID;
+  if (!c->scene_ok) return fail(c, SPPM_ERR_INVALID, "sppm_scene_upload must be called first");
+  if (!c->index_ok && !c->keep_all_deposits) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
+  if (c->scene.n_light <= 0 || photon_count == 0) return SPPM_OK;
+  if (photon_begin + photon_count > (1ull << 40)) return fail(c, SPPM_ERR_INVALID, "photon index exceeds 2^40");
+  Bind b(c);
+  const uint64_t per_light_batch = std::max<uint64_t>(1, PHOTON_BATCH / (uint64_t)c->scene.n_light);
+  bool pend_sg = false;
+  for (uint64_t off = 0; off < photon_count; off += per_light_batch) {
+    const uint64_t cnt = std::min(per_light_batch, photon_count - off);
+    const int64_t cap = (int64_t)(cnt * c->scene.n_light) * (c->prm.max_dep + 1);
+    int rc = ensure_deposit_capacity(c, cap);
+    if (rc) return rc;
+    CU(c, cudaMemsetAsync(scalars(c) + 1, 0, 16, c->stream));  // deposit count, photon cursor
+    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    CU(c, launch_photon_trace(c, photon_begin + off, cnt, pass_id));
+    CU(c, cudaEventRecord(c->ev[4], c->stream));
+    unsigned long long m = 0;
+    CU(c, cudaMemcpyAsync(&m, scalars(c) + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    fold_timings(c, true, pend_sg);
+    pend_sg = false;
+    if ((int64_t)m > c->dep_cap) return fail(c, SPPM_ERR_CAPACITY, "deposit buffer overflow");
+    c->n_dep = (int64_t)m;
+    if (c->index_ok && m > 0 && c->n_hp > 0) {
+      CU(c, sort_and_gather(c, (int64_t)m));
+      pend_sg = true;
+    }
+  }
+  if (pend_sg) {  // timings of the last batch need its events to complete
+    CU(c, cudaEventSynchronize(c->ev[3]));
+    fold_timings(c, false, true);
+  }
+  return SPPM_OK;
+}
+
+int sppm_allreduce(sppm_ctx* c) {
+  if (!c) return SPPM_ERR_INVALID;
+  if (!c->nccl_comm || c->nranks <= 1 || c->n_hp == 0) return SPPM_OK;
+  Bind b(c);
+  NcclApi& n = nccl();
+  ncclResult_t r = n.GroupStart();
+  if (r == ncclSuccess) r = n.AllReduce(c->soa.dN, c->soa.dN, (size_t)c->n_hp, ncclInt32, ncclSum, (ncclComm_t)c->nccl_comm, c->stream);
+  if (r == ncclSuccess)
+    r = n.AllReduce(c->soa.dtao, c->soa.dtao, (size_t)c->n_hp * 3, ncclFloat64, ncclSum, (ncclComm_t)c->nccl_comm, c->stream);
+  ncclResult_t r2 = n.GroupEnd();
+  if (r == ncclSuccess) r = r2;
+  if (r != ncclSuccess) return fail(c, SPPM_ERR_NCCL, std::string("ncclAllReduce: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
+  return SPPM_OK;
+}
+
+int sppm_update(sppm_ctx* c) {
+  if (!c) return SPPM_ERR_INVALID;
+  if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
+  Bind b(c);
+  CU(c, launch_update(c));
+  return SPPM_OK;
+}
+
+int sppm_resolve(sppm_ctx* c, int32_t cnt, int32_t onetime, double* film_hw3) {
+  if (!c || !film_hw3) return SPPM_ERR_INVALID;
+  if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
+  Bind b(c);
+  CU(c, cudaEventRecord(c->ev[4], c->stream));
+  CU(c, launch_resolve(c, cnt, onetime));
+  CU(c, cudaEventRecord(c->ev[5], c->stream));
+  CU(c, cudaMemcpyAsync(film_hw3, c->film.p, (size_t)c->film_w * c->film_h * 24, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+  c->host_counters.ms_resolve = ms;
+  return SPPM_OK;
+}
+
+int sppm_tonemap(sppm_ctx* c, const double* film_hw3, int32_t w, int32_t h, double div, uint8_t* bgr_hw3) {
+  if (!c || !film_hw3 || !bgr_hw3 || w <= 0 || h <= 0) return SPPM_ERR_INVALID;
+  Bind b(c);
+  const size_t n = (size_t)w * h * 3;
+  CU(c, dev_reserve(c->film, n * 8));
+  CU(c, dev_reserve(c->scratch, n));
+  CU(c, cudaMemcpyAsync(c->film.p, film_hw3, n * 8, cudaMemcpyHostToDevice, c->stream));
+  tonemap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const double*)c->film.p, w, h, div, (uint8_t*)c->scratch.p);
+  c->host_counters.launches++;
+  CU(c, cudaGetLastError());
+  CU(c, cudaMemcpyAsync(bgr_hw3, c->scratch.p, n, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SPPM_OK;
+}
+
+int sppm_comm_unique_id(void* id128) {
+  if (!id128) return SPPM_ERR_INVALID;
+  NcclApi& n = nccl();
+  if (!n.ok) return SPPM_ERR_NCCL;
+  ncclUniqueId id;
+  if (n.GetUniqueId(&id) != ncclSuccess) return SPPM_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id128, &id, 128);
+  return SPPM_OK;
+}
+
+int sppm_comm_init_rank(sppm_ctx* c, int rank, int nranks, const void* id128) {
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return SPPM_ERR_INVALID;
+  NcclApi& n = nccl();
+  if (!n.ok) return fail(c, SPPM_ERR_NCCL, "libnccl.so.2 not found (dlopen)");
+  Bind b(c);
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclComm_t comm;
+  ncclResult_t r = n.CommInitRank(&comm, nranks, id, rank);
+  if (r != ncclSuccess) return fail(c, SPPM_ERR_NCCL, std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
+  c->nccl_comm = comm;
+  c->nranks = nranks;
+  c->rank = rank;
+  return SPPM_OK;
+}
+
+int sppm_accum_device_ptrs(sppm_ctx* c, void** dN, void** dtao, int64_t* n) {
+  if (!c) return SPPM_ERR_INVALID;
+  if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
+  if (dN) *dN = c->soa.dN;
+  if (dtao) *dtao = c->soa.dtao;
+  if (n) *n = c->n_hp;
+  return SPPM_OK;
+}
+
+int sppm_device_synchronize(sppm_ctx* c) {
+  if (!c) return SPPM_ERR_INVALID;
+  Bind b(c);
+  CU(c, cudaStreamSynchronize(c->stream));
+  return SPPM_OK;
+}
+
+void* sppm_stream_handle(sppm_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+/* CUDA-event stopwatch on the context's stream (slots 0..1 of ev[6..7]). */
+int sppm_timer_record(sppm_ctx* c, int slot) {
+  if (!c || slot < 0 || slot > 1) return SPPM_ERR_INVALID;
+  Bind b(c);
+  CU(c, cudaEventRecord(c->ev[6 + slot], c->stream));
+  return SPPM_OK;
+}
+int sppm_timer_elapsed_ms(sppm_ctx* c, double* ms) {
+  if (!c || !ms) return SPPM_ERR_INVALID;
+  Bind b(c);
+  CU(c, cudaEventSynchronize(c->ev[7]));
+  float f = 0;
+  CU(c, cudaEventElapsedTime(&f, c->ev[6], c->ev[7]));
+  *ms = f;
+  return SPPM_OK;
+}
+
+// ---- test / measurement hooks ------------------------------------------------------------
+int sppm_intersect_batch(sppm_ctx* c, const double* rays6, int64_t n, const uint64_t* ids, uint64_t pass_id,
+                         int32_t node, SppmHit* out) {
+  if (!c || !rays6 || !out || n < 0) return SPPM_ERR_INVALID;
+  if (!c->scene_ok) return fail(c, SPPM_ERR_INVALID, "sppm_scene_upload must be called first");
+  if (n == 0) return SPPM_OK;
+  Bind b(c);
+  DevBuf dr, di, dout;
+  int rc = SPPM_OK;
+  cudaError_t e;
+  do {
+    if ((e = dev_reserve(dr, (size_t)n * 48))) break;
+    if ((e = dev_reserve(dout, (size_t)n * sizeof(SppmHit)))) break;
+    if (ids && (e = dev_reserve(di, (size_t)n * 8))) break;
+    if ((e = cudaMemcpyAsync(dr.p, rays6, (size_t)n * 48, cudaMemcpyHostToDevice, c->stream))) break;
+    if (ids && (e = cudaMemcpyAsync(di.p, ids, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream))) break;
+    if ((e = launch_intersect(c, (const double*)dr.p, n, ids ? (const uint64_t*)di.p : nullptr, pass_id, node, (SppmHit*)dout.p))) break;
+    if ((e = cudaMemcpyAsync(out, dout.p, (size_t)n * sizeof(SppmHit), cudaMemcpyDeviceToHost, c->stream))) break;
+    e = cudaStreamSynchronize(c->stream);
+  } while (0);
+  if (e) rc = cuda_fail(c, e, "sppm_intersect_batch");
+  dev_free(dr);
+  dev_free(di);
+  dev_free(dout);
+  return rc;
+}
+
+int sppm_bezier_patch_batch(sppm_ctx* c, const double* rays6, const int32_t* patch_idx, int64_t n, const double* seeds_uv,
+                            double* tuv_out) {
+  if (!c || !rays6 || !patch_idx || !tuv_out || n < 0) return SPPM_ERR_INVALID;
+  if (!c->scene_ok) return fail(c, SPPM_ERR_INVALID, "sppm_scene_upload must be called first");
+  for (int64_t i = 0; i < n; i++)
+    if (patch_idx[i] < 0 || patch_idx[i] >= c->scene.n_patch) return fail(c, SPPM_ERR_INVALID, "patch index out of range");
+  if (n == 0) return SPPM_OK;
+  Bind b(c);
+  DevBuf dr, dp, ds, dt;
+  int rc = SPPM_OK;
+  cudaError_t e;
+  const size_t sbytes = (size_t)n * c->prm.newton_restarts * 16;
+  do {
+    if ((e = dev_reserve(dr, (size_t)n * 48))) break;
+    if ((e = dev_reserve(dp, (size_t)n * 4))) break;
+    if ((e = dev_reserve(dt, (size_t)n * 24))) break;
+    if (seeds_uv && (e = dev_reserve(ds, sbytes))) break;
+    if ((e = cudaMemcpyAsync(dr.p, rays6, (size_t)n * 48, cudaMemcpyHostToDevice, c->stream))) break;
+    if ((e = cudaMemcpyAsync(dp.p, patch_idx, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream))) break;
+    if (seeds_uv && (e = cudaMemcpyAsync(ds.p, seeds_uv, sbytes, cudaMemcpyHostToDevice, c->stream))) break;
+    if ((e = launch_patch_batch(c, (const double*)dr.p, (const int32_t*)dp.p, n, seeds_uv ? (const double*)ds.p : nullptr, (double*)dt.p))) break;
+    if ((e = cudaMemcpyAsync(tuv_out, dt.p, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream))) break;
+    e = cudaStreamSynchronize(c->stream);
+  } while (0);
+  if (e) rc = cuda_fail(c, e, "sppm_bezier_patch_batch");
+  dev_free(dr);
+  dev_free(dp);
+  dev_free(ds);
+  dev_free(dt);
+  return rc;
+}
+
+int sppm_bezier_patch_bench(sppm_ctx* c, int64_t n, int32_t reps, uint64_t seed, double* ms_per_rep) {
+  if (!c || n <= 0 || reps <= 0 || !ms_per_rep) return SPPM_ERR_INVALID;
+  if (!c->scene_ok || c->scene.n_patch <= 0) return fail(c, SPPM_ERR_INVALID, "a scene with Bezier patches must be uploaded first");
+  Bind b(c);
+  DevBuf dr, dp, dt;
+  int rc = SPPM_OK;
+  cudaError_t e;
+  do {
+    if ((e = dev_reserve(dr, (size_t)n * 48))) break;
+    if ((e = dev_reserve(dp, (size_t)n * 4))) break;
+    if ((e = dev_reserve(dt, (size_t)n * 24))) break;
+    synth_pairs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->scene, n, seed, (double*)dr.p, (int32_t*)dp.p);
+    if ((e = cudaGetLastError())) break;
+    if ((e = launch_patch_batch(c, (const double*)dr.p, (const int32_t*)dp.p, n, nullptr, (double*)dt.p))) break;  // warm-up
+    if ((e = cudaEventRecord(c->ev[4], c->stream))) break;
+    for (int r = 0; r < reps && !e; r++) e = launch_patch_batch(c, (const double*)dr.p, (const int32_t*)dp.p, n, nullptr, (double*)dt.p);
+    if (e) break;
+    if ((e = cudaEventRecord(c->ev[5], c->stream))) break;
+    if ((e = cudaStreamSynchronize(c->stream))) break;
+    float ms = 0;
+    if ((e = cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]))) break;
+    *ms_per_rep = ms / reps;
+  } while (0);
+  if (e) rc = cuda_fail(c, e, "sppm_bezier_patch_bench");
+  dev_free(dr);
+  dev_free(dp);
+  dev_free(dt);
+  return rc;
+}
+
+int sppm_import_hitpoints(sppm_ctx* c, int64_t n, const double* pos3, const double* n3, const double* wgt3,
+                          const double* r2, const int32_t* pix, int32_t w, int32_t h) {
+  if (!c || n < 0 || w <= 0 || h <= 0) return SPPM_ERR_INVALID;
+  if (n > 0 && (!pos3 || !n3 || !wgt3 || !r2 || !pix)) return SPPM_ERR_INVALID;
+  Bind b(c);
+  std::vector<HpRaw> raw((size_t)n);
+  for (int64_t i = 0; i < n; i++) {
+    HpRaw& r = raw[i];
+    for (int k = 0; k < 3; k++) {
+      r.pos[k] = pos3[3 * i + k];
+      r.n[k] = n3[3 * i + k];
+      r.wgt[k] = wgt3[3 * i + k];
+    }
+    r.r2 = r2[i];
+    r.row = pix[2 * i];
+    r.col = pix[2 * i + 1];
+    if (r.row < 0 || r.row >= h || r.col < 0 || r.col >= w) return fail(c, SPPM_ERR_INVALID, "hit-point pixel outside the film");
+    r.okey = (uint64_t)i;
+  }
+  c->hp_cap = std::max<int64_t>(n, 1);
+  CU(c, dev_reserve(c->hp_raw, (size_t)c->hp_cap * sizeof(HpRaw)));
+  if (n) CU(c, cudaMemcpyAsync(c->hp_raw.p, raw.data(), (size_t)n * sizeof(HpRaw), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->n_hp = n;
+  c->film_w = w;
+  c->film_h = h;
+  c->index_ok = false;
+  return SPPM_OK;
+}
+
+int sppm_export_hitpoints(sppm_ctx* c, int64_t cap, double* pos3, double* n3, double* wgt3, double* r2, int32_t* pix,
+                          uint32_t* node, int64_t* n_out) {
+  if (!c) return SPPM_ERR_INVALID;
+  Bind b(c);
+  const int64_t n = c->n_hp;
+  if (n_out) *n_out = n;
+  if (n == 0) return SPPM_OK;
+  std::vector<HpRaw> raw((size_t)n);
+  CU(c, cudaMemcpyAsync(raw.data(), c->hp_raw.p, (size_t)n * sizeof(HpRaw), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  std::vector<uint64_t> okey((size_t)n);
+  for (int64_t i = 0; i < n; i++) okey[i] = raw[i].okey;
+  const std::vector<int64_t> ord = canonical_order(okey);
+  for (int64_t j = 0; j < std::min(n, cap); j++) {
+    const HpRaw& r = raw[ord[j]];
+    for (int k = 0; k < 3; k++) {
+      if (pos3) pos3[3 * j + k] = r.pos[k];
+      if (n3) n3[3 * j + k] = r.n[k];
+      if (wgt3) wgt3[3 * j + k] = r.wgt[k];
+    }
+    if (r2) r2[j] = r.r2;
+    if (pix) {
+      pix[2 * j] = r.row;
+      pix[2 * j + 1] = r.col;
+    }
+    if (node) node[j] = (uint32_t)(r.okey & 0xfffffu);
+  }
+  return SPPM_OK;
+}
+
+int sppm_gather_deposits(sppm_ctx* c, int64_t m, const double* x3, const double* n3, const double* flux3) {
+  if (!c || m < 0) return SPPM_ERR_INVALID;
+  if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
+  if (m == 0) return SPPM_OK;
+  if (!x3 || !n3 || !flux3) return SPPM_ERR_INVALID;
+  Bind b(c);
+  int rc = ensure_deposit_capacity(c, m);
+  if (rc) return rc;
+  std::vector<Deposit> d((size_t)m);
+  for (int64_t i = 0; i < m; i++) {
+    for (int k = 0; k < 3; k++) {
+      d[i].x[k] = x3[3 * i + k];
+      d[i].n[k] = n3[3 * i + k];
+      d[i].flux[k] = flux3[3 * i + k];
+    }
+    d[i].meta = (uint64_t)i;
+  }
+  CU(c, cudaMemcpyAsync(c->dep_raw.p, d.data(), (size_t)m * sizeof(Deposit), cudaMemcpyHostToDevice, c->stream));
+  if (c->n_hp > 0) {
+    CU(c, key_host_deposits(c, m));
+    CU(c, sort_and_gather(c, m));
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  fold_timings(c, false, c->n_hp > 0);
+  return SPPM_OK;
+}
+
+int sppm_export_stats(sppm_ctx* c, int64_t cap, int32_t* newN, int32_t* N, double* r2, double* tao3) {
+  if (!c) return SPPM_ERR_INVALID;
+  if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
+  Bind b(c);
+  const int64_t n = c->n_hp;
+  if (n == 0) return SPPM_OK;
+  std::vector<uint64_t> okey((size_t)n);
+  std::vector<int32_t> hN((size_t)n), hnewN((size_t)n);
+  std::vector<double> hr2((size_t)n), htao((size_t)n * 3);
+  CU(c, cudaMemcpyAsync(okey.data(), c->soa.okey, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(hN.data(), c->soa.N, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(hnewN.data(), c->soa.newN, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(hr2.data(), c->soa.r2, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(htao.data(), c->soa.tao, (size_t)n * 24, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const std::vector<int64_t> ord = canonical_order(okey);
+  for (int64_t j = 0; j < std::min(n, cap); j++) {
+    const int64_t i = ord[j];
+    if (newN) newN[j] = hnewN[i];
+    if (N) N[j] = hN[i];
+    if (r2) r2[j] = hr2[i];
+    if (tao3)
+      for (int k = 0; k < 3; k++) tao3[3 * j + k] = htao[(size_t)k * n + i];
+  }
+  return SPPM_OK;
+}
+
+int sppm_keep_deposits(sppm_ctx* c, int32_t keep_all) {
+  if (!c) return SPPM_ERR_INVALID;
+  c->keep_all_deposits = keep_all != 0;
+  return SPPM_OK;
+}
+
+int sppm_export_deposits(sppm_ctx* c, int64_t cap, double* x3, double* n3, double* flux3, uint64_t* photon_id,
+                         int32_t* bounce, int64_t* m_out) {
+  if (!c) return SPPM_ERR_INVALID;
+  Bind b(c);
+  const int64_t m = c->n_dep;
+  if (m_out) *m_out = m;
+  if (m == 0) return SPPM_OK;
+  std::vector<Deposit> d((size_t)m);
+  CU(c, cudaMemcpyAsync(d.data(), c->dep_raw.p, (size_t)m * sizeof(Deposit), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  // canonical order: (photon id, bounce)
+  std::vector<int64_t> ord((size_t)m);
+  std::iota(ord.begin(), ord.end(), 0);
+  auto keyf = [&](int64_t i) { return ((d[i].meta & 0x00ffffffffffffffull) << 8) | (d[i].meta >> 56); };
+  std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t bb) { return keyf(a) < keyf(bb); });
+  for (int64_t j = 0; j < std::min(m, cap); j++) {
+    const Deposit& r = d[ord[j]];
+    for (int k = 0; k < 3; k++) {
+      if (x3) x3[3 * j + k] = r.x[k];
+      if (n3) n3[3 * j + k] = r.n[k];
+      if (flux3) flux3[3 * j + k] = r.flux[k];
+    }
+    if (photon_id) photon_id[j] = r.meta & 0x00ffffffffffffffull;
+    if (bounce) bounce[j] = (int32_t)(r.meta >> 56);
+  }
+  return SPPM_OK;
+}
+
+int sppm_get_counters(sppm_ctx* c, SppmCounters* out) {
+  if (!c || !out) return SPPM_ERR_INVALID;
+  Bind b(c);
+  CU(c, cudaStreamSynchronize(c->stream));
+  DevCounters d;
+  CU(c, cudaMemcpy(&d, c->counters.p, sizeof(d), cudaMemcpyDeviceToHost));
+  SppmCounters& h = c->host_counters;
+  h.photons = d.photons;
+  h.isect_queries = d.isect_queries;
+  h.patch_solves = d.patch_solves;
+  h.deposits = d.deposits;
+  h.deposits_kept = d.deposits_kept;
+  h.cand_pairs = d.cand_pairs;
+  h.acc_pairs = d.acc_pairs;
+  h.hit_points = (uint64_t)c->n_hp;
+  h.grid_cells = (uint64_t)c->grid.n_cells;
+  *out = h;
+  return SPPM_OK;
+}
+
+int sppm_reset_counters(sppm_ctx* c) {
+  if (!c) return SPPM_ERR_INVALID;
+  Bind b(c);
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaMemset(c->counters.p, 0, sizeof(DevCounters)));
+  const uint64_t launches = c->host_counters.launches;
+  c->host_counters = SppmCounters{};
+  c->host_counters.launches = launches;
+  return SPPM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+// ctx.h — host-side context of libsppm_b200.so and the launch interfaces between its
+// translation units (abi.cu = C ABI + orchestration, trace.cu = eye/photon/intersection
+// kernels, gather.cu = hash-grid build, deposit sort, gather, update, film).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sppm_b200.h"
+#include "scene.cuh"
+
+namespace sppm {
+
+// Raw (arrival-order) hit point written by the eye pass; 96 B.
+struct HpRaw {
+  double pos[3], n[3], wgt[3];
+  double r2;
+  int32_t row, col;
+  uint64_t okey;  // canonical order key: pixel index << 20 | eye-path node
+};
+// Deposit record (Raytracer.h:139-156 inputs): x, N, flux; 80 B, 16-byte aligned for
+// 128-bit broadcast loads in the gather.  meta = photon id | bounce << 56.
+struct __align__(16) Deposit {
+  double x[3], n[3], flux[3];
+  uint64_t meta;
+};
+
+// Hash grid over the hit points (replaces the flann kd-tree, Raytracer.h:370-380).
+struct Grid {
+  double org[3];
+  double inv_cell;
+  int dim[3];
+  int64_t n_cells;
+};
+__host__ __device__ inline int64_t grid_cell(const Grid& g, double x, double y, double z) {
+#ifdef __CUDA_ARCH__
+  int ix = __double2int_rd((x - g.org[0]) * g.inv_cell);
+  int iy = __double2int_rd((y - g.org[1]) * g.inv_cell);
+  int iz = __double2int_rd((z - g.org[2]) * g.inv_cell);
+#else
+  int ix = 0, iy = 0, iz = 0;
+  (void)x; (void)y; (void)z;
+#endif
+  ix = ix < 0 ? 0 : (ix >= g.dim[0] ? g.dim[0] - 1 : ix);
+  iy = iy < 0 ? 0 : (iy >= g.dim[1] ? g.dim[1] - 1 : iy);
+  iz = iz < 0 ? 0 : (iz >= g.dim[2] ? g.dim[2] - 1 : iz);
+  return ((int64_t)iz * g.dim[1] + iy) * g.dim[0] + ix;
+}
+
+// Sorted structure-of-arrays hit-point map (device pointers, length n).
+struct HpSoA {
+  double *px, *py, *pz, *nx, *ny, *nz, *r2, *wx, *wy, *wz;
+  double* tao;    // [3][n]
+  double* dtao;   // [3][n] per-round accumulator
+  int32_t *N, *newN, *dN;
+  int32_t *row, *col;
+  uint64_t* okey;
+};
+
+struct DevCounters {
+  unsigned long long photons, isect_queries, patch_solves, deposits, deposits_kept, cand_pairs, acc_pairs, overflow;
+};
+
+struct DevBuf {  // growable device allocation
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace sppm
+
+struct sppm_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  SppmParams prm;
+  // scene
+  sppm::DevScene scene{};
+  std::vector<sppm::DevBuf> scene_bufs;
+  bool scene_ok = false;
+  bool patches_in_smem = true;
+  size_t trace_smem = 0;
+  // hit points
+  sppm::DevBuf hp_raw;     // HpRaw[cap]
+  int64_t hp_cap = 0, n_hp = 0;
+  int film_w = 0, film_h = 0;
+  sppm::DevBuf soa_store;  // backing store of HpSoA
+  sppm::HpSoA soa{};
+  bool index_ok = false;
+  // grid
+  sppm::Grid grid{};
+  sppm::DevBuf cell_slot;     // int32[n_cells]: compact id of cells near hit points, -1 otherwise
+  int32_t n_slots = 0;
+  sppm::DevBuf occ_cell, occ_start;  // occupied cells: grid id [n_occ], hp start [n_occ+1]
+  int32_t n_occ = 0;
+  sppm::DevBuf occ_nbr;       // int32[n_occ][27] compact slots of the neighbourhood
+  // deposits
+  sppm::DevBuf dep_raw, dep_sorted, dep_key, dep_key2, dep_idx, dep_idx2, dep_start, cub_tmp;
+  int64_t dep_cap = 0, n_dep = 0, n_dep_kept = 0;
+  sppm::DevBuf dev_scalars;   // [0] hp count, [1] deposit count, [2] photon cursor ...
+  sppm::DevBuf counters;      // DevCounters
+  sppm::DevBuf film;          // double[h][w][3]
+  sppm::DevBuf scratch;
+  bool keep_all_deposits = false;
+  SppmCounters host_counters{};
+  cudaEvent_t ev[8] = {};  // 0 trace start, 1 sort start, 2 gather start, 3 gather end, 4/5 generic
+  // NCCL (dlopen)
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+
+namespace sppm {
+// trace.cu
+cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pass_id);
+cudaError_t launch_photon_trace(sppm_ctx* c, uint64_t begin, uint64_t count, uint64_t pass_id);
+cudaError_t launch_intersect(sppm_ctx* c, const double* d_rays6, int64_t n, const uint64_t* d_ids, uint64_t pass_id,
+                             int node, SppmHit* d_out);
+cudaError_t launch_patch_batch(sppm_ctx* c, const double* d_rays6, const int32_t* d_patch, int64_t n,
+                               const double* d_seeds, double* d_tuv);
+cudaError_t trace_configure(sppm_ctx* c);
+// gather.cu
+cudaError_t build_index(sppm_ctx* c);
+cudaError_t key_host_deposits(sppm_ctx* c, int64_t m);
+cudaError_t sort_and_gather(sppm_ctx* c, int64_t m);
+cudaError_t launch_update(sppm_ctx* c);
+cudaError_t launch_resolve(sppm_ctx* c, int cnt, int onetime);
+cudaError_t dev_reserve(DevBuf& b, size_t bytes);
+void dev_free(DevBuf& b);
+}  // namespace sppm

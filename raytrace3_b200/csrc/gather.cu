@@ -1,0 +1,528 @@
+// gather.cu — the hit-point hash grid and the photon gather for sm_100a.
+//
+// Replaces flann::KDTreeSingleIndex + radiusSearch + the accumulate loop of
+// RayTracer::PhotonTrace (Raytracer.h:92-96, 139-159, 370-380) by
+//   build_index:     cell key per hit point -> CUB radix sort -> SoA permute -> occupied-cell
+//                    list, neighbourhood slot table (once per eye pass)
+//   sort_and_gather: deposits of one photon batch binned by cell with a CUB radix sort,
+//                    then a hit-point-centric gather: each hit point scans the deposits of
+//                    its 27 neighbour cells and accumulates newN / tao in registers — no
+//                    atomics, each accumulator is written once per batch.
+// and HitPoint::update / the film resolve (Raytracer.h:69-79, 281-293).
+//
+// Bit-exactness: the acceptance predicate is evaluated in FP64 with the reference's
+// operation order and no FMA (the library is built with -fmad=false), so newN is exact.
+#include <cub/cub.cuh>
+
+#include "ctx.h"
+
+namespace sppm {
+
+cudaError_t dev_reserve(DevBuf& b, size_t bytes) {
+  if (bytes <= b.bytes && b.p) return cudaSuccess;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e == cudaSuccess) b.bytes = want;
+  return e;
+}
+void dev_free(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned nblk(long long n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb); }
+#define CK(x)                      \
+  do {                             \
+    cudaError_t e__ = (x);         \
+    if (e__ != cudaSuccess) return e__; \
+  } while (0)
+
+__global__ void bounds_kernel(const HpRaw* hp, long long n, unsigned long long* mm /*[6]*/, double* sum /*[3]*/) {
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, s[3] = {0, 0, 0};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    for (int k = 0; k < 3; k++) {
+      const double v = hp[i].pos[k];
+      lo[k] = fmin(lo[k], v);
+      hi[k] = fmax(hi[k], v);
+      s[k] += v;
+    }
+  for (int k = 0; k < 3; k++) {
+    for (int off = 16; off > 0; off >>= 1) {
+      lo[k] = fmin(lo[k], __shfl_xor_sync(FULL, lo[k], off));
+      hi[k] = fmax(hi[k], __shfl_xor_sync(FULL, hi[k], off));
+      s[k] += __shfl_xor_sync(FULL, s[k], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(mm + k, dbl_key(lo[k]));
+      atomicMax(mm + 3 + k, dbl_key(hi[k]));
+      atomicAdd(sum + k, s[k]);
+    }
+  }
+}
+
+__global__ void hp_okey_kernel(const HpRaw* hp, long long n, uint64_t* okey, uint32_t* idx) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  okey[i] = hp[i].okey;
+  idx[i] = (uint32_t)i;
+}
+// cell key of the hit points taken in canonical (okey) order
+__global__ void hp_key_kernel(const HpRaw* hp, const uint32_t* idx, long long n, Grid g, uint32_t* key) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const HpRaw& r = hp[idx[i]];
+  key[i] = (uint32_t)grid_cell(g, r.pos[0], r.pos[1], r.pos[2]);
+}
+
+__global__ void hp_permute_kernel(const HpRaw* hp, const uint32_t* idx, long long n, HpSoA s) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const HpRaw r = hp[idx[i]];
+  s.px[i] = r.pos[0]; s.py[i] = r.pos[1]; s.pz[i] = r.pos[2];
+  s.nx[i] = r.n[0]; s.ny[i] = r.n[1]; s.nz[i] = r.n[2];
+  s.wx[i] = r.wgt[0]; s.wy[i] = r.wgt[1]; s.wz[i] = r.wgt[2];
+  s.r2[i] = r.r2;
+  s.row[i] = r.row; s.col[i] = r.col;
+  s.okey[i] = r.okey;
+  s.N[i] = 0; s.newN[i] = 0; s.dN[i] = 0;
+  for (int k = 0; k < 3; k++) {
+    s.tao[(size_t)k * n + i] = 0;
+    s.dtao[(size_t)k * n + i] = 0;
+  }
+}
+
+__global__ void mark_nbr_kernel(const uint32_t* occ_cell, int n_occ, Grid g, int32_t* flag) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_occ * 27) return;
+  const int o = (int)(t / 27), k = (int)(t % 27);
+  const uint32_t c = occ_cell[o];
+  const int ix = c % g.dim[0], iy = (c / g.dim[0]) % g.dim[1], iz = c / (g.dim[0] * g.dim[1]);
+  const int jx = ix + k % 3 - 1, jy = iy + (k / 3) % 3 - 1, jz = iz + k / 9 - 1;
+  if (jx < 0 || jy < 0 || jz < 0 || jx >= g.dim[0] || jy >= g.dim[1] || jz >= g.dim[2]) return;
+  flag[((long long)jz * g.dim[1] + jy) * g.dim[0] + jx] = 1;
+}
+__global__ void finalize_slot_kernel(int32_t* flag_to_slot, const int32_t* scan, long long n_cells, int32_t* n_slots) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cells) return;
+  const int f = flag_to_slot[i];
+  if (i == n_cells - 1) *n_slots = scan[i] + f;
+  flag_to_slot[i] = f ? scan[i] : -1;
+}
+__global__ void occ_nbr_kernel(const uint32_t* occ_cell, int n_occ, Grid g, const int32_t* cell_slot, int32_t* occ_nbr) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_occ * 27) return;
+  const int o = (int)(t / 27), k = (int)(t % 27);
+  const uint32_t c = occ_cell[o];
+  const int ix = c % g.dim[0], iy = (c / g.dim[0]) % g.dim[1], iz = c / (g.dim[0] * g.dim[1]);
+  const int jx = ix + k % 3 - 1, jy = iy + (k / 3) % 3 - 1, jz = iz + k / 9 - 1;
+  int32_t s = -1;
+  if (!(jx < 0 || jy < 0 || jz < 0 || jx >= g.dim[0] || jy >= g.dim[1] || jz >= g.dim[2]))
+    s = cell_slot[((long long)jz * g.dim[1] + jy) * g.dim[0] + jx];
+  occ_nbr[t] = s;
+}
+__global__ void set_last_kernel(int32_t* starts, int n_occ, int32_t n_hp) { starts[n_occ] = n_hp; }
+
+// ---- deposits --------------------------------------------------------------------------
+__global__ void iota_kernel(uint32_t* idx, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) idx[i] = (uint32_t)i;
+}
+__global__ void dep_key_kernel(const Deposit* dep, long long m, Grid g, const int32_t* cell_slot, int32_t n_slots,
+                               uint32_t* key) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int32_t s = cell_slot[grid_cell(g, dep[i].x[0], dep[i].x[1], dep[i].x[2])];
+  key[i] = s >= 0 ? (uint32_t)s : (uint32_t)n_slots;
+}
+// sorted[i] = raw[idx[i]] and the [start, end) deposit range of every slot
+__global__ void dep_permute_kernel(const Deposit* raw, const uint32_t* key, const uint32_t* idx, long long m,
+                                   int32_t n_slots, Deposit* sorted, int2* range, unsigned long long* n_kept) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double2* src = reinterpret_cast<const double2*>(raw + idx[i]);
+  double2* dst = reinterpret_cast<double2*>(sorted + i);
+#pragma unroll
+  for (int k = 0; k < 5; k++) dst[k] = src[k];
+  const uint32_t kk = key[i];
+  if (kk >= (uint32_t)n_slots) {
+    if (i == 0 || key[i - 1] < (uint32_t)n_slots) *n_kept = (unsigned long long)i;
+    return;
+  }
+  if (i == 0 || key[i - 1] != kk) range[kk].x = (int)i;
+  if (i == m - 1 || key[i + 1] != kk) {
+    range[kk].y = (int)i + 1;
+    if (i == m - 1) *n_kept = (unsigned long long)m;
+  }
+}
+
+struct GatherArgs {
+  HpSoA s;
+  long long n_hp;
+  const int32_t* occ_start;
+  const int32_t* occ_nbr;
+  int n_occ;
+  const int2* range;
+  const Deposit* dep;
+  double search_r2;
+  DevCounters* counters;
+};
+
+// One warp per occupied hit-point cell.  The warp's lanes are split hl x dl: hl lanes hold
+// hit points of the cell (pos, n, R2 in registers), dl = 32/hl lanes stride over the
+// deposits of the 27 neighbour cells; all lanes with the same deposit index read the same
+// 80-byte record (five 128-bit broadcast loads).  Partial sums are combined with shuffles
+// and each hit point's accumulators are written once.
+__global__ void __launch_bounds__(256) gather_kernel(const GatherArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long cand = 0, acc = 0;
+  for (long long c = warp0; c < a.n_occ; c += nwarps) {
+    const int hs = a.occ_start[c], he = a.occ_start[c + 1];
+    int2 myr = make_int2(0, 0);
+    if (lane < 27) {
+      const int32_t slot = a.occ_nbr[c * 27 + lane];
+      if (slot >= 0) myr = a.range[slot];
+    }
+    if (!__any_sync(FULL, myr.y > myr.x)) continue;  // no deposit near this cell in this batch
+    for (int h0 = hs; h0 < he; h0 += 32) {
+      const int H = min(32, he - h0);
+      int hl = 1;
+      while (hl < H) hl <<= 1;
+      const int dl = 32 / hl;
+      const int my_h = lane & (hl - 1), my_d = lane / hl;
+      const int i = h0 + my_h;
+      const bool valid = my_h < H;
+      double px = 0, py = 0, pz = 0, nx = 0, ny = 0, nz = 0, r2 = -1;
+      if (valid) {
+        px = a.s.px[i]; py = a.s.py[i]; pz = a.s.pz[i];
+        nx = a.s.nx[i]; ny = a.s.ny[i]; nz = a.s.nz[i];
+        r2 = a.s.r2[i];
+      }
+      int cnt = 0;
+      double s0 = 0, s1 = 0, s2 = 0;
+      for (int nb = 0; nb < 27; nb++) {
+        const int ds = __shfl_sync(FULL, myr.x, nb), de = __shfl_sync(FULL, myr.y, nb);
+        for (int d = ds + my_d; d < de; d += dl) {
+          const double2* q = reinterpret_cast<const double2*>(a.dep + d);
+          const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
+          // x = (q0.x, q0.y, q1.x)  N = (q1.y, q2.x, q2.y)  flux = (q3.x, q3.y, q4.x)
+          const double vx = px - q0.x, vy = py - q0.y, vz = pz - q1.x;  // Raytracer.h:152
+          const double vv = (vx * vx + vy * vy) + vz * vz;
+          if (valid && vv < a.search_r2) {  // flann radiusSearch, strict '<' (Q3)
+            cand++;
+            const double nn = (nx * q1.y + ny * q2.x) + nz * q2.y;
+            if (nn > SPPM_NORMAL_AGREE && vv <= r2) {  // Raytracer.h:154
+              cnt++;
+              s0 += q3.x; s1 += q3.y; s2 += q4.x;
+              acc++;
+            }
+          }
+        }
+      }
+      for (int off = hl; off < 32; off <<= 1) {
+        cnt += __shfl_xor_sync(FULL, cnt, off);
+        s0 += __shfl_xor_sync(FULL, s0, off);
+        s1 += __shfl_xor_sync(FULL, s1, off);
+        s2 += __shfl_xor_sync(FULL, s2, off);
+      }
+      if (valid && my_d == 0 && cnt > 0) {  // hp->newN++, hp->tao += wgt.mul(flux)*PI_INV (Raytracer.h:155-156)
+        a.s.dN[i] += cnt;
+        a.s.dtao[i] += (a.s.wx[i] * s0) * SPPM_PI_INV;
+        a.s.dtao[a.n_hp + i] += (a.s.wy[i] * s1) * SPPM_PI_INV;
+        a.s.dtao[2 * a.n_hp + i] += (a.s.wz[i] * s2) * SPPM_PI_INV;
+      }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    cand += __shfl_xor_sync(FULL, cand, off);
+    acc += __shfl_xor_sync(FULL, acc, off);
+  }
+  if (lane == 0 && cand) {
+    atomicAdd(&a.counters->cand_pairs, cand);
+    atomicAdd(&a.counters->acc_pairs, acc);
+  }
+}
+
+// newN += dN, tao += dtao, then HitPoint::update (Raytracer.h:69-79)
+__global__ void update_kernel(HpSoA s, long long n, int mode, double alpha) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int newN = s.newN[i] + s.dN[i];
+  double t0 = s.tao[i] + s.dtao[i], t1 = s.tao[n + i] + s.dtao[n + i], t2 = s.tao[2 * n + i] + s.dtao[2 * n + i];
+  s.dN[i] = 0;
+  s.dtao[i] = 0; s.dtao[n + i] = 0; s.dtao[2 * n + i] = 0;
+  int N = s.N[i];
+  const bool skip = (mode == SPPM_UPDATE_REFERENCE) ? (N <= 0 || newN <= 0) : (newN <= 0);
+  if (!skip) {
+    const double k = (N + alpha * newN) / (N + newN);
+    s.r2[i] *= k;
+    t0 *= k; t1 *= k; t2 *= k;
+    N = (int)(N + alpha * newN);  // int += double: computed in double, truncated
+    newN = 0;
+    s.N[i] = N;
+  }
+  s.newN[i] = newN;
+  s.tao[i] = t0; s.tao[n + i] = t1; s.tao[2 * n + i] = t2;
+}
+
+// camera->pic[x][y] += tao * (1.0 / PI / (R2*cnt*onetime))  (Raytracer.h:288-293)
+__global__ void resolve_kernel(HpSoA s, long long n, int cnt, int onetime, int w, double* film) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double sc = 1.0 / SPPM_PI / (s.r2[i] * cnt * onetime);
+  double* px = film + ((size_t)s.row[i] * w + s.col[i]) * 3;
+  atomicAdd(px + 0, s.tao[i] * sc);
+  atomicAdd(px + 1, s.tao[n + i] * sc);
+  atomicAdd(px + 2, s.tao[2 * n + i] * sc);
+}
+
+inline int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 32 && (max_value >> b)) b++;
+  return b;
+}
+
+cudaError_t layout_soa(sppm_ctx* c, int64_t n) {
+  const size_t nd = (size_t)(n > 0 ? n : 1);
+  const size_t bytes = nd * (10 * 8 + 6 * 8 + 3 * 4 + 2 * 4 + 8) + 4096;
+  CK(dev_reserve(c->soa_store, bytes));
+  unsigned char* p = (unsigned char*)c->soa_store.p;
+  auto takeD = [&](size_t k) { double* r = (double*)p; p += k * 8; return r; };
+  HpSoA& s = c->soa;
+  s.px = takeD(nd); s.py = takeD(nd); s.pz = takeD(nd);
+  s.nx = takeD(nd); s.ny = takeD(nd); s.nz = takeD(nd);
+  s.r2 = takeD(nd);
+  s.wx = takeD(nd); s.wy = takeD(nd); s.wz = takeD(nd);
+  s.tao = takeD(3 * nd);
+  s.dtao = takeD(3 * nd);
+  s.okey = (uint64_t*)p; p += nd * 8;
+  auto takeI = [&](size_t k) { int32_t* r = (int32_t*)p; p += k * 4; return r; };
+  s.N = takeI(nd); s.newN = takeI(nd); s.dN = takeI(nd); s.row = takeI(nd); s.col = takeI(nd);
+  return cudaSuccess;
+}
+
+}  // namespace
+
+cudaError_t build_index(sppm_ctx* c) {
+  cudaStream_t st = c->stream;
+  const int64_t n = c->n_hp;
+  c->index_ok = false;
+  CK(layout_soa(c, n));
+  if (n == 0) {
+    c->n_occ = 0;
+    c->n_slots = 0;
+    c->grid = Grid{{0, 0, 0}, 1.0, {1, 1, 1}, 1};
+    CK(dev_reserve(c->cell_slot, 4));
+    CK(cudaMemsetAsync(c->cell_slot.p, 0xff, 4, st));
+    CK(dev_reserve(c->occ_start, 8));
+    CK(dev_reserve(c->occ_cell, 4));
+    CK(dev_reserve(c->occ_nbr, 27 * 4));
+    CK(dev_reserve(c->dep_start, 16));
+    c->index_ok = true;
+    return cudaSuccess;
+  }
+  const HpRaw* raw = (const HpRaw*)c->hp_raw.p;
+  // 1. bounds + centroid
+  CK(dev_reserve(c->scratch, 256));
+  {
+    unsigned long long init[9];
+    for (int k = 0; k < 3; k++) {
+      init[k] = ~0ull;
+      init[3 + k] = 0ull;
+      init[6 + k] = 0ull;  // double 0.0
+    }
+    CK(cudaMemcpyAsync(c->scratch.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    bounds_kernel<<<min(nblk(n), 1184u), TPB, 0, st>>>(raw, n, (unsigned long long*)c->scratch.p,
+                                                        (double*)((unsigned long long*)c->scratch.p + 6));
+    c->host_counters.launches++;
+    CK(cudaMemcpyAsync(init, c->scratch.p, sizeof(init), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // 2. grid: cell edge = sqrt(searchR2) (1+1e-9) so a radius-sqrt(searchR2) ball spans <= 3 cells
+    // per axis; coordinates outside the gridded region are clamped into its boundary cells, which
+    // keeps neighbours neighbours.  The region is capped at 2^26 cells around the centroid.
+    const double cell = sqrt(c->prm.init_r2) * (1.0 + 1e-9);
+    double lo[3], hi[3], mean[3];
+    int dim[3];
+    for (int k = 0; k < 3; k++) {
+      lo[k] = key_dbl(init[k]);
+      hi[k] = key_dbl(init[3 + k]);
+      double s;
+      memcpy(&s, &init[6 + k], 8);
+      mean[k] = s / (double)n;
+      double cells = floor((hi[k] - lo[k]) / cell) + 1;
+      dim[k] = cells > 1e9 ? 1000000000 : (int)cells;
+    }
+    auto shrink = [&](int k, int nd) {
+      double half = 0.5 * nd * cell;
+      double ctr = mean[k];
+      if (ctr - half < lo[k]) ctr = lo[k] + half;
+      if (ctr + half > hi[k]) ctr = hi[k] - half;
+      lo[k] = ctr - half;
+      dim[k] = nd;
+    };
+    for (int k = 0; k < 3; k++)
+      if (dim[k] > 2048) shrink(k, 2048);
+    while ((int64_t)dim[0] * dim[1] * dim[2] > ((int64_t)1 << 26)) {
+      int k = 0;
+      for (int j = 1; j < 3; j++)
+        if (dim[j] > dim[k]) k = j;
+      shrink(k, dim[k] / 2);
+    }
+    Grid g;
+    for (int k = 0; k < 3; k++) {
+      g.org[k] = lo[k];
+      g.dim[k] = dim[k];
+    }
+    g.inv_cell = 1.0 / cell;
+    g.n_cells = (int64_t)dim[0] * dim[1] * dim[2];
+    c->grid = g;
+  }
+  const Grid g = c->grid;
+  // 3. canonical order first (radix sort by okey = pixel, eye-path node: the eye pass appends in
+  // arrival order), then a stable radix sort by cell key, then the SoA permute.  Every rank of a
+  // multi-GPU run therefore holds the hit points in the same order.
+  CK(dev_reserve(c->dep_key, (size_t)n * 8));  // reuse the deposit key/index buffers as sort scratch
+  CK(dev_reserve(c->dep_key2, (size_t)n * 8));
+  CK(dev_reserve(c->dep_idx, (size_t)n * 4));
+  CK(dev_reserve(c->dep_idx2, (size_t)n * 4));
+  uint32_t *k1 = (uint32_t*)c->dep_key.p, *k2 = (uint32_t*)c->dep_key2.p, *i1 = (uint32_t*)c->dep_idx.p,
+           *i2 = (uint32_t*)c->dep_idx2.p;
+  size_t tmp = 0;
+  {
+    uint64_t *o1 = (uint64_t*)c->dep_key.p, *o2 = (uint64_t*)c->dep_key2.p;
+    hp_okey_kernel<<<nblk(n), TPB, 0, st>>>(raw, n, o1, i2);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, o1, o2, i2, i1, (int)n, 0, 64, st));
+    CK(dev_reserve(c->cub_tmp, tmp));
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, o1, o2, i2, i1, (int)n, 0, 64, st));
+    c->host_counters.launches += 2;
+  }
+  hp_key_kernel<<<nblk(n), TPB, 0, st>>>(raw, i1, n, g, k1);
+  c->host_counters.launches++;
+  const int end_bit = bits_for((uint64_t)g.n_cells - 1);
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k1, k2, i1, i2, (int)n, 0, end_bit, st));
+  CK(dev_reserve(c->cub_tmp, tmp));
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k1, k2, i1, i2, (int)n, 0, end_bit, st));
+  hp_permute_kernel<<<nblk(n), TPB, 0, st>>>(raw, i2, n, c->soa);
+  c->host_counters.launches += 3;
+  // 4. occupied cells (run-length encode of the sorted keys) and their hit-point ranges
+  CK(dev_reserve(c->occ_cell, (size_t)n * 4));
+  CK(dev_reserve(c->occ_start, ((size_t)n + 1) * 4));
+  int32_t* counts = (int32_t*)c->dep_idx.p;  // i1 is free now
+  int32_t* d_nruns = (int32_t*)c->scratch.p;
+  CK(cub::DeviceRunLengthEncode::Encode(nullptr, tmp, k2, (uint32_t*)c->occ_cell.p, counts, d_nruns, (int)n, st));
+  CK(dev_reserve(c->cub_tmp, tmp));
+  CK(cub::DeviceRunLengthEncode::Encode(c->cub_tmp.p, tmp, k2, (uint32_t*)c->occ_cell.p, counts, d_nruns, (int)n, st));
+  int32_t n_occ = 0;
+  CK(cudaMemcpyAsync(&n_occ, d_nruns, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  c->n_occ = n_occ;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, counts, (int32_t*)c->occ_start.p, n_occ, st));
+  CK(dev_reserve(c->cub_tmp, tmp));
+  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, counts, (int32_t*)c->occ_start.p, n_occ, st));
+  set_last_kernel<<<1, 1, 0, st>>>((int32_t*)c->occ_start.p, n_occ, (int32_t)n);
+  c->host_counters.launches += 4;
+  // 5. cells whose 27-neighbourhood holds a hit point get a compact slot (others: -1)
+  CK(dev_reserve(c->cell_slot, (size_t)g.n_cells * 4));
+  CK(dev_reserve(c->dep_sorted, (size_t)g.n_cells * 4));  // scan scratch (deposit buffer is idle here)
+  CK(cudaMemsetAsync(c->cell_slot.p, 0, (size_t)g.n_cells * 4, st));
+  mark_nbr_kernel<<<nblk((long long)n_occ * 27), TPB, 0, st>>>((uint32_t*)c->occ_cell.p, n_occ, g, (int32_t*)c->cell_slot.p);
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (int32_t*)c->cell_slot.p, (int32_t*)c->dep_sorted.p, (int)g.n_cells, st));
+  CK(dev_reserve(c->cub_tmp, tmp));
+  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, (int32_t*)c->cell_slot.p, (int32_t*)c->dep_sorted.p, (int)g.n_cells, st));
+  finalize_slot_kernel<<<nblk(g.n_cells), TPB, 0, st>>>((int32_t*)c->cell_slot.p, (int32_t*)c->dep_sorted.p, g.n_cells, d_nruns);
+  int32_t n_slots = 0;
+  CK(cudaMemcpyAsync(&n_slots, d_nruns, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  c->n_slots = n_slots;
+  CK(dev_reserve(c->occ_nbr, (size_t)n_occ * 27 * 4));
+  occ_nbr_kernel<<<nblk((long long)n_occ * 27), TPB, 0, st>>>((uint32_t*)c->occ_cell.p, n_occ, g, (int32_t*)c->cell_slot.p,
+                                                               (int32_t*)c->occ_nbr.p);
+  CK(dev_reserve(c->dep_start, ((size_t)n_slots + 1) * 8));
+  c->host_counters.launches += 4;
+  CK(cudaGetLastError());
+  c->host_counters.hit_points = (uint64_t)n;
+  c->host_counters.grid_cells = (uint64_t)g.n_cells;
+  c->index_ok = true;
+  return cudaSuccess;
+}
+
+cudaError_t key_host_deposits(sppm_ctx* c, int64_t m) {
+  if (m <= 0) return cudaSuccess;
+  dep_key_kernel<<<nblk(m), TPB, 0, c->stream>>>((const Deposit*)c->dep_raw.p, m, c->grid, (const int32_t*)c->cell_slot.p,
+                                                 c->n_slots, (uint32_t*)c->dep_key.p);
+  c->host_counters.launches++;
+  return cudaGetLastError();
+}
+
+// Bin the m raw deposits (keys already in dep_key; key == n_slots marks "near no hit point")
+// and run the gather into the per-round accumulators dN / dtao.
+cudaError_t sort_and_gather(sppm_ctx* c, int64_t m) {
+  cudaStream_t st = c->stream;
+  c->n_dep = m;
+  c->n_dep_kept = 0;
+  if (m <= 0 || c->n_hp == 0) return cudaSuccess;
+  CK(dev_reserve(c->dep_key2, (size_t)m * 4));
+  CK(dev_reserve(c->dep_idx, (size_t)m * 4));
+  CK(dev_reserve(c->dep_idx2, (size_t)m * 4));
+  CK(dev_reserve(c->dep_sorted, (size_t)m * sizeof(Deposit)));
+  uint32_t *k1 = (uint32_t*)c->dep_key.p, *k2 = (uint32_t*)c->dep_key2.p, *i1 = (uint32_t*)c->dep_idx.p,
+           *i2 = (uint32_t*)c->dep_idx2.p;
+  CK(cudaEventRecord(c->ev[1], st));
+  iota_kernel<<<nblk(m), TPB, 0, st>>>(i1, m);
+  size_t tmp = 0;
+  const int end_bit = bits_for((uint64_t)c->n_slots);
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k1, k2, i1, i2, (int)m, 0, end_bit, st));
+  CK(dev_reserve(c->cub_tmp, tmp));
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k1, k2, i1, i2, (int)m, 0, end_bit, st));
+  CK(cudaMemsetAsync(c->dep_start.p, 0, ((size_t)c->n_slots + 1) * 8, st));
+  unsigned long long* n_kept = (unsigned long long*)c->dev_scalars.p + 3;
+  CK(cudaMemsetAsync(n_kept, 0, 8, st));
+  dep_permute_kernel<<<nblk(m), TPB, 0, st>>>((const Deposit*)c->dep_raw.p, k2, i2, m, c->n_slots, (Deposit*)c->dep_sorted.p,
+                                               (int2*)c->dep_start.p, n_kept);
+  CK(cudaEventRecord(c->ev[2], st));
+  GatherArgs a;
+  a.s = c->soa;
+  a.n_hp = c->n_hp;
+  a.occ_start = (const int32_t*)c->occ_start.p;
+  a.occ_nbr = (const int32_t*)c->occ_nbr.p;
+  a.n_occ = c->n_occ;
+  a.range = (const int2*)c->dep_start.p;
+  a.dep = (const Deposit*)c->dep_sorted.p;
+  a.search_r2 = c->prm.init_r2;
+  a.counters = (DevCounters*)c->counters.p;
+  const long long warps = c->n_occ;
+  unsigned blocks = nblk(warps * 32, 256);
+  const unsigned cap = (unsigned)c->sm_count * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  gather_kernel<<<blocks, 256, 0, st>>>(a);
+  CK(cudaEventRecord(c->ev[3], st));
+  c->host_counters.launches += 4;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_update(sppm_ctx* c) {
+  if (c->n_hp == 0) return cudaSuccess;
+  update_kernel<<<nblk(c->n_hp), TPB, 0, c->stream>>>(c->soa, c->n_hp, c->prm.update_mode, c->prm.alpha);
+  c->host_counters.launches++;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(sppm_ctx* c, int cnt, int onetime) {
+  const size_t bytes = (size_t)c->film_w * c->film_h * 3 * 8;
+  CK(dev_reserve(c->film, bytes));
+  CK(cudaMemsetAsync(c->film.p, 0, bytes, c->stream));
+  if (c->n_hp == 0) return cudaSuccess;
+  resolve_kernel<<<nblk(c->n_hp), TPB, 0, c->stream>>>(c->soa, c->n_hp, cnt, onetime, c->film_w, (double*)c->film.p);
+  c->host_counters.launches++;
+  return cudaGetLastError();
+}
+
+}  // namespace sppm

@@ -1,0 +1,521 @@
+// scene.cuh — device scene view and Scene::NearCollide as a warp-cooperative routine.
+//
+// Analytic objects (planes, spheres) are tested per lane.  Bezier objects are handled by
+// the whole warp: every lane culls its ray against the object / patch AABBs
+// (Bezier.h:20-51, 176-186, 240-250), surviving (ray, patch) pairs go to a per-warp queue
+// in shared memory, and the queue's (pair, restart) Newton tasks are spread over all 32
+// lanes — lanes = restarts, control points read from shared memory, 3x3 inverse in
+// registers — followed by a warp min-reduction on t (Bezier.h:146-158).
+// Citations: /root/reference/raytracer/<file>:<line>.
+#pragma once
+#include "../../include/sppm_b200.h"
+#include "device_math.cuh"
+
+namespace sppm {
+
+constexpr int MAX_OBJECTS = 64;
+constexpr int QCAP = 96;  // (ray, patch) queue entries per warp
+constexpr int TRACE_THREADS = 128;
+constexpr int TRACE_WARPS = TRACE_THREADS / 32;
+
+struct DevObject {
+  int kind, tex_id, first_patch, n_patch;
+  int isDiff, isRefl, isRefr;  // Element.h:16-18
+  int udex, vdex;              // Obj.h:89-96
+  int pad;
+  double diffr, reflr, refrr, allr;  // Obj.h:12-15
+  double diff[3], refl[3], refr[3], refrn;
+  double color[3];
+  double p0[3], norm[3], radius;
+  double texU[3], texV[3], texW[3];  // texW = texU x texV (Obj.h:151)
+  double texUmod, texVmod;           // Obj.h:97-98 Module()
+  double box[6];                     // Bezier3Obj::aabb
+};
+struct DevTexture {
+  int rows, cols;
+  const uint8_t* bgr;
+};
+struct DevScene {
+  int n_obj, n_patch, n_light, n_tex;
+  const DevObject* obj;     // [n_obj]
+  const double* patchP;     // [n_patch][48]
+  const double* patchBox;   // [n_patch][6]
+  const SppmLight* lights;  // [n_light]
+  const DevTexture* tex;    // [n_tex]
+};
+struct NewtonCfg {
+  int restarts, iters, mode;
+  uint64_t seed;
+};
+
+// per-warp shared-memory scratch of near_collide
+struct WarpScratch {
+  double ray[6][32];
+  unsigned long long id[32];
+  unsigned int node[32];
+  unsigned int item[QCAP];  // lane | global patch << 8
+  double it_t[QCAP], it_u[QCAP], it_v[QCAP];
+};
+// block-level shared view of the scene (objects + patches staged by stage_scene)
+struct SceneView {
+  const DevObject* obj;
+  const double* patchP;
+  const double* patchBox;
+  const DevTexture* tex;
+  int n_obj;
+};
+
+__host__ __device__ inline size_t scene_smem_bytes(int n_obj, int n_patch, bool patches_in_smem) {
+  size_t b = (size_t)n_obj * sizeof(DevObject);
+  if (patches_in_smem) b += (size_t)n_patch * 54 * sizeof(double);
+  return (b + 15) & ~(size_t)15;
+}
+
+// Copy objects (and patches if they fit) into dynamic shared memory; all threads call.
+__device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, bool patches_in_smem) {
+  SceneView v;
+  {
+    const int n = s.n_obj * (int)(sizeof(DevObject) / 8);
+    double* dst = reinterpret_cast<double*>(smem);
+    const double* src = reinterpret_cast<const double*>(s.obj);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    v.obj = reinterpret_cast<const DevObject*>(smem);
+  }
+  if (patches_in_smem) {
+    double* dp = reinterpret_cast<double*>(smem + (size_t)s.n_obj * sizeof(DevObject));
+    double* db = dp + (size_t)s.n_patch * 48;
+    for (int i = threadIdx.x; i < s.n_patch * 48; i += blockDim.x) dp[i] = s.patchP[i];
+    for (int i = threadIdx.x; i < s.n_patch * 6; i += blockDim.x) db[i] = s.patchBox[i];
+    v.patchP = dp;
+    v.patchBox = db;
+  } else {
+    v.patchP = s.patchP;
+    v.patchBox = s.patchBox;
+  }
+  v.tex = s.tex;
+  v.n_obj = s.n_obj;
+  __syncthreads();
+  return v;
+}
+
+// ---- Element.h:61-72 Texture::colorUV ------------------------------------------------
+__device__ inline d3 color_uv(const DevTexture& t, double u, double v) {
+  const int rows = t.rows, cols = t.cols;
+  double row = (u - floor(u)) * rows, col = (v - floor(v)) * cols;
+  int r1 = (int)floor(row + 1e-10), r2 = r1 + 1;
+  int c1 = (int)floor(col + 1e-10), c2 = c1 + 1;
+  double detR = r2 - row, detC = c2 - col;
+  r1 = (r1 >= 0) ? (r1 >= rows ? 0 : r1) : (rows - 1);
+  c1 = (c1 >= 0) ? (c1 >= cols ? 0 : c1) : (cols - 1);
+  r2 = (r2 < rows) ? r2 : 0;
+  c2 = (c2 < cols) ? c2 : 0;
+  const uint8_t* p11 = t.bgr + ((size_t)r1 * cols + c1) * 3;
+  const uint8_t* p12 = t.bgr + ((size_t)r1 * cols + c2) * 3;
+  const uint8_t* p21 = t.bgr + ((size_t)r2 * cols + c1) * 3;
+  const uint8_t* p22 = t.bgr + ((size_t)r2 * cols + c2) * 3;
+  double o[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double a = __ldg(p11 + k) / 255.0, b = __ldg(p12 + k) / 255.0, c = __ldg(p21 + k) / 255.0,
+           d = __ldg(p22 + k) / 255.0;
+    o[k] = ((a * detR * detC + b * detR * (1 - detC)) + c * (1 - detR) * detC) + d * (1 - detR) * (1 - detC);
+  }
+  return d3{o[0], o[1], o[2]};
+}
+
+// ---- Bezier.h:20-51 AABBbox::intersect (entry faces only, Q5) ---------------------------
+__device__ inline bool aabb_intersect(const double* box, d3 org, d3 dir) {
+  const double o[3] = {org.x, org.y, org.z}, d[3] = {dir.x, dir.y, dir.z};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    if (!is_zero(d[i])) {
+      double t = (d[i] > 0) ? (box[i] - o[i]) / d[i] : (box[3 + i] - o[i]) / d[i];
+      if (t > 0) {
+        bool flag = true;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          if (j != i) {
+            double c = o[j] + t * d[j];
+            if (box[3 + j] < c || box[j] > c) flag = false;
+          }
+        }
+        if (flag) return true;
+      }
+    }
+  }
+  return false;
+}
+
+// ---- Bezier.h:69-111 patch evaluation --------------------------------------------------
+struct PatchEval {
+  d3 S, Su, Sv;
+};
+__device__ __forceinline__ void bern(double t, double c[4]) {  // Bezier.h:71-74
+  c[0] = (1 - t) * (1 - t) * (1 - t);
+  c[1] = 3 * t * (1 - t) * (1 - t);
+  c[2] = 3 * t * t * (1 - t);
+  c[3] = t * t * t;
+}
+__device__ __forceinline__ void dbern(double t, double c[4]) {  // Bezier.h:79-82
+  c[0] = -3 * (1 - t) * (1 - t);
+  c[1] = 3 * (1 - t) * (1 - t) - 6 * t * (1 - t);
+  c[2] = 6 * t * (1 - t) - 3 * t * t;
+  c[3] = 3 * t * t;
+}
+// P[0]*c0 + P[1]*c1 + P[2]*c2 + P[3]*c3, left-associated (Bezier.h:75)
+#define SPPM_COMB(a, b, c, d, w) ((((a) * (w)[0] + (b) * (w)[1]) + (c) * (w)[2]) + (d) * (w)[3])
+
+// EXACT: the operations of evalPatchPoint / evalPatchDerivU / evalPatchDerivV in the
+// reference's order (rows at u are shared by Point and DerivV — same inputs, same bits).
+__device__ __forceinline__ PatchEval eval_exact(const double* __restrict__ P, double u, double v) {
+  double cu[4], cv[4], du[4], dv[4];
+  bern(u, cu);
+  bern(v, cv);
+  dbern(u, du);
+  dbern(v, dv);
+  PatchEval e;
+  double row[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      row[i][k] = SPPM_COMB(P[(4 * i) * 3 + k], P[(4 * i + 1) * 3 + k], P[(4 * i + 2) * 3 + k], P[(4 * i + 3) * 3 + k], cu);
+  e.S.x = SPPM_COMB(row[0][0], row[1][0], row[2][0], row[3][0], cv);
+  e.S.y = SPPM_COMB(row[0][1], row[1][1], row[2][1], row[3][1], cv);
+  e.S.z = SPPM_COMB(row[0][2], row[1][2], row[2][2], row[3][2], cv);
+  e.Sv.x = SPPM_COMB(row[0][0], row[1][0], row[2][0], row[3][0], dv);
+  e.Sv.y = SPPM_COMB(row[0][1], row[1][1], row[2][1], row[3][1], dv);
+  e.Sv.z = SPPM_COMB(row[0][2], row[1][2], row[2][2], row[3][2], dv);
+  double col[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      col[i][k] = SPPM_COMB(P[i * 3 + k], P[(i + 4) * 3 + k], P[(i + 8) * 3 + k], P[(i + 12) * 3 + k], cv);
+  e.Su.x = SPPM_COMB(col[0][0], col[1][0], col[2][0], col[3][0], du);
+  e.Su.y = SPPM_COMB(col[0][1], col[1][1], col[2][1], col[3][1], du);
+  e.Su.z = SPPM_COMB(col[0][2], col[1][2], col[2][2], col[3][2], du);
+  return e;
+}
+// FAST: joint tensor-form evaluation with FMA: rows and row derivatives in u, then three
+// combinations in v.  Same polynomial, different rounding (<= a few ulp).
+__device__ __forceinline__ PatchEval eval_fast(const double* __restrict__ P, double u, double v) {
+  double cu[4], cv[4], du[4], dv[4];
+  const double mu = 1 - u, mv = 1 - v;
+  cu[0] = mu * mu * mu; cu[1] = 3 * u * mu * mu; cu[2] = 3 * u * u * mu; cu[3] = u * u * u;
+  cv[0] = mv * mv * mv; cv[1] = 3 * v * mv * mv; cv[2] = 3 * v * v * mv; cv[3] = v * v * v;
+  du[0] = -3 * mu * mu; du[1] = 3 * mu * (mu - 2 * u); du[2] = 3 * u * (2 * mu - u); du[3] = 3 * u * u;
+  dv[0] = -3 * mv * mv; dv[1] = 3 * mv * (mv - 2 * v); dv[2] = 3 * v * (2 * mv - v); dv[3] = 3 * v * v;
+  double S[3] = {0, 0, 0}, Su[3] = {0, 0, 0}, Sv[3] = {0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double p0 = P[(4 * i) * 3 + k], p1 = P[(4 * i + 1) * 3 + k], p2 = P[(4 * i + 2) * 3 + k],
+                   p3 = P[(4 * i + 3) * 3 + k];
+      const double r = fma(p3, cu[3], fma(p2, cu[2], fma(p1, cu[1], p0 * cu[0])));
+      const double dr = fma(p3, du[3], fma(p2, du[2], fma(p1, du[1], p0 * du[0])));
+      S[k] = fma(r, cv[i], S[k]);
+      Sv[k] = fma(r, dv[i], Sv[k]);
+      Su[k] = fma(dr, cv[i], Su[k]);
+    }
+  }
+  PatchEval e;
+  e.S = d3{S[0], S[1], S[2]};
+  e.Su = d3{Su[0], Su[1], Su[2]};
+  e.Sv = d3{Sv[0], Sv[1], Sv[2]};
+  return e;
+}
+
+// One Newton step x = prevX - inv([dir, -Su, -Sv]) * (org + dir*t - S)  (Bezier.h:121-131).
+// The inverse is cv::Matx33d::inv's closed form (adjugate / determinant, zeros when the
+// determinant is exactly 0) held in registers.
+template <bool FAST>
+__device__ __forceinline__ void newton_step(d3 org, d3 dir, const PatchEval& e, double& t, double& u, double& v) {
+  const d3 L = org + dir * t;
+  const d3 r = L - e.S;
+  const double a00 = dir.x, a01 = -e.Su.x, a02 = -e.Sv.x;
+  const double a10 = dir.y, a11 = -e.Su.y, a12 = -e.Sv.y;
+  const double a20 = dir.z, a21 = -e.Su.z, a22 = -e.Sv.z;
+  if (FAST) {
+    const double c00 = fma(a11, a22, -(a12 * a21)), c01 = fma(a02, a21, -(a01 * a22)), c02 = fma(a01, a12, -(a02 * a11));
+    const double c10 = fma(a12, a20, -(a10 * a22)), c11 = fma(a00, a22, -(a02 * a20)), c12 = fma(a02, a10, -(a00 * a12));
+    const double c20 = fma(a10, a21, -(a11 * a20)), c21 = fma(a01, a20, -(a00 * a21)), c22 = fma(a00, a11, -(a01 * a10));
+    double d = fma(a02, c20, fma(a01, c10, a00 * c00));
+    if (d != 0) {
+      d = 1 / d;
+      t -= fma(c02, r.z, fma(c01, r.y, c00 * r.x)) * d;
+      u -= fma(c12, r.z, fma(c11, r.y, c10 * r.x)) * d;
+      v -= fma(c22, r.z, fma(c21, r.y, c20 * r.x)) * d;
+    }
+  } else {
+    double d = a00 * (a11 * a22 - a21 * a12) - a01 * (a10 * a22 - a20 * a12) + a02 * (a10 * a21 - a20 * a11);
+    double b00 = 0, b01 = 0, b02 = 0, b10 = 0, b11 = 0, b12 = 0, b20 = 0, b21 = 0, b22 = 0;
+    if (d != 0) {
+      d = 1 / d;
+      b00 = (a11 * a22 - a12 * a21) * d;
+      b01 = (a02 * a21 - a01 * a22) * d;
+      b02 = (a01 * a12 - a02 * a11) * d;
+      b10 = (a12 * a20 - a10 * a22) * d;
+      b11 = (a00 * a22 - a02 * a20) * d;
+      b12 = (a02 * a10 - a00 * a12) * d;
+      b20 = (a10 * a21 - a11 * a20) * d;
+      b21 = (a01 * a20 - a00 * a21) * d;
+      b22 = (a00 * a11 - a01 * a10) * d;
+    }
+    // Matx * Vec: s = 0; s += m(i,k) * r(k)
+    t = t - (((0.0 + b00 * r.x) + b01 * r.y) + b02 * r.z);
+    u = u - (((0.0 + b10 * r.x) + b11 * r.y) + b12 * r.z);
+    v = v - (((0.0 + b20 * r.x) + b21 * r.y) + b22 * r.z);
+  }
+}
+
+// One restart of Bezier3::newton (Bezier.h:116-141): from (0,u0,v0) run `iters`
+// iterations, keep the first strict minimum of t over the accepted iterates (Q4).
+template <bool FAST>
+__device__ __forceinline__ bool newton_restart(const double* __restrict__ P, d3 org, d3 dir, double u0, double v0,
+                                               int iters, double& bt, double& bu, double& bv) {
+  double t = 0, u = u0, v = v0;
+  bool found = false;
+  bt = SPPM_MAX_NUM;
+  PatchEval e = FAST ? eval_fast(P, u, v) : eval_exact(P, u, v);
+  for (int it = 0; it < iters; it++) {
+    newton_step<FAST>(org, dir, e, t, u, v);
+    e = FAST ? eval_fast(P, u, v) : eval_exact(P, u, v);
+    const d3 r = (org + dir * t) - e.S;
+    const double res = ((0.0 + r.x * r.x) + r.y * r.y) + r.z * r.z;
+    if (res < SPPM_M_EPS && u <= 1 && u >= 0 && v >= 0 && v <= 1) {
+      if (t < bt) {
+        bt = t;
+        bu = u;
+        bv = v;
+        found = true;
+      }
+    }
+  }
+  return found;
+}
+
+// Process the warp's queued (ray, patch) items: n_items * restarts Newton tasks spread over
+// the 32 lanes, per-item min-t written to ws->it_{t,u,v}.  seeds_uv (nullable) = injected
+// seeds double[pair][restarts][2], pair = seed_pair_base + item.
+__device__ inline void flush_items(const SceneView& sv, WarpScratch* ws, int n_items, const NewtonCfg& cfg,
+                                   uint64_t pass, uint32_t domain, const double* seeds_uv, long long seed_pair_base,
+                                   int lane) {
+  for (int i = lane; i < n_items; i += 32) {
+    ws->it_t[i] = SPPM_MAX_NUM;
+    ws->it_u[i] = SPPM_MAX_NUM;
+    ws->it_v[i] = SPPM_MAX_NUM;
+  }
+  __syncwarp();
+  const int R = cfg.restarts;
+  const int total = n_items * R;
+  for (int base = 0; base < total; base += 32) {
+    const int k = base + lane;
+    const bool valid = k < total;
+    const int item = valid ? k / R : -1;
+    double t = 0, u = 0, v = 0;
+    bool found = false;
+    if (valid) {
+      const int r = k - item * R;
+      const unsigned it = ws->item[item];
+      const int owner = it & 31, gp = it >> 8;
+      const d3 org = d3{ws->ray[0][owner], ws->ray[1][owner], ws->ray[2][owner]};
+      const d3 dir = d3{ws->ray[3][owner], ws->ray[4][owner], ws->ray[5][owner]};
+      double u0, v0;
+      if (seeds_uv) {
+        const double* s = seeds_uv + ((size_t)(seed_pair_base + item) * R + r) * 2;
+        u0 = s[0];
+        v0 = s[1];
+      } else {
+        draw2(cfg.seed, pass, ws->id[owner], ws->node[owner], domain, (uint32_t)r, (uint32_t)gp, u0, v0);
+      }
+      const double* P = sv.patchP + (size_t)gp * 48;
+      found = (cfg.mode == SPPM_NEWTON_FAST) ? newton_restart<true>(P, org, dir, u0, v0, cfg.iters, t, u, v)
+                                             : newton_restart<false>(P, org, dir, u0, v0, cfg.iters, t, u, v);
+    }
+    // segmented arg-min over the (at most a few) items present in this round; restart order = lane order
+    const int first = base / R;
+    const int last = (min(base + 31, total - 1)) / R;
+    for (int itx = first; itx <= last; itx++) {
+      double tt = (found && item == itx) ? t : CUDART_INF;
+      int ll = lane;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ot = __shfl_xor_sync(FULL, tt, off);
+        const int ol = __shfl_xor_sync(FULL, ll, off);
+        if (ot < tt || (ot == tt && ol < ll)) {
+          tt = ot;
+          ll = ol;
+        }
+      }
+      if (tt < CUDART_INF) {  // warp-uniform
+        const double wu = __shfl_sync(FULL, u, ll), wv = __shfl_sync(FULL, v, ll);
+        if (lane == 0 && tt < ws->it_t[itx]) {
+          ws->it_t[itx] = tt;
+          ws->it_u[itx] = wu;
+          ws->it_v[itx] = wv;
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+struct Hit {  // Element.h:20-39 Collision, the fields the path reads
+  double dist;
+  int obj;    // -1 = NoneColl
+  int patch;  // Bezier winner
+  double u, v;
+  bool inside;
+};
+
+// Scene::NearCollide (Scene.h:165-182) for the 32 rays of a warp.  All lanes must call
+// (inactive lanes pass active=false).  Keeps the strictly nearest hit, first object wins ties.
+__device__ inline Hit near_collide(const SceneView& sv, WarpScratch* ws, const NewtonCfg& cfg, bool active, d3 org,
+                                   d3 dir, uint64_t pass, uint64_t id, uint32_t node, uint32_t domain,
+                                   unsigned long long& solves) {
+  const int lane = threadIdx.x & 31;
+  Hit best;
+  best.dist = SPPM_MAX_NUM;
+  best.obj = -1;
+  best.patch = -1;
+  best.u = best.v = 0;
+  best.inside = false;
+  bool staged = false;
+  for (int a = 0; a < sv.n_obj; a++) {
+    const DevObject& ob = sv.obj[a];
+    if (ob.kind == SPPM_OBJ_PLANE) {  // PlaneObj::GetIntersect (Obj.h:65-85)
+      if (active) {
+        const d3 norm = ld3(ob.norm);
+        const double project = dot3(dir, norm);
+        if (!is_zero(project)) {
+          const double dist = dot3(ld3(ob.p0) - org, norm) / project;
+          if (dist > SPPM_M_EPS && dist < best.dist) {
+            best.dist = dist;
+            best.obj = a;
+            best.inside = false;
+          }
+        }
+      }
+    } else if (ob.kind == SPPM_OBJ_SPHERE) {  // SphereObj::GetIntersect (Obj.h:111-139)
+      if (active) {
+        const d3 L = ld3(ob.p0) - org;
+        const double project = dot3(L, dir);
+        const double det2 = ob.radius * ob.radius - (module2(L) - project * project);
+        if (!(det2 < SPPM_M_EPS)) {
+          const double det = sqrt(det2);
+          const double dist1 = project - det, dist2 = project + det;
+          if (!(dist2 < SPPM_M_EPS)) {
+            const double dist = (dist1 > SPPM_M_EPS) ? dist1 : dist2;
+            if (dist < best.dist) {
+              best.dist = dist;
+              best.obj = a;
+              best.inside = (dist1 < SPPM_M_EPS);
+            }
+          }
+        }
+      }
+    } else {  // Bezier3Obj::GetIntersect (Bezier.h:240-282)
+      const bool in_box = active && aabb_intersect(ob.box, org, dir);
+      if (__any_sync(FULL, in_box)) {
+        if (!staged) {
+          ws->ray[0][lane] = org.x; ws->ray[1][lane] = org.y; ws->ray[2][lane] = org.z;
+          ws->ray[3][lane] = dir.x; ws->ray[4][lane] = dir.y; ws->ray[5][lane] = dir.z;
+          ws->id[lane] = id;
+          ws->node[lane] = node;
+          staged = true;
+          __syncwarp();
+        }
+        double pt = SPPM_MAX_NUM, pu = SPPM_MAX_NUM, pv = SPPM_MAX_NUM;  // para (Bezier.h:246)
+        int index = -1;
+        int n_items = 0;
+        for (int p = 0; p <= ob.n_patch; p++) {
+          bool hitp = false;
+          if (p < ob.n_patch) {
+            hitp = in_box && aabb_intersect(sv.patchBox + (size_t)(ob.first_patch + p) * 6, org, dir);  // Bezier.h:178
+            const unsigned b = __ballot_sync(FULL, hitp);
+            if (hitp) ws->item[n_items + __popc(b & ((1u << lane) - 1))] = (unsigned)lane | ((unsigned)(ob.first_patch + p) << 8);
+            n_items += __popc(b);
+          }
+          if (n_items > QCAP - 32 || (p == ob.n_patch && n_items > 0)) {
+            __syncwarp();
+            flush_items(sv, ws, n_items, cfg, pass, domain, nullptr, 0, lane);
+            if (lane == 0) solves += (unsigned long long)n_items;
+            // per-lane filter in patch order (Bezier.h:249-261)
+            for (int i = 0; i < n_items; i++) {
+              const unsigned it = ws->item[i];
+              if ((int)(it & 31) == lane) {
+                const double qt = ws->it_t[i], qu = ws->it_u[i], qv = ws->it_v[i];
+                if (qt < SPPM_M_EPS || qt > pt || qu < -SPPM_M_EPS || qu > 1 + SPPM_M_EPS || qv < -SPPM_M_EPS ||
+                    qv > 1 + SPPM_M_EPS)
+                  continue;
+                if (qt < pt) {
+                  pt = qt; pu = qu; pv = qv;
+                  index = (int)(it >> 8);
+                }
+              }
+            }
+            __syncwarp();
+            n_items = 0;
+          }
+        }
+        if (index != -1 && pt < best.dist) {
+          best.dist = pt;
+          best.obj = a;
+          best.patch = index;
+          best.u = pu;
+          best.v = pv;
+          best.inside = false;
+        }
+      }
+    }
+  }
+  return best;
+}
+
+struct Surface {  // what the callers need of the winning Collision
+  d3 pos, n, color;
+};
+// Pos / N / color of the winning object (Obj.h:79-80,86-100; :131-137,140-153; Bezier.h:263-279).
+__device__ inline Surface shade_hit(const SceneView& sv, const Hit& h, d3 org, d3 dir) {
+  const DevObject& ob = sv.obj[h.obj];
+  Surface s;
+  s.pos = org + dir * h.dist;
+  if (ob.kind == SPPM_OBJ_PLANE) {
+    s.n = ld3(ob.norm);
+    if (ob.tex_id < 0) {
+      s.color = ld3(ob.color);
+    } else {
+      const double P[3] = {s.pos.x, s.pos.y, s.pos.z};
+      const double v = 0.5 + (P[ob.vdex] - ob.p0[ob.vdex]) / ob.texUmod;
+      const double u = 0.5 + (P[ob.udex] - ob.p0[ob.udex]) / ob.texVmod;
+      s.color = color_uv(sv.tex[ob.tex_id], u, v);
+    }
+  } else if (ob.kind == SPPM_OBJ_SPHERE) {
+    const d3 N = get_unit(s.pos - ld3(ob.p0));
+    s.n = N;
+    if (ob.tex_id < 0) {
+      s.color = ld3(ob.color);
+    } else {
+      const double theta = acos(dot3(N, ld3(ob.texV)));
+      double t = dot3(N, ld3(ob.texU)) / sin(theta);
+      t = (t >= -1) ? t : -1;
+      t = (t <= 1) ? t : 1;
+      const double phi = acos(t);
+      const double u = theta / SPPM_PI;
+      double v = phi / (2 * SPPM_PI);
+      v = (dot3(N, ld3(ob.texW)) < 0) ? (1 - v) : v;
+      s.color = color_uv(sv.tex[ob.tex_id], u, v);
+    }
+  } else {
+    const PatchEval e = eval_exact(sv.patchP + (size_t)h.patch * 48, h.u, h.v);
+    d3 N = cross3(e.Su, e.Sv);
+    if (dot3(N, dir) > 0) N = -N;
+    s.n = normalize3(N);
+    s.color = (ob.tex_id < 0) ? ld3(ob.color) : color_uv(sv.tex[ob.tex_id], h.u, h.dist);  // Q6
+  }
+  return s;
+}
+
+}  // namespace sppm
