@@ -1,0 +1,331 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star): intersection t/u/v <= 1e-6 relative (EXACT
+mode: bit-identical), gather newN bit-exact and tao <= 1e-5 relative, image rRMSE <= 1%."""
+import numpy as np
+import pytest
+
+from conftest import rays_at_patches, rays_at_teapot, rays_in_room
+from raytrace3_b200 import abi
+from raytrace3_b200.scene import make_scene, reference_camera
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(**kw):
+    p = abi.default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def test_patch_newton_injected_seeds_exact(ctx, oracle):
+    """Bezier3::newton (Bezier.h:112-159) with injected (u0,v0): EXACT mode is bit-identical."""
+    sc = make_scene("reference", textures=None)
+    prm = _params(newton_mode=abi.SPPM_NEWTON_EXACT)
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    n = 700
+    rng = np.random.RandomState(5)
+    patch = rng.randint(0, 32, size=n).astype(np.int32)
+    rays = rays_at_patches(patch, 11, sc)
+    rays[:100] = rays_at_teapot(100, 11, sc)  # and some that mostly miss their patch
+    seeds = rng.uniform(size=(n, prm.newton_restarts, 2))
+    ref = oracle.bezier_patch_batch(sc, prm, rays, patch, seeds)
+    got = ctx.bezier_patch_batch(rays, patch, seeds)
+    assert (ref[:, 0] < 1e19).sum() > 300 and (ref[:, 0] >= 1e19).sum() > 50  # solutions and misses
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_patch_newton_fast_within_1e6(ctx, oracle):
+    sc = make_scene("reference", textures=None)
+    prm = _params(newton_mode=abi.SPPM_NEWTON_FAST)
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    n = 3000
+    patch = (np.arange(n) % 32).astype(np.int32)
+    rays = rays_at_patches(patch, 12, sc)
+    ref = oracle.bezier_patch_batch(sc, prm, rays, patch, None)  # counter-RNG seeds
+    got = ctx.bezier_patch_batch(rays, patch, None)
+    hit_r, hit_g = ref[:, 0] < 1e19, got[:, 0] < 1e19
+    assert hit_r.sum() > 1500
+    assert (hit_r == hit_g).all()
+    rel = np.abs(got[hit_r] - ref[hit_r]) / np.maximum(np.abs(ref[hit_r]), 1e-12)
+    assert rel.max() <= 1e-6  # north-star tolerance on (t, u, v)
+
+
+@pytest.mark.parametrize("scene_name,textured", [("cornell", False), ("reference", False), ("reference", True), ("stress", False)])
+def test_near_collide_matches_oracle(ctx, oracle, scene_name, textured):
+    """Scene::NearCollide (Scene.h:165-182): same object, same hit/miss, same t/Pos/N/colour."""
+    sc = make_scene(scene_name, textures="synthetic" if textured else None)
+    prm = _params()
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    rays = np.concatenate([rays_in_room(4000, 3), rays_at_teapot(1500, 4, sc) if scene_name != "cornell" else rays_in_room(500, 9)])
+    ids = np.arange(rays.shape[0], dtype=np.uint64) * 7 + 3
+    ref = oracle.intersect_batch(sc, prm, rays, ids, pass_id=2, node=5)
+    got = ctx.intersect_batch(rays, ids, pass_id=2, node=5)
+    np.testing.assert_array_equal(got["obj"], ref["obj"])
+    np.testing.assert_array_equal(got["patch"], ref["patch"])
+    np.testing.assert_array_equal(got["inside"], ref["inside"])
+    np.testing.assert_array_equal(got["t"], ref["t"])  # +,-,*,/,sqrt only: bit-exact
+    np.testing.assert_array_equal(got["pos"], ref["pos"])
+    np.testing.assert_array_equal(got["u"], ref["u"])
+    np.testing.assert_array_equal(got["v"], ref["v"])
+    np.testing.assert_allclose(got["n"], ref["n"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(got["color"], ref["color"], rtol=1e-12, atol=1e-15)  # sphere texture uses acos/sin
+    if scene_name != "cornell":
+        assert (ref["patch"] >= 0).sum() > 100
+
+
+def test_eye_pass_hitpoints(ctx, oracle):
+    """GetHitPoint/ViewTrace (Raytracer.h:102-116, 296-357) incl. mirror + glass chains."""
+    sc = make_scene("reference", textures="synthetic")
+    prm = _params()
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    cam = reference_camera(96, 72)
+    ref = oracle.eye_pass(sc, prm, cam, pass_id=3)
+    n = ctx.eye_pass(cam, pass_id=3)
+    assert n == ref["pos"].shape[0]
+    got = ctx.export_hitpoints()
+    order = np.lexsort((ref["node"], ref["pix"][:, 0] * cam.w + ref["pix"][:, 1]))  # canonical: pixel, node
+    for k in ("pix", "node"):
+        np.testing.assert_array_equal(got[k], ref[k][order])
+    np.testing.assert_array_equal(got["pos"], ref["pos"][order])
+    np.testing.assert_allclose(got["n"], ref["n"][order], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(got["wgt"], ref["wgt"][order], rtol=1e-12, atol=0)
+    np.testing.assert_array_equal(got["r2"], ref["r2"][order])
+
+
+def _random_hitpoints(rng, n, w=64, h=48):
+    pos = np.stack([rng.uniform(0, 30, n), rng.uniform(0, 2, n), rng.uniform(0, 30, n)], axis=1)
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    wgt = rng.uniform(0.1, 1, size=(n, 3))
+    r2 = rng.uniform(0.2, 2.0, size=n)
+    pix = np.stack([rng.randint(0, h, n), rng.randint(0, w, n)], axis=1).astype(np.int32)
+    return dict(pos=pos, n=nrm, wgt=wgt, r2=r2, pix=pix), w, h
+
+
+def test_gather_bit_exact_newN(ctx, oracle):
+    """Raytracer.h:139-159: newN bit-exact, tao <= 1e-5 relative vs the exhaustive oracle,
+    incl. deposits exactly at distance^2 == searchR2 (strict '<', Q3) and == R2 ('<=')."""
+    rng = np.random.RandomState(7)
+    hp, w, h = _random_hitpoints(rng, 6000)
+    m = 20000
+    x = np.stack([rng.uniform(-2, 32, m), rng.uniform(-1, 3, m), rng.uniform(-2, 32, m)], axis=1)
+    dn = rng.normal(size=(m, 3))
+    dn /= np.linalg.norm(dn, axis=1, keepdims=True)
+    flux = rng.uniform(0, 100, size=(m, 3))
+    # boundary cases: hit point 0 at the origin of a 3-4-5 style exact offset
+    hp["pos"][0] = (10.0, 1.0, 10.0)
+    hp["r2"][0] = 2.0
+    hp["n"][0] = (0, 1, 0)
+    x[0] = (11.0, 2.0, 10.0)   # vv == 2.0 exactly -> excluded by the strict radius search
+    x[1] = (11.0, 1.0, 10.0)   # vv == 1.0 -> included
+    hp["pos"][1] = (20.0, 1.0, 20.0)
+    hp["r2"][1] = 1.0          # vv == R2 exactly -> accepted ('<=')
+    hp["n"][1] = (0, 1, 0)
+    x[2] = (21.0, 1.0, 20.0)
+    dn[0] = dn[1] = dn[2] = (0, 1, 0)
+    prm = _params()
+    ctx.set_params(prm)
+    ctx.import_hitpoints(hp["pos"], hp["n"], hp["wgt"], hp["r2"], hp["pix"], w, h)
+    ctx.build_index()
+    ctx.reset_counters()
+    ctx.gather_deposits(x, dn, flux)
+    ctx.update()
+    got = ctx.export_stats(6000)
+    newN, tao, cand, acc = oracle.gather_brute(hp, dict(x=x, n=dn, flux=flux), prm.init_r2)
+    assert newN.sum() > 1000
+    np.testing.assert_array_equal(got["newN"], newN)
+    np.testing.assert_allclose(got["tao"], tao, rtol=1e-5, atol=0)
+    c = ctx.counters()
+    assert c["cand_pairs"] == cand and c["acc_pairs"] == acc
+    # a second batch accumulates on top (Q1: newN is never reset in REFERENCE mode)
+    ctx.gather_deposits(x[:5000], dn[:5000], flux[:5000])
+    ctx.update()
+    got2 = ctx.export_stats(6000)
+    newN2, tao2, _, _ = oracle.gather_brute(hp, dict(x=x[:5000], n=dn[:5000], flux=flux[:5000]), prm.init_r2, newN.copy(), tao.copy())
+    np.testing.assert_array_equal(got2["newN"], newN2)
+    np.testing.assert_allclose(got2["tao"], tao2, rtol=1e-5, atol=0)
+
+
+def test_gather_edge_cases(ctx, oracle):
+    prm = _params()
+    ctx.set_params(prm)
+    rng = np.random.RandomState(1)
+    # empty hit-point map, empty deposit list, single far-away hit point, clustered cell
+    ctx.import_hitpoints(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 3)), np.zeros(0), np.zeros((0, 2), np.int32), 4, 4)
+    ctx.build_index()
+    ctx.gather_deposits(rng.uniform(size=(10, 3)), rng.uniform(size=(10, 3)), rng.uniform(size=(10, 3)))
+    ctx.update()
+    hp, w, h = _random_hitpoints(rng, 300)
+    hp["pos"][:200] = hp["pos"][0] + rng.uniform(-0.2, 0.2, size=(200, 3))  # > 32 hit points in one cell
+    hp["pos"][299] = (1e7, -1e7, 3e6)                                        # clamped into a boundary cell
+    ctx.import_hitpoints(hp["pos"], hp["n"], hp["wgt"], hp["r2"], hp["pix"], w, h)
+    ctx.build_index()
+    ctx.gather_deposits(np.zeros((0, 3)), np.zeros((0, 3)), np.zeros((0, 3)))
+    x = np.concatenate([hp["pos"][:250] + rng.uniform(-0.5, 0.5, size=(250, 3)), [[1e7 + 0.5, -1e7, 3e6]]])
+    dn = np.repeat(hp["n"][:1], x.shape[0], axis=0)
+    dn[-1] = hp["n"][299]
+    flux = rng.uniform(1, 2, size=x.shape)
+    ctx.gather_deposits(x, dn, flux)
+    ctx.update()
+    got = ctx.export_stats(300)
+    newN, tao, _, _ = oracle.gather_brute(hp, dict(x=x, n=dn, flux=flux), prm.init_r2)
+    assert newN[299] == 1 and newN[:200].max() > 32
+    np.testing.assert_array_equal(got["newN"], newN)
+    np.testing.assert_allclose(got["tao"], tao, rtol=1e-5, atol=0)
+
+
+@pytest.mark.parametrize("mode", [abi.SPPM_UPDATE_REFERENCE, abi.SPPM_UPDATE_PROGRESSIVE])
+def test_update_modes(ctx, oracle, mode):
+    """HitPoint::update (Raytracer.h:69-79): verbatim no-op (Q1) and the progressive variant."""
+    rng = np.random.RandomState(3)
+    hp, w, h = _random_hitpoints(rng, 2000)
+    hp["r2"][:] = 2.0
+    prm = _params(update_mode=mode)
+    ctx.set_params(prm)
+    ctx.import_hitpoints(hp["pos"], hp["n"], hp["wgt"], hp["r2"], hp["pix"], w, h)
+    ctx.build_index()
+    newN, N = np.zeros(2000, np.int32), np.zeros(2000, np.int32)
+    r2, tao = hp["r2"].copy(), np.zeros((2000, 3))
+    for rnd in range(3):
+        m = 4000
+        x = np.stack([rng.uniform(0, 30, m), rng.uniform(0, 2, m), rng.uniform(0, 30, m)], axis=1)
+        dn = hp["n"][rng.randint(0, 2000, m)]
+        flux = rng.uniform(0, 10, size=(m, 3))
+        ctx.gather_deposits(x, dn, flux)
+        ctx.update()
+        cur = dict(hp, r2=r2)
+        oracle.gather_brute(cur, dict(x=x, n=dn, flux=flux), prm.init_r2, newN, tao)
+        oracle.update(mode, prm.alpha, newN, N, r2, tao)
+    got = ctx.export_stats(2000)
+    np.testing.assert_array_equal(got["newN"], newN)
+    np.testing.assert_array_equal(got["N"], N)
+    np.testing.assert_allclose(got["r2"], r2, rtol=1e-14)
+    np.testing.assert_allclose(got["tao"], tao, rtol=1e-5, atol=0)
+    if mode == abi.SPPM_UPDATE_PROGRESSIVE:
+        assert (r2 < 2.0).any() and N.max() > 0
+    else:
+        assert (r2 == 2.0).all() and N.max() == 0
+
+
+def test_photon_pass_deposits_and_stats(ctx, oracle):
+    """Light::emit + PhotonTrace (Light.h:8-13, Raytracer.h:117-209): same photons -> same
+    deposit list (x, N, flux per (photon, bounce)); gathered newN equal, tao <= 1e-5."""
+    sc = make_scene("reference", textures="synthetic")
+    prm = _params()
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    cam = reference_camera(80, 60)
+    ctx.eye_pass(cam, 0)
+    ctx.build_index()
+    hp = ctx.export_hitpoints()
+    count = 6000
+    ctx.keep_deposits(True)
+    try:
+        ctx.reset_counters()
+        ctx.photon_pass(100, count, 9)
+        ctx.update()
+        dep = ctx.export_deposits()
+    finally:
+        ctx.keep_deposits(False)
+    ref = oracle.photon_pass(sc, prm, 100, count, 9, hp=hp, keep_deposits=True)
+    c = ctx.counters()
+    rc = ref["counters"]
+    # transcendental functions (acos/sin/cos) differ by ulps between libm and CUDA, which can
+    # flip a discrete decision on a rare path: allow a 0.1% mismatch in the path structure
+    assert abs(c["isect_queries"] - rc["queries"]) <= 0.001 * rc["queries"]
+    assert abs(c["deposits"] - rc["deposits"]) <= 0.001 * rc["deposits"]
+    assert c["photons"] == rc["photons"] == count
+    rd = ref["dep"]
+    okey = np.lexsort((rd["bounce"], rd["photon"]))
+    key_r = {(int(p), int(b)): i for i, (p, b) in enumerate(zip(rd["photon"], rd["bounce"]))}
+    matched = 0
+    maxerr = 0.0
+    for j in range(dep["x"].shape[0]):
+        i = key_r.get((int(dep["photon"][j]), int(dep["bounce"][j])))
+        if i is None:
+            continue
+        err = np.abs(dep["x"][j] - rd["x"][i]).max()
+        if err < 1e-6:
+            matched += 1
+            maxerr = max(maxerr, err)
+    assert matched >= 0.998 * rd["x"].shape[0], (matched, rd["x"].shape[0], len(okey))
+    assert maxerr < 1e-8
+    got = ctx.export_stats(hp["pos"].shape[0])
+    # statistics: identical deposits up to ulps -> newN equal except where a deposit sits within
+    # ulps of a radius boundary; require near-total agreement and close totals
+    assert (got["newN"] == ref["newN"]).mean() > 0.995
+    assert abs(int(got["newN"].sum()) - int(ref["newN"].sum())) <= 0.002 * ref["newN"].sum()
+    np.testing.assert_allclose(got["tao"].sum(0), ref["tao"].sum(0), rtol=2e-3)
+
+
+def test_gather_of_exported_deposits_is_bit_exact(ctx, oracle):
+    """Parity level (2) on a traced pass: feed the GPU's own deposit list to the exhaustive
+    oracle gather -> newN bit-exact, tao <= 1e-5."""
+    sc = make_scene("cornell", textures=None)
+    prm = _params()
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    cam = reference_camera(128, 96)
+    ctx.eye_pass(cam, 0)
+    ctx.build_index()
+    hp = ctx.export_hitpoints()
+    ctx.keep_deposits(True)
+    try:
+        ctx.photon_pass(0, 20000, 1)
+        ctx.update()
+        dep = ctx.export_deposits()
+    finally:
+        ctx.keep_deposits(False)
+    got = ctx.export_stats(hp["pos"].shape[0])
+    newN, tao, _, _ = oracle.gather_brute(hp, dep, prm.init_r2)
+    assert newN.sum() > 10000
+    np.testing.assert_array_equal(got["newN"], newN)
+    np.testing.assert_allclose(got["tao"], tao, rtol=1e-5, atol=0)
+
+
+def test_image_rrmse(ctx, oracle):
+    """Parity level (3): film after matched photon counts, relative RMSE <= 1%."""
+    from raytrace3_b200 import RayTracer
+    sc = make_scene("reference", textures="synthetic")
+    prm = _params()
+    ctx.set_params(prm)
+    w, h, cnt, onetime = 64, 48, 2, 30000
+    cam = reference_camera(w, h)
+    rt = RayTracer(ctx)
+    rt.camera, rt.scene, rt.cnt, rt.onetime = cam, sc, cnt, onetime
+    rt.render()
+    ref = oracle.render_replicas(sc, prm, cam.pos, cam.look, w, h, cnt, onetime, threads=1, jitter=0.0)
+    film_ref, film = ref["film"], cam.pic
+    assert film_ref.max() > 0
+    rrmse = np.sqrt(((film - film_ref) ** 2).mean()) / np.sqrt((film_ref ** 2).mean())
+    assert rrmse <= 0.01, rrmse
+    img = ctx.tonemap(film, 1.0)
+    img_ref = oracle.tonemap(film_ref, 1.0)
+    assert np.abs(img.astype(int) - img_ref.astype(int)).max() <= 2
+
+
+def test_photon_range_invariance(ctx):
+    """§8(e): splitting a round's photons over R ranks gives the same accumulators (newN
+    bit-exact, tao to rounding) because the RNG is keyed by the global photon id."""
+    sc = make_scene("cornell", textures=None)
+    prm = _params()
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    cam = reference_camera(96, 72)
+    n = ctx.eye_pass(cam, 0)
+    from raytrace3_b200 import photon_range
+    res = []
+    for world in (1, 3):
+        ctx.build_index()
+        for r in range(world):
+            b, c = photon_range(20001, r, world)
+            ctx.photon_pass(b, c, 4)
+        ctx.update()
+        res.append(ctx.export_stats(n))
+    np.testing.assert_array_equal(res[0]["newN"], res[1]["newN"])
+    np.testing.assert_allclose(res[0]["tao"], res[1]["tao"], rtol=1e-12)
