@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — photons traced+gathered per second (BASELINE.json metric M1) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+
+A step = one round of RayTracer::PhotonMap (Raytracer.h:226-246): every rank traces
+`onetime` photons through the scene (Light::emit + PhotonTrace), gathers them into the
+replicated hit-point map, the per-round accumulators are summed over ranks (NCCL, N > 1) and
+HitPoint::update runs.  Weak scaling: `onetime` photons PER GPU per step.  The hit-point map
+(eye pass + hash grid) is built once before the timed region, as in the reference where one
+eye pass serves cnt rounds; `e2e` times the whole RayTracer::render() (scene upload from host
+memory, eye pass, grid build, one round, film resolve + read-back) through the public API.
+
+--impl reference times the CPU restatement of the reference (oracle/, OpenMP over all host
+cores, each thread an independent photon tracer as in Raytracer.h:442-447) on a bounded
+sample of the same workload; the GPU is not touched.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# name -> scene, film size, photons per light per round (BASELINE.json configs[1..4])
+WORKLOADS = {
+    "ref-main-320x240": dict(scene="reference", w=320, h=240, onetime=100_000),
+    "cornell-1024x768": dict(scene="cornell", w=1024, h=768, onetime=1_000_000),
+    "teapot-room-1024x768": dict(scene="reference", w=1024, h=768, onetime=2_000_000),
+    "caustics-1080p": dict(scene="cornell", w=1920, h=1080, onetime=16_000_000),
+    "stress-4k": dict(scene="stress", w=3840, h=2160, onetime=64_000_000),
+}
+DEFAULT_WORKLOAD = "teapot-room-1024x768"  # the scene the north-star target (>=1e9 photons/s on 8 GPUs) is quoted on
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+                pw.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "power_w_max": max(pw), "samples": len(sm)}
+        return out
+
+
+def make_params(abi, fast=True):
+    p = abi.default_params()
+    p.newton_mode = abi.SPPM_NEWTON_FAST if fast else abi.SPPM_NEWTON_EXACT
+    return p
+
+
+def cpu_photon_baseline(wl, scene, prm, hp, target_s=12.0):
+    """The oracle's photon pass on all host cores (each thread an independent tracer over the
+    shared hit-point map + exact kd-tree), sized to ~target_s seconds."""
+    from oracle import Oracle
+    orc = Oracle()
+    threads = orc.max_threads()
+    s, c = orc.photon_bench(scene, prm, hp, 1500, threads, pass_id=1000)
+    rate = c["photons"] / max(s, 1e-6)
+    per_thread = int(max(1500, min(4_000_000, rate * target_s / threads)))
+    s, c = orc.photon_bench(scene, prm, hp, per_thread, threads, pass_id=1001)
+    return dict(value=c["photons"] / s, unit="photons/s", cores=threads, kind="port",
+                sample=f"{threads} threads x {per_thread} photons of {wl} (hit-point map {hp['pos'].shape[0]} pts, exact kd-tree), "
+                       f"{s:.1f} s wall; {c['solves']} Bezier solves"), s, c
+
+
+def run_reference(args):
+    """CPU arm: no GPU.  Eye pass + kd-tree by the oracle (untimed setup, as for the GPU arm),
+    then K steps, each a bounded photon sample on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import Oracle
+    from raytrace3_b200 import abi
+    from raytrace3_b200.scene import make_scene, reference_camera
+    wl = WORKLOADS[args.workload]
+    orc = Oracle()
+    prm = make_params(abi, fast=False)
+    scene = make_scene(wl["scene"])
+    cam = reference_camera(wl["w"], wl["h"])
+    t0 = time.time()
+    hp = orc.eye_pass(scene, prm, cam, 0)
+    t_eye = time.time() - t0
+    threads = orc.max_threads()
+    s, c = orc.photon_bench(scene, prm, hp, 1000, threads, pass_id=999)
+    rate = c["photons"] / max(s, 1e-6)
+    budget = 150.0 / max(1, args.steps + args.warmup)  # whole run within a few minutes
+    per_thread = int(max(500, min(2_000_000, rate * min(budget, 10.0) / threads)))
+    times, photons, solves = [], 0, 0
+    for i in range(args.warmup + args.steps):
+        s, c = orc.photon_bench(scene, prm, hp, per_thread, threads, pass_id=i)
+        if i >= args.warmup:
+            times.append(s)
+            photons += c["photons"]
+            solves += c["solves"]
+    total = sum(times)
+    value = photons / total
+    sample = (f"{threads} threads x {per_thread} photons per step of {args.workload} "
+              f"(CPU eye pass {t_eye:.1f} s untimed, {hp['pos'].shape[0]} hit points, exact kd-tree)")
+    line = {
+        "impl": "reference", "metric": "photons traced+gathered/sec", "value": value, "unit": "photons/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "scene": wl["scene"], "film": [wl["w"], wl["h"]],
+                   "photons_per_step": threads * per_thread, "newton": "50x10 exact order"},
+        "cpu_baseline": {"value": value, "unit": "photons/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "bezier_isects_per_s": solves / total,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--newton", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1 and args.gpus == 1, f"launch with torchrun --nproc-per-node {args.gpus}"
+
+    import torch
+    from raytrace3_b200 import Context, abi
+    from raytrace3_b200.scene import make_scene, reference_camera
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    wl = WORKLOADS[args.workload]
+    prm = make_params(abi, fast=args.newton == "fast")
+    ctx = Context(local_rank, prm)
+    scene = make_scene(wl["scene"])
+    cam = reference_camera(wl["w"], wl["h"])
+    onetime = wl["onetime"]
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ---- setup (untimed): scene, eye pass, hash grid, communicator
+    ctx.upload_scene(scene)
+    n_hp = ctx.eye_pass(cam, 0)
+    ctx.build_index()
+    setup = ctx.counters()
+    if world > 1:
+        uid = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init_rank(rank, world, uid[0])
+
+    def step(i):
+        # weak scaling: rank r traces the global photon indices [r*onetime, (r+1)*onetime) of round i
+        ctx.photon_pass(rank * onetime, onetime, 1 + i)
+        if world > 1:
+            ctx.allreduce()
+        ctx.update()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ctx.reset_counters()
+    launches0 = ctx.counters()["launches"]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.timer_record(0)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ctx.timer_record(1)
+    ms = ctx.timer_elapsed_ms()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    cnt = ctx.counters()
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    total_photons = onetime * len(scene.plvec) * world * args.steps
+    value = total_photons / (ms * 1e-3)
+
+    # ---- e2e: RayTracer::render() through the public API with host buffers
+    from raytrace3_b200 import RayTracer
+    e2e_ms, e2e_phases = [], None
+    film = np.zeros((wl["h"], wl["w"], 3))
+    h2d = scene.texture_bytes() + sum(o.P.nbytes for o in scene.objvec if o.kind == 2) + 328 * len(scene.objvec) + 256
+    d2h = film.nbytes + 8 * 3
+    for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
+        barrier()
+        t0 = time.perf_counter()
+        ctx.upload_scene(scene)                      # H2D: objects, patches, textures (host memory)
+        t1 = time.perf_counter()
+        ctx.eye_pass(cam, 100 + i)
+        t2 = time.perf_counter()
+        ctx.build_index()
+        t3 = time.perf_counter()
+        ctx.photon_pass(rank * onetime, onetime, 200 + i)
+        if world > 1:
+            ctx.allreduce()
+        ctx.update()
+        ctx.synchronize()
+        t4 = time.perf_counter()
+        ctx.resolve(1, onetime * world, wl["w"], wl["h"], out=film)   # D2H: the film
+        barrier()
+        t5 = time.perf_counter()
+        if i > 0:
+            e2e_ms.append((t5 - t0) * 1e3)
+            e2e_phases = {"upload": (t1 - t0) * 1e3, "eye": (t2 - t1) * 1e3, "build": (t3 - t2) * 1e3,
+                          "photon_round": (t4 - t3) * 1e3, "resolve_readback": (t5 - t4) * 1e3}
+    e2e = statistics.median(e2e_ms) if e2e_ms else float('nan')
+    if dist is not None:
+        t = torch.tensor([e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = float(t.item())
+    e2e_value = onetime * len(scene.plvec) * world / (e2e * 1e-3)
+    e2e_counters = ctx.counters()
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per launch = per step at this batch size)
+    peaks, peak_kind = measured_peaks()
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    fp64_peak = ctx.fp64_peak()
+    steps = args.steps
+    ms_trace, ms_sort, ms_gather = cnt["ms_trace"] / steps, cnt["ms_sort"] / steps, cnt["ms_gather"] / steps
+    dep_kept, cand, acc = cnt["deposits_kept"] / steps, cnt["cand_pairs"] / steps, cnt["acc_pairs"] / steps
+    solves, queries = cnt["patch_solves"] / steps, cnt["isect_queries"] / steps
+    gather_bytes = 136.0 * n_hp + 72.0 * dep_kept
+    gather_flops = 13.0 * cand + 9.0 * acc
+    trace_bytes = 84.0 * dep_kept                                      # deposits written (80 B + 4 B key)
+    trace_flops = 175000.0 * solves + 140.0 * queries                  # Newton (350 x 500) + analytic tests
+    kern = {
+        "photon_trace_kernel": dict(ms=ms_trace, bytes=trace_bytes, flops=trace_flops),
+        "gather_kernel": dict(ms=ms_gather, bytes=gather_bytes, flops=gather_flops),
+    }
+    dom = max(kern, key=lambda k: kern[k]["ms"])
+    d = kern[dom]
+    achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, sustained copy)",
+                "ms_per_launch": d["ms"], "share_of_step": d["ms"] / (ms / steps),
+                "fp64_tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0, "fp64_peak_tflops": fp64_peak,
+                "fp64_frac": (d["flops"] / (d["ms"] * 1e-3) / 1e12 / fp64_peak) if d["ms"] > 0 and fp64_peak > 0 else None,
+                "note": "binding resource is the FP64 pipe / latency, not HBM: algorithmic bytes are tiny next to the arithmetic"}
+    kernels = {k: {"ms_per_step": v["ms"], "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0,
+                   "hbm_frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak if v["ms"] > 0 else 0.0,
+                   "fp64_tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0} for k, v in kern.items()}
+    kernels["deposit_sort"] = {"ms_per_step": ms_sort}
+
+    # ---- Bezier ray-patch intersections per second (metric M2), device-resident microbench
+    m2 = None
+    if any(o.kind == 2 for o in scene.objvec):
+        npairs = 1 << 18
+        ms_rep = ctx.bezier_patch_bench(npairs, 3)
+        m2 = {"value": npairs / (ms_rep * 1e-3), "unit": "ray-patch isects/s", "pairs": npairs, "ms": ms_rep,
+              "fp64_tflops": 175000.0 * npairs / (ms_rep * 1e-3) / 1e12, "fp64_peak_tflops": fp64_peak,
+              "in_render": solves * steps / (cnt["ms_trace"] * 1e-3) if cnt["ms_trace"] > 0 else None}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        hp = ctx.export_hitpoints()
+        cpu, _, _ = cpu_photon_baseline(args.workload, scene, make_params(abi, fast=False), hp)
+
+    line = {
+        "metric": "photons traced+gathered/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "scene": wl["scene"], "film": [wl["w"], wl["h"]], "hit_points": n_hp,
+                   "photons_per_gpu_per_step": onetime * len(scene.plvec), "newton": f"50x10 {args.newton}",
+                   "update_mode": "reference", "l2": "inputs larger than L2 (deposit list + hit-point map > 126 MB); new photons every step",
+                   "textures": "synthetic, reference sizes", "parallelism": f"photons x{world}, hit points replicated"},
+        "e2e": {"value": e2e_value, "unit": "photons/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e, "phases_ms": e2e_phases, "what": "RayTracer::render(): scene upload + eye pass + grid build + 1 round + resolve + film read-back"},
+        "gpu_launches": int(cnt["launches"] - launches0),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+        "bezier_isects": m2,
+        "per_photon": {"isect_queries": queries / (onetime * len(scene.plvec)), "deposits": cnt["deposits"] / steps / (onetime * len(scene.plvec)),
+                       "deposits_kept": dep_kept / (onetime * len(scene.plvec)), "cand_pairs": cand / (onetime * len(scene.plvec)),
+                       "patch_solves": solves / (onetime * len(scene.plvec))},
+        "setup_ms": {"eye": setup["ms_eye"], "build": setup["ms_build"], "eye_e2e": e2e_counters["ms_eye"], "build_e2e": e2e_counters["ms_build"]},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -213,6 +213,9 @@ int sppm_bezier_patch_batch(sppm_ctx* ctx, const double* rays6, const int32_t* p
 /* Same solve on n synthetic device-resident pairs, repeated reps times; returns the
  * average milliseconds of one repetition (CUDA events). */
 int sppm_bezier_patch_bench(sppm_ctx* ctx, int64_t n, int32_t reps, uint64_t seed, double* ms_per_rep);
+/* Measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2), the roofline denominator
+ * of the Newton and gather arithmetic. */
+int sppm_fp64_peak(sppm_ctx* ctx, double* tflops);
 /* Hit-point map import/export (AoS of the live HitPoint fields, Raytracer.h:47-58):
  * pos3,n3,wgt3 = double[n][3], r2 = double[n], pix = int32[n][2] (row, col). */
 int sppm_import_hitpoints(sppm_ctx* ctx, int64_t n, const double* pos3, const double* n3,

@@ -63,6 +63,11 @@ class Oracle:
         L.orc_photon_pass.argtypes = [C.POINTER(abi.SppmSceneDesc), C.POINTER(abi.SppmParams), U64, U64, U64, VP, I64,
                                       VP, VP, VP, VP, VP, VP, I64, VP, VP, VP, VP, VP, VP]
         L.orc_photon_pass.restype = I64
+        L.orc_photon_bench.argtypes = [C.POINTER(abi.SppmSceneDesc), C.POINTER(abi.SppmParams), U64, U64, I32, VP, I64,
+                                       VP, VP, VP, VP, VP]
+        L.orc_photon_bench.restype = DBL
+        L.orc_patch_bench.argtypes = [C.POINTER(abi.SppmSceneDesc), C.POINTER(abi.SppmParams), VP, VP, I64, I32, VP]
+        L.orc_patch_bench.restype = DBL
         L.orc_update.argtypes = [I64, I32, DBL, VP, VP, VP, VP]
         L.orc_resolve.argtypes = [I64, VP, VP, VP, I32, I32, I32, I32, VP]
         L.orc_tonemap.argtypes = [VP, I32, I32, DBL, VP]
@@ -222,6 +227,28 @@ class Oracle:
         if keep_deposits:
             out["dep"] = dict(x=dx[:m], n=dn[:m], flux=df[:m], photon=dpid[:m], bounce=dbn[:m])
         return out
+
+    def photon_bench(self, scene, prm, hp, count_per_thread, threads, pass_id=0):
+        """Wall seconds for `threads` replicas x count_per_thread photons (per light) + counters."""
+        d = self._desc(scene)
+        a = [_f64(hp[k]) for k in ("pos", "n", "wgt", "r2")]
+        n = a[0].shape[0]
+        tree = self.lib.orc_kdtree_build(n, _p(a[0]))
+        counters = np.zeros(4, dtype=np.uint64)
+        try:
+            s = self.lib.orc_photon_bench(C.byref(d), C.byref(prm), count_per_thread, pass_id, threads, tree, n, _p(a[0]),
+                                          _p(a[1]), _p(a[2]), _p(a[3]), _p(counters))
+        finally:
+            self.lib.orc_kdtree_free(tree)
+        return s, dict(zip(("queries", "solves", "deposits", "photons"), counters.tolist()))
+
+    def patch_bench(self, scene, prm, rays6, patch_idx, threads):
+        d = self._desc(scene)
+        rays6 = _f64(rays6, (-1, 6))
+        patch_idx = np.ascontiguousarray(patch_idx, dtype=np.int32)
+        out = np.empty((rays6.shape[0], 3))
+        s = self.lib.orc_patch_bench(C.byref(d), C.byref(prm), _p(rays6), _p(patch_idx), rays6.shape[0], threads, _p(out))
+        return s, out
 
     def update(self, mode, alpha, newN, N, r2, tao):
         self.lib.orc_update(newN.shape[0], mode, alpha, _p(newN), _p(N), _p(r2), _p(tao))

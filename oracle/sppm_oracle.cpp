@@ -869,14 +869,47 @@ void orc_bezier_patch_batch(const SppmSceneDesc* scene, const SppmParams* prm, c
 int64_t orc_eye_pass(const SppmSceneDesc* scene, const SppmParams* prm, const SppmCameraDesc* cam, uint64_t pass_id,
                      int64_t cap, double* pos3, double* n3, double* wgt3, double* r2, int32_t* pix, uint32_t* node) {
   SceneC sc(scene);
-  HpSink out{cap, 0, pos3, n3, wgt3, r2, pix, node, prm->init_r2};
-  for (int i = 0; i < cam->h; i++)  // GetHitPoint (Raytracer.h:105-113)
+  // GetHitPoint (Raytracer.h:105-113).  Rows are traced in parallel into per-row buffers and
+  // concatenated in row order, so Hvec's order is the reference's (pixels are independent).
+  struct Row {
+    std::vector<double> pos, nrm, wgt, r2;
+    std::vector<int32_t> pix;
+    std::vector<uint32_t> node;
+  };
+  std::vector<Row> rows(cam->h);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < cam->h; i++) {
+    Row& R = rows[i];
+    const int64_t rcap = (int64_t)cam->w * 64;
+    R.pos.resize(3 * rcap); R.nrm.resize(3 * rcap); R.wgt.resize(3 * rcap); R.r2.resize(rcap);
+    R.pix.resize(2 * rcap); R.node.resize(rcap);
+    HpSink out{rcap, 0, R.pos.data(), R.nrm.data(), R.wgt.data(), R.r2.data(), R.pix.data(), R.node.data(), prm->init_r2};
     for (int j = 0; j < cam->w; j++) {
       V3 o, d;
       cameraEmit(cam, i, j, o, d);
       ViewTrace(sc, *prm, o, d, 0, V3(1, 1, 1), i, j, pass_id, (uint64_t)i * cam->w + j, 1, out, nullptr);
     }
-  return out.n;
+    const int64_t n = std::min(out.n, rcap);
+    R.pos.resize(3 * n); R.nrm.resize(3 * n); R.wgt.resize(3 * n); R.r2.resize(n); R.pix.resize(2 * n); R.node.resize(n);
+  }
+  int64_t total = 0;
+  for (int i = 0; i < cam->h; i++) {
+    const Row& R = rows[i];
+    const int64_t n = (int64_t)R.r2.size();
+    for (int64_t k = 0; k < n; k++, total++) {
+      if (total >= cap) continue;
+      for (int c = 0; c < 3; c++) {
+        pos3[3 * total + c] = R.pos[3 * k + c];
+        n3[3 * total + c] = R.nrm[3 * k + c];
+        wgt3[3 * total + c] = R.wgt[3 * k + c];
+      }
+      r2[total] = R.r2[k];
+      pix[2 * total] = R.pix[2 * k];
+      pix[2 * total + 1] = R.pix[2 * k + 1];
+      if (node) node[total] = R.node[k];
+    }
+  }
+  return total;
 }
 
 void orc_gather_brute(int64_t n_hp, const double* pos3, const double* n3, const double* wgt3, const double* r2,
@@ -934,6 +967,63 @@ int64_t orc_photon_pass(const SppmSceneDesc* scene, const SppmParams* prm, uint6
                   counters);
     }
   return sink.n;
+}
+
+// Timing leg: `threads` OpenMP threads, each an independent photon tracer with private
+// accumulators over the shared read-only hit-point map + kd-tree (the reference's replica
+// structure, Raytracer.h:442-447, restricted to the photon pass).  Thread t traces photons
+// [t*count, (t+1)*count) of every light.  Returns wall seconds of the parallel region.
+double orc_photon_bench(const SppmSceneDesc* scene, const SppmParams* prm, uint64_t count, uint64_t pass_id,
+                        int32_t threads, void* tree, int64_t n_hp, const double* pos3, const double* n3,
+                        const double* wgt3, const double* r2, uint64_t* counters) {
+  SceneC sc(scene);
+  HitPoints hp{n_hp, pos3, n3, wgt3, r2};
+  std::vector<std::vector<uint64_t>> cnts(threads, std::vector<uint64_t>(4, 0));
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  std::vector<std::vector<int32_t>> newN(threads);
+  std::vector<std::vector<double>> tao(threads);
+  for (int t = 0; t < threads; t++) {
+    newN[t].assign(n_hp, 0);
+    tao[t].assign(3 * n_hp, 0.0);
+  }
+  const double t0 = now();
+#pragma omp parallel for num_threads(threads) schedule(static, 1)
+  for (int t = 0; t < threads; t++) {
+    for (size_t pl = 0; pl < sc.lights.size(); pl++)
+      for (uint64_t j = (uint64_t)t * count; j < (uint64_t)(t + 1) * count; j++) {
+        uint64_t id = ((uint64_t)pl << 40) | j;
+        V3 flux = V3(sc.lights[pl].color) * PI_ * 4;
+        V3 dir = GetUnitRandVec(prm->seed, pass_id, id, P_EMIT);
+        cnts[t][3]++;
+        PhotonTrace(sc, *prm, V3(sc.lights[pl].pos), dir, flux, pass_id, id, hp, (KdTree*)tree, newN[t].data(),
+                    tao[t].data(), nullptr, cnts[t].data());
+      }
+  }
+  const double t1 = now();
+  if (counters)
+    for (int k = 0; k < 4; k++) {
+      counters[k] = 0;
+      for (int t = 0; t < threads; t++) counters[k] += cnts[t][k];
+    }
+  return t1 - t0;
+}
+
+// Timing leg for M2: `threads` threads solve n (ray, patch) pairs with Bezier3::newton.
+double orc_patch_bench(const SppmSceneDesc* scene, const SppmParams* prm, const double* rays6,
+                       const int32_t* patch_idx, int64_t n, int32_t threads, double* tuv_out) {
+  SceneC sc(scene);
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 8)
+  for (int64_t i = 0; i < n; i++) {
+    int gp = patch_idx[i];
+    V3 r = newton(&sc.P[(size_t)gp * 16], V3(rays6 + 6 * i), V3(rays6 + 6 * i + 3), prm->newton_restarts,
+                  prm->newton_iters, [&](int o, double uv[2]) {
+                    draw2(prm->seed, 0, (uint64_t)i, 0, SPPM_DOMAIN_TEST, (uint32_t)o, (uint32_t)gp, uv);
+                  });
+    for (int k = 0; k < 3; k++) tuv_out[3 * i + k] = r[k];
+  }
+  return now() - t0;
 }
 
 void orc_update(int64_t n_hp, int32_t mode, double alpha, int32_t* newN, int32_t* N, double* r2, double* tao3) {

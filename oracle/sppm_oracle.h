@@ -80,6 +80,13 @@ int64_t orc_photon_pass(const SppmSceneDesc* scene, const SppmParams* prm, uint6
                         double* dep_x3, double* dep_n3, double* dep_flux3, uint64_t* dep_photon,
                         int32_t* dep_bounce, uint64_t* counters /* [4]: queries, solves, deposits, photons */);
 
+/* Timing legs (bench.py cpu_baseline / --impl reference): see sppm_oracle.cpp. */
+double orc_photon_bench(const SppmSceneDesc* scene, const SppmParams* prm, uint64_t count, uint64_t pass_id,
+                        int32_t threads, void* tree, int64_t n_hp, const double* pos3, const double* n3,
+                        const double* wgt3, const double* r2, uint64_t* counters);
+double orc_patch_bench(const SppmSceneDesc* scene, const SppmParams* prm, const double* rays6,
+                       const int32_t* patch_idx, int64_t n, int32_t threads, double* tuv_out);
+
 /* HitPoint::update (Raytracer.h:69-79) over all hit points. */
 void orc_update(int64_t n_hp, int32_t mode, double alpha, int32_t* newN, int32_t* N, double* r2, double* tao3);
 /* Film resolve (Raytracer.h:281-293). film = double[h][w][3], zeroed first. */

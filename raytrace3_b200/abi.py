@@ -114,6 +114,7 @@ PROTOTYPES = {
     "sppm_intersect_batch": (C.c_int, [VP, VP, I64, VP, U64, I32, VP]),
     "sppm_bezier_patch_batch": (C.c_int, [VP, VP, VP, I64, VP, VP]),
     "sppm_bezier_patch_bench": (C.c_int, [VP, I64, I32, U64, C.POINTER(DBL)]),
+    "sppm_fp64_peak": (C.c_int, [VP, C.POINTER(DBL)]),
     "sppm_import_hitpoints": (C.c_int, [VP, I64, VP, VP, VP, VP, VP, I32, I32]),
     "sppm_export_hitpoints": (C.c_int, [VP, I64, VP, VP, VP, VP, VP, VP, C.POINTER(I64)]),
     "sppm_gather_deposits": (C.c_int, [VP, I64, VP, VP, VP]),

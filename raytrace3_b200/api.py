@@ -173,6 +173,11 @@ class Context:
         self._ck(self.lib.sppm_bezier_patch_bench(self.h, n, reps, seed, C.byref(ms)), "sppm_bezier_patch_bench")
         return ms.value
 
+    def fp64_peak(self) -> float:
+        tf = C.c_double()
+        self._ck(self.lib.sppm_fp64_peak(self.h, C.byref(tf)), "sppm_fp64_peak")
+        return tf.value
+
     def import_hitpoints(self, pos3, n3, wgt3, r2, pix, w, h):
         pos3, n3, wgt3 = _f64(pos3, (-1, 3)), _f64(n3, (-1, 3)), _f64(wgt3, (-1, 3))
         r2 = _f64(r2, (-1,))

@@ -74,6 +74,17 @@ __global__ void tonemap_kernel(const double* film, int w, int h, double div, uin
   bgr[((size_t)(h - 1 - i1) * w + j) * 3 + k] = (uint8_t)v;    // row flip (Raytracer.h:467)
 }
 
+// FP64 FMA throughput probe (the roofline denominator of the Newton / gather kernels; not in
+// MEASURED_PEAKS.json): 8 independent DFMA chains per thread.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 __global__ void synth_pairs_kernel(DevScene s, long long n, uint64_t seed, double* rays6, int32_t* patch) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -128,13 +139,15 @@ void free_scene(sppm_ctx* c) {
   c->scene_bufs.clear();
   c->scene_ok = false;
 }
+// Scene arrays live in grow-only device buffers (slot i of scene_bufs) that are reused by the
+// next upload: re-uploading a scene of the same shape costs only the copies.
 template <class T>
-cudaError_t upload(sppm_ctx* c, const std::vector<T>& v, const T** out) {
-  DevBuf b;
-  cudaError_t e = dev_reserve(b, std::max<size_t>(v.size() * sizeof(T), 16));
+cudaError_t upload(sppm_ctx* c, size_t slot, const T* host, size_t count, const T** out) {
+  if (c->scene_bufs.size() <= slot) c->scene_bufs.resize(slot + 1);
+  DevBuf& b = c->scene_bufs[slot];
+  cudaError_t e = dev_reserve(b, std::max<size_t>(count * sizeof(T), 16));
   if (e) return e;
-  c->scene_bufs.push_back(b);
-  if (!v.empty()) e = cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+  if (count) e = cudaMemcpyAsync(b.p, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream);
   *out = (const T*)b.p;
   return e;
 }
@@ -248,7 +261,7 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
   if (s->n_patches < 0 || s->n_patches >= (1 << 16)) return fail(c, SPPM_ERR_INVALID, "n_patches out of range");
   Bind b(c);
   CU(c, cudaStreamSynchronize(c->stream));
-  free_scene(c);
+  c->scene_ok = false;
   // per-patch AABBs (Bezier.h:165-175) and per-object AABBs (Bezier.h:219-222), addpoint semantics
   std::vector<double> patchP((size_t)s->n_patches * 48), patchBox((size_t)s->n_patches * 6);
   for (int p = 0; p < s->n_patches; p++) {
@@ -324,25 +337,22 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
   for (int t = 0; t < s->n_textures; t++) {
     const SppmTexture& ht = s->textures[t];
     if (ht.rows <= 0 || ht.cols <= 0 || !ht.bgr8) return fail(c, SPPM_ERR_INVALID, "empty texture (Q18: the reference would read out of range)");
-    DevBuf tb;
-    const size_t bytes = (size_t)ht.rows * ht.cols * 3;
-    CU(c, dev_reserve(tb, bytes));
-    c->scene_bufs.push_back(tb);
-    CU(c, cudaMemcpyAsync(tb.p, ht.bgr8, bytes, cudaMemcpyHostToDevice, c->stream));
+    const uint8_t* dev = nullptr;
+    CU(c, upload(c, 5 + (size_t)t, ht.bgr8, (size_t)ht.rows * ht.cols * 3, &dev));
     tex[t].rows = ht.rows;
     tex[t].cols = ht.cols;
-    tex[t].bgr = (const uint8_t*)tb.p;
+    tex[t].bgr = dev;
   }
   DevScene ds;
   ds.n_obj = s->n_objects;
   ds.n_patch = s->n_patches;
   ds.n_light = s->n_lights;
   ds.n_tex = s->n_textures;
-  CU(c, upload(c, objs, &ds.obj));
-  CU(c, upload(c, patchP, &ds.patchP));
-  CU(c, upload(c, patchBox, &ds.patchBox));
-  CU(c, upload(c, lights, &ds.lights));
-  CU(c, upload(c, tex, &ds.tex));
+  CU(c, upload(c, 0, objs.data(), objs.size(), &ds.obj));
+  CU(c, upload(c, 1, patchP.data(), patchP.size(), &ds.patchP));
+  CU(c, upload(c, 2, patchBox.data(), patchBox.size(), &ds.patchBox));
+  CU(c, upload(c, 3, lights.data(), lights.size(), &ds.lights));
+  CU(c, upload(c, 4, tex.data(), tex.size(), &ds.tex));
   CU(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
   c->scene = ds;
   CU(c, trace_configure(c));
@@ -629,6 +639,26 @@ int sppm_bezier_patch_bench(sppm_ctx* c, int64_t n, int32_t reps, uint64_t seed,
   dev_free(dp);
   dev_free(dt);
   return rc;
+}
+
+int sppm_fp64_peak(sppm_ctx* c, double* tflops) {
+  if (!c || !tflops) return SPPM_ERR_INVALID;
+  Bind b(c);
+  const int blocks = c->sm_count * 8, iters = 1 << 14;
+  CU(c, dev_reserve(c->scratch, (size_t)blocks * 256 * 8));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CU(c, cudaEventRecord(c->ev[4], c->stream));
+    fp64_peak_kernel<<<blocks, 256, 0, c->stream>>>((double*)c->scratch.p, iters, 0.999999, 1e-6);
+    CU(c, cudaEventRecord(c->ev[5], c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CU(c, cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]));
+    const double tf = 2.0 * 8 * iters * (double)blocks * 256 / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  *tflops = best;
+  return SPPM_OK;
 }
 
 int sppm_import_hitpoints(sppm_ctx* c, int64_t n, const double* pos3, const double* n3, const double* wgt3,

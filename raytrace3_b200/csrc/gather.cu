@@ -174,30 +174,56 @@ struct GatherArgs {
   DevCounters* counters;
 };
 
-// One warp per occupied hit-point cell.  The warp's lanes are split hl x dl: hl lanes hold
-// hit points of the cell (pos, n, R2 in registers), dl = 32/hl lanes stride over the
-// deposits of the 27 neighbour cells; all lanes with the same deposit index read the same
-// 80-byte record (five 128-bit broadcast loads).  Partial sums are combined with shuffles
-// and each hit point's accumulators are written once.
-__global__ void __launch_bounds__(256) gather_kernel(const GatherArgs a) {
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+// One CTA per occupied hit-point cell (cells are taken from a global work counter).  The
+// deposits of the cell's 27 neighbour cells are streamed through a shared-memory tile with
+// coalesced 128-bit loads (their ranges are contiguous runs of the cell-sorted list); the 256
+// threads are split hl x dl: hl threads hold hit points of the cell (pos, n, R2 in registers),
+// dl = 256/hl threads stride over the tile, so a warp reads each 80-byte record as five
+// broadcast 128-bit shared loads.  Partial sums are combined with shuffles + shared memory
+// and every hit point's accumulators are written exactly once per batch (no atomics).
+constexpr int G_THREADS = 256;
+constexpr int G_TILE = 384;  // deposits per tile: 30 KB
+
+__global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, unsigned int* work_counter) {
+  __shared__ double2 tile[G_TILE * 5];
+  __shared__ int rs[27], rl[27];
+  __shared__ int s_cell, s_total;
+  __shared__ int red_cnt[G_THREADS];
+  __shared__ double red_s[3][G_THREADS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned long long cand = 0, acc = 0;
-  for (long long c = warp0; c < a.n_occ; c += nwarps) {
-    const int hs = a.occ_start[c], he = a.occ_start[c + 1];
-    int2 myr = make_int2(0, 0);
-    if (lane < 27) {
-      const int32_t slot = a.occ_nbr[c * 27 + lane];
-      if (slot >= 0) myr = a.range[slot];
+  for (;;) {
+    __syncthreads();  // previous cell fully done (rs/rl/s_cell reusable)
+    if (tid == 0) s_cell = (int)atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const int c = s_cell;
+    if (c >= a.n_occ) break;
+    if (tid < 32) {
+      int st = 0, ln = 0;
+      if (tid < 27) {
+        const int32_t slot = a.occ_nbr[(long long)c * 27 + tid];
+        if (slot >= 0) {
+          const int2 r = a.range[slot];
+          st = r.x;
+          ln = r.y - r.x;
+        }
+        rs[tid] = st;
+        rl[tid] = ln;
+      }
+      int tot = ln;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) tot += __shfl_xor_sync(FULL, tot, off);
+      if (tid == 0) s_total = tot;
     }
-    if (!__any_sync(FULL, myr.y > myr.x)) continue;  // no deposit near this cell in this batch
-    for (int h0 = hs; h0 < he; h0 += 32) {
-      const int H = min(32, he - h0);
+    __syncthreads();
+    if (s_total == 0) continue;  // no deposit near this cell in this batch
+    const int hs = a.occ_start[c], he = a.occ_start[c + 1];
+    for (int h0 = hs; h0 < he; h0 += G_THREADS) {
+      const int H = min(G_THREADS, he - h0);
       int hl = 1;
       while (hl < H) hl <<= 1;
-      const int dl = 32 / hl;
-      const int my_h = lane & (hl - 1), my_d = lane / hl;
+      const int dl = G_THREADS / hl;
+      const int my_h = tid & (hl - 1), my_d = tid / hl;
       const int i = h0 + my_h;
       const bool valid = my_h < H;
       double px = 0, py = 0, pz = 0, nx = 0, ny = 0, nz = 0, r2 = -1;
@@ -208,39 +234,82 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs a) {
       }
       int cnt = 0;
       double s0 = 0, s1 = 0, s2 = 0;
-      for (int nb = 0; nb < 27; nb++) {
-        const int ds = __shfl_sync(FULL, myr.x, nb), de = __shfl_sync(FULL, myr.y, nb);
-        for (int d = ds + my_d; d < de; d += dl) {
-          const double2* q = reinterpret_cast<const double2*>(a.dep + d);
-          const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3), q4 = __ldg(q + 4);
-          // x = (q0.x, q0.y, q1.x)  N = (q1.y, q2.x, q2.y)  flux = (q3.x, q3.y, q4.x)
-          const double vx = px - q0.x, vy = py - q0.y, vz = pz - q1.x;  // Raytracer.h:152
-          const double vv = (vx * vx + vy * vy) + vz * vz;
-          if (valid && vv < a.search_r2) {  // flann radiusSearch, strict '<' (Q3)
-            cand++;
-            const double nn = (nx * q1.y + ny * q2.x) + nz * q2.y;
-            if (nn > SPPM_NORMAL_AGREE && vv <= r2) {  // Raytracer.h:154
-              cnt++;
-              s0 += q3.x; s1 += q3.y; s2 += q4.x;
-              acc++;
+      int r = 0, off = 0, fill = 0;
+      while (r < 27) {
+        const int take = min(rl[r] - off, G_TILE - fill);
+        if (take > 0) {
+          const double2* src = reinterpret_cast<const double2*>(a.dep + rs[r] + off);
+          double2* dst = tile + fill * 5;
+          for (int k = tid; k < take * 5; k += G_THREADS) dst[k] = __ldg(src + k);
+          fill += take;
+          off += take;
+        }
+        if (off >= rl[r]) {
+          r++;
+          off = 0;
+        }
+        if (fill == G_TILE || (r == 27 && fill > 0)) {
+          __syncthreads();
+          if (valid) {
+            for (int d = my_d; d < fill; d += dl) {
+              const double2* q = tile + d * 5;
+              const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+              // x = (q0.x, q0.y, q1.x)  N = (q1.y, q2.x, q2.y)  flux = (q3.x, q3.y, q4.x)
+              const double vx = px - q0.x, vy = py - q0.y, vz = pz - q1.x;  // Raytracer.h:152
+              const double vv = (vx * vx + vy * vy) + vz * vz;
+              if (vv < a.search_r2) {  // flann radiusSearch, strict '<' (Q3)
+                cand++;
+                const double nn = (nx * q1.y + ny * q2.x) + nz * q2.y;
+                if (nn > SPPM_NORMAL_AGREE && vv <= r2) {  // Raytracer.h:154
+                  const double2 q3 = q[3], q4 = q[4];
+                  cnt++;
+                  s0 += q3.x; s1 += q3.y; s2 += q4.x;
+                  acc++;
+                }
+              }
             }
           }
+          __syncthreads();
+          fill = 0;
         }
       }
-      for (int off = hl; off < 32; off <<= 1) {
-        cnt += __shfl_xor_sync(FULL, cnt, off);
-        s0 += __shfl_xor_sync(FULL, s0, off);
-        s1 += __shfl_xor_sync(FULL, s1, off);
-        s2 += __shfl_xor_sync(FULL, s2, off);
+      // combine the dl partial sums of every hit point
+      if (hl < 32) {
+        for (int o = hl; o < 32; o <<= 1) {
+          cnt += __shfl_xor_sync(FULL, cnt, o);
+          s0 += __shfl_xor_sync(FULL, s0, o);
+          s1 += __shfl_xor_sync(FULL, s1, o);
+          s2 += __shfl_xor_sync(FULL, s2, o);
+        }
       }
-      if (valid && my_d == 0 && cnt > 0) {  // hp->newN++, hp->tao += wgt.mul(flux)*PI_INV (Raytracer.h:155-156)
-        a.s.dN[i] += cnt;
-        a.s.dtao[i] += (a.s.wx[i] * s0) * SPPM_PI_INV;
-        a.s.dtao[a.n_hp + i] += (a.s.wy[i] * s1) * SPPM_PI_INV;
-        a.s.dtao[2 * a.n_hp + i] += (a.s.wz[i] * s2) * SPPM_PI_INV;
+      red_cnt[tid] = cnt;
+      red_s[0][tid] = s0; red_s[1][tid] = s1; red_s[2][tid] = s2;
+      __syncthreads();
+      if (tid < hl && valid) {
+        int tc = 0;
+        double t0 = 0, t1 = 0, t2 = 0;
+        if (hl < 32) {
+          for (int w = 0; w < G_THREADS / 32; w++) {
+            tc += red_cnt[w * 32 + tid];
+            t0 += red_s[0][w * 32 + tid]; t1 += red_s[1][w * 32 + tid]; t2 += red_s[2][w * 32 + tid];
+          }
+        } else {
+          for (int d = 0; d < dl; d++) {
+            tc += red_cnt[d * hl + tid];
+            t0 += red_s[0][d * hl + tid]; t1 += red_s[1][d * hl + tid]; t2 += red_s[2][d * hl + tid];
+          }
+        }
+        if (tc > 0) {  // hp->newN++, hp->tao += wgt.mul(flux)*PI_INV (Raytracer.h:155-156)
+          a.s.dN[i] += tc;
+          a.s.dtao[i] += (a.s.wx[i] * t0) * SPPM_PI_INV;
+          a.s.dtao[a.n_hp + i] += (a.s.wy[i] * t1) * SPPM_PI_INV;
+          a.s.dtao[2 * a.n_hp + i] += (a.s.wz[i] * t2) * SPPM_PI_INV;
+        }
       }
+      __syncthreads();
     }
   }
+  (void)warp;
   for (int off = 16; off > 0; off >>= 1) {
     cand += __shfl_xor_sync(FULL, cand, off);
     acc += __shfl_xor_sync(FULL, acc, off);
@@ -498,11 +567,11 @@ cudaError_t sort_and_gather(sppm_ctx* c, int64_t m) {
   a.dep = (const Deposit*)c->dep_sorted.p;
   a.search_r2 = c->prm.init_r2;
   a.counters = (DevCounters*)c->counters.p;
-  const long long warps = c->n_occ;
-  unsigned blocks = nblk(warps * 32, 256);
-  const unsigned cap = (unsigned)c->sm_count * 8 * 4;
-  if (blocks > cap) blocks = cap;
-  gather_kernel<<<blocks, 256, 0, st>>>(a);
+  unsigned int* work_counter = (unsigned int*)((unsigned long long*)c->dev_scalars.p + 4);
+  CK(cudaMemsetAsync(work_counter, 0, 4, st));
+  unsigned blocks = (unsigned)c->sm_count * 4;  // persistent CTAs, cells handed out dynamically
+  if (blocks > (unsigned)c->n_occ) blocks = (unsigned)c->n_occ;
+  gather_kernel<<<blocks, G_THREADS, 0, st>>>(a, work_counter);
   CK(cudaEventRecord(c->ev[3], st));
   c->host_counters.launches += 4;
   return cudaGetLastError();

@@ -249,12 +249,12 @@ def test_photon_pass_deposits_and_stats(ctx, oracle):
         i = key_r.get((int(dep["photon"][j]), int(dep["bounce"][j])))
         if i is None:
             continue
-        err = np.abs(dep["x"][j] - rd["x"][i]).max()
+        err = (np.abs(dep["x"][j] - rd["x"][i]) / np.maximum(1.0, np.abs(rd["x"][i]))).max()
         if err < 1e-6:
             matched += 1
             maxerr = max(maxerr, err)
     assert matched >= 0.998 * rd["x"].shape[0], (matched, rd["x"].shape[0], len(okey))
-    assert maxerr < 1e-8
+    assert maxerr < 1e-10  # relative: positions agree to ulps (sin/cos/acos differ by ulps)
     got = ctx.export_stats(hp["pos"].shape[0])
     # statistics: identical deposits up to ulps -> newN equal except where a deposit sits within
     # ulps of a radius boundary; require near-total agreement and close totals
