@@ -62,11 +62,12 @@ struct SceneView {
   const double* patchP;
   const double* patchBox;
   const DevTexture* tex;
+  const double* lut255;  // lut255[b] = b / 255.0 (Element.h:54-57), exact quotients
   int n_obj;
 };
 
 __host__ __device__ inline size_t scene_smem_bytes(int n_obj, int n_patch, bool patches_in_smem) {
-  size_t b = (size_t)n_obj * sizeof(DevObject);
+  size_t b = (size_t)n_obj * sizeof(DevObject) + 256 * sizeof(double);
   if (patches_in_smem) b += (size_t)n_patch * 54 * sizeof(double);
   return (b + 15) & ~(size_t)15;
 }
@@ -81,8 +82,13 @@ __device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, 
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
     v.obj = reinterpret_cast<const DevObject*>(smem);
   }
+  {
+    double* lut = reinterpret_cast<double*>(smem + (size_t)s.n_obj * sizeof(DevObject));
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = i / 255.0;
+    v.lut255 = lut;
+  }
   if (patches_in_smem) {
-    double* dp = reinterpret_cast<double*>(smem + (size_t)s.n_obj * sizeof(DevObject));
+    double* dp = reinterpret_cast<double*>(smem + (size_t)s.n_obj * sizeof(DevObject)) + 256;
     double* db = dp + (size_t)s.n_patch * 48;
     for (int i = threadIdx.x; i < s.n_patch * 48; i += blockDim.x) dp[i] = s.patchP[i];
     for (int i = threadIdx.x; i < s.n_patch * 6; i += blockDim.x) db[i] = s.patchBox[i];
@@ -99,7 +105,7 @@ __device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, 
 }
 
 // ---- Element.h:61-72 Texture::colorUV ------------------------------------------------
-__device__ inline d3 color_uv(const DevTexture& t, double u, double v) {
+__device__ inline d3 color_uv(const DevTexture& t, const double* __restrict__ lut255, double u, double v) {
   const int rows = t.rows, cols = t.cols;
   double row = (u - floor(u)) * rows, col = (v - floor(v)) * cols;
   int r1 = (int)floor(row + 1e-10), r2 = r1 + 1;
@@ -116,8 +122,8 @@ __device__ inline d3 color_uv(const DevTexture& t, double u, double v) {
   double o[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    double a = __ldg(p11 + k) / 255.0, b = __ldg(p12 + k) / 255.0, c = __ldg(p21 + k) / 255.0,
-           d = __ldg(p22 + k) / 255.0;
+    const double a = lut255[__ldg(p11 + k)], b = lut255[__ldg(p12 + k)], c = lut255[__ldg(p21 + k)],
+                 d = lut255[__ldg(p22 + k)];
     o[k] = ((a * detR * detC + b * detR * (1 - detC)) + c * (1 - detR) * detC) + d * (1 - detR) * (1 - detC);
   }
   return d3{o[0], o[1], o[2]};
@@ -430,35 +436,50 @@ __device__ inline Hit near_collide(const SceneView& sv, WarpScratch* ws, const N
         double pt = SPPM_MAX_NUM, pu = SPPM_MAX_NUM, pv = SPPM_MAX_NUM;  // para (Bezier.h:246)
         int index = -1;
         int n_items = 0;
-        for (int p = 0; p <= ob.n_patch; p++) {
-          bool hitp = false;
-          if (p < ob.n_patch) {
-            hitp = in_box && aabb_intersect(sv.patchBox + (size_t)(ob.first_patch + p) * 6, org, dir);  // Bezier.h:178
+        // Patch culling is cooperative: for every ray inside the object box (usually one or
+        // two lanes of a photon warp) the 32 lanes test 32 patch boxes at once (Bezier.h:178);
+        // items are queued in (ray lane, patch) order, which the per-lane filter below needs.
+        // The queue is flushed (Newton tasks over all lanes) whenever it cannot take 32 more.
+        unsigned boxmask = __ballot_sync(FULL, in_box);
+        const int n_chunks = (ob.n_patch + 31) >> 5;
+        int src = -1, ch = 0;  // ray (lane) being culled and its next 32-patch chunk; warp-uniform
+        for (;;) {
+          while (n_items <= QCAP - 32) {
+            if (src < 0) {
+              if (!boxmask) break;
+              src = __ffs(boxmask) - 1;
+              boxmask &= boxmask - 1;
+              ch = 0;
+            }
+            const d3 so = d3{ws->ray[0][src], ws->ray[1][src], ws->ray[2][src]};
+            const d3 sd = d3{ws->ray[3][src], ws->ray[4][src], ws->ray[5][src]};
+            const int p = (ch << 5) + lane;
+            const bool hitp = p < ob.n_patch && aabb_intersect(sv.patchBox + (size_t)(ob.first_patch + p) * 6, so, sd);
             const unsigned b = __ballot_sync(FULL, hitp);
-            if (hitp) ws->item[n_items + __popc(b & ((1u << lane) - 1))] = (unsigned)lane | ((unsigned)(ob.first_patch + p) << 8);
+            if (hitp) ws->item[n_items + __popc(b & ((1u << lane) - 1))] = (unsigned)src | ((unsigned)(ob.first_patch + p) << 8);
             n_items += __popc(b);
+            if (++ch == n_chunks) src = -1;
           }
-          if (n_items > QCAP - 32 || (p == ob.n_patch && n_items > 0)) {
-            __syncwarp();
-            flush_items(sv, ws, n_items, cfg, pass, domain, nullptr, 0, lane);
-            if (lane == 0) solves += (unsigned long long)n_items;
-            // per-lane filter in patch order (Bezier.h:249-261)
-            for (int i = 0; i < n_items; i++) {
-              const unsigned it = ws->item[i];
-              if ((int)(it & 31) == lane) {
-                const double qt = ws->it_t[i], qu = ws->it_u[i], qv = ws->it_v[i];
-                if (qt < SPPM_M_EPS || qt > pt || qu < -SPPM_M_EPS || qu > 1 + SPPM_M_EPS || qv < -SPPM_M_EPS ||
-                    qv > 1 + SPPM_M_EPS)
-                  continue;
-                if (qt < pt) {
-                  pt = qt; pu = qu; pv = qv;
-                  index = (int)(it >> 8);
-                }
+          if (n_items == 0) break;
+          __syncwarp();
+          flush_items(sv, ws, n_items, cfg, pass, domain, nullptr, 0, lane);
+          if (lane == 0) solves += (unsigned long long)n_items;
+          // per-lane filter in patch order (Bezier.h:249-261)
+          for (int i = 0; i < n_items; i++) {
+            const unsigned it = ws->item[i];
+            if ((int)(it & 31) == lane) {
+              const double qt = ws->it_t[i], qu = ws->it_u[i], qv = ws->it_v[i];
+              if (qt < SPPM_M_EPS || qt > pt || qu < -SPPM_M_EPS || qu > 1 + SPPM_M_EPS || qv < -SPPM_M_EPS ||
+                  qv > 1 + SPPM_M_EPS)
+                continue;
+              if (qt < pt) {
+                pt = qt; pu = qu; pv = qv;
+                index = (int)(it >> 8);
               }
             }
-            __syncwarp();
-            n_items = 0;
           }
+          __syncwarp();
+          n_items = 0;
         }
         if (index != -1 && pt < best.dist) {
           best.dist = pt;
@@ -490,7 +511,7 @@ __device__ inline Surface shade_hit(const SceneView& sv, const Hit& h, d3 org, d
       const double P[3] = {s.pos.x, s.pos.y, s.pos.z};
       const double v = 0.5 + (P[ob.vdex] - ob.p0[ob.vdex]) / ob.texUmod;
       const double u = 0.5 + (P[ob.udex] - ob.p0[ob.udex]) / ob.texVmod;
-      s.color = color_uv(sv.tex[ob.tex_id], u, v);
+      s.color = color_uv(sv.tex[ob.tex_id], sv.lut255, u, v);
     }
   } else if (ob.kind == SPPM_OBJ_SPHERE) {
     const d3 N = get_unit(s.pos - ld3(ob.p0));
@@ -506,14 +527,14 @@ __device__ inline Surface shade_hit(const SceneView& sv, const Hit& h, d3 org, d
       const double u = theta / SPPM_PI;
       double v = phi / (2 * SPPM_PI);
       v = (dot3(N, ld3(ob.texW)) < 0) ? (1 - v) : v;
-      s.color = color_uv(sv.tex[ob.tex_id], u, v);
+      s.color = color_uv(sv.tex[ob.tex_id], sv.lut255, u, v);
     }
   } else {
     const PatchEval e = eval_exact(sv.patchP + (size_t)h.patch * 48, h.u, h.v);
     d3 N = cross3(e.Su, e.Sv);
     if (dot3(N, dir) > 0) N = -N;
     s.n = normalize3(N);
-    s.color = (ob.tex_id < 0) ? ld3(ob.color) : color_uv(sv.tex[ob.tex_id], h.u, h.dist);  // Q6
+    s.color = (ob.tex_id < 0) ? ld3(ob.color) : color_uv(sv.tex[ob.tex_id], sv.lut255, h.u, h.dist);  // Q6
   }
   return s;
 }

@@ -6,6 +6,10 @@
 // All of them go through the warp-cooperative near_collide of scene.cuh.
 #include "ctx.h"
 
+#ifndef SPPM_TRACE_MINBLOCKS
+#define SPPM_TRACE_MINBLOCKS 2  // CTAs per SM the photon kernel's register budget is sized for
+#endif
+
 namespace sppm {
 
 namespace {
@@ -160,7 +164,7 @@ struct PhotonArgs {
 // Persistent warps: a lane whose photon ended picks the next photon index from a global
 // cursor, so lanes stay busy although path lengths differ (1..15 queries, Q9).  The RNG is
 // addressed by photon id, so the result does not depend on which lane traces what.
-__global__ void __launch_bounds__(TRACE_THREADS) photon_trace_kernel(const PhotonArgs a) {
+__global__ void __launch_bounds__(TRACE_THREADS, SPPM_TRACE_MINBLOCKS) photon_trace_kernel(const PhotonArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const size_t scene_bytes = scene_smem_bytes(a.c.scene.n_obj, a.c.scene.n_patch, a.c.patches_in_smem);
   const SceneView sv = stage_scene(a.c.scene, smem, a.c.patches_in_smem);
