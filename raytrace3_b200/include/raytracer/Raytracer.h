@@ -1,0 +1,188 @@
+// Raytracer.h — drop-in for raytracer/Raytracer.h: HitPoint, RayTracer, SPPMRayTracer.
+// render() keeps its signature; its body flattens the scene / camera and drives the sm_100a
+// kernels through the C ABI (include/sppm_b200.h).  There is no CPU render path.
+#pragma once
+#include <cstdio>
+#include <iostream>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "Camera.h"
+#include "Scene.h"
+#include "SppmBridge.h"
+using namespace std;
+
+#define MIN_WGT 1e-3
+#define MAX_DEP 13
+#define INIT_R2 2.0
+
+typedef unsigned char uchar;
+inline int toInt(double x) { return int(pow(1 - exp(-x), 1 / 2.2) * 255 + .5); }  // Raytracer.h:24-26
+
+const double alpha = 0.7;
+
+struct HitPoint {  // Raytracer.h:47-80 (host mirror of one device hit point, see SyncHitPoints)
+  Vec3 pos, n, v;
+  Obj* obj = nullptr;
+  int x = -1, y = -1;
+  Color wgt;
+  double R2 = INIT_R2;
+  int N = 0;
+  Color tao;
+  int newN = 0;
+};
+
+class RayTracer {
+ public:
+  Camera* camera = nullptr;
+  Scene* scene = nullptr;
+  vector<HitPoint*> Hvec;  // filled on demand by SyncHitPoints(); the live map stays on the device
+  int onetime = 100;       // Raytracer.h:218
+  int cnt = 10000;         // Raytracer.h:384
+  uint64_t pass_base = 0;  // distinguishes replicas in the counter RNG
+  SppmParams params;
+
+  explicit RayTracer(sppm_ctx* shared = nullptr) : ctx(shared), own(shared == nullptr) { sppm_default_params(&params); }
+  ~RayTracer() {
+    clearHvec();
+    if (own && ctx) sppm_ctx_destroy(ctx);
+    camera = nullptr;
+    scene = nullptr;
+  }
+  RayTracer(const RayTracer&) = delete;
+  RayTracer& operator=(const RayTracer&) = delete;
+
+  void GetHitPoint() {  // Raytracer.h:102-116
+    ensure();
+    sppm_host::FlatScene fs;
+    scene->flatten(fs);
+    SppmSceneDesc d = fs.desc();
+    sppm_host::check(sppm_set_params(ctx, &params), ctx, "sppm_set_params");
+    sppm_host::check(sppm_scene_upload(ctx, &d), ctx, "sppm_scene_upload");
+    SppmCameraDesc cd = camera->desc();
+    int64_t n = 0;
+    sppm_host::check(sppm_eye_pass(ctx, &cd, pass_base, &n), ctx, "sppm_eye_pass");
+    n_hitpoints = n;
+    cout << "hitpoint::" << n << endl;
+  }
+  void PhotonMap(int cnt_) {  // Raytracer.h:210-295
+    for (int i = 0; i < cnt_; i++) {
+      sppm_host::check(sppm_photon_pass(ctx, 0, (uint64_t)onetime, pass_base * (uint64_t)cnt_ + i), ctx, "sppm_photon_pass");
+      sppm_host::check(sppm_allreduce(ctx), ctx, "sppm_allreduce");
+      sppm_host::check(sppm_update(ctx), ctx, "sppm_update");
+    }
+    vector<double> film((size_t)camera->w * camera->h * 3);
+    sppm_host::check(sppm_resolve(ctx, cnt_, onetime, film.data()), ctx, "sppm_resolve");
+    for (int i1 = 0; i1 < camera->h; i1++)
+      for (int j = 0; j < camera->w; j++)
+        for (int k = 0; k < 3; k++) camera->pic[i1][j].val[k] = film[((size_t)i1 * camera->w + j) * 3 + k];
+  }
+  void render() {  // Raytracer.h:366-387
+    GetHitPoint();
+    sppm_host::check(sppm_build_index(ctx), ctx, "sppm_build_index");
+    PhotonMap(cnt);
+  }
+  // Copy the device hit-point map (positions, normals, weights, statistics) into Hvec.
+  void SyncHitPoints() {
+    clearHvec();
+    int64_t n = n_hitpoints;
+    vector<double> pos(3 * n), nn(3 * n), wgt(3 * n), r2(n), tao(3 * n);
+    vector<int32_t> pix(2 * n), newN(n), N(n);
+    sppm_host::check(sppm_export_hitpoints(ctx, n, pos.data(), nn.data(), wgt.data(), r2.data(), pix.data(), nullptr, &n), ctx, "sppm_export_hitpoints");
+    sppm_host::check(sppm_export_stats(ctx, n, newN.data(), N.data(), r2.data(), tao.data()), ctx, "sppm_export_stats");
+    for (int64_t i = 0; i < n; i++) {
+      HitPoint* hp = new HitPoint();
+      hp->pos = Vec3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+      hp->n = Vec3(nn[3 * i], nn[3 * i + 1], nn[3 * i + 2]);
+      hp->wgt = Vec3(wgt[3 * i], wgt[3 * i + 1], wgt[3 * i + 2]);
+      hp->tao = Vec3(tao[3 * i], tao[3 * i + 1], tao[3 * i + 2]);
+      hp->x = pix[2 * i];
+      hp->y = pix[2 * i + 1];
+      hp->R2 = r2[i];
+      hp->N = N[i];
+      hp->newN = newN[i];
+      Hvec.push_back(hp);
+    }
+  }
+  sppm_ctx* context() { ensure(); return ctx; }
+  int64_t n_hitpoints = 0;
+
+ private:
+  sppm_ctx* ctx;
+  bool own;
+  void ensure() {
+    if (!ctx) ctx = sppm_host::create_ctx(std::getenv("SPPM_DEVICE") ? std::atoi(std::getenv("SPPM_DEVICE")) : 0);
+  }
+  void clearHvec() {
+    for (auto hp : Hvec) delete hp;
+    vector<HitPoint*>().swap(Hvec);
+  }
+};
+
+class SPPMRayTracer {  // Raytracer.h:421-477
+ public:
+  int sppmtime = 100000;      // Raytracer.h:425
+  int replicas = 4;           // Raytracer.h:426-429
+  int cnt = 10000, onetime = 100;
+  double jitter = 0.00015;    // Raytracer.h:434
+  std::vector<int> devices;   // GPUs the replicas are spread over (default: device 0)
+  std::string out_prefix = "aaanew";
+  std::vector<uchar> image;   // last tone-mapped image, BGR, row-flipped as the reference writes it
+
+  void render(Scene scene, Camera camera) {
+    if (devices.empty()) devices.push_back(std::getenv("SPPM_DEVICE") ? std::atoi(std::getenv("SPPM_DEVICE")) : 0);
+    const int ndev = (int)devices.size();
+    std::vector<sppm_ctx*> ctxs(ndev);
+    for (int d = 0; d < ndev; d++) ctxs[d] = sppm_host::create_ctx(devices[d]);
+    std::vector<Camera> c(replicas);
+    for (int i = 0; i < sppmtime; i++) {
+      for (int j = 0; j < replicas; j++) {
+        c[j] = camera;
+        c[j].MoveTo(camera.pos + jitter * Vec3::GetUnitRandVec());
+        c[j].lookAt(camera.look, 1.);
+      }
+      // the reference runs its 4 RayTracers on 4 OpenMP threads; here one host thread per GPU
+#pragma omp parallel for num_threads(ndev) schedule(static, 1)
+      for (int d = 0; d < ndev; d++) {
+        for (int j = d; j < replicas; j += ndev) {
+          RayTracer rt(ctxs[d]);
+          rt.camera = &c[j];
+          rt.scene = &scene;
+          rt.cnt = cnt;
+          rt.onetime = onetime;
+          rt.pass_base = (uint64_t)i * replicas + j;
+          rt.render();
+        }
+      }
+      for (int j = 0; j < replicas; j++)  // Raytracer.h:449-458
+        for (int i1 = 0; i1 < camera.h; i1++)
+          for (int jj = 0; jj < camera.w; jj++) camera.pic[i1][jj] += c[j].pic[i1][jj];
+      // tone map (Raytracer.h:460-470) on the device, then save (PPM instead of cv::imwrite)
+      std::vector<double> film((size_t)camera.w * camera.h * 3);
+      for (int i1 = 0; i1 < camera.h; i1++)
+        for (int jj = 0; jj < camera.w; jj++)
+          for (int k = 0; k < 3; k++) film[((size_t)i1 * camera.w + jj) * 3 + k] = camera.pic[i1][jj].val[k];
+      image.resize(film.size());
+      sppm_host::check(sppm_tonemap(ctxs[0], film.data(), camera.w, camera.h, (i + 1) * (double)replicas, image.data()), ctxs[0], "sppm_tonemap");
+      std::string pic = out_prefix + std::to_string(i / 10) + ".ppm";
+      std::cerr << "save:" << pic << std::endl;
+      savePPM(pic, camera.w, camera.h);
+    }
+    for (sppm_ctx* x : ctxs) sppm_ctx_destroy(x);
+  }
+
+ private:
+  void savePPM(const std::string& path, int w, int h) const {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return;
+    std::fprintf(f, "P6\n%d %d\n255\n", w, h);
+    for (size_t p = 0; p < (size_t)w * h; p++) {
+      const uchar rgb[3] = {image[3 * p + 2], image[3 * p + 1], image[3 * p]};  // film channels are BGR (Q11)
+      std::fwrite(rgb, 1, 3, f);
+    }
+    std::fclose(f);
+  }
+};

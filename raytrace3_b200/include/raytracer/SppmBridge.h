@@ -1,0 +1,49 @@
+// SppmBridge.h — glue between the reference-shaped host classes and the C ABI
+// (include/sppm_b200.h): error handling, the per-process device context used by the
+// single-ray compatibility calls, and the flattened scene holder.
+#pragma once
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/sppm_b200.h"
+
+namespace sppm_host {
+
+inline void check(int rc, sppm_ctx* c, const char* what) {
+  if (rc != SPPM_OK) throw std::runtime_error(std::string(what) + " failed [" + std::to_string(rc) + "]: " + sppm_last_error(c));
+}
+inline sppm_ctx* create_ctx(int device) {
+  sppm_ctx* c = nullptr;
+  int rc = sppm_ctx_create(device, &c);
+  if (rc != SPPM_OK) throw std::runtime_error(std::string("sppm_ctx_create failed (no CPU fallback exists): ") + sppm_last_error(nullptr));
+  return c;
+}
+// context for Scene::NearCollide / Obj::GetIntersect compatibility calls (device $SPPM_DEVICE or 0)
+inline sppm_ctx* compat_ctx() {
+  static sppm_ctx* c = create_ctx(std::getenv("SPPM_DEVICE") ? std::atoi(std::getenv("SPPM_DEVICE")) : 0);
+  return c;
+}
+struct FlatScene {
+  std::vector<SppmObject> objs;
+  std::vector<double> patches;  // [n][16][3]
+  std::vector<SppmLight> lights;
+  std::vector<SppmTexture> tex;
+  std::vector<const void*> tex_key;
+  SppmSceneDesc desc() const {
+    SppmSceneDesc d;
+    d.n_objects = (int32_t)objs.size();
+    d.n_patches = (int32_t)(patches.size() / 48);
+    d.n_lights = (int32_t)lights.size();
+    d.n_textures = (int32_t)tex.size();
+    d.objects = objs.data();
+    d.patches = patches.data();
+    d.lights = lights.data();
+    d.textures = tex.data();
+    return d;
+  }
+};
+inline void put3(double dst[3], const double src[3]) { dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; }
+
+}  // namespace sppm_host

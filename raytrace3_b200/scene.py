@@ -111,6 +111,24 @@ def read_bpt(path):
     return out
 
 
+def write_bpt(path, patches):
+    """Write patches [n][16][3] in the .bpt format of read_bpt / Bezier.h:204-218."""
+    with open(path, "w") as f:
+        f.write(f"{len(patches)}\n")
+        for P in patches:
+            f.write("3 3\n")
+            for q in range(16):
+                f.write(" ".join(repr(float(x)) for x in P[q]) + "\n")
+
+
+def write_bgr8(path, tex):
+    """Write a pre-decoded texture for the C++ host mirror (include/raytracer/Element.h)."""
+    m = tex.map if isinstance(tex, Texture) else np.ascontiguousarray(tex, dtype=np.uint8)
+    with open(path, "wb") as f:
+        f.write(f"BGR8 {m.shape[0]} {m.shape[1]}\n".encode())
+        f.write(m.tobytes())
+
+
 def teapot_patches():
     """The 32 bicubic patches of the Utah teapot (Newell's data set), raw file coordinates."""
     return np.load(os.path.join(DATA_DIR, "teapot32.npy"))
