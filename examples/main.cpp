@@ -36,7 +36,8 @@ int main()
 	r2.render(scene, camera);
 
 	double sum = 0;
-	for (int i = 0; i < camera.h; i++) for (int j = 0; j < camera.w; j++) sum += camera.pic[i][j].val[0] + camera.pic[i][j].val[1] + camera.pic[i][j].val[2];
+	for (double v : r2.film) sum += v;  // render() takes the camera by value (as upstream): read the renderer's film
+	std::cout.precision(17);
 	std::cout << "film sum " << sum << std::endl;
 	return 0;
 }

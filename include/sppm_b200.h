@@ -47,6 +47,10 @@ enum { SPPM_UPDATE_REFERENCE = 0, SPPM_UPDATE_PROGRESSIVE = 1 };
  * contraction (bit-identical to the oracle); FAST = joint tensor-form evaluation with
  * FMA (within 1e-6 relative of EXACT, the north-star tolerance). */
 enum { SPPM_NEWTON_EXACT = 0, SPPM_NEWTON_FAST = 1 };
+/* Photon tracer organisation.  WAVEFRONT = one kernel step per bounce over a compacted
+ * queue of live photons + a separate Newton kernel over the queued (ray, patch) items;
+ * PERSISTENT = one persistent-warp megakernel.  Same results (the RNG is keyed by photon). */
+enum { SPPM_TRACE_WAVEFRONT = 0, SPPM_TRACE_PERSISTENT = 1 };
 /* Random-number domains of the counter RNG (who asks for Newton seeds). */
 enum { SPPM_DOMAIN_PHOTON = 2, SPPM_DOMAIN_EYE = 3, SPPM_DOMAIN_TEST = 5 };
 
@@ -122,7 +126,7 @@ typedef struct SppmParams {
   int32_t newton_restarts; /* Bezier.h:115    maxIter*5 = 50 (<= 4095) */
   int32_t update_mode;     /* SPPM_UPDATE_* */
   int32_t newton_mode;     /* SPPM_NEWTON_* */
-  int32_t reserved;
+  int32_t trace_mode;      /* SPPM_TRACE_* */
   uint64_t seed;           /* key of the Philox4x32-10 counter RNG */
 } SppmParams;
 

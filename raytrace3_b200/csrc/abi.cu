@@ -185,7 +185,7 @@ int sppm_default_params(SppmParams* p) {
   p->newton_restarts = 50;
   p->update_mode = SPPM_UPDATE_REFERENCE;
   p->newton_mode = SPPM_NEWTON_EXACT;
-  p->reserved = 0;
+  p->trace_mode = SPPM_TRACE_WAVEFRONT;
   p->seed = 0x5EED5EEDull;
   return SPPM_OK;
 }
@@ -237,7 +237,7 @@ void sppm_ctx_destroy(sppm_ctx* c) {
   free_scene(c);
   DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->dep_raw,
                     &c->dep_sorted, &c->dep_key, &c->dep_key2, &c->dep_idx, &c->dep_idx2, &c->dep_start, &c->cub_tmp,
-                    &c->dev_scalars, &c->counters, &c->film, &c->scratch};
+                    &c->dev_scalars, &c->counters, &c->film, &c->scratch, &c->wf_store};
   for (DevBuf* d : bufs) dev_free(*d);
   for (int i = 0; i < 8; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -248,6 +248,7 @@ void sppm_ctx_destroy(sppm_ctx* c) {
 int sppm_set_params(sppm_ctx* c, const SppmParams* p) {
   if (!c || !p) return SPPM_ERR_INVALID;
   if (p->max_dep < 0 || p->max_dep > 13) return fail(c, SPPM_ERR_INVALID, "max_dep must be in [0,13]");
+  if (p->trace_mode != SPPM_TRACE_WAVEFRONT && p->trace_mode != SPPM_TRACE_PERSISTENT) return fail(c, SPPM_ERR_INVALID, "bad trace_mode");
   if (p->newton_restarts < 1 || p->newton_restarts > 4095) return fail(c, SPPM_ERR_INVALID, "newton_restarts out of range");
   if (p->newton_iters < 1) return fail(c, SPPM_ERR_INVALID, "newton_iters must be >= 1");
   if (!(p->init_r2 > 0)) return fail(c, SPPM_ERR_INVALID, "init_r2 must be > 0");
@@ -416,7 +417,8 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
     if (rc) return rc;
     CU(c, cudaMemsetAsync(scalars(c) + 1, 0, 16, c->stream));  // deposit count, photon cursor
     CU(c, cudaEventRecord(c->ev[0], c->stream));
-    CU(c, launch_photon_trace(c, photon_begin + off, cnt, pass_id));
+    if (c->prm.trace_mode == SPPM_TRACE_PERSISTENT) CU(c, launch_photon_trace(c, photon_begin + off, cnt, pass_id));
+    else CU(c, launch_photon_trace_wavefront(c, photon_begin + off, cnt, pass_id));
     CU(c, cudaEventRecord(c->ev[4], c->stream));
     unsigned long long m = 0;
     CU(c, cudaMemcpyAsync(&m, scalars(c) + 1, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -424,6 +426,11 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
     fold_timings(c, true, pend_sg);
     pend_sg = false;
     if ((int64_t)m > c->dep_cap) return fail(c, SPPM_ERR_CAPACITY, "deposit buffer overflow");
+    if (c->prm.trace_mode != SPPM_TRACE_PERSISTENT) {
+      bool ovf = false;
+      CU(c, wavefront_overflowed(c, &ovf));
+      if (ovf) return fail(c, SPPM_ERR_CAPACITY, "Bezier work-item list overflow (more than 2 (ray, patch) items per photon in one bounce)");
+    }
     c->n_dep = (int64_t)m;
     if (c->index_ok && m > 0 && c->n_hp > 0) {
       CU(c, sort_and_gather(c, (int64_t)m));

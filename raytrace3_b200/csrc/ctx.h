@@ -103,6 +103,8 @@ struct sppm_ctx {
   sppm::DevBuf counters;      // DevCounters
   sppm::DevBuf film;          // double[h][w][3]
   sppm::DevBuf scratch;
+  sppm::DevBuf wf_store;      // wavefront photon queues + item lists
+  int64_t wf_cap = 0;
   bool keep_all_deposits = false;
   SppmCounters host_counters{};
   cudaEvent_t ev[8] = {};  // 0 trace start, 1 sort start, 2 gather start, 3 gather end, 4/5 generic
@@ -120,6 +122,9 @@ cudaError_t launch_intersect(sppm_ctx* c, const double* d_rays6, int64_t n, cons
 cudaError_t launch_patch_batch(sppm_ctx* c, const double* d_rays6, const int32_t* d_patch, int64_t n,
                                const double* d_seeds, double* d_tuv);
 cudaError_t trace_configure(sppm_ctx* c);
+// wavefront.cu
+cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, uint64_t begin, uint64_t count, uint64_t pass_id);
+cudaError_t wavefront_overflowed(sppm_ctx* c, bool* overflow);
 // gather.cu
 cudaError_t build_index(sppm_ctx* c);
 cudaError_t key_host_deposits(sppm_ctx* c, int64_t m);

@@ -376,6 +376,38 @@ struct Hit {  // Element.h:20-39 Collision, the fields the path reads
   bool inside;
 };
 
+// PlaneObj::GetIntersect (Obj.h:65-85): keep the hit if strictly nearer than best.
+__device__ __forceinline__ void test_plane(const DevObject& ob, int a, d3 org, d3 dir, Hit& best) {
+  const d3 norm = ld3(ob.norm);
+  const double project = dot3(dir, norm);
+  if (!is_zero(project)) {
+    const double dist = dot3(ld3(ob.p0) - org, norm) / project;
+    if (dist > SPPM_M_EPS && dist < best.dist) {
+      best.dist = dist;
+      best.obj = a;
+      best.inside = false;
+    }
+  }
+}
+// SphereObj::GetIntersect (Obj.h:111-139)
+__device__ __forceinline__ void test_sphere(const DevObject& ob, int a, d3 org, d3 dir, Hit& best) {
+  const d3 L = ld3(ob.p0) - org;
+  const double project = dot3(L, dir);
+  const double det2 = ob.radius * ob.radius - (module2(L) - project * project);
+  if (!(det2 < SPPM_M_EPS)) {
+    const double det = sqrt(det2);
+    const double dist1 = project - det, dist2 = project + det;
+    if (!(dist2 < SPPM_M_EPS)) {
+      const double dist = (dist1 > SPPM_M_EPS) ? dist1 : dist2;
+      if (dist < best.dist) {
+        best.dist = dist;
+        best.obj = a;
+        best.inside = (dist1 < SPPM_M_EPS);
+      }
+    }
+  }
+}
+
 // Scene::NearCollide (Scene.h:165-182) for the 32 rays of a warp.  All lanes must call
 // (inactive lanes pass active=false).  Keeps the strictly nearest hit, first object wins ties.
 __device__ inline Hit near_collide(const SceneView& sv, WarpScratch* ws, const NewtonCfg& cfg, bool active, d3 org,
@@ -391,37 +423,10 @@ __device__ inline Hit near_collide(const SceneView& sv, WarpScratch* ws, const N
   bool staged = false;
   for (int a = 0; a < sv.n_obj; a++) {
     const DevObject& ob = sv.obj[a];
-    if (ob.kind == SPPM_OBJ_PLANE) {  // PlaneObj::GetIntersect (Obj.h:65-85)
-      if (active) {
-        const d3 norm = ld3(ob.norm);
-        const double project = dot3(dir, norm);
-        if (!is_zero(project)) {
-          const double dist = dot3(ld3(ob.p0) - org, norm) / project;
-          if (dist > SPPM_M_EPS && dist < best.dist) {
-            best.dist = dist;
-            best.obj = a;
-            best.inside = false;
-          }
-        }
-      }
-    } else if (ob.kind == SPPM_OBJ_SPHERE) {  // SphereObj::GetIntersect (Obj.h:111-139)
-      if (active) {
-        const d3 L = ld3(ob.p0) - org;
-        const double project = dot3(L, dir);
-        const double det2 = ob.radius * ob.radius - (module2(L) - project * project);
-        if (!(det2 < SPPM_M_EPS)) {
-          const double det = sqrt(det2);
-          const double dist1 = project - det, dist2 = project + det;
-          if (!(dist2 < SPPM_M_EPS)) {
-            const double dist = (dist1 > SPPM_M_EPS) ? dist1 : dist2;
-            if (dist < best.dist) {
-              best.dist = dist;
-              best.obj = a;
-              best.inside = (dist1 < SPPM_M_EPS);
-            }
-          }
-        }
-      }
+    if (ob.kind == SPPM_OBJ_PLANE) {
+      if (active) test_plane(ob, a, org, dir, best);
+    } else if (ob.kind == SPPM_OBJ_SPHERE) {
+      if (active) test_sphere(ob, a, org, dir, best);
     } else {  // Bezier3Obj::GetIntersect (Bezier.h:240-282)
       const bool in_box = active && aabb_intersect(ob.box, org, dir);
       if (__any_sync(FULL, in_box)) {

@@ -1,0 +1,490 @@
+// wavefront.cu — the photon pass as a bounce-synchronous wavefront (sm_100a).
+//
+// Light::emit + RayTracer::PhotonTrace (Light.h:8-13, Raytracer.h:117-209) are split into two
+// kernels per bounce over a COMPACTED queue of live photons (SoA in HBM, ping-pong):
+//
+//   photon_step_kernel(b)   per live photon: [b = 0: emit | b > 0: finish the previous query —
+//                           combine the analytic best with the Bezier solves, depth check,
+//                           shade, deposit, Roulette, next direction]; then the next query's
+//                           analytic tests (planes / spheres) and the cooperative Bezier AABB
+//                           culling, which appends (photon slot, patch) items to a global list;
+//                           survivors are re-compacted with a warp-aggregated counter.
+//   newton_items_kernel(b)  Bezier3::newton (Bezier.h:112-159) for all queued items, the
+//                           item x restart tasks packed over full warps.
+//
+// Compared with the persistent megakernel (trace.cu) every kernel is coherent: no lane idles
+// on a finished photon, the register-heavy Newton solver does not limit the occupancy of the
+// light per-photon code, and the Newton tasks of the whole GPU are packed densely.
+// Results are identical: the RNG is addressed by (pass, photon id, bounce, ...).
+#include "ctx.h"
+
+namespace sppm {
+
+namespace {
+
+constexpr int STEP_THREADS = 128;
+constexpr unsigned long long ID_MASK = 0x00ffffffffffffffull;
+
+struct Queue {  // SoA photon state, one entry per live photon
+  double *ox, *oy, *oz, *dx, *dy, *dz, *fx, *fy, *fz, *hdist;
+  unsigned long long* idd;  // photon id | dep << 56
+  int* hobj;                // analytic best of the pending query: obj | inside << 16, -1 = none
+  unsigned *item_begin, *item_cnt;
+};
+struct Items {
+  unsigned* slot;   // photon slot in the queue the items were generated for
+  unsigned* patch;  // global patch | object << 16
+  double *t, *u, *v;
+};
+
+struct StepArgs {
+  DevScene scene;
+  int patches_in_smem, max_dep, bounce, do_intersect;
+  uint64_t seed, pass;
+  DevCounters* counters;
+  Queue qin, qout;
+  Items it_in, it_out;
+  const unsigned* n_in_ptr;
+  unsigned n_in_host;
+  unsigned* n_out;
+  unsigned* n_items_out;
+  unsigned item_cap;
+  unsigned* overflow;
+  uint64_t begin, count;  // photon range per light of this batch
+  Grid grid;
+  const int32_t* cell_slot;
+  int32_t n_slots;
+  int keep_all;
+  Deposit* dep;
+  uint32_t* dep_key;
+  unsigned long long dep_cap;
+  unsigned long long* dep_count;
+};
+
+__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+  return v;
+}
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
+
+__global__ void __launch_bounds__(STEP_THREADS) photon_step_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem);
+  const int lane = threadIdx.x & 31;
+  const unsigned n_in = a.bounce == 0 ? a.n_in_host : *a.n_in_ptr;
+  const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  unsigned long long queries = 0, solves = 0, photons = 0, deposits = 0, kept = 0;
+
+  for (unsigned base = warp_global * 32; base < n_in; base += n_warps * 32) {
+    const unsigned i = base + lane;
+    const bool active = i < n_in;
+    bool alive = false, want = false;
+    d3 org = mk(0, 0, 0), dir = mk(0, 0, 1), flux = mk(0, 0, 0);
+    uint64_t id = 0;
+    int dep = 0;
+    Deposit rec;
+    uint32_t key = 0;
+    if (active) {
+      if (a.bounce == 0) {  // Light::emit (Light.h:8-13)
+        const unsigned pl = (unsigned)(i / a.count);
+        id = ((uint64_t)pl << 40) | (a.begin + i % a.count);
+        const SppmLight& L = a.scene.lights[pl];
+        flux = ld3(L.color) * SPPM_PI * 4;
+        dir = unit_rand_vec(a.seed, a.pass, id, P_EMIT);
+        org = ld3(L.pos);
+        alive = true;
+        photons++;
+      } else {
+        // ---- finish the pending query: nearest of the analytic best and the Bezier solves
+        const unsigned long long idd = a.qin.idd[i];
+        id = idd & ID_MASK;
+        dep = (int)(idd >> 56);
+        org = mk(a.qin.ox[i], a.qin.oy[i], a.qin.oz[i]);
+        dir = mk(a.qin.dx[i], a.qin.dy[i], a.qin.dz[i]);
+        Hit h;
+        h.dist = a.qin.hdist[i];
+        const int ho = a.qin.hobj[i];
+        h.obj = ho < 0 ? -1 : (ho & 0xffff);
+        h.inside = ho >= 0 && ((ho >> 16) & 1);
+        h.patch = -1;
+        h.u = h.v = 0;
+        const unsigned ic = a.qin.item_cnt[i];
+        if (ic) {  // Bezier3Obj::GetIntersect filter, per object in patch order (Bezier.h:246-261)
+          const unsigned ib = a.qin.item_begin[i];
+          int cur = -1, index = -1;
+          double pt = SPPM_MAX_NUM, pu = SPPM_MAX_NUM, pv = SPPM_MAX_NUM;
+          for (unsigned k = 0; k <= ic; k++) {
+            const unsigned pk = k < ic ? a.it_in.patch[ib + k] : 0xffffffffu;
+            const int ob = k < ic ? (int)(pk >> 16) : -2;
+            if (ob != cur) {
+              if (cur >= 0 && index != -1 && (pt < h.dist || (pt == h.dist && cur < h.obj))) {
+                h.dist = pt; h.obj = cur; h.patch = index; h.u = pu; h.v = pv; h.inside = false;
+              }
+              cur = ob;
+              index = -1;
+              pt = pu = pv = SPPM_MAX_NUM;
+            }
+            if (k < ic) {
+              const double qt = a.it_in.t[ib + k], qu = a.it_in.u[ib + k], qv = a.it_in.v[ib + k];
+              if (!(qt < SPPM_M_EPS || qt > pt || qu < -SPPM_M_EPS || qu > 1 + SPPM_M_EPS || qv < -SPPM_M_EPS ||
+                    qv > 1 + SPPM_M_EPS)) {
+                if (qt < pt) {
+                  pt = qt; pu = qu; pv = qv;
+                  index = (int)(pk & 0xffffu);
+                }
+              }
+            }
+          }
+        }
+        if (!(h.obj < 0 || dep > a.max_dep)) {  // Raytracer.h:127-133
+          flux = mk(a.qin.fx[i], a.qin.fy[i], a.qin.fz[i]);
+          const int node = dep;
+          dep++;
+          const DevObject& ob = sv.obj[h.obj];
+          const Surface s = shade_hit(sv, h, org, dir);
+          if (ob.isDiff) {  // Raytracer.h:136-160: the gather input (x, N, incoming flux)
+            deposits++;
+            int32_t slot = -1;
+            if (a.cell_slot) slot = __ldg(a.cell_slot + grid_cell(a.grid, s.pos.x, s.pos.y, s.pos.z));
+            if (slot >= 0 || a.keep_all) {
+              want = true;
+              key = slot >= 0 ? (uint32_t)slot : (uint32_t)a.n_slots;
+              rec.x[0] = s.pos.x; rec.x[1] = s.pos.y; rec.x[2] = s.pos.z;
+              rec.n[0] = s.n.x; rec.n[1] = s.n.y; rec.n[2] = s.n.z;
+              rec.flux[0] = flux.x; rec.flux[1] = flux.y; rec.flux[2] = flux.z;
+              rec.meta = id | ((uint64_t)node << 56);
+            }
+          }
+          // Obj::Roulette (Obj.h:30-45) and the single continuation (Raytracer.h:162-190)
+          double ur, U1;
+          draw2(a.seed, a.pass, id, (uint32_t)node, P_BOUNCE, 0, 0, ur, U1);
+          const double r = randu(ur, 0., ob.allr);
+          d3 ndir;
+          if (ob.diffr > r) {
+            double U2, unused;
+            draw2(a.seed, a.pass, id, (uint32_t)node, P_BOUNCE, 1, 0, U2, unused);
+            ndir = unit_rand_refl(s.n, U1, U2);
+          } else if (ob.diffr + ob.reflr > r) {
+            ndir = get_unit(get_refl(dir, s.n));
+          } else {
+            const double refrn = h.inside ? ob.refrn : 1 / ob.refrn;
+            ndir = normalize3(refracted(dir, h.inside ? -s.n : s.n, refrn));
+          }
+          flux = mul3(s.color, flux);
+          org = s.pos;
+          dir = ndir;
+          alive = true;
+        }
+      }
+    }
+    // ---- deposits: warp-aggregated append
+    {
+      const unsigned m = __ballot_sync(FULL, want);
+      if (m) {
+        unsigned long long dbase = 0;
+        if (lane == 0) dbase = atomicAdd(a.dep_count, (unsigned long long)__popc(m));
+        dbase = __shfl_sync(FULL, dbase, 0);
+        if (want) {
+          const unsigned long long slot = dbase + __popc(m & ((1u << lane) - 1));
+          if (slot < a.dep_cap) {
+            a.dep[slot] = rec;
+            a.dep_key[slot] = key;
+            kept++;
+          }
+        }
+      }
+    }
+    // ---- next query: analytic objects per lane, Bezier object boxes noted in a bit mask
+    Hit best;
+    best.dist = SPPM_MAX_NUM;
+    best.obj = -1;
+    best.inside = false;
+    unsigned long long boxobj = 0;
+    if (alive) {
+      queries++;
+      if (a.do_intersect) {
+        for (int o = 0; o < sv.n_obj; o++) {
+          const DevObject& ob = sv.obj[o];
+          if (ob.kind == SPPM_OBJ_PLANE) test_plane(ob, o, org, dir, best);
+          else if (ob.kind == SPPM_OBJ_SPHERE) test_sphere(ob, o, org, dir, best);
+          else if (aabb_intersect(ob.box, org, dir)) boxobj |= 1ull << o;  // Bezier.h:244
+        }
+      } else {
+        alive = false;  // the last query's result is never used (depth limit, Raytracer.h:129-132)
+      }
+    }
+    // ---- compaction of the survivors into the output queue
+    const unsigned am = __ballot_sync(FULL, alive);
+    if (!am) continue;
+    unsigned qbase = 0;
+    if (lane == 0) qbase = atomicAdd(a.n_out, (unsigned)__popc(am));
+    qbase = __shfl_sync(FULL, qbase, 0);
+    const unsigned my_slot = qbase + __popc(am & ((1u << lane) - 1));
+    // ---- cooperative Bezier culling: per in-box ray, 32 lanes test 32 patch boxes (Bezier.h:178)
+    unsigned my_begin = 0, my_cnt = 0;
+    unsigned bm = __ballot_sync(FULL, alive && boxobj != 0);
+    while (bm) {
+      const int src = __ffs(bm) - 1;
+      bm &= bm - 1;
+      const d3 so = mk(shfl_d(org.x, src), shfl_d(org.y, src), shfl_d(org.z, src));
+      const d3 sd = mk(shfl_d(dir.x, src), shfl_d(dir.y, src), shfl_d(dir.z, src));
+      const unsigned long long omask = __shfl_sync(FULL, boxobj, src);
+      const unsigned sslot = __shfl_sync(FULL, my_slot, src);
+      unsigned total = 0, ibase = 0;
+      for (int pass2 = 0; pass2 < 2; pass2++) {  // count, reserve one contiguous range, then write
+        unsigned off = 0;
+        unsigned long long om = omask;
+        while (om) {
+          const int o = __ffsll((long long)om) - 1;
+          om &= om - 1;
+          const DevObject& ob = sv.obj[o];
+          for (int ch = 0; ch < ob.n_patch; ch += 32) {
+            const int p = ch + lane;
+            const bool hitp = p < ob.n_patch && aabb_intersect(sv.patchBox + (size_t)(ob.first_patch + p) * 6, so, sd);
+            const unsigned b = __ballot_sync(FULL, hitp);
+            if (pass2 && hitp) {
+              const unsigned k = ibase + off + __popc(b & ((1u << lane) - 1));
+              if (k < a.item_cap) {
+                a.it_out.slot[k] = sslot;
+                a.it_out.patch[k] = (unsigned)(ob.first_patch + p) | ((unsigned)o << 16);
+              }
+            }
+            off += __popc(b);
+          }
+        }
+        if (!pass2) {
+          total = off;
+          if (total == 0) break;
+          if (lane == 0) ibase = atomicAdd(a.n_items_out, total);
+          ibase = __shfl_sync(FULL, ibase, 0);
+          if (ibase + total > a.item_cap) {  // item list full: drop (flagged, the host reports it)
+            if (lane == 0) atomicExch(a.overflow, 1u);
+            total = ibase < a.item_cap ? a.item_cap - ibase : 0;
+          }
+        }
+      }
+      if (lane == src) {
+        my_begin = ibase;
+        my_cnt = total;
+      }
+      if (lane == 0) solves += total;
+    }
+    if (alive) {
+      const unsigned s = my_slot;
+      a.qout.ox[s] = org.x; a.qout.oy[s] = org.y; a.qout.oz[s] = org.z;
+      a.qout.dx[s] = dir.x; a.qout.dy[s] = dir.y; a.qout.dz[s] = dir.z;
+      a.qout.fx[s] = flux.x; a.qout.fy[s] = flux.y; a.qout.fz[s] = flux.z;
+      a.qout.idd[s] = id | ((unsigned long long)dep << 56);
+      a.qout.hdist[s] = best.dist;
+      a.qout.hobj[s] = best.obj < 0 ? -1 : (best.obj | (best.inside ? 1 << 16 : 0));
+      a.qout.item_begin[s] = my_begin;
+      a.qout.item_cnt[s] = my_cnt;
+    }
+  }
+  queries = warp_sum64(queries);
+  solves = warp_sum64(solves);
+  photons = warp_sum64(photons);
+  deposits = warp_sum64(deposits);
+  kept = warp_sum64(kept);
+  if (lane == 0) {
+    if (queries) atomicAdd(&a.counters->isect_queries, queries);
+    if (solves) atomicAdd(&a.counters->patch_solves, solves);
+    if (photons) atomicAdd(&a.counters->photons, photons);
+    if (deposits) atomicAdd(&a.counters->deposits, deposits);
+    if (kept) atomicAdd(&a.counters->deposits_kept, kept);
+  }
+}
+
+struct NewtonArgs {
+  DevScene scene;
+  NewtonCfg ncfg;
+  int patches_in_smem;
+  uint64_t pass;
+  Queue q;
+  Items it;
+  const unsigned* n_items_ptr;
+  unsigned item_cap;
+};
+
+// Bezier3::newton for the queued (photon slot, patch) items.  Each warp takes chunks of C items
+// (C chosen so that all warps of the grid get work) and runs the C*restarts tasks over its 32
+// lanes with flush_items (scene.cuh): lanes = restarts, arg-min on (t, restart) per item.
+__global__ void __launch_bounds__(TRACE_THREADS) newton_items_kernel(const NewtonArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const unsigned n = min(*a.n_items_ptr, a.item_cap);
+  if (n == 0) return;
+  const size_t scene_bytes = scene_smem_bytes(a.scene.n_obj, a.scene.n_patch, a.patches_in_smem);
+  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem);
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + scene_bytes) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  unsigned C = (n + n_warps - 1) / n_warps;
+  C = C < 4 ? 4 : (C > 32 ? 32 : C);
+  for (unsigned c0 = warp_global * C; c0 < n; c0 += n_warps * C) {
+    const int cnt = (int)min(C, n - c0);
+    if (lane < cnt) {
+      const unsigned s = a.it.slot[c0 + lane];
+      const unsigned pk = a.it.patch[c0 + lane];
+      ws->ray[0][lane] = a.q.ox[s]; ws->ray[1][lane] = a.q.oy[s]; ws->ray[2][lane] = a.q.oz[s];
+      ws->ray[3][lane] = a.q.dx[s]; ws->ray[4][lane] = a.q.dy[s]; ws->ray[5][lane] = a.q.dz[s];
+      const unsigned long long idd = a.q.idd[s];
+      ws->id[lane] = idd & ID_MASK;
+      ws->node[lane] = (unsigned)(idd >> 56);
+      ws->item[lane] = (unsigned)lane | ((pk & 0xffffu) << 8);
+    }
+    __syncwarp();
+    flush_items(sv, ws, cnt, a.ncfg, a.pass, SPPM_DOMAIN_PHOTON, nullptr, 0, lane);
+    if (lane < cnt) {
+      a.it.t[c0 + lane] = ws->it_t[lane];
+      a.it.u[c0 + lane] = ws->it_u[lane];
+      a.it.v[c0 + lane] = ws->it_v[lane];
+    }
+    __syncwarp();
+  }
+}
+
+struct WfLayout {
+  Queue q[2];
+  Items it[2];
+  unsigned* counters;  // [0..31] queue counts per bounce, [32..63] item counts per bounce, [64] overflow
+  unsigned item_cap;
+};
+
+size_t wf_bytes(int64_t cap, int64_t item_cap) {
+  return 2 * (size_t)cap * (10 * 8 + 8 + 4 + 4 + 4) + 2 * (size_t)item_cap * (4 + 4 + 24) + 128 * 4 + 4096;
+}
+WfLayout wf_layout(void* store, int64_t cap, int64_t item_cap) {
+  WfLayout L;
+  unsigned char* p = (unsigned char*)store;
+  auto take = [&](size_t bytes) {
+    void* r = p;
+    p += (bytes + 255) & ~(size_t)255;
+    return r;
+  };
+  for (int k = 0; k < 2; k++) {
+    Queue& q = L.q[k];
+    double** d[] = {&q.ox, &q.oy, &q.oz, &q.dx, &q.dy, &q.dz, &q.fx, &q.fy, &q.fz, &q.hdist};
+    for (double** x : d) *x = (double*)take((size_t)cap * 8);
+    q.idd = (unsigned long long*)take((size_t)cap * 8);
+    q.hobj = (int*)take((size_t)cap * 4);
+    q.item_begin = (unsigned*)take((size_t)cap * 4);
+    q.item_cnt = (unsigned*)take((size_t)cap * 4);
+    Items& it = L.it[k];
+    it.slot = (unsigned*)take((size_t)item_cap * 4);
+    it.patch = (unsigned*)take((size_t)item_cap * 4);
+    it.t = (double*)take((size_t)item_cap * 8);
+    it.u = (double*)take((size_t)item_cap * 8);
+    it.v = (double*)take((size_t)item_cap * 8);
+  }
+  L.counters = (unsigned*)take(128 * 4);
+  L.item_cap = (unsigned)item_cap;
+  return L;
+}
+
+}  // namespace
+
+cudaError_t wavefront_configure(sppm_ctx* c, int* step_blocks, int* newton_blocks, size_t* step_smem, size_t* newton_smem) {
+  const size_t scene = scene_smem_bytes(c->scene.n_obj, c->scene.n_patch, c->patches_in_smem);
+  *step_smem = scene;
+  *newton_smem = scene + TRACE_WARPS * sizeof(WarpScratch);
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(photon_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*step_smem))) return e;
+  if ((e = cudaFuncSetAttribute(newton_items_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*newton_smem))) return e;
+  int a = 1, b = 1;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, photon_step_kernel, STEP_THREADS, *step_smem))) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, newton_items_kernel, TRACE_THREADS, *newton_smem))) return e;
+  *step_blocks = c->sm_count * (a < 1 ? 1 : a);
+  *newton_blocks = c->sm_count * (b < 1 ? 1 : b);
+  return cudaSuccess;
+}
+
+// One batch of photons [begin, begin+count) per light through all bounces.
+cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, uint64_t begin, uint64_t count, uint64_t pass_id) {
+  const int64_t total = (int64_t)c->scene.n_light * (int64_t)count;
+  if (total <= 0) return cudaSuccess;
+  const int64_t item_cap = std::max<int64_t>(total * 2, 1 << 16);
+  cudaError_t e;
+  if (total > c->wf_cap) {
+    if ((e = dev_reserve(c->wf_store, wf_bytes(total, item_cap)))) return e;
+    c->wf_cap = total;
+  }
+  const WfLayout L = wf_layout(c->wf_store.p, c->wf_cap, std::max<int64_t>(c->wf_cap * 2, 1 << 16));
+  int step_blocks, newton_blocks;
+  size_t step_smem, newton_smem;
+  if ((e = wavefront_configure(c, &step_blocks, &newton_blocks, &step_smem, &newton_smem))) return e;
+  cudaStream_t st = c->stream;
+  if ((e = cudaMemsetAsync(L.counters, 0, 128 * 4, st))) return e;
+  const int n_steps = c->prm.max_dep + 2;  // queries at dep = 0 .. max_dep+1 (Q9)
+  for (int b = 0; b < n_steps; b++) {
+    StepArgs a;
+    a.scene = c->scene;
+    a.patches_in_smem = c->patches_in_smem ? 1 : 0;
+    a.max_dep = c->prm.max_dep;
+    a.bounce = b;
+    a.do_intersect = b < n_steps - 1;
+    a.seed = c->prm.seed;
+    a.pass = pass_id;
+    a.counters = (DevCounters*)c->counters.p;
+    a.qin = L.q[b & 1];
+    a.qout = L.q[(b + 1) & 1];
+    a.it_in = L.it[b & 1];
+    a.it_out = L.it[(b + 1) & 1];
+    a.n_in_ptr = L.counters + b;
+    a.n_in_host = (unsigned)total;
+    a.n_out = L.counters + b + 1;
+    a.n_items_out = L.counters + 32 + b + 1;
+    a.item_cap = L.item_cap;
+    a.overflow = L.counters + 64;
+    a.begin = begin;
+    a.count = count;
+    a.grid = c->grid;
+    a.cell_slot = c->index_ok ? (const int32_t*)c->cell_slot.p : nullptr;
+    a.n_slots = c->n_slots;
+    a.keep_all = c->keep_all_deposits ? 1 : 0;
+    a.dep = (Deposit*)c->dep_raw.p;
+    a.dep_key = (uint32_t*)c->dep_key.p;
+    a.dep_cap = (unsigned long long)c->dep_cap;
+    a.dep_count = (unsigned long long*)c->dev_scalars.p + 1;
+    int blocks = step_blocks;
+    if (b == 0) {
+      const int64_t want = (total + STEP_THREADS - 1) / STEP_THREADS;
+      if (want < blocks) blocks = (int)want;
+    }
+    photon_step_kernel<<<blocks, STEP_THREADS, step_smem, st>>>(a);
+    c->host_counters.launches++;
+    if (a.do_intersect && c->scene.n_patch > 0) {
+      NewtonArgs n;
+      n.scene = c->scene;
+      n.ncfg.restarts = c->prm.newton_restarts;
+      n.ncfg.iters = c->prm.newton_iters;
+      n.ncfg.mode = c->prm.newton_mode;
+      n.ncfg.seed = c->prm.seed;
+      n.patches_in_smem = a.patches_in_smem;
+      n.pass = pass_id;
+      n.q = a.qout;
+      n.it = a.it_out;
+      n.n_items_ptr = a.n_items_out;
+      n.item_cap = L.item_cap;
+      newton_items_kernel<<<newton_blocks, TRACE_THREADS, newton_smem, st>>>(n);
+      c->host_counters.launches++;
+    }
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t wavefront_overflowed(sppm_ctx* c, bool* overflow) {
+  *overflow = false;
+  if (!c->wf_store.p || c->wf_cap <= 0) return cudaSuccess;
+  const WfLayout L = wf_layout(c->wf_store.p, c->wf_cap, std::max<int64_t>(c->wf_cap * 2, 1 << 16));
+  unsigned v = 0;
+  cudaError_t e = cudaMemcpyAsync(&v, L.counters + 64, 4, cudaMemcpyDeviceToHost, c->stream);
+  if (e) return e;
+  if ((e = cudaStreamSynchronize(c->stream))) return e;
+  *overflow = v != 0;
+  return cudaSuccess;
+}
+
+}  // namespace sppm

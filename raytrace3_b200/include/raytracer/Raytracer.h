@@ -131,6 +131,7 @@ class SPPMRayTracer {  // Raytracer.h:421-477
   std::vector<int> devices;   // GPUs the replicas are spread over (default: device 0)
   std::string out_prefix = "aaanew";
   std::vector<uchar> image;   // last tone-mapped image, BGR, row-flipped as the reference writes it
+  std::vector<double> film;   // accumulated film [h][w][3] (camera is passed by value, as upstream)
 
   void render(Scene scene, Camera camera) {
     if (devices.empty()) devices.push_back(std::getenv("SPPM_DEVICE") ? std::atoi(std::getenv("SPPM_DEVICE")) : 0);
@@ -161,7 +162,7 @@ class SPPMRayTracer {  // Raytracer.h:421-477
         for (int i1 = 0; i1 < camera.h; i1++)
           for (int jj = 0; jj < camera.w; jj++) camera.pic[i1][jj] += c[j].pic[i1][jj];
       // tone map (Raytracer.h:460-470) on the device, then save (PPM instead of cv::imwrite)
-      std::vector<double> film((size_t)camera.w * camera.h * 3);
+      film.resize((size_t)camera.w * camera.h * 3);
       for (int i1 = 0; i1 < camera.h; i1++)
         for (int jj = 0; jj < camera.w; jj++)
           for (int k = 0; k < 3; k++) film[((size_t)i1 * camera.w + jj) * 3 + k] = camera.pic[i1][jj].val[k];

@@ -212,11 +212,13 @@ def test_update_modes(ctx, oracle, mode):
         assert (r2 == 2.0).all() and N.max() == 0
 
 
-def test_photon_pass_deposits_and_stats(ctx, oracle):
+@pytest.mark.parametrize("trace_mode", [abi.SPPM_TRACE_WAVEFRONT, abi.SPPM_TRACE_PERSISTENT])
+def test_photon_pass_deposits_and_stats(ctx, oracle, trace_mode):
     """Light::emit + PhotonTrace (Light.h:8-13, Raytracer.h:117-209): same photons -> same
-    deposit list (x, N, flux per (photon, bounce)); gathered newN equal, tao <= 1e-5."""
+    deposit list (x, N, flux per (photon, bounce)); gathered newN equal, tao <= 1e-5.
+    Both tracer organisations (bounce-synchronous wavefront, persistent megakernel)."""
     sc = make_scene("reference", textures="synthetic")
-    prm = _params()
+    prm = _params(trace_mode=trace_mode)
     ctx.set_params(prm)
     ctx.upload_scene(sc)
     cam = reference_camera(80, 60)
@@ -239,6 +241,7 @@ def test_photon_pass_deposits_and_stats(ctx, oracle):
     # flip a discrete decision on a rare path: allow a 0.1% mismatch in the path structure
     assert abs(c["isect_queries"] - rc["queries"]) <= 0.001 * rc["queries"]
     assert abs(c["deposits"] - rc["deposits"]) <= 0.001 * rc["deposits"]
+    assert abs(c["patch_solves"] - rc["solves"]) <= 0.002 * rc["solves"] + 2
     assert c["photons"] == rc["photons"] == count
     rd = ref["dep"]
     okey = np.lexsort((rd["bounce"], rd["photon"]))
@@ -329,3 +332,32 @@ def test_photon_range_invariance(ctx):
         res.append(ctx.export_stats(n))
     np.testing.assert_array_equal(res[0]["newN"], res[1]["newN"])
     np.testing.assert_allclose(res[0]["tao"], res[1]["tao"], rtol=1e-12)
+
+
+def test_wavefront_equals_persistent(ctx):
+    """The two tracer organisations trace the same photons: identical deposit lists (bitwise:
+    same arithmetic, same RNG addresses) and identical gathered statistics."""
+    sc = make_scene("stress", textures=None)
+    cam = reference_camera(64, 48)
+    out = []
+    for mode in (abi.SPPM_TRACE_WAVEFRONT, abi.SPPM_TRACE_PERSISTENT):
+        ctx.set_params(_params(trace_mode=mode, newton_mode=abi.SPPM_NEWTON_FAST))
+        ctx.upload_scene(sc)
+        n = ctx.eye_pass(cam, 0)
+        ctx.build_index()
+        ctx.keep_deposits(True)
+        try:
+            ctx.reset_counters()
+            ctx.photon_pass(7, 30000, 2)
+            ctx.update()
+            out.append((ctx.export_deposits(), ctx.export_stats(n), ctx.counters()))
+        finally:
+            ctx.keep_deposits(False)
+    (d0, s0, c0), (d1, s1, c1) = out
+    for k in ("photon", "bounce", "x", "n", "flux"):
+        np.testing.assert_array_equal(d0[k], d1[k])
+    np.testing.assert_array_equal(s0["newN"], s1["newN"])
+    np.testing.assert_allclose(s0["tao"], s1["tao"], rtol=1e-12)
+    for k in ("photons", "isect_queries", "patch_solves", "deposits", "deposits_kept", "cand_pairs", "acc_pairs"):
+        assert c0[k] == c1[k], k
+    assert c0["patch_solves"] > 1000
