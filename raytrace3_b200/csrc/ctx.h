@@ -95,7 +95,7 @@ struct sppm_ctx {
   int32_t n_slots = 0;
   sppm::DevBuf occ_cell, occ_start;  // occupied cells: grid id [n_occ], hp start [n_occ+1]
   int32_t n_occ = 0;
-  sppm::DevBuf occ_nbr;       // int32[n_occ][27] compact slots of the neighbourhood
+  sppm::DevBuf occ_nbr;       // int2[n_occ][9]: the neighbourhood as 9 x-runs of compact slots
   // deposits
   sppm::DevBuf dep_raw, dep_sorted, dep_key, dep_key2, dep_idx, dep_idx2, dep_start, cub_tmp;
   int64_t dep_cap = 0, n_dep = 0, n_dep_kept = 0;

@@ -115,17 +115,25 @@ __global__ void finalize_slot_kernel(int32_t* flag_to_slot, const int32_t* scan,
   if (i == n_cells - 1) *n_slots = scan[i] + f;
   flag_to_slot[i] = f ? scan[i] : -1;
 }
-__global__ void occ_nbr_kernel(const uint32_t* occ_cell, int n_occ, Grid g, const int32_t* cell_slot, int32_t* occ_nbr) {
+// The 27-neighbourhood of an occupied cell as 9 runs along x.  Compact slots are assigned in
+// linear cell order and every neighbour of an occupied cell has a slot, so the (up to) three
+// x-adjacent cells of a row have consecutive slots: run = [slot_lo, slot_hi_exclusive), or
+// (0,0) for a row outside the grid.  With cell-sorted deposits a run is ONE contiguous range.
+__global__ void occ_run_kernel(const uint32_t* occ_cell, int n_occ, Grid g, const int32_t* cell_slot, int2* occ_run) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)n_occ * 27) return;
-  const int o = (int)(t / 27), k = (int)(t % 27);
+  if (t >= (long long)n_occ * 9) return;
+  const int o = (int)(t / 9), k = (int)(t % 9);
   const uint32_t c = occ_cell[o];
   const int ix = c % g.dim[0], iy = (c / g.dim[0]) % g.dim[1], iz = c / (g.dim[0] * g.dim[1]);
-  const int jx = ix + k % 3 - 1, jy = iy + (k / 3) % 3 - 1, jz = iz + k / 9 - 1;
-  int32_t s = -1;
-  if (!(jx < 0 || jy < 0 || jz < 0 || jx >= g.dim[0] || jy >= g.dim[1] || jz >= g.dim[2]))
-    s = cell_slot[((long long)jz * g.dim[1] + jy) * g.dim[0] + jx];
-  occ_nbr[t] = s;
+  const int jy = iy + k % 3 - 1, jz = iz + k / 3 - 1;
+  int2 r = make_int2(0, 0);
+  if (!(jy < 0 || jz < 0 || jy >= g.dim[1] || jz >= g.dim[2])) {
+    const int x0 = max(ix - 1, 0), x1 = min(ix + 1, g.dim[0] - 1);
+    const long long row = ((long long)jz * g.dim[1] + jy) * g.dim[0];
+    r.x = cell_slot[row + x0];
+    r.y = cell_slot[row + x1] + 1;
+  }
+  occ_run[t] = r;
 }
 __global__ void set_last_kernel(int32_t* starts, int n_occ, int32_t n_hp) { starts[n_occ] = n_hp; }
 
@@ -141,71 +149,119 @@ __global__ void dep_key_kernel(const Deposit* dep, long long m, Grid g, const in
   const int32_t s = cell_slot[grid_cell(g, dep[i].x[0], dep[i].x[1], dep[i].x[2])];
   key[i] = s >= 0 ? (uint32_t)s : (uint32_t)n_slots;
 }
-// sorted[i] = raw[idx[i]] and the [start, end) deposit range of every slot
+// sorted[i] = raw[idx[i]] (i < m) and the CSR offsets of the slots: off[s] = first sorted
+// deposit whose key is >= s, for s = 0..n_slots (keys == n_slots mark dropped deposits, so
+// off[n_slots] = number of kept deposits).  Launched with m + 1 threads.
 __global__ void dep_permute_kernel(const Deposit* raw, const uint32_t* key, const uint32_t* idx, long long m,
-                                   int32_t n_slots, Deposit* sorted, int2* range, unsigned long long* n_kept) {
+                                   int32_t n_slots, Deposit* sorted, int32_t* off) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const double2* src = reinterpret_cast<const double2*>(raw + idx[i]);
-  double2* dst = reinterpret_cast<double2*>(sorted + i);
+  if (i > m) return;
+  if (i < m) {
+    const double2* src = reinterpret_cast<const double2*>(raw + idx[i]);
+    double2* dst = reinterpret_cast<double2*>(sorted + i);
 #pragma unroll
-  for (int k = 0; k < 5; k++) dst[k] = src[k];
-  const uint32_t kk = key[i];
-  if (kk >= (uint32_t)n_slots) {
-    if (i == 0 || key[i - 1] < (uint32_t)n_slots) *n_kept = (unsigned long long)i;
-    return;
+    for (int k = 0; k < 5; k++) dst[k] = src[k];
   }
-  if (i == 0 || key[i - 1] != kk) range[kk].x = (int)i;
-  if (i == m - 1 || key[i + 1] != kk) {
-    range[kk].y = (int)i + 1;
-    if (i == m - 1) *n_kept = (unsigned long long)m;
-  }
+  const long long prev = i == 0 ? -1 : (long long)min(key[i - 1], (uint32_t)n_slots);
+  const long long cur = i == m ? (long long)n_slots : (long long)min(key[i], (uint32_t)n_slots);
+  for (long long sl = prev + 1; sl <= cur; sl++) off[sl] = (int32_t)i;
 }
 
 struct GatherArgs {
   HpSoA s;
   long long n_hp;
   const int32_t* occ_start;
-  const int32_t* occ_nbr;
+  const int2* occ_run;  // [n_occ][9] slot runs
   int n_occ;
-  const int2* range;
+  const int32_t* dep_off;  // CSR offsets [n_slots + 1]
   const Deposit* dep;
   double search_r2;
   DevCounters* counters;
 };
 
-// One CTA per occupied hit-point cell (cells are taken from a global work counter).  The
-// deposits of the cell's 27 neighbour cells are streamed through a shared-memory tile with
-// coalesced 128-bit loads (their ranges are contiguous runs of the cell-sorted list); the 256
-// threads are split hl x dl: hl threads hold hit points of the cell (pos, n, R2 in registers),
-// dl = 256/hl threads stride over the tile, so a warp reads each 80-byte record as five
-// broadcast 128-bit shared loads.  Partial sums are combined with shuffles + shared memory
-// and every hit point's accumulators are written exactly once per batch (no atomics).
+// ---- TMA (cp.async.bulk) + mbarrier helpers -----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done = 0;
+  for (unsigned spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();  // a lost transaction must abort, not hang the GPU
+  }
+}
+
+// One CTA per occupied hit-point cell (cells are handed out by a global work counter).  The
+// deposits of the cell's 27 neighbour cells are 9 contiguous ranges of the cell-sorted list;
+// one thread streams them into a double-buffered shared-memory tile with TMA bulk copies
+// (cp.async.bulk + mbarrier) one tile ahead of the math.  The 256 threads are split hl x dl:
+// hl threads hold hit points of the cell (pos, n, R2 in registers), dl = 256/hl threads stride
+// over the tile, so a warp reads each 80-byte record as 128-bit shared-memory broadcasts.
+// Partial sums are combined with shuffles + shared memory and every hit point's accumulators
+// are written exactly once per batch (no atomics).
 constexpr int G_THREADS = 256;
-constexpr int G_TILE = 384;  // deposits per tile: 30 KB
+constexpr int G_TILE = 256;  // deposits per tile: 20 KB, two tiles in flight
+
+struct RunCursor {  // walks the concatenation of the 9 deposit ranges tile by tile (uniform)
+  int r, off;
+};
+// next piece of at most `room` deposits; returns its length and start (0 when exhausted)
+__device__ __forceinline__ int next_piece(RunCursor& c, const int* rs, const int* rl, int room, int& start) {
+  while (c.r < 9 && c.off >= rl[c.r]) {
+    c.r++;
+    c.off = 0;
+  }
+  if (c.r >= 9) return 0;
+  const int take = min(rl[c.r] - c.off, room);
+  start = rs[c.r] + c.off;
+  c.off += take;
+  return take;
+}
 
 __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, unsigned int* work_counter) {
-  __shared__ double2 tile[G_TILE * 5];
-  __shared__ int rs[27], rl[27];
+  __shared__ __align__(128) double2 tile[2][G_TILE * 5];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int rs[9], rl[9];
   __shared__ int s_cell, s_total;
   __shared__ int red_cnt[G_THREADS];
   __shared__ double red_s[3][G_THREADS];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned phase[2] = {0, 0};  // parity of the next completion of each barrier (uniform)
+  unsigned cand32 = 0, acc32 = 0;
   unsigned long long cand = 0, acc = 0;
   for (;;) {
-    __syncthreads();  // previous cell fully done (rs/rl/s_cell reusable)
+    __syncthreads();  // previous cell fully done (rs/rl/s_cell/red reusable)
     if (tid == 0) s_cell = (int)atomicAdd(work_counter, 1u);
     __syncthreads();
     const int c = s_cell;
     if (c >= a.n_occ) break;
     if (tid < 32) {
-      int st = 0, ln = 0;
-      if (tid < 27) {
-        const int32_t slot = a.occ_nbr[(long long)c * 27 + tid];
-        if (slot >= 0) {
-          const int2 r = a.range[slot];
-          st = r.x;
-          ln = r.y - r.x;
+      int ln = 0;
+      if (tid < 9) {
+        const int2 run = a.occ_run[(long long)c * 9 + tid];
+        int st = 0;
+        if (run.y > run.x) {
+          st = a.dep_off[run.x];
+          ln = a.dep_off[run.y] - st;
         }
         rs[tid] = st;
         rl[tid] = ln;
@@ -234,45 +290,59 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
       }
       int cnt = 0;
       double s0 = 0, s1 = 0, s2 = 0;
-      int r = 0, off = 0, fill = 0;
-      while (r < 27) {
-        const int take = min(rl[r] - off, G_TILE - fill);
-        if (take > 0) {
-          const double2* src = reinterpret_cast<const double2*>(a.dep + rs[r] + off);
-          double2* dst = tile + fill * 5;
-          for (int k = tid; k < take * 5; k += G_THREADS) dst[k] = __ldg(src + k);
+      // producer cursor runs one tile ahead of the consumer cursor; both are warp-uniform
+      RunCursor pc{0, 0};
+      auto issue = [&](int buf) -> int {  // thread 0 issues the bulk copies of the next tile
+        int fill = 0, start = 0, take;
+        RunCursor t = pc;
+        unsigned bytes = 0;
+        {  // total bytes first (expect_tx precedes the copies)
+          RunCursor q = pc;
+          int f = 0, st2 = 0, tk;
+          while (f < G_TILE && (tk = next_piece(q, rs, rl, G_TILE - f, st2)) > 0) f += tk;
+          bytes = (unsigned)f * (unsigned)sizeof(Deposit);
+        }
+        if (bytes == 0) return 0;
+        if (tid == 0) mbar_expect_tx(&bar[buf], bytes);
+        while (fill < G_TILE && (take = next_piece(t, rs, rl, G_TILE - fill, start)) > 0) {
+          if (tid == 0) bulk_g2s(&tile[buf][fill * 5], a.dep + start, (unsigned)take * (unsigned)sizeof(Deposit), &bar[buf]);
           fill += take;
-          off += take;
         }
-        if (off >= rl[r]) {
-          r++;
-          off = 0;
-        }
-        if (fill == G_TILE || (r == 27 && fill > 0)) {
-          __syncthreads();
-          if (valid) {
-            for (int d = my_d; d < fill; d += dl) {
-              const double2* q = tile + d * 5;
-              const double2 q0 = q[0], q1 = q[1], q2 = q[2];
-              // x = (q0.x, q0.y, q1.x)  N = (q1.y, q2.x, q2.y)  flux = (q3.x, q3.y, q4.x)
-              const double vx = px - q0.x, vy = py - q0.y, vz = pz - q1.x;  // Raytracer.h:152
-              const double vv = (vx * vx + vy * vy) + vz * vz;
-              if (vv < a.search_r2) {  // flann radiusSearch, strict '<' (Q3)
-                cand++;
-                const double nn = (nx * q1.y + ny * q2.x) + nz * q2.y;
-                if (nn > SPPM_NORMAL_AGREE && vv <= r2) {  // Raytracer.h:154
-                  const double2 q3 = q[3], q4 = q[4];
-                  cnt++;
-                  s0 += q3.x; s1 += q3.y; s2 += q4.x;
-                  acc++;
-                }
+        pc = t;
+        return fill;
+      };
+      int fill_cur = issue(0);
+      int k = 0;
+      while (fill_cur > 0) {
+        const int buf = k & 1;
+        const int fill_next = issue(buf ^ 1);  // prefetch tile k+1 while tile k is consumed
+        mbar_wait(&bar[buf], phase[buf]);
+        phase[buf] ^= 1;
+        if (valid) {
+          const double2* tb = tile[buf];
+#pragma unroll 2
+          for (int d = my_d; d < fill_cur; d += dl) {
+            const double2* q = tb + d * 5;
+            const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+            // x = (q0.x, q0.y, q1.x)  N = (q1.y, q2.x, q2.y)  flux = (q3.x, q3.y, q4.x)
+            const double vx = px - q0.x, vy = py - q0.y, vz = pz - q1.x;  // Raytracer.h:152
+            const double vv = (vx * vx + vy * vy) + vz * vz;
+            if (vv < a.search_r2) {  // flann radiusSearch, strict '<' (Q3)
+              cand32++;
+              const double nn = (nx * q1.y + ny * q2.x) + nz * q2.y;
+              if (nn > SPPM_NORMAL_AGREE && vv <= r2) {  // Raytracer.h:154
+                const double2 q3 = q[3], q4 = q[4];
+                cnt++;
+                s0 += q3.x; s1 += q3.y; s2 += q4.x;
               }
             }
           }
-          __syncthreads();
-          fill = 0;
         }
+        __syncthreads();  // tile k fully consumed: its buffer may be refilled (tile k+2)
+        fill_cur = fill_next;
+        k++;
       }
+      acc32 += (unsigned)cnt;
       // combine the dl partial sums of every hit point
       if (hl < 32) {
         for (int o = hl; o < 32; o <<= 1) {
@@ -308,8 +378,10 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
       }
       __syncthreads();
     }
+    cand += cand32;
+    acc += acc32;
+    cand32 = acc32 = 0;
   }
-  (void)warp;
   for (int off = 16; off > 0; off >>= 1) {
     cand += __shfl_xor_sync(FULL, cand, off);
     acc += __shfl_xor_sync(FULL, acc, off);
@@ -393,7 +465,7 @@ cudaError_t build_index(sppm_ctx* c) {
     CK(cudaMemsetAsync(c->cell_slot.p, 0xff, 4, st));
     CK(dev_reserve(c->occ_start, 8));
     CK(dev_reserve(c->occ_cell, 4));
-    CK(dev_reserve(c->occ_nbr, 27 * 4));
+    CK(dev_reserve(c->occ_nbr, 9 * 8));
     CK(dev_reserve(c->dep_start, 16));
     c->index_ok = true;
     return cudaSuccess;
@@ -511,10 +583,10 @@ cudaError_t build_index(sppm_ctx* c) {
   CK(cudaMemcpyAsync(&n_slots, d_nruns, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   c->n_slots = n_slots;
-  CK(dev_reserve(c->occ_nbr, (size_t)n_occ * 27 * 4));
-  occ_nbr_kernel<<<nblk((long long)n_occ * 27), TPB, 0, st>>>((uint32_t*)c->occ_cell.p, n_occ, g, (int32_t*)c->cell_slot.p,
-                                                               (int32_t*)c->occ_nbr.p);
-  CK(dev_reserve(c->dep_start, ((size_t)n_slots + 1) * 8));
+  CK(dev_reserve(c->occ_nbr, (size_t)n_occ * 9 * 8));
+  occ_run_kernel<<<nblk((long long)n_occ * 9), TPB, 0, st>>>((uint32_t*)c->occ_cell.p, n_occ, g, (int32_t*)c->cell_slot.p,
+                                                             (int2*)c->occ_nbr.p);
+  CK(dev_reserve(c->dep_start, ((size_t)n_slots + 2) * 4));
   c->host_counters.launches += 4;
   CK(cudaGetLastError());
   c->host_counters.hit_points = (uint64_t)n;
@@ -551,19 +623,16 @@ cudaError_t sort_and_gather(sppm_ctx* c, int64_t m) {
   CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k1, k2, i1, i2, (int)m, 0, end_bit, st));
   CK(dev_reserve(c->cub_tmp, tmp));
   CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k1, k2, i1, i2, (int)m, 0, end_bit, st));
-  CK(cudaMemsetAsync(c->dep_start.p, 0, ((size_t)c->n_slots + 1) * 8, st));
-  unsigned long long* n_kept = (unsigned long long*)c->dev_scalars.p + 3;
-  CK(cudaMemsetAsync(n_kept, 0, 8, st));
-  dep_permute_kernel<<<nblk(m), TPB, 0, st>>>((const Deposit*)c->dep_raw.p, k2, i2, m, c->n_slots, (Deposit*)c->dep_sorted.p,
-                                               (int2*)c->dep_start.p, n_kept);
+  dep_permute_kernel<<<nblk(m + 1), TPB, 0, st>>>((const Deposit*)c->dep_raw.p, k2, i2, m, c->n_slots, (Deposit*)c->dep_sorted.p,
+                                                   (int32_t*)c->dep_start.p);
   CK(cudaEventRecord(c->ev[2], st));
   GatherArgs a;
   a.s = c->soa;
   a.n_hp = c->n_hp;
   a.occ_start = (const int32_t*)c->occ_start.p;
-  a.occ_nbr = (const int32_t*)c->occ_nbr.p;
+  a.occ_run = (const int2*)c->occ_nbr.p;
   a.n_occ = c->n_occ;
-  a.range = (const int2*)c->dep_start.p;
+  a.dep_off = (const int32_t*)c->dep_start.p;
   a.dep = (const Deposit*)c->dep_sorted.p;
   a.search_r2 = c->prm.init_r2;
   a.counters = (DevCounters*)c->counters.p;
