@@ -276,12 +276,19 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
     const int hs = a.occ_start[c], he = a.occ_start[c + 1];
     for (int h0 = hs; h0 < he; h0 += G_THREADS) {
       const int H = min(G_THREADS, he - h0);
-      int hl = 1;
-      while (hl < H) hl <<= 1;
+      // thread -> (hit point, deposit slice).  Cells with few hit points use a power-of-two
+      // split (partials combined with shuffles); otherwise hl = H exactly, dl = 256 / H slices
+      // and at most H - 1 idle threads (90 % of the pair tests sit in cells with 17..128 points).
+      const bool pow2 = H < 9;
+      int hl = H;
+      if (pow2) {
+        hl = 1;
+        while (hl < H) hl <<= 1;
+      }
       const int dl = G_THREADS / hl;
-      const int my_h = tid & (hl - 1), my_d = tid / hl;
+      const int my_h = pow2 ? (tid & (hl - 1)) : (tid % hl), my_d = tid / hl;
       const int i = h0 + my_h;
-      const bool valid = my_h < H;
+      const bool valid = my_h < H && my_d < dl;
       double px = 0, py = 0, pz = 0, nx = 0, ny = 0, nz = 0, r2 = -1;
       if (valid) {
         px = a.s.px[i]; py = a.s.py[i]; pz = a.s.pz[i];
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
       }
       acc32 += (unsigned)cnt;
       // combine the dl partial sums of every hit point
-      if (hl < 32) {
+      if (pow2) {
         for (int o = hl; o < 32; o <<= 1) {
           cnt += __shfl_xor_sync(FULL, cnt, o);
           s0 += __shfl_xor_sync(FULL, s0, o);
@@ -352,13 +359,13 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
           s2 += __shfl_xor_sync(FULL, s2, o);
         }
       }
-      red_cnt[tid] = cnt;
+      red_cnt[tid] = valid ? cnt : 0;
       red_s[0][tid] = s0; red_s[1][tid] = s1; red_s[2][tid] = s2;
       __syncthreads();
-      if (tid < hl && valid) {
+      if (tid < H) {
         int tc = 0;
         double t0 = 0, t1 = 0, t2 = 0;
-        if (hl < 32) {
+        if (pow2) {  // lanes 0..hl-1 of every warp hold that warp's sums
           for (int w = 0; w < G_THREADS / 32; w++) {
             tc += red_cnt[w * 32 + tid];
             t0 += red_s[0][w * 32 + tid]; t1 += red_s[1][w * 32 + tid]; t2 += red_s[2][w * 32 + tid];

@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) newton_items_kernel(const Newto
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
   unsigned C = (n + n_warps - 1) / n_warps;
-  C = C < 4 ? 4 : (C > 32 ? 32 : C);
+  C = C < 1 ? 1 : (C > 32 ? 32 : C);  // few items: one per warp keeps the serial Newton chain short
   for (unsigned c0 = warp_global * C; c0 < n; c0 += n_warps * C) {
     const int cnt = (int)min(C, n - c0);
     if (lane < cnt) {
