@@ -165,11 +165,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--newton", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--trace", default="wavefront", choices=["wavefront", "persistent"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
@@ -193,6 +194,7 @@ def main():
 
     wl = WORKLOADS[args.workload]
     prm = make_params(abi, fast=args.newton == "fast")
+    prm.trace_mode = abi.SPPM_TRACE_PERSISTENT if args.trace == "persistent" else abi.SPPM_TRACE_WAVEFRONT
     ctx = Context(local_rank, prm)
     scene = make_scene(wl["scene"])
     cam = reference_camera(wl["w"], wl["h"])
@@ -295,8 +297,9 @@ def main():
     gather_flops = 13.0 * cand + 9.0 * acc
     trace_bytes = 84.0 * dep_kept                                      # deposits written (80 B + 4 B key)
     trace_flops = 175000.0 * solves + 140.0 * queries                  # Newton (350 x 500) + analytic tests
+    trace_name = "photon_trace_kernel" if prm.trace_mode == abi.SPPM_TRACE_PERSISTENT else "photon_step_kernel+newton_items_kernel"
     kern = {
-        "photon_trace_kernel": dict(ms=ms_trace, bytes=trace_bytes, flops=trace_flops),
+        trace_name: dict(ms=ms_trace, bytes=trace_bytes, flops=trace_flops),
         "gather_kernel": dict(ms=ms_gather, bytes=gather_bytes, flops=gather_flops),
     }
     dom = max(kern, key=lambda k: kern[k]["ms"])
@@ -332,7 +335,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "scene": wl["scene"], "film": [wl["w"], wl["h"]], "hit_points": n_hp,
-                   "photons_per_gpu_per_step": onetime * len(scene.plvec), "newton": f"50x10 {args.newton}",
+                   "photons_per_gpu_per_step": onetime * len(scene.plvec), "newton": f"50x10 {args.newton}", "tracer": args.trace,
                    "update_mode": "reference", "l2": "inputs larger than L2 (deposit list + hit-point map > 126 MB); new photons every step",
                    "textures": "synthetic, reference sizes", "parallelism": f"photons x{world}, hit points replicated"},
         "e2e": {"value": e2e_value, "unit": "photons/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -18,6 +18,13 @@
 // Results are identical: the RNG is addressed by (pass, photon id, bounce, ...).
 #include "ctx.h"
 
+#ifndef SPPM_STEP_MINBLOCKS
+#define SPPM_STEP_MINBLOCKS 4    // CTAs/SM the step kernel's register budget is sized for
+#endif
+#ifndef SPPM_NEWTON_MINBLOCKS
+#define SPPM_NEWTON_MINBLOCKS 2  // same for the Newton item kernel
+#endif
+
 namespace sppm {
 
 namespace {
@@ -68,7 +75,7 @@ __device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
 }
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
 
-__global__ void __launch_bounds__(STEP_THREADS) photon_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem);
   const int lane = threadIdx.x & 31;
@@ -311,7 +318,7 @@ struct NewtonArgs {
 // Bezier3::newton for the queued (photon slot, patch) items.  Each warp takes chunks of C items
 // (C chosen so that all warps of the grid get work) and runs the C*restarts tasks over its 32
 // lanes with flush_items (scene.cuh): lanes = restarts, arg-min on (t, restart) per item.
-__global__ void __launch_bounds__(TRACE_THREADS) newton_items_kernel(const NewtonArgs a) {
+__global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_items_kernel(const NewtonArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned n = min(*a.n_items_ptr, a.item_cap);
   if (n == 0) return;
