@@ -55,6 +55,9 @@ class Oracle:
         L.orc_eye_pass.argtypes = [C.POINTER(abi.SppmSceneDesc), C.POINTER(abi.SppmParams), C.POINTER(abi.SppmCameraDesc),
                                    U64, I64, VP, VP, VP, VP, VP, VP]
         L.orc_eye_pass.restype = I64
+        L.orc_view_trace_pixel.argtypes = [C.POINTER(abi.SppmSceneDesc), C.POINTER(abi.SppmParams), C.POINTER(abi.SppmCameraDesc),
+                                           U64, C.c_int, C.c_int, I64, VP, VP, VP, VP, VP]
+        L.orc_view_trace_pixel.restype = I64
         L.orc_gather_brute.argtypes = [I64, VP, VP, VP, VP, I64, VP, VP, VP, DBL, VP, VP, VP, VP]
         L.orc_kdtree_build.argtypes = [I64, VP]
         L.orc_kdtree_build.restype = VP
@@ -74,6 +77,8 @@ class Oracle:
         L.orc_render_replicas.argtypes = [C.POINTER(abi.SppmSceneDesc), C.POINTER(abi.SppmParams), VP, VP, I32, I32, I32,
                                           I32, I32, DBL, VP, VP, VP]
         L.orc_max_threads.restype = C.c_int
+        L.orc_log_end.argtypes = [VP, VP, I64]
+        L.orc_log_end.restype = I64
 
     # -- small pieces
     def philox(self, ctr, key):
@@ -177,6 +182,16 @@ class Oracle:
         return dict(pos=pos3[:n].copy(), n=n3[:n].copy(), wgt=wgt3[:n].copy(), r2=r2[:n].copy(), pix=pix[:n].copy(),
                     node=node[:n].copy())
 
+    def view_trace_pixel(self, scene, prm, cam, i, j, pass_id=0, cap=64):
+        d = self._desc(scene)
+        cd = cam.desc() if isinstance(cam, Camera) else cam
+        p3, n3, w3 = np.zeros((cap, 3)), np.zeros((cap, 3)), np.zeros((cap, 3))
+        r2 = np.zeros(cap)
+        pix = np.zeros((cap, 2), dtype=np.int32)
+        n = self.lib.orc_view_trace_pixel(C.byref(d), C.byref(prm), C.byref(cd), pass_id, i, j, cap, _p(p3), _p(n3), _p(w3),
+                                          _p(r2), _p(pix))
+        return dict(pos=p3[:n], n=n3[:n], wgt=w3[:n], r2=r2[:n], pix=pix[:n])
+
     def gather_brute(self, hp, dep, search_r2, newN=None, tao=None):
         n = hp["pos"].shape[0]
         m = dep["x"].shape[0]
@@ -266,6 +281,16 @@ class Oracle:
         out = np.zeros((h, w, 3), dtype=np.uint8)
         self.lib.orc_tonemap(_p(film), w, h, div, _p(out))
         return out
+
+    def log_begin(self):
+        self.lib.orc_log_begin()
+
+    def log_end(self, cap=1 << 20):
+        vals = np.empty(cap)
+        kinds = np.empty(cap, dtype=np.int8)
+        n = self.lib.orc_log_end(_p(vals), _p(kinds), cap)
+        assert n <= cap
+        return vals[:n].copy(), kinds[:n].copy()
 
     def max_threads(self):
         return self.lib.orc_max_threads()

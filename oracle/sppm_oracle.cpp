@@ -1,6 +1,7 @@
 // sppm_oracle.cpp — CPU oracle: a line-by-line restatement of wondergo2017/raytrace3's
-// render path.  TEST INFRASTRUCTURE ONLY (see sppm_oracle.h).  PARITY UNPINNED by the
-// reference's own tests (none exist); pins are listed in sppm_oracle.h / DESIGN.md.
+// render path.  TEST INFRASTRUCTURE ONLY (see sppm_oracle.h).  The reference has no tests of
+// its own; this file is pinned bit-for-bit against the reference's own code compiled here
+// (oracle/_ref, tests/test_ref_pin_cpu.py); all pins are listed in sppm_oracle.h / DESIGN.md.
 //
 // Build: g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC (MSVC x64 /fp:precise does not
 // contract to FMA either).  All arithmetic is double and keeps the reference's
@@ -145,6 +146,18 @@ inline void draw2(uint64_t seed, uint64_t pass, uint64_t id, uint32_t node, uint
   out[0] = u53(o[0], o[1]);
   out[1] = u53(o[2], o[3]);
 }
+// Optional log of the uniforms in the order the REFERENCE would consume them (used to feed the
+// real reference code, oracle/_ref, with the same numbers).  kind: 0 single draw, 1 = u0 and
+// 2 = v0 of a Newton restart (their consumption order in `Vec3 x(0, GetRandu(), GetRandu())`,
+// Bezier.h:117, is compiler-dependent, Q16).  Not thread-safe: single-ray calls only.
+std::vector<double>* g_draw_log = nullptr;
+std::vector<signed char>* g_draw_kind = nullptr;
+inline void log_draw(double u, int kind) {
+  if (g_draw_log) {
+    g_draw_log->push_back(u);
+    g_draw_kind->push_back((signed char)kind);
+  }
+}
 // cv::RNG::uniform(double a, double b) = u*(b-a)+a (Vec3.h:15-18).
 inline double GetRandu(double u, double r1, double r2) { return u * (r2 - r1) + r1; }
 
@@ -159,6 +172,9 @@ V3 GetUnitRandVec(uint64_t seed, uint64_t pass, uint64_t id, uint32_t purpose) {
     x = GetRandu(d0[0], -1., 1.);
     y = GetRandu(d0[1], -1., 1.);
     z = GetRandu(d1[0], -1., 1.);
+    log_draw(d0[0], 0);
+    log_draw(d0[1], 0);
+    log_draw(d1[0], 0);
     a++;
   } while ((x * x + y * y + z * z > 1 || x * x + y * y + z * z < M_EPS_) && a < 2000);
   return GetUnit(V3(x, y, z));
@@ -466,6 +482,8 @@ Coll bezierIntersect(const SceneC& sc, int idx, const V3& o, const V3& d, const 
       if (solves) (*solves)++;
       paratmp = newton(&sc.P[(size_t)gp * 16], o, d, prm.newton_restarts, prm.newton_iters, [&](int r, double uv[2]) {
         draw2(ra.seed, ra.pass, ra.id, ra.node, ra.domain, (uint32_t)r, (uint32_t)gp, uv);
+        log_draw(uv[0], 1);
+        log_draw(uv[1], 2);
       });
     }
     if (paratmp[0] < M_EPS_ || paratmp[0] > para[0] || paratmp[1] < -M_EPS_ || paratmp[1] > 1 + M_EPS_ ||
@@ -646,9 +664,12 @@ void PhotonTrace(const SceneC& sc, const SppmParams& prm, V3 org, V3 dir, V3 flu
     double d0[2], d1[2];
     draw2(prm.seed, pass, id, (uint32_t)node, P_BOUNCE, 0, 0, d0);
     double r = GetRandu(d0[0], 0., obj.allr);
+    log_draw(d0[0], 0);
     V3 nflux = mul(c1.color, flux);
     if (obj.diffr > r) {  // DIFF (Raytracer.h:163-166)
       draw2(prm.seed, pass, id, (uint32_t)node, P_BOUNCE, 1, 0, d1);
+      log_draw(d0[1], 0);
+      log_draw(d1[0], 0);
       dir = GetUnitRandRefl(c1.N, d0[1], d1[0]);
     } else if (obj.diffr + obj.reflr > r) {  // REFL (:177-181)
       dir = GetUnitRefl(c1.From, c1.N);
@@ -912,6 +933,17 @@ int64_t orc_eye_pass(const SppmSceneDesc* scene, const SppmParams* prm, const Sp
   return total;
 }
 
+// ViewTrace of one pixel (Raytracer.h:111), single-threaded (usable with the draw log).
+int64_t orc_view_trace_pixel(const SppmSceneDesc* scene, const SppmParams* prm, const SppmCameraDesc* cam, uint64_t pass_id,
+                             int i, int j, int64_t cap, double* pos3, double* n3, double* wgt3, double* r2, int32_t* pix) {
+  SceneC sc(scene);
+  HpSink out{cap, 0, pos3, n3, wgt3, r2, pix, nullptr, prm->init_r2};
+  V3 o, d;
+  cameraEmit(cam, i, j, o, d);
+  ViewTrace(sc, *prm, o, d, 0, V3(1, 1, 1), i, j, pass_id, (uint64_t)i * cam->w + j, 1, out, nullptr);
+  return out.n;
+}
+
 void orc_gather_brute(int64_t n_hp, const double* pos3, const double* n3, const double* wgt3, const double* r2,
                       int64_t m, const double* x3, const double* dn3, const double* flux3, double search_r2,
                       int32_t* newN, double* tao3, uint64_t* cand_pairs, uint64_t* acc_pairs) {
@@ -1038,6 +1070,25 @@ void orc_tonemap(const double* film, int32_t w, int32_t h, double div, uint8_t* 
     for (int j = 0; j < w; j++)
       for (int k = 0; k < 3; k++)
         bgr[((size_t)(h - 1 - i1) * w + j) * 3 + k] = (uint8_t)toInt(film[((size_t)i1 * w + j) * 3 + k] / div);
+}
+
+void orc_log_begin(void) {
+  static std::vector<double> vals;
+  static std::vector<signed char> kinds;
+  vals.clear();
+  kinds.clear();
+  g_draw_log = &vals;
+  g_draw_kind = &kinds;
+}
+int64_t orc_log_end(double* vals, signed char* kinds, int64_t cap) {
+  int64_t n = g_draw_log ? (int64_t)g_draw_log->size() : 0;
+  for (int64_t i = 0; i < n && i < cap; i++) {
+    vals[i] = (*g_draw_log)[i];
+    kinds[i] = (*g_draw_kind)[i];
+  }
+  g_draw_log = nullptr;
+  g_draw_kind = nullptr;
+  return n;
 }
 
 int orc_max_threads(void) {

@@ -4,11 +4,16 @@
  * The oracle is a dependency-free restatement of wondergo2017/raytrace3's render path
  * (raytracer/{Vec3,Element,Obj,Bezier,Light,Scene,Camera,Raytracer}.h).  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load
- * it.  PARITY UNPINNED by the reference's own tests (it has none); the
- * pins are: cv2.invert for the 3x3 inverse, Random123 known-answer vectors for Philox,
- * cv2.flann for the strict '<' radius semantics, committed golden vectors produced by
- * this oracle (tests/golden), and — in this container only — oracle/_ref, the
- * reference's own headers compiled against a thin OpenCV/FLANN shim.
+ * it.  Parity status: the reference ships no tests or golden vectors, so the
+ * oracle is pinned against THE REFERENCE'S OWN CODE run here: oracle/_ref/libref.so = the
+ * reference's headers compiled from /root/reference/raytracer (three MSVC-only tokens patched
+ * in a scratch copy) against a thin OpenCV/FLANN shim (oracle/ref_shim), with the random
+ * numbers injected in the reference's consumption order; tests/test_ref_pin_cpu.py shows the
+ * oracle bit-identical to it for patch evaluation, AABB, Newton, sampling, optics, camera,
+ * textures, NearCollide, PhotonTrace + gather, ViewTrace, update, resolve and tone map.
+ * The third-party arithmetic the shim restates is pinned separately: cv2.invert for
+ * cv::Matx33d::inv, cv2.flann for the strict '<' radius search; Philox against Random123
+ * known answers; plus committed golden vectors (tests/golden).
  *
  * The PODs are the ones of include/sppm_b200.h so the same flattened scene feeds both.
  */
@@ -60,6 +65,9 @@ int64_t orc_eye_pass(const SppmSceneDesc* scene, const SppmParams* prm, const Sp
                      uint64_t pass_id, int64_t cap, double* pos3, double* n3, double* wgt3, double* r2,
                      int32_t* pix, uint32_t* node);
 
+int64_t orc_view_trace_pixel(const SppmSceneDesc* scene, const SppmParams* prm, const SppmCameraDesc* cam, uint64_t pass_id,
+                             int i, int j, int64_t cap, double* pos3, double* n3, double* wgt3, double* r2, int32_t* pix);
+
 /* The gather of Raytracer.h:139-159 by exhaustive search (the semantic definition). */
 void orc_gather_brute(int64_t n_hp, const double* pos3, const double* n3, const double* wgt3,
                       const double* r2, int64_t m, const double* x3, const double* dn3, const double* flux3,
@@ -104,6 +112,9 @@ void orc_render_replicas(const SppmSceneDesc* scene, const SppmParams* prm, cons
                          const double cam_look[3], int32_t w, int32_t h, int32_t cnt, int32_t onetime,
                          int32_t threads, double jitter, double* film, double* times, uint64_t* counters);
 int orc_max_threads(void);
+/* Draw log for feeding oracle/_ref (single-ray calls only; see sppm_oracle.cpp). */
+void orc_log_begin(void);
+int64_t orc_log_end(double* vals, signed char* kinds, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -361,3 +361,33 @@ def test_wavefront_equals_persistent(ctx):
     for k in ("photons", "isect_queries", "patch_solves", "deposits", "deposits_kept", "cand_pairs", "acc_pairs"):
         assert c0[k] == c1[k], k
     assert c0["patch_solves"] > 1000
+
+
+def test_gpu_matches_the_reference_itself(ctx, oracle):
+    """CUDA NearCollide against the reference's OWN compiled code (oracle/_ref, built from
+    /root/reference/raytracer/*.h; the oracle only supplies the draw log that tells which
+    Newton seeds the addressed RNG hands to each (ray, patch, restart))."""
+    ref_mod = pytest.importorskip("oracle.ref")
+    if not ref_mod.available():
+        pytest.skip("oracle/_ref/libref.so not built (needs /root/reference)")
+    ref = ref_mod.Reference()
+    sc = make_scene("reference", textures="synthetic")
+    prm = _params()
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    rays = np.concatenate([rays_in_room(150, 41), rays_at_teapot(150, 42, sc)])
+    ids = np.arange(rays.shape[0], dtype=np.uint64) + 11
+    got = ctx.intersect_batch(rays, ids, pass_id=3, node=1)
+    h = ref.scene(sc)
+    bez = 0
+    for i in range(rays.shape[0]):
+        oracle.log_begin()
+        oracle.intersect_batch(sc, prm, rays[i:i + 1], ids[i:i + 1], pass_id=3, node=1)
+        vals, kinds = oracle.log_end()
+        b = ref.near_collide(h, rays[i], vals, kinds)
+        assert got["obj"][i] == b["obj"] and got["inside"][i] == b["inside"]
+        assert got["t"][i] == b["t"] and np.array_equal(got["pos"][i], b["pos"])
+        np.testing.assert_allclose(got["n"][i], b["n"], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(got["color"][i], b["color"], rtol=1e-12, atol=1e-15)
+        bez += got["patch"][i] >= 0
+    assert bez > 20
