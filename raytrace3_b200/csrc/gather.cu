@@ -213,7 +213,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 // Partial sums are combined with shuffles + shared memory and every hit point's accumulators
 // are written exactly once per batch (no atomics).
 constexpr int G_THREADS = 256;
-constexpr int G_TILE = 256;  // deposits per tile: 20 KB, two tiles in flight
+#ifndef SPPM_G_TILE
+#define SPPM_G_TILE 256
+#endif
+constexpr int G_TILE = SPPM_G_TILE;  // deposits per tile: 20 KB at 256, two tiles in flight
 
 struct RunCursor {  // walks the concatenation of the 9 deposit ranges tile by tile (uniform)
   int r, off;
@@ -232,7 +235,8 @@ __device__ __forceinline__ int next_piece(RunCursor& c, const int* rs, const int
 }
 
 __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, unsigned int* work_counter) {
-  __shared__ __align__(128) double2 tile[2][G_TILE * 5];
+  extern __shared__ __align__(128) unsigned char gsm[];
+  double2(*tile)[G_TILE * 5] = reinterpret_cast<double2(*)[G_TILE * 5]>(gsm);  // tile[2][G_TILE * 5]
   __shared__ __align__(8) uint64_t bar[2];
   __shared__ int rs[9], rl[9];
   __shared__ int s_cell, s_total;
@@ -272,7 +276,9 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
       if (tid == 0) s_total = tot;
     }
     __syncthreads();
-    if (s_total == 0) continue;  // no deposit near this cell in this batch
+    const int D = s_total;  // deposits in the 27-cell neighbourhood = concatenation of the 9 runs
+    if (D == 0) continue;   // no deposit near this cell in this batch
+    const int n_tiles = (D + G_TILE - 1) / G_TILE;
     const int hs = a.occ_start[c], he = a.occ_start[c + 1];
     for (int h0 = hs; h0 < he; h0 += G_THREADS) {
       const int H = min(G_THREADS, he - h0);
@@ -297,32 +303,25 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
       }
       int cnt = 0;
       double s0 = 0, s1 = 0, s2 = 0;
-      // producer cursor runs one tile ahead of the consumer cursor; both are warp-uniform
+      // Tile k holds deposits [k*G_TILE, min(D, (k+1)*G_TILE)) of the concatenation.  Only the
+      // producer (thread 0) walks the runs; it issues the bulk copies of tile k+1 while every
+      // thread consumes tile k.
       RunCursor pc{0, 0};
-      auto issue = [&](int buf) -> int {  // thread 0 issues the bulk copies of the next tile
+      auto issue = [&](int k) {
+        const int buf = k & 1;
+        const int fill_k = min(G_TILE, D - k * G_TILE);
+        mbar_expect_tx(&bar[buf], (unsigned)fill_k * (unsigned)sizeof(Deposit));
         int fill = 0, start = 0, take;
-        RunCursor t = pc;
-        unsigned bytes = 0;
-        {  // total bytes first (expect_tx precedes the copies)
-          RunCursor q = pc;
-          int f = 0, st2 = 0, tk;
-          while (f < G_TILE && (tk = next_piece(q, rs, rl, G_TILE - f, st2)) > 0) f += tk;
-          bytes = (unsigned)f * (unsigned)sizeof(Deposit);
-        }
-        if (bytes == 0) return 0;
-        if (tid == 0) mbar_expect_tx(&bar[buf], bytes);
-        while (fill < G_TILE && (take = next_piece(t, rs, rl, G_TILE - fill, start)) > 0) {
-          if (tid == 0) bulk_g2s(&tile[buf][fill * 5], a.dep + start, (unsigned)take * (unsigned)sizeof(Deposit), &bar[buf]);
+        while (fill < fill_k && (take = next_piece(pc, rs, rl, fill_k - fill, start)) > 0) {
+          bulk_g2s(&tile[buf][fill * 5], a.dep + start, (unsigned)take * (unsigned)sizeof(Deposit), &bar[buf]);
           fill += take;
         }
-        pc = t;
-        return fill;
       };
-      int fill_cur = issue(0);
-      int k = 0;
-      while (fill_cur > 0) {
+      if (tid == 0) issue(0);
+      for (int k = 0; k < n_tiles; k++) {
         const int buf = k & 1;
-        const int fill_next = issue(buf ^ 1);  // prefetch tile k+1 while tile k is consumed
+        if (tid == 0 && k + 1 < n_tiles) issue(k + 1);  // prefetch: buffer (k+1)&1 was released by the barrier below
+        const int fill_cur = min(G_TILE, D - k * G_TILE);
         mbar_wait(&bar[buf], phase[buf]);
         phase[buf] ^= 1;
         if (valid) {
@@ -346,8 +345,6 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
           }
         }
         __syncthreads();  // tile k fully consumed: its buffer may be refilled (tile k+2)
-        fill_cur = fill_next;
-        k++;
       }
       acc32 += (unsigned)cnt;
       // combine the dl partial sums of every hit point
@@ -647,7 +644,13 @@ cudaError_t sort_and_gather(sppm_ctx* c, int64_t m) {
   CK(cudaMemsetAsync(work_counter, 0, 4, st));
   unsigned blocks = (unsigned)c->sm_count * 4;  // persistent CTAs, cells handed out dynamically
   if (blocks > (unsigned)c->n_occ) blocks = (unsigned)c->n_occ;
-  gather_kernel<<<blocks, G_THREADS, 0, st>>>(a, work_counter);
+  const size_t tile_bytes = 2 * (size_t)G_TILE * sizeof(Deposit);
+  CK(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));  // per device
+  int per_sm = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel, G_THREADS, tile_bytes));
+  blocks = (unsigned)c->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm);
+  if (blocks > (unsigned)c->n_occ) blocks = (unsigned)c->n_occ;
+  gather_kernel<<<blocks, G_THREADS, tile_bytes, st>>>(a, work_counter);
   CK(cudaEventRecord(c->ev[3], st));
   c->host_counters.launches += 4;
   return cudaGetLastError();

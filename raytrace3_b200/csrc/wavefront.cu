@@ -16,10 +16,12 @@
 // on a finished photon, the register-heavy Newton solver does not limit the occupancy of the
 // light per-photon code, and the Newton tasks of the whole GPU are packed densely.
 // Results are identical: the RNG is addressed by (pass, photon id, bounce, ...).
+#include <cooperative_groups.h>
+
 #include "ctx.h"
 
 #ifndef SPPM_STEP_MINBLOCKS
-#define SPPM_STEP_MINBLOCKS 4    // CTAs/SM the step kernel's register budget is sized for
+#define SPPM_STEP_MINBLOCKS 6    // CTAs/SM the step kernel's register budget is sized for (80 regs; measured best)
 #endif
 #ifndef SPPM_NEWTON_MINBLOCKS
 #define SPPM_NEWTON_MINBLOCKS 2  // same for the Newton item kernel
@@ -82,17 +84,15 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
   const unsigned n_in = a.bounce == 0 ? a.n_in_host : *a.n_in_ptr;
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-  unsigned long long queries = 0, solves = 0, photons = 0, deposits = 0, kept = 0;
+  unsigned queries = 0, solves = 0, photons = 0, deposits = 0, kept = 0;  // per thread, < 2^32
 
   for (unsigned base = warp_global * 32; base < n_in; base += n_warps * 32) {
     const unsigned i = base + lane;
     const bool active = i < n_in;
-    bool alive = false, want = false;
+    bool alive = false;
     d3 org = mk(0, 0, 0), dir = mk(0, 0, 1), flux = mk(0, 0, 0);
     uint64_t id = 0;
     int dep = 0;
-    Deposit rec;
-    uint32_t key = 0;
     if (active) {
       if (a.bounce == 0) {  // Light::emit (Light.h:8-13)
         const unsigned pl = (unsigned)(i / a.count);
@@ -156,12 +156,21 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
             int32_t slot = -1;
             if (a.cell_slot) slot = __ldg(a.cell_slot + grid_cell(a.grid, s.pos.x, s.pos.y, s.pos.z));
             if (slot >= 0 || a.keep_all) {
-              want = true;
-              key = slot >= 0 ? (uint32_t)slot : (uint32_t)a.n_slots;
-              rec.x[0] = s.pos.x; rec.x[1] = s.pos.y; rec.x[2] = s.pos.z;
-              rec.n[0] = s.n.x; rec.n[1] = s.n.y; rec.n[2] = s.n.z;
-              rec.flux[0] = flux.x; rec.flux[1] = flux.y; rec.flux[2] = flux.z;
-              rec.meta = id | ((uint64_t)node << 56);
+              // append with one atomic per group of lanes that are here together
+              const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+              unsigned long long dbase = 0;
+              if (g.thread_rank() == 0) dbase = atomicAdd(a.dep_count, (unsigned long long)g.size());
+              const unsigned long long ds = g.shfl(dbase, 0) + g.thread_rank();
+              if (ds < a.dep_cap) {
+                Deposit rec;
+                rec.x[0] = s.pos.x; rec.x[1] = s.pos.y; rec.x[2] = s.pos.z;
+                rec.n[0] = s.n.x; rec.n[1] = s.n.y; rec.n[2] = s.n.z;
+                rec.flux[0] = flux.x; rec.flux[1] = flux.y; rec.flux[2] = flux.z;
+                rec.meta = id | ((uint64_t)node << 56);
+                a.dep[ds] = rec;
+                a.dep_key[ds] = slot >= 0 ? (uint32_t)slot : (uint32_t)a.n_slots;
+                kept++;
+              }
             }
           }
           // Obj::Roulette (Obj.h:30-45) and the single continuation (Raytracer.h:162-190)
@@ -183,23 +192,6 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
           org = s.pos;
           dir = ndir;
           alive = true;
-        }
-      }
-    }
-    // ---- deposits: warp-aggregated append
-    {
-      const unsigned m = __ballot_sync(FULL, want);
-      if (m) {
-        unsigned long long dbase = 0;
-        if (lane == 0) dbase = atomicAdd(a.dep_count, (unsigned long long)__popc(m));
-        dbase = __shfl_sync(FULL, dbase, 0);
-        if (want) {
-          const unsigned long long slot = dbase + __popc(m & ((1u << lane) - 1));
-          if (slot < a.dep_cap) {
-            a.dep[slot] = rec;
-            a.dep_key[slot] = key;
-            kept++;
-          }
         }
       }
     }
@@ -290,17 +282,14 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
       a.qout.item_cnt[s] = my_cnt;
     }
   }
-  queries = warp_sum64(queries);
-  solves = warp_sum64(solves);
-  photons = warp_sum64(photons);
-  deposits = warp_sum64(deposits);
-  kept = warp_sum64(kept);
+  const unsigned long long q64 = warp_sum64(queries), s64 = warp_sum64(solves), p64 = warp_sum64(photons),
+                           d64 = warp_sum64(deposits), k64 = warp_sum64(kept);
   if (lane == 0) {
-    if (queries) atomicAdd(&a.counters->isect_queries, queries);
-    if (solves) atomicAdd(&a.counters->patch_solves, solves);
-    if (photons) atomicAdd(&a.counters->photons, photons);
-    if (deposits) atomicAdd(&a.counters->deposits, deposits);
-    if (kept) atomicAdd(&a.counters->deposits_kept, kept);
+    if (q64) atomicAdd(&a.counters->isect_queries, q64);
+    if (s64) atomicAdd(&a.counters->patch_solves, s64);
+    if (p64) atomicAdd(&a.counters->photons, p64);
+    if (d64) atomicAdd(&a.counters->deposits, d64);
+    if (k64) atomicAdd(&a.counters->deposits_kept, k64);
   }
 }
 
