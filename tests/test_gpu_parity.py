@@ -391,3 +391,43 @@ def test_gpu_matches_the_reference_itself(ctx, oracle):
         np.testing.assert_allclose(got["color"][i], b["color"], rtol=1e-12, atol=1e-15)
         bez += got["patch"][i] >= 0
     assert bez > 20
+
+
+def test_full_size_properties(ctx):
+    """BASELINE config 3 at full size (1024x768, 2 M photons): size-independent properties.
+    (a) sum(newN) == accepted-pair counter and every pair was distance-tested first;
+    (b) linearity: two half rounds == one full round (newN bit-exact, tao to rounding);
+    (c) the film is the density estimate of tao (resolve), row-major [h][w][3];
+    (d) per-photon statistics match the CPU probe (5.9 queries, 3.7 deposits)."""
+    sc = make_scene("reference", textures="synthetic")
+    prm = _params(newton_mode=abi.SPPM_NEWTON_FAST)
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    w, h, onetime = 1024, 768, 2_000_000
+    cam = reference_camera(w, h)
+    n = ctx.eye_pass(cam, 0)
+    assert n == w * h  # 1.000 hit points per pixel in this scene
+    ctx.build_index()
+    ctx.reset_counters()
+    ctx.photon_pass(0, onetime, 1)
+    ctx.update()
+    full = ctx.export_stats(n)
+    c = ctx.counters()
+    assert int(full["newN"].astype(np.int64).sum()) == c["acc_pairs"] > 0
+    assert c["cand_pairs"] >= c["acc_pairs"] > 0.95 * c["cand_pairs"]
+    assert c["photons"] == onetime
+    assert 5.7 < c["isect_queries"] / onetime < 6.1 and 3.6 < c["deposits"] / onetime < 3.9
+    assert c["isect_queries"] <= 15 * onetime  # Q9
+    assert 0.03 < c["patch_solves"] / onetime < 0.045
+    film = ctx.resolve(1, onetime, w, h)
+    hp = ctx.export_hitpoints()
+    want = np.zeros((h, w, 3))
+    np.add.at(want, (hp["pix"][:, 0], hp["pix"][:, 1]), full["tao"] * (1.0 / 3.1415926 / (full["r2"] * 1 * onetime))[:, None])
+    np.testing.assert_allclose(film, want, rtol=1e-12, atol=0)
+    ctx.build_index()  # fresh accumulators, same hit points
+    ctx.photon_pass(0, onetime // 2, 1)
+    ctx.photon_pass(onetime // 2, onetime - onetime // 2, 1)
+    ctx.update()
+    halves = ctx.export_stats(n)
+    np.testing.assert_array_equal(halves["newN"], full["newN"])
+    np.testing.assert_allclose(halves["tao"], full["tao"], rtol=1e-11, atol=0)
