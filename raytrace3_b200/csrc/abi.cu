@@ -48,19 +48,38 @@ constexpr uint64_t PHOTON_BATCH = 1ull << 21;  // photons traced per kernel laun
 
 unsigned long long* scalars(sppm_ctx* c) { return (unsigned long long*)c->dev_scalars.p; }
 
-// pending per-phase timings are folded into the host counters at the next sync point
-struct Pending {
-  bool trace = false, sg = false;
-};
-thread_local Pending g_unused;
-
-void fold_timings(sppm_ctx* c, bool trace, bool sg) {
-  float ms = 0;
-  if (trace && cudaEventElapsedTime(&ms, c->ev[0], c->ev[4]) == cudaSuccess) c->host_counters.ms_trace += ms;
-  if (sg) {
-    if (cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]) == cudaSuccess) c->host_counters.ms_sort += ms;
-    if (cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->host_counters.ms_gather += ms;
+// Per-batch timings (trace / bin / gather) are taken with a ring of CUDA events and folded
+// into the host counters when the ring is full or at the next natural sync point, so the
+// photon pass itself never waits for the device.
+void fold_timings(sppm_ctx* c) {
+  if (c->t_pending == 0) return;
+  cudaEventSynchronize(c->tev[c->t_pending - 1][c->t_has_gather[c->t_pending - 1] ? 3 : 1]);
+  for (int i = 0; i < c->t_pending; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->tev[i][0], c->tev[i][1]) == cudaSuccess) c->host_counters.ms_trace += ms;
+    if (c->t_has_gather[i]) {
+      if (cudaEventElapsedTime(&ms, c->tev[i][1], c->tev[i][2]) == cudaSuccess) c->host_counters.ms_sort += ms;
+      if (cudaEventElapsedTime(&ms, c->tev[i][2], c->tev[i][3]) == cudaSuccess) c->host_counters.ms_gather += ms;
+    }
   }
+  c->t_pending = 0;
+}
+
+// Device-side overflow flags (deposit list, Bezier work-item list) are checked at sync points.
+int check_overflow(sppm_ctx* c) {
+  unsigned long long m = 0;
+  if (cudaMemcpyAsync(&m, (unsigned long long*)c->dev_scalars.p + 1, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+      cudaStreamSynchronize(c->stream) != cudaSuccess)
+    return cuda_fail(c, cudaGetLastError(), "check_overflow");
+  c->n_dep = (int64_t)std::min<unsigned long long>(m, (unsigned long long)std::max<int64_t>(c->dep_cap, 0));
+  if (c->dep_cap > 0 && (int64_t)m > c->dep_cap) return fail(c, SPPM_ERR_CAPACITY, "deposit buffer overflow");
+  if (c->prm.trace_mode != SPPM_TRACE_PERSISTENT) {
+    bool ovf = false;
+    cudaError_t e = wavefront_overflowed(c, &ovf);
+    if (e) return cuda_fail(c, e, "wavefront_overflowed");
+    if (ovf) return fail(c, SPPM_ERR_CAPACITY, "Bezier work-item list overflow (more than 2 (ray, patch) items per photon in one bounce)");
+  }
+  return SPPM_OK;
 }
 
 __global__ void tonemap_kernel(const double* film, int w, int h, double div, uint8_t* bgr) {
@@ -156,6 +175,7 @@ int ensure_deposit_capacity(sppm_ctx* c, int64_t cap) {
   if (cap <= c->dep_cap) return SPPM_OK;
   CU(c, dev_reserve(c->dep_raw, (size_t)cap * sizeof(Deposit)));
   CU(c, dev_reserve(c->dep_key, (size_t)cap * 4));
+  CU(c, dev_reserve(c->dep_rank, (size_t)cap * 4));
   c->dep_cap = cap;
   return SPPM_OK;
 }
@@ -215,6 +235,8 @@ int sppm_ctx_create(int device, sppm_ctx** out) {
   }
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 8 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  for (int i = 0; i < sppm_ctx::TIMING_RING && ok; i++)
+    for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&c->tev[i][k]) == cudaSuccess;
   ok = ok && dev_reserve(c->dev_scalars, 64) == cudaSuccess && dev_reserve(c->counters, sizeof(DevCounters)) == cudaSuccess;
   if (ok) {
     cudaMemset(c->dev_scalars.p, 0, 64);
@@ -236,11 +258,14 @@ void sppm_ctx_destroy(sppm_ctx* c) {
   if (c->nccl_comm && nccl().ok) nccl().CommDestroy((ncclComm_t)c->nccl_comm);
   free_scene(c);
   DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->dep_raw,
-                    &c->dep_sorted, &c->dep_key, &c->dep_key2, &c->dep_idx, &c->dep_idx2, &c->dep_start, &c->cub_tmp,
+                    &c->dep_sorted, &c->dep_key, &c->dep_key2, &c->dep_idx, &c->dep_idx2, &c->dep_start, &c->cub_tmp, &c->dep_rank, &c->slot_count,
                     &c->dev_scalars, &c->counters, &c->film, &c->scratch, &c->wf_store};
   for (DevBuf* d : bufs) dev_free(*d);
   for (int i = 0; i < 8; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (int i = 0; i < sppm_ctx::TIMING_RING; i++)
+    for (int k = 0; k < 4; k++)
+      if (c->tev[i][k]) cudaEventDestroy(c->tev[i][k]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -409,39 +434,26 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
   if (photon_begin + photon_count > (1ull << 40)) return fail(c, SPPM_ERR_INVALID, "photon index exceeds 2^40");
   Bind b(c);
   const uint64_t per_light_batch = std::max<uint64_t>(1, PHOTON_BATCH / (uint64_t)c->scene.n_light);
-  bool pend_sg = false;
+  const bool gather = c->index_ok && c->n_hp > 0;
+  if (!c->slot_count.p) CU(c, dev_reserve(c->slot_count, 16));
   for (uint64_t off = 0; off < photon_count; off += per_light_batch) {
     const uint64_t cnt = std::min(per_light_batch, photon_count - off);
     const int64_t cap = (int64_t)(cnt * c->scene.n_light) * (c->prm.max_dep + 1);
     int rc = ensure_deposit_capacity(c, cap);
     if (rc) return rc;
+    if (c->t_pending == sppm_ctx::TIMING_RING) fold_timings(c);
+    cudaEvent_t* te = c->tev[c->t_pending];
     CU(c, cudaMemsetAsync(scalars(c) + 1, 0, 16, c->stream));  // deposit count, photon cursor
-    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    CU(c, cudaMemsetAsync(c->slot_count.p, 0, ((size_t)(c->index_ok ? c->n_slots : 0) + 2) * 4, c->stream));
+    CU(c, cudaEventRecord(te[0], c->stream));
     if (c->prm.trace_mode == SPPM_TRACE_PERSISTENT) CU(c, launch_photon_trace(c, photon_begin + off, cnt, pass_id));
     else CU(c, launch_photon_trace_wavefront(c, photon_begin + off, cnt, pass_id));
-    CU(c, cudaEventRecord(c->ev[4], c->stream));
-    unsigned long long m = 0;
-    CU(c, cudaMemcpyAsync(&m, scalars(c) + 1, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-    fold_timings(c, true, pend_sg);
-    pend_sg = false;
-    if ((int64_t)m > c->dep_cap) return fail(c, SPPM_ERR_CAPACITY, "deposit buffer overflow");
-    if (c->prm.trace_mode != SPPM_TRACE_PERSISTENT) {
-      bool ovf = false;
-      CU(c, wavefront_overflowed(c, &ovf));
-      if (ovf) return fail(c, SPPM_ERR_CAPACITY, "Bezier work-item list overflow (more than 2 (ray, patch) items per photon in one bounce)");
-    }
-    c->n_dep = (int64_t)m;
-    if (c->index_ok && m > 0 && c->n_hp > 0) {
-      CU(c, sort_and_gather(c, (int64_t)m));
-      pend_sg = true;
-    }
+    CU(c, cudaEventRecord(te[1], c->stream));
+    if (gather) CU(c, bin_and_gather(c, te[2], te[3]));
+    c->t_has_gather[c->t_pending] = gather;
+    c->t_pending++;
   }
-  if (pend_sg) {  // timings of the last batch need its events to complete
-    CU(c, cudaEventSynchronize(c->ev[3]));
-    fold_timings(c, false, true);
-  }
-  return SPPM_OK;
+  return SPPM_OK;  // stream-ordered: nothing above waited for the device
 }
 
 int sppm_allreduce(sppm_ctx* c) {
@@ -479,7 +491,8 @@ int sppm_resolve(sppm_ctx* c, int32_t cnt, int32_t onetime, double* film_hw3) {
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
   c->host_counters.ms_resolve = ms;
-  return SPPM_OK;
+  fold_timings(c);
+  return check_overflow(c);
 }
 
 int sppm_tonemap(sppm_ctx* c, const double* film_hw3, int32_t w, int32_t h, double div, uint8_t* bgr_hw3) {
@@ -537,7 +550,8 @@ int sppm_device_synchronize(sppm_ctx* c) {
   if (!c) return SPPM_ERR_INVALID;
   Bind b(c);
   CU(c, cudaStreamSynchronize(c->stream));
-  return SPPM_OK;
+  fold_timings(c);
+  return check_overflow(c);
 }
 
 void* sppm_stream_handle(sppm_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -746,12 +760,21 @@ int sppm_gather_deposits(sppm_ctx* c, int64_t m, const double* x3, const double*
     d[i].meta = (uint64_t)i;
   }
   CU(c, cudaMemcpyAsync(c->dep_raw.p, d.data(), (size_t)m * sizeof(Deposit), cudaMemcpyHostToDevice, c->stream));
+  const unsigned long long m64 = (unsigned long long)m;
+  CU(c, cudaMemcpyAsync(scalars(c) + 1, &m64, 8, cudaMemcpyHostToDevice, c->stream));
   if (c->n_hp > 0) {
+    if (c->t_pending == sppm_ctx::TIMING_RING) fold_timings(c);
+    cudaEvent_t* te = c->tev[c->t_pending];
+    CU(c, cudaMemsetAsync(c->slot_count.p, 0, ((size_t)c->n_slots + 2) * 4, c->stream));
+    CU(c, cudaEventRecord(te[0], c->stream));
+    CU(c, cudaEventRecord(te[1], c->stream));
     CU(c, key_host_deposits(c, m));
-    CU(c, sort_and_gather(c, m));
+    CU(c, bin_and_gather(c, te[2], te[3]));
+    c->t_has_gather[c->t_pending] = true;
+    c->t_pending++;
   }
   CU(c, cudaStreamSynchronize(c->stream));
-  fold_timings(c, false, c->n_hp > 0);
+  fold_timings(c);
   return SPPM_OK;
 }
 
@@ -792,6 +815,7 @@ int sppm_export_deposits(sppm_ctx* c, int64_t cap, double* x3, double* n3, doubl
                          int32_t* bounce, int64_t* m_out) {
   if (!c) return SPPM_ERR_INVALID;
   Bind b(c);
+  { int rc = check_overflow(c); if (rc) return rc; }  // also refreshes n_dep from the device counter
   const int64_t m = c->n_dep;
   if (m_out) *m_out = m;
   if (m == 0) return SPPM_OK;
@@ -820,6 +844,7 @@ int sppm_get_counters(sppm_ctx* c, SppmCounters* out) {
   if (!c || !out) return SPPM_ERR_INVALID;
   Bind b(c);
   CU(c, cudaStreamSynchronize(c->stream));
+  fold_timings(c);
   DevCounters d;
   CU(c, cudaMemcpy(&d, c->counters.p, sizeof(d), cudaMemcpyDeviceToHost));
   SppmCounters& h = c->host_counters;
@@ -840,6 +865,7 @@ int sppm_reset_counters(sppm_ctx* c) {
   if (!c) return SPPM_ERR_INVALID;
   Bind b(c);
   CU(c, cudaStreamSynchronize(c->stream));
+  fold_timings(c);
   CU(c, cudaMemset(c->counters.p, 0, sizeof(DevCounters)));
   const uint64_t launches = c->host_counters.launches;
   c->host_counters = SppmCounters{};

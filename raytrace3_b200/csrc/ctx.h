@@ -98,6 +98,8 @@ struct sppm_ctx {
   sppm::DevBuf occ_nbr;       // int2[n_occ][9]: the neighbourhood as 9 x-runs of compact slots
   // deposits
   sppm::DevBuf dep_raw, dep_sorted, dep_key, dep_key2, dep_idx, dep_idx2, dep_start, cub_tmp;
+  sppm::DevBuf dep_rank;      // u32 per raw deposit: arrival rank within its slot (counting sort)
+  sppm::DevBuf slot_count;    // u32[n_slots + 2]: deposits per slot of the current batch
   int64_t dep_cap = 0, n_dep = 0, n_dep_kept = 0;
   sppm::DevBuf dev_scalars;   // [0] hp count, [1] deposit count, [2] photon cursor ...
   sppm::DevBuf counters;      // DevCounters
@@ -107,7 +109,11 @@ struct sppm_ctx {
   int64_t wf_cap = 0;
   bool keep_all_deposits = false;
   SppmCounters host_counters{};
-  cudaEvent_t ev[8] = {};  // 0 trace start, 1 sort start, 2 gather start, 3 gather end, 4/5 generic
+  cudaEvent_t ev[8] = {};  // 4/5 generic, 6/7 user stopwatch
+  static constexpr int TIMING_RING = 32;
+  cudaEvent_t tev[TIMING_RING][4] = {};  // per batch: trace start, bin start, gather start, gather end
+  int t_pending = 0;          // batches whose timings are not folded into host_counters yet
+  bool t_has_gather[TIMING_RING] = {};
   // NCCL (dlopen)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
@@ -128,7 +134,7 @@ cudaError_t wavefront_overflowed(sppm_ctx* c, bool* overflow);
 // gather.cu
 cudaError_t build_index(sppm_ctx* c);
 cudaError_t key_host_deposits(sppm_ctx* c, int64_t m);
-cudaError_t sort_and_gather(sppm_ctx* c, int64_t m);
+cudaError_t bin_and_gather(sppm_ctx* c, cudaEvent_t ev_gather_start, cudaEvent_t ev_gather_end);
 cudaError_t launch_update(sppm_ctx* c);
 cudaError_t launch_resolve(sppm_ctx* c, int cnt, int onetime);
 cudaError_t dev_reserve(DevBuf& b, size_t bytes);

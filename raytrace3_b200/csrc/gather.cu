@@ -4,8 +4,9 @@
 // RayTracer::PhotonTrace (Raytracer.h:92-96, 139-159, 370-380) by
 //   build_index:     cell key per hit point -> CUB radix sort -> SoA permute -> occupied-cell
 //                    list, neighbourhood slot table (once per eye pass)
-//   sort_and_gather: deposits of one photon batch binned by cell with a CUB radix sort,
-//                    then a hit-point-centric gather: each hit point scans the deposits of
+//   bin_and_gather:  deposits of one photon batch binned by cell with a counting sort (slot
+//                    counts + ranks taken at append time, one scan, one scatter), then a
+//                    hit-point-centric gather: each hit point scans the deposits of
 //                    its 27 neighbour cells and accumulates newN / tao in registers — no
 //                    atomics, each accumulator is written once per batch.
 // and HitPoint::update / the film resolve (Raytracer.h:69-79, 281-293).
@@ -138,33 +139,31 @@ __global__ void occ_run_kernel(const uint32_t* occ_cell, int n_occ, Grid g, cons
 __global__ void set_last_kernel(int32_t* starts, int n_occ, int32_t n_hp) { starts[n_occ] = n_hp; }
 
 // ---- deposits --------------------------------------------------------------------------
-__global__ void iota_kernel(uint32_t* idx, long long n) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) idx[i] = (uint32_t)i;
-}
 __global__ void dep_key_kernel(const Deposit* dep, long long m, Grid g, const int32_t* cell_slot, int32_t n_slots,
-                               uint32_t* key) {
+                               uint32_t* key, uint32_t* rank, unsigned int* slot_count) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int32_t s = cell_slot[grid_cell(g, dep[i].x[0], dep[i].x[1], dep[i].x[2])];
-  key[i] = s >= 0 ? (uint32_t)s : (uint32_t)n_slots;
+  const uint32_t k = s >= 0 ? (uint32_t)s : (uint32_t)n_slots;
+  key[i] = k;
+  rank[i] = atomicAdd(slot_count + k, 1u);
 }
-// sorted[i] = raw[idx[i]] (i < m) and the CSR offsets of the slots: off[s] = first sorted
-// deposit whose key is >= s, for s = 0..n_slots (keys == n_slots mark dropped deposits, so
-// off[n_slots] = number of kept deposits).  Launched with m + 1 threads.
-__global__ void dep_permute_kernel(const Deposit* raw, const uint32_t* key, const uint32_t* idx, long long m,
-                                   int32_t n_slots, Deposit* sorted, int32_t* off) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > m) return;
-  if (i < m) {
-    const double2* src = reinterpret_cast<const double2*>(raw + idx[i]);
-    double2* dst = reinterpret_cast<double2*>(sorted + i);
-#pragma unroll
-    for (int k = 0; k < 5; k++) dst[k] = src[k];
+// Counting sort, last step: off[] = exclusive scan of the per-slot counts (the CSR offsets the
+// gather reads; off[n_slots] = number of kept deposits), every deposit knows its slot and its
+// arrival rank within the slot, so sorted[off[key] + rank] = raw.  The deposit count stays on
+// the device (no host round trip between tracing and gathering).
+__global__ void __launch_bounds__(320) dep_scatter_kernel(const Deposit* raw, const uint32_t* key, const uint32_t* rank,
+                                                          const unsigned long long* m_ptr, unsigned long long cap,
+                                                          const int32_t* off, Deposit* sorted) {
+  // five threads move one 80-byte record (16 B each), so every record is read and written as
+  // one contiguous 80-byte piece of a warp-wide request; blockDim = 320 = 64 records per CTA pass
+  const unsigned long long m = min(*m_ptr, cap);
+  const unsigned part = threadIdx.x % 5;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * 64 + threadIdx.x / 5; i < m; i += (unsigned long long)gridDim.x * 64) {
+    const double2* src = reinterpret_cast<const double2*>(raw + i);
+    double2* dst = reinterpret_cast<double2*>(sorted + (off[key[i]] + (int32_t)rank[i]));
+    dst[part] = src[part];
   }
-  const long long prev = i == 0 ? -1 : (long long)min(key[i - 1], (uint32_t)n_slots);
-  const long long cur = i == m ? (long long)n_slots : (long long)min(key[i], (uint32_t)n_slots);
-  for (long long sl = prev + 1; sl <= cur; sl++) off[sl] = (int32_t)i;
 }
 
 struct GatherArgs {
@@ -471,6 +470,7 @@ cudaError_t build_index(sppm_ctx* c) {
     CK(dev_reserve(c->occ_cell, 4));
     CK(dev_reserve(c->occ_nbr, 9 * 8));
     CK(dev_reserve(c->dep_start, 16));
+    CK(dev_reserve(c->slot_count, 16));
     c->index_ok = true;
     return cudaSuccess;
   }
@@ -590,7 +590,8 @@ cudaError_t build_index(sppm_ctx* c) {
   CK(dev_reserve(c->occ_nbr, (size_t)n_occ * 9 * 8));
   occ_run_kernel<<<nblk((long long)n_occ * 9), TPB, 0, st>>>((uint32_t*)c->occ_cell.p, n_occ, g, (int32_t*)c->cell_slot.p,
                                                              (int2*)c->occ_nbr.p);
-  CK(dev_reserve(c->dep_start, ((size_t)n_slots + 2) * 4));
+  CK(dev_reserve(c->dep_start, ((size_t)n_slots + 4) * 4));
+  CK(dev_reserve(c->slot_count, ((size_t)n_slots + 4) * 4));
   c->host_counters.launches += 4;
   CK(cudaGetLastError());
   c->host_counters.hit_points = (uint64_t)n;
@@ -602,34 +603,30 @@ cudaError_t build_index(sppm_ctx* c) {
 cudaError_t key_host_deposits(sppm_ctx* c, int64_t m) {
   if (m <= 0) return cudaSuccess;
   dep_key_kernel<<<nblk(m), TPB, 0, c->stream>>>((const Deposit*)c->dep_raw.p, m, c->grid, (const int32_t*)c->cell_slot.p,
-                                                 c->n_slots, (uint32_t*)c->dep_key.p);
+                                                 c->n_slots, (uint32_t*)c->dep_key.p, (uint32_t*)c->dep_rank.p,
+                                                 (unsigned int*)c->slot_count.p);
   c->host_counters.launches++;
   return cudaGetLastError();
 }
 
-// Bin the m raw deposits (keys already in dep_key; key == n_slots marks "near no hit point")
-// and run the gather into the per-round accumulators dN / dtao.
-cudaError_t sort_and_gather(sppm_ctx* c, int64_t m) {
+// Bin the raw deposits of the current batch by slot (counting sort: per-slot counts and ranks
+// were taken when the deposits were appended) and run the gather into the per-round accumulators
+// dN / dtao.  Everything is stream-ordered; the deposit count is read on the device.
+cudaError_t bin_and_gather(sppm_ctx* c, cudaEvent_t ev_gather_start, cudaEvent_t ev_gather_end) {
   cudaStream_t st = c->stream;
-  c->n_dep = m;
-  c->n_dep_kept = 0;
-  if (m <= 0 || c->n_hp == 0) return cudaSuccess;
-  CK(dev_reserve(c->dep_key2, (size_t)m * 4));
-  CK(dev_reserve(c->dep_idx, (size_t)m * 4));
-  CK(dev_reserve(c->dep_idx2, (size_t)m * 4));
-  CK(dev_reserve(c->dep_sorted, (size_t)m * sizeof(Deposit)));
-  uint32_t *k1 = (uint32_t*)c->dep_key.p, *k2 = (uint32_t*)c->dep_key2.p, *i1 = (uint32_t*)c->dep_idx.p,
-           *i2 = (uint32_t*)c->dep_idx2.p;
-  CK(cudaEventRecord(c->ev[1], st));
-  iota_kernel<<<nblk(m), TPB, 0, st>>>(i1, m);
+  if (c->n_hp == 0 || c->dep_cap <= 0) return cudaSuccess;
+  CK(dev_reserve(c->dep_sorted, (size_t)c->dep_cap * sizeof(Deposit)));
   size_t tmp = 0;
-  const int end_bit = bits_for((uint64_t)c->n_slots);
-  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k1, k2, i1, i2, (int)m, 0, end_bit, st));
+  const int n_scan = c->n_slots + 2;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int32_t*)c->slot_count.p, (int32_t*)c->dep_start.p, n_scan, st));
   CK(dev_reserve(c->cub_tmp, tmp));
-  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k1, k2, i1, i2, (int)m, 0, end_bit, st));
-  dep_permute_kernel<<<nblk(m + 1), TPB, 0, st>>>((const Deposit*)c->dep_raw.p, k2, i2, m, c->n_slots, (Deposit*)c->dep_sorted.p,
-                                                   (int32_t*)c->dep_start.p);
-  CK(cudaEventRecord(c->ev[2], st));
+  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, (const int32_t*)c->slot_count.p, (int32_t*)c->dep_start.p, n_scan, st));
+  dep_scatter_kernel<<<(unsigned)c->sm_count * 6, 320, 0, st>>>((const Deposit*)c->dep_raw.p, (const uint32_t*)c->dep_key.p,
+                                                                (const uint32_t*)c->dep_rank.p,
+                                                                (const unsigned long long*)c->dev_scalars.p + 1,
+                                                                (unsigned long long)c->dep_cap, (const int32_t*)c->dep_start.p,
+                                                                (Deposit*)c->dep_sorted.p);
+  if (ev_gather_start) CK(cudaEventRecord(ev_gather_start, st));
   GatherArgs a;
   a.s = c->soa;
   a.n_hp = c->n_hp;
@@ -642,16 +639,14 @@ cudaError_t sort_and_gather(sppm_ctx* c, int64_t m) {
   a.counters = (DevCounters*)c->counters.p;
   unsigned int* work_counter = (unsigned int*)((unsigned long long*)c->dev_scalars.p + 4);
   CK(cudaMemsetAsync(work_counter, 0, 4, st));
-  unsigned blocks = (unsigned)c->sm_count * 4;  // persistent CTAs, cells handed out dynamically
-  if (blocks > (unsigned)c->n_occ) blocks = (unsigned)c->n_occ;
   const size_t tile_bytes = 2 * (size_t)G_TILE * sizeof(Deposit);
   CK(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));  // per device
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel, G_THREADS, tile_bytes));
-  blocks = (unsigned)c->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm);
+  unsigned blocks = (unsigned)c->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm);  // persistent CTAs, cells handed out dynamically
   if (blocks > (unsigned)c->n_occ) blocks = (unsigned)c->n_occ;
-  gather_kernel<<<blocks, G_THREADS, tile_bytes, st>>>(a, work_counter);
-  CK(cudaEventRecord(c->ev[3], st));
+  if (blocks) gather_kernel<<<blocks, G_THREADS, tile_bytes, st>>>(a, work_counter);
+  if (ev_gather_end) CK(cudaEventRecord(ev_gather_end, st));
   c->host_counters.launches += 4;
   return cudaGetLastError();
 }

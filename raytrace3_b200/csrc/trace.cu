@@ -155,6 +155,8 @@ struct PhotonArgs {
   int keep_all;
   Deposit* dep;
   uint32_t* dep_key;
+  uint32_t* dep_rank;
+  unsigned int* slot_count;
   unsigned long long dep_cap;
   unsigned long long* dep_count;
   unsigned long long* cursor;
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_TRACE_MINBLOCKS) photon_tr
         if (slot < a.dep_cap) {
           a.dep[slot] = rec;
           a.dep_key[slot] = key;
+          a.dep_rank[slot] = atomicAdd(a.slot_count + key, 1u);  // counting sort: rank within the slot
           kept++;
         }
       }
@@ -411,6 +414,8 @@ cudaError_t launch_photon_trace(sppm_ctx* c, uint64_t begin, uint64_t count, uin
   a.keep_all = c->keep_all_deposits ? 1 : 0;
   a.dep = (Deposit*)c->dep_raw.p;
   a.dep_key = (uint32_t*)c->dep_key.p;
+  a.dep_rank = (uint32_t*)c->dep_rank.p;
+  a.slot_count = (unsigned int*)c->slot_count.p;
   a.dep_cap = (unsigned long long)c->dep_cap;
   a.dep_count = (unsigned long long*)c->dev_scalars.p + 1;
   a.cursor = (unsigned long long*)c->dev_scalars.p + 2;

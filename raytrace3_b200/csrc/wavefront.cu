@@ -66,6 +66,8 @@ struct StepArgs {
   int keep_all;
   Deposit* dep;
   uint32_t* dep_key;
+  uint32_t* dep_rank;
+  unsigned int* slot_count;
   unsigned long long dep_cap;
   unsigned long long* dep_count;
 };
@@ -168,7 +170,9 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
                 rec.flux[0] = flux.x; rec.flux[1] = flux.y; rec.flux[2] = flux.z;
                 rec.meta = id | ((uint64_t)node << 56);
                 a.dep[ds] = rec;
-                a.dep_key[ds] = slot >= 0 ? (uint32_t)slot : (uint32_t)a.n_slots;
+                const uint32_t key = slot >= 0 ? (uint32_t)slot : (uint32_t)a.n_slots;
+                a.dep_key[ds] = key;
+                a.dep_rank[ds] = atomicAdd(a.slot_count + key, 1u);  // counting sort: rank within the slot
                 kept++;
               }
             }
@@ -442,6 +446,8 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, uint64_t begin, uint64_t 
     a.keep_all = c->keep_all_deposits ? 1 : 0;
     a.dep = (Deposit*)c->dep_raw.p;
     a.dep_key = (uint32_t*)c->dep_key.p;
+    a.dep_rank = (uint32_t*)c->dep_rank.p;
+    a.slot_count = (unsigned int*)c->slot_count.p;
     a.dep_cap = (unsigned long long)c->dep_cap;
     a.dep_count = (unsigned long long*)c->dev_scalars.p + 1;
     int blocks = step_blocks;
