@@ -67,17 +67,22 @@ void fold_timings(sppm_ctx* c) {
 
 // Device-side overflow flags (deposit list, Bezier work-item list) are checked at sync points.
 int check_overflow(sppm_ctx* c) {
-  unsigned long long m = 0;
-  if (cudaMemcpyAsync(&m, (unsigned long long*)c->dev_scalars.p + 1, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-      cudaStreamSynchronize(c->stream) != cudaSuccess)
-    return cuda_fail(c, cudaGetLastError(), "check_overflow");
-  c->n_dep = (int64_t)std::min<unsigned long long>(m, (unsigned long long)std::max<int64_t>(c->dep_cap, 0));
-  if (c->dep_cap > 0 && (int64_t)m > c->dep_cap) return fail(c, SPPM_ERR_CAPACITY, "deposit buffer overflow");
-  if (c->prm.trace_mode != SPPM_TRACE_PERSISTENT) {
-    bool ovf = false;
-    cudaError_t e = wavefront_overflowed(c, &ovf);
-    if (e) return cuda_fail(c, e, "wavefront_overflowed");
-    if (ovf) return fail(c, SPPM_ERR_CAPACITY, "Bezier work-item list overflow (more than 2 (ray, patch) items per photon in one bounce)");
+  for (int j = 0; j < 2; j++) {
+    Lane& L = c->lanes[j];
+    if (!L.scalars.p || L.dep_cap <= 0) continue;
+    unsigned long long m = 0;
+    if (cudaStreamSynchronize(L.stream) != cudaSuccess ||
+        cudaMemcpyAsync(&m, (unsigned long long*)L.scalars.p + 1, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess)
+      return cuda_fail(c, cudaGetLastError(), "check_overflow");
+    if (j == c->last_lane) c->n_dep = (int64_t)std::min<unsigned long long>(m, (unsigned long long)L.dep_cap);
+    if ((int64_t)m > L.dep_cap) return fail(c, SPPM_ERR_CAPACITY, "deposit buffer overflow");
+    if (c->prm.trace_mode != SPPM_TRACE_PERSISTENT) {
+      bool ovf = false;
+      cudaError_t e = wavefront_overflowed(c, L, &ovf);
+      if (e) return cuda_fail(c, e, "wavefront_overflowed");
+      if (ovf) return fail(c, SPPM_ERR_CAPACITY, "Bezier work-item list overflow (more than 2 (ray, patch) items per photon in one bounce)");
+    }
   }
   return SPPM_OK;
 }
@@ -171,14 +176,19 @@ cudaError_t upload(sppm_ctx* c, size_t slot, const T* host, size_t count, const 
   return e;
 }
 
-int ensure_deposit_capacity(sppm_ctx* c, int64_t cap) {
-  if (cap <= c->dep_cap) return SPPM_OK;
-  CU(c, dev_reserve(c->dep_raw, (size_t)cap * sizeof(Deposit)));
-  CU(c, dev_reserve(c->dep_key, (size_t)cap * 4));
-  CU(c, dev_reserve(c->dep_rank, (size_t)cap * 4));
-  c->dep_cap = cap;
+int ensure_deposit_capacity(sppm_ctx* c, Lane& L, int64_t cap) {
+  const size_t slots = ((size_t)(c->index_ok ? c->n_slots : 0) + 4) * 4;
+  CU(c, dev_reserve(L.slot_count, slots));
+  CU(c, dev_reserve(L.dep_start, slots));
+  if (cap <= L.dep_cap) return SPPM_OK;
+  CU(c, dev_reserve(L.dep_raw, (size_t)cap * sizeof(Deposit)));
+  CU(c, dev_reserve(L.dep_key, (size_t)cap * 4));
+  CU(c, dev_reserve(L.dep_rank, (size_t)cap * 4));
+  L.dep_cap = cap;
   return SPPM_OK;
 }
+// every later trace must see the scene / hit-point map that the main stream just produced
+cudaError_t mark_setup(sppm_ctx* c) { return cudaEventRecord(c->ev_setup, c->stream); }
 
 // canonical export order = ascending okey
 std::vector<int64_t> canonical_order(const std::vector<uint64_t>& okey) {
@@ -238,9 +248,18 @@ int sppm_ctx_create(int device, sppm_ctx** out) {
   for (int i = 0; i < sppm_ctx::TIMING_RING && ok; i++)
     for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&c->tev[i][k]) == cudaSuccess;
   ok = ok && dev_reserve(c->dev_scalars, 64) == cudaSuccess && dev_reserve(c->counters, sizeof(DevCounters)) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->ev_setup, cudaEventDisableTiming) == cudaSuccess;
+  for (int j = 0; j < 2 && ok; j++) {
+    Lane& L = c->lanes[j];
+    ok = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&L.ev_trace_done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&L.ev_gather_done, cudaEventDisableTiming) == cudaSuccess &&
+         dev_reserve(L.scalars, 64) == cudaSuccess && cudaMemset(L.scalars.p, 0, 64) == cudaSuccess;
+  }
   if (ok) {
     cudaMemset(c->dev_scalars.p, 0, 64);
     cudaMemset(c->counters.p, 0, sizeof(DevCounters));
+    ok = cudaEventRecord(c->ev_setup, c->stream) == cudaSuccess;
   }
   if (!ok) {
     e = cudaGetLastError();
@@ -254,12 +273,22 @@ int sppm_ctx_create(int device, sppm_ctx** out) {
 void sppm_ctx_destroy(sppm_ctx* c) {
   if (!c) return;
   Bind b(c);
+  for (int j = 0; j < 2; j++)
+    if (c->lanes[j].stream) cudaStreamSynchronize(c->lanes[j].stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->nccl_comm && nccl().ok) nccl().CommDestroy((ncclComm_t)c->nccl_comm);
+  for (int j = 0; j < 2; j++) {
+    Lane& L = c->lanes[j];
+    DevBuf* lb[] = {&L.dep_raw, &L.dep_sorted, &L.dep_key, &L.dep_rank, &L.slot_count, &L.dep_start, &L.wf_store, &L.scalars, &L.cub_tmp};
+    for (DevBuf* d : lb) dev_free(*d);
+    if (L.ev_trace_done) cudaEventDestroy(L.ev_trace_done);
+    if (L.ev_gather_done) cudaEventDestroy(L.ev_gather_done);
+    if (L.stream) cudaStreamDestroy(L.stream);
+  }
+  if (c->ev_setup) cudaEventDestroy(c->ev_setup);
   free_scene(c);
-  DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->dep_raw,
-                    &c->dep_sorted, &c->dep_key, &c->dep_key2, &c->dep_idx, &c->dep_idx2, &c->dep_start, &c->cub_tmp, &c->dep_rank, &c->slot_count,
-                    &c->dev_scalars, &c->counters, &c->film, &c->scratch, &c->wf_store};
+  DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->dep_key, &c->dep_key2,
+                    &c->dep_idx, &c->dep_idx2, &c->scan_scratch, &c->cub_tmp, &c->dev_scalars, &c->counters, &c->film, &c->scratch};
   for (DevBuf* d : bufs) dev_free(*d);
   for (int i = 0; i < 8; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -383,6 +412,7 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
   c->scene = ds;
   CU(c, trace_configure(c));
   c->scene_ok = true;
+  CU(c, mark_setup(c));
   return SPPM_OK;
 }
 
@@ -423,6 +453,7 @@ int sppm_build_index(sppm_ctx* c) {
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
   c->host_counters.ms_build = ms;
+  CU(c, mark_setup(c));
   return SPPM_OK;
 }
 
@@ -433,23 +464,41 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
   if (c->scene.n_light <= 0 || photon_count == 0) return SPPM_OK;
   if (photon_begin + photon_count > (1ull << 40)) return fail(c, SPPM_ERR_INVALID, "photon index exceeds 2^40");
   Bind b(c);
-  const uint64_t per_light_batch = std::max<uint64_t>(1, PHOTON_BATCH / (uint64_t)c->scene.n_light);
+  // Batches of up to PHOTON_BATCH photons alternate between two lanes (own stream + buffers):
+  // lane stream = trace + deposit binning, main stream = gather.  The gather of one batch
+  // overlaps the trace of the next — across rounds too, since nothing here waits for the host.
+  // (A round is not split further: halving a batch doubles the per-cell and per-launch overheads.)
   const bool gather = c->index_ok && c->n_hp > 0;
-  if (!c->slot_count.p) CU(c, dev_reserve(c->slot_count, 16));
+  const uint64_t n_light = (uint64_t)c->scene.n_light;
+  uint64_t per_light_batch = std::max<uint64_t>(1, PHOTON_BATCH / n_light);
+  const bool split = !c->keep_all_deposits;
+  if (photon_count > per_light_batch) {  // equal batches
+    const uint64_t nb = (photon_count + per_light_batch - 1) / per_light_batch;
+    per_light_batch = (photon_count + nb - 1) / nb;
+  }
   for (uint64_t off = 0; off < photon_count; off += per_light_batch) {
     const uint64_t cnt = std::min(per_light_batch, photon_count - off);
-    const int64_t cap = (int64_t)(cnt * c->scene.n_light) * (c->prm.max_dep + 1);
-    int rc = ensure_deposit_capacity(c, cap);
+    const int j = split ? (c->lane_rr++ & 1) : 0;
+    Lane& L = c->lanes[j];
+    c->last_lane = j;
+    const int64_t cap = (int64_t)(cnt * n_light) * (c->prm.max_dep + 1);
+    int rc = ensure_deposit_capacity(c, L, cap);
     if (rc) return rc;
     if (c->t_pending == sppm_ctx::TIMING_RING) fold_timings(c);
     cudaEvent_t* te = c->tev[c->t_pending];
-    CU(c, cudaMemsetAsync(scalars(c) + 1, 0, 16, c->stream));  // deposit count, photon cursor
-    CU(c, cudaMemsetAsync(c->slot_count.p, 0, ((size_t)(c->index_ok ? c->n_slots : 0) + 2) * 4, c->stream));
-    CU(c, cudaEventRecord(te[0], c->stream));
-    if (c->prm.trace_mode == SPPM_TRACE_PERSISTENT) CU(c, launch_photon_trace(c, photon_begin + off, cnt, pass_id));
-    else CU(c, launch_photon_trace_wavefront(c, photon_begin + off, cnt, pass_id));
-    CU(c, cudaEventRecord(te[1], c->stream));
-    if (gather) CU(c, bin_and_gather(c, te[2], te[3]));
+    CU(c, cudaStreamWaitEvent(L.stream, c->ev_setup, 0));        // scene + hit-point map are ready
+    CU(c, cudaStreamWaitEvent(L.stream, L.ev_gather_done, 0));   // the lane's previous deposits were consumed
+    CU(c, cudaMemsetAsync((unsigned long long*)L.scalars.p + 1, 0, 16, L.stream));  // deposit count, photon cursor
+    CU(c, cudaMemsetAsync(L.slot_count.p, 0, ((size_t)(c->index_ok ? c->n_slots : 0) + 2) * 4, L.stream));
+    CU(c, cudaEventRecord(te[0], L.stream));
+    if (c->prm.trace_mode == SPPM_TRACE_PERSISTENT) CU(c, launch_photon_trace(c, L, photon_begin + off, cnt, pass_id));
+    else CU(c, launch_photon_trace_wavefront(c, L, photon_begin + off, cnt, pass_id));
+    if (gather) CU(c, bin_deposits(c, L, L.stream));
+    CU(c, cudaEventRecord(te[1], L.stream));
+    CU(c, cudaEventRecord(L.ev_trace_done, L.stream));
+    CU(c, cudaStreamWaitEvent(c->stream, L.ev_trace_done, 0));
+    if (gather) CU(c, launch_gather(c, L, te[2], te[3]));
+    CU(c, cudaEventRecord(L.ev_gather_done, c->stream));
     c->t_has_gather[c->t_pending] = gather;
     c->t_pending++;
   }
@@ -748,7 +797,10 @@ int sppm_gather_deposits(sppm_ctx* c, int64_t m, const double* x3, const double*
   if (m == 0) return SPPM_OK;
   if (!x3 || !n3 || !flux3) return SPPM_ERR_INVALID;
   Bind b(c);
-  int rc = ensure_deposit_capacity(c, m);
+  Lane& L = c->lanes[0];
+  c->last_lane = 0;
+  CU(c, cudaStreamSynchronize(L.stream));
+  int rc = ensure_deposit_capacity(c, L, m);
   if (rc) return rc;
   std::vector<Deposit> d((size_t)m);
   for (int64_t i = 0; i < m; i++) {
@@ -759,17 +811,19 @@ int sppm_gather_deposits(sppm_ctx* c, int64_t m, const double* x3, const double*
     }
     d[i].meta = (uint64_t)i;
   }
-  CU(c, cudaMemcpyAsync(c->dep_raw.p, d.data(), (size_t)m * sizeof(Deposit), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(L.dep_raw.p, d.data(), (size_t)m * sizeof(Deposit), cudaMemcpyHostToDevice, c->stream));
   const unsigned long long m64 = (unsigned long long)m;
-  CU(c, cudaMemcpyAsync(scalars(c) + 1, &m64, 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync((unsigned long long*)L.scalars.p + 1, &m64, 8, cudaMemcpyHostToDevice, c->stream));
   if (c->n_hp > 0) {
     if (c->t_pending == sppm_ctx::TIMING_RING) fold_timings(c);
     cudaEvent_t* te = c->tev[c->t_pending];
-    CU(c, cudaMemsetAsync(c->slot_count.p, 0, ((size_t)c->n_slots + 2) * 4, c->stream));
+    CU(c, cudaMemsetAsync(L.slot_count.p, 0, ((size_t)c->n_slots + 2) * 4, c->stream));
     CU(c, cudaEventRecord(te[0], c->stream));
+    CU(c, key_host_deposits(c, L, m, c->stream));
+    CU(c, bin_deposits(c, L, c->stream));
     CU(c, cudaEventRecord(te[1], c->stream));
-    CU(c, key_host_deposits(c, m));
-    CU(c, bin_and_gather(c, te[2], te[3]));
+    CU(c, launch_gather(c, L, te[2], te[3]));
+    CU(c, cudaEventRecord(L.ev_gather_done, c->stream));
     c->t_has_gather[c->t_pending] = true;
     c->t_pending++;
   }
@@ -820,7 +874,7 @@ int sppm_export_deposits(sppm_ctx* c, int64_t cap, double* x3, double* n3, doubl
   if (m_out) *m_out = m;
   if (m == 0) return SPPM_OK;
   std::vector<Deposit> d((size_t)m);
-  CU(c, cudaMemcpyAsync(d.data(), c->dep_raw.p, (size_t)m * sizeof(Deposit), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(d.data(), c->lanes[c->last_lane].dep_raw.p, (size_t)m * sizeof(Deposit), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   // canonical order: (photon id, bounce)
   std::vector<int64_t> ord((size_t)m);

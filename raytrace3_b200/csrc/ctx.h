@@ -68,6 +68,20 @@ struct DevBuf {  // growable device allocation
   size_t bytes = 0;
 };
 
+// A photon "lane": its own stream and buffers for tracing one sub-batch of photons and
+// binning its deposits.  A round's photons are split over two lanes so that the trace of
+// one sub-batch overlaps the gather (main stream) of the other.
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_trace_done = nullptr, ev_gather_done = nullptr;
+  DevBuf dep_raw, dep_sorted, dep_key, dep_rank;  // deposits: arrival order / cell order, slot key, rank in slot
+  DevBuf slot_count, dep_start;                   // u32[n_slots+2] counts and their exclusive scan (CSR offsets)
+  DevBuf wf_store;                                // wavefront photon queues + item lists
+  DevBuf scalars;                                 // u64[8]: [1] deposit count, [2] photon cursor
+  DevBuf cub_tmp;
+  int64_t dep_cap = 0, wf_cap = 0;
+};
+
 }  // namespace sppm
 
 struct sppm_ctx {
@@ -97,16 +111,15 @@ struct sppm_ctx {
   int32_t n_occ = 0;
   sppm::DevBuf occ_nbr;       // int2[n_occ][9]: the neighbourhood as 9 x-runs of compact slots
   // deposits
-  sppm::DevBuf dep_raw, dep_sorted, dep_key, dep_key2, dep_idx, dep_idx2, dep_start, cub_tmp;
-  sppm::DevBuf dep_rank;      // u32 per raw deposit: arrival rank within its slot (counting sort)
-  sppm::DevBuf slot_count;    // u32[n_slots + 2]: deposits per slot of the current batch
-  int64_t dep_cap = 0, n_dep = 0, n_dep_kept = 0;
+  sppm::Lane lanes[2];
+  int lane_rr = 0, last_lane = 0;
+  cudaEvent_t ev_setup = nullptr;  // recorded on the main stream after scene / hit-point map changes
+  sppm::DevBuf dep_key, dep_key2, dep_idx, dep_idx2, scan_scratch, cub_tmp;  // build_index scratch
+  int64_t n_dep = 0;
   sppm::DevBuf dev_scalars;   // [0] hp count, [1] deposit count, [2] photon cursor ...
   sppm::DevBuf counters;      // DevCounters
   sppm::DevBuf film;          // double[h][w][3]
   sppm::DevBuf scratch;
-  sppm::DevBuf wf_store;      // wavefront photon queues + item lists
-  int64_t wf_cap = 0;
   bool keep_all_deposits = false;
   SppmCounters host_counters{};
   cudaEvent_t ev[8] = {};  // 4/5 generic, 6/7 user stopwatch
@@ -122,19 +135,20 @@ struct sppm_ctx {
 namespace sppm {
 // trace.cu
 cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pass_id);
-cudaError_t launch_photon_trace(sppm_ctx* c, uint64_t begin, uint64_t count, uint64_t pass_id);
+cudaError_t launch_photon_trace(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t count, uint64_t pass_id);
 cudaError_t launch_intersect(sppm_ctx* c, const double* d_rays6, int64_t n, const uint64_t* d_ids, uint64_t pass_id,
                              int node, SppmHit* d_out);
 cudaError_t launch_patch_batch(sppm_ctx* c, const double* d_rays6, const int32_t* d_patch, int64_t n,
                                const double* d_seeds, double* d_tuv);
 cudaError_t trace_configure(sppm_ctx* c);
 // wavefront.cu
-cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, uint64_t begin, uint64_t count, uint64_t pass_id);
-cudaError_t wavefront_overflowed(sppm_ctx* c, bool* overflow);
+cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t count, uint64_t pass_id);
+cudaError_t wavefront_overflowed(sppm_ctx* c, Lane& L, bool* overflow);
 // gather.cu
 cudaError_t build_index(sppm_ctx* c);
-cudaError_t key_host_deposits(sppm_ctx* c, int64_t m);
-cudaError_t bin_and_gather(sppm_ctx* c, cudaEvent_t ev_gather_start, cudaEvent_t ev_gather_end);
+cudaError_t key_host_deposits(sppm_ctx* c, Lane& L, int64_t m, cudaStream_t st);
+cudaError_t bin_deposits(sppm_ctx* c, Lane& L, cudaStream_t st);
+cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cudaEvent_t ev_gather_end);
 cudaError_t launch_update(sppm_ctx* c);
 cudaError_t launch_resolve(sppm_ctx* c, int cnt, int onetime);
 cudaError_t dev_reserve(DevBuf& b, size_t bytes);

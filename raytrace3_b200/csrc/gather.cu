@@ -15,6 +15,9 @@
 // operation order and no FMA (the library is built with -fmad=false), so newN is exact.
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "ctx.h"
 
 namespace sppm {
@@ -469,8 +472,6 @@ cudaError_t build_index(sppm_ctx* c) {
     CK(dev_reserve(c->occ_start, 8));
     CK(dev_reserve(c->occ_cell, 4));
     CK(dev_reserve(c->occ_nbr, 9 * 8));
-    CK(dev_reserve(c->dep_start, 16));
-    CK(dev_reserve(c->slot_count, 16));
     c->index_ok = true;
     return cudaSuccess;
   }
@@ -576,13 +577,13 @@ cudaError_t build_index(sppm_ctx* c) {
   c->host_counters.launches += 4;
   // 5. cells whose 27-neighbourhood holds a hit point get a compact slot (others: -1)
   CK(dev_reserve(c->cell_slot, (size_t)g.n_cells * 4));
-  CK(dev_reserve(c->dep_sorted, (size_t)g.n_cells * 4));  // scan scratch (deposit buffer is idle here)
+  CK(dev_reserve(c->scan_scratch, (size_t)g.n_cells * 4));
   CK(cudaMemsetAsync(c->cell_slot.p, 0, (size_t)g.n_cells * 4, st));
   mark_nbr_kernel<<<nblk((long long)n_occ * 27), TPB, 0, st>>>((uint32_t*)c->occ_cell.p, n_occ, g, (int32_t*)c->cell_slot.p);
-  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (int32_t*)c->cell_slot.p, (int32_t*)c->dep_sorted.p, (int)g.n_cells, st));
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (int32_t*)c->cell_slot.p, (int32_t*)c->scan_scratch.p, (int)g.n_cells, st));
   CK(dev_reserve(c->cub_tmp, tmp));
-  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, (int32_t*)c->cell_slot.p, (int32_t*)c->dep_sorted.p, (int)g.n_cells, st));
-  finalize_slot_kernel<<<nblk(g.n_cells), TPB, 0, st>>>((int32_t*)c->cell_slot.p, (int32_t*)c->dep_sorted.p, g.n_cells, d_nruns);
+  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, (int32_t*)c->cell_slot.p, (int32_t*)c->scan_scratch.p, (int)g.n_cells, st));
+  finalize_slot_kernel<<<nblk(g.n_cells), TPB, 0, st>>>((int32_t*)c->cell_slot.p, (int32_t*)c->scan_scratch.p, g.n_cells, d_nruns);
   int32_t n_slots = 0;
   CK(cudaMemcpyAsync(&n_slots, d_nruns, 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
@@ -590,8 +591,6 @@ cudaError_t build_index(sppm_ctx* c) {
   CK(dev_reserve(c->occ_nbr, (size_t)n_occ * 9 * 8));
   occ_run_kernel<<<nblk((long long)n_occ * 9), TPB, 0, st>>>((uint32_t*)c->occ_cell.p, n_occ, g, (int32_t*)c->cell_slot.p,
                                                              (int2*)c->occ_nbr.p);
-  CK(dev_reserve(c->dep_start, ((size_t)n_slots + 4) * 4));
-  CK(dev_reserve(c->slot_count, ((size_t)n_slots + 4) * 4));
   c->host_counters.launches += 4;
   CK(cudaGetLastError());
   c->host_counters.hit_points = (uint64_t)n;
@@ -600,54 +599,62 @@ cudaError_t build_index(sppm_ctx* c) {
   return cudaSuccess;
 }
 
-cudaError_t key_host_deposits(sppm_ctx* c, int64_t m) {
+cudaError_t key_host_deposits(sppm_ctx* c, Lane& L, int64_t m, cudaStream_t st) {
   if (m <= 0) return cudaSuccess;
-  dep_key_kernel<<<nblk(m), TPB, 0, c->stream>>>((const Deposit*)c->dep_raw.p, m, c->grid, (const int32_t*)c->cell_slot.p,
-                                                 c->n_slots, (uint32_t*)c->dep_key.p, (uint32_t*)c->dep_rank.p,
-                                                 (unsigned int*)c->slot_count.p);
+  dep_key_kernel<<<nblk(m), TPB, 0, st>>>((const Deposit*)L.dep_raw.p, m, c->grid, (const int32_t*)c->cell_slot.p, c->n_slots,
+                                          (uint32_t*)L.dep_key.p, (uint32_t*)L.dep_rank.p, (unsigned int*)L.slot_count.p);
   c->host_counters.launches++;
   return cudaGetLastError();
 }
 
-// Bin the raw deposits of the current batch by slot (counting sort: per-slot counts and ranks
-// were taken when the deposits were appended) and run the gather into the per-round accumulators
-// dN / dtao.  Everything is stream-ordered; the deposit count is read on the device.
-cudaError_t bin_and_gather(sppm_ctx* c, cudaEvent_t ev_gather_start, cudaEvent_t ev_gather_end) {
-  cudaStream_t st = c->stream;
-  if (c->n_hp == 0 || c->dep_cap <= 0) return cudaSuccess;
-  CK(dev_reserve(c->dep_sorted, (size_t)c->dep_cap * sizeof(Deposit)));
+// Bin the lane's raw deposits by slot (counting sort: per-slot counts and ranks were taken when
+// the deposits were appended): one scan + one scatter on stream st.  The deposit count is read
+// on the device, nothing here waits for the host.
+cudaError_t bin_deposits(sppm_ctx* c, Lane& L, cudaStream_t st) {
+  if (c->n_hp == 0 || L.dep_cap <= 0) return cudaSuccess;
+  CK(dev_reserve(L.dep_sorted, (size_t)L.dep_cap * sizeof(Deposit)));
   size_t tmp = 0;
   const int n_scan = c->n_slots + 2;
-  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int32_t*)c->slot_count.p, (int32_t*)c->dep_start.p, n_scan, st));
-  CK(dev_reserve(c->cub_tmp, tmp));
-  CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, (const int32_t*)c->slot_count.p, (int32_t*)c->dep_start.p, n_scan, st));
-  dep_scatter_kernel<<<(unsigned)c->sm_count * 6, 320, 0, st>>>((const Deposit*)c->dep_raw.p, (const uint32_t*)c->dep_key.p,
-                                                                (const uint32_t*)c->dep_rank.p,
-                                                                (const unsigned long long*)c->dev_scalars.p + 1,
-                                                                (unsigned long long)c->dep_cap, (const int32_t*)c->dep_start.p,
-                                                                (Deposit*)c->dep_sorted.p);
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int32_t*)L.slot_count.p, (int32_t*)L.dep_start.p, n_scan, st));
+  CK(dev_reserve(L.cub_tmp, tmp));
+  CK(cub::DeviceScan::ExclusiveSum(L.cub_tmp.p, tmp, (const int32_t*)L.slot_count.p, (int32_t*)L.dep_start.p, n_scan, st));
+  dep_scatter_kernel<<<(unsigned)c->sm_count * 6, 320, 0, st>>>((const Deposit*)L.dep_raw.p, (const uint32_t*)L.dep_key.p,
+                                                                (const uint32_t*)L.dep_rank.p,
+                                                                (const unsigned long long*)L.scalars.p + 1,
+                                                                (unsigned long long)L.dep_cap, (const int32_t*)L.dep_start.p,
+                                                                (Deposit*)L.dep_sorted.p);
+  c->host_counters.launches += 2;
+  return cudaGetLastError();
+}
+
+// The gather of the lane's binned deposits into the per-round accumulators dN / dtao (main stream).
+cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cudaEvent_t ev_gather_end) {
+  cudaStream_t st = c->stream;
   if (ev_gather_start) CK(cudaEventRecord(ev_gather_start, st));
-  GatherArgs a;
-  a.s = c->soa;
-  a.n_hp = c->n_hp;
-  a.occ_start = (const int32_t*)c->occ_start.p;
-  a.occ_run = (const int2*)c->occ_nbr.p;
-  a.n_occ = c->n_occ;
-  a.dep_off = (const int32_t*)c->dep_start.p;
-  a.dep = (const Deposit*)c->dep_sorted.p;
-  a.search_r2 = c->prm.init_r2;
-  a.counters = (DevCounters*)c->counters.p;
-  unsigned int* work_counter = (unsigned int*)((unsigned long long*)c->dev_scalars.p + 4);
-  CK(cudaMemsetAsync(work_counter, 0, 4, st));
-  const size_t tile_bytes = 2 * (size_t)G_TILE * sizeof(Deposit);
-  CK(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));  // per device
-  int per_sm = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel, G_THREADS, tile_bytes));
-  unsigned blocks = (unsigned)c->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm);  // persistent CTAs, cells handed out dynamically
-  if (blocks > (unsigned)c->n_occ) blocks = (unsigned)c->n_occ;
-  if (blocks) gather_kernel<<<blocks, G_THREADS, tile_bytes, st>>>(a, work_counter);
+  if (c->n_hp > 0 && L.dep_cap > 0 && c->n_occ > 0) {
+    GatherArgs a;
+    a.s = c->soa;
+    a.n_hp = c->n_hp;
+    a.occ_start = (const int32_t*)c->occ_start.p;
+    a.occ_run = (const int2*)c->occ_nbr.p;
+    a.n_occ = c->n_occ;
+    a.dep_off = (const int32_t*)L.dep_start.p;
+    a.dep = (const Deposit*)L.dep_sorted.p;
+    a.search_r2 = c->prm.init_r2;
+    a.counters = (DevCounters*)c->counters.p;
+    unsigned int* work_counter = (unsigned int*)((unsigned long long*)c->dev_scalars.p + 4);
+    CK(cudaMemsetAsync(work_counter, 0, 4, st));
+    const size_t tile_bytes = 2 * (size_t)G_TILE * sizeof(Deposit);
+    CK(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));  // per device
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel, G_THREADS, tile_bytes));
+    if (const char* e = getenv("SPPM_GATHER_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // tuning knob
+    unsigned blocks = (unsigned)c->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm);  // persistent CTAs, cells handed out dynamically
+    if (blocks > (unsigned)c->n_occ) blocks = (unsigned)c->n_occ;
+    gather_kernel<<<blocks, G_THREADS, tile_bytes, st>>>(a, work_counter);
+    c->host_counters.launches++;
+  }
   if (ev_gather_end) CK(cudaEventRecord(ev_gather_end, st));
-  c->host_counters.launches += 4;
   return cudaGetLastError();
 }
 

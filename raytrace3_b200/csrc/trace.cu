@@ -405,20 +405,20 @@ cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pas
   return cudaGetLastError();
 }
 
-cudaError_t launch_photon_trace(sppm_ctx* c, uint64_t begin, uint64_t count, uint64_t pass_id) {
+cudaError_t launch_photon_trace(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t count, uint64_t pass_id) {
   PhotonArgs a;
   a.c = make_common(c, pass_id);
   a.grid = c->grid;
   a.cell_slot = c->index_ok ? (const int32_t*)c->cell_slot.p : nullptr;
   a.n_slots = c->n_slots;
   a.keep_all = c->keep_all_deposits ? 1 : 0;
-  a.dep = (Deposit*)c->dep_raw.p;
-  a.dep_key = (uint32_t*)c->dep_key.p;
-  a.dep_rank = (uint32_t*)c->dep_rank.p;
-  a.slot_count = (unsigned int*)c->slot_count.p;
-  a.dep_cap = (unsigned long long)c->dep_cap;
-  a.dep_count = (unsigned long long*)c->dev_scalars.p + 1;
-  a.cursor = (unsigned long long*)c->dev_scalars.p + 2;
+  a.dep = (Deposit*)L.dep_raw.p;
+  a.dep_key = (uint32_t*)L.dep_key.p;
+  a.dep_rank = (uint32_t*)L.dep_rank.p;
+  a.slot_count = (unsigned int*)L.slot_count.p;
+  a.dep_cap = (unsigned long long)L.dep_cap;
+  a.dep_count = (unsigned long long*)L.scalars.p + 1;
+  a.cursor = (unsigned long long*)L.scalars.p + 2;
   a.begin = begin;
   a.count = count;
   int per_sm = 1;
@@ -429,7 +429,7 @@ cudaError_t launch_photon_trace(sppm_ctx* c, uint64_t begin, uint64_t count, uin
   unsigned long long want = (total + TRACE_THREADS - 1) / TRACE_THREADS;
   unsigned long long blocks = (unsigned long long)c->sm_count * per_sm;  // persistent: a whole number of waves
   if (want < blocks) blocks = want ? want : 1;
-  photon_trace_kernel<<<(unsigned)blocks, TRACE_THREADS, c->trace_smem, c->stream>>>(a);
+  photon_trace_kernel<<<(unsigned)blocks, TRACE_THREADS, c->trace_smem, L.stream>>>(a);
   c->host_counters.launches++;
   return cudaGetLastError();
 }

@@ -18,6 +18,9 @@
 // Results are identical: the RNG is addressed by (pass, photon id, bounce, ...).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "ctx.h"
 
 #ifndef SPPM_STEP_MINBLOCKS
@@ -396,26 +399,28 @@ cudaError_t wavefront_configure(sppm_ctx* c, int* step_blocks, int* newton_block
   int a = 1, b = 1;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, photon_step_kernel, STEP_THREADS, *step_smem))) return e;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, newton_items_kernel, TRACE_THREADS, *newton_smem))) return e;
+  if (const char* e = getenv("SPPM_STEP_CTAS")) a = std::max(1, std::min(a, atoi(e)));  // tuning knobs
+  if (const char* e = getenv("SPPM_NEWTON_CTAS")) b = std::max(1, std::min(b, atoi(e)));
   *step_blocks = c->sm_count * (a < 1 ? 1 : a);
   *newton_blocks = c->sm_count * (b < 1 ? 1 : b);
   return cudaSuccess;
 }
 
 // One batch of photons [begin, begin+count) per light through all bounces.
-cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, uint64_t begin, uint64_t count, uint64_t pass_id) {
+cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin, uint64_t count, uint64_t pass_id) {
   const int64_t total = (int64_t)c->scene.n_light * (int64_t)count;
   if (total <= 0) return cudaSuccess;
   const int64_t item_cap = std::max<int64_t>(total * 2, 1 << 16);
   cudaError_t e;
-  if (total > c->wf_cap) {
-    if ((e = dev_reserve(c->wf_store, wf_bytes(total, item_cap)))) return e;
-    c->wf_cap = total;
+  if (total > Ln.wf_cap) {
+    if ((e = dev_reserve(Ln.wf_store, wf_bytes(total, item_cap)))) return e;
+    Ln.wf_cap = total;
   }
-  const WfLayout L = wf_layout(c->wf_store.p, c->wf_cap, std::max<int64_t>(c->wf_cap * 2, 1 << 16));
+  const WfLayout L = wf_layout(Ln.wf_store.p, Ln.wf_cap, std::max<int64_t>(Ln.wf_cap * 2, 1 << 16));
   int step_blocks, newton_blocks;
   size_t step_smem, newton_smem;
   if ((e = wavefront_configure(c, &step_blocks, &newton_blocks, &step_smem, &newton_smem))) return e;
-  cudaStream_t st = c->stream;
+  cudaStream_t st = Ln.stream;
   if ((e = cudaMemsetAsync(L.counters, 0, 128 * 4, st))) return e;
   const int n_steps = c->prm.max_dep + 2;  // queries at dep = 0 .. max_dep+1 (Q9)
   for (int b = 0; b < n_steps; b++) {
@@ -444,12 +449,12 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, uint64_t begin, uint64_t 
     a.cell_slot = c->index_ok ? (const int32_t*)c->cell_slot.p : nullptr;
     a.n_slots = c->n_slots;
     a.keep_all = c->keep_all_deposits ? 1 : 0;
-    a.dep = (Deposit*)c->dep_raw.p;
-    a.dep_key = (uint32_t*)c->dep_key.p;
-    a.dep_rank = (uint32_t*)c->dep_rank.p;
-    a.slot_count = (unsigned int*)c->slot_count.p;
-    a.dep_cap = (unsigned long long)c->dep_cap;
-    a.dep_count = (unsigned long long*)c->dev_scalars.p + 1;
+    a.dep = (Deposit*)Ln.dep_raw.p;
+    a.dep_key = (uint32_t*)Ln.dep_key.p;
+    a.dep_rank = (uint32_t*)Ln.dep_rank.p;
+    a.slot_count = (unsigned int*)Ln.slot_count.p;
+    a.dep_cap = (unsigned long long)Ln.dep_cap;
+    a.dep_count = (unsigned long long*)Ln.scalars.p + 1;
     int blocks = step_blocks;
     if (b == 0) {
       const int64_t want = (total + STEP_THREADS - 1) / STEP_THREADS;
@@ -477,10 +482,10 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, uint64_t begin, uint64_t 
   return cudaGetLastError();
 }
 
-cudaError_t wavefront_overflowed(sppm_ctx* c, bool* overflow) {
+cudaError_t wavefront_overflowed(sppm_ctx* c, Lane& Ln, bool* overflow) {
   *overflow = false;
-  if (!c->wf_store.p || c->wf_cap <= 0) return cudaSuccess;
-  const WfLayout L = wf_layout(c->wf_store.p, c->wf_cap, std::max<int64_t>(c->wf_cap * 2, 1 << 16));
+  if (!Ln.wf_store.p || Ln.wf_cap <= 0) return cudaSuccess;
+  const WfLayout L = wf_layout(Ln.wf_store.p, Ln.wf_cap, std::max<int64_t>(Ln.wf_cap * 2, 1 << 16));
   unsigned v = 0;
   cudaError_t e = cudaMemcpyAsync(&v, L.counters + 64, 4, cudaMemcpyDeviceToHost, c->stream);
   if (e) return e;
