@@ -44,9 +44,10 @@ enum { SPPM_OBJ_PLANE = 0, SPPM_OBJ_SPHERE = 1, SPPM_OBJ_BEZIER = 2 };
  * shipped because N starts at 0); PROGRESSIVE drops the N<=0 guard. */
 enum { SPPM_UPDATE_REFERENCE = 0, SPPM_UPDATE_PROGRESSIVE = 1 };
 /* Newton arithmetic.  EXACT = operation order of Bezier.h:69-134 without FMA
- * contraction (bit-identical to the oracle); FAST = joint tensor-form evaluation with
- * FMA (within 1e-6 relative of EXACT, the north-star tolerance). */
-enum { SPPM_NEWTON_EXACT = 0, SPPM_NEWTON_FAST = 1 };
+ * contraction (bit-identical to the oracle); FAST = the patch in the monomial basis,
+ * Horner + FMA, 84 FMA per evaluation (within 1e-6 relative of EXACT, the north-star
+ * tolerance); FAST_BERNSTEIN = Bernstein tensor form + FMA (~165 per evaluation). */
+enum { SPPM_NEWTON_EXACT = 0, SPPM_NEWTON_FAST = 1, SPPM_NEWTON_FAST_BERNSTEIN = 2 };
 /* Photon tracer organisation.  WAVEFRONT = one kernel step per bounce over a compacted
  * queue of live photons + a separate Newton kernel over the queued (ray, patch) items;
  * PERSISTENT = one persistent-warp megakernel.  Same results (the RNG is keyed by photon). */

@@ -16,7 +16,7 @@ c_double3 = C.c_double * 3
 
 SPPM_OBJ_PLANE, SPPM_OBJ_SPHERE, SPPM_OBJ_BEZIER = 0, 1, 2
 SPPM_UPDATE_REFERENCE, SPPM_UPDATE_PROGRESSIVE = 0, 1
-SPPM_NEWTON_EXACT, SPPM_NEWTON_FAST = 0, 1
+SPPM_NEWTON_EXACT, SPPM_NEWTON_FAST, SPPM_NEWTON_FAST_BERNSTEIN = 0, 1, 2
 SPPM_TRACE_WAVEFRONT, SPPM_TRACE_PERSISTENT = 0, 1
 SPPM_DOMAIN_PHOTON, SPPM_DOMAIN_EYE, SPPM_DOMAIN_TEST = 2, 3, 5
 

@@ -302,6 +302,7 @@ void sppm_ctx_destroy(sppm_ctx* c) {
 int sppm_set_params(sppm_ctx* c, const SppmParams* p) {
   if (!c || !p) return SPPM_ERR_INVALID;
   if (p->max_dep < 0 || p->max_dep > 13) return fail(c, SPPM_ERR_INVALID, "max_dep must be in [0,13]");
+  if (p->newton_mode < 0 || p->newton_mode > 2) return fail(c, SPPM_ERR_INVALID, "bad newton_mode");
   if (p->trace_mode != SPPM_TRACE_WAVEFRONT && p->trace_mode != SPPM_TRACE_PERSISTENT) return fail(c, SPPM_ERR_INVALID, "bad trace_mode");
   if (p->newton_restarts < 1 || p->newton_restarts > 4095) return fail(c, SPPM_ERR_INVALID, "newton_restarts out of range");
   if (p->newton_iters < 1) return fail(c, SPPM_ERR_INVALID, "newton_iters must be >= 1");
@@ -331,6 +332,30 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
         patchP[((size_t)p * 16 + q) * 3 + k] = v;
         if (bx[k] > v) bx[k] = v;
         if (bx[3 + k] < v) bx[3 + k] = v;
+      }
+  }
+  // monomial coefficients per patch and component: A = M G M^T with G[i][k] = P[4i+k] (i <-> v,
+  // k <-> u) and M the cubic Bernstein -> power basis matrix
+  std::vector<double> patchA((size_t)s->n_patches * 48);
+  {
+    static const double M[4][4] = {{1, 0, 0, 0}, {-3, 3, 0, 0}, {3, -6, 3, 0}, {-1, 3, -3, 1}};
+    for (int p = 0; p < s->n_patches; p++)
+      for (int k = 0; k < 3; k++) {
+        double G[4][4], T[4][4];
+        for (int i = 0; i < 4; i++)
+          for (int j = 0; j < 4; j++) G[i][j] = patchP[((size_t)p * 16 + 4 * i + j) * 3 + k];
+        for (int i = 0; i < 4; i++)      // T = M G  (v direction)
+          for (int j = 0; j < 4; j++) {
+            double t = 0;
+            for (int q = 0; q < 4; q++) t += M[i][q] * G[q][j];
+            T[i][j] = t;
+          }
+        for (int i = 0; i < 4; i++)      // A = T M^T (u direction)
+          for (int j = 0; j < 4; j++) {
+            double t = 0;
+            for (int q = 0; q < 4; q++) t += T[i][q] * M[j][q];
+            patchA[((size_t)p * 16 + 4 * i + j) * 3 + k] = t;
+          }
       }
   }
   std::vector<DevObject> objs(s->n_objects);
@@ -393,7 +418,7 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
     const SppmTexture& ht = s->textures[t];
     if (ht.rows <= 0 || ht.cols <= 0 || !ht.bgr8) return fail(c, SPPM_ERR_INVALID, "empty texture (Q18: the reference would read out of range)");
     const uint8_t* dev = nullptr;
-    CU(c, upload(c, 5 + (size_t)t, ht.bgr8, (size_t)ht.rows * ht.cols * 3, &dev));
+    CU(c, upload(c, 6 + (size_t)t, ht.bgr8, (size_t)ht.rows * ht.cols * 3, &dev));
     tex[t].rows = ht.rows;
     tex[t].cols = ht.cols;
     tex[t].bgr = dev;
@@ -408,6 +433,7 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
   CU(c, upload(c, 2, patchBox.data(), patchBox.size(), &ds.patchBox));
   CU(c, upload(c, 3, lights.data(), lights.size(), &ds.lights));
   CU(c, upload(c, 4, tex.data(), tex.size(), &ds.tex));
+  CU(c, upload(c, 5, patchA.data(), patchA.size(), &ds.patchA));
   CU(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
   c->scene = ds;
   CU(c, trace_configure(c));

@@ -38,7 +38,8 @@ struct DevTexture {
 struct DevScene {
   int n_obj, n_patch, n_light, n_tex;
   const DevObject* obj;     // [n_obj]
-  const double* patchP;     // [n_patch][48]
+  const double* patchP;     // [n_patch][48] Bernstein control points
+  const double* patchA;     // [n_patch][48] the same patches in the monomial basis: A[i][k][c], S = sum A u^k v^i
   const double* patchBox;   // [n_patch][6]
   const SppmLight* lights;  // [n_light]
   const DevTexture* tex;    // [n_tex]
@@ -60,20 +61,22 @@ struct WarpScratch {
 struct SceneView {
   const DevObject* obj;
   const double* patchP;
+  const double* patchA;
   const double* patchBox;
   const DevTexture* tex;
   const double* lut255;  // lut255[b] = b / 255.0 (Element.h:54-57), exact quotients
   int n_obj;
 };
 
-__host__ __device__ inline size_t scene_smem_bytes(int n_obj, int n_patch, bool patches_in_smem) {
+// with_A: also stage the monomial coefficients (only kernels that run the FAST Newton need them)
+__host__ __device__ inline size_t scene_smem_bytes(int n_obj, int n_patch, bool patches_in_smem, bool with_A = true) {
   size_t b = (size_t)n_obj * sizeof(DevObject) + 256 * sizeof(double);
-  if (patches_in_smem) b += (size_t)n_patch * 54 * sizeof(double);
+  if (patches_in_smem) b += (size_t)n_patch * (with_A ? 102 : 54) * sizeof(double);
   return (b + 15) & ~(size_t)15;
 }
 
 // Copy objects (and patches if they fit) into dynamic shared memory; all threads call.
-__device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, bool patches_in_smem) {
+__device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, bool patches_in_smem, bool with_A = true) {
   SceneView v;
   {
     const int n = s.n_obj * (int)(sizeof(DevObject) / 8);
@@ -94,8 +97,15 @@ __device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, 
     for (int i = threadIdx.x; i < s.n_patch * 6; i += blockDim.x) db[i] = s.patchBox[i];
     v.patchP = dp;
     v.patchBox = db;
+    v.patchA = s.patchA;
+    if (with_A) {
+      double* da = db + (size_t)s.n_patch * 6;
+      for (int i = threadIdx.x; i < s.n_patch * 48; i += blockDim.x) da[i] = s.patchA[i];
+      v.patchA = da;
+    }
   } else {
     v.patchP = s.patchP;
+    v.patchA = s.patchA;
     v.patchBox = s.patchBox;
   }
   v.tex = s.tex;
@@ -233,6 +243,32 @@ __device__ __forceinline__ PatchEval eval_fast(const double* __restrict__ P, dou
   return e;
 }
 
+// FAST (default): the patch in the monomial basis (coefficients precomputed at scene upload,
+// A = M P M^T), Horner in u for the four v-rows and their u-derivatives, Horner in v for S, Su
+// and the v-derivative: 84 FMA per evaluation instead of ~165 in Bernstein tensor form.
+__device__ __forceinline__ PatchEval eval_mono(const double* __restrict__ A, double u, double v) {
+  const double u2 = 2 * u, u3 = 3 * u * u, v2 = 2 * v, v3 = 3 * v * v;
+  double S[3], Su[3], Sv[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double r[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const double a0 = A[(4 * i) * 3 + k], a1 = A[(4 * i + 1) * 3 + k], a2 = A[(4 * i + 2) * 3 + k], a3 = A[(4 * i + 3) * 3 + k];
+      r[i] = fma(fma(fma(a3, u, a2), u, a1), u, a0);
+      d[i] = fma(a3, u3, fma(a2, u2, a1));
+    }
+    S[k] = fma(fma(fma(r[3], v, r[2]), v, r[1]), v, r[0]);
+    Sv[k] = fma(r[3], v3, fma(r[2], v2, r[1]));
+    Su[k] = fma(fma(fma(d[3], v, d[2]), v, d[1]), v, d[0]);
+  }
+  PatchEval e;
+  e.S = d3{S[0], S[1], S[2]};
+  e.Su = d3{Su[0], Su[1], Su[2]};
+  e.Sv = d3{Sv[0], Sv[1], Sv[2]};
+  return e;
+}
+
 // One Newton step x = prevX - inv([dir, -Su, -Sv]) * (org + dir*t - S)  (Bezier.h:121-131).
 // The inverse is cv::Matx33d::inv's closed form (adjugate / determinant, zeros when the
 // determinant is exactly 0) held in registers.
@@ -278,16 +314,22 @@ __device__ __forceinline__ void newton_step(d3 org, d3 dir, const PatchEval& e, 
 
 // One restart of Bezier3::newton (Bezier.h:116-141): from (0,u0,v0) run `iters`
 // iterations, keep the first strict minimum of t over the accepted iterates (Q4).
-template <bool FAST>
+// MODE: 0 EXACT (P = control points), 1 FAST (P = monomial coefficients), 2 Bernstein tensor form + FMA
+template <int MODE>
+__device__ __forceinline__ PatchEval eval_mode(const double* __restrict__ P, double u, double v) {
+  return MODE == 0 ? eval_exact(P, u, v) : (MODE == 1 ? eval_mono(P, u, v) : eval_fast(P, u, v));
+}
+template <int MODE>
 __device__ __forceinline__ bool newton_restart(const double* __restrict__ P, d3 org, d3 dir, double u0, double v0,
                                                int iters, double& bt, double& bu, double& bv) {
+  constexpr bool FAST = MODE != 0;
   double t = 0, u = u0, v = v0;
   bool found = false;
   bt = SPPM_MAX_NUM;
-  PatchEval e = FAST ? eval_fast(P, u, v) : eval_exact(P, u, v);
+  PatchEval e = eval_mode<MODE>(P, u, v);
   for (int it = 0; it < iters; it++) {
     newton_step<FAST>(org, dir, e, t, u, v);
-    e = FAST ? eval_fast(P, u, v) : eval_exact(P, u, v);
+    e = eval_mode<MODE>(P, u, v);
     const d3 r = (org + dir * t) - e.S;
     const double res = ((0.0 + r.x * r.x) + r.y * r.y) + r.z * r.z;
     if (res < SPPM_M_EPS && u <= 1 && u >= 0 && v >= 0 && v <= 1) {
@@ -337,8 +379,9 @@ __device__ inline void flush_items(const SceneView& sv, WarpScratch* ws, int n_i
         draw2(cfg.seed, pass, ws->id[owner], ws->node[owner], domain, (uint32_t)r, (uint32_t)gp, u0, v0);
       }
       const double* P = sv.patchP + (size_t)gp * 48;
-      found = (cfg.mode == SPPM_NEWTON_FAST) ? newton_restart<true>(P, org, dir, u0, v0, cfg.iters, t, u, v)
-                                             : newton_restart<false>(P, org, dir, u0, v0, cfg.iters, t, u, v);
+      if (cfg.mode == SPPM_NEWTON_FAST) found = newton_restart<1>(sv.patchA + (size_t)gp * 48, org, dir, u0, v0, cfg.iters, t, u, v);
+      else if (cfg.mode == SPPM_NEWTON_EXACT) found = newton_restart<0>(P, org, dir, u0, v0, cfg.iters, t, u, v);
+      else found = newton_restart<2>(P, org, dir, u0, v0, cfg.iters, t, u, v);
     }
     // segmented arg-min over the (at most a few) items present in this round; restart order = lane order
     const int first = base / R;

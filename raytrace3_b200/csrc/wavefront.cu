@@ -84,7 +84,7 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 
 __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem);
+  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem, false);
   const int lane = threadIdx.x & 31;
   const unsigned n_in = a.bounce == 0 ? a.n_in_host : *a.n_in_ptr;
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -390,8 +390,8 @@ WfLayout wf_layout(void* store, int64_t cap, int64_t item_cap) {
 }  // namespace
 
 cudaError_t wavefront_configure(sppm_ctx* c, int* step_blocks, int* newton_blocks, size_t* step_smem, size_t* newton_smem) {
-  const size_t scene = scene_smem_bytes(c->scene.n_obj, c->scene.n_patch, c->patches_in_smem);
-  *step_smem = scene;
+  const size_t scene = scene_smem_bytes(c->scene.n_obj, c->scene.n_patch, c->patches_in_smem, true);
+  *step_smem = scene_smem_bytes(c->scene.n_obj, c->scene.n_patch, c->patches_in_smem, false);
   *newton_smem = scene + TRACE_WARPS * sizeof(WarpScratch);
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(photon_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*step_smem))) return e;

@@ -36,9 +36,11 @@ def test_patch_newton_injected_seeds_exact(ctx, oracle):
     np.testing.assert_array_equal(got, ref)
 
 
-def test_patch_newton_fast_within_1e6(ctx, oracle):
+@pytest.mark.parametrize("mode", [abi.SPPM_NEWTON_FAST, abi.SPPM_NEWTON_FAST_BERNSTEIN])
+def test_patch_newton_fast_within_1e6(ctx, oracle, mode):
+    """FAST (monomial Horner + FMA, the bench default) and FAST_BERNSTEIN against the oracle."""
     sc = make_scene("reference", textures=None)
-    prm = _params(newton_mode=abi.SPPM_NEWTON_FAST)
+    prm = _params(newton_mode=mode)
     ctx.set_params(prm)
     ctx.upload_scene(sc)
     n = 3000
@@ -431,3 +433,24 @@ def test_full_size_properties(ctx):
     halves = ctx.export_stats(n)
     np.testing.assert_array_equal(halves["newN"], full["newN"])
     np.testing.assert_allclose(halves["tao"], full["tao"], rtol=1e-11, atol=0)
+
+
+def test_newton_fast_sweep_against_exact(ctx):
+    """40 000 (ray, patch) pairs: FAST Newton vs EXACT (bit-identical to the reference) — same
+    hit/miss on every pair, (t, u, v) within the north-star 1e-6 relative."""
+    sc = make_scene("reference", textures=None)
+    n = 40_000
+    patch = (np.arange(n) % 32).astype(np.int32)
+    rays = rays_at_patches(patch, 77, sc)
+    rays[: n // 4] = rays_at_teapot(n // 4, 78, sc)
+    ctx.upload_scene(sc)
+    out = {}
+    for mode in (abi.SPPM_NEWTON_EXACT, abi.SPPM_NEWTON_FAST):
+        ctx.set_params(_params(newton_mode=mode))
+        out[mode] = ctx.bezier_patch_batch(rays, patch, None)
+    ref, got = out[abi.SPPM_NEWTON_EXACT], out[abi.SPPM_NEWTON_FAST]
+    hr, hg = ref[:, 0] < 1e19, got[:, 0] < 1e19
+    assert hr.sum() > 20_000 and (~hr).sum() > 2_000
+    assert (hr == hg).all()
+    rel = np.abs(got[hr] - ref[hr]) / np.maximum(np.abs(ref[hr]), 1e-12)
+    assert rel.max() <= 1e-6, rel.max()
