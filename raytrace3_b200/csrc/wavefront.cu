@@ -56,9 +56,10 @@ struct StepArgs {
   DevCounters* counters;
   Queue qin, qout;
   Items it_in, it_out;
-  const unsigned* n_in_ptr;
+  const unsigned* n_in_ptr;  // [2]: photons queued from the front (plane hits) and from the back (others)
   unsigned n_in_host;
-  unsigned* n_out;
+  unsigned* n_out;           // [2]
+  unsigned q_cap;
   unsigned* n_items_out;
   unsigned item_cap;
   unsigned* overflow;
@@ -86,14 +87,22 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
   extern __shared__ __align__(16) unsigned char smem[];
   const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem, false);
   const int lane = threadIdx.x & 31;
-  const unsigned n_in = a.bounce == 0 ? a.n_in_host : *a.n_in_ptr;
+  // The queue is filled from both ends: photons whose pending hit is a plane (3/4 of them, one
+  // coherent shading path) from slot 0 upwards, all others from slot q_cap-1 downwards; photons
+  // that hit nothing are dropped when they are found.  Warps therefore shade uniform work.
+  const unsigned n_front = a.bounce == 0 ? a.n_in_host : a.n_in_ptr[0];
+  const unsigned n_back = a.bounce == 0 ? 0u : a.n_in_ptr[1];
+  const unsigned front_chunks = (n_front + 31) >> 5;
+  const unsigned n_in = front_chunks * 32 + n_back;  // virtual index space: [front chunks | back]
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
   unsigned queries = 0, solves = 0, photons = 0, deposits = 0, kept = 0;  // per thread, < 2^32
 
   for (unsigned base = warp_global * 32; base < n_in; base += n_warps * 32) {
-    const unsigned i = base + lane;
-    const bool active = i < n_in;
+    const unsigned vi = base + lane;
+    const bool in_front = base < front_chunks * 32;
+    const bool active = in_front ? vi < n_front : vi < n_in;
+    const unsigned i = in_front ? vi : a.q_cap - 1 - (vi - front_chunks * 32);
     bool alive = false;
     d3 org = mk(0, 0, 0), dir = mk(0, 0, 1), flux = mk(0, 0, 0);
     uint64_t id = 0;
@@ -221,13 +230,21 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
         alive = false;  // the last query's result is never used (depth limit, Raytracer.h:129-132)
       }
     }
-    // ---- compaction of the survivors into the output queue
+    // ---- compaction of the survivors into the output queue (front: plane hits, back: the rest)
+    if (alive && best.obj < 0 && boxobj == 0) alive = false;  // hit nothing (Raytracer.h:127): the photon is gone
+    const bool to_front = alive && boxobj == 0 && sv.obj[best.obj < 0 ? 0 : best.obj].kind == SPPM_OBJ_PLANE;
     const unsigned am = __ballot_sync(FULL, alive);
     if (!am) continue;
-    unsigned qbase = 0;
-    if (lane == 0) qbase = atomicAdd(a.n_out, (unsigned)__popc(am));
-    qbase = __shfl_sync(FULL, qbase, 0);
-    const unsigned my_slot = qbase + __popc(am & ((1u << lane) - 1));
+    const unsigned fm = __ballot_sync(FULL, to_front), bm0 = am & ~fm;
+    unsigned fbase = 0, bbase = 0;
+    if (lane == 0) {
+      if (fm) fbase = atomicAdd(a.n_out, (unsigned)__popc(fm));
+      if (bm0) bbase = atomicAdd(a.n_out + 1, (unsigned)__popc(bm0));
+    }
+    fbase = __shfl_sync(FULL, fbase, 0);
+    bbase = __shfl_sync(FULL, bbase, 0);
+    const unsigned lt = (1u << lane) - 1;
+    const unsigned my_slot = to_front ? fbase + __popc(fm & lt) : a.q_cap - 1 - (bbase + __popc(bm0 & lt));
     // ---- cooperative Bezier culling: per in-box ray, 32 lanes test 32 patch boxes (Bezier.h:178)
     unsigned my_begin = 0, my_cnt = 0;
     unsigned bm = __ballot_sync(FULL, alive && boxobj != 0);
@@ -352,7 +369,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_i
 struct WfLayout {
   Queue q[2];
   Items it[2];
-  unsigned* counters;  // [0..31] queue counts per bounce, [32..63] item counts per bounce, [64] overflow
+  unsigned* counters;  // [2*b], [2*b+1] queue counts (front, back) of bounce b, [40+b] item counts, [64] overflow
   unsigned item_cap;
 };
 
@@ -437,10 +454,11 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
     a.qout = L.q[(b + 1) & 1];
     a.it_in = L.it[b & 1];
     a.it_out = L.it[(b + 1) & 1];
-    a.n_in_ptr = L.counters + b;
+    a.n_in_ptr = L.counters + 2 * b;
     a.n_in_host = (unsigned)total;
-    a.n_out = L.counters + b + 1;
-    a.n_items_out = L.counters + 32 + b + 1;
+    a.n_out = L.counters + 2 * (b + 1);
+    a.q_cap = (unsigned)Ln.wf_cap;
+    a.n_items_out = L.counters + 40 + b + 1;
     a.item_cap = L.item_cap;
     a.overflow = L.counters + 64;
     a.begin = begin;
