@@ -58,8 +58,8 @@ __host__ __device__ inline d3 get_anormal(d3 a) {                               
 }
 __device__ inline d3 rotated(d3 s, d3 ax, double angle) {  // Vec3.h:99-115
   if (fabs(angle) < SPPM_M_EPS) return s;
-  double cost = cos(angle);
-  double sint = sin(angle);
+  double sint, cost;
+  sincos(angle, &sint, &cost);  // one range reduction for both (same values as sin() and cos())
   d3 r;
   r.x = ((0.0 + s.x * (ax.x * ax.x + (1 - ax.x * ax.x) * cost)) + s.y * (ax.x * ax.y * (1 - cost) - ax.z * sint)) +
         s.z * (ax.x * ax.z * (1 - cost) + ax.y * sint);
