@@ -171,6 +171,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--newton", default="fast", choices=["fast", "exact"])
     ap.add_argument("--trace", default="wavefront", choices=["wavefront", "persistent"])
+    ap.add_argument("--gather", default="filtered", choices=["filtered", "exact"],
+                    help="gather predicate: packed-FP32 interval filter + FP64 fallback (same newN), or FP64 on every pair")
+    ap.add_argument("--count-pairs", action="store_true", help="keep the diagnostic cand_pairs counter on in the timed loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-rounds", type=int, default=10, help="PhotonMap rounds per RayTracer::render() in the e2e leg "
@@ -197,6 +200,8 @@ def main():
     wl = WORKLOADS[args.workload]
     prm = make_params(abi, fast=args.newton == "fast")
     prm.trace_mode = abi.SPPM_TRACE_PERSISTENT if args.trace == "persistent" else abi.SPPM_TRACE_WAVEFRONT
+    prm.gather_mode = abi.SPPM_GATHER_EXACT if args.gather == "exact" else abi.SPPM_GATHER_FILTERED
+    prm.count_pairs = 1 if args.count_pairs else 0   # diagnostic pair counter: off in the timed loop, see below
     ctx = Context(local_rank, prm)
     scene = make_scene(wl["scene"])
     cam = reference_camera(wl["w"], wl["h"])
@@ -243,6 +248,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     total_photons = onetime * len(scene.plvec) * world * args.steps
+    # work statistics (cand_pairs feeds the SURVEY 8d flop count): two untimed rounds with the
+    # diagnostic counter on -- the timed loop above runs with it off unless --count-pairs
+    prm.count_pairs = 1
+    ctx.set_params(prm)
+    ctx.reset_counters()
+    for i in range(2):
+        step(args.warmup + args.steps + i)
+    barrier()
+    stat = ctx.counters()
+    cnt["cand_pairs"] = stat["cand_pairs"] * args.steps // 2
     value = total_photons / (ms * 1e-3)
 
     # ---- e2e: RayTracer::render() through the public API with host buffers
@@ -350,7 +365,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "scene": wl["scene"], "film": [wl["w"], wl["h"]], "hit_points": n_hp,
-                   "photons_per_gpu_per_step": onetime * len(scene.plvec), "newton": f"50x10 {args.newton}", "tracer": args.trace,
+                   "photons_per_gpu_per_step": onetime * len(scene.plvec), "newton": f"50x10 {args.newton}", "tracer": args.trace, "gather": args.gather,
                    "update_mode": "reference", "l2": "inputs larger than L2 (deposit list + hit-point map > 126 MB); new photons every step",
                    "textures": "synthetic, reference sizes", "parallelism": f"photons x{world}, hit points replicated"},
         "e2e": {"value": e2e_value, "unit": "photons/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SPPM_ABI_VERSION 1
+#define SPPM_ABI_VERSION 2
 
 typedef enum SppmError {
   SPPM_OK = 0,
@@ -52,6 +52,11 @@ enum { SPPM_NEWTON_EXACT = 0, SPPM_NEWTON_FAST = 1, SPPM_NEWTON_FAST_BERNSTEIN =
  * queue of live photons + a separate Newton kernel over the queued (ray, patch) items;
  * PERSISTENT = one persistent-warp megakernel.  Same results (the RNG is keyed by photon). */
 enum { SPPM_TRACE_WAVEFRONT = 0, SPPM_TRACE_PERSISTENT = 1 };
+/* Gather predicate evaluation (Raytracer.h:152-154).  EXACT = three FP64 comparisons on every
+ * (hit point, deposit) pair of the 27-cell neighbourhood; FILTERED = the same decisions taken
+ * from a packed-FP32 evaluation with a rigorous error bound, FP64 only for the pairs inside the
+ * bound of a threshold: newN is bit-identical to EXACT, tao is summed in FP64 in both. */
+enum { SPPM_GATHER_EXACT = 0, SPPM_GATHER_FILTERED = 1 };
 /* Random-number domains of the counter RNG (who asks for Newton seeds). */
 enum { SPPM_DOMAIN_PHOTON = 2, SPPM_DOMAIN_EYE = 3, SPPM_DOMAIN_TEST = 5 };
 
@@ -129,6 +134,8 @@ typedef struct SppmParams {
   int32_t newton_mode;     /* SPPM_NEWTON_* */
   int32_t trace_mode;      /* SPPM_TRACE_* */
   uint64_t seed;           /* key of the Philox4x32-10 counter RNG */
+  int32_t gather_mode;     /* SPPM_GATHER_* (ABI version 2) */
+  int32_t count_pairs;     /* 1: the gather counts cand_pairs (diagnostic; a few % of its time), 0: cand_pairs stays 0 */
 } SppmParams;
 
 /* Result of one Scene::NearCollide (Scene.h:165-182 / Element.h:20-39 Collision). */

@@ -217,6 +217,8 @@ int sppm_default_params(SppmParams* p) {
   p->newton_mode = SPPM_NEWTON_EXACT;
   p->trace_mode = SPPM_TRACE_WAVEFRONT;
   p->seed = 0x5EED5EEDull;
+  p->gather_mode = SPPM_GATHER_FILTERED;
+  p->count_pairs = 1;
   return SPPM_OK;
 }
 
@@ -287,7 +289,7 @@ void sppm_ctx_destroy(sppm_ctx* c) {
   }
   if (c->ev_setup) cudaEventDestroy(c->ev_setup);
   free_scene(c);
-  DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->dep_key, &c->dep_key2,
+  DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->units, &c->item_parts, &c->item_off, &c->items, &c->dep_key, &c->dep_key2,
                     &c->dep_idx, &c->dep_idx2, &c->scan_scratch, &c->cub_tmp, &c->dev_scalars, &c->counters, &c->film, &c->scratch};
   for (DevBuf* d : bufs) dev_free(*d);
   for (int i = 0; i < 8; i++)
@@ -304,6 +306,7 @@ int sppm_set_params(sppm_ctx* c, const SppmParams* p) {
   if (p->max_dep < 0 || p->max_dep > 13) return fail(c, SPPM_ERR_INVALID, "max_dep must be in [0,13]");
   if (p->newton_mode < 0 || p->newton_mode > 2) return fail(c, SPPM_ERR_INVALID, "bad newton_mode");
   if (p->trace_mode != SPPM_TRACE_WAVEFRONT && p->trace_mode != SPPM_TRACE_PERSISTENT) return fail(c, SPPM_ERR_INVALID, "bad trace_mode");
+  if (p->gather_mode != SPPM_GATHER_EXACT && p->gather_mode != SPPM_GATHER_FILTERED) return fail(c, SPPM_ERR_INVALID, "bad gather_mode");
   if (p->newton_restarts < 1 || p->newton_restarts > 4095) return fail(c, SPPM_ERR_INVALID, "newton_restarts out of range");
   if (p->newton_iters < 1) return fail(c, SPPM_ERR_INVALID, "newton_iters must be >= 1");
   if (!(p->init_r2 > 0)) return fail(c, SPPM_ERR_INVALID, "init_r2 must be > 0");

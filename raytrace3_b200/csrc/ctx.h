@@ -59,6 +59,17 @@ struct HpSoA {
   uint64_t* okey;
 };
 
+// Work unit of the filtered gather: up to 64 hit points that are consecutive in the cell-sorted
+// map and lie in one run of x-adjacent occupied cells.  The deposits that can reach them are
+// 9 contiguous ranges of the cell-sorted deposit list (rows dy,dz in -1..1, cells x_first-1 ..
+// x_last+1), given as compact-slot runs.
+struct GUnit {
+  int32_t hp_begin, hp_count;
+  int32_t n_cells_x, pad;
+  double org[3];   // centre of the unit's cells: origin of the FP32 coordinates
+  int2 run[9];     // [slot_lo, slot_hi_exclusive) per row, (0,0) outside the grid
+};
+
 struct DevCounters {
   unsigned long long photons, isect_queries, patch_solves, deposits, deposits_kept, cand_pairs, acc_pairs, overflow;
 };
@@ -110,6 +121,9 @@ struct sppm_ctx {
   sppm::DevBuf occ_cell, occ_start;  // occupied cells: grid id [n_occ], hp start [n_occ+1]
   int32_t n_occ = 0;
   sppm::DevBuf occ_nbr;       // int2[n_occ][9]: the neighbourhood as 9 x-runs of compact slots
+  sppm::DevBuf units;         // GUnit[n_units]: work units of the filtered gather
+  int32_t n_units = 0;
+  sppm::DevBuf item_parts, item_off, items;  // per-batch work items of the filtered gather
   // deposits
   sppm::Lane lanes[2];
   int lane_rr = 0, last_lane = 0;

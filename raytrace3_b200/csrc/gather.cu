@@ -141,6 +141,65 @@ __global__ void occ_run_kernel(const uint32_t* occ_cell, int n_occ, Grid g, cons
 }
 __global__ void set_last_kernel(int32_t* starts, int n_occ, int32_t n_hp) { starts[n_occ] = n_hp; }
 
+// ---- work units of the filtered gather ----------------------------------------------------
+constexpr int UNIT_HP = 64;  // hit points per unit (two per lane)
+// flag[o] = 1 when occupied cell o starts a run of x-adjacent occupied cells
+__global__ void run_flag_kernel(const uint32_t* occ_cell, int n_occ, int dim0, int32_t* flag) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_occ) return;
+  const uint32_t c = occ_cell[o];
+  flag[o] = (o == 0 || occ_cell[o - 1] + 1 != c || c % (uint32_t)dim0 == 0) ? 1 : 0;
+}
+// units per run (a run's hit points are contiguous: cut them every UNIT_HP)
+__global__ void unit_count_kernel(const int32_t* run_first, const int32_t* n_runs_p, int n_occ, const int32_t* occ_start,
+                                  int32_t* cnt) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_runs = *n_runs_p;
+  if (r >= n_runs) return;
+  const int o0 = run_first[r], o1 = r + 1 < n_runs ? run_first[r + 1] : n_occ;
+  cnt[r] = (occ_start[o1] - occ_start[o0] + UNIT_HP - 1) / UNIT_HP;
+}
+__global__ void unit_fill_kernel(const int32_t* run_first, const int32_t* n_runs_p, int n_occ, const int32_t* occ_start,
+                                 const uint32_t* occ_cell, const int32_t* unit_off, Grid g, const int32_t* cell_slot,
+                                 GUnit* units) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_runs = *n_runs_p;
+  if (r >= n_runs) return;
+  const int o0 = run_first[r], o1 = r + 1 < n_runs ? run_first[r + 1] : n_occ;
+  const int p0 = occ_start[o0], p1 = occ_start[o1];
+  const double cell = 1.0 / g.inv_cell;
+  int o = o0;  // first cell of the current unit
+  for (int u = unit_off[r], b = p0; b < p1; u++, b += UNIT_HP) {
+    const int e = min(b + UNIT_HP, p1);
+    while (occ_start[o + 1] <= b) o++;
+    int ol = o;
+    while (occ_start[ol + 1] < e) ol++;  // cell of hit point e-1
+    const uint32_t c = occ_cell[o];
+    const int ix = c % g.dim[0], iy = (c / g.dim[0]) % g.dim[1], iz = c / (g.dim[0] * g.dim[1]);
+    const int nx = ol - o + 1;
+    GUnit un;
+    un.hp_begin = b;
+    un.hp_count = e - b;
+    un.n_cells_x = nx;
+    un.pad = 0;
+    un.org[0] = g.org[0] + (ix + 0.5 * nx) * cell;
+    un.org[1] = g.org[1] + (iy + 0.5) * cell;
+    un.org[2] = g.org[2] + (iz + 0.5) * cell;
+    for (int k = 0; k < 9; k++) {
+      const int jy = iy + k % 3 - 1, jz = iz + k / 3 - 1;
+      int2 rr = make_int2(0, 0);
+      if (!(jy < 0 || jz < 0 || jy >= g.dim[1] || jz >= g.dim[2])) {
+        const int x0 = max(ix - 1, 0), x1 = min(ix + nx, g.dim[0] - 1);
+        const long long row = ((long long)jz * g.dim[1] + jy) * g.dim[0];
+        rr.x = cell_slot[row + x0];
+        rr.y = cell_slot[row + x1] + 1;
+      }
+      un.run[k] = rr;
+    }
+    units[u] = un;
+  }
+}
+
 // ---- deposits --------------------------------------------------------------------------
 __global__ void dep_key_kernel(const Deposit* dep, long long m, Grid g, const int32_t* cell_slot, int32_t n_slots,
                                uint32_t* key, uint32_t* rank, unsigned int* slot_count) {
@@ -169,6 +228,29 @@ __global__ void __launch_bounds__(320) dep_scatter_kernel(const Deposit* raw, co
   }
 }
 
+// Per batch: a unit whose 9 deposit ranges hold D deposits becomes ceil(D / ITEM_DEP) work items
+// (none when D = 0), so a boundary cell that collected 10^5 clamped deposits is spread over many
+// warps.  parts[u] -> exclusive scan -> items[off[u] + k] = (u, k << 16 | parts).
+constexpr int ITEM_SLICES = 32;              // 32-deposit slices per work item
+constexpr int ITEM_DEP = ITEM_SLICES * 32;   // deposits per work item
+__global__ void unit_parts_kernel(const GUnit* units, int n_units, const int32_t* dep_off, int32_t* parts) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u > n_units) return;
+  int d = 0;
+  if (u < n_units)
+    for (int k = 0; k < 9; k++) {
+      const int2 r = units[u].run[k];
+      if (r.y > r.x) d += dep_off[r.y] - dep_off[r.x];
+    }
+  parts[u] = (d + ITEM_DEP - 1) / ITEM_DEP;  // parts[n_units] = 0: the scan's last element is the item count
+}
+__global__ void item_fill_kernel(int n_units, const int32_t* parts, const int32_t* off, int2* items) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
+  const int n = parts[u], o = off[u];
+  for (int k = 0; k < n; k++) items[o + k] = make_int2(u, (k << 16) | n);
+}
+
 struct GatherArgs {
   HpSoA s;
   long long n_hp;
@@ -179,6 +261,12 @@ struct GatherArgs {
   const Deposit* dep;
   double search_r2;
   DevCounters* counters;
+  Grid grid;                 // filtered kernel: cell centres
+  const uint32_t* occ_cell;  // grid id of occupied cell c
+  const GUnit* units;        // filtered kernel: work units
+  int n_units;
+  const int2* items;         // (unit, part << 16 | parts) work items of this batch
+  const int32_t* n_items;
 };
 
 // ---- TMA (cp.async.bulk) + mbarrier helpers -----------------------------------------------
@@ -398,6 +486,445 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
   }
 }
 
+// ---- filtered gather: FP32 interval classification, FP64 only where it matters -----------
+//
+// The acceptance predicate of Raytracer.h:152-154 is three FP64 comparisons per (hit point,
+// deposit) pair, and ~80 % of the pairs of a 27-cell neighbourhood fail the first one.  The
+// filtered kernel evaluates the predicate in packed FP32 (sm_100 FADD2/FMUL2/FFMA2, two
+// deposits per instruction) on coordinates taken relative to the centre o of the CTA's cell,
+// with a rigorous error bound, and falls back to the FP64 evaluation of the reference for the
+// (rare) pairs whose FP32 value lies within the bound of a threshold.  newN is therefore
+// bit-identical to the all-FP64 kernel, and tao is summed in FP64 in the same order.
+//
+// Error bound (u = 2^-24, M = bound on |p_k - o_k| and |x_k - o_k| of non-"far" points):
+//   p^_k = fl32(fl64(p_k - o_k)), x^_k likewise:  |p^_k - (p_k - o_k)| <= u M (1 + 2^-28)
+//   v^_k = fl32(p^_k - x^_k):                     |v^_k - (p_k - x_k)| <= 4 u M (1 + 2^-20)
+//   S^   = fma(v^z,v^z, fma(v^y,v^y, v^x v^x)):   |S^ - sum v^_k^2|    <= 3.01 u * 12 M^2
+//   |sum v^_k^2 - sum v_k^2| <= 3 * 4uM * 4M = 48 u M^2;  FP64 rounding of the reference's own
+//   vv: < 1e-15 * 12 M^2.  Total |S^ - vv64| < 85 u M^2; the kernel uses 100 u M^2 (+ the
+//   rounding of the thresholds to FP32).  M = 1.5 cell edges (1 + 1e-6): every point of a
+//   neighbour cell that was not clamped into the grid from outside satisfies it; a tile holding
+//   a "far" deposit, and a "far" hit point, take the FP64 path wholesale.
+//   nn^ = fma(n^z,N^z, fma(n^y,N^y, n^x N^x)) with |n_k|,|N_k| <= 1.0001 (else "far"):
+//   |nn^ - nn64| <= 5.1 u * 3.0006 < 9.2e-7; the kernel uses 1.5e-6.
+// Pairs are classified by the sign of fl32(S^ - fl32(searchR2)) etc. (exact in sign); a slice
+// (the deposits one thread visits in one tile) whose smallest |difference| is inside the bound
+// is recomputed in FP64 by exact_slice(), in the same deposit order.
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rr;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(rr) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rr);
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rr;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(rr) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rr);
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rr;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rr) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rr);
+}
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+
+// Organisation: persistent, fully autonomous warps; no CTA-wide barrier after start-up.  A warp
+// takes a work unit (GUnit: <= 64 consecutive hit points of one run of x-adjacent occupied cells,
+// so sparse cells are merged and dense cells are split) from a global counter.  The deposits
+// that can reach the unit are 9 contiguous ranges of the cell-sorted list; their concatenation
+// is cut into slices of 32.  Lane 0 streams the slices into a warp-private, double-buffered raw
+// buffer with TMA bulk copies (cp.async.bulk + one mbarrier per buffer); the 32 lanes convert
+// one deposit each to FP32 relative to the unit's centre, drop those farther than
+// sqrt(searchR2) from the bounding box of the unit's hit points (ballot compaction), and write
+// the survivors as interleaved pairs.  Then lane = hit point (two hit points per lane for units
+// of 33..64; 32/hl deposit sub-slices when the unit has hl <= 16 hit points) and every lane
+// walks the warp's pairs with broadcast 128-bit shared-memory loads.  A deposit outside the
+// 27-cell neighbourhood of a lane's hit point simply fails the distance test.  Every hit point
+// belongs to exactly one unit: its accumulators are written once, without atomics.
+// With M_x = (n_cells_x / 2 + 1) cell edges the bound above is applied in its sharper form
+//   |S^ - vv64| <= u (5.01 vv + 4 sqrt(vv) |M|) + O(u^2),  |M| = sqrt(M_x^2 + M_y^2 + M_z^2),
+// (E_k <= u (|v_k| + 2 M_k) per coordinate, Cauchy-Schwarz on sum |v_k| M_k), which is monotone
+// in vv, so its value at vv = searchR2 bounds the classification error at the threshold; the
+// kernel uses u (8 searchR2 + 6 sqrt(searchR2) |M|) plus the FP32 rounding of the thresholds.
+constexpr int W_WARPS = 8;
+constexpr int W_THREADS = W_WARPS * 32;
+constexpr int W_SLICE = 32;                                   // deposits per warp slice
+constexpr int W_RAW_BYTES = W_SLICE * (int)sizeof(Deposit);   // 2560
+constexpr int F_PAIR_F4 = 6;                                  // 16-byte words per converted pair (96 B)
+constexpr int W_CONV_BYTES = (W_SLICE / 2) * F_PAIR_F4 * 16;  // 1536
+constexpr int W_PER_WARP = 2 * W_RAW_BYTES + W_CONV_BYTES + 64;  // + kept-index list
+constexpr size_t F_SMEM = (size_t)W_WARPS * W_PER_WARP;
+constexpr int W_CHUNK = 64;                                   // hit points per chunk (2 per lane)
+#define SPPM_F_U 5.9604644775390625e-8 /* 2^-24 */
+#define SPPM_F_NMAX 1.0001
+#define SPPM_F_NBAND 1.5e-6f
+#define SPPM_F_PAD 3.0e18f /* coordinate of a deposit that can never be close */
+
+struct HpF {  // one hit point in FP32, relative to the cell centre
+  float x, y, z, nx, ny, nz;
+  float r2f;   // fl32(R2)
+  float band;  // classification bound for S^ against searchR2 / R2
+};
+
+// FP64 evaluation (the reference's operation order) of one lane's share of a warp slice:
+// list positions 2j, 2j+1 for j = j0, j0+jstep, ...; position q is raw record kidx[q] of the slice
+// (use_list) or raw record q itself.
+__device__ __noinline__ void exact_pairs(const HpSoA s, const int i, const double search_r2, const double2* raw,
+                                         const unsigned char* kidx, const bool use_list, const int n_list, const int j0,
+                                         const int jstep, int& cnt, unsigned& cand, double& t0, double& t1, double& t2) {
+  const double px = s.px[i], py = s.py[i], pz = s.pz[i], nx = s.nx[i], ny = s.ny[i], nz = s.nz[i], r2 = s.r2[i];
+  int c = 0;
+  unsigned cd = 0;
+  double a0 = 0, a1 = 0, a2 = 0;
+  const int npair = (n_list + 1) >> 1;
+  for (int j = j0; j < npair; j += jstep) {
+    for (int h = 0; h < 2; h++) {
+      const int qi = 2 * j + h;
+      if (qi >= n_list) break;
+      const int d = use_list ? (int)kidx[qi] : qi;
+      const double2* q = raw + d * 5;
+      const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+      const double vx = px - q0.x, vy = py - q0.y, vz = pz - q1.x;  // Raytracer.h:152
+      const double vv = (vx * vx + vy * vy) + vz * vz;
+      if (vv < search_r2) {  // flann radiusSearch, strict '<' (Q3)
+        cd++;
+        const double nn = (nx * q1.y + ny * q2.x) + nz * q2.y;
+        if (nn > SPPM_NORMAL_AGREE && vv <= r2) {  // Raytracer.h:154
+          const double2 q3 = q[3], q4 = q[4];
+          c++;
+          a0 += q3.x; a1 += q3.y; a2 += q4.x;
+        }
+      }
+    }
+  }
+  cnt = c; cand = cd; t0 = a0; t1 = a1; t2 = a2;
+}
+
+// FP32 classification of one lane's pairs against its HB hit points; uv / un return the
+// smallest distance of a classified value from its threshold.  UNI: R2 == searchR2 for all hit
+// points of the chunk.  A converted pair is 96 bytes: {x0,x1,y0,y1} {z0,z1,nx0,nx1}
+// {ny0,ny1,nz0,nz1} in FP32 and the two fluxes {fx0,fy0} {fz0,fx1} {fy1,fz1} in FP64; the
+// accumulation is predicated, not branched.
+template <bool UNI, bool COUNT, int HB>
+__device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const int j0, const int jstep, const int npair,
+                                           const HpF (&h)[2], const float sr2f, int (&c)[2], unsigned& cand,
+                                           double (&acc)[2][3], float (&uv)[2], float (&un)[2]) {
+  const float thrf = (float)SPPM_NORMAL_AGREE;
+  unsigned cd = 0;
+  const float4* q = cv + j0 * F_PAIR_F4;
+  const int stride = jstep * F_PAIR_F4;
+#pragma unroll 2
+  for (int j = j0; j < npair; j += jstep, q += stride) {
+    const float4 A = q[0], B = q[1], C = q[2];
+    const double2 F0 = *reinterpret_cast<const double2*>(q + 3), F1 = *reinterpret_cast<const double2*>(q + 4),
+                  F2 = *reinterpret_cast<const double2*>(q + 5);
+#pragma unroll
+    for (int b = 0; b < HB; b++) {
+      const float2 vx = f2sub(bc2(h[b].x), make_float2(A.x, A.y));
+      const float2 vy = f2sub(bc2(h[b].y), make_float2(A.z, A.w));
+      const float2 vz = f2sub(bc2(h[b].z), make_float2(B.x, B.y));
+      float2 vv = f2mul(vx, vx);
+      vv = f2fma(vy, vy, vv);
+      vv = f2fma(vz, vz, vv);
+      float2 nn = f2mul(bc2(h[b].nx), make_float2(B.z, B.w));
+      nn = f2fma(bc2(h[b].ny), make_float2(C.x, C.y), nn);
+      nn = f2fma(bc2(h[b].nz), make_float2(C.z, C.w), nn);
+      const float2 dv = f2sub(vv, bc2(sr2f));
+      const float2 dn = f2sub(nn, bc2(thrf));
+      uv[b] = fminf(uv[b], fminf(fabsf(dv.x), fabsf(dv.y)));
+      un[b] = fminf(un[b], fminf(fabsf(dn.x), fabsf(dn.y)));
+      bool in0 = vv.x < sr2f, in1 = vv.y < sr2f;
+      if (COUNT) cd += (__float_as_uint(dv.x) >> 31) + (__float_as_uint(dv.y) >> 31);  // dv < 0 (never -0)
+      if (!UNI) {
+        const float2 dr = f2sub(vv, bc2(h[b].r2f));
+        uv[b] = fminf(uv[b], fminf(fabsf(dr.x), fabsf(dr.y)));
+        in0 = in0 && vv.x < h[b].r2f;
+        in1 = in1 && vv.y < h[b].r2f;
+      }
+      if (in0 && nn.x > thrf) {
+        c[b]++;
+        acc[b][0] += F0.x; acc[b][1] += F0.y; acc[b][2] += F1.x;
+      }
+      if (in1 && nn.y > thrf) {
+        c[b]++;
+        acc[b][0] += F1.y; acc[b][1] += F2.x; acc[b][2] += F2.y;
+      }
+    }
+  }
+  cand += cd;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const GatherArgs a, unsigned int* work_counter) {
+  extern __shared__ __align__(128) unsigned char wsm[];
+  __shared__ __align__(8) uint64_t bar[W_WARPS][2];
+  __shared__ int run_pre[W_WARPS][12];  // per warp: run starts [0..8] are kept in registers; prefix of run lengths here
+  __shared__ int run_st[W_WARPS][12];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  unsigned char* my = wsm + w * W_PER_WARP;
+  float4* conv = reinterpret_cast<float4*>(my + 2 * W_RAW_BYTES);
+  unsigned char* kidx = my + 2 * W_RAW_BYTES + W_CONV_BYTES;
+  if (lane == 0) {
+    mbar_init(&bar[w][0], 1);
+    mbar_init(&bar[w][1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const double cell = 1.0 / a.grid.inv_cell;
+  const double M_yz = 1.5 * cell * (1.0 + 1e-6);
+  const double half_in = 0.5 * cell * (1.0 + 1e-7);  // a hit point that really lies in its cell
+  const float sr2f = __double2float_rn(a.search_r2);
+  unsigned phase0 = 0, phase1 = 0;  // parity of the next completion of the warp's two barriers
+  unsigned long long cand = 0, acc_total = 0;
+  for (;;) {
+    int it = 0;
+    if (lane == 0) it = (int)atomicAdd(work_counter, 1u);
+    it = __shfl_sync(FULL, it, 0);
+    if (it >= *a.n_items) break;
+    const int2 item = a.items[it];
+    const int u = item.x, part = item.y >> 16;
+    const bool shared_unit = (item.y & 0xffff) > 1;  // several warps accumulate into this unit's hit points
+    const GUnit* un = a.units + u;
+    const int h0 = un->hp_begin, H = un->hp_count, ncx = un->n_cells_x;
+    const double ox = un->org[0], oy = un->org[1], oz = un->org[2];
+    // the 9 deposit ranges and the prefix sums of their lengths (lanes 0..8, then shared)
+    int D;
+    {
+      int st = 0, ln = 0;
+      if (lane < 9) {
+        const int2 run = un->run[lane];
+        if (run.y > run.x) {
+          st = a.dep_off[run.x];
+          ln = a.dep_off[run.y] - st;
+        }
+      }
+      int inc = ln;  // inclusive prefix over lanes 0..8
+#pragma unroll
+      for (int off = 1; off < 16; off <<= 1) {
+        const int t = __shfl_up_sync(FULL, inc, off);
+        if (lane >= off) inc += t;
+      }
+      D = __shfl_sync(FULL, inc, 8);
+      __syncwarp();
+      if (lane < 9) {
+        run_st[w][lane] = st;
+        run_pre[w][lane] = inc - ln;  // exclusive prefix = position of the run's first deposit
+      }
+      if (lane == 9) run_pre[w][9] = D;
+      __syncwarp();
+    }
+    if (D == 0) continue;
+    const int sl0 = part * ITEM_SLICES;  // this item: slices [sl0, sl0 + n_sl) of the concatenation
+    const int n_sl = min(ITEM_SLICES, (D + W_SLICE - 1) / W_SLICE - sl0);
+    // lane 0: stream slice k of the item (deposits [32 (sl0 + k), +32) of the concatenation) into raw buffer k & 1
+    auto issue = [&](int k) {
+      const int buf = k & 1;
+      int p = (sl0 + k) * W_SLICE;
+      int left = min(W_SLICE, D - p);
+      mbar_expect_tx(&bar[w][buf], (unsigned)left * (unsigned)sizeof(Deposit));
+      unsigned char* dst = my + buf * W_RAW_BYTES;
+      int r = 0;
+#pragma unroll
+      for (int i = 1; i < 9; i++) r += (p >= run_pre[w][i]) ? 1 : 0;  // run holding position p (empty runs are skipped)
+      while (left > 0) {
+        const int off = p - run_pre[w][r];
+        const int take = min(run_pre[w][r + 1] - p, left);
+        if (take > 0) {
+          bulk_g2s(dst, a.dep + run_st[w][r] + off, (unsigned)take * (unsigned)sizeof(Deposit), &bar[w][buf]);
+          dst += take * sizeof(Deposit);
+          left -= take;
+          p += take;
+        }
+        r++;
+      }
+    };
+    if (lane == 0) {
+      issue(0);
+      if (n_sl > 1) issue(1);
+    }
+    // hit points of the unit: lane = hit point (+32), sub-slices when there are <= 16
+    const bool two = H > 32;
+    int hl = 32, lg = 5;
+    if (!two) {
+      hl = 1; lg = 0;
+      while (hl < H) { hl <<= 1; lg++; }
+    }
+    const int sub = 32 >> lg, my_h = lane & (hl - 1), sub_id = lane >> lg;
+    const int idx[2] = {h0 + my_h, h0 + 32 + lane};
+    const bool valid[2] = {my_h < H, two && 32 + lane < H};
+    const double half_x = 0.5 * ncx * cell * (1.0 + 1e-7), M_x = (0.5 * ncx + 1.0) * cell * (1.0 + 1e-6);
+    const double Mn = sqrt(M_x * M_x + 2.0 * M_yz * M_yz);
+    const double band_v = SPPM_F_U * (8.0 * a.search_r2 + 6.0 * sqrt(a.search_r2) * Mn) + 1e-13 * Mn * Mn;
+    const float cull_thr = __double2float_ru(a.search_r2 + 2.0 * band_v);
+    HpF hp[2];
+    bool far_hp[2] = {false, false};
+    bool uni_me = true;
+    float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      hp[b] = HpF{-SPPM_F_PAD, -SPPM_F_PAD, -SPPM_F_PAD, 0.f, 0.f, 0.f, 0.f, 0.f};  // never close, not even to a padding deposit
+      if (valid[b]) {
+        const int i = idx[b];
+        const double ax = a.s.px[i] - ox, ay = a.s.py[i] - oy, az = a.s.pz[i] - oz;
+        const double nx = a.s.nx[i], ny = a.s.ny[i], nz = a.s.nz[i], r2 = a.s.r2[i];
+        far_hp[b] = !(fabs(ax) <= half_x && fabs(ay) <= half_in && fabs(az) <= half_in && fabs(nx) <= SPPM_F_NMAX &&
+                      fabs(ny) <= SPPM_F_NMAX && fabs(nz) <= SPPM_F_NMAX && r2 >= 0 && r2 < 1e30);
+        if (!far_hp[b]) {
+          hp[b].x = __double2float_rn(ax); hp[b].y = __double2float_rn(ay); hp[b].z = __double2float_rn(az);
+          hp[b].nx = __double2float_rn(nx); hp[b].ny = __double2float_rn(ny); hp[b].nz = __double2float_rn(nz);
+          hp[b].r2f = __double2float_rn(r2);
+          hp[b].band = __double2float_ru(1.01 * (band_v + 2.0 * SPPM_F_U * fmax(r2, a.search_r2)));
+          blo[0] = fminf(blo[0], hp[b].x); blo[1] = fminf(blo[1], hp[b].y); blo[2] = fminf(blo[2], hp[b].z);
+          bhi[0] = fmaxf(bhi[0], hp[b].x); bhi[1] = fmaxf(bhi[1], hp[b].y); bhi[2] = fmaxf(bhi[2], hp[b].z);
+          uni_me = uni_me && (r2 == a.search_r2);
+        }
+      }
+    }
+    const bool uni = __all_sync(FULL, uni_me);
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        blo[k] = fminf(blo[k], __shfl_xor_sync(FULL, blo[k], off));
+        bhi[k] = fmaxf(bhi[k], __shfl_xor_sync(FULL, bhi[k], off));
+      }
+    int cnt[2] = {0, 0};
+    double sum[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    unsigned cand32 = 0;
+    for (int k = 0; k < n_sl; k++) {
+      const int buf = k & 1;
+      const int fill = min(W_SLICE, D - (sl0 + k) * W_SLICE);
+      const double2* raw = reinterpret_cast<const double2*>(my + buf * W_RAW_BYTES);
+      if (buf == 0) { mbar_wait(&bar[w][0], phase0); phase0 ^= 1; } else { mbar_wait(&bar[w][1], phase1); phase1 ^= 1; }
+      // convert one deposit per lane; keep it if it can be within sqrt(searchR2) of the unit's
+      // bounding box.  A deposit farther than M from the centre in some coordinate (clamped into
+      // a boundary cell from outside the grid) is more than a cell edge away from every hit
+      // point lying inside the unit's cells and is dropped.
+      bool keep = false, badn = false;
+      float fx = 0, fy = 0, fz = 0, gx = 0, gy = 0, gz = 0;
+      double2 q3 = make_double2(0, 0), q4 = make_double2(0, 0);
+      if (lane < fill) {
+        const double2* q = raw + lane * 5;
+        const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+        q3 = q[3]; q4 = q[4];
+        const double ax = q0.x - ox, ay = q0.y - oy, az = q1.x - oz;
+        const bool out = !(fabs(ax) <= M_x && fabs(ay) <= M_yz && fabs(az) <= M_yz);
+        badn = !(fabs(q1.y) <= SPPM_F_NMAX && fabs(q2.x) <= SPPM_F_NMAX && fabs(q2.y) <= SPPM_F_NMAX);
+        fx = __double2float_rn(ax); fy = __double2float_rn(ay); fz = __double2float_rn(az);
+        gx = __double2float_rn(q1.y); gy = __double2float_rn(q2.x); gz = __double2float_rn(q2.y);
+        const float ex = fmaxf(fmaxf(blo[0] - fx, fx - bhi[0]), 0.f), ey = fmaxf(fmaxf(blo[1] - fy, fy - bhi[1]), 0.f),
+                    ez = fmaxf(fmaxf(blo[2] - fz, fz - bhi[2]), 0.f);
+        keep = !out && !(fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > cull_thr);
+      }
+      const unsigned kmask = __ballot_sync(FULL, keep);
+      const bool any_badn = __any_sync(FULL, badn);
+      const int n_k = __popc(kmask);
+      if (keep) {
+        const int pos = __popc(kmask & ((1u << lane) - 1u));
+        float4* pr = conv + (pos >> 1) * F_PAIR_F4;
+        float* f = reinterpret_cast<float*>(pr) + (pos & 1);
+        f[0] = fx; f[2] = fy; f[4] = fz; f[6] = gx; f[8] = gy; f[10] = gz;
+        double* g = reinterpret_cast<double*>(pr + 3) + (pos & 1) * 3;
+        g[0] = q3.x; g[1] = q3.y; g[2] = q4.x;
+        kidx[pos] = (unsigned char)lane;
+      }
+      if (lane == 0 && (n_k & 1)) {  // pad the last pair
+        float4* pr = conv + (n_k >> 1) * F_PAIR_F4;
+        float* f = reinterpret_cast<float*>(pr) + 1;
+        f[0] = SPPM_F_PAD; f[2] = SPPM_F_PAD; f[4] = SPPM_F_PAD; f[6] = 0.f; f[8] = 0.f; f[10] = 0.f;
+        double* g = reinterpret_cast<double*>(pr + 3) + 3;
+        g[0] = 0; g[1] = 0; g[2] = 0;
+      }
+      __syncwarp();
+      {
+        int c_t[2] = {0, 0};
+        double t[2][3] = {{0, 0, 0}, {0, 0, 0}};
+        float uv[2] = {3.0e38f, 3.0e38f}, un2[2] = {3.0e38f, 3.0e38f};
+        unsigned cd_t = 0;
+        const int npair = (n_k + 1) >> 1;
+        if (!any_badn) {
+          if (two) {
+            if (uni) fast_pairs<true, COUNT, 2>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+            else fast_pairs<false, COUNT, 2>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+          } else {
+            if (uni) fast_pairs<true, COUNT, 1>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+            else fast_pairs<false, COUNT, 1>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+          }
+        }
+        bool redo[2];
+#pragma unroll
+        for (int b = 0; b < 2; b++)
+          redo[b] = valid[b] && (any_badn || far_hp[b] || !(uv[b] > hp[b].band) || !(un2[b] > SPPM_F_NBAND));
+        if (redo[0] || redo[1]) {
+          // the fast counters of this lane cover both hit points: recount them exactly
+          unsigned cd_x = 0;
+#pragma unroll
+          for (int b = 0; b < 2; b++) {
+            if (!valid[b]) continue;
+            const bool whole = any_badn || far_hp[b];  // not list based: every raw record of the slice
+            int c_x;
+            unsigned cd_b;
+            double x0, x1, x2;
+            exact_pairs(a.s, idx[b], a.search_r2, raw, kidx, !whole, whole ? fill : n_k, sub_id, sub, c_x, cd_b, x0, x1, x2);
+            c_t[b] = c_x; t[b][0] = x0; t[b][1] = x1; t[b][2] = x2;
+            cd_x += cd_b;
+          }
+          cd_t = cd_x;
+        }
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+          cnt[b] += c_t[b];
+          sum[b][0] += t[b][0]; sum[b][1] += t[b][1]; sum[b][2] += t[b][2];
+        }
+        cand32 += cd_t;
+      }
+      __syncwarp();  // raw / conv / kidx consumed by every lane
+      if (lane == 0 && k + 2 < n_sl) issue(k + 2);
+    }
+    acc_total += (unsigned)(cnt[0] + cnt[1]);
+    cand += cand32;
+    // combine the sub-slices of a hit point (lanes my_h, my_h + hl, ...)
+    for (int o = hl; o < 32; o <<= 1) {
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        cnt[b] += __shfl_xor_sync(FULL, cnt[b], o);
+        sum[b][0] += __shfl_xor_sync(FULL, sum[b][0], o);
+        sum[b][1] += __shfl_xor_sync(FULL, sum[b][1], o);
+        sum[b][2] += __shfl_xor_sync(FULL, sum[b][2], o);
+      }
+    }
+    if (sub_id == 0) {
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        if (valid[b] && cnt[b] > 0) {  // hp->newN++, hp->tao += wgt.mul(flux)*PI_INV (Raytracer.h:155-156)
+          const int i = idx[b];
+          const double d0 = (a.s.wx[i] * sum[b][0]) * SPPM_PI_INV, d1 = (a.s.wy[i] * sum[b][1]) * SPPM_PI_INV,
+                       d2 = (a.s.wz[i] * sum[b][2]) * SPPM_PI_INV;
+          if (shared_unit) {
+            atomicAdd(&a.s.dN[i], cnt[b]);
+            atomicAdd(&a.s.dtao[i], d0);
+            atomicAdd(&a.s.dtao[a.n_hp + i], d1);
+            atomicAdd(&a.s.dtao[2 * a.n_hp + i], d2);
+          } else {
+            a.s.dN[i] += cnt[b];
+            a.s.dtao[i] += d0;
+            a.s.dtao[a.n_hp + i] += d1;
+            a.s.dtao[2 * a.n_hp + i] += d2;
+          }
+        }
+      }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    cand += __shfl_xor_sync(FULL, cand, off);
+    acc_total += __shfl_xor_sync(FULL, acc_total, off);
+  }
+  if (lane == 0 && (cand || acc_total)) {
+    atomicAdd(&a.counters->cand_pairs, cand);
+    atomicAdd(&a.counters->acc_pairs, acc_total);
+  }
+}
+
 // newN += dN, tao += dtao, then HitPoint::update (Raytracer.h:69-79)
 __global__ void update_kernel(HpSoA s, long long n, int mode, double alpha) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,6 +993,7 @@ cudaError_t build_index(sppm_ctx* c) {
   if (n == 0) {
     c->n_occ = 0;
     c->n_slots = 0;
+    c->n_units = 0;
     c->grid = Grid{{0, 0, 0}, 1.0, {1, 1, 1}, 1};
     CK(dev_reserve(c->cell_slot, 4));
     CK(cudaMemsetAsync(c->cell_slot.p, 0xff, 4, st));
@@ -592,6 +1120,33 @@ cudaError_t build_index(sppm_ctx* c) {
   occ_run_kernel<<<nblk((long long)n_occ * 9), TPB, 0, st>>>((uint32_t*)c->occ_cell.p, n_occ, g, (int32_t*)c->cell_slot.p,
                                                              (int2*)c->occ_nbr.p);
   c->host_counters.launches += 4;
+  // 6. work units of the filtered gather: runs of x-adjacent occupied cells, cut every UNIT_HP hit points
+  {
+    int32_t* flag = (int32_t*)c->dep_idx.p;        // [n_occ] (free again)
+    int32_t* run_first = (int32_t*)c->dep_idx2.p;  // [n_runs]
+    int32_t* ucnt = (int32_t*)c->dep_key.p;        // [n_runs]
+    int32_t* uoff = (int32_t*)c->dep_key2.p;       // [n_runs + 1]
+    int32_t* d_nr = d_nruns + 1;
+    run_flag_kernel<<<nblk(n_occ), TPB, 0, st>>>((const uint32_t*)c->occ_cell.p, n_occ, g.dim[0], flag);
+    cub::CountingInputIterator<int32_t> iota(0);
+    CK(cub::DeviceSelect::Flagged(nullptr, tmp, iota, flag, run_first, d_nr, n_occ, st));
+    CK(dev_reserve(c->cub_tmp, tmp));
+    CK(cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, iota, flag, run_first, d_nr, n_occ, st));
+    CK(cudaMemsetAsync(ucnt, 0, ((size_t)n_occ + 1) * 4, st));
+    unit_count_kernel<<<nblk(n_occ), TPB, 0, st>>>(run_first, d_nr, n_occ, (const int32_t*)c->occ_start.p, ucnt);
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, ucnt, uoff, n_occ + 1, st));
+    CK(dev_reserve(c->cub_tmp, tmp));
+    CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, ucnt, uoff, n_occ + 1, st));
+    int32_t n_units = 0;
+    CK(cudaMemcpyAsync(&n_units, uoff + n_occ, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    c->n_units = n_units;
+    CK(dev_reserve(c->units, (size_t)(n_units > 0 ? n_units : 1) * sizeof(GUnit)));
+    unit_fill_kernel<<<nblk(n_occ), TPB, 0, st>>>(run_first, d_nr, n_occ, (const int32_t*)c->occ_start.p,
+                                                  (const uint32_t*)c->occ_cell.p, uoff, g, (const int32_t*)c->cell_slot.p,
+                                                  (GUnit*)c->units.p);
+    c->host_counters.launches += 5;
+  }
   CK(cudaGetLastError());
   c->host_counters.hit_points = (uint64_t)n;
   c->host_counters.grid_cells = (uint64_t)g.n_cells;
@@ -644,14 +1199,39 @@ cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cud
     a.counters = (DevCounters*)c->counters.p;
     unsigned int* work_counter = (unsigned int*)((unsigned long long*)c->dev_scalars.p + 4);
     CK(cudaMemsetAsync(work_counter, 0, 4, st));
-    const size_t tile_bytes = 2 * (size_t)G_TILE * sizeof(Deposit);
-    CK(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));  // per device
+    a.grid = c->grid;
+    a.occ_cell = (const uint32_t*)c->occ_cell.p;
+    a.units = (const GUnit*)c->units.p;
+    a.n_units = c->n_units;
+    const bool filtered = c->prm.gather_mode == SPPM_GATHER_FILTERED;
+    auto kern = !filtered ? gather_kernel : (c->prm.count_pairs ? gather_filtered_kernel<true> : gather_filtered_kernel<false>);
+    const size_t tile_bytes = filtered ? F_SMEM : 2 * (size_t)G_TILE * sizeof(Deposit);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));  // per device
     int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel, G_THREADS, tile_bytes));
+    const int threads = filtered ? W_THREADS : G_THREADS;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, tile_bytes));
     if (const char* e = getenv("SPPM_GATHER_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // tuning knob
     unsigned blocks = (unsigned)c->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm);  // persistent CTAs, cells handed out dynamically
-    if (blocks > (unsigned)c->n_occ) blocks = (unsigned)c->n_occ;
-    gather_kernel<<<blocks, G_THREADS, tile_bytes, st>>>(a, work_counter);
+    const unsigned max_blocks = filtered ? (unsigned)((c->n_units + W_WARPS - 1) / W_WARPS) : (unsigned)c->n_occ;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (filtered) {
+      // work items of this batch (see unit_parts_kernel); the item count stays on the device
+      const int nu = c->n_units;
+      const size_t items_cap = (size_t)nu + (size_t)L.dep_cap / ITEM_DEP + 16;
+      CK(dev_reserve(c->item_parts, ((size_t)nu + 1) * 4));
+      CK(dev_reserve(c->item_off, ((size_t)nu + 1) * 4));
+      CK(dev_reserve(c->items, items_cap * sizeof(int2)));
+      unit_parts_kernel<<<nblk(nu + 1), TPB, 0, st>>>(a.units, nu, a.dep_off, (int32_t*)c->item_parts.p);
+      size_t tmp = 0;
+      CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (int32_t*)c->item_parts.p, (int32_t*)c->item_off.p, nu + 1, st));
+      CK(dev_reserve(c->cub_tmp, tmp));
+      CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, (int32_t*)c->item_parts.p, (int32_t*)c->item_off.p, nu + 1, st));
+      item_fill_kernel<<<nblk(nu), TPB, 0, st>>>(nu, (const int32_t*)c->item_parts.p, (const int32_t*)c->item_off.p, (int2*)c->items.p);
+      a.items = (const int2*)c->items.p;
+      a.n_items = (const int32_t*)c->item_off.p + nu;
+      c->host_counters.launches += 3;
+    }
+    kern<<<blocks, threads, tile_bytes, st>>>(a, work_counter);
     c->host_counters.launches++;
   }
   if (ev_gather_end) CK(cudaEventRecord(ev_gather_end, st));

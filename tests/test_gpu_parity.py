@@ -109,7 +109,11 @@ def _random_hitpoints(rng, n, w=64, h=48):
     return dict(pos=pos, n=nrm, wgt=wgt, r2=r2, pix=pix), w, h
 
 
-def test_gather_bit_exact_newN(ctx, oracle):
+GATHER_MODES = [abi.SPPM_GATHER_EXACT, abi.SPPM_GATHER_FILTERED]
+
+
+@pytest.mark.parametrize("gmode", GATHER_MODES)
+def test_gather_bit_exact_newN(ctx, oracle, gmode):
     """Raytracer.h:139-159: newN bit-exact, tao <= 1e-5 relative vs the exhaustive oracle,
     incl. deposits exactly at distance^2 == searchR2 (strict '<', Q3) and == R2 ('<=')."""
     rng = np.random.RandomState(7)
@@ -130,7 +134,7 @@ def test_gather_bit_exact_newN(ctx, oracle):
     hp["n"][1] = (0, 1, 0)
     x[2] = (21.0, 1.0, 20.0)
     dn[0] = dn[1] = dn[2] = (0, 1, 0)
-    prm = _params()
+    prm = _params(gather_mode=gmode)
     ctx.set_params(prm)
     ctx.import_hitpoints(hp["pos"], hp["n"], hp["wgt"], hp["r2"], hp["pix"], w, h)
     ctx.build_index()
@@ -153,8 +157,9 @@ def test_gather_bit_exact_newN(ctx, oracle):
     np.testing.assert_allclose(got2["tao"], tao2, rtol=1e-5, atol=0)
 
 
-def test_gather_edge_cases(ctx, oracle):
-    prm = _params()
+@pytest.mark.parametrize("gmode", GATHER_MODES)
+def test_gather_edge_cases(ctx, oracle, gmode):
+    prm = _params(gather_mode=gmode)
     ctx.set_params(prm)
     rng = np.random.RandomState(1)
     # empty hit-point map, empty deposit list, single far-away hit point, clustered cell
@@ -181,13 +186,60 @@ def test_gather_edge_cases(ctx, oracle):
     np.testing.assert_allclose(got["tao"], tao, rtol=1e-5, atol=0)
 
 
+@pytest.mark.parametrize("gmode", GATHER_MODES)
+def test_gather_threshold_band_adversarial(ctx, oracle, gmode):
+    """The FILTERED gather classifies pairs in FP32 and must fall back to FP64 inside its error
+    bound: deposits placed at dist^2 = T(1+d) for T in {searchR2, R2} and |d| from 1e-16 to
+    1e-4 (both signs, and d = 0), normals with n.N = 1e-3(1+d), coordinates near 150 where an
+    FP32 ulp is 1.5e-5.  newN and the pair counters must equal the FP64 oracle exactly."""
+    rng = np.random.RandomState(11)
+    n_hp, m = 3000, 60000
+    pos = np.stack([rng.uniform(120, 150, n_hp), rng.uniform(100, 103, n_hp), rng.uniform(130, 150, n_hp)], axis=1)
+    nrm = rng.normal(size=(n_hp, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    r2 = np.where(rng.uniform(size=n_hp) < 0.5, 2.0, rng.uniform(0.3, 2.0, size=n_hp))
+    hp = dict(pos=pos, n=nrm, wgt=rng.uniform(0.1, 1, size=(n_hp, 3)), r2=r2,
+              pix=np.stack([rng.randint(0, 48, n_hp), rng.randint(0, 64, n_hp)], axis=1).astype(np.int32))
+    who = rng.randint(0, n_hp, m)
+    e = rng.normal(size=(m, 3))
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    delta = np.sign(rng.uniform(-1, 1, m)) * 10.0 ** rng.uniform(-16, -4, m)
+    delta[rng.uniform(size=m) < 0.05] = 0.0
+    T = np.where(rng.uniform(size=m) < 0.5, 2.0, r2[who])
+    x = pos[who] + e * np.sqrt(T * (1 + delta))[:, None]
+    # normals: half agree clearly, half sit at the 1e-3 threshold
+    t = np.cross(nrm[who], rng.normal(size=(m, 3)))
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    d2 = np.sign(rng.uniform(-1, 1, m)) * 10.0 ** rng.uniform(-16, -3, m)
+    cosv = np.where(rng.uniform(size=m) < 0.5, 1e-3 * (1 + d2), rng.uniform(0.2, 1.0, m))
+    dn = nrm[who] * cosv[:, None] + t * np.sqrt(1 - cosv ** 2)[:, None]
+    near_dist = rng.uniform(size=m) < 0.3      # some threshold-normal deposits well inside the ball
+    x[near_dist] = pos[who[near_dist]] + e[near_dist] * rng.uniform(0.1, 1.0, near_dist.sum())[:, None]
+    flux = rng.uniform(0, 100, size=(m, 3))
+    prm = _params(gather_mode=gmode)
+    ctx.set_params(prm)
+    ctx.import_hitpoints(hp["pos"], hp["n"], hp["wgt"], hp["r2"], hp["pix"], 64, 48)
+    ctx.build_index()
+    ctx.reset_counters()
+    ctx.gather_deposits(x, dn, flux)
+    ctx.update()
+    got = ctx.export_stats(n_hp)
+    newN, tao, cand, acc = oracle.gather_brute(hp, dict(x=x, n=dn, flux=flux), prm.init_r2)
+    assert newN.sum() > 10000
+    np.testing.assert_array_equal(got["newN"], newN)
+    np.testing.assert_allclose(got["tao"], tao, rtol=1e-5, atol=0)
+    c = ctx.counters()
+    assert c["cand_pairs"] == cand and c["acc_pairs"] == acc
+
+
+@pytest.mark.parametrize("gmode", GATHER_MODES)
 @pytest.mark.parametrize("mode", [abi.SPPM_UPDATE_REFERENCE, abi.SPPM_UPDATE_PROGRESSIVE])
-def test_update_modes(ctx, oracle, mode):
+def test_update_modes(ctx, oracle, mode, gmode):
     """HitPoint::update (Raytracer.h:69-79): verbatim no-op (Q1) and the progressive variant."""
     rng = np.random.RandomState(3)
     hp, w, h = _random_hitpoints(rng, 2000)
     hp["r2"][:] = 2.0
-    prm = _params(update_mode=mode)
+    prm = _params(update_mode=mode, gather_mode=gmode)
     ctx.set_params(prm)
     ctx.import_hitpoints(hp["pos"], hp["n"], hp["wgt"], hp["r2"], hp["pix"], w, h)
     ctx.build_index()
