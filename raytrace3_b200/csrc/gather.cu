@@ -600,6 +600,52 @@ __device__ __noinline__ void exact_pairs(const HpSoA s, const int i, const doubl
   cnt = c; cand = cd; t0 = a0; t1 = a1; t2 = a2;
 }
 
+// A lane whose fast pass came within the error bound of a threshold repeats its share of the
+// slice pair by pair: FP32 classification where it is decisive, the FP64 evaluation of the
+// reference for the (hit point, deposit) pairs inside the bound only.  Same order of summation.
+__device__ __noinline__ void careful_pairs(const HpSoA s, const int i, const double search_r2, const double2* raw,
+                                           const unsigned char* kidx, const int n_list, const float4* cv, const HpF h,
+                                           const float sr2f, const int j0, const int jstep, int& cnt, unsigned& cand,
+                                           double& t0, double& t1, double& t2) {
+  const float thrf = (float)SPPM_NORMAL_AGREE;
+  const double px = s.px[i], py = s.py[i], pz = s.pz[i], nx = s.nx[i], ny = s.ny[i], nz = s.nz[i], r2 = s.r2[i];
+  int c = 0;
+  unsigned cd = 0;
+  double a0 = 0, a1 = 0, a2 = 0;
+  const int npair = (n_list + 1) >> 1;
+  for (int j = j0; j < npair; j += jstep) {
+    const float* f = reinterpret_cast<const float*>(cv + j * F_PAIR_F4);
+    const double* g = reinterpret_cast<const double*>(cv + j * F_PAIR_F4 + 3);
+    for (int hf = 0; hf < 2; hf++) {
+      const int qi = 2 * j + hf;
+      if (qi >= n_list) break;
+      const float vx = h.x - f[hf], vy = h.y - f[2 + hf], vz = h.z - f[4 + hf];
+      const float vv = fmaf(vz, vz, fmaf(vy, vy, vx * vx));
+      const float nn = fmaf(h.nz, f[10 + hf], fmaf(h.ny, f[8 + hf], h.nx * f[6 + hf]));
+      const bool unc = !(fabsf(vv - sr2f) > h.band) || !(fabsf(vv - h.r2f) > h.band) || !(fabsf(nn - thrf) > SPPM_F_NBAND);
+      bool is_cand, is_acc;
+      if (unc) {
+        const double2* q = raw + (int)kidx[qi] * 5;
+        const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+        const double wx = px - q0.x, wy = py - q0.y, wz = pz - q1.x;  // Raytracer.h:152
+        const double ww = (wx * wx + wy * wy) + wz * wz;
+        const double mm = (nx * q1.y + ny * q2.x) + nz * q2.y;
+        is_cand = ww < search_r2;                                      // flann radiusSearch, strict '<' (Q3)
+        is_acc = is_cand && mm > SPPM_NORMAL_AGREE && ww <= r2;        // Raytracer.h:154
+      } else {
+        is_cand = vv < sr2f;
+        is_acc = is_cand && vv < h.r2f && nn > thrf;
+      }
+      cd += is_cand ? 1u : 0u;
+      if (is_acc) {
+        c++;
+        a0 += g[3 * hf]; a1 += g[3 * hf + 1]; a2 += g[3 * hf + 2];
+      }
+    }
+  }
+  cnt = c; cand = cd; t0 = a0; t1 = a1; t2 = a2;
+}
+
 // FP32 classification of one lane's pairs against its HB hit points; uv / un return the
 // smallest distance of a classified value from its threshold.  UNI: R2 == searchR2 for all hit
 // points of the chunk.  A converted pair is 96 bytes: {x0,x1,y0,y1} {z0,z1,nx0,nx1}
@@ -716,26 +762,29 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
     if (D == 0) continue;
     const int sl0 = part * ITEM_SLICES;  // this item: slices [sl0, sl0 + n_sl) of the concatenation
     const int n_sl = min(ITEM_SLICES, (D + W_SLICE - 1) / W_SLICE - sl0);
-    // lane 0: stream slice k of the item (deposits [32 (sl0 + k), +32) of the concatenation) into raw buffer k & 1
+    // lane 0: stream the item's next slice (32 deposits of the concatenation from position cur_p,
+    // which lies in run cur_r) into raw buffer k & 1; the cursor advances slice by slice
+    int cur_p = sl0 * W_SLICE, cur_r = 0;
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 1; i < 9; i++) cur_r += (cur_p >= run_pre[w][i]) ? 1 : 0;
+    }
     auto issue = [&](int k) {
       const int buf = k & 1;
-      int p = (sl0 + k) * W_SLICE;
-      int left = min(W_SLICE, D - p);
+      int left = min(W_SLICE, D - cur_p);
       mbar_expect_tx(&bar[w][buf], (unsigned)left * (unsigned)sizeof(Deposit));
       unsigned char* dst = my + buf * W_RAW_BYTES;
-      int r = 0;
-#pragma unroll
-      for (int i = 1; i < 9; i++) r += (p >= run_pre[w][i]) ? 1 : 0;  // run holding position p (empty runs are skipped)
       while (left > 0) {
-        const int off = p - run_pre[w][r];
-        const int take = min(run_pre[w][r + 1] - p, left);
+        const int end = run_pre[w][cur_r + 1];
+        const int take = min(end - cur_p, left);
         if (take > 0) {
-          bulk_g2s(dst, a.dep + run_st[w][r] + off, (unsigned)take * (unsigned)sizeof(Deposit), &bar[w][buf]);
+          bulk_g2s(dst, a.dep + run_st[w][cur_r] + (cur_p - run_pre[w][cur_r]), (unsigned)take * (unsigned)sizeof(Deposit),
+                   &bar[w][buf]);
           dst += take * sizeof(Deposit);
           left -= take;
-          p += take;
+          cur_p += take;
         }
-        r++;
+        if (cur_p >= end) cur_r++;
       }
     };
     if (lane == 0) {
@@ -861,11 +910,12 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
 #pragma unroll
           for (int b = 0; b < 2; b++) {
             if (!valid[b]) continue;
-            const bool whole = any_badn || far_hp[b];  // not list based: every raw record of the slice
+            const bool whole = any_badn || far_hp[b];  // not list based: every raw record of the slice in FP64
             int c_x;
             unsigned cd_b;
             double x0, x1, x2;
-            exact_pairs(a.s, idx[b], a.search_r2, raw, kidx, !whole, whole ? fill : n_k, sub_id, sub, c_x, cd_b, x0, x1, x2);
+            if (whole) exact_pairs(a.s, idx[b], a.search_r2, raw, kidx, false, fill, sub_id, sub, c_x, cd_b, x0, x1, x2);
+            else careful_pairs(a.s, idx[b], a.search_r2, raw, kidx, n_k, conv, hp[b], sr2f, sub_id, sub, c_x, cd_b, x0, x1, x2);
             c_t[b] = c_x; t[b][0] = x0; t[b][1] = x1; t[b][2] = x2;
             cd_x += cd_b;
           }
