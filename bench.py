@@ -98,6 +98,7 @@ class ClockSampler:
 def make_params(abi, fast=True):
     p = abi.default_params()
     p.newton_mode = abi.SPPM_NEWTON_FAST if fast else abi.SPPM_NEWTON_EXACT
+    p.math_mode = abi.SPPM_MATH_FAST if fast else abi.SPPM_MATH_EXACT
     return p
 
 

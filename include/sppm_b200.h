@@ -57,6 +57,10 @@ enum { SPPM_TRACE_WAVEFRONT = 0, SPPM_TRACE_PERSISTENT = 1 };
  * from a packed-FP32 evaluation with a rigorous error bound, FP64 only for the pairs inside the
  * bound of a threshold: newN is bit-identical to EXACT, tao is summed in FP64 in both. */
 enum { SPPM_GATHER_EXACT = 0, SPPM_GATHER_FILTERED = 1 };
+/* Direction sampling arithmetic (Vec3.h:90-98 GetUnitRandRefl).  EXACT = theta = acos(sqrt(U1))
+ * followed by sin/cos of theta as written; FAST = sin(theta) = sqrt(1-U1), cos(theta) = sqrt(U1)
+ * taken directly (the same distribution, directions equal to a few ulps). */
+enum { SPPM_MATH_EXACT = 0, SPPM_MATH_FAST = 1 };
 /* Random-number domains of the counter RNG (who asks for Newton seeds). */
 enum { SPPM_DOMAIN_PHOTON = 2, SPPM_DOMAIN_EYE = 3, SPPM_DOMAIN_TEST = 5 };
 
@@ -136,6 +140,8 @@ typedef struct SppmParams {
   uint64_t seed;           /* key of the Philox4x32-10 counter RNG */
   int32_t gather_mode;     /* SPPM_GATHER_* (ABI version 2) */
   int32_t count_pairs;     /* 1: the gather counts cand_pairs (diagnostic; a few % of its time), 0: cand_pairs stays 0 */
+  int32_t math_mode;       /* SPPM_MATH_* */
+  int32_t reserved;
 } SppmParams;
 
 /* Result of one Scene::NearCollide (Scene.h:165-182 / Element.h:20-39 Collision). */

@@ -67,7 +67,7 @@ void fold_timings(sppm_ctx* c) {
 
 // Device-side overflow flags (deposit list, Bezier work-item list) are checked at sync points.
 int check_overflow(sppm_ctx* c) {
-  for (int j = 0; j < 2; j++) {
+  for (int j = 0; j < sppm_ctx::MAX_LANES; j++) {
     Lane& L = c->lanes[j];
     if (!L.scalars.p || L.dep_cap <= 0) continue;
     unsigned long long m = 0;
@@ -219,6 +219,8 @@ int sppm_default_params(SppmParams* p) {
   p->seed = 0x5EED5EEDull;
   p->gather_mode = SPPM_GATHER_FILTERED;
   p->count_pairs = 1;
+  p->math_mode = SPPM_MATH_EXACT;
+  p->reserved = 0;
   return SPPM_OK;
 }
 
@@ -251,7 +253,8 @@ int sppm_ctx_create(int device, sppm_ctx** out) {
     for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&c->tev[i][k]) == cudaSuccess;
   ok = ok && dev_reserve(c->dev_scalars, 64) == cudaSuccess && dev_reserve(c->counters, sizeof(DevCounters)) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->ev_setup, cudaEventDisableTiming) == cudaSuccess;
-  for (int j = 0; j < 2 && ok; j++) {
+  if (const char* e = getenv("SPPM_LANES")) c->n_lanes = std::max(1, std::min((int)sppm_ctx::MAX_LANES, atoi(e)));
+  for (int j = 0; j < sppm_ctx::MAX_LANES && ok; j++) {
     Lane& L = c->lanes[j];
     ok = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&L.ev_trace_done, cudaEventDisableTiming) == cudaSuccess &&
@@ -275,11 +278,11 @@ int sppm_ctx_create(int device, sppm_ctx** out) {
 void sppm_ctx_destroy(sppm_ctx* c) {
   if (!c) return;
   Bind b(c);
-  for (int j = 0; j < 2; j++)
+  for (int j = 0; j < sppm_ctx::MAX_LANES; j++)
     if (c->lanes[j].stream) cudaStreamSynchronize(c->lanes[j].stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->nccl_comm && nccl().ok) nccl().CommDestroy((ncclComm_t)c->nccl_comm);
-  for (int j = 0; j < 2; j++) {
+  for (int j = 0; j < sppm_ctx::MAX_LANES; j++) {
     Lane& L = c->lanes[j];
     DevBuf* lb[] = {&L.dep_raw, &L.dep_sorted, &L.dep_key, &L.dep_rank, &L.slot_count, &L.dep_start, &L.wf_store, &L.scalars, &L.cub_tmp};
     for (DevBuf* d : lb) dev_free(*d);
@@ -307,6 +310,7 @@ int sppm_set_params(sppm_ctx* c, const SppmParams* p) {
   if (p->newton_mode < 0 || p->newton_mode > 2) return fail(c, SPPM_ERR_INVALID, "bad newton_mode");
   if (p->trace_mode != SPPM_TRACE_WAVEFRONT && p->trace_mode != SPPM_TRACE_PERSISTENT) return fail(c, SPPM_ERR_INVALID, "bad trace_mode");
   if (p->gather_mode != SPPM_GATHER_EXACT && p->gather_mode != SPPM_GATHER_FILTERED) return fail(c, SPPM_ERR_INVALID, "bad gather_mode");
+  if (p->math_mode != SPPM_MATH_EXACT && p->math_mode != SPPM_MATH_FAST) return fail(c, SPPM_ERR_INVALID, "bad math_mode");
   if (p->newton_restarts < 1 || p->newton_restarts > 4095) return fail(c, SPPM_ERR_INVALID, "newton_restarts out of range");
   if (p->newton_iters < 1) return fail(c, SPPM_ERR_INVALID, "newton_iters must be >= 1");
   if (!(p->init_r2 > 0)) return fail(c, SPPM_ERR_INVALID, "init_r2 must be > 0");
@@ -507,7 +511,7 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
   }
   for (uint64_t off = 0; off < photon_count; off += per_light_batch) {
     const uint64_t cnt = std::min(per_light_batch, photon_count - off);
-    const int j = split ? (c->lane_rr++ & 1) : 0;
+    const int j = split ? (c->lane_rr++ % c->n_lanes) : 0;
     Lane& L = c->lanes[j];
     c->last_lane = j;
     const int64_t cap = (int64_t)(cnt * n_light) * (c->prm.max_dep + 1);

@@ -125,7 +125,9 @@ struct sppm_ctx {
   int32_t n_units = 0;
   sppm::DevBuf item_parts, item_off, items;  // per-batch work items of the filtered gather
   // deposits
-  sppm::Lane lanes[2];
+  static constexpr int MAX_LANES = 4;
+  sppm::Lane lanes[MAX_LANES];
+  int n_lanes = 3;            // lanes used round-robin (SPPM_LANES, 1..MAX_LANES)
   int lane_rr = 0, last_lane = 0;
   cudaEvent_t ev_setup = nullptr;  // recorded on the main stream after scene / hit-point map changes
   sppm::DevBuf dep_key, dep_key2, dep_idx, dep_idx2, scan_scratch, cub_tmp;  // build_index scratch

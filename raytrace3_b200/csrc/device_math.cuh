@@ -56,10 +56,8 @@ __host__ __device__ inline d3 get_refl(d3 I, d3 n) { return I - n * (2 * dot3(I,
 __host__ __device__ inline d3 get_anormal(d3 a) {                                         // Vec3.h:85-89
   return (a.x == 0 && a.y == 0) ? d3{1, 0, 0} : get_unit(d3{a.y, -a.x, 0});
 }
-__device__ inline d3 rotated(d3 s, d3 ax, double angle) {  // Vec3.h:99-115
-  if (fabs(angle) < SPPM_M_EPS) return s;
-  double sint, cost;
-  sincos(angle, &sint, &cost);  // one range reduction for both (same values as sin() and cos())
+// Rodrigues rotation of s about the unit axis ax, given sin and cos of the angle (Vec3.h:102-114)
+__device__ inline d3 rotated_sc(d3 s, d3 ax, double sint, double cost) {
   d3 r;
   r.x = ((0.0 + s.x * (ax.x * ax.x + (1 - ax.x * ax.x) * cost)) + s.y * (ax.x * ax.y * (1 - cost) - ax.z * sint)) +
         s.z * (ax.x * ax.z * (1 - cost) + ax.y * sint);
@@ -69,10 +67,26 @@ __device__ inline d3 rotated(d3 s, d3 ax, double angle) {  // Vec3.h:99-115
         s.z * (ax.z * ax.z + (1 - ax.z * ax.z) * cost);
   return r;
 }
-__device__ inline d3 unit_rand_refl(d3 norm, double U1, double U2) {  // Vec3.h:90-98
-  double theta = acos(sqrt(U1));
-  double phi = 2 * SPPM_PI * U2;
-  d3 ret = rotated(norm, get_anormal(norm), theta);
+__device__ inline d3 rotated(d3 s, d3 ax, double angle) {  // Vec3.h:99-115
+  if (fabs(angle) < SPPM_M_EPS) return s;
+  double sint, cost;
+  sincos(angle, &sint, &cost);  // one range reduction for both (same values as sin() and cos())
+  return rotated_sc(s, ax, sint, cost);
+}
+// Cosine-weighted direction about norm (Vec3.h:90-98).  fast = SPPM_MATH_FAST: theta =
+// acos(sqrt(U1)) is only ever used through its sine and cosine, which are sqrt(1-U1) and
+// sqrt(U1) exactly; taking them directly saves acos() and one sincos() and differs from the
+// acos -> sincos round trip by a few ulps.  The reference's "no rotation below 1e-4 rad"
+// rule (Vec3.h:100) is kept: theta < 1e-4  <=>  cos(theta) > cos(1e-4).
+__device__ inline d3 unit_rand_refl(d3 norm, double U1, double U2, bool fast = false) {
+  const double phi = 2 * SPPM_PI * U2;
+  d3 ret;
+  if (fast) {
+    const double cost = sqrt(U1), sint = sqrt(1 - U1);
+    ret = (cost > 0.999999995) ? norm : rotated_sc(norm, get_anormal(norm), sint, cost);
+  } else {
+    ret = rotated(norm, get_anormal(norm), acos(sqrt(U1)));
+  }
   return get_unit(rotated(ret, norm, phi));
 }
 __device__ inline d3 refracted(d3 I, d3 N, double n) {  // Vec3.h:124-134

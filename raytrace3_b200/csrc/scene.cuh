@@ -145,7 +145,9 @@ __device__ inline bool aabb_intersect(const double* box, d3 org, d3 dir) {
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     if (!is_zero(d[i])) {
-      double t = (d[i] > 0) ? (box[i] - o[i]) / d[i] : (box[3 + i] - o[i]) / d[i];
+      const double num = (d[i] > 0) ? (box[i] - o[i]) : (box[3 + i] - o[i]);
+      if ((num > 0) != (d[i] > 0) || num == 0) continue;  // t <= 0: no division needed to know it
+      const double t = num / d[i];
       if (t > 0) {
         bool flag = true;
 #pragma unroll
@@ -424,7 +426,15 @@ __device__ __forceinline__ void test_plane(const DevObject& ob, int a, d3 org, d
   const d3 norm = ld3(ob.norm);
   const double project = dot3(dir, norm);
   if (!is_zero(project)) {
-    const double dist = dot3(ld3(ob.p0) - org, norm) / project;
+    const double num = dot3(ld3(ob.p0) - org, norm);
+    // dist = num / project is only needed when it can win.  It cannot when the signs differ
+    // (dist <= 0), nor when an FP32 estimate of the quotient (relative error < 2^-20) already
+    // exceeds the current best by more than that: both shortcuts skip exactly the cases the
+    // reference's test rejects, so the result is unchanged and most FP64 divisions go away.
+    if ((num > 0) != (project > 0)) return;
+    const float est = __fdividef(__double2float_rn(num), __double2float_rn(project));
+    if ((double)est > best.dist * (1.0 + 1e-5)) return;
+    const double dist = num / project;
     if (dist > SPPM_M_EPS && dist < best.dist) {
       best.dist = dist;
       best.obj = a;

@@ -19,6 +19,7 @@ struct TraceCommon {
   NewtonCfg ncfg;
   int patches_in_smem;
   int max_dep;
+  int fast_math;
   uint64_t pass;
   DevCounters* counters;
 };
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_TRACE_MINBLOCKS) photon_tr
         if (ob.diffr > r) {
           double U2, unused;
           draw2(a.c.ncfg.seed, a.c.pass, id, (uint32_t)node, P_BOUNCE, 1, 0, U2, unused);
-          ndir = unit_rand_refl(s.n, U1, U2);
+          ndir = unit_rand_refl(s.n, U1, U2, a.c.fast_math != 0);
         } else if (ob.diffr + ob.reflr > r) {
           ndir = get_unit(get_refl(dir, s.n));
         } else {
@@ -368,6 +369,7 @@ TraceCommon make_common(sppm_ctx* c, uint64_t pass) {
   t.ncfg.seed = c->prm.seed;
   t.patches_in_smem = c->patches_in_smem ? 1 : 0;
   t.max_dep = c->prm.max_dep;
+  t.fast_math = c->prm.math_mode == SPPM_MATH_FAST ? 1 : 0;
   t.pass = pass;
   t.counters = (DevCounters*)c->counters.p;
   return t;

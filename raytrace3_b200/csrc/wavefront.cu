@@ -51,7 +51,7 @@ struct Items {
 
 struct StepArgs {
   DevScene scene;
-  int patches_in_smem, max_dep, bounce, do_intersect;
+  int patches_in_smem, max_dep, bounce, do_intersect, fast_math;
   uint64_t seed, pass;
   DevCounters* counters;
   Queue qin, qout;
@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
     const bool active = in_front ? vi < n_front : vi < n_in;
     const unsigned i = in_front ? vi : a.q_cap - 1 - (vi - front_chunks * 32);
     bool alive = false;
+    unsigned rank_val = 0;
+    unsigned long long rank_at = ~0ull;  // deposit whose rank-in-slot is still in flight
     d3 org = mk(0, 0, 0), dir = mk(0, 0, 1), flux = mk(0, 0, 0);
     uint64_t id = 0;
     int dep = 0;
@@ -165,10 +167,28 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
           dep++;
           const DevObject& ob = sv.obj[h.obj];
           const Surface s = shade_hit(sv, h, org, dir);
+          // Raytracer.h:136-160: the gather input (x, N, incoming flux).  The slot lookup is issued
+          // before the Roulette / direction arithmetic and consumed after it, and the rank atomic's
+          // result is stored at the end of the iteration, so neither latency is waited for here.
+          int32_t slot = -1;
+          if (ob.isDiff && a.cell_slot) slot = __ldg(a.cell_slot + grid_cell(a.grid, s.pos.x, s.pos.y, s.pos.z));
+          // Obj::Roulette (Obj.h:30-45) and the single continuation (Raytracer.h:162-190)
+          double ur, U1;
+          draw2(a.seed, a.pass, id, (uint32_t)node, P_BOUNCE, 0, 0, ur, U1);
+          const double r = randu(ur, 0., ob.allr);
+          d3 ndir;
+          if (ob.diffr > r) {
+            double U2, unused;
+            draw2(a.seed, a.pass, id, (uint32_t)node, P_BOUNCE, 1, 0, U2, unused);
+            ndir = unit_rand_refl(s.n, U1, U2, a.fast_math != 0);
+          } else if (ob.diffr + ob.reflr > r) {
+            ndir = get_unit(get_refl(dir, s.n));
+          } else {
+            const double refrn = h.inside ? ob.refrn : 1 / ob.refrn;
+            ndir = normalize3(refracted(dir, h.inside ? -s.n : s.n, refrn));
+          }
           if (ob.isDiff) {  // Raytracer.h:136-160: the gather input (x, N, incoming flux)
             deposits++;
-            int32_t slot = -1;
-            if (a.cell_slot) slot = __ldg(a.cell_slot + grid_cell(a.grid, s.pos.x, s.pos.y, s.pos.z));
             if (slot >= 0 || a.keep_all) {
               // append with one atomic per group of lanes that are here together
               const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
@@ -184,25 +204,11 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
                 a.dep[ds] = rec;
                 const uint32_t key = slot >= 0 ? (uint32_t)slot : (uint32_t)a.n_slots;
                 a.dep_key[ds] = key;
-                a.dep_rank[ds] = atomicAdd(a.slot_count + key, 1u);  // counting sort: rank within the slot
+                rank_val = atomicAdd(a.slot_count + key, 1u);  // counting sort: rank within the slot
+                rank_at = ds;
                 kept++;
               }
             }
-          }
-          // Obj::Roulette (Obj.h:30-45) and the single continuation (Raytracer.h:162-190)
-          double ur, U1;
-          draw2(a.seed, a.pass, id, (uint32_t)node, P_BOUNCE, 0, 0, ur, U1);
-          const double r = randu(ur, 0., ob.allr);
-          d3 ndir;
-          if (ob.diffr > r) {
-            double U2, unused;
-            draw2(a.seed, a.pass, id, (uint32_t)node, P_BOUNCE, 1, 0, U2, unused);
-            ndir = unit_rand_refl(s.n, U1, U2);
-          } else if (ob.diffr + ob.reflr > r) {
-            ndir = get_unit(get_refl(dir, s.n));
-          } else {
-            const double refrn = h.inside ? ob.refrn : 1 / ob.refrn;
-            ndir = normalize3(refracted(dir, h.inside ? -s.n : s.n, refrn));
           }
           flux = mul3(s.color, flux);
           org = s.pos;
@@ -230,6 +236,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
         alive = false;  // the last query's result is never used (depth limit, Raytracer.h:129-132)
       }
     }
+    if (rank_at != ~0ull) a.dep_rank[rank_at] = rank_val;  // the atomic issued before the Roulette has landed by now
     // ---- compaction of the survivors into the output queue (front: plane hits, back: the rest)
     if (alive && best.obj < 0 && boxobj == 0) alive = false;  // hit nothing (Raytracer.h:127): the photon is gone
     const bool to_front = alive && boxobj == 0 && sv.obj[best.obj < 0 ? 0 : best.obj].kind == SPPM_OBJ_PLANE;
@@ -447,6 +454,7 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
     a.max_dep = c->prm.max_dep;
     a.bounce = b;
     a.do_intersect = b < n_steps - 1;
+    a.fast_math = c->prm.math_mode == SPPM_MATH_FAST ? 1 : 0;
     a.seed = c->prm.seed;
     a.pass = pass_id;
     a.counters = (DevCounters*)c->counters.p;

@@ -417,6 +417,42 @@ def test_wavefront_equals_persistent(ctx):
     assert c0["patch_solves"] > 1000
 
 
+def test_fast_math_directions_match_exact(ctx):
+    """SPPM_MATH_FAST takes sin/cos of theta = acos(sqrt(U1)) as sqrt(1-U1), sqrt(U1) (Vec3.h:90-98
+    without the acos -> sincos round trip): the same photons deposit at the same places to
+    rounding (paths are chaotic, so a few may split at an edge after many bounces)."""
+    sc = make_scene("reference", textures=None)
+    cam = reference_camera(64, 48)
+    out = []
+    for mm in (abi.SPPM_MATH_EXACT, abi.SPPM_MATH_FAST):
+        ctx.set_params(_params(math_mode=mm))
+        ctx.upload_scene(sc)
+        ctx.eye_pass(cam, 0)
+        ctx.build_index()
+        ctx.keep_deposits(True)
+        try:
+            ctx.photon_pass(0, 20000, 3)
+            out.append(ctx.export_deposits())
+        finally:
+            ctx.keep_deposits(False)
+    d0, d1 = out
+    k0 = {(int(p), int(b)): i for i, (p, b) in enumerate(zip(d0["photon"], d0["bounce"]))}
+    idx0, idx1 = [], []
+    for j, (p, b) in enumerate(zip(d1["photon"], d1["bounce"])):
+        i = k0.get((int(p), int(b)))
+        if i is not None:
+            idx0.append(i)
+            idx1.append(j)
+    assert len(idx0) >= 0.995 * max(len(d0["photon"]), len(d1["photon"]))
+    err = np.abs(d0["x"][idx0] - d1["x"][idx1]).max(axis=1)
+    assert np.mean(err < 1e-8) > 0.995
+    # after one sampled direction: rounding of a ~100-unit path; acos() near 1 is ill-conditioned
+    # (d theta = eps / theta), so the EXACT chain itself carries ~1e-9 at small theta / grazing hits
+    first = d0["bounce"][idx0] == 1
+    assert np.abs(d0["x"][idx0][first] - d1["x"][idx1][first]).max() < 1e-7
+    assert np.median(np.abs(d0["x"][idx0][first] - d1["x"][idx1][first]).max(axis=1)) < 1e-12
+
+
 def test_gpu_matches_the_reference_itself(ctx, oracle):
     """CUDA NearCollide against the reference's OWN compiled code (oracle/_ref, built from
     /root/reference/raytracer/*.h; the oracle only supplies the draw log that tells which
