@@ -317,34 +317,46 @@ def main():
     trace_bytes = 84.0 * dep_kept                                      # deposits written (80 B + 4 B key)
     trace_flops = 175000.0 * solves + 140.0 * queries                  # Newton (350 x 500) + analytic tests
     trace_name = "photon_trace_kernel" if prm.trace_mode == abi.SPPM_TRACE_PERSISTENT else "photon_step_kernel+newton_items_kernel"
+    gather_name = "gather_kernel" if args.gather == "exact" else "gather_filtered_kernel"
     kern = {
         trace_name: dict(ms=ms_trace, bytes=trace_bytes, flops=trace_flops),
-        "gather_kernel": dict(ms=ms_gather, bytes=gather_bytes, flops=gather_flops),
+        gather_name: dict(ms=ms_gather, bytes=gather_bytes, flops=gather_flops),
     }
     # the dominant KERNEL is the largest single launch: gather_kernel (one launch per step); the
     # tracer's time is spread over ~29 launches (15 step + 14 Newton kernels, <= 0.5 ms each)
-    dom = "gather_kernel" if ms_gather * 4 >= ms_trace or prm.trace_mode != abi.SPPM_TRACE_PERSISTENT else trace_name
+    dom = gather_name if ms_gather * 4 >= ms_trace or prm.trace_mode != abi.SPPM_TRACE_PERSISTENT else trace_name
     if prm.trace_mode == abi.SPPM_TRACE_PERSISTENT and ms_trace > ms_gather:
         dom = trace_name
     d = kern[dom]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
-    # dram__bytes_read.sum + dram__bytes_write.sum of one gather_kernel launch on this workload,
-    # ncu --set full capture profiles/r1_h_gather_ncu.md (621.3 MB read + 26.4 MB written)
-    traffic = 647.7e6 if (dom == "gather_kernel" and args.workload == DEFAULT_WORKLOAD and world == 1) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of one gather launch on this workload, from the
+    # ncu --set full captures profiles/r1_o_gather_filtered_ncu.md (548.3 MB read + 30.2 MB written)
+    # and profiles/r1_h_gather_ncu.md (exact kernel: 621.3 + 26.4 MB)
+    traffic = None
+    if dom == gather_name and args.workload == DEFAULT_WORKLOAD and world == 1:
+        traffic = 647.7e6 if args.gather == "exact" else 578.5e6
+    if args.gather == "exact":
+        note = ("the binding resource is the FP64 pipe (ncu: 46 % FP64-pipe active, DRAM 2 % busy): per step the kernel "
+                "distance-tests ~5x more (hit point, deposit) pairs than cand_pairs (27-cell neighbourhood vs ball), "
+                "8 FP64 ops each, against 0.5 GB of compulsory traffic; fp64_tflops counts only the SURVEY 8d flops")
+    else:
+        note = ("instruction-issue bound, not HBM bound (ncu r1_o: issue slots 68 % busy, ALU pipe 37 %, FMA pipe 21 % "
+                "[packed FADD2/FFMA2], FP64 pipe 16 %, DRAM 6 % busy): ~0.5 G (hit point, deposit) pairs survive the "
+                "bounding-box cull and are classified in FP32 at ~17 warp instructions per 64 pairs, against 0.5 GB of "
+                "compulsory traffic; the timed span is measured while a photon-tracing lane shares the SMs "
+                "(1.24 ms when the kernel runs alone); fp64_tflops counts only the SURVEY 8d flops")
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": d["bytes"],
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, sustained copy)",
                 "ms_per_launch": d["ms"], "share_of_step": d["ms"] / (ms / steps),
                 "fp64_tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0, "fp64_peak_tflops": fp64_peak,
                 "fp64_frac": (d["flops"] / (d["ms"] * 1e-3) / 1e12 / fp64_peak) if d["ms"] > 0 and fp64_peak > 0 else None,
-                "note": "the binding resource is the FP64 pipe (ncu: 46 % FP64-pipe active, DRAM 2 % busy): per step the kernel "
-                        "distance-tests ~5x more (hit point, deposit) pairs than cand_pairs (27-cell neighbourhood vs ball), "
-                        "8 FP64 ops each, against 0.5 GB of compulsory traffic; fp64_tflops counts only the SURVEY §8d flops"}
+                "note": note}
     kernels = {k: {"ms_per_step": v["ms"], "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0,
                    "hbm_frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak if v["ms"] > 0 else 0.0,
                    "fp64_tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0} for k, v in kern.items()}
     kernels["deposit_binning"] = {"ms_per_step": ms_sort}
-    kernels["note"] = ("rounds alternate between two lanes: the trace of round i+1 (lane stream) overlaps the gather of round i "
+    kernels["note"] = ("rounds rotate over three lanes: the traces of rounds i+1, i+2 (lane streams) overlap the gather of round i "
                        "(main stream); per-kernel ms are event spans on their own stream and sum to more than ms_per_step")
 
     # ---- Bezier ray-patch intersections per second (metric M2), device-resident microbench
