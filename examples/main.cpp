@@ -33,6 +33,7 @@ int main()
 	r2.cnt = env_int("SPPM_CNT", 10);
 	r2.onetime = env_int("SPPM_ONETIME", 100000);
 	if (std::getenv("SPPM_JITTER")) r2.jitter = std::atof(std::getenv("SPPM_JITTER"));
+	r2.shared_statistics = env_int("SPPM_SHARED", 0) != 0;  // SPPM proper instead of the average of PPM renders
 	r2.render(scene, camera);
 
 	double sum = 0;

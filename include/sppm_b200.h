@@ -204,6 +204,24 @@ int sppm_resolve(sppm_ctx* ctx, int32_t cnt, int32_t onetime, double* film_hw3);
  * bgr[h-1-i][j][k] = toInt(film[i][j][k] / div).  All host buffers. */
 int sppm_tonemap(sppm_ctx* ctx, const double* film_hw3, int32_t w, int32_t h, double div, uint8_t* bgr_hw3);
 
+/* ---- shared statistics across eye passes ------------------------------------
+ * The reference averages independent PPM renders: every RayTracer::render restarts from
+ * R2 = 2 and its HitPoint::update is a no-op (Raytracer.h:69-79, 429-458; README.md:9-17 names
+ * SPPM).  These entry points keep ONE set of per-pixel statistics (R2, N, tau) while the camera
+ * jitters between eye passes (Hachisuka & Jensen 2009):
+ *   N' = N + alpha M,  R2' = R2 (N + alpha M)/(N + M),  tau' = (tau + Phi) R2'/R2,
+ *   film = tau / (PI R2 photons_emitted).
+ * Per pass: sppm_eye_pass, sppm_build_index, sppm_shared_load, photon rounds with
+ * update_mode = REFERENCE (sppm_photon_pass / sppm_allreduce / sppm_update), sppm_shared_fold. */
+int sppm_shared_begin(sppm_ctx* ctx, int32_t w, int32_t h);
+/* Every hit point of the current map takes the radius of its pixel; its own counters restart. */
+int sppm_shared_load(sppm_ctx* ctx);
+/* Fold the pass into the pixels: M = sum newN, Phi = sum tao over the pixel's hit points. */
+int sppm_shared_fold(sppm_ctx* ctx, uint64_t photons_emitted);
+int sppm_shared_resolve(sppm_ctx* ctx, double* film_hw3);
+/* Test hook: r2, n = double[h][w]; tau3 = double[3][h][w]; any may be NULL. */
+int sppm_shared_export(sppm_ctx* ctx, double* r2_hw, double* n_hw, double* tau3, uint64_t* photons_emitted);
+
 /* ---- multi-GPU: one context per rank, NCCL found with dlopen ------------------- */
 int sppm_comm_unique_id(void* id128);                         /* ncclGetUniqueId */
 int sppm_comm_init_rank(sppm_ctx* ctx, int rank, int nranks, const void* id128);

@@ -268,6 +268,25 @@ class Oracle:
     def update(self, mode, alpha, newN, N, r2, tao):
         self.lib.orc_update(newN.shape[0], mode, alpha, _p(newN), _p(N), _p(r2), _p(tao))
 
+    @staticmethod
+    def shared_fold(r2, n, tau, pix, newN, tao, alpha):
+        """Per-pixel SPPM statistics update (Hachisuka & Jensen 2009, eq. 9-12; the estimator the
+        reference's README.md:9-17 names but Raytracer.h:69-79,429-458 does not implement):
+        M = sum newN, Phi = sum tao over the pixel's hit points; N' = N + alpha M;
+        R2' = R2 (N + alpha M)/(N + M); tau' = (tau + Phi) R2'/R2.  In place on r2, n [h,w], tau [h,w,3]."""
+        h, w = r2.shape
+        m = np.zeros((h, w), dtype=np.int64)
+        phi = np.zeros((h, w, 3))
+        np.add.at(m, (pix[:, 0], pix[:, 1]), newN)
+        np.add.at(phi, (pix[:, 0], pix[:, 1]), tao)
+        hit = m > 0
+        n1 = n + alpha * m
+        k = np.where(hit, n1 / np.where(hit, n + m, 1.0), 1.0)
+        n[...] = np.where(hit, n1, n)
+        r2 *= k
+        tau[...] = np.where(hit[..., None], (tau + phi) * k[..., None], tau)
+        return m, phi
+
     def resolve(self, pix, r2, tao, cnt, onetime, w, h):
         film = np.zeros((h, w, 3))
         pix = np.ascontiguousarray(pix, dtype=np.int32)

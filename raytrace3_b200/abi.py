@@ -107,6 +107,11 @@ PROTOTYPES = {
     "sppm_update": (C.c_int, [VP]),
     "sppm_resolve": (C.c_int, [VP, I32, I32, VP]),
     "sppm_tonemap": (C.c_int, [VP, VP, I32, I32, DBL, VP]),
+    "sppm_shared_begin": (C.c_int, [VP, I32, I32]),
+    "sppm_shared_load": (C.c_int, [VP]),
+    "sppm_shared_fold": (C.c_int, [VP, U64]),
+    "sppm_shared_resolve": (C.c_int, [VP, VP]),
+    "sppm_shared_export": (C.c_int, [VP, VP, VP, VP, C.POINTER(U64)]),
     "sppm_comm_unique_id": (C.c_int, [VP]),
     "sppm_comm_init_rank": (C.c_int, [VP, C.c_int, C.c_int, VP]),
     "sppm_accum_device_ptrs": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(I64)]),

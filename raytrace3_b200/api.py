@@ -107,6 +107,32 @@ class Context:
         self._ck(self.lib.sppm_resolve(self.h, cnt, onetime, film.ctypes.data), "sppm_resolve")
         return film
 
+    # ---- shared statistics across eye passes
+    def shared_begin(self, w: int, h: int):
+        self._ck(self.lib.sppm_shared_begin(self.h, w, h), "sppm_shared_begin")
+        self._shared_wh = (w, h)
+
+    def shared_load(self):
+        self._ck(self.lib.sppm_shared_load(self.h), "sppm_shared_load")
+
+    def shared_fold(self, photons_emitted: int):
+        self._ck(self.lib.sppm_shared_fold(self.h, int(photons_emitted)), "sppm_shared_fold")
+
+    def shared_resolve(self, out: np.ndarray | None = None) -> np.ndarray:
+        w, h = self._shared_wh
+        film = out if out is not None else np.empty((h, w, 3), dtype=np.float64)
+        assert film.flags.c_contiguous and film.dtype == np.float64 and film.shape == (h, w, 3)
+        self._ck(self.lib.sppm_shared_resolve(self.h, film.ctypes.data), "sppm_shared_resolve")
+        return film
+
+    def shared_export(self) -> dict:
+        w, h = self._shared_wh
+        r2, n, tau = np.empty((h, w)), np.empty((h, w)), np.empty((3, h, w))
+        ph = C.c_uint64()
+        self._ck(self.lib.sppm_shared_export(self.h, r2.ctypes.data, n.ctypes.data, tau.ctypes.data, C.byref(ph)),
+                 "sppm_shared_export")
+        return dict(r2=r2, n=n, tau=np.ascontiguousarray(tau.transpose(1, 2, 0)), photons=ph.value)
+
     def tonemap(self, film: np.ndarray, div: float) -> np.ndarray:
         film = _f64(film)
         h, w = film.shape[:2]
@@ -292,10 +318,16 @@ class SPPMRayTracer:
         self.onetime = 100
         self.jitter = 0.00015
         self.image = None
+        # False: the reference's estimator, the average of independent PPM renders
+        # (Raytracer.h:429-458).  True: one set of per-pixel statistics shared by all eye passes
+        # (SPPM proper); camera.pic then holds the estimate itself.
+        self.shared_statistics = False
 
     def render(self, scene: Scene, camera: Camera):
         from .rng import unit_rand_vec, P_JITTER
         seed = self.ctx.params.seed
+        if self.shared_statistics:
+            return self._render_shared(scene, camera)
         for i in range(self.sppmtime):
             for j in range(self.replicas):
                 c = camera.copy()
@@ -309,4 +341,30 @@ class SPPMRayTracer:
                 rt.render()
                 camera.pic += c.pic  # Raytracer.h:449-458
             self.image = self.ctx.tonemap(camera.pic, (i + 1) * float(self.replicas))  # Raytracer.h:460-470
+        return self.image
+
+    def _render_shared(self, scene: Scene, camera: Camera):
+        from .rng import unit_rand_vec, P_JITTER
+        ctx, seed = self.ctx, self.ctx.params.seed
+        if ctx.params.update_mode != abi.SPPM_UPDATE_REFERENCE:
+            raise ValueError("shared statistics: the per-hit-point update must stay the reference's (update_mode REFERENCE)")
+        ctx.upload_scene(scene)
+        ctx.shared_begin(camera.w, camera.h)
+        n_light = len(scene.plvec)
+        for i in range(self.sppmtime):
+            for j in range(self.replicas):
+                c = camera.copy()
+                if self.jitter:
+                    c.MoveTo(camera.pos + self.jitter * unit_rand_vec(seed, i, j, P_JITTER))
+                c.lookAt(camera.look, 1.)
+                pass_base = i * self.replicas + j
+                ctx.eye_pass(c, pass_base)
+                ctx.build_index()
+                ctx.shared_load()
+                for k in range(self.cnt):
+                    ctx.photon_pass(0, self.onetime, pass_base * self.cnt + k)
+                    ctx.update()
+                ctx.shared_fold(self.cnt * self.onetime * n_light)
+            ctx.shared_resolve(out=camera.pic)
+            self.image = ctx.tonemap(camera.pic, 1.0)
         return self.image

@@ -292,7 +292,7 @@ void sppm_ctx_destroy(sppm_ctx* c) {
   }
   if (c->ev_setup) cudaEventDestroy(c->ev_setup);
   free_scene(c);
-  DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->units, &c->item_parts, &c->item_off, &c->items, &c->dep_key, &c->dep_key2,
+  DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->units, &c->item_parts, &c->item_off, &c->items, &c->px_store, &c->dep_key, &c->dep_key2,
                     &c->dep_idx, &c->dep_idx2, &c->scan_scratch, &c->cub_tmp, &c->dev_scalars, &c->counters, &c->film, &c->scratch};
   for (DevBuf* d : bufs) dev_free(*d);
   for (int i = 0; i < 8; i++)
@@ -575,6 +575,53 @@ int sppm_resolve(sppm_ctx* c, int32_t cnt, int32_t onetime, double* film_hw3) {
   c->host_counters.ms_resolve = ms;
   fold_timings(c);
   return check_overflow(c);
+}
+
+int sppm_shared_begin(sppm_ctx* c, int32_t w, int32_t h) {
+  if (!c || w <= 0 || h <= 0) return SPPM_ERR_INVALID;
+  Bind b(c);
+  CU(c, shared_begin(c, w, h));
+  return SPPM_OK;
+}
+
+int sppm_shared_load(sppm_ctx* c) {
+  if (!c) return SPPM_ERR_INVALID;
+  if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
+  if (!c->px_store.p || c->px_w != c->film_w || c->px_h != c->film_h)
+    return fail(c, SPPM_ERR_INVALID, "sppm_shared_begin must be called with the film size of the eye pass");
+  Bind b(c);
+  CU(c, shared_load(c));
+  CU(c, mark_setup(c));  // the lanes read the hit-point radii
+  return SPPM_OK;
+}
+
+int sppm_shared_fold(sppm_ctx* c, uint64_t photons_emitted) {
+  if (!c) return SPPM_ERR_INVALID;
+  if (!c->index_ok || !c->px_store.p) return fail(c, SPPM_ERR_INVALID, "sppm_shared_load must be called first");
+  Bind b(c);
+  CU(c, shared_fold(c));
+  c->px_photons += photons_emitted;
+  return SPPM_OK;
+}
+
+int sppm_shared_resolve(sppm_ctx* c, double* film_hw3) {
+  if (!c || !film_hw3) return SPPM_ERR_INVALID;
+  if (!c->px_store.p) return fail(c, SPPM_ERR_INVALID, "sppm_shared_begin must be called first");
+  Bind b(c);
+  CU(c, shared_resolve(c));
+  CU(c, cudaMemcpyAsync(film_hw3, c->film.p, (size_t)c->px_w * c->px_h * 24, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  fold_timings(c);
+  return check_overflow(c);
+}
+
+int sppm_shared_export(sppm_ctx* c, double* r2_hw, double* n_hw, double* tau3, uint64_t* photons_emitted) {
+  if (!c) return SPPM_ERR_INVALID;
+  if (!c->px_store.p) return fail(c, SPPM_ERR_INVALID, "sppm_shared_begin must be called first");
+  Bind b(c);
+  CU(c, shared_export(c, r2_hw, n_hw, tau3));
+  if (photons_emitted) *photons_emitted = c->px_photons;
+  return SPPM_OK;
 }
 
 int sppm_tonemap(sppm_ctx* c, const double* film_hw3, int32_t w, int32_t h, double div, uint8_t* bgr_hw3) {

@@ -136,6 +136,10 @@ struct sppm_ctx {
   sppm::DevBuf counters;      // DevCounters
   sppm::DevBuf film;          // double[h][w][3]
   sppm::DevBuf scratch;
+  // shared statistics across eye passes: per pixel R2, N, tau[3], per-pass M, Phi[3]
+  sppm::DevBuf px_store;
+  int px_w = 0, px_h = 0;
+  uint64_t px_photons = 0;   // photons emitted into the shared statistics so far
   bool keep_all_deposits = false;
   SppmCounters host_counters{};
   cudaEvent_t ev[8] = {};  // 4/5 generic, 6/7 user stopwatch
@@ -167,6 +171,11 @@ cudaError_t bin_deposits(sppm_ctx* c, Lane& L, cudaStream_t st);
 cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cudaEvent_t ev_gather_end);
 cudaError_t launch_update(sppm_ctx* c);
 cudaError_t launch_resolve(sppm_ctx* c, int cnt, int onetime);
+cudaError_t shared_begin(sppm_ctx* c, int w, int h);
+cudaError_t shared_load(sppm_ctx* c);
+cudaError_t shared_fold(sppm_ctx* c);
+cudaError_t shared_resolve(sppm_ctx* c);
+cudaError_t shared_export(sppm_ctx* c, double* r2, double* n, double* tau3);
 cudaError_t dev_reserve(DevBuf& b, size_t bytes);
 void dev_free(DevBuf& b);
 }  // namespace sppm

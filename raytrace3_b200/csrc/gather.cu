@@ -1008,6 +1008,84 @@ __global__ void resolve_kernel(HpSoA s, long long n, int cnt, int onetime, int w
   atomicAdd(px + 2, s.tao[2 * n + i] * sc);
 }
 
+// ---- shared statistics across eye passes -------------------------------------
+// The reference averages independent PPM renders (every RayTracer::render starts from R2 = 2,
+// Raytracer.h:429-458; its update() is a no-op, Q1).  Stochastic progressive photon mapping
+// proper (Hachisuka & Jensen 2009, the method the reference's README names) keeps ONE set of
+// statistics per pixel while the measurement point moves with the jittered camera:
+//   N' = N + alpha M,   R2' = R2 (N + alpha M) / (N + M),   tau' = (tau + Phi) R2' / R2
+// with M / Phi the photons / weighted flux gathered by the pixel's hit points in the pass, and
+// L = tau / (PI R2 N_emitted).  Layout of px_store: r2[np] n[np] tau[3][np] phi[3][np] (f64) m[np] (i32).
+struct PxStats {
+  double *r2, *n, *tau, *phi;
+  int32_t* m;
+  long long np;
+};
+__global__ void shared_init_kernel(PxStats p, double r2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.np) return;
+  p.r2[i] = r2;
+  p.n[i] = 0;
+  p.m[i] = 0;
+  for (int k = 0; k < 3; k++) {
+    p.tau[k * p.np + i] = 0;
+    p.phi[k * p.np + i] = 0;
+  }
+}
+// every hit point measures with the radius its pixel has reached; its own N / newN / tao restart
+__global__ void shared_load_kernel(HpSoA s, long long n, PxStats p, int w) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long px = (long long)s.row[i] * w + s.col[i];
+  s.r2[i] = p.r2[px];
+  s.N[i] = 0;
+  s.newN[i] = 0;
+  s.tao[i] = 0; s.tao[n + i] = 0; s.tao[2 * n + i] = 0;
+}
+__global__ void shared_accum_kernel(HpSoA s, long long n, PxStats p, int w) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int m = s.newN[i];
+  if (m <= 0) return;
+  const long long px = (long long)s.row[i] * w + s.col[i];
+  atomicAdd(p.m + px, m);
+  atomicAdd(p.phi + px, s.tao[i]);
+  atomicAdd(p.phi + p.np + px, s.tao[n + i]);
+  atomicAdd(p.phi + 2 * p.np + px, s.tao[2 * n + i]);
+}
+__global__ void shared_update_kernel(PxStats p, double alpha) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.np) return;
+  const int m = p.m[i];
+  if (m <= 0) return;
+  const double n0 = p.n[i], n1 = n0 + alpha * m;
+  const double k = n1 / (n0 + m);
+  p.n[i] = n1;
+  p.r2[i] *= k;
+  for (int c = 0; c < 3; c++) {
+    p.tau[c * p.np + i] = (p.tau[c * p.np + i] + p.phi[c * p.np + i]) * k;
+    p.phi[c * p.np + i] = 0;
+  }
+  p.m[i] = 0;
+}
+__global__ void shared_resolve_kernel(PxStats p, double photons, double* film) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.np) return;
+  const double sc = photons > 0 ? 1.0 / SPPM_PI / (p.r2[i] * photons) : 0.0;
+  for (int c = 0; c < 3; c++) film[i * 3 + c] = p.tau[c * p.np + i] * sc;
+}
+inline PxStats px_view(sppm_ctx* c) {
+  PxStats p;
+  p.np = (long long)c->px_w * c->px_h;
+  double* d = (double*)c->px_store.p;
+  p.r2 = d;
+  p.n = d + p.np;
+  p.tau = d + 2 * p.np;
+  p.phi = d + 5 * p.np;
+  p.m = (int32_t*)(d + 8 * p.np);
+  return p;
+}
+
 inline int bits_for(uint64_t max_value) {
   int b = 1;
   while (b < 32 && (max_value >> b)) b++;
@@ -1303,6 +1381,44 @@ cudaError_t launch_resolve(sppm_ctx* c, int cnt, int onetime) {
   resolve_kernel<<<nblk(c->n_hp), TPB, 0, c->stream>>>(c->soa, c->n_hp, cnt, onetime, c->film_w, (double*)c->film.p);
   c->host_counters.launches++;
   return cudaGetLastError();
+}
+
+cudaError_t shared_begin(sppm_ctx* c, int w, int h) {
+  c->px_w = w;
+  c->px_h = h;
+  c->px_photons = 0;
+  const size_t np = (size_t)w * h;
+  CK(dev_reserve(c->px_store, np * (8 * 8 + 4) + 64));
+  shared_init_kernel<<<nblk((long long)np), TPB, 0, c->stream>>>(px_view(c), c->prm.init_r2);
+  c->host_counters.launches++;
+  return cudaGetLastError();
+}
+cudaError_t shared_load(sppm_ctx* c) {
+  if (c->n_hp == 0) return cudaSuccess;
+  shared_load_kernel<<<nblk(c->n_hp), TPB, 0, c->stream>>>(c->soa, c->n_hp, px_view(c), c->px_w);
+  c->host_counters.launches++;
+  return cudaGetLastError();
+}
+cudaError_t shared_fold(sppm_ctx* c) {
+  if (c->n_hp > 0) shared_accum_kernel<<<nblk(c->n_hp), TPB, 0, c->stream>>>(c->soa, c->n_hp, px_view(c), c->px_w);
+  shared_update_kernel<<<nblk((long long)c->px_w * c->px_h), TPB, 0, c->stream>>>(px_view(c), c->prm.alpha);
+  c->host_counters.launches += 2;
+  return cudaGetLastError();
+}
+cudaError_t shared_resolve(sppm_ctx* c) {
+  const size_t bytes = (size_t)c->px_w * c->px_h * 3 * 8;
+  CK(dev_reserve(c->film, bytes));
+  shared_resolve_kernel<<<nblk((long long)c->px_w * c->px_h), TPB, 0, c->stream>>>(px_view(c), (double)c->px_photons, (double*)c->film.p);
+  c->host_counters.launches++;
+  return cudaGetLastError();
+}
+cudaError_t shared_export(sppm_ctx* c, double* r2, double* n, double* tau3) {
+  const PxStats p = px_view(c);
+  const size_t np = (size_t)p.np;
+  if (r2) CK(cudaMemcpyAsync(r2, p.r2, np * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (n) CK(cudaMemcpyAsync(n, p.n, np * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (tau3) CK(cudaMemcpyAsync(tau3, p.tau, 3 * np * 8, cudaMemcpyDeviceToHost, c->stream));  // [3][h][w] planes
+  return cudaStreamSynchronize(c->stream);
 }
 
 }  // namespace sppm

@@ -132,9 +132,17 @@ class SPPMRayTracer {  // Raytracer.h:421-477
   std::string out_prefix = "aaanew";
   std::vector<uchar> image;   // last tone-mapped image, BGR, row-flipped as the reference writes it
   std::vector<double> film;   // accumulated film [h][w][3] (camera is passed by value, as upstream)
+  // false: the reference's estimator, the average of independent PPM renders (Raytracer.h:429-458).
+  // true: one set of per-pixel statistics (R2, N, tau) shared by all eye passes while the camera
+  // jitters -- SPPM proper (sppm_shared_*); runs on devices[0].
+  bool shared_statistics = false;
 
   void render(Scene scene, Camera camera) {
     if (devices.empty()) devices.push_back(std::getenv("SPPM_DEVICE") ? std::atoi(std::getenv("SPPM_DEVICE")) : 0);
+    if (shared_statistics) {
+      renderShared(scene, camera);
+      return;
+    }
     const int ndev = (int)devices.size();
     std::vector<sppm_ctx*> ctxs(ndev);
     for (int d = 0; d < ndev; d++) ctxs[d] = sppm_host::create_ctx(devices[d]);
@@ -176,6 +184,43 @@ class SPPMRayTracer {  // Raytracer.h:421-477
   }
 
  private:
+  void renderShared(Scene& scene, Camera& camera) {
+    sppm_ctx* ctx = sppm_host::create_ctx(devices[0]);
+    SppmParams prm;
+    sppm_default_params(&prm);
+    sppm_host::check(sppm_set_params(ctx, &prm), ctx, "sppm_set_params");
+    sppm_host::FlatScene fs;
+    scene.flatten(fs);
+    SppmSceneDesc d = fs.desc();
+    sppm_host::check(sppm_scene_upload(ctx, &d), ctx, "sppm_scene_upload");
+    sppm_host::check(sppm_shared_begin(ctx, camera.w, camera.h), ctx, "sppm_shared_begin");
+    film.assign((size_t)camera.w * camera.h * 3, 0.0);
+    image.resize(film.size());
+    for (int i = 0; i < sppmtime; i++) {
+      for (int j = 0; j < replicas; j++) {
+        Camera c = camera;
+        c.MoveTo(camera.pos + jitter * Vec3::GetUnitRandVec());
+        c.lookAt(camera.look, 1.);
+        SppmCameraDesc cd = c.desc();
+        const uint64_t pass_base = (uint64_t)i * replicas + j;
+        int64_t n = 0;
+        sppm_host::check(sppm_eye_pass(ctx, &cd, pass_base, &n), ctx, "sppm_eye_pass");
+        sppm_host::check(sppm_build_index(ctx), ctx, "sppm_build_index");
+        sppm_host::check(sppm_shared_load(ctx), ctx, "sppm_shared_load");
+        for (int k = 0; k < cnt; k++) {
+          sppm_host::check(sppm_photon_pass(ctx, 0, (uint64_t)onetime, pass_base * (uint64_t)cnt + k), ctx, "sppm_photon_pass");
+          sppm_host::check(sppm_update(ctx), ctx, "sppm_update");
+        }
+        sppm_host::check(sppm_shared_fold(ctx, (uint64_t)cnt * onetime * scene.plvec.size()), ctx, "sppm_shared_fold");
+      }
+      sppm_host::check(sppm_shared_resolve(ctx, film.data()), ctx, "sppm_shared_resolve");
+      sppm_host::check(sppm_tonemap(ctx, film.data(), camera.w, camera.h, 1.0, image.data()), ctx, "sppm_tonemap");
+      std::string pic = out_prefix + std::to_string(i / 10) + ".ppm";
+      std::cerr << "save:" << pic << std::endl;
+      savePPM(pic, camera.w, camera.h);
+    }
+    sppm_ctx_destroy(ctx);
+  }
   void savePPM(const std::string& path, int w, int h) const {
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) return;

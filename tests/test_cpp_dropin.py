@@ -49,3 +49,11 @@ def test_cpp_render_matches_python_mirror(tmp_path, ctx):
     assert film_sum > 0
     np.testing.assert_allclose(film_sum, cam.pic.sum(), rtol=1e-9)
     assert (tmp_path / "aaanew0.ppm").exists()
+    # shared per-pixel statistics across the 4 eye passes: C++ mirror == Python mirror
+    r = subprocess.run([exe], capture_output=True, text=True, env=dict(env, SPPM_SHARED="1"), cwd=tmp_path, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    film_sum = float([l for l in r.stdout.splitlines() if l.startswith("film sum")][-1].split()[-1])
+    sp.shared_statistics = True
+    cam = reference_camera(48, 36)
+    sp.render(sc, cam)
+    np.testing.assert_allclose(film_sum, cam.pic.sum(), rtol=1e-9)

@@ -453,6 +453,56 @@ def test_fast_math_directions_match_exact(ctx):
     assert np.median(np.abs(d0["x"][idx0][first] - d1["x"][idx1][first]).max(axis=1)) < 1e-12
 
 
+def test_shared_statistics_across_eye_passes(ctx, oracle):
+    """per-pixel R2 / N / tau persist while the camera jitters.  (a) After one eye
+    pass the estimate equals the reference's film (N = 0: R2' = alpha R2, tau' = alpha Phi, so
+    tau'/(PI R2' Ne) = Phi/(PI R2 Ne) = Raytracer.h:288-293).  (b) Over three jittered passes
+    the device statistics follow the restated update fed with the exported per-pass hit-point
+    counters.  (c) Radii only shrink and every hit point measures with its pixel's radius."""
+    from raytrace3_b200.rng import unit_rand_vec, P_JITTER
+    sc = make_scene("reference", textures=None)
+    cam0 = reference_camera(64, 48)
+    prm = _params(newton_mode=abi.SPPM_NEWTON_FAST)
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    w, h, onetime, rounds = 64, 48, 20000, 2
+    ctx.shared_begin(w, h)
+    r2 = np.full((h, w), prm.init_r2)
+    n = np.zeros((h, w))
+    tau = np.zeros((h, w, 3))
+    emitted = 0
+    for p in range(3):
+        cam = cam0.copy()
+        cam.MoveTo(cam0.pos + 0.00015 * unit_rand_vec(prm.seed, 0, p, P_JITTER))
+        cam.lookAt(cam0.look, 1.)
+        nh = ctx.eye_pass(cam, p)
+        ctx.build_index()
+        ctx.shared_load()
+        hp = ctx.export_hitpoints()
+        np.testing.assert_array_equal(ctx.export_stats(nh)["r2"], r2[hp["pix"][:, 0], hp["pix"][:, 1]])   # (c)
+        for k in range(rounds):
+            ctx.photon_pass(0, onetime, p * rounds + k)
+            ctx.update()
+        st = ctx.export_stats(nh)
+        if p == 0:
+            film_ref = ctx.resolve(rounds, onetime, w, h)
+        ctx.shared_fold(rounds * onetime)
+        emitted += rounds * onetime
+        r2_before = r2.copy()
+        oracle.shared_fold(r2, n, tau, hp["pix"], st["newN"], st["tao"], prm.alpha)
+        assert np.all(r2 <= r2_before)
+        got = ctx.shared_export()
+        assert got["photons"] == emitted
+        np.testing.assert_allclose(got["r2"], r2, rtol=1e-13)
+        np.testing.assert_allclose(got["n"], n, rtol=1e-13)
+        np.testing.assert_allclose(got["tau"], tau, rtol=1e-11, atol=1e-300)
+        film = ctx.shared_resolve()
+        if p == 0:
+            np.testing.assert_allclose(film, film_ref, rtol=1e-12, atol=1e-300)        # (a)
+        np.testing.assert_allclose(film, tau / (3.1415926 * r2[..., None] * emitted), rtol=1e-11, atol=1e-300)
+    assert (n > 0).mean() > 0.5 and r2.min() < prm.init_r2 * prm.alpha
+
+
 def test_gpu_matches_the_reference_itself(ctx, oracle):
     """CUDA NearCollide against the reference's OWN compiled code (oracle/_ref, built from
     /root/reference/raytracer/*.h; the oracle only supplies the draw log that tells which
