@@ -222,6 +222,16 @@ int sppm_shared_resolve(sppm_ctx* ctx, double* film_hw3);
 /* Test hook: r2, n = double[h][w]; tau3 = double[3][h][w]; any may be NULL. */
 int sppm_shared_export(sppm_ctx* ctx, double* r2_hw, double* n_hw, double* tau3, uint64_t* photons_emitted);
 
+/* ---- host image I/O on the GPU ------------------------------------------------
+ * Replaces cv::imread in the Texture constructor (Element.h:47-59) and cv::imwrite of the
+ * tone-mapped film (Raytracer.h:474) by nvJPEG (dlopen).  Pixels are interleaved B,G,R bytes,
+ * row-major, as cv::Mat / SppmTexture hold them.  All buffers are host memory. */
+int sppm_jpeg_info(sppm_ctx* ctx, const uint8_t* jpeg, int64_t n_bytes, int32_t* rows, int32_t* cols);
+int sppm_jpeg_decode(sppm_ctx* ctx, const uint8_t* jpeg, int64_t n_bytes, int32_t rows, int32_t cols, uint8_t* bgr8);
+/* out may be NULL to query the size; n_bytes returns the length of the JPEG stream. */
+int sppm_jpeg_encode(sppm_ctx* ctx, const uint8_t* bgr8, int32_t rows, int32_t cols, int32_t quality,
+                     uint8_t* out, int64_t cap, int64_t* n_bytes);
+
 /* ---- multi-GPU: one context per rank, NCCL found with dlopen ------------------- */
 int sppm_comm_unique_id(void* id128);                         /* ncclGetUniqueId */
 int sppm_comm_init_rank(sppm_ctx* ctx, int rank, int nranks, const void* id128);

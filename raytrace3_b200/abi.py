@@ -112,6 +112,9 @@ PROTOTYPES = {
     "sppm_shared_fold": (C.c_int, [VP, U64]),
     "sppm_shared_resolve": (C.c_int, [VP, VP]),
     "sppm_shared_export": (C.c_int, [VP, VP, VP, VP, C.POINTER(U64)]),
+    "sppm_jpeg_info": (C.c_int, [VP, VP, I64, C.POINTER(I32), C.POINTER(I32)]),
+    "sppm_jpeg_decode": (C.c_int, [VP, VP, I64, I32, I32, VP]),
+    "sppm_jpeg_encode": (C.c_int, [VP, VP, I32, I32, I32, VP, I64, C.POINTER(I64)]),
     "sppm_comm_unique_id": (C.c_int, [VP]),
     "sppm_comm_init_rank": (C.c_int, [VP, C.c_int, C.c_int, VP]),
     "sppm_accum_device_ptrs": (C.c_int, [VP, C.POINTER(VP), C.POINTER(VP), C.POINTER(I64)]),

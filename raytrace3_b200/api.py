@@ -133,6 +133,25 @@ class Context:
                  "sppm_shared_export")
         return dict(r2=r2, n=n, tau=np.ascontiguousarray(tau.transpose(1, 2, 0)), photons=ph.value)
 
+    # ---- JPEG decode / encode on the device (replaces cv::imread / cv::imwrite)
+    def jpeg_decode(self, data: bytes) -> np.ndarray:
+        buf = np.frombuffer(data, dtype=np.uint8)
+        rows, cols = C.c_int32(), C.c_int32()
+        self._ck(self.lib.sppm_jpeg_info(self.h, buf.ctypes.data, buf.size, C.byref(rows), C.byref(cols)), "sppm_jpeg_info")
+        out = np.empty((rows.value, cols.value, 3), dtype=np.uint8)
+        self._ck(self.lib.sppm_jpeg_decode(self.h, buf.ctypes.data, buf.size, rows.value, cols.value, out.ctypes.data), "sppm_jpeg_decode")
+        return out
+
+    def jpeg_encode(self, bgr8: np.ndarray, quality: int = 95) -> bytes:
+        img = np.ascontiguousarray(bgr8, dtype=np.uint8)
+        assert img.ndim == 3 and img.shape[2] == 3
+        n = C.c_int64()
+        self._ck(self.lib.sppm_jpeg_encode(self.h, img.ctypes.data, img.shape[0], img.shape[1], quality, None, 0, C.byref(n)), "sppm_jpeg_encode")
+        out = np.empty(n.value + 4096, dtype=np.uint8)
+        self._ck(self.lib.sppm_jpeg_encode(self.h, img.ctypes.data, img.shape[0], img.shape[1], quality, out.ctypes.data, out.size, C.byref(n)),
+                 "sppm_jpeg_encode")
+        return out[:n.value].tobytes()
+
     def tonemap(self, film: np.ndarray, div: float) -> np.ndarray:
         film = _f64(film)
         h, w = film.shape[:2]

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
 LIBDIR = os.path.join(ROOT, "lib")
 LIB = os.path.join(LIBDIR, "libsppm_b200.so")
-SOURCES = ["abi.cu", "trace.cu", "wavefront.cu", "gather.cu"]
+SOURCES = ["abi.cu", "trace.cu", "wavefront.cu", "gather.cu", "imageio.cu"]
 HEADERS = ["ctx.h", "scene.cuh", "device_math.cuh", os.path.join("..", "..", "include", "sppm_b200.h")]
 
 NVCC_FLAGS = [

@@ -14,6 +14,7 @@
 // Bit-exactness: the acceptance predicate is evaluated in FP64 with the reference's
 // operation order and no FMA (the library is built with -fmad=false), so newN is exact.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -1256,7 +1257,7 @@ cudaError_t build_index(sppm_ctx* c) {
     int32_t* uoff = (int32_t*)c->dep_key2.p;       // [n_runs + 1]
     int32_t* d_nr = d_nruns + 1;
     run_flag_kernel<<<nblk(n_occ), TPB, 0, st>>>((const uint32_t*)c->occ_cell.p, n_occ, g.dim[0], flag);
-    cub::CountingInputIterator<int32_t> iota(0);
+    thrust::counting_iterator<int32_t> iota(0);
     CK(cub::DeviceSelect::Flagged(nullptr, tmp, iota, flag, run_first, d_nr, n_occ, st));
     CK(dev_reserve(c->cub_tmp, tmp));
     CK(cub::DeviceSelect::Flagged(c->cub_tmp.p, tmp, iota, flag, run_first, d_nr, n_occ, st));

@@ -503,6 +503,36 @@ def test_shared_statistics_across_eye_passes(ctx, oracle):
     assert (n > 0).mean() > 0.5 and r2.min() < prm.init_r2 * prm.alpha
 
 
+def test_jpeg_decode_encode_on_device(ctx):
+    """SURVEY 8f-3: nvJPEG replaces cv::imread (Element.h:47-59) / cv::imwrite (Raytracer.h:474).
+    The CPU check is OpenCV's own decoder (the library family the reference uses): interleaved
+    BGR, same size, pixel values equal up to the decoders' IDCT / upsampling rounding."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(5)
+    yy, xx = np.mgrid[0:203, 0:317]
+    img = np.stack([127 + 100 * np.sin(xx / 23.0) * np.cos(yy / 17.0), (xx * 255.0 / 316), 255 - (yy * 255.0 / 202)], axis=2)
+    img = np.clip(img + rng.normal(0, 2, img.shape), 0, 255).astype(np.uint8)
+    # measured on B200 against OpenCV 4.13: 4:4:4 max 4 / mean 0.51; default 4:2:0 (different chroma
+    # upsampling filters) max 6 / mean 0.99
+    for flags, max_tol, mean_tol in (([cv2.IMWRITE_JPEG_QUALITY, 95, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444], 6, 0.8),
+                                     ([cv2.IMWRITE_JPEG_QUALITY, 90], 24, 1.5)):
+        ok, enc = cv2.imencode(".jpg", img, flags)
+        assert ok
+        ref = cv2.imdecode(enc, cv2.IMREAD_COLOR)
+        got = ctx.jpeg_decode(enc.tobytes())
+        assert got.shape == ref.shape == img.shape and got.dtype == np.uint8
+        d = np.abs(got.astype(int) - ref.astype(int))
+        assert d.max() <= max_tol and d.mean() < mean_tol, (d.max(), d.mean())
+    out = ctx.jpeg_encode(img, quality=95)
+    assert out[:2] == b"\xff\xd8" and out[-2:] == b"\xff\xd9"
+    back = cv2.imdecode(np.frombuffer(out, np.uint8), cv2.IMREAD_COLOR)
+    assert back.shape == img.shape
+    mse = np.mean((back.astype(float) - img.astype(float)) ** 2)
+    assert 10 * np.log10(255.0 ** 2 / mse) > 35.0
+    with pytest.raises(Exception):
+        ctx.jpeg_decode(b"not a jpeg at all")
+
+
 def test_gpu_matches_the_reference_itself(ctx, oracle):
     """CUDA NearCollide against the reference's OWN compiled code (oracle/_ref, built from
     /root/reference/raytracer/*.h; the oracle only supplies the draw log that tells which
