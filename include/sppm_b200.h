@@ -221,6 +221,8 @@ int sppm_shared_fold(sppm_ctx* ctx, uint64_t photons_emitted);
 int sppm_shared_resolve(sppm_ctx* ctx, double* film_hw3);
 /* Test hook: r2, n = double[h][w]; tau3 = double[3][h][w]; any may be NULL. */
 int sppm_shared_export(sppm_ctx* ctx, double* r2_hw, double* n_hw, double* tau3, uint64_t* photons_emitted);
+/* Restore statistics saved by sppm_shared_export (film checkpoint / resume); after sppm_shared_begin. */
+int sppm_shared_import(sppm_ctx* ctx, const double* r2_hw, const double* n_hw, const double* tau3, uint64_t photons_emitted);
 
 /* ---- host image I/O on the GPU ------------------------------------------------
  * Replaces cv::imread in the Texture constructor (Element.h:47-59) and cv::imwrite of the

@@ -112,6 +112,7 @@ PROTOTYPES = {
     "sppm_shared_fold": (C.c_int, [VP, U64]),
     "sppm_shared_resolve": (C.c_int, [VP, VP]),
     "sppm_shared_export": (C.c_int, [VP, VP, VP, VP, C.POINTER(U64)]),
+    "sppm_shared_import": (C.c_int, [VP, VP, VP, VP, U64]),
     "sppm_jpeg_info": (C.c_int, [VP, VP, I64, C.POINTER(I32), C.POINTER(I32)]),
     "sppm_jpeg_decode": (C.c_int, [VP, VP, I64, I32, I32, VP]),
     "sppm_jpeg_encode": (C.c_int, [VP, VP, I32, I32, I32, VP, I64, C.POINTER(I64)]),

@@ -624,6 +624,15 @@ int sppm_shared_export(sppm_ctx* c, double* r2_hw, double* n_hw, double* tau3, u
   return SPPM_OK;
 }
 
+int sppm_shared_import(sppm_ctx* c, const double* r2_hw, const double* n_hw, const double* tau3, uint64_t photons_emitted) {
+  if (!c || !r2_hw || !n_hw || !tau3) return SPPM_ERR_INVALID;
+  if (!c->px_store.p) return fail(c, SPPM_ERR_INVALID, "sppm_shared_begin must be called first");
+  Bind b(c);
+  CU(c, shared_import(c, r2_hw, n_hw, tau3));
+  c->px_photons = photons_emitted;
+  return SPPM_OK;
+}
+
 int sppm_tonemap(sppm_ctx* c, const double* film_hw3, int32_t w, int32_t h, double div, uint8_t* bgr_hw3) {
   if (!c || !film_hw3 || !bgr_hw3 || w <= 0 || h <= 0) return SPPM_ERR_INVALID;
   Bind b(c);

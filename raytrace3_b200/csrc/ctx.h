@@ -176,6 +176,7 @@ cudaError_t shared_load(sppm_ctx* c);
 cudaError_t shared_fold(sppm_ctx* c);
 cudaError_t shared_resolve(sppm_ctx* c);
 cudaError_t shared_export(sppm_ctx* c, double* r2, double* n, double* tau3);
+cudaError_t shared_import(sppm_ctx* c, const double* r2, const double* n, const double* tau3);
 cudaError_t dev_reserve(DevBuf& b, size_t bytes);
 void dev_free(DevBuf& b);
 }  // namespace sppm

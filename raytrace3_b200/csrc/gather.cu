@@ -1422,4 +1422,13 @@ cudaError_t shared_export(sppm_ctx* c, double* r2, double* n, double* tau3) {
   return cudaStreamSynchronize(c->stream);
 }
 
+cudaError_t shared_import(sppm_ctx* c, const double* r2, const double* n, const double* tau3) {
+  const PxStats p = px_view(c);
+  const size_t np = (size_t)p.np;
+  CK(cudaMemcpyAsync(p.r2, r2, np * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(p.n, n, np * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(p.tau, tau3, 3 * np * 8, cudaMemcpyHostToDevice, c->stream));
+  return cudaStreamSynchronize(c->stream);
+}
+
 }  // namespace sppm

@@ -136,6 +136,17 @@ class SPPMRayTracer {  // Raytracer.h:421-477
   // true: one set of per-pixel statistics (R2, N, tau) shared by all eye passes while the camera
   // jitters -- SPPM proper (sppm_shared_*); runs on devices[0].
   bool shared_statistics = false;
+  SppmParams params;                 // arithmetic modes / seed of every RayTracer of the loop
+  std::string format = "ppm";        // "ppm" or "jpg" (nvJPEG, the reference's cv::imwrite target, Raytracer.h:474)
+  int jpeg_quality = 95;
+  // Film checkpoint: every `checkpoint_every` iterations the accumulated film (or
+  // the shared statistics), the iteration count and the jitter generator are written to
+  // `checkpoint_path`; with `resume` the loop continues from such a file.
+  std::string checkpoint_path;
+  int checkpoint_every = 0;
+  bool resume = false;
+
+  SPPMRayTracer() { sppm_default_params(&params); }
 
   void render(Scene scene, Camera camera) {
     if (devices.empty()) devices.push_back(std::getenv("SPPM_DEVICE") ? std::atoi(std::getenv("SPPM_DEVICE")) : 0);
@@ -147,7 +158,15 @@ class SPPMRayTracer {  // Raytracer.h:421-477
     std::vector<sppm_ctx*> ctxs(ndev);
     for (int d = 0; d < ndev; d++) ctxs[d] = sppm_host::create_ctx(devices[d]);
     std::vector<Camera> c(replicas);
-    for (int i = 0; i < sppmtime; i++) {
+    int first = 0;
+    if (resume) {
+      std::vector<double> saved;
+      first = loadCheckpoint(camera.w, camera.h, false, saved, nullptr);
+      for (int i1 = 0; i1 < camera.h; i1++)
+        for (int jj = 0; jj < camera.w; jj++)
+          for (int k = 0; k < 3; k++) camera.pic[i1][jj].val[k] = saved[((size_t)i1 * camera.w + jj) * 3 + k];
+    }
+    for (int i = first; i < sppmtime; i++) {
       for (int j = 0; j < replicas; j++) {
         c[j] = camera;
         c[j].MoveTo(camera.pos + jitter * Vec3::GetUnitRandVec());
@@ -158,6 +177,7 @@ class SPPMRayTracer {  // Raytracer.h:421-477
       for (int d = 0; d < ndev; d++) {
         for (int j = d; j < replicas; j += ndev) {
           RayTracer rt(ctxs[d]);
+          rt.params = params;
           rt.camera = &c[j];
           rt.scene = &scene;
           rt.cnt = cnt;
@@ -176,9 +196,9 @@ class SPPMRayTracer {  // Raytracer.h:421-477
           for (int k = 0; k < 3; k++) film[((size_t)i1 * camera.w + jj) * 3 + k] = camera.pic[i1][jj].val[k];
       image.resize(film.size());
       sppm_host::check(sppm_tonemap(ctxs[0], film.data(), camera.w, camera.h, (i + 1) * (double)replicas, image.data()), ctxs[0], "sppm_tonemap");
-      std::string pic = out_prefix + std::to_string(i / 10) + ".ppm";
-      std::cerr << "save:" << pic << std::endl;
-      savePPM(pic, camera.w, camera.h);
+      saveImage(ctxs[0], i, camera.w, camera.h);
+      if (checkpoint_every > 0 && !checkpoint_path.empty() && (i + 1) % checkpoint_every == 0)
+        saveCheckpoint(camera.w, camera.h, false, i + 1, film, 0);
     }
     for (sppm_ctx* x : ctxs) sppm_ctx_destroy(x);
   }
@@ -186,8 +206,8 @@ class SPPMRayTracer {  // Raytracer.h:421-477
  private:
   void renderShared(Scene& scene, Camera& camera) {
     sppm_ctx* ctx = sppm_host::create_ctx(devices[0]);
-    SppmParams prm;
-    sppm_default_params(&prm);
+    SppmParams prm = params;
+    prm.update_mode = SPPM_UPDATE_REFERENCE;  // the per-hit-point update stays the reference's no-op; the pixels are updated
     sppm_host::check(sppm_set_params(ctx, &prm), ctx, "sppm_set_params");
     sppm_host::FlatScene fs;
     scene.flatten(fs);
@@ -196,7 +216,15 @@ class SPPMRayTracer {  // Raytracer.h:421-477
     sppm_host::check(sppm_shared_begin(ctx, camera.w, camera.h), ctx, "sppm_shared_begin");
     film.assign((size_t)camera.w * camera.h * 3, 0.0);
     image.resize(film.size());
-    for (int i = 0; i < sppmtime; i++) {
+    const size_t np = (size_t)camera.w * camera.h;
+    int first = 0;
+    if (resume) {
+      std::vector<double> st;
+      uint64_t photons = 0;
+      first = loadCheckpoint(camera.w, camera.h, true, st, &photons);
+      sppm_host::check(sppm_shared_import(ctx, st.data(), st.data() + np, st.data() + 2 * np, photons), ctx, "sppm_shared_import");
+    }
+    for (int i = first; i < sppmtime; i++) {
       for (int j = 0; j < replicas; j++) {
         Camera c = camera;
         c.MoveTo(camera.pos + jitter * Vec3::GetUnitRandVec());
@@ -215,11 +243,68 @@ class SPPMRayTracer {  // Raytracer.h:421-477
       }
       sppm_host::check(sppm_shared_resolve(ctx, film.data()), ctx, "sppm_shared_resolve");
       sppm_host::check(sppm_tonemap(ctx, film.data(), camera.w, camera.h, 1.0, image.data()), ctx, "sppm_tonemap");
-      std::string pic = out_prefix + std::to_string(i / 10) + ".ppm";
-      std::cerr << "save:" << pic << std::endl;
-      savePPM(pic, camera.w, camera.h);
+      saveImage(ctx, i, camera.w, camera.h);
+      if (checkpoint_every > 0 && !checkpoint_path.empty() && (i + 1) % checkpoint_every == 0) {
+        std::vector<double> st(5 * np);
+        uint64_t photons = 0;
+        sppm_host::check(sppm_shared_export(ctx, st.data(), st.data() + np, st.data() + 2 * np, &photons), ctx, "sppm_shared_export");
+        saveCheckpoint(camera.w, camera.h, true, i + 1, st, photons);
+      }
     }
     sppm_ctx_destroy(ctx);
+  }
+  // checkpoint file: "SPPMCKP1", w, h, shared, iterations done, photons, jitter generator state, doubles
+  void saveCheckpoint(int w, int h, bool shared, int done, const std::vector<double>& data, uint64_t photons) const {
+    const std::string tmp = checkpoint_path + ".tmp";
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) throw std::runtime_error("checkpoint: cannot write " + tmp);
+    const int64_t hdr[5] = {w, h, shared ? 1 : 0, done, (int64_t)data.size()};
+    const uint64_t extra[2] = {photons, sppm_host::rng_state()};
+    bool ok = std::fwrite("SPPMCKP1", 1, 8, f) == 8 && std::fwrite(hdr, 8, 5, f) == 5 && std::fwrite(extra, 8, 2, f) == 2 &&
+              std::fwrite(data.data(), 8, data.size(), f) == data.size();
+    ok = std::fclose(f) == 0 && ok;
+    if (!ok || std::rename(tmp.c_str(), checkpoint_path.c_str()) != 0) throw std::runtime_error("checkpoint: write failed: " + checkpoint_path);
+  }
+  int loadCheckpoint(int w, int h, bool shared, std::vector<double>& data, uint64_t* photons) const {
+    FILE* f = std::fopen(checkpoint_path.c_str(), "rb");
+    if (!f) throw std::runtime_error("checkpoint: cannot open " + checkpoint_path);
+    char magic[8];
+    int64_t hdr[5];
+    uint64_t extra[2];
+    bool ok = std::fread(magic, 1, 8, f) == 8 && std::string(magic, 8) == "SPPMCKP1" && std::fread(hdr, 8, 5, f) == 5 &&
+              std::fread(extra, 8, 2, f) == 2;
+    if (ok && (hdr[0] != w || hdr[1] != h || hdr[2] != (shared ? 1 : 0))) {
+      std::fclose(f);
+      throw std::runtime_error("checkpoint: film size / estimator differ from this job: " + checkpoint_path);
+    }
+    if (ok) {
+      data.resize((size_t)hdr[4]);
+      ok = std::fread(data.data(), 8, data.size(), f) == data.size();
+    }
+    std::fclose(f);
+    if (!ok) throw std::runtime_error("checkpoint: malformed file " + checkpoint_path);
+    if (photons) *photons = extra[0];
+    sppm_host::rng_state() = extra[1];
+    return (int)hdr[3];
+  }
+  void saveImage(sppm_ctx* ctx, int i, int w, int h) const {
+    if (format == "jpg") {
+      // the tone-mapped image is stored bottom-up BGR (Raytracer.h:462-469); JPEG takes it as it is
+      int64_t n = 0;
+      sppm_host::check(sppm_jpeg_encode(ctx, image.data(), h, w, jpeg_quality, nullptr, 0, &n), ctx, "sppm_jpeg_encode");
+      std::vector<uchar> out((size_t)n + 4096);
+      sppm_host::check(sppm_jpeg_encode(ctx, image.data(), h, w, jpeg_quality, out.data(), (int64_t)out.size(), &n), ctx, "sppm_jpeg_encode");
+      const std::string pic = out_prefix + std::to_string(i / 10) + ".jpg";
+      std::cerr << "save:" << pic << std::endl;
+      FILE* f = std::fopen(pic.c_str(), "wb");
+      if (!f) return;
+      std::fwrite(out.data(), 1, (size_t)n, f);
+      std::fclose(f);
+      return;
+    }
+    const std::string pic = out_prefix + std::to_string(i / 10) + ".ppm";
+    std::cerr << "save:" << pic << std::endl;
+    savePPM(pic, w, h);
   }
   void savePPM(const std::string& path, int w, int h) const {
     FILE* f = std::fopen(path.c_str(), "wb");

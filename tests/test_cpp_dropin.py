@@ -57,3 +57,43 @@ def test_cpp_render_matches_python_mirror(tmp_path, ctx):
     cam = reference_camera(48, 36)
     sp.render(sc, cam)
     np.testing.assert_allclose(film_sum, cam.pic.sum(), rtol=1e-9)
+
+
+@pytest.mark.gpu
+def test_cli_scene_file_checkpoint_resume_and_jpeg(tmp_path, ctx):
+    """examples/sppm_render renders a scene description file (JPEG texture decoded
+    by nvJPEG), resumes from a film checkpoint to exactly the film of an uninterrupted run (both
+    estimators), writes JPEG, and agrees with the Python twin on the same file."""
+    cv2 = pytest.importorskip("cv2")
+    import shutil
+    from raytrace3_b200.scene import Texture, synthetic_texture, teapot_patches, write_bpt
+    from raytrace3_b200.scenefile import load_scene_file, render_job
+    _build()
+    exe = os.path.join(ROOT, "examples", "sppm_render")
+    shutil.copy(os.path.join(ROOT, "examples", "scenes", "reference.scene"), tmp_path / "ref.scene")
+    write_bpt(tmp_path / "teapot.bpt", teapot_patches())
+    ok, enc = cv2.imencode(".jpg", synthetic_texture(120, 160, 4), [cv2.IMWRITE_JPEG_QUALITY, 92])
+    assert ok
+    (tmp_path / "wall.jpg").write_bytes(enc.tobytes())          # timg.jpg / planet.jpg stay absent: untextured
+
+    def run(*opts):
+        r = subprocess.run([exe, "ref.scene", "--size", "48x36", "--replicas", "2", "--rounds", "1", "--photons", "20000", *opts],
+                           capture_output=True, text=True, cwd=tmp_path, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        return [l for l in r.stdout.splitlines() if l.startswith("film sum")][-1].split()[-1]
+
+    for mode in ([], ["--shared"]):
+        straight = run("--passes", "2", *mode)
+        run("--passes", "1", "--checkpoint", "ck.bin", *mode)
+        resumed = run("--passes", "2", "--checkpoint", "ck.bin", "--resume", *mode)
+        assert resumed == straight and float(straight) > 0          # bit-identical film after resume
+    run("--passes", "1", "--format", "jpg", "--out", "shot")
+    img = cv2.imread(str(tmp_path / "shot0.jpg"))
+    assert img is not None and img.shape == (36, 48, 3) and img.mean() > 1
+    # the Python twin on the same file (jitter 0: the two hosts draw their jitter differently)
+    cpp = float(run("--passes", "1", "--jitter", "0"))
+    sc, job = load_scene_file(str(tmp_path / "ref.scene"),
+                              texture_loader=lambda p: Texture(ctx.jpeg_decode(open(p, "rb").read())))
+    job.w, job.h, job.replicas, job.rounds, job.photons, job.passes, job.jitter = 48, 36, 2, 1, 20000, 1, 0.0
+    film, _ = render_job(ctx, sc, job)
+    np.testing.assert_allclose(cpp, film.sum(), rtol=1e-9)
