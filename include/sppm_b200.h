@@ -187,6 +187,14 @@ int sppm_scene_upload(sppm_ctx* ctx, const SppmSceneDesc* scene);
 /* ---- the render path ---------------------------------------------------------- */
 /* RayTracer::GetHitPoint + ViewTrace (Raytracer.h:102-116, 296-357). */
 int sppm_eye_pass(sppm_ctx* ctx, const SppmCameraDesc* cam, uint64_t pass_id, int64_t* n_hitpoints);
+/* Eye-pass sharding: the same pass restricted to film rows [row_begin, row_end);
+ * append != 0 adds to the hit points already traced for this film.  Draws are addressed by the
+ * pixel index, so any split of the rows yields the hit points of the whole pass. */
+int sppm_eye_pass_rows(sppm_ctx* ctx, const SppmCameraDesc* cam, uint64_t pass_id, int32_t row_begin, int32_t row_end,
+                       int32_t append, int64_t* n_hitpoints);
+/* Exchange the ranks' shares over NCCL so that every rank holds the whole map (no-op without a
+ * communicator); call before sppm_build_index. */
+int sppm_allgather_hitpoints(sppm_ctx* ctx, int64_t* n_hitpoints);
 /* Replaces the flann kd-tree build (Raytracer.h:370-380) by a cell-sorted hash grid. */
 int sppm_build_index(sppm_ctx* ctx);
 /* One round of RayTracer::PhotonMap (Raytracer.h:226-233) restricted to photons

@@ -101,6 +101,8 @@ PROTOTYPES = {
     "sppm_set_params": (C.c_int, [VP, C.POINTER(SppmParams)]),
     "sppm_scene_upload": (C.c_int, [VP, C.POINTER(SppmSceneDesc)]),
     "sppm_eye_pass": (C.c_int, [VP, C.POINTER(SppmCameraDesc), U64, C.POINTER(I64)]),
+    "sppm_eye_pass_rows": (C.c_int, [VP, C.POINTER(SppmCameraDesc), U64, I32, I32, I32, C.POINTER(I64)]),
+    "sppm_allgather_hitpoints": (C.c_int, [VP, C.POINTER(I64)]),
     "sppm_build_index": (C.c_int, [VP]),
     "sppm_photon_pass": (C.c_int, [VP, U64, U64, U64]),
     "sppm_allreduce": (C.c_int, [VP]),

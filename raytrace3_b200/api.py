@@ -89,6 +89,19 @@ class Context:
         self._ck(self.lib.sppm_eye_pass(self.h, C.byref(d), pass_id, C.byref(n)), "sppm_eye_pass")
         return n.value
 
+    def eye_pass_rows(self, cam, pass_id: int, row_begin: int, row_end: int, append: bool = False) -> int:
+        """Eye-pass sharding: only film rows [row_begin, row_end)."""
+        desc = cam.desc() if isinstance(cam, Camera) else cam
+        n = C.c_int64()
+        self._ck(self.lib.sppm_eye_pass_rows(self.h, C.byref(desc), pass_id, row_begin, row_end, 1 if append else 0, C.byref(n)),
+                 "sppm_eye_pass_rows")
+        return n.value
+
+    def allgather_hitpoints(self) -> int:
+        n = C.c_int64()
+        self._ck(self.lib.sppm_allgather_hitpoints(self.h, C.byref(n)), "sppm_allgather_hitpoints")
+        return n.value
+
     def build_index(self):
         self._ck(self.lib.sppm_build_index(self.h), "sppm_build_index")
 

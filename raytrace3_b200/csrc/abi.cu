@@ -132,6 +132,8 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
@@ -150,6 +152,8 @@ NcclApi& nccl() {
   api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
   api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
   api.AllReduce = (decltype(api.AllReduce))dlsym(api.h, "ncclAllReduce");
+  api.AllGather = (decltype(api.AllGather))dlsym(api.h, "ncclAllGather");
+  api.Broadcast = (decltype(api.Broadcast))dlsym(api.h, "ncclBroadcast");
   api.GroupStart = (decltype(api.GroupStart))dlsym(api.h, "ncclGroupStart");
   api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.h, "ncclGroupEnd");
   api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
@@ -449,20 +453,24 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
   return SPPM_OK;
 }
 
-int sppm_eye_pass(sppm_ctx* c, const SppmCameraDesc* cam, uint64_t pass_id, int64_t* n_hitpoints) {
+int sppm_eye_pass_rows(sppm_ctx* c, const SppmCameraDesc* cam, uint64_t pass_id, int32_t row_begin, int32_t row_end,
+                       int32_t append, int64_t* n_hitpoints) {
   if (!c || !cam) return SPPM_ERR_INVALID;
   if (!c->scene_ok) return fail(c, SPPM_ERR_INVALID, "sppm_scene_upload must be called first");
   if (cam->w <= 0 || cam->h <= 0) return fail(c, SPPM_ERR_INVALID, "bad film size");
+  if (row_begin < 0 || row_end > cam->h || row_begin > row_end) return fail(c, SPPM_ERR_INVALID, "bad row range");
   Bind b(c);
   const int64_t npix = (int64_t)cam->w * cam->h;
+  if (append && (c->film_w != cam->w || c->film_h != cam->h || !c->hp_raw.p))
+    return fail(c, SPPM_ERR_INVALID, "append: the film size differs from the hit points already traced");
   c->hp_cap = npix * 4 + 1024;
   CU(c, dev_reserve(c->hp_raw, (size_t)c->hp_cap * sizeof(HpRaw)));
   c->film_w = cam->w;
   c->film_h = cam->h;
   c->index_ok = false;
-  CU(c, cudaMemsetAsync(scalars(c), 0, 8, c->stream));
+  if (!append) CU(c, cudaMemsetAsync(scalars(c), 0, 8, c->stream));
   CU(c, cudaEventRecord(c->ev[4], c->stream));
-  CU(c, launch_eye_pass(c, *cam, pass_id));
+  CU(c, launch_eye_pass(c, *cam, pass_id, row_begin, row_end));
   CU(c, cudaEventRecord(c->ev[5], c->stream));
   unsigned long long n = 0;
   CU(c, cudaMemcpyAsync(&n, scalars(c), 8, cudaMemcpyDeviceToHost, c->stream));
@@ -472,6 +480,67 @@ int sppm_eye_pass(sppm_ctx* c, const SppmCameraDesc* cam, uint64_t pass_id, int6
   c->host_counters.ms_eye = ms;
   if ((int64_t)n > c->hp_cap) return fail(c, SPPM_ERR_CAPACITY, "hit-point buffer overflow (more than 4 hit points per pixel)");
   c->n_hp = (int64_t)n;
+  if (n_hitpoints) *n_hitpoints = c->n_hp;
+  return SPPM_OK;
+}
+
+int sppm_eye_pass(sppm_ctx* c, const SppmCameraDesc* cam, uint64_t pass_id, int64_t* n_hitpoints) {
+  if (!c || !cam) return SPPM_ERR_INVALID;
+  return sppm_eye_pass_rows(c, cam, pass_id, 0, cam->h, 0, n_hitpoints);
+}
+
+// Eye-pass sharding: every rank traced its rows; exchange the raw hit points so that
+// all ranks hold the whole map.  Counts differ per rank, so the exchange is one 8-byte all-gather
+// of the counts followed by a group of broadcasts (rank r's records into slot r of the result).
+// build_index sorts by (pixel, eye-path node), so the map is identical to a one-GPU eye pass.
+int sppm_allgather_hitpoints(sppm_ctx* c, int64_t* n_hitpoints) {
+  if (!c) return SPPM_ERR_INVALID;
+  if (!c->hp_raw.p) return fail(c, SPPM_ERR_INVALID, "sppm_eye_pass_rows must be called first");
+  if (!c->nccl_comm || c->nranks <= 1) {
+    if (n_hitpoints) *n_hitpoints = c->n_hp;
+    return SPPM_OK;
+  }
+  Bind b(c);
+  NcclApi& n = nccl();
+  if (!n.AllGather || !n.Broadcast) return fail(c, SPPM_ERR_NCCL, "ncclAllGather / ncclBroadcast not found");
+  const int R = c->nranks;
+  CU(c, dev_reserve(c->scratch, (size_t)(R + 1) * 8 + 256));
+  unsigned long long* d_counts = (unsigned long long*)c->scratch.p;
+  const unsigned long long mine = (unsigned long long)c->n_hp;
+  CU(c, cudaMemcpyAsync(d_counts + R, &mine, 8, cudaMemcpyHostToDevice, c->stream));
+  ncclResult_t r = n.AllGather(d_counts + R, d_counts, 1, ncclUint64, (ncclComm_t)c->nccl_comm, c->stream);
+  if (r != ncclSuccess) return fail(c, SPPM_ERR_NCCL, "ncclAllGather (hit-point counts) failed");
+  std::vector<unsigned long long> counts((size_t)R);
+  CU(c, cudaMemcpyAsync(counts.data(), d_counts, (size_t)R * 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  unsigned long long total = 0;
+  for (auto v : counts) total += v;
+  if ((int64_t)total > c->hp_cap) return fail(c, SPPM_ERR_CAPACITY, "hit-point buffer overflow in the all-gather");
+  DevBuf all;
+  CU(c, dev_reserve(all, (size_t)c->hp_cap * sizeof(HpRaw)));
+  r = n.GroupStart();
+  unsigned long long off = 0;
+  for (int k = 0; k < R && r == ncclSuccess; k++) {
+    HpRaw* dst = (HpRaw*)all.p + off;
+    if (counts[k])
+      r = n.Broadcast(k == c->rank ? c->hp_raw.p : (const void*)dst, dst, (size_t)counts[k] * sizeof(HpRaw), ncclChar, k,
+                      (ncclComm_t)c->nccl_comm, c->stream);
+    off += counts[k];
+  }
+  const ncclResult_t r2 = n.GroupEnd();
+  if (r == ncclSuccess) r = r2;
+  if (r != ncclSuccess) {
+    dev_free(all);
+    return fail(c, SPPM_ERR_NCCL, std::string("hit-point exchange: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  dev_free(c->hp_raw);
+  c->hp_raw = all;
+  c->n_hp = (int64_t)total;
+  const unsigned long long t = total;
+  CU(c, cudaMemcpyAsync(scalars(c), &t, 8, cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->index_ok = false;
   if (n_hitpoints) *n_hitpoints = c->n_hp;
   return SPPM_OK;
 }

@@ -154,7 +154,7 @@ struct sppm_ctx {
 
 namespace sppm {
 // trace.cu
-cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pass_id);
+cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pass_id, int row_begin, int row_end);
 cudaError_t launch_photon_trace(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t count, uint64_t pass_id);
 cudaError_t launch_intersect(sppm_ctx* c, const double* d_rays6, int64_t n, const uint64_t* d_ids, uint64_t pass_id,
                              int node, SppmHit* d_out);

@@ -42,6 +42,7 @@ struct EyeArgs {
   unsigned long long cap;
   unsigned long long* hp_count;
   double init_r2;
+  long long pix_begin, pix_end;  // pixels [row_begin * w, row_end * w) of this launch (eye-pass sharding)
 };
 struct EyeStackEnt {
   d3 org, dir, wgt;
@@ -55,8 +56,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) eye_pass_kernel(const EyeArgs a
   const SceneView sv = stage_scene(a.c.scene, smem, a.c.patches_in_smem);
   WarpScratch* ws = warp_scratch(smem, scene_bytes);
   const int lane = threadIdx.x & 31;
-  const long long npix = (long long)a.cam.w * a.cam.h;
-  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npix = a.pix_end;
+  const long long p = a.pix_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int row = (int)(p / a.cam.w), col = (int)(p % a.cam.w);
 
   EyeStackEnt stack[16];
@@ -392,7 +393,7 @@ cudaError_t trace_configure(sppm_ctx* c) {
   return cudaSuccess;
 }
 
-cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pass_id) {
+cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pass_id, int row_begin, int row_end) {
   EyeArgs a;
   a.c = make_common(c, pass_id);
   a.cam = cam;
@@ -400,7 +401,10 @@ cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pas
   a.cap = (unsigned long long)c->hp_cap;
   a.hp_count = (unsigned long long*)c->dev_scalars.p + 0;
   a.init_r2 = c->prm.init_r2;
-  const long long npix = (long long)cam.w * cam.h;
+  a.pix_begin = (long long)row_begin * cam.w;
+  a.pix_end = (long long)row_end * cam.w;
+  const long long npix = a.pix_end - a.pix_begin;
+  if (npix <= 0) return cudaSuccess;
   const unsigned blocks = (unsigned)((npix + TRACE_THREADS - 1) / TRACE_THREADS);
   eye_pass_kernel<<<blocks, TRACE_THREADS, c->trace_smem, c->stream>>>(a);
   c->host_counters.launches++;

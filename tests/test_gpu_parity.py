@@ -533,6 +533,28 @@ def test_jpeg_decode_encode_on_device(ctx):
         ctx.jpeg_decode(b"not a jpeg at all")
 
 
+def test_eye_pass_row_sharding(ctx):
+    """the eye pass restricted to row ranges, appended, is the eye pass of the whole
+    film (draws are addressed by pixel): same hit points in canonical order, bit for bit."""
+    sc = make_scene("reference", textures=None)
+    cam = reference_camera(96, 72)
+    ctx.set_params(_params())
+    ctx.upload_scene(sc)
+    n = ctx.eye_pass(cam, 3)
+    whole = ctx.export_hitpoints()
+    m = ctx.eye_pass_rows(cam, 3, 40, 72)
+    assert 0 < m < n
+    assert ctx.eye_pass_rows(cam, 3, 0, 17, append=True) > m
+    k = ctx.eye_pass_rows(cam, 3, 17, 17, append=True)          # empty range: nothing added
+    assert ctx.eye_pass_rows(cam, 3, 17, 40, append=True) == n > k
+    parts = ctx.export_hitpoints()
+    assert ctx.allgather_hitpoints() == parts["pos"].shape[0]   # no communicator: a no-op
+    for k in ("pos", "n", "wgt", "r2", "pix", "node"):
+        np.testing.assert_array_equal(parts[k], whole[k])
+    with pytest.raises(Exception):
+        ctx.eye_pass_rows(cam, 3, 10, 100)
+
+
 def test_gpu_matches_the_reference_itself(ctx, oracle):
     """CUDA NearCollide against the reference's OWN compiled code (oracle/_ref, built from
     /root/reference/raytracer/*.h; the oracle only supplies the draw log that tells which

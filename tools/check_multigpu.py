@@ -1,4 +1,4 @@
-"""Multi-GPU correctness check (run with torchrun, one rank per GPU):
+"""Multi-GPU correctness check (run with torchrun, one rank per GPU; also checks the sharded eye pass):
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multigpu.py
 Every rank traces its photon_range() slice of two rounds, the per-round accumulators are summed
 with sppm_allreduce (NCCL), and rank 0 compares the result with a single-GPU run of the whole
@@ -25,11 +25,25 @@ def main():
     sc = make_scene("reference", textures=None)
     cam = reference_camera(256, 192)
     ctx.upload_scene(sc)
-    n = ctx.eye_pass(cam, 0)
-    ctx.build_index()
     uid = [ctx.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     ctx.comm_init_rank(rank, world, uid[0])
+    # eye-pass sharding: every rank traces its rows, the shares are exchanged over
+    # NCCL, and the map must equal the one-GPU eye pass hit point by hit point
+    r0, r1 = cam.h * rank // world, cam.h * (rank + 1) // world
+    mine = ctx.eye_pass_rows(cam, 0, r0, r1)
+    n = ctx.allgather_hitpoints()
+    assert n >= mine > 0
+    ctx.build_index()
+    sharded = ctx.export_hitpoints()
+    if rank == 0:
+        one = Context(local, prm)
+        one.upload_scene(sc)
+        assert one.eye_pass(cam, 0) == n, "sharded eye pass lost or duplicated hit points"
+        whole = one.export_hitpoints()
+        for k in ("pos", "n", "wgt", "r2", "pix", "node"):
+            np.testing.assert_array_equal(sharded[k], whole[k])
+        one.close()
     onetime = 300_001
     for rnd in range(2):
         b, c = photon_range(onetime, rank, world)
