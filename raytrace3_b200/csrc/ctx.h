@@ -123,7 +123,7 @@ struct sppm_ctx {
   sppm::DevBuf occ_nbr;       // int2[n_occ][9]: the neighbourhood as 9 x-runs of compact slots
   sppm::DevBuf units;         // GUnit[n_units]: work units of the filtered gather
   int32_t n_units = 0;
-  sppm::DevBuf item_parts, item_off, items;  // per-batch work items of the filtered gather
+  sppm::DevBuf item_parts, item_off;  // per-batch work-item counts of the units and their exclusive scan
   // deposits
   static constexpr int MAX_LANES = 4;
   sppm::Lane lanes[MAX_LANES];

@@ -231,7 +231,10 @@ __global__ void __launch_bounds__(320) dep_scatter_kernel(const Deposit* raw, co
 
 // Per batch: a unit whose 9 deposit ranges hold D deposits becomes ceil(D / ITEM_DEP) work items
 // (none when D = 0), so a boundary cell that collected 10^5 clamped deposits is spread over many
-// warps.  parts[u] -> exclusive scan -> items[off[u] + k] = (u, k << 16 | parts).
+// warps.  parts[u] -> exclusive scan off[]; work item `it` is part it - off[u] of the unit u with
+// off[u] <= it < off[u+1], which the warp finds with a 32-ary search (each step the 32 lanes probe
+// 32 evenly spaced entries of off[] and a ballot narrows the range 32-fold): no item list has to
+// be materialised, so no capacity can be exceeded however many units a deposit can reach.
 constexpr int ITEM_SLICES = 32;              // 32-deposit slices per work item
 constexpr int ITEM_DEP = ITEM_SLICES * 32;   // deposits per work item
 __global__ void unit_parts_kernel(const GUnit* units, int n_units, const int32_t* dep_off, int32_t* parts) {
@@ -245,13 +248,6 @@ __global__ void unit_parts_kernel(const GUnit* units, int n_units, const int32_t
     }
   parts[u] = (d + ITEM_DEP - 1) / ITEM_DEP;  // parts[n_units] = 0: the scan's last element is the item count
 }
-__global__ void item_fill_kernel(int n_units, const int32_t* parts, const int32_t* off, int2* items) {
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= n_units) return;
-  const int n = parts[u], o = off[u];
-  for (int k = 0; k < n; k++) items[o + k] = make_int2(u, (k << 16) | n);
-}
-
 struct GatherArgs {
   HpSoA s;
   long long n_hp;
@@ -266,8 +262,7 @@ struct GatherArgs {
   const uint32_t* occ_cell;  // grid id of occupied cell c
   const GUnit* units;        // filtered kernel: work units
   int n_units;
-  const int2* items;         // (unit, part << 16 | parts) work items of this batch
-  const int32_t* n_items;
+  const int32_t* item_off;   // [n_units + 1] exclusive scan of the units' work-item counts (this batch)
 };
 
 // ---- TMA (cp.async.bulk) + mbarrier helpers -----------------------------------------------
@@ -727,10 +722,23 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
     int it = 0;
     if (lane == 0) it = (int)atomicAdd(work_counter, 1u);
     it = __shfl_sync(FULL, it, 0);
-    if (it >= *a.n_items) break;
-    const int2 item = a.items[it];
-    const int u = item.x, part = item.y >> 16;
-    const bool shared_unit = (item.y & 0xffff) > 1;  // several warps accumulate into this unit's hit points
+    if (it >= a.item_off[a.n_units]) break;
+    int u = 0;
+    {  // 32-ary search: the last u with item_off[u] <= it
+      int lo = 0, hi = a.n_units;
+      while (hi - lo > 1) {
+        const int step = (hi - lo + 31) >> 5;
+        const int probe = lo + (lane + 1) * step;
+        const bool le = probe < hi && a.item_off[probe] <= it;
+        const int k = __popc(__ballot_sync(FULL, le));  // off[] is non-decreasing: the lanes that answer yes are a prefix
+        lo += k * step;
+        hi = min(hi, lo + step);
+      }
+      u = lo;
+    }
+    const int off_u = a.item_off[u];
+    const int part = it - off_u;
+    const bool shared_unit = a.item_off[u + 1] - off_u > 1;  // several warps accumulate into this unit's hit points
     const GUnit* un = a.units + u;
     const int h0 = un->hp_begin, H = un->hp_count, ncx = un->n_cells_x;
     const double ox = un->org[0], oy = un->org[1], oz = un->org[2];
@@ -1346,19 +1354,15 @@ cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cud
     if (filtered) {
       // work items of this batch (see unit_parts_kernel); the item count stays on the device
       const int nu = c->n_units;
-      const size_t items_cap = (size_t)nu + (size_t)L.dep_cap / ITEM_DEP + 16;
       CK(dev_reserve(c->item_parts, ((size_t)nu + 1) * 4));
       CK(dev_reserve(c->item_off, ((size_t)nu + 1) * 4));
-      CK(dev_reserve(c->items, items_cap * sizeof(int2)));
       unit_parts_kernel<<<nblk(nu + 1), TPB, 0, st>>>(a.units, nu, a.dep_off, (int32_t*)c->item_parts.p);
       size_t tmp = 0;
       CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (int32_t*)c->item_parts.p, (int32_t*)c->item_off.p, nu + 1, st));
       CK(dev_reserve(c->cub_tmp, tmp));
       CK(cub::DeviceScan::ExclusiveSum(c->cub_tmp.p, tmp, (int32_t*)c->item_parts.p, (int32_t*)c->item_off.p, nu + 1, st));
-      item_fill_kernel<<<nblk(nu), TPB, 0, st>>>(nu, (const int32_t*)c->item_parts.p, (const int32_t*)c->item_off.p, (int2*)c->items.p);
-      a.items = (const int2*)c->items.p;
-      a.n_items = (const int32_t*)c->item_off.p + nu;
-      c->host_counters.launches += 3;
+      a.item_off = (const int32_t*)c->item_off.p;
+      c->host_counters.launches += 2;
     }
     kern<<<blocks, threads, tile_bytes, st>>>(a, work_counter);
     c->host_counters.launches++;
