@@ -170,6 +170,7 @@ typedef struct SppmCounters {
   uint64_t grid_cells;       /* cells of the current hash grid */
   uint64_t launches;         /* kernels launched by this library */
   double ms_eye, ms_build, ms_trace, ms_sort, ms_gather, ms_update, ms_resolve; /* last call of each */
+  uint64_t patch_culled;     /* ... of patch_solves, proven empty by the 13-DOP line test and not run */
 } SppmCounters;
 
 typedef struct sppm_ctx sppm_ctx;

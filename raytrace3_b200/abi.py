@@ -76,7 +76,7 @@ class SppmCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "photons", "isect_queries", "patch_solves", "deposits", "deposits_kept", "cand_pairs", "acc_pairs",
         "hit_points", "grid_cells", "launches")] + [(n, C.c_double) for n in (
-            "ms_eye", "ms_build", "ms_trace", "ms_sort", "ms_gather", "ms_update", "ms_resolve")]
+            "ms_eye", "ms_build", "ms_trace", "ms_sort", "ms_gather", "ms_update", "ms_resolve")] + [("patch_culled", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

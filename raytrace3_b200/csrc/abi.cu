@@ -345,6 +345,27 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
         if (bx[3 + k] < v) bx[3 + k] = v;
       }
   }
+  // 13-DOP of every patch's control points, grown by the Newton acceptance radius (scene.cuh dop_line_miss)
+  std::vector<double> patchDop((size_t)s->n_patches * 26);
+  {
+    static const double A13[13][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, -1, 0}, {1, 0, 1}, {1, 0, -1},
+                                      {0, 1, 1}, {0, 1, -1}, {1, 1, 1}, {1, 1, -1}, {1, -1, 1}, {-1, 1, 1}};
+    for (int p = 0; p < s->n_patches; p++)
+      for (int k = 0; k < 13; k++) {
+        double lo = 1e300, hi = -1e300, big = 0;
+        for (int q = 0; q < 16; q++) {
+          const double* v = &patchP[((size_t)p * 16 + q) * 3];
+          const double e = A13[k][0] * v[0] + A13[k][1] * v[1] + A13[k][2] * v[2];
+          lo = std::min(lo, e);
+          hi = std::max(hi, e);
+          big = std::max(big, std::fabs(v[0]) + std::fabs(v[1]) + std::fabs(v[2]));
+        }
+        const double len = std::sqrt(A13[k][0] * A13[k][0] + A13[k][1] * A13[k][1] + A13[k][2] * A13[k][2]);
+        const double grow = 0.0101 * len + 1e-12 * big;  // sqrt(M_EPS) = 0.01 plus slack for rounding
+        patchDop[(size_t)p * 26 + k] = lo - grow;
+        patchDop[(size_t)p * 26 + 13 + k] = hi + grow;
+      }
+  }
   // monomial coefficients per patch and component: A = M G M^T with G[i][k] = P[4i+k] (i <-> v,
   // k <-> u) and M the cubic Bernstein -> power basis matrix
   std::vector<double> patchA((size_t)s->n_patches * 48);
@@ -429,7 +450,7 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
     const SppmTexture& ht = s->textures[t];
     if (ht.rows <= 0 || ht.cols <= 0 || !ht.bgr8) return fail(c, SPPM_ERR_INVALID, "empty texture (Q18: the reference would read out of range)");
     const uint8_t* dev = nullptr;
-    CU(c, upload(c, 6 + (size_t)t, ht.bgr8, (size_t)ht.rows * ht.cols * 3, &dev));
+    CU(c, upload(c, 7 + (size_t)t, ht.bgr8, (size_t)ht.rows * ht.cols * 3, &dev));
     tex[t].rows = ht.rows;
     tex[t].cols = ht.cols;
     tex[t].bgr = dev;
@@ -445,6 +466,8 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
   CU(c, upload(c, 3, lights.data(), lights.size(), &ds.lights));
   CU(c, upload(c, 4, tex.data(), tex.size(), &ds.tex));
   CU(c, upload(c, 5, patchA.data(), patchA.size(), &ds.patchA));
+  CU(c, upload(c, 6, patchDop.data(), patchDop.size(), &ds.patchDop));
+  ds.culled = &((DevCounters*)c->counters.p)->patch_culled;
   CU(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
   c->scene = ds;
   CU(c, trace_configure(c));
@@ -846,6 +869,7 @@ int sppm_bezier_patch_bench(sppm_ctx* c, int64_t n, int32_t reps, uint64_t seed,
   DevBuf dr, dp, dt;
   int rc = SPPM_OK;
   cudaError_t e;
+  c->newton_cull = false;  // the microbenchmark times full 50 x 10 solves, not the 13-DOP shortcut
   do {
     if ((e = dev_reserve(dr, (size_t)n * 48))) break;
     if ((e = dev_reserve(dp, (size_t)n * 4))) break;
@@ -862,6 +886,7 @@ int sppm_bezier_patch_bench(sppm_ctx* c, int64_t n, int32_t reps, uint64_t seed,
     if ((e = cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]))) break;
     *ms_per_rep = ms / reps;
   } while (0);
+  c->newton_cull = true;
   if (e) rc = cuda_fail(c, e, "sppm_bezier_patch_bench");
   dev_free(dr);
   dev_free(dp);
@@ -1063,6 +1088,7 @@ int sppm_get_counters(sppm_ctx* c, SppmCounters* out) {
   h.photons = d.photons;
   h.isect_queries = d.isect_queries;
   h.patch_solves = d.patch_solves;
+  h.patch_culled = d.patch_culled;
   h.deposits = d.deposits;
   h.deposits_kept = d.deposits_kept;
   h.cand_pairs = d.cand_pairs;

@@ -71,7 +71,7 @@ struct GUnit {
 };
 
 struct DevCounters {
-  unsigned long long photons, isect_queries, patch_solves, deposits, deposits_kept, cand_pairs, acc_pairs, overflow;
+  unsigned long long photons, isect_queries, patch_solves, deposits, deposits_kept, cand_pairs, acc_pairs, overflow, patch_culled;
 };
 
 struct DevBuf {  // growable device allocation
@@ -140,6 +140,7 @@ struct sppm_ctx {
   sppm::DevBuf px_store;
   int px_w = 0, px_h = 0;
   uint64_t px_photons = 0;   // photons emitted into the shared statistics so far
+  bool newton_cull = true;    // 13-DOP line test before Newton solves (off only inside sppm_bezier_patch_bench)
   bool keep_all_deposits = false;
   SppmCounters host_counters{};
   cudaEvent_t ev[8] = {};  // 4/5 generic, 6/7 user stopwatch

@@ -368,6 +368,7 @@ TraceCommon make_common(sppm_ctx* c, uint64_t pass) {
   t.ncfg.iters = c->prm.newton_iters;
   t.ncfg.mode = c->prm.newton_mode;
   t.ncfg.seed = c->prm.seed;
+  t.ncfg.cull = c->newton_cull ? 1 : 0;
   t.patches_in_smem = c->patches_in_smem ? 1 : 0;
   t.max_dep = c->prm.max_dep;
   t.fast_math = c->prm.math_mode == SPPM_MATH_FAST ? 1 : 0;

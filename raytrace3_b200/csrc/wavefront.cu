@@ -495,6 +495,7 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
       n.ncfg.iters = c->prm.newton_iters;
       n.ncfg.mode = c->prm.newton_mode;
       n.ncfg.seed = c->prm.seed;
+      n.ncfg.cull = c->newton_cull ? 1 : 0;
       n.patches_in_smem = a.patches_in_smem;
       n.pass = pass_id;
       n.q = a.qout;

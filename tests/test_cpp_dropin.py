@@ -62,8 +62,7 @@ def test_cpp_render_matches_python_mirror(tmp_path, ctx):
 @pytest.mark.gpu
 def test_cli_scene_file_checkpoint_resume_and_jpeg(tmp_path, ctx):
     """examples/sppm_render renders a scene description file (JPEG texture decoded
-    by nvJPEG), resumes from a film checkpoint to exactly the film of an uninterrupted run (both
-    estimators), writes JPEG, and agrees with the Python twin on the same file."""
+    by nvJPEG), resumes from a film checkpoint to the film of an uninterrupted run (both estimators), writes JPEG, and agrees with the Python twin on the same file."""
     cv2 = pytest.importorskip("cv2")
     import shutil
     from raytrace3_b200.scene import Texture, synthetic_texture, teapot_patches, write_bpt
@@ -86,7 +85,9 @@ def test_cli_scene_file_checkpoint_resume_and_jpeg(tmp_path, ctx):
         straight = run("--passes", "2", *mode)
         run("--passes", "1", "--checkpoint", "ck.bin", *mode)
         resumed = run("--passes", "2", "--checkpoint", "ck.bin", "--resume", *mode)
-        assert resumed == straight and float(straight) > 0          # bit-identical film after resume
+        # same film after resume; the order in which a round's deposits are summed is not fixed
+        # (atomic arrival order), so two runs agree to rounding, not bit for bit
+        assert float(straight) > 0 and abs(float(resumed) - float(straight)) <= 1e-12 * float(straight)
     run("--passes", "1", "--format", "jpg", "--out", "shot")
     img = cv2.imread(str(tmp_path / "shot0.jpg"))
     assert img is not None and img.shape == (36, 48, 3) and img.mean() > 1
