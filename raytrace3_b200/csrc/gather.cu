@@ -235,8 +235,7 @@ __global__ void __launch_bounds__(320) dep_scatter_kernel(const Deposit* raw, co
 // off[u] <= it < off[u+1], which the warp finds with a 32-ary search (each step the 32 lanes probe
 // 32 evenly spaced entries of off[] and a ballot narrows the range 32-fold): no item list has to
 // be materialised, so no capacity can be exceeded however many units a deposit can reach.
-constexpr int ITEM_SLICES = 32;              // 32-deposit slices per work item
-constexpr int ITEM_DEP = ITEM_SLICES * 32;   // deposits per work item
+constexpr int ITEM_DEP = 1024;               // deposits per work item
 __global__ void unit_parts_kernel(const GUnit* units, int n_units, const int32_t* dep_off, int32_t* parts) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   if (u > n_units) return;
@@ -544,11 +543,14 @@ __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 // kernel uses u (8 searchR2 + 6 sqrt(searchR2) |M|) plus the FP32 rounding of the thresholds.
 constexpr int W_WARPS = 8;
 constexpr int W_THREADS = W_WARPS * 32;
-constexpr int W_SLICE = 32;                                   // deposits per warp slice
+#ifndef SPPM_W_SLICE
+#define SPPM_W_SLICE 32
+#endif
+constexpr int W_SLICE = SPPM_W_SLICE;                          // deposits per warp slice (32 or 64)
 constexpr int W_RAW_BYTES = W_SLICE * (int)sizeof(Deposit);   // 2560
 constexpr int F_PAIR_F4 = 6;                                  // 16-byte words per converted pair (96 B)
 constexpr int W_CONV_BYTES = (W_SLICE / 2) * F_PAIR_F4 * 16;  // 1536
-constexpr int W_PER_WARP = 2 * W_RAW_BYTES + W_CONV_BYTES + 64;  // + kept-index list
+constexpr int W_PER_WARP = 2 * W_RAW_BYTES + W_CONV_BYTES + 128;  // + kept-index list
 constexpr size_t F_SMEM = (size_t)W_WARPS * W_PER_WARP;
 constexpr int W_CHUNK = 64;                                   // hit points per chunk (2 per lane)
 #define SPPM_F_U 5.9604644775390625e-8 /* 2^-24 */
@@ -769,6 +771,7 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
       __syncwarp();
     }
     if (D == 0) continue;
+    constexpr int ITEM_SLICES = ITEM_DEP / W_SLICE;
     const int sl0 = part * ITEM_SLICES;  // this item: slices [sl0, sl0 + n_sl) of the concatenation
     const int n_sl = min(ITEM_SLICES, (D + W_SLICE - 1) / W_SLICE - sl0);
     // lane 0: stream the item's next slice (32 deposits of the concatenation from position cur_p,
@@ -858,34 +861,40 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
       // bounding box.  A deposit farther than M from the centre in some coordinate (clamped into
       // a boundary cell from outside the grid) is more than a cell edge away from every hit
       // point lying inside the unit's cells and is dropped.
-      bool keep = false, badn = false;
-      float fx = 0, fy = 0, fz = 0, gx = 0, gy = 0, gz = 0;
-      double2 q3 = make_double2(0, 0), q4 = make_double2(0, 0);
-      if (lane < fill) {
-        const double2* q = raw + lane * 5;
-        const double2 q0 = q[0], q1 = q[1], q2 = q[2];
-        q3 = q[3]; q4 = q[4];
-        const double ax = q0.x - ox, ay = q0.y - oy, az = q1.x - oz;
-        const bool out = !(fabs(ax) <= M_x && fabs(ay) <= M_yz && fabs(az) <= M_yz);
-        badn = !(fabs(q1.y) <= SPPM_F_NMAX && fabs(q2.x) <= SPPM_F_NMAX && fabs(q2.y) <= SPPM_F_NMAX);
-        fx = __double2float_rn(ax); fy = __double2float_rn(ay); fz = __double2float_rn(az);
-        gx = __double2float_rn(q1.y); gy = __double2float_rn(q2.x); gz = __double2float_rn(q2.y);
-        const float ex = fmaxf(fmaxf(blo[0] - fx, fx - bhi[0]), 0.f), ey = fmaxf(fmaxf(blo[1] - fy, fy - bhi[1]), 0.f),
-                    ez = fmaxf(fmaxf(blo[2] - fz, fz - bhi[2]), 0.f);
-        keep = !out && !(fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > cull_thr);
+      bool badn = false;
+      int n_k = 0;
+#pragma unroll
+      for (int rd = 0; rd < W_SLICE / 32; rd++) {  // W_SLICE / 32 deposits per lane
+        const int di = rd * 32 + lane;
+        bool keep = false;
+        float fx = 0, fy = 0, fz = 0, gx = 0, gy = 0, gz = 0;
+        double2 q3 = make_double2(0, 0), q4 = make_double2(0, 0);
+        if (di < fill) {
+          const double2* q = raw + di * 5;
+          const double2 q0 = q[0], q1 = q[1], q2 = q[2];
+          q3 = q[3]; q4 = q[4];
+          const double ax = q0.x - ox, ay = q0.y - oy, az = q1.x - oz;
+          const bool out = !(fabs(ax) <= M_x && fabs(ay) <= M_yz && fabs(az) <= M_yz);
+          badn = badn || !(fabs(q1.y) <= SPPM_F_NMAX && fabs(q2.x) <= SPPM_F_NMAX && fabs(q2.y) <= SPPM_F_NMAX);
+          fx = __double2float_rn(ax); fy = __double2float_rn(ay); fz = __double2float_rn(az);
+          gx = __double2float_rn(q1.y); gy = __double2float_rn(q2.x); gz = __double2float_rn(q2.y);
+          const float ex = fmaxf(fmaxf(blo[0] - fx, fx - bhi[0]), 0.f), ey = fmaxf(fmaxf(blo[1] - fy, fy - bhi[1]), 0.f),
+                      ez = fmaxf(fmaxf(blo[2] - fz, fz - bhi[2]), 0.f);
+          keep = !out && !(fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > cull_thr);
+        }
+        const unsigned kmask = __ballot_sync(FULL, keep);
+        if (keep) {
+          const int pos = n_k + __popc(kmask & ((1u << lane) - 1u));
+          float4* pr = conv + (pos >> 1) * F_PAIR_F4;
+          float* f = reinterpret_cast<float*>(pr) + (pos & 1);
+          f[0] = fx; f[2] = fy; f[4] = fz; f[6] = gx; f[8] = gy; f[10] = gz;
+          double* g = reinterpret_cast<double*>(pr + 3) + (pos & 1) * 3;
+          g[0] = q3.x; g[1] = q3.y; g[2] = q4.x;
+          kidx[pos] = (unsigned char)di;
+        }
+        n_k += __popc(kmask);
       }
-      const unsigned kmask = __ballot_sync(FULL, keep);
       const bool any_badn = __any_sync(FULL, badn);
-      const int n_k = __popc(kmask);
-      if (keep) {
-        const int pos = __popc(kmask & ((1u << lane) - 1u));
-        float4* pr = conv + (pos >> 1) * F_PAIR_F4;
-        float* f = reinterpret_cast<float*>(pr) + (pos & 1);
-        f[0] = fx; f[2] = fy; f[4] = fz; f[6] = gx; f[8] = gy; f[10] = gz;
-        double* g = reinterpret_cast<double*>(pr + 3) + (pos & 1) * 3;
-        g[0] = q3.x; g[1] = q3.y; g[2] = q4.x;
-        kidx[pos] = (unsigned char)lane;
-      }
       if (lane == 0 && (n_k & 1)) {  // pad the last pair
         float4* pr = conv + (n_k >> 1) * F_PAIR_F4;
         float* f = reinterpret_cast<float*>(pr) + 1;
