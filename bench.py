@@ -160,7 +160,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "bezier_isects_per_s": solves / total,
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 def main():
@@ -396,10 +396,22 @@ def main():
                        "patch_solves": solves / (onetime * len(scene.plvec))},
         "setup_ms": {"eye": setup["ms_eye"], "build": setup["ms_build"], "eye_e2e": e2e_counters["ms_eye"], "build_e2e": e2e_counters["ms_build"]},
     }
-    print(json.dumps(line))
+    _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _emit(line: dict):
+    """The ONE JSON line of the contract goes to the real stdout; everything else libraries print
+    while the benchmark runs (NCCL's version banner, build logs) was redirected to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# keep stdout clean for the driver: fd 1 -> stderr until the result line is written
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 if __name__ == "__main__":
