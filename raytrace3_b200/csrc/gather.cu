@@ -486,25 +486,31 @@ __global__ void __launch_bounds__(G_THREADS) gather_kernel(const GatherArgs a, u
 // The acceptance predicate of Raytracer.h:152-154 is three FP64 comparisons per (hit point,
 // deposit) pair, and ~80 % of the pairs of a 27-cell neighbourhood fail the first one.  The
 // filtered kernel evaluates the predicate in packed FP32 (sm_100 FADD2/FMUL2/FFMA2, two
-// deposits per instruction) on coordinates taken relative to the centre o of the CTA's cell,
-// with a rigorous error bound, and falls back to the FP64 evaluation of the reference for the
-// (rare) pairs whose FP32 value lies within the bound of a threshold.  newN is therefore
-// bit-identical to the all-FP64 kernel, and tao is summed in FP64 in the same order.
+// deposits per instruction) on coordinates taken relative to an origin o close to both points
+// (the centre of the work unit's cells), with a rigorous error bound, and falls back to the FP64
+// evaluation of the reference for the (rare) pairs whose FP32 value lies within the bound of a
+// threshold.  newN is therefore bit-identical to the all-FP64 kernel; tao is summed in FP64.
 //
-// Error bound (u = 2^-24, M = bound on |p_k - o_k| and |x_k - o_k| of non-"far" points):
-//   p^_k = fl32(fl64(p_k - o_k)), x^_k likewise:  |p^_k - (p_k - o_k)| <= u M (1 + 2^-28)
-//   v^_k = fl32(p^_k - x^_k):                     |v^_k - (p_k - x_k)| <= 4 u M (1 + 2^-20)
-//   S^   = fma(v^z,v^z, fma(v^y,v^y, v^x v^x)):   |S^ - sum v^_k^2|    <= 3.01 u * 12 M^2
-//   |sum v^_k^2 - sum v_k^2| <= 3 * 4uM * 4M = 48 u M^2;  FP64 rounding of the reference's own
-//   vv: < 1e-15 * 12 M^2.  Total |S^ - vv64| < 85 u M^2; the kernel uses 100 u M^2 (+ the
-//   rounding of the thresholds to FP32).  M = 1.5 cell edges (1 + 1e-6): every point of a
-//   neighbour cell that was not clamped into the grid from outside satisfies it; a tile holding
-//   a "far" deposit, and a "far" hit point, take the FP64 path wholesale.
-//   nn^ = fma(n^z,N^z, fma(n^y,N^y, n^x N^x)) with |n_k|,|N_k| <= 1.0001 (else "far"):
+// Error bound (u = 2^-24; M_k bounds |p_k - o_k| and |x_k - o_k| in coordinate k for the points
+// that take the FP32 path; v = p - x, vv = |v|^2 as the reference computes it in FP64):
+//   p^_k = fl32(fl64(p_k - o_k)), x^_k likewise:  |p^_k - (p_k - o_k)| <= u M_k (1 + 2^-28)
+//   v^_k = fl32(p^_k - x^_k):                     E_k = |v^_k - v_k| <= u (|v_k| + 2 M_k) + O(u^2)
+//   S^   = fma(v^z,v^z, fma(v^y,v^y, v^x v^x)):   |S^ - sum v^_k^2| <= 3.01 u sum v^_k^2
+//   |sum v^_k^2 - vv| <= sum E_k (2 |v_k| + E_k) <= 2 u vv + 4 u sqrt(vv) |M| + O(u^2)   (Cauchy-Schwarz)
+//   => |S^ - vv64| <= u (5.01 vv + 4 sqrt(vv) |M|) + O(u^2) + 1e-15 vv,  |M| = sqrt(M_x^2 + M_y^2 + M_z^2).
+//   vv -/+ this bound is increasing in vv, so its value at the threshold bounds the classification
+//   error there; the kernel uses u (8 T + 6 sqrt(T) |M|) plus the FP32 rounding of T for
+//   T = searchR2 and T = R2.  M_y = M_z = 1.5 cell edges, M_x = n_cells_x / 2 + 1 cell edges (all
+//   x (1 + 1e-6)): every deposit of the unit's 9 ranges that was not clamped into the grid from
+//   outside satisfies it, and one that does not is more than a cell edge > sqrt(searchR2) from
+//   every hit point lying inside the unit's cells, so it is dropped.  A hit point that does not lie
+//   inside the unit's cells (clamped), and a slice holding a deposit whose normal has a component
+//   above 1.0001, take the FP64 path wholesale.
+//   nn^ = fma(n^z,N^z, fma(n^y,N^y, n^x N^x)) with |n_k|, |N_k| <= 1.0001:
 //   |nn^ - nn64| <= 5.1 u * 3.0006 < 9.2e-7; the kernel uses 1.5e-6.
-// Pairs are classified by the sign of fl32(S^ - fl32(searchR2)) etc. (exact in sign); a slice
-// (the deposits one thread visits in one tile) whose smallest |difference| is inside the bound
-// is recomputed in FP64 by exact_slice(), in the same deposit order.
+// Pairs are classified by comparing S^, nn^ with the FP32 thresholds while FMNMX3 tracks the
+// smallest |S^ - T|, |nn^ - 1e-3| a lane has seen in the slice; a lane whose minimum is inside the
+// bound repeats its share pair by pair (careful_pairs: FP64 only for the pairs inside the bound).
 __device__ __forceinline__ float2 f2sub(float2 a, float2 b) {
   unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rr;
   asm("sub.f32x2 %0, %1, %2;" : "=l"(rr) : "l"(ra), "l"(rb));
@@ -535,12 +541,9 @@ __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 // of 33..64; 32/hl deposit sub-slices when the unit has hl <= 16 hit points) and every lane
 // walks the warp's pairs with broadcast 128-bit shared-memory loads.  A deposit outside the
 // 27-cell neighbourhood of a lane's hit point simply fails the distance test.  Every hit point
-// belongs to exactly one unit: its accumulators are written once, without atomics.
-// With M_x = (n_cells_x / 2 + 1) cell edges the bound above is applied in its sharper form
-//   |S^ - vv64| <= u (5.01 vv + 4 sqrt(vv) |M|) + O(u^2),  |M| = sqrt(M_x^2 + M_y^2 + M_z^2),
-// (E_k <= u (|v_k| + 2 M_k) per coordinate, Cauchy-Schwarz on sum |v_k| M_k), which is monotone
-// in vv, so its value at vv = searchR2 bounds the classification error at the threshold; the
-// kernel uses u (8 searchR2 + 6 sqrt(searchR2) |M|) plus the FP32 rounding of the thresholds.
+// belongs to exactly one unit.
+// A unit whose ranges hold more than ITEM_DEP deposits is processed by several warps (work items,
+// see unit_parts_kernel); only those units accumulate with atomics.
 constexpr int W_WARPS = 8;
 constexpr int W_THREADS = W_WARPS * 32;
 #ifndef SPPM_W_SLICE
@@ -834,7 +837,8 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
           hp[b].x = __double2float_rn(ax); hp[b].y = __double2float_rn(ay); hp[b].z = __double2float_rn(az);
           hp[b].nx = __double2float_rn(nx); hp[b].ny = __double2float_rn(ny); hp[b].nz = __double2float_rn(nz);
           hp[b].r2f = __double2float_rn(r2);
-          hp[b].band = __double2float_ru(1.01 * (band_v + 2.0 * SPPM_F_U * fmax(r2, a.search_r2)));
+          const double Tm = fmax(r2, a.search_r2);  // the larger threshold this hit point is classified against
+          hp[b].band = __double2float_ru(1.01 * (SPPM_F_U * (8.0 * Tm + 6.0 * sqrt(Tm) * Mn + 2.0 * Tm) + 1e-13 * Mn * Mn));
           blo[0] = fminf(blo[0], hp[b].x); blo[1] = fminf(blo[1], hp[b].y); blo[2] = fminf(blo[2], hp[b].z);
           bhi[0] = fmaxf(bhi[0], hp[b].x); bhi[1] = fmaxf(bhi[1], hp[b].y); bhi[2] = fmaxf(bhi[2], hp[b].z);
           uni_me = uni_me && (r2 == a.search_r2);
