@@ -264,13 +264,23 @@ def main():
     # ---- e2e: RayTracer::render() through the public API with host buffers
     from raytrace3_b200 import RayTracer
     e2e_ms, e2e_phases = [], None
-    film = np.zeros((wl["h"], wl["w"], 3))
+    # host buffers of the e2e leg live in pinned memory (the contract's H2D / D2H from pinned host memory):
+    # the texture pixels the scene hands to sppm_scene_upload and the film sppm_resolve writes
+    pins = []
+    for tex in {id(o.texture): o.texture for o in scene.objvec if o.texture is not None}.values():
+        buf = torch.empty(tex.map.shape, dtype=torch.uint8, pin_memory=True)
+        arr = buf.numpy()
+        arr[...] = tex.map
+        tex.map = arr
+        pins.append(buf)
+    film_pin = torch.zeros((wl["h"], wl["w"], 3), dtype=torch.float64, pin_memory=True)
+    film = film_pin.numpy()
     h2d = scene.texture_bytes() + sum(o.P.nbytes for o in scene.objvec if o.kind == 2) + 328 * len(scene.objvec) + 256
     d2h = film.nbytes + 8 * 3
     for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         barrier()
         t0 = time.perf_counter()
-        ctx.upload_scene(scene)                      # H2D: objects, patches, textures (host memory)
+        ctx.upload_scene(scene)                      # H2D: objects, patches, textures (pinned host memory)
         t1 = time.perf_counter()
         ctx.eye_pass(cam, 100 + i)
         t2 = time.perf_counter()
