@@ -138,7 +138,8 @@ def run_reference(args):
     s, c = orc.photon_bench(scene, prm, hp, 1000, threads, pass_id=999)
     rate = c["photons"] / max(s, 1e-6)
     budget = 150.0 / max(1, args.steps + args.warmup)  # whole run within a few minutes
-    per_thread = int(max(500, min(2_000_000, rate * min(budget, 10.0) / threads)))
+    step_s = float(os.environ.get("SPPM_BENCH_SAMPLE_S", "10.0"))  # seconds of CPU work per step (tests shrink it)
+    per_thread = int(max(500, min(2_000_000, rate * min(budget, step_s) / threads)))
     times, photons, solves = [], 0, 0
     for i in range(args.warmup + args.steps):
         s, c = orc.photon_bench(scene, prm, hp, per_thread, threads, pass_id=i)
