@@ -36,6 +36,12 @@ def photon_range(onetime: int, rank: int, world: int):
     return begin, base + (1 if rank < rem else 0)
 
 
+def row_range(h: int, rank: int, world: int):
+    """Film rows [begin, end) `rank` traces in a sharded eye pass: contiguous, disjoint,
+    covering [0, h); feed to Context.eye_pass_rows, then Context.allgather_hitpoints."""
+    return int(h) * rank // world, int(h) * (rank + 1) // world
+
+
 class Context:
     """One sppm_ctx = one CUDA device.  Methods map 1:1 onto include/sppm_b200.h."""
 

@@ -80,3 +80,57 @@ def test_sharded_photon_pass_equals_single_rank():
     assert ref_N.sum() > 0
     np.testing.assert_array_equal(newN, ref_N)
     np.testing.assert_allclose(tao, ref_tao, rtol=1e-12, atol=0)
+
+
+def _eye_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "1"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import Oracle
+    from raytrace3_b200 import abi, row_range
+    from raytrace3_b200.scene import make_scene, reference_camera
+    orc = Oracle()
+    prm = abi.default_params()
+    sc = make_scene("cornell", textures=None)
+    cam = reference_camera(24, 18)
+    r0, r1 = row_range(cam.h, rank, world)
+    mine = [orc.view_trace_pixel(sc, prm, cam, i, j, 0) for i in range(r0, r1) for j in range(cam.w)]
+    share = {k: np.concatenate([m[k] for m in mine]) for k in ("pos", "n", "wgt", "r2", "pix")}
+    parts = [None] * world
+    dist.all_gather_object(parts, share)          # the exchange sppm_allgather_hitpoints does over NCCL
+    if rank == 0:
+        q.put(({k: np.concatenate([p[k] for p in parts]) for k in share}, (r0, r1)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_eye_pass_equals_single_rank():
+    """SURVEY §8f-4 on CPU: every rank traces its film rows (draws are addressed by pixel), the
+    shares are exchanged, and the union is the hit-point map of the whole eye pass."""
+    sys.path.insert(0, ROOT)
+    from raytrace3_b200 import row_range
+    assert [row_range(10, r, 3) for r in range(3)] == [(0, 3), (3, 6), (6, 10)]
+    assert row_range(5, 7, 8) == (4, 5) and row_range(5, 0, 8) == (0, 0)
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eye_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, rows0 = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert rows0 == (0, 9)
+    from oracle import Oracle
+    from raytrace3_b200 import abi
+    from raytrace3_b200.scene import make_scene, reference_camera
+    whole = Oracle().eye_pass(make_scene("cornell", textures=None), abi.default_params(), reference_camera(24, 18), 0)
+    order = np.lexsort((got["pix"][:, 1], got["pix"][:, 0]))          # canonical order: by pixel (stable within a pixel)
+    worder = np.lexsort((whole["pix"][:, 1], whole["pix"][:, 0]))
+    assert got["pos"].shape == whole["pos"].shape
+    for k in ("pos", "n", "wgt", "r2", "pix"):
+        np.testing.assert_array_equal(got[k][order], whole[k][worder])

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from raytrace3_b200 import Context, abi, photon_range  # noqa: E402
+from raytrace3_b200 import Context, abi, photon_range, row_range  # noqa: E402
 from raytrace3_b200.scene import make_scene, reference_camera  # noqa: E402
 
 
@@ -30,7 +30,7 @@ def main():
     ctx.comm_init_rank(rank, world, uid[0])
     # eye-pass sharding: every rank traces its rows, the shares are exchanged over
     # NCCL, and the map must equal the one-GPU eye pass hit point by hit point
-    r0, r1 = cam.h * rank // world, cam.h * (rank + 1) // world
+    r0, r1 = row_range(cam.h, rank, world)
     mine = ctx.eye_pass_rows(cam, 0, r0, r1)
     n = ctx.allgather_hitpoints()
     assert n >= mine > 0
