@@ -112,9 +112,12 @@ def cpu_photon_baseline(wl, scene, prm, hp, target_s=12.0):
     rate = c["photons"] / max(s, 1e-6)
     per_thread = int(max(1500, min(4_000_000, rate * target_s / threads)))
     s, c = orc.photon_bench(scene, prm, hp, per_thread, threads, pass_id=1001)
+    # the reference as shipped runs 4 OpenMP threads = 4 independent replicas (Raytracer.h:429-447)
+    s4, c4 = orc.photon_bench(scene, prm, hp, max(1500, per_thread // 3), min(4, threads), pass_id=1002)
     return dict(value=c["photons"] / s, unit="photons/s", cores=threads, kind="port",
                 sample=f"{threads} threads x {per_thread} photons of {wl} (hit-point map {hp['pos'].shape[0]} pts, exact kd-tree), "
-                       f"{s:.1f} s wall; {c['solves']} Bezier solves"), s, c
+                       f"{s:.1f} s wall; {c['solves']} Bezier solves",
+                as_shipped_4_threads=c4["photons"] / s4), s, c
 
 
 def run_reference(args):
@@ -413,17 +416,23 @@ def main():
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
 def _emit(line: dict):
     """The ONE JSON line of the contract goes to the real stdout; everything else libraries print
     while the benchmark runs (NCCL's version banner, build logs) was redirected to stderr."""
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
-# keep stdout clean for the driver: fd 1 -> stderr until the result line is written
-sys.stdout.flush()
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+def _quiet_stdout():
+    """Keep stdout clean for the driver: fd 1 -> stderr until the result line is written."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 if __name__ == "__main__":
+    _quiet_stdout()
     main()
