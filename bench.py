@@ -102,12 +102,23 @@ def make_params(abi, fast=True):
     return p
 
 
+def host_threads(orc) -> int:
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1, which would
+    silently turn the CPU arm into a single-thread run: the oracle takes an explicit thread
+    count (num_threads clause), so ask the OS instead of OpenMP."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(n, orc.max_threads(), 1)
+
+
 def cpu_photon_baseline(wl, scene, prm, hp, target_s=12.0):
     """The oracle's photon pass on all host cores (each thread an independent tracer over the
     shared hit-point map + exact kd-tree), sized to ~target_s seconds."""
     from oracle import Oracle
     orc = Oracle()
-    threads = orc.max_threads()
+    threads = host_threads(orc)
     s, c = orc.photon_bench(scene, prm, hp, 1500, threads, pass_id=1000)
     rate = c["photons"] / max(s, 1e-6)
     per_thread = int(max(1500, min(4_000_000, rate * target_s / threads)))
@@ -137,7 +148,7 @@ def run_reference(args):
     t0 = time.time()
     hp = orc.eye_pass(scene, prm, cam, 0)
     t_eye = time.time() - t0
-    threads = orc.max_threads()
+    threads = host_threads(orc)
     s, c = orc.photon_bench(scene, prm, hp, 1000, threads, pass_id=999)
     rate = c["photons"] / max(s, 1e-6)
     budget = 150.0 / max(1, args.steps + args.warmup)  # whole run within a few minutes
