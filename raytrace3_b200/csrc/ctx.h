@@ -33,7 +33,18 @@ struct Grid {
   double inv_cell;
   int dim[3];
   int64_t n_cells;
+  // A deposit outside [keep_lo, keep_hi] in some coordinate is farther than sqrt(searchR2) from
+  // every hit point and is not kept: keep_lo/hi = the hit points' bounding box (true
+  // coordinates) grown by one cell edge.  Without this, photons that escape to the far reaches
+  // of the scene's infinite planes are clamped into the grid's boundary cells next to the
+  // visible walls and streamed through the gather for nothing (43 % of the deposits of the
+  // reference scene).
+  double keep_lo[3], keep_hi[3];
 };
+__host__ __device__ inline bool grid_keeps(const Grid& g, double x, double y, double z) {
+  return x >= g.keep_lo[0] && x <= g.keep_hi[0] && y >= g.keep_lo[1] && y <= g.keep_hi[1] && z >= g.keep_lo[2] &&
+         z <= g.keep_hi[2];
+}
 __host__ __device__ inline int64_t grid_cell(const Grid& g, double x, double y, double z) {
 #ifdef __CUDA_ARCH__
   int ix = __double2int_rd((x - g.org[0]) * g.inv_cell);

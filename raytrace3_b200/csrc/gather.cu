@@ -206,7 +206,7 @@ __global__ void dep_key_kernel(const Deposit* dep, long long m, Grid g, const in
                                uint32_t* key, uint32_t* rank, unsigned int* slot_count) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  const int32_t s = cell_slot[grid_cell(g, dep[i].x[0], dep[i].x[1], dep[i].x[2])];
+  const int32_t s = grid_keeps(g, dep[i].x[0], dep[i].x[1], dep[i].x[2]) ? cell_slot[grid_cell(g, dep[i].x[0], dep[i].x[1], dep[i].x[2])] : -1;
   const uint32_t k = s >= 0 ? (uint32_t)s : (uint32_t)n_slots;
   key[i] = k;
   rank[i] = atomicAdd(slot_count + k, 1u);
@@ -1144,7 +1144,7 @@ cudaError_t build_index(sppm_ctx* c) {
     c->n_occ = 0;
     c->n_slots = 0;
     c->n_units = 0;
-    c->grid = Grid{{0, 0, 0}, 1.0, {1, 1, 1}, 1};
+    c->grid = Grid{{0, 0, 0}, 1.0, {1, 1, 1}, 1, {-1e300, -1e300, -1e300}, {1e300, 1e300, 1e300}};
     CK(dev_reserve(c->cell_slot, 4));
     CK(cudaMemsetAsync(c->cell_slot.p, 0xff, 4, st));
     CK(dev_reserve(c->occ_start, 8));
@@ -1184,6 +1184,11 @@ cudaError_t build_index(sppm_ctx* c) {
       double cells = floor((hi[k] - lo[k]) / cell) + 1;
       dim[k] = cells > 1e9 ? 1000000000 : (int)cells;
     }
+    double keep_lo[3], keep_hi[3];
+    for (int k = 0; k < 3; k++) {  // the hit points' own bounds (true coordinates: capping the gridded region does not change them)
+      keep_lo[k] = lo[k] - cell;
+      keep_hi[k] = hi[k] + cell;
+    }
     auto shrink = [&](int k, int nd) {
       double half = 0.5 * nd * cell;
       double ctr = mean[k];
@@ -1207,6 +1212,10 @@ cudaError_t build_index(sppm_ctx* c) {
     }
     g.inv_cell = 1.0 / cell;
     g.n_cells = (int64_t)dim[0] * dim[1] * dim[2];
+    for (int k = 0; k < 3; k++) {
+      g.keep_lo[k] = keep_lo[k];
+      g.keep_hi[k] = keep_hi[k];
+    }
     c->grid = g;
   }
   const Grid g = c->grid;

@@ -222,7 +222,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_TRACE_MINBLOCKS) photon_tr
         if (ob.isDiff) {  // Raytracer.h:136-160: the gather input (x, N, incoming flux)
           deposits++;
           int32_t slot = -1;
-          if (a.cell_slot) slot = __ldg(a.cell_slot + grid_cell(a.grid, s.pos.x, s.pos.y, s.pos.z));
+          if (a.cell_slot && grid_keeps(a.grid, s.pos.x, s.pos.y, s.pos.z))
+            slot = __ldg(a.cell_slot + grid_cell(a.grid, s.pos.x, s.pos.y, s.pos.z));
           if (slot >= 0 || a.keep_all) {
             want = true;
             key = slot >= 0 ? (uint32_t)slot : (uint32_t)a.n_slots;

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
           // before the Roulette / direction arithmetic and consumed after it, and the rank atomic's
           // result is stored at the end of the iteration, so neither latency is waited for here.
           int32_t slot = -1;
-          if (ob.isDiff && a.cell_slot) slot = __ldg(a.cell_slot + grid_cell(a.grid, s.pos.x, s.pos.y, s.pos.z));
+          if (ob.isDiff && a.cell_slot && grid_keeps(a.grid, s.pos.x, s.pos.y, s.pos.z))
+            slot = __ldg(a.cell_slot + grid_cell(a.grid, s.pos.x, s.pos.y, s.pos.z));
           // Obj::Roulette (Obj.h:30-45) and the single continuation (Raytracer.h:162-190)
           double ur, U1;
           draw2(a.seed, a.pass, id, (uint32_t)node, P_BOUNCE, 0, 0, ur, U1);
