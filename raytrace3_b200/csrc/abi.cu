@@ -366,6 +366,60 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
         patchDop[(size_t)p * 26 + 13 + k] = hi + grow;
       }
   }
+  // AABBs of the 4x4 de Casteljau sub-patches (scene.cuh sub_boxes_miss), grown by the same radius
+  std::vector<double> patchSub((size_t)s->n_patches * 96);
+  {
+    // split a cubic Bezier curve c[4] at 1/4, 1/2, 3/4 into four cubic segments seg[4][4] (de Casteljau twice)
+    auto split4 = [](const double c[4], double seg[4][4]) {
+      auto halve = [](const double a[4], double l[4], double r[4]) {
+        const double b0 = 0.5 * (a[0] + a[1]), b1 = 0.5 * (a[1] + a[2]), b2 = 0.5 * (a[2] + a[3]);
+        const double c0 = 0.5 * (b0 + b1), c1 = 0.5 * (b1 + b2), d0 = 0.5 * (c0 + c1);
+        l[0] = a[0]; l[1] = b0; l[2] = c0; l[3] = d0;
+        r[0] = d0; r[1] = c1; r[2] = b2; r[3] = a[3];
+      };
+      double l[4], r[4];
+      halve(c, l, r);
+      halve(l, seg[0], seg[1]);
+      halve(r, seg[2], seg[3]);
+    };
+    for (int p = 0; p < s->n_patches; p++) {
+      double lo[16][3], hi[16][3], big = 0;
+      for (int b = 0; b < 16; b++)
+        for (int k = 0; k < 3; k++) {
+          lo[b][k] = 1e300;
+          hi[b][k] = -1e300;
+        }
+      for (int k = 0; k < 3; k++) {
+        // rows (fixed v index i) split along u, then the columns of every u-segment split along v
+        double rowseg[4][4][4];  // [i][su][j]
+        for (int i = 0; i < 4; i++) {
+          double c[4];
+          for (int j = 0; j < 4; j++) {
+            c[j] = patchP[((size_t)p * 16 + 4 * i + j) * 3 + k];
+            big = std::max(big, std::fabs(c[j]));
+          }
+          split4(c, rowseg[i]);
+        }
+        for (int su = 0; su < 4; su++)
+          for (int j = 0; j < 4; j++) {
+            double c[4], colseg[4][4];
+            for (int i = 0; i < 4; i++) c[i] = rowseg[i][su][j];
+            split4(c, colseg);
+            for (int sv = 0; sv < 4; sv++)
+              for (int i = 0; i < 4; i++) {
+                lo[su * 4 + sv][k] = std::min(lo[su * 4 + sv][k], colseg[sv][i]);
+                hi[su * 4 + sv][k] = std::max(hi[su * 4 + sv][k], colseg[sv][i]);
+              }
+          }
+      }
+      const double grow = 0.0101 + 1e-12 * big;
+      for (int b = 0; b < 16; b++)
+        for (int k = 0; k < 3; k++) {
+          patchSub[(size_t)p * 96 + b * 6 + k] = lo[b][k] - grow;
+          patchSub[(size_t)p * 96 + b * 6 + 3 + k] = hi[b][k] + grow;
+        }
+    }
+  }
   // monomial coefficients per patch and component: A = M G M^T with G[i][k] = P[4i+k] (i <-> v,
   // k <-> u) and M the cubic Bernstein -> power basis matrix
   std::vector<double> patchA((size_t)s->n_patches * 48);
@@ -450,7 +504,7 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
     const SppmTexture& ht = s->textures[t];
     if (ht.rows <= 0 || ht.cols <= 0 || !ht.bgr8) return fail(c, SPPM_ERR_INVALID, "empty texture (Q18: the reference would read out of range)");
     const uint8_t* dev = nullptr;
-    CU(c, upload(c, 7 + (size_t)t, ht.bgr8, (size_t)ht.rows * ht.cols * 3, &dev));
+    CU(c, upload(c, 8 + (size_t)t, ht.bgr8, (size_t)ht.rows * ht.cols * 3, &dev));
     tex[t].rows = ht.rows;
     tex[t].cols = ht.cols;
     tex[t].bgr = dev;
@@ -467,6 +521,7 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
   CU(c, upload(c, 4, tex.data(), tex.size(), &ds.tex));
   CU(c, upload(c, 5, patchA.data(), patchA.size(), &ds.patchA));
   CU(c, upload(c, 6, patchDop.data(), patchDop.size(), &ds.patchDop));
+  CU(c, upload(c, 7, patchSub.data(), patchSub.size(), &ds.patchSub));
   ds.culled = &((DevCounters*)c->counters.p)->patch_culled;
   CU(c, cudaStreamSynchronize(c->stream));  // host vectors go out of scope
   c->scene = ds;
