@@ -355,21 +355,21 @@ def main():
     d = kern[dom]
     achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
     # dram__bytes_read.sum + dram__bytes_write.sum of one gather launch on this workload, from the
-    # ncu --set full captures profiles/r1_u_gather_filtered_ncu.md (550.9 MB read + 47.5 MB written)
+    # ncu --set full captures profiles/r1_A_gather_filtered_ncu.md (297.9 MB read + 30.8 MB written)
     # and profiles/r1_h_gather_ncu.md (exact kernel: 621.3 + 26.4 MB)
     traffic = None
     if dom == gather_name and args.workload == DEFAULT_WORKLOAD and world == 1:
-        traffic = 647.7e6 if args.gather == "exact" else 598.4e6
+        traffic = 647.7e6 if args.gather == "exact" else 328.7e6
     if args.gather == "exact":
         note = ("the binding resource is the FP64 pipe (ncu: 46 % FP64-pipe active, DRAM 2 % busy): per step the kernel "
                 "distance-tests ~5x more (hit point, deposit) pairs than cand_pairs (27-cell neighbourhood vs ball), "
                 "8 FP64 ops each, against 0.5 GB of compulsory traffic; fp64_tflops counts only the SURVEY 8d flops")
     else:
-        note = ("instruction-issue bound, not HBM bound (ncu r1_u: issue slots 66 % busy, ALU pipe 36 %, FMA pipe 19 % "
-                "[packed FADD2/FFMA2], FP64 pipe 16 %, DRAM 6 % busy): ~0.5 G (hit point, deposit) pairs survive the "
-                "bounding-box cull and are classified in FP32 at ~17 warp instructions per 64 pairs, against 0.5 GB of "
+        note = ("instruction-issue bound, not HBM bound (ncu r1_A: issue slots 70 % busy, ALU pipe 39 %, FMA pipe 24 % "
+                "[packed FADD2/FFMA2], FP64 pipe 20 %, DRAM 5 % busy): ~0.5 G (hit point, deposit) pairs survive the "
+                "bounding-box cull and are classified in FP32 at ~17 warp instructions per 64 pairs, against 0.3 GB of "
                 "compulsory traffic; the timed span is measured while a photon-tracing lane shares the SMs "
-                "(1.28 ms when the kernel runs alone); fp64_tflops counts only the SURVEY 8d flops")
+                "(0.84 ms when the kernel runs alone); fp64_tflops counts only the SURVEY 8d flops")
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": d["bytes"],
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, sustained copy)",
