@@ -590,7 +590,8 @@ def test_full_size_properties(ctx):
     (a) sum(newN) == accepted-pair counter and every pair was distance-tested first;
     (b) linearity: two half rounds == one full round (newN bit-exact, tao to rounding);
     (c) the film is the density estimate of tao (resolve), row-major [h][w][3];
-    (d) per-photon statistics match the CPU probe (5.9 queries, 3.7 deposits)."""
+    (d) per-photon statistics match the CPU probe (SURVEY §8d: 5.9 queries, 3.7 deposits);
+    (e) FILTERED gather == EXACT gather: newN and the pair counters bit for bit."""
     sc = make_scene("reference", textures="synthetic")
     prm = _params(newton_mode=abi.SPPM_NEWTON_FAST)
     ctx.set_params(prm)
@@ -623,6 +624,18 @@ def test_full_size_properties(ctx):
     halves = ctx.export_stats(n)
     np.testing.assert_array_equal(halves["newN"], full["newN"])
     np.testing.assert_allclose(halves["tao"], full["tao"], rtol=1e-11, atol=0)
+    # (e) the packed-FP32 filtered gather (default) against the FP64-on-every-pair kernel on the
+    # same 2 M photons: identical decisions on all 213 M candidate pairs
+    ctx.set_params(_params(newton_mode=abi.SPPM_NEWTON_FAST, gather_mode=abi.SPPM_GATHER_EXACT))
+    ctx.build_index()
+    ctx.reset_counters()
+    ctx.photon_pass(0, onetime, 1)
+    ctx.update()
+    exact = ctx.export_stats(n)
+    ce = ctx.counters()
+    np.testing.assert_array_equal(exact["newN"], full["newN"])
+    np.testing.assert_allclose(exact["tao"], full["tao"], rtol=1e-11, atol=0)
+    assert (ce["cand_pairs"], ce["acc_pairs"], ce["deposits_kept"]) == (c["cand_pairs"], c["acc_pairs"], c["deposits_kept"])
 
 
 def test_newton_fast_sweep_against_exact(ctx):
