@@ -204,7 +204,7 @@ def main():
     assert world == args.gpus or world == 1 and args.gpus == 1, f"launch with torchrun --nproc-per-node {args.gpus}"
 
     import torch
-    from raytrace3_b200 import Context, abi
+    from raytrace3_b200 import Context, abi, row_range
     from raytrace3_b200.scene import make_scene, reference_camera
 
     dist = None
@@ -297,7 +297,12 @@ def main():
         t0 = time.perf_counter()
         ctx.upload_scene(scene)                      # H2D: objects, patches, textures (pinned host memory)
         t1 = time.perf_counter()
-        ctx.eye_pass(cam, 100 + i)
+        if world > 1:  # eye-pass sharding: every rank traces its film rows, the shares are exchanged over NCCL
+            r0, r1 = row_range(cam.h, rank, world)
+            ctx.eye_pass_rows(cam, 100 + i, r0, r1)
+            ctx.allgather_hitpoints()
+        else:
+            ctx.eye_pass(cam, 100 + i)
         t2 = time.perf_counter()
         ctx.build_index()
         t3 = time.perf_counter()

@@ -296,7 +296,7 @@ void sppm_ctx_destroy(sppm_ctx* c) {
   }
   if (c->ev_setup) cudaEventDestroy(c->ev_setup);
   free_scene(c);
-  DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->units, &c->item_parts, &c->item_off, &c->px_store, &c->dep_key, &c->dep_key2,
+  DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->units, &c->item_parts, &c->item_off, &c->px_store, &c->hp_raw_alt, &c->dep_key, &c->dep_key2,
                     &c->dep_idx, &c->dep_idx2, &c->scan_scratch, &c->cub_tmp, &c->dev_scalars, &c->counters, &c->film, &c->scratch};
   for (DevBuf* d : bufs) dev_free(*d);
   for (int i = 0; i < 8; i++)
@@ -594,7 +594,7 @@ int sppm_allgather_hitpoints(sppm_ctx* c, int64_t* n_hitpoints) {
   unsigned long long total = 0;
   for (auto v : counts) total += v;
   if ((int64_t)total > c->hp_cap) return fail(c, SPPM_ERR_CAPACITY, "hit-point buffer overflow in the all-gather");
-  DevBuf all;
+  DevBuf& all = c->hp_raw_alt;  // second raw buffer, kept across calls (no allocation in steady state)
   CU(c, dev_reserve(all, (size_t)c->hp_cap * sizeof(HpRaw)));
   r = n.GroupStart();
   unsigned long long off = 0;
@@ -607,17 +607,13 @@ int sppm_allgather_hitpoints(sppm_ctx* c, int64_t* n_hitpoints) {
   }
   const ncclResult_t r2 = n.GroupEnd();
   if (r == ncclSuccess) r = r2;
-  if (r != ncclSuccess) {
-    dev_free(all);
+  if (r != ncclSuccess)
     return fail(c, SPPM_ERR_NCCL, std::string("hit-point exchange: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
-  }
-  CU(c, cudaStreamSynchronize(c->stream));
-  dev_free(c->hp_raw);
-  c->hp_raw = all;
+  std::swap(c->hp_raw, c->hp_raw_alt);  // stream-ordered: later work on c->stream sees the gathered map
   c->n_hp = (int64_t)total;
   const unsigned long long t = total;
   CU(c, cudaMemcpyAsync(scalars(c), &t, 8, cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));  // t is a stack variable
   c->index_ok = false;
   if (n_hitpoints) *n_hitpoints = c->n_hp;
   return SPPM_OK;

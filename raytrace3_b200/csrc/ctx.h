@@ -120,6 +120,7 @@ struct sppm_ctx {
   size_t trace_smem = 0;
   // hit points
   sppm::DevBuf hp_raw;     // HpRaw[cap]
+  sppm::DevBuf hp_raw_alt; // receive buffer of sppm_allgather_hitpoints (swapped with hp_raw)
   int64_t hp_cap = 0, n_hp = 0;
   int film_w = 0, film_h = 0;
   sppm::DevBuf soa_store;  // backing store of HpSoA
