@@ -341,6 +341,17 @@ __device__ __forceinline__ PatchEval eval_mono(const double* __restrict__ A, dou
   return e;
 }
 
+// 1/x to ~1 ulp without the IEEE division routine: hardware seed (20 bits) + two Newton-Raphson
+// steps in FMA.  FAST Newton mode only (its results are already "the same polynomial, different
+// rounding", checked against EXACT to 1e-6 by the sweep tests).
+__device__ __forceinline__ double rcp_newton(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 // One Newton step x = prevX - inv([dir, -Su, -Sv]) * (org + dir*t - S)  (Bezier.h:121-131).
 // The inverse is cv::Matx33d::inv's closed form (adjugate / determinant, zeros when the
 // determinant is exactly 0) held in registers.
@@ -357,7 +368,7 @@ __device__ __forceinline__ void newton_step(d3 org, d3 dir, const PatchEval& e, 
     const double c20 = fma(a10, a21, -(a11 * a20)), c21 = fma(a01, a20, -(a00 * a21)), c22 = fma(a00, a11, -(a01 * a10));
     double d = fma(a02, c20, fma(a01, c10, a00 * c00));
     if (d != 0) {
-      d = 1 / d;
+      d = rcp_newton(d);
       t -= fma(c02, r.z, fma(c01, r.y, c00 * r.x)) * d;
       u -= fma(c12, r.z, fma(c11, r.y, c10 * r.x)) * d;
       v -= fma(c22, r.z, fma(c21, r.y, c20 * r.x)) * d;
