@@ -275,6 +275,18 @@ def main():
     stat = ctx.counters()
     cnt["cand_pairs"] = stat["cand_pairs"] * args.steps // 2
     value = total_photons / (ms * 1e-3)
+    # serialised rounds (a device sync after every step, so no lane overlaps another): per-kernel
+    # times as ncu's launch list sees them, to check the kernels' shares of a round against it
+    prm.count_pairs = 1 if args.count_pairs else 0
+    ctx.set_params(prm)
+    ctx.reset_counters()
+    n_serial = 4
+    for i in range(n_serial):
+        step(args.warmup + args.steps + 2 + i)
+        barrier()
+    ser = ctx.counters()
+    serial = {k: ser[f"ms_{k}"] / n_serial for k in ("trace", "sort", "gather")}
+    serial["round"] = serial["trace"] + serial["sort"] + serial["gather"]  # + update, 0.05 ms
 
     # ---- e2e: RayTracer::render() through the public API with host buffers
     from raytrace3_b200 import RayTracer
@@ -379,6 +391,10 @@ def main():
                 "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": d["bytes"],
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, sustained copy)",
                 "ms_per_launch": d["ms"], "share_of_step": d["ms"] / (ms / steps),
+                "serialized": {"what": "rounds separated by device syncs (no overlap between lanes): the view ncu's launch list has",
+                               "ms_per_launch": serial["gather"], "trace_and_binning_ms": serial["trace"],
+                               "share_of_round": serial["gather"] / serial["round"] if serial["round"] > 0 else None,
+                               "GBps": d["bytes"] / (serial["gather"] * 1e-3) / 1e9 if dom == gather_name and serial["gather"] > 0 else None},
                 "fp64_tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0, "fp64_peak_tflops": fp64_peak,
                 "fp64_frac": (d["flops"] / (d["ms"] * 1e-3) / 1e12 / fp64_peak) if d["ms"] > 0 and fp64_peak > 0 else None,
                 "note": note}
