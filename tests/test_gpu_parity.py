@@ -232,6 +232,57 @@ def test_gather_threshold_band_adversarial(ctx, oracle, gmode):
     assert c["cand_pairs"] == cand and c["acc_pairs"] == acc
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_gather_filtered_fuzz_against_exact(ctx, seed):
+    """Random hit-point / deposit clouds of very different shapes (isolated hit points, long sparse
+    runs along x, one cell with hundreds of hit points, planar sheets, thousands of deposits on a few
+    cells so that units are split into several work items, deposits far outside the hit points'
+    bounds, per-hit-point radii): the FILTERED kernel must reproduce the EXACT kernel's newN and pair
+    counters bit for bit and tao to rounding."""
+    rng = np.random.RandomState(100 + seed)
+    parts = []
+    n_sheet = rng.randint(200, 4000)
+    parts.append(np.stack([rng.uniform(0, 40, n_sheet), np.full(n_sheet, 3.0) + rng.normal(0, 1e-3, n_sheet), rng.uniform(0, 25, n_sheet)], 1))
+    n_run = rng.randint(5, 80)                                   # a sparse run along x: one hit point per cell
+    parts.append(np.stack([50 + 1.42 * np.arange(n_run) + rng.uniform(0, 0.3, n_run), np.full(n_run, 10.0), np.full(n_run, 5.0)], 1))
+    n_blob = rng.randint(70, 600)                                # one dense cell
+    parts.append(np.array([20.0, 20.0, 20.0]) + rng.uniform(-0.6, 0.6, size=(n_blob, 3)))
+    parts.append(rng.uniform(-30, 120, size=(rng.randint(1, 30), 3)))  # isolated points
+    pos = np.concatenate(parts)
+    n = pos.shape[0]
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[:n_sheet] = (0, 1, 0)
+    r2 = np.where(rng.uniform(size=n) < 0.6, 2.0, rng.uniform(0.05, 2.0, size=n))
+    pix = np.stack([rng.randint(0, 48, n), rng.randint(0, 64, n)], axis=1).astype(np.int32)
+    wgt = rng.uniform(0.1, 1, size=(n, 3))
+    m = rng.randint(2000, 60000)
+    x = pos[rng.randint(0, n, m)] + rng.normal(0, rng.choice([0.3, 1.0, 3.0]), size=(m, 3))
+    heavy = rng.randint(0, m, m // 3)                            # a third of them on the dense cell and the sheet corner
+    x[heavy] = np.array([20.0, 20.0, 20.0]) + rng.normal(0, 1.0, size=(heavy.size, 3))
+    x[: m // 50] = rng.uniform(-5000, 5000, size=(m // 50, 3))   # far outside the hit points' bounds
+    dn = rng.normal(size=(m, 3))
+    dn /= np.linalg.norm(dn, axis=1, keepdims=True)
+    flat = rng.uniform(size=m) < 0.5
+    dn[flat] = (0, 1, 0)
+    flux = rng.uniform(0, 50, size=(m, 3))
+    out = []
+    for gmode in GATHER_MODES:
+        ctx.set_params(_params(gather_mode=gmode))
+        ctx.import_hitpoints(pos, nrm, wgt, r2, pix, 64, 48)
+        ctx.build_index()
+        ctx.reset_counters()
+        ctx.gather_deposits(x, dn, flux)
+        ctx.update()
+        c = ctx.counters()
+        out.append((ctx.export_stats(n), (c["cand_pairs"], c["acc_pairs"])))
+    (se, ce), (sf, cf) = out
+    assert se["newN"].sum() > 100
+    np.testing.assert_array_equal(sf["newN"], se["newN"])
+    assert cf == ce
+    np.testing.assert_allclose(sf["tao"], se["tao"], rtol=1e-11, atol=0)
+
+
 @pytest.mark.parametrize("gmode", GATHER_MODES)
 @pytest.mark.parametrize("mode", [abi.SPPM_UPDATE_REFERENCE, abi.SPPM_UPDATE_PROGRESSIVE])
 def test_update_modes(ctx, oracle, mode, gmode):
