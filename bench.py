@@ -402,7 +402,7 @@ def main():
                    "hbm_frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak if v["ms"] > 0 else 0.0,
                    "fp64_tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0} for k, v in kern.items()}
     kernels["deposit_binning"] = {"ms_per_step": ms_sort}
-    kernels["note"] = ("rounds rotate over three lanes: the traces of rounds i+1, i+2 (lane streams) overlap the gather of round i "
+    kernels["note"] = ("rounds rotate over four lanes: the traces of rounds i+1 .. i+3 (lane streams) overlap the gather of round i "
                        "(main stream); per-kernel ms are event spans on their own stream and sum to more than ms_per_step")
 
     # ---- Bezier ray-patch intersections per second (metric M2), device-resident microbench
