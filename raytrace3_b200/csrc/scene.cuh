@@ -214,32 +214,22 @@ static __device__ __noinline__ bool sub_boxes_miss(const double* __restrict__ su
   double inv[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) inv[k] = dd[k] != 0 ? 1.0 / dd[k] : 0.0;
-  // four boxes per round: their 24 bounds are loaded together (one memory latency per round, not per box)
-  for (int b0 = 0; b0 < 16; b0 += 4) {
-    double bx[4][6];
+  for (int b = 0; b < 16; b++) {
+    const double* bx = sub + b * 6;
+    double tmin = -1e300, tmax = 1e300;
+    bool miss = false;
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-#pragma unroll
-      for (int k = 0; k < 6; k++) bx[j][k] = __ldg(sub + (b0 + j) * 6 + k);
-    bool touch = false;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      double tmin = -1e300, tmax = 1e300;
-      bool miss = false;
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        const double lo = bx[j][k] - oo[k], hi = bx[j][3 + k] - oo[k];
-        if (dd[k] == 0) {
-          miss = miss || lo > 0 || hi < 0;
-        } else {
-          const double t0 = lo * inv[k], t1 = hi * inv[k];
-          tmin = fmax(tmin, fmin(t0, t1));
-          tmax = fmin(tmax, fmax(t0, t1));
-        }
+    for (int k = 0; k < 3; k++) {
+      const double lo = __ldg(bx + k) - oo[k], hi = __ldg(bx + 3 + k) - oo[k];
+      if (dd[k] == 0) {
+        miss = miss || lo > 0 || hi < 0;
+      } else {
+        const double t0 = lo * inv[k], t1 = hi * inv[k];
+        tmin = fmax(tmin, fmin(t0, t1));
+        tmax = fmin(tmax, fmax(t0, t1));
       }
-      touch = touch || (!miss && !(tmin > tmax + 1e-9 * (1.0 + fabs(tmin) + fabs(tmax))));
     }
-    if (touch) return false;  // the line may come within the acceptance radius of one of these sub-patches
+    if (!miss && !(tmin > tmax + 1e-9 * (1.0 + fabs(tmin) + fabs(tmax)))) return false;  // the line may touch this box
   }
   return true;
 }
