@@ -167,6 +167,10 @@ void free_scene(sppm_ctx* c) {
   c->scene_bufs.clear();
   c->scene_ok = false;
 }
+__global__ void tex_expand_kernel(const uint8_t* bgr, size_t n, uint32_t* out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)bgr[3 * i] | ((uint32_t)bgr[3 * i + 1] << 8) | ((uint32_t)bgr[3 * i + 2] << 16);
+}
 // Scene arrays live in grow-only device buffers (slot i of scene_bufs) that are reused by the
 // next upload: re-uploading a scene of the same shape costs only the copies.
 template <class T>
@@ -508,6 +512,13 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
     tex[t].rows = ht.rows;
     tex[t].cols = ht.cols;
     tex[t].bgr = dev;
+    // one 32-bit word per texel for the tracers (scene.cuh tex_fetch), expanded on the device
+    const size_t slot = 8 + (size_t)s->n_textures + (size_t)t, ntexel = (size_t)ht.rows * ht.cols;
+    if (c->scene_bufs.size() <= slot) c->scene_bufs.resize(slot + 1);
+    CU(c, dev_reserve(c->scene_bufs[slot], ntexel * 4));
+    tex_expand_kernel<<<(unsigned)((ntexel + 255) / 256), 256, 0, c->stream>>>(dev, ntexel, (uint32_t*)c->scene_bufs[slot].p);
+    c->host_counters.launches++;
+    tex[t].bgrx = (const uint32_t*)c->scene_bufs[slot].p;
   }
   DevScene ds;
   ds.n_obj = s->n_objects;

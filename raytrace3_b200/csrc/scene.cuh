@@ -34,6 +34,7 @@ struct DevObject {
 struct DevTexture {
   int rows, cols;
   const uint8_t* bgr;
+  const uint32_t* bgrx;  // the same texels, one 32-bit word each (B | G << 8 | R << 16): one load per texel
 };
 struct DevScene {
   int n_obj, n_patch, n_light, n_tex;
@@ -126,28 +127,45 @@ __device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, 
 }
 
 // ---- Element.h:61-72 Texture::colorUV ------------------------------------------------
-__device__ inline d3 color_uv(const DevTexture& t, const double* __restrict__ lut255, double u, double v) {
+// tex_fetch issues the four texel loads (one 32-bit word per texel instead of three byte loads),
+// tex_finish does the look-ups of b / 255.0 and the bilinear blend in the reference's expression
+// order.  (Deferring tex_finish behind the direction arithmetic was measured: the extra live
+// registers cost more than the hidden latency.)
+struct TexFetch {
+  uint32_t p11, p12, p21, p22;
+  double detR, detC;
+};
+__device__ __forceinline__ TexFetch tex_fetch(const DevTexture& t, double u, double v) {
   const int rows = t.rows, cols = t.cols;
   double row = (u - floor(u)) * rows, col = (v - floor(v)) * cols;
   int r1 = (int)floor(row + 1e-10), r2 = r1 + 1;
   int c1 = (int)floor(col + 1e-10), c2 = c1 + 1;
-  double detR = r2 - row, detC = c2 - col;
+  TexFetch f;
+  f.detR = r2 - row;
+  f.detC = c2 - col;
   r1 = (r1 >= 0) ? (r1 >= rows ? 0 : r1) : (rows - 1);
   c1 = (c1 >= 0) ? (c1 >= cols ? 0 : c1) : (cols - 1);
   r2 = (r2 < rows) ? r2 : 0;
   c2 = (c2 < cols) ? c2 : 0;
-  const uint8_t* p11 = t.bgr + ((size_t)r1 * cols + c1) * 3;
-  const uint8_t* p12 = t.bgr + ((size_t)r1 * cols + c2) * 3;
-  const uint8_t* p21 = t.bgr + ((size_t)r2 * cols + c1) * 3;
-  const uint8_t* p22 = t.bgr + ((size_t)r2 * cols + c2) * 3;
+  f.p11 = __ldg(t.bgrx + (size_t)r1 * cols + c1);
+  f.p12 = __ldg(t.bgrx + (size_t)r1 * cols + c2);
+  f.p21 = __ldg(t.bgrx + (size_t)r2 * cols + c1);
+  f.p22 = __ldg(t.bgrx + (size_t)r2 * cols + c2);
+  return f;
+}
+__device__ __forceinline__ d3 tex_finish(const TexFetch& f, const double* __restrict__ lut255) {
   double o[3];
+  const double detR = f.detR, detC = f.detC;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    const double a = lut255[__ldg(p11 + k)], b = lut255[__ldg(p12 + k)], c = lut255[__ldg(p21 + k)],
-                 d = lut255[__ldg(p22 + k)];
+    const double a = lut255[(f.p11 >> (8 * k)) & 255u], b = lut255[(f.p12 >> (8 * k)) & 255u], c = lut255[(f.p21 >> (8 * k)) & 255u],
+                 d = lut255[(f.p22 >> (8 * k)) & 255u];
     o[k] = ((a * detR * detC + b * detR * (1 - detC)) + c * (1 - detR) * detC) + d * (1 - detR) * (1 - detC);
   }
   return d3{o[0], o[1], o[2]};
+}
+__device__ inline d3 color_uv(const DevTexture& t, const double* __restrict__ lut255, double u, double v) {
+  return tex_finish(tex_fetch(t, u, v), lut255);
 }
 
 // ---- Bezier.h:20-51 AABBbox::intersect (entry faces only, Q5) ---------------------------
