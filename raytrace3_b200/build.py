@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
     "--expt-relaxed-constexpr",
-    "-Xptxas", "-v",
+    "-Xptxas", "-v", *(os.environ.get("SPPM_NVCC_EXTRA", "").split()),
 ]
 
 

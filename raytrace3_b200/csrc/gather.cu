@@ -143,7 +143,10 @@ __global__ void occ_run_kernel(const uint32_t* occ_cell, int n_occ, Grid g, cons
 __global__ void set_last_kernel(int32_t* starts, int n_occ, int32_t n_hp) { starts[n_occ] = n_hp; }
 
 // ---- work units of the filtered gather ----------------------------------------------------
-constexpr int UNIT_HP = 64;  // hit points per unit (two per lane)
+#ifndef SPPM_UNIT_HP
+#define SPPM_UNIT_HP 64
+#endif
+constexpr int UNIT_HP = SPPM_UNIT_HP;  // hit points per unit: 64 (two per lane) or 32
 // flag[o] = 1 when occupied cell o starts a run of x-adjacent occupied cells
 __global__ void run_flag_kernel(const uint32_t* occ_cell, int n_occ, int dim0, int32_t* flag) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
@@ -652,10 +655,11 @@ __device__ __noinline__ void careful_pairs(const HpSoA s, const int i, const dou
 // points of the chunk.  A converted pair is 96 bytes: {x0,x1,y0,y1} {z0,z1,nx0,nx1}
 // {ny0,ny1,nz0,nz1} in FP32 and the two fluxes {fx0,fy0} {fz0,fx1} {fy1,fz1} in FP64; the
 // accumulation is predicated, not branched.
+constexpr int HBMAX = UNIT_HP > 32 ? 2 : 1;  // hit points per lane
 template <bool UNI, bool COUNT, int HB>
 __device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const int j0, const int jstep, const int npair,
-                                           const HpF (&h)[2], const float sr2f, int (&c)[2], unsigned& cand,
-                                           double (&acc)[2][3], float (&uv)[2], float (&un)[2]) {
+                                           const HpF (&h)[HBMAX], const float sr2f, int (&c)[HBMAX], unsigned& cand,
+                                           double (&acc)[HBMAX][3], float (&uv)[HBMAX], float (&un)[HBMAX]) {
   const float thrf = (float)SPPM_NORMAL_AGREE;
   unsigned cd = 0;
   const float4* q = cv + j0 * F_PAIR_F4;
@@ -701,8 +705,11 @@ __device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const 
   cand += cd;
 }
 
+#ifndef SPPM_GATHER_MINBLOCKS
+#define SPPM_GATHER_MINBLOCKS 2
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const GatherArgs a, unsigned int* work_counter) {
+__global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filtered_kernel(const GatherArgs a, unsigned int* work_counter) {
   extern __shared__ __align__(128) unsigned char wsm[];
   __shared__ __align__(8) uint64_t bar[W_WARPS][2];
   __shared__ int run_pre[W_WARPS][12];  // per warp: run starts [0..8] are kept in registers; prefix of run lengths here
@@ -807,25 +814,31 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
       if (n_sl > 1) issue(1);
     }
     // hit points of the unit: lane = hit point (+32), sub-slices when there are <= 16
-    const bool two = H > 32;
+    const bool two = HBMAX > 1 && H > 32;
     int hl = 32, lg = 5;
     if (!two) {
       hl = 1; lg = 0;
       while (hl < H) { hl <<= 1; lg++; }
     }
     const int sub = 32 >> lg, my_h = lane & (hl - 1), sub_id = lane >> lg;
-    const int idx[2] = {h0 + my_h, h0 + 32 + lane};
-    const bool valid[2] = {my_h < H, two && 32 + lane < H};
+    int idx[HBMAX];
+    bool valid[HBMAX];
+    idx[0] = h0 + my_h;
+    valid[0] = my_h < H;
+    if (HBMAX > 1) {
+      idx[HBMAX - 1] = h0 + 32 + lane;
+      valid[HBMAX - 1] = two && 32 + lane < H;
+    }
     const double half_x = 0.5 * ncx * cell * (1.0 + 1e-7), M_x = (0.5 * ncx + 1.0) * cell * (1.0 + 1e-6);
     const double Mn = sqrt(M_x * M_x + 2.0 * M_yz * M_yz);
     const double band_v = SPPM_F_U * (8.0 * a.search_r2 + 6.0 * sqrt(a.search_r2) * Mn) + 1e-13 * Mn * Mn;
     const float cull_thr = __double2float_ru(a.search_r2 + 2.0 * band_v);
-    HpF hp[2];
-    bool far_hp[2] = {false, false};
+    HpF hp[HBMAX];
+    bool far_hp[HBMAX] = {};
     bool uni_me = true;
     float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
 #pragma unroll
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < HBMAX; b++) {
       hp[b] = HpF{-SPPM_F_PAD, -SPPM_F_PAD, -SPPM_F_PAD, 0.f, 0.f, 0.f, 0.f, 0.f};  // never close, not even to a padding deposit
       if (valid[b]) {
         const int i = idx[b];
@@ -853,8 +866,8 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
         blo[k] = fminf(blo[k], __shfl_xor_sync(FULL, blo[k], off));
         bhi[k] = fmaxf(bhi[k], __shfl_xor_sync(FULL, bhi[k], off));
       }
-    int cnt[2] = {0, 0};
-    double sum[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    int cnt[HBMAX] = {};
+    double sum[HBMAX][3] = {};
     unsigned cand32 = 0;
     for (int k = 0; k < n_sl; k++) {
       const int buf = k & 1;
@@ -908,29 +921,34 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
       }
       __syncwarp();
       {
-        int c_t[2] = {0, 0};
-        double t[2][3] = {{0, 0, 0}, {0, 0, 0}};
-        float uv[2] = {3.0e38f, 3.0e38f}, un2[2] = {3.0e38f, 3.0e38f};
+        int c_t[HBMAX] = {};
+        double t[HBMAX][3] = {};
+        float uv[HBMAX], un2[HBMAX];
+#pragma unroll
+        for (int b = 0; b < HBMAX; b++) uv[b] = un2[b] = 3.0e38f;
         unsigned cd_t = 0;
         const int npair = (n_k + 1) >> 1;
         if (!any_badn) {
-          if (two) {
-            if (uni) fast_pairs<true, COUNT, 2>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
-            else fast_pairs<false, COUNT, 2>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+          if (HBMAX > 1 && two) {
+            if (uni) fast_pairs<true, COUNT, HBMAX>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+            else fast_pairs<false, COUNT, HBMAX>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
           } else {
             if (uni) fast_pairs<true, COUNT, 1>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
             else fast_pairs<false, COUNT, 1>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
           }
         }
-        bool redo[2];
+        bool redo[HBMAX];
+        bool any_redo = false;
 #pragma unroll
-        for (int b = 0; b < 2; b++)
+        for (int b = 0; b < HBMAX; b++) {
           redo[b] = valid[b] && (any_badn || far_hp[b] || !(uv[b] > hp[b].band) || !(un2[b] > SPPM_F_NBAND));
-        if (redo[0] || redo[1]) {
+          any_redo = any_redo || redo[b];
+        }
+        if (any_redo) {
           // the fast counters of this lane cover both hit points: recount them exactly
           unsigned cd_x = 0;
 #pragma unroll
-          for (int b = 0; b < 2; b++) {
+          for (int b = 0; b < HBMAX; b++) {
             if (!valid[b]) continue;
             const bool whole = any_badn || far_hp[b];  // not list based: every raw record of the slice in FP64
             int c_x;
@@ -944,7 +962,7 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
           cd_t = cd_x;
         }
 #pragma unroll
-        for (int b = 0; b < 2; b++) {
+        for (int b = 0; b < HBMAX; b++) {
           cnt[b] += c_t[b];
           sum[b][0] += t[b][0]; sum[b][1] += t[b][1]; sum[b][2] += t[b][2];
         }
@@ -953,12 +971,12 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
       __syncwarp();  // raw / conv / kidx consumed by every lane
       if (lane == 0 && k + 2 < n_sl) issue(k + 2);
     }
-    acc_total += (unsigned)(cnt[0] + cnt[1]);
+    acc_total += (unsigned)(cnt[0] + (HBMAX > 1 ? cnt[HBMAX - 1] : 0));
     cand += cand32;
     // combine the sub-slices of a hit point (lanes my_h, my_h + hl, ...)
     for (int o = hl; o < 32; o <<= 1) {
 #pragma unroll
-      for (int b = 0; b < 2; b++) {
+      for (int b = 0; b < HBMAX; b++) {
         cnt[b] += __shfl_xor_sync(FULL, cnt[b], o);
         sum[b][0] += __shfl_xor_sync(FULL, sum[b][0], o);
         sum[b][1] += __shfl_xor_sync(FULL, sum[b][1], o);
@@ -967,7 +985,7 @@ __global__ void __launch_bounds__(W_THREADS, 2) gather_filtered_kernel(const Gat
     }
     if (sub_id == 0) {
 #pragma unroll
-      for (int b = 0; b < 2; b++) {
+      for (int b = 0; b < HBMAX; b++) {
         if (valid[b] && cnt[b] > 0) {  // hp->newN++, hp->tao += wgt.mul(flux)*PI_INV (Raytracer.h:155-156)
           const int i = idx[b];
           const double d0 = (a.s.wx[i] * sum[b][0]) * SPPM_PI_INV, d1 = (a.s.wy[i] * sum[b][1]) * SPPM_PI_INV,
