@@ -8,7 +8,8 @@
 //                           shade, deposit, Roulette, next direction]; then the next query's
 //                           analytic tests (planes / spheres) and the cooperative Bezier AABB
 //                           culling, which appends (photon slot, patch) items to a global list;
-//                           survivors are re-compacted with a warp-aggregated counter.
+//                           survivors are re-compacted into four regions of the queue, by what
+//                           their pending hit makes the next step do.
 //   newton_items_kernel(b)  Bezier3::newton (Bezier.h:112-159) for all queued items, the
 //                           item x restart tasks packed over full warps.
 //
@@ -56,9 +57,9 @@ struct StepArgs {
   DevCounters* counters;
   Queue qin, qout;
   Items it_in, it_out;
-  const unsigned* n_in_ptr;  // [2]: photons queued from the front (plane hits) and from the back (others)
+  const unsigned* n_in_ptr;  // [4]: photons queued in the four regions (see photon_step_kernel)
   unsigned n_in_host;
-  unsigned* n_out;           // [2]
+  unsigned* n_out;           // [4]
   unsigned q_cap;
   unsigned* n_items_out;
   unsigned item_cap;
@@ -87,22 +88,30 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
   extern __shared__ __align__(16) unsigned char smem[];
   const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem, false);
   const int lane = threadIdx.x & 31;
-  // The queue is filled from both ends: photons whose pending hit is a plane (3/4 of them, one
-  // coherent shading path) from slot 0 upwards, all others from slot q_cap-1 downwards; photons
-  // that hit nothing are dropped when they are found.  Warps therefore shade uniform work.
-  const unsigned n_front = a.bounce == 0 ? a.n_in_host : a.n_in_ptr[0];
-  const unsigned n_back = a.bounce == 0 ? 0u : a.n_in_ptr[1];
-  const unsigned front_chunks = (n_front + 31) >> 5;
-  const unsigned n_in = front_chunks * 32 + n_back;  // virtual index space: [front chunks | back]
+  // The queue arrays hold 2 x q_cap entries and are filled from four ends, by what the pending hit
+  // will make the next step do, so that warps shade uniform work:
+  //   region 0 [0 ->)             a plane with a diffuse part (most photons: one coherent path)
+  //   region 1 [<- q_cap)         a purely specular object (mirror / glass: short reflect / refract paths)
+  //   region 2 [q_cap ->)         a sphere with a diffuse part
+  //   region 3 [<- 2 q_cap)       Bezier solves pending (the item merge + patch evaluation path)
+  // Photons that hit nothing are dropped when they are found.  The virtual index space of a step is
+  // [region 0 | region 1 | region 2 | region 3], the first three padded to whole warps.
+  unsigned nreg[4];
+  nreg[0] = a.bounce == 0 ? a.n_in_host : a.n_in_ptr[0];
+#pragma unroll
+  for (int r = 1; r < 4; r++) nreg[r] = a.bounce == 0 ? 0u : a.n_in_ptr[r];
+  const unsigned c0 = ((nreg[0] + 31) >> 5) * 32, c1 = c0 + ((nreg[1] + 31) >> 5) * 32, c2 = c1 + ((nreg[2] + 31) >> 5) * 32;
+  const unsigned n_in = c2 + nreg[3];
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
   unsigned queries = 0, solves = 0, photons = 0, deposits = 0, kept = 0;  // per thread, < 2^32
 
   for (unsigned base = warp_global * 32; base < n_in; base += n_warps * 32) {
     const unsigned vi = base + lane;
-    const bool in_front = base < front_chunks * 32;
-    const bool active = in_front ? vi < n_front : vi < n_in;
-    const unsigned i = in_front ? vi : a.q_cap - 1 - (vi - front_chunks * 32);
+    const int reg = base < c0 ? 0 : (base < c1 ? 1 : (base < c2 ? 2 : 3));  // warp-uniform
+    const unsigned k = vi - (reg == 0 ? 0u : (reg == 1 ? c0 : (reg == 2 ? c1 : c2)));  // index within the region
+    const bool active = k < nreg[reg];
+    const unsigned i = reg == 0 ? k : (reg == 1 ? a.q_cap - 1 - k : (reg == 2 ? a.q_cap + k : 2 * a.q_cap - 1 - k));
     bool alive = false;
     unsigned rank_val = 0;
     unsigned long long rank_at = ~0ull;  // deposit whose rank-in-slot is still in flight
@@ -240,19 +249,22 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
     if (rank_at != ~0ull) a.dep_rank[rank_at] = rank_val;  // the atomic issued before the Roulette has landed by now
     // ---- compaction of the survivors into the output queue (front: plane hits, back: the rest)
     if (alive && best.obj < 0 && boxobj == 0) alive = false;  // hit nothing (Raytracer.h:127): the photon is gone
-    const bool to_front = alive && boxobj == 0 && sv.obj[best.obj < 0 ? 0 : best.obj].kind == SPPM_OBJ_PLANE;
+    int oreg = 3;  // Bezier solves pending
+    if (alive && boxobj == 0) {
+      const DevObject& bo = sv.obj[best.obj];
+      oreg = !bo.isDiff ? 1 : (bo.kind == SPPM_OBJ_PLANE ? 0 : 2);
+    }
     const unsigned am = __ballot_sync(FULL, alive);
     if (!am) continue;
-    const unsigned fm = __ballot_sync(FULL, to_front), bm0 = am & ~fm;
-    unsigned fbase = 0, bbase = 0;
-    if (lane == 0) {
-      if (fm) fbase = atomicAdd(a.n_out, (unsigned)__popc(fm));
-      if (bm0) bbase = atomicAdd(a.n_out + 1, (unsigned)__popc(bm0));
-    }
-    fbase = __shfl_sync(FULL, fbase, 0);
-    bbase = __shfl_sync(FULL, bbase, 0);
+    unsigned rm[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) rm[r] = __ballot_sync(FULL, alive && oreg == r);
+    unsigned rbase = 0;
+    if (lane < 4 && rm[lane]) rbase = atomicAdd(a.n_out + lane, (unsigned)__popc(rm[lane]));  // one atomic per non-empty region
+    rbase = __shfl_sync(FULL, rbase, oreg);
     const unsigned lt = (1u << lane) - 1;
-    const unsigned my_slot = to_front ? fbase + __popc(fm & lt) : a.q_cap - 1 - (bbase + __popc(bm0 & lt));
+    const unsigned kk = rbase + __popc(rm[oreg] & lt);
+    const unsigned my_slot = oreg == 0 ? kk : (oreg == 1 ? a.q_cap - 1 - kk : (oreg == 2 ? a.q_cap + kk : 2 * a.q_cap - 1 - kk));
     // ---- cooperative Bezier culling: per in-box ray, 32 lanes test 32 patch boxes (Bezier.h:178)
     unsigned my_begin = 0, my_cnt = 0;
     unsigned bm = __ballot_sync(FULL, alive && boxobj != 0);
@@ -377,12 +389,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_i
 struct WfLayout {
   Queue q[2];
   Items it[2];
-  unsigned* counters;  // [2*b], [2*b+1] queue counts (front, back) of bounce b, [40+b] item counts, [64] overflow
+  unsigned* counters;  // [4*b + r] queue count of region r at bounce b, [64+b] item counts, [96] overflow
   unsigned item_cap;
 };
 
 size_t wf_bytes(int64_t cap, int64_t item_cap) {
-  return 2 * (size_t)cap * (10 * 8 + 8 + 4 + 4 + 4) + 2 * (size_t)item_cap * (4 + 4 + 24) + 128 * 4 + 4096;
+  return 2 * (size_t)(2 * cap) * (10 * 8 + 8 + 4 + 4 + 4) + 2 * (size_t)item_cap * (4 + 4 + 24) + 128 * 4 + 65536;
 }
 WfLayout wf_layout(void* store, int64_t cap, int64_t item_cap) {
   WfLayout L;
@@ -395,11 +407,11 @@ WfLayout wf_layout(void* store, int64_t cap, int64_t item_cap) {
   for (int k = 0; k < 2; k++) {
     Queue& q = L.q[k];
     double** d[] = {&q.ox, &q.oy, &q.oz, &q.dx, &q.dy, &q.dz, &q.fx, &q.fy, &q.fz, &q.hdist};
-    for (double** x : d) *x = (double*)take((size_t)cap * 8);
-    q.idd = (unsigned long long*)take((size_t)cap * 8);
-    q.hobj = (int*)take((size_t)cap * 4);
-    q.item_begin = (unsigned*)take((size_t)cap * 4);
-    q.item_cnt = (unsigned*)take((size_t)cap * 4);
+    for (double** x : d) *x = (double*)take((size_t)cap * 16);  // 2 x cap entries: four regions, see photon_step_kernel
+    q.idd = (unsigned long long*)take((size_t)cap * 16);
+    q.hobj = (int*)take((size_t)cap * 8);
+    q.item_begin = (unsigned*)take((size_t)cap * 8);
+    q.item_cnt = (unsigned*)take((size_t)cap * 8);
     Items& it = L.it[k];
     it.slot = (unsigned*)take((size_t)item_cap * 4);
     it.patch = (unsigned*)take((size_t)item_cap * 4);
@@ -463,13 +475,13 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
     a.qout = L.q[(b + 1) & 1];
     a.it_in = L.it[b & 1];
     a.it_out = L.it[(b + 1) & 1];
-    a.n_in_ptr = L.counters + 2 * b;
+    a.n_in_ptr = L.counters + 4 * b;
     a.n_in_host = (unsigned)total;
-    a.n_out = L.counters + 2 * (b + 1);
+    a.n_out = L.counters + 4 * (b + 1);
     a.q_cap = (unsigned)Ln.wf_cap;
-    a.n_items_out = L.counters + 40 + b + 1;
+    a.n_items_out = L.counters + 64 + b + 1;
     a.item_cap = L.item_cap;
-    a.overflow = L.counters + 64;
+    a.overflow = L.counters + 96;
     a.begin = begin;
     a.count = count;
     a.grid = c->grid;
@@ -515,7 +527,7 @@ cudaError_t wavefront_overflowed(sppm_ctx* c, Lane& Ln, bool* overflow) {
   if (!Ln.wf_store.p || Ln.wf_cap <= 0) return cudaSuccess;
   const WfLayout L = wf_layout(Ln.wf_store.p, Ln.wf_cap, std::max<int64_t>(Ln.wf_cap * 2, 1 << 16));
   unsigned v = 0;
-  cudaError_t e = cudaMemcpyAsync(&v, L.counters + 64, 4, cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaMemcpyAsync(&v, L.counters + 96, 4, cudaMemcpyDeviceToHost, c->stream);
   if (e) return e;
   if ((e = cudaStreamSynchronize(c->stream))) return e;
   *overflow = v != 0;
