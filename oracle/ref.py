@@ -1,6 +1,7 @@
 """ctypes wrapper of oracle/_ref/libref.so — the reference's OWN code (built by
 oracle/ref_shim/build_ref.py from /root/reference/raytracer/*.h against a thin OpenCV/FLANN
-shim).  TEST INFRASTRUCTURE: pins the oracle (tests/test_ref_pin_cpu.py)."""
+shim).  TEST INFRASTRUCTURE: pins the oracle (tests/test_ref_pin_cpu.py) and times the
+reference's own PhotonMap for bench.py's cpu_baseline (time_photon_map)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -56,6 +57,11 @@ class Reference:
         L.ref_view_trace.restype = I64
         L.ref_update.argtypes = [I64, VP, VP, VP, VP]
         L.ref_resolve_one.argtypes = [VP, DBL, C.c_int, C.c_int, VP]
+        self.can_time = hasattr(L, "ref_time_photon_map")  # a libref.so built before the timing entry existed
+        if self.can_time:
+            L.ref_flann_selfcheck.argtypes = [C.c_int, C.c_int, DBL, DBL, C.c_uint, VP]
+            L.ref_flann_selfcheck.restype = C.c_long
+            L.ref_time_photon_map.argtypes = [VP, VP, VP, C.c_int, C.c_int, C.c_int, C.c_int, DBL, VP]
         self.u_first = bool(L.ref_arg_order_u_first())
         self._keep = []
         self._tmp = tempfile.TemporaryDirectory()
@@ -172,3 +178,16 @@ class Reference:
         t, o = _f64(tao, (3,)), np.empty(3)
         self.lib.ref_resolve_one(_p(t), float(r2), cnt, onetime, _p(o))
         return o
+
+    # -- the shim's kd-tree against its exhaustive scan; returns (queries that differ, neighbours compared)
+    def flann_selfcheck(self, n, nq, side, radius2, seed=1):
+        found = C.c_long(0)
+        bad = self.lib.ref_flann_selfcheck(n, nq, float(side), float(radius2), seed, C.addressof(found))
+        return int(bad), int(found.value)
+
+    # -- the reference's own GetHitPoint + index build (untimed) and PhotonMap(cnt) (timed), one replica per thread
+    def time_photon_map(self, h, cam_pos, cam_look, w, hgt, cnt, threads, target_s=0.0):
+        """target_s > 0: the round count is chosen from a 10-round probe (cnt is the upper limit)."""
+        pos, look, out = _f64(cam_pos, (3,)), _f64(cam_look, (3,)), np.zeros(5)
+        self.lib.ref_time_photon_map(h, _p(pos), _p(look), w, hgt, cnt, threads, float(target_s), _p(out))
+        return dict(setup_s=float(out[0]), map_s=float(out[1]), hit_points=int(out[2]), photons=int(out[3]), rounds=int(out[4]))

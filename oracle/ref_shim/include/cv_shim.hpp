@@ -8,7 +8,8 @@
 //     (adjugate / determinant, zeros when det == 0) — pinned against cv2.invert in
 //     tests/test_oracle_cpu.py;
 //   cv::RNG::uniform(a,b) = u*(b-a)+a with u taken from an INJECTED sequence
-//     (ref_shim::push_uniforms), because the real generator's stream is not a parity target;
+//     (ref_shim::push_uniforms), because the real generator's stream is not a parity target
+//     (timing runs switch to a free-running multiply-with-carry generator, ref_shim::free_state);
 //   cv::imread: returns images registered by the harness (no codec); Mat/imwrite/imshow: stubs.
 #pragma once
 #include <math.h>
@@ -32,6 +33,13 @@ inline std::deque<double>& uniforms() {
 inline long& underflows() {
   static thread_local long n = 0;
   return n;
+}
+// Timing runs (ref_time_photon_map) let the generator run freely instead: state != 0 selects
+// cv::RNG's own multiply-with-carry recurrence (core.hpp: CV_RNG_COEFF 4164903690, a double is
+// two 32-bit draws scaled by 2^-64), one state per thread.
+inline unsigned long long& free_state() {
+  static thread_local unsigned long long s = 0;
+  return s;
 }
 struct Image {
   int rows = 0, cols = 0;
@@ -134,6 +142,13 @@ inline Vec3d operator*(const Matx33d& a, const Vec3d& b) {
 class RNG {  // uniform(a,b) = ((double)*this)*(b-a)+a, the uniform coming from the injected queue
  public:
   double next01() {
+    unsigned long long& st = ref_shim::free_state();
+    if (st) {
+      st = (unsigned long long)(unsigned)st * 4164903690U + (unsigned)(st >> 32);
+      unsigned hi = (unsigned)st;
+      st = (unsigned long long)(unsigned)st * 4164903690U + (unsigned)(st >> 32);
+      return (((unsigned long long)hi << 32) | (unsigned)st) * 5.4210108624275221700372640043497e-20;
+    }
     auto& q = ref_shim::uniforms();
     if (q.empty()) {
       ref_shim::underflows()++;

@@ -1,7 +1,9 @@
 // ref_harness.cpp — C entry points into the reference's OWN code (compiled from
 // /root/reference/raytracer/*.h against the shim).  TEST INFRASTRUCTURE: used only to pin the
-// oracle (tests/test_ref_pin_cpu.py).  Random numbers are injected (ref_push_uniforms) in the
-// order the reference consumes them.
+// oracle (tests/test_ref_pin_cpu.py) and, in ref_time_photon_map, to time the reference's own
+// RayTracer::PhotonMap on the host cores (bench.py, cpu_baseline.reference_code).  Random numbers
+// are injected (ref_push_uniforms) in the order the reference consumes them; the timing entry
+// point lets the generator run freely.
 #include "Vec3.h"
 #include "Obj.h"
 #include "Camera.h"
@@ -11,6 +13,11 @@
 #include "Scene.h"
 #include "Raytracer.h"
 
+#include <fcntl.h>
+#include <omp.h>
+#include <unistd.h>
+
+#include <chrono>
 #include <fstream>
 
 #include "sppm_b200.h"
@@ -223,6 +230,113 @@ void ref_resolve_one(const double tao[3], double R2, int cnt, int onetime, doubl
   hp.tao = V(tao); hp.R2 = R2;
   HitPoint* p = &hp;
   put(out, p->tao * (1.0 / PI / (p->R2 * cnt * onetime)));
+}
+
+// kd-tree of the FLANN shim against its exhaustive scan: n random points in [0,side)^3 (many of them
+// on shared planes, like hit points on walls), nq queries; returns the number of queries whose
+// (index, distance) lists differ — 0 expected.  total_found reports how many neighbours were compared.
+long ref_flann_selfcheck(int n, int nq, double side, double radius2, unsigned seed, long* total_found) {
+  std::vector<double> data((size_t)3 * n + 3), q(3);
+  unsigned long long st = seed * 2654435761ULL + 12345;
+  auto rnd = [&]() { st = st * 6364136223846793005ULL + 1442695040888963407ULL; return (double)(st >> 11) * (1.0 / 9007199254740992.0); };
+  for (int i = 0; i < n; i++) {
+    for (int k = 0; k < 3; k++) data[3 * i + k] = rnd() * side;
+    int flat = (int)(rnd() * 6);                      // a third of the points lie exactly on a coordinate plane
+    if (flat < 3 && (i & 1)) data[3 * i + flat] = 0.0;
+    if (i % 97 == 0 && i) for (int k = 0; k < 3; k++) data[3 * i + k] = data[3 * (i - 1) + k];  // duplicates
+  }
+  flann::Index<flann::L2<double> > index(flann::Matrix<double>(data.data(), 1, 3), flann::KDTreeSingleIndexParams());
+  index.buildIndex(flann::Matrix<double>(data.data(), (size_t)n, 3));
+  std::vector<std::vector<int> > i1, i2;
+  std::vector<std::vector<double> > d1, d2;
+  long bad = 0, found = 0;
+  for (int j = 0; j < nq; j++) {
+    if (j & 1) for (int k = 0; k < 3; k++) q[k] = rnd() * side;
+    else for (int k = 0; k < 3; k++) q[k] = data[3 * (size_t)(rnd() * n) + k] + (j % 4 == 0 ? 0.0 : (rnd() - 0.5) * 1e-3);
+    flann::Matrix<double> qm(q.data(), 1, 3);
+    found += index.radiusSearch(qm, i1, d1, (float)radius2, flann::SearchParams());
+    index.radiusSearch(qm, i2, d2, (float)radius2, flann::SearchParams(), true);
+    if (i1 != i2 || d1 != d2) bad++;
+  }
+  if (total_found) *total_found = found;
+  return bad;
+}
+
+// The reference's own photon pass, timed.  `threads` independent replicas, one RayTracer + Camera
+// per thread over the shared Scene, exactly the structure of SPPMRayTracer::render
+// (Raytracer.h:429-447) minus the 0.00015 camera jitter: each runs GetHitPoint (Raytracer.h:102),
+// flattens its hit points and builds the index as render() does (:369-380) — untimed set-up —
+// and then, after a barrier, PhotonMap(cnt) (:210-295): cnt rounds of onetime = 100 photons per
+// light (hard-coded, :219), each followed by the update sweep over ALL hit points (:238-245), and
+// the final film resolve.  With target_s > 0 the round count is chosen from a 10-round probe so
+// that the timed call lasts about target_s seconds (cnt is then only the upper limit).  out =
+// {set-up seconds, PhotonMap seconds (wall, all threads), hit points per replica, photons traced
+// by all threads in the timed call, rounds}.  The reference prints a progress line per
+// row and per round; stdout/stderr are parked on /dev/null while it runs.  Known quirk kept: the
+// query buffer `qdata` (Raytracer.h:43) is one global shared by all threads (a race in the
+// reference, part of Q15), so a timing run is not a parity run.
+int ref_time_photon_map(void* h, const double cam_pos[3], const double cam_look[3], int w, int hgt, int cnt, int threads,
+                        double target_s, double out[5]) {
+  RefScene* rs = (RefScene*)h;
+  if (threads < 1) threads = 1;
+  fflush(stdout); fflush(stderr); std::cout.flush(); std::cerr.flush();
+  int null_fd = open("/dev/null", O_WRONLY), save1 = dup(1), save2 = dup(2);
+  if (null_fd >= 0) { dup2(null_fd, 1); dup2(null_fd, 2); }
+  double t_setup = 0, t_map = 0;
+  long n_hp = 0;
+  std::chrono::steady_clock::time_point t0, tp, t1, t2;
+  t0 = std::chrono::steady_clock::now();
+#pragma omp parallel num_threads(threads)
+  {
+    ref_shim::free_state() = 0x9E3779B97F4A7C15ULL ^ ((unsigned long long)(omp_get_thread_num() + 1) * 0xD1B54A32D192ED03ULL);
+    Camera c;
+    c.init(w, hgt);
+    c.MoveTo(V(cam_pos));
+    c.lookAt(V(cam_look), 1.);
+    {
+      RayTracer rt;
+      rt.camera = &c;
+      rt.scene = &rs->scene;
+      rt.GetHitPoint();
+      std::vector<double> rdata(3 * rt.Hvec.size() + 3);
+      for (size_t i = 0; i < rt.Hvec.size(); i++) for (int j = 0; j < 3; j++) rdata[i * 3 + j] = rt.Hvec[i]->pos[j];
+      flann::Matrix<double> dataset(rdata.data(), rt.Hvec.size(), 3);
+      rt.index.buildIndex(dataset);
+      if (target_s > 0) {
+#pragma omp barrier
+#pragma omp master
+        tp = std::chrono::steady_clock::now();
+        rt.PhotonMap(10);
+#pragma omp barrier
+#pragma omp master
+        {
+          double per_round = std::chrono::duration<double>(std::chrono::steady_clock::now() - tp).count() / 10.0;
+          long want = (long)(target_s / (per_round > 1e-9 ? per_round : 1e-9));
+          cnt = (int)std::max(10L, std::min((long)cnt, want));
+        }
+      }
+#pragma omp barrier
+#pragma omp master
+      { t1 = std::chrono::steady_clock::now(); n_hp = (long)rt.Hvec.size(); }
+      rt.PhotonMap(cnt);
+#pragma omp barrier
+#pragma omp master
+      t2 = std::chrono::steady_clock::now();
+    }
+    ref_shim::free_state() = 0;
+  }
+  t_setup = std::chrono::duration<double>(t1 - t0).count();
+  t_map = std::chrono::duration<double>(t2 - t1).count();
+  fflush(stdout); fflush(stderr); std::cout.flush(); std::cerr.flush();
+  if (null_fd >= 0) { dup2(save1, 1); dup2(save2, 2); close(null_fd); }
+  if (save1 >= 0) close(save1);
+  if (save2 >= 0) close(save2);
+  out[0] = t_setup;
+  out[1] = t_map;
+  out[2] = (double)n_hp;
+  out[3] = (double)threads * cnt * 100.0 * (double)rs->scene.plvec.size();
+  out[4] = (double)cnt;
+  return 0;
 }
 
 }  // extern "C"

@@ -25,7 +25,14 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
     assert d["config"]["workload"] == "ref-main-320x240"
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "threads" in cb["sample"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["port_value"] > 0
+    rc = cb["reference_code"]                      # the reference's own PhotonMap, when oracle/_ref/libref.so is there
+    if rc is not None:
+        assert rc["value"] > 0 and "onetime as shipped" in rc["sample"], rc
+        assert cb["value"] == max(cb["port_value"], rc["value"])          # the faster CPU implementation is the baseline
+        assert cb["kind"] == ("reference" if rc["value"] > cb["port_value"] else "port")
+    else:
+        assert cb["kind"] == "port" and "threads" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -210,3 +210,32 @@ def test_view_trace_bit_identical(oracle, ref, params):
         assert count >= (hh // 2) * (w // 3 + 1) * 0.9
         if name == "custom":
             assert count > (hh // 2) * (w // 3 + 1)  # branching produced extra hit points
+
+
+def test_flann_shim_tree_equals_scan(ref):
+    """The kd-tree the FLANN shim builds (so that the reference's own PhotonMap can be timed with an
+    index of the right complexity) returns exactly the exhaustive scan's (index, distance) lists:
+    random clouds with points on shared planes and duplicates, queries on and next to data points."""
+    if not ref.can_time:
+        pytest.skip("libref.so predates the timing entry points")
+    compared = 0
+    for n, nq, side, seed in ((5, 40, 2.0, 1), (11, 60, 1.0, 2), (3000, 800, 12.0, 3), (60000, 600, 40.0, 4)):
+        bad, found = ref.flann_selfcheck(n, nq, side, 2.0, seed)
+        assert bad == 0, (n, bad)
+        compared += found
+    assert compared > 10000
+
+
+def test_reference_photon_map_runs_and_is_timed(ref):
+    """RayTracer::GetHitPoint + index build + PhotonMap(cnt) of the reference's own code on two replicas
+    (bench.py's cpu_baseline.reference_code leg): one hit point per pixel in the reference scene,
+    100 photons per round and light, stdout left usable afterwards."""
+    if not ref.can_time:
+        pytest.skip("libref.so predates the timing entry points")
+    sc = make_scene("reference", textures=None)
+    cam = reference_camera(48, 36)
+    o = ref.time_photon_map(ref.scene(sc), cam.pos, cam.look, cam.w, cam.h, 7, 2)
+    assert o["hit_points"] == 48 * 36 and o["rounds"] == 7 and o["photons"] == 2 * 7 * 100 * len(sc.plvec)
+    assert o["map_s"] > 0 and o["setup_s"] > 0
+    o = ref.time_photon_map(ref.scene(sc), cam.pos, cam.look, cam.w, cam.h, 100000, 2, target_s=0.2)
+    assert 10 <= o["rounds"] < 100000 and o["map_s"] < 5.0
