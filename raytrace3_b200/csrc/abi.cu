@@ -330,6 +330,10 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
   if (!c || !s) return SPPM_ERR_INVALID;
   if (s->n_objects < 0 || s->n_objects > MAX_OBJECTS) return fail(c, SPPM_ERR_INVALID, "n_objects out of range (max 64)");
   if (s->n_patches < 0 || s->n_patches >= (1 << 16)) return fail(c, SPPM_ERR_INVALID, "n_patches out of range");
+  if (s->n_lights < 0 || s->n_textures < 0) return fail(c, SPPM_ERR_INVALID, "negative light / texture count");
+  if ((s->n_objects > 0 && !s->objects) || (s->n_patches > 0 && !s->patches) || (s->n_lights > 0 && !s->lights) ||
+      (s->n_textures > 0 && !s->textures))
+    return fail(c, SPPM_ERR_INVALID, "a scene array is null while its count is positive");
   Bind b(c);
   CU(c, cudaStreamSynchronize(c->stream));
   c->scene_ok = false;
@@ -651,9 +655,9 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
   if (c->scene.n_light <= 0 || photon_count == 0) return SPPM_OK;
   if (photon_begin + photon_count > (1ull << 40)) return fail(c, SPPM_ERR_INVALID, "photon index exceeds 2^40");
   Bind b(c);
-  // Batches of up to PHOTON_BATCH photons alternate between two lanes (own stream + buffers):
+  // Batches of up to PHOTON_BATCH photons rotate over the context's lanes (own stream + buffers):
   // lane stream = trace + deposit binning, main stream = gather.  The gather of one batch
-  // overlaps the trace of the next — across rounds too, since nothing here waits for the host.
+  // overlaps the traces of the next ones — across rounds too, since nothing here waits for the host.
   // (A round is not split further: halving a batch doubles the per-cell and per-launch overheads.)
   const bool gather = c->index_ok && c->n_hp > 0;
   const uint64_t n_light = (uint64_t)c->scene.n_light;

@@ -90,9 +90,9 @@ struct DevBuf {  // growable device allocation
   size_t bytes = 0;
 };
 
-// A photon "lane": its own stream and buffers for tracing one sub-batch of photons and
-// binning its deposits.  A round's photons are split over two lanes so that the trace of
-// one sub-batch overlaps the gather (main stream) of the other.
+// A photon "lane": its own stream and buffers for tracing one batch of photons and binning its
+// deposits.  Batches rotate over the lanes (sppm_ctx::n_lanes) so that the traces of the next
+// batches overlap the gather (main stream) of the current one.
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_trace_done = nullptr, ev_gather_done = nullptr;

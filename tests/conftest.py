@@ -70,3 +70,15 @@ def rays_at_patches(patch_idx, seed, scene):
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     org = tgt + d * rng.uniform(20, 60, size=(n, 1))
     return np.ascontiguousarray(np.concatenate([org, -d], axis=1))
+
+
+def custom_scene():
+    """Materials the shipped scene never combines: diffuse+mirror+glass on one object (eye
+    paths branch, Raytracer.h:312-335) and a textured sphere (Obj.h:140-153)."""
+    from raytrace3_b200.scene import Material, SpotLight, Texture, make_scene, synthetic_texture
+    s = make_scene("cornell", textures=None)
+    s.objvec[5].material = Material((.3, .3, .3), (.4, .4, .4), (.3, .3, .3), 1.5)
+    s.objvec[7].setTexture(Texture(synthetic_texture(40, 60, 9)))
+    s.objvec[0].setTexture(Texture(synthetic_texture(50, 30, 8)))
+    s.plvec.append(SpotLight((10, 40, 140), (0., 2000., 2000.)))  # Scene.h:158 (commented-out second light)
+    return s

@@ -708,3 +708,102 @@ def test_newton_fast_sweep_against_exact(ctx):
     assert (hr == hg).all()
     rel = np.abs(got[hr] - ref[hr]) / np.maximum(np.abs(ref[hr]), 1e-12)
     assert rel.max() <= 1e-6, rel.max()
+
+
+# ---- against golden vectors produced by the reference's OWN code (tests/golden/ref_*.npz, frozen by
+# tools/make_ref_golden.py from the reference's headers compiled against the OpenCV/FLANN shim) --------
+def _ref_golden(name):
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+
+
+def _ref_scene(name):
+    from conftest import custom_scene
+    if name == "custom":
+        return custom_scene()
+    return make_scene(name, textures="synthetic" if name == "reference" else None)
+
+
+def test_ref_golden_newton_exact(ctx):
+    """Parity level 1 against the reference itself: Bezier3::newton with the reference's initial
+    guesses injected — EXACT mode returns the reference's (t, u, v) bit for bit, FAST within 1e-6."""
+    g = _ref_golden("ref_newton")
+    sc = make_scene("reference", textures=None)
+    ctx.set_params(_params(newton_mode=abi.SPPM_NEWTON_EXACT))
+    ctx.upload_scene(sc)
+    got = ctx.bezier_patch_batch(g["rays"], g["patch"], g["seeds"])
+    np.testing.assert_array_equal(got, g["tuv"])
+    assert 30 < (g["tuv"][:, 0] < 1e19).sum() < g["tuv"].shape[0]
+    ctx.set_params(_params(newton_mode=abi.SPPM_NEWTON_FAST))
+    fast = ctx.bezier_patch_batch(g["rays"], g["patch"], g["seeds"])
+    hit = g["tuv"][:, 0] < 1e19
+    assert ((fast[:, 0] < 1e19) == hit).all()
+    rel = np.abs(fast[hit] - g["tuv"][hit]) / np.maximum(np.abs(g["tuv"][hit]), 1e-12)
+    assert rel.max() <= 1e-6  # north-star tolerance on (t, u, v)
+
+
+@pytest.mark.parametrize("name", ["cornell", "custom", "reference", "stress"])
+def test_ref_golden_near_collide(ctx, name):
+    """Scene::NearCollide as computed by the reference's own PlaneObj / SphereObj / Bezier3Obj classes."""
+    g = _ref_golden("ref_near_collide")
+    ctx.set_params(_params())
+    ctx.upload_scene(_ref_scene(name))
+    rays = g[name + "_rays"]
+    got = ctx.intersect_batch(rays, np.arange(rays.shape[0], dtype=np.uint64), pass_id=1, node=2)
+    np.testing.assert_array_equal(got["obj"], g[name + "_obj"])
+    np.testing.assert_array_equal(got["inside"], g[name + "_inside"])
+    np.testing.assert_array_equal(got["t"], g[name + "_t"])      # + - * / sqrt only: bit-exact
+    np.testing.assert_array_equal(got["pos"], g[name + "_pos"])
+    np.testing.assert_allclose(got["n"], g[name + "_n"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(got["color"], g[name + "_color"], rtol=1e-12, atol=1e-15)  # sphere texture: acos / sin
+
+
+@pytest.mark.parametrize("name", ["custom", "reference"])
+def test_ref_golden_view_trace(ctx, name):
+    """GetHitPoint / ViewTrace: the hit points the reference's own recursion produces for a grid of pixels
+    (mirror and glass chains, branching materials, the teapot) are the eye pass's hit points of those pixels."""
+    g = _ref_golden("ref_view_trace")
+    w, h = (int(v) for v in g["film"])
+    ctx.set_params(_params())
+    ctx.upload_scene(_ref_scene(name))
+    ctx.eye_pass(reference_camera(w, h), pass_id=0)
+    got = ctx.export_hitpoints()
+    gp = got["pix"][:, 0].astype(np.int64) * w + got["pix"][:, 1]
+    off = 0
+    for (i, j), cnt in zip(g[name + "_pixels"], g[name + "_counts"]):
+        sel = np.nonzero(gp == int(i) * w + int(j))[0]
+        assert sel.size == cnt, (i, j)
+        want = {f: g[f"{name}_{f}"][off:off + cnt] for f in ("pos", "n", "wgt", "r2")}
+        off += cnt
+        # the reference appends in recursion order, the GPU exports in (pixel, path node) order: compare as sets
+        a = sel[np.lexsort(got["pos"][sel].T[::-1])]
+        b = np.lexsort(want["pos"].T[::-1])
+        np.testing.assert_array_equal(got["pos"][a], want["pos"][b])
+        np.testing.assert_allclose(got["n"][a], want["n"][b], rtol=0, atol=1e-15)
+        np.testing.assert_allclose(got["wgt"][a], want["wgt"][b], rtol=1e-12, atol=0)
+        np.testing.assert_array_equal(got["r2"][a], want["r2"][b])
+    assert off == g[name + "_pos"].shape[0]
+
+
+@pytest.mark.parametrize("name", ["cornell", "custom", "reference"])
+def test_ref_golden_photon_pass(ctx, name):
+    """Light::emit + PhotonTrace + radius search / accumulate as run by the reference's own code, 300
+    photons per light: the GPU photon pass over the same hit points gives the same newN (bit-exact
+    except where ulp differences of acos / sin / cos between libm and CUDA move a deposit across a
+    radius boundary or flip a path decision: near-total agreement required) and tao within 1e-5."""
+    g = _ref_golden("ref_photon")
+    hp = {k: g[f"{name}_hp_{k}"] for k in ("pos", "n", "wgt", "r2", "pix")}
+    ctx.set_params(_params())
+    ctx.upload_scene(_ref_scene(name))
+    ctx.import_hitpoints(hp["pos"], hp["n"], hp["wgt"], hp["r2"], hp["pix"], 64, 48)
+    ctx.build_index()
+    count = g[f"{name}_tot_newN"].shape[0]
+    ctx.photon_pass(0, count, 5)
+    ctx.update()
+    got = ctx.export_stats(hp["pos"].shape[0])
+    want_n, want_t = g[f"{name}_acc_newN"], g[f"{name}_acc_tao"]
+    assert want_n.sum() > 50
+    assert (got["newN"] == want_n).mean() > 0.995
+    assert abs(int(got["newN"].sum()) - int(want_n.sum())) <= max(2, 0.01 * want_n.sum())
+    same = got["newN"] == want_n
+    np.testing.assert_allclose(got["tao"][same], want_t[same], rtol=1e-5, atol=1e-12)

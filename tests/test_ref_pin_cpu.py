@@ -8,7 +8,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import rays_at_patches, rays_at_teapot, rays_in_room
+from conftest import custom_scene as _custom_scene, rays_at_patches, rays_at_teapot, rays_in_room
 from raytrace3_b200 import abi
 from raytrace3_b200.scene import Material, PlaneObj, Scene, SphereObj, SpotLight, make_scene, reference_camera, teapot_patches
 
@@ -132,18 +132,6 @@ def test_texture_update_tonemap(oracle, ref):
     pix = np.array([[0, 0]], np.int32)
     f = oracle.resolve(pix, np.array([1.7]), np.array([[3.0, 4.0, 5.5]]), 7, 100, 1, 1)
     assert np.array_equal(f[0, 0], ref.resolve_one([3.0, 4.0, 5.5], 1.7, 7, 100))
-
-
-def _custom_scene():
-    """Materials the shipped scene never combines: diffuse+mirror+glass on one object (eye
-    paths branch, Raytracer.h:312-335) and a textured sphere (Obj.h:140-153)."""
-    from raytrace3_b200.scene import Texture, synthetic_texture
-    s = make_scene("cornell", textures=None)
-    s.objvec[5].material = Material((.3, .3, .3), (.4, .4, .4), (.3, .3, .3), 1.5)
-    s.objvec[7].setTexture(Texture(synthetic_texture(40, 60, 9)))
-    s.objvec[0].setTexture(Texture(synthetic_texture(50, 30, 8)))
-    s.plvec.append(SpotLight((10, 40, 140), (0., 2000., 2000.)))  # Scene.h:158 (commented-out second light)
-    return s
 
 
 @pytest.mark.parametrize("name", ["cornell", "reference", "stress", "custom"])
