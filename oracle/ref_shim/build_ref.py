@@ -2,15 +2,17 @@
 compiled against the thin OpenCV/FLANN shim in oracle/ref_shim/include, plus a C harness.
 Only possible where /root/reference exists (the dev container); the built .so travels to the
 GPU box with the snapshot.  The headers are read where they lie; three MSVC-only constructs are
-patched in a scratch copy under oracle/_ref/src (git-ignored, never committed):
+patched in a scratch copy in a temporary directory outside the repo (removed after the compile;
+no reference source text ever lands in the tree):
     Element.h:5   `extern class Obj;`            -> `class Obj;`
     Obj.h:47      `virtual ~Obj() = 0 {};`       -> `virtual ~Obj() {};`
     Bezier.h:236  `freopen("CON", "r", stdin);`  -> `freopen("/dev/null", "r", stdin);`
 Everything else — every arithmetic statement — is the reference's code, unmodified."""
 import os
-import re
+import shutil
 import subprocess
 import sys
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = "/root/reference/raytracer"
@@ -26,8 +28,16 @@ def main():
     if not os.path.isdir(REF):
         print("build_ref: /root/reference not present; keeping any prebuilt oracle/_ref/libref.so")
         return 0
-    src = os.path.join(OUT, "src")
-    os.makedirs(src, exist_ok=True)
+    os.makedirs(OUT, exist_ok=True)
+    shutil.rmtree(os.path.join(OUT, "src"), ignore_errors=True)    # older builds kept the scratch copy here
+    src = tempfile.mkdtemp(prefix="sppm_ref_src_")
+    try:
+        return compile_ref(src)
+    finally:
+        shutil.rmtree(src, ignore_errors=True)
+
+
+def compile_ref(src):
     for name in ("Vec3.h", "Element.h", "Obj.h", "Bezier.h", "Light.h", "Camera.h", "Scene.h", "Raytracer.h"):
         text = open(os.path.join(REF, name), encoding="latin-1").read()
         for f, a, b in PATCHES:
