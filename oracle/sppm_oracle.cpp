@@ -1143,11 +1143,12 @@ void orc_render_replicas(const SppmSceneDesc* scene, const SppmParams* prm, cons
     for (int i = 0; i < cnt; i++) {  // PhotonMap (Raytracer.h:220-246)
       for (size_t pl = 0; pl < sc.lights.size(); pl++)
         for (int k = 0; k < onetime; k++) {
-          uint64_t id = ((uint64_t)pl << 40) | (uint64_t)k;
+          // draw addressing of the host mirrors: photon k of round i = photon i*onetime + k of pass j
+          uint64_t id = ((uint64_t)pl << 40) | ((uint64_t)i * (uint64_t)onetime + (uint64_t)k);
           V3 flux = V3(sc.lights[pl].color) * PI_ * 4;
-          V3 dir = GetUnitRandVec(prm->seed, (uint64_t)j * cnt + i, id, P_EMIT);
+          V3 dir = GetUnitRandVec(prm->seed, (uint64_t)j, id, P_EMIT);
           cnts[j][3]++;
-          PhotonTrace(sc, *prm, V3(sc.lights[pl].pos), dir, flux, (uint64_t)j * cnt + i, id, hp, &tree, newN.data(),
+          PhotonTrace(sc, *prm, V3(sc.lights[pl].pos), dir, flux, (uint64_t)j, id, hp, &tree, newN.data(),
                       tao.data(), nullptr, cnts[j].data());
         }
       updateAll(n_hp, prm->update_mode, prm->alpha, newN.data(), N.data(), r2.data(), tao.data());

@@ -36,6 +36,30 @@ def photon_range(onetime: int, rank: int, world: int):
     return begin, base + (1 if rank < rem else 0)
 
 
+FUSE_PHOTONS = 1 << 28
+
+
+def rounds_per_call(onetime: int, fuse: bool) -> int:
+    """Rounds of `onetime` photons handed to one photon pass by RayTracer.PhotonMap (twin of
+    sppm_host::rounds_per_call): whole rounds, at most FUSE_PHOTONS photons per light and call,
+    one round when the rounds are not independent."""
+    if not fuse or onetime <= 0:
+        return 1
+    return max(1, FUSE_PHOTONS // int(onetime))
+
+
+def photon_calls(cnt: int, onetime: int, fuse: bool, rank: int = 0, world: int = 1):
+    """(begin, count) of every photon pass `rank` issues for PhotonMap(cnt): photon k of round i is
+    photon i*onetime + k of the eye pass (ids stay global, any fusion / any world traces the same set)."""
+    step = rounds_per_call(onetime, fuse)
+    out = []
+    for i in range(0, int(cnt), step):
+        nr = min(step, cnt - i)
+        b, c = photon_range(nr * onetime, rank, world)
+        out.append((i * onetime + b, c))
+    return out
+
+
 def row_range(h: int, rank: int, world: int):
     """Film rows [begin, end) `rank` traces in a sharded eye pass: contiguous, disjoint,
     covering [0, h); feed to Context.eye_pass_rows, then Context.allgather_hitpoints."""
@@ -307,8 +331,15 @@ class RayTracer:
     reference (Raytracer.h:439-445); the film lands in `camera.pic`.
 
     cnt / onetime default to the reference's literals (Raytracer.h:218, 384).  With
-    world > 1 every rank traces its share of each round's photons and the per-round
-    accumulators are summed over ranks (NCCL) before HitPoint::update."""
+    world > 1 every rank traces its share of each call's photons and the accumulators are
+    summed over ranks (NCCL) before HitPoint::update.
+
+    Photon k of round i is photon i*onetime + k of pass `pass_base` in the counter RNG.  While
+    HitPoint::update is the reference's (a no-op for the hit points of a fresh eye pass, N = 0,
+    Raytracer.h:70, Q1) the rounds are independent and `fuse_rounds` traces them as one photon
+    pass of cnt*onetime photons (2 Mi-photon batches over the library's lanes) instead of cnt
+    launch sequences of onetime = 100 photons: same photons, same newN, tao in another summation
+    order.  PROGRESSIVE updates keep one pass per round."""
 
     def __init__(self, ctx: Context | None = None, device: int = 0, rank: int = 0, world: int = 1):
         self.ctx = ctx if ctx is not None else Context(device)
@@ -317,6 +348,7 @@ class RayTracer:
         self.cnt = 10000
         self.onetime = 100
         self.pass_base = 0
+        self.fuse_rounds = True
         self.rank, self.world = rank, world
         self.n_hitpoints = 0
         self._scene_uploaded = None
@@ -329,9 +361,9 @@ class RayTracer:
         return self.n_hitpoints
 
     def PhotonMap(self, cnt: int):  # Raytracer.h:210-295
-        begin, count = photon_range(self.onetime, self.rank, self.world)
-        for i in range(cnt):
-            self.ctx.photon_pass(begin, count, self.pass_base * cnt + i)
+        fuse = self.fuse_rounds and self.ctx.params.update_mode == abi.SPPM_UPDATE_REFERENCE
+        for begin, count in photon_calls(cnt, self.onetime, fuse, self.rank, self.world):
+            self.ctx.photon_pass(begin, count, self.pass_base)
             if self.world > 1:
                 self.ctx.allreduce()
             self.ctx.update()
@@ -360,6 +392,7 @@ class SPPMRayTracer:
         # (Raytracer.h:429-458).  True: one set of per-pixel statistics shared by all eye passes
         # (SPPM proper); camera.pic then holds the estimate itself.
         self.shared_statistics = False
+        self.fuse_rounds = True  # see RayTracer
 
     def render(self, scene: Scene, camera: Camera):
         from .rng import unit_rand_vec, P_JITTER
@@ -376,6 +409,7 @@ class SPPMRayTracer:
                 rt._scene_uploaded = scene if (i or j) else None
                 rt.camera, rt.scene, rt.cnt, rt.onetime = c, scene, self.cnt, self.onetime
                 rt.pass_base = i * self.replicas + j
+                rt.fuse_rounds = self.fuse_rounds
                 rt.render()
                 camera.pic += c.pic  # Raytracer.h:449-458
             self.image = self.ctx.tonemap(camera.pic, (i + 1) * float(self.replicas))  # Raytracer.h:460-470
@@ -399,8 +433,8 @@ class SPPMRayTracer:
                 ctx.eye_pass(c, pass_base)
                 ctx.build_index()
                 ctx.shared_load()
-                for k in range(self.cnt):
-                    ctx.photon_pass(0, self.onetime, pass_base * self.cnt + k)
+                for begin, count in photon_calls(self.cnt, self.onetime, self.fuse_rounds):
+                    ctx.photon_pass(begin, count, pass_base)
                     ctx.update()
                 ctx.shared_fold(self.cnt * self.onetime * n_light)
             ctx.shared_resolve(out=camera.pic)

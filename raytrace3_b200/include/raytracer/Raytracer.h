@@ -2,6 +2,7 @@
 // render() keeps its signature; its body flattens the scene / camera and drives the sm_100a
 // kernels through the C ABI (include/sppm_b200.h).  There is no CPU render path.
 #pragma once
+#include <algorithm>
 #include <cstdio>
 #include <iostream>
 #include <string>
@@ -44,6 +45,13 @@ class RayTracer {
   int cnt = 10000;         // Raytracer.h:384
   uint64_t pass_base = 0;  // distinguishes replicas in the counter RNG
   SppmParams params;
+  // Photon k of round i is photon i*onetime + k of pass `pass_base` in the counter RNG.  While
+  // HitPoint::update is the reference's -- a no-op for the hit points of a fresh eye pass (N = 0,
+  // Raytracer.h:70, Q1) -- the rounds of PhotonMap are independent, so they are traced as one
+  // photon pass of cnt*onetime photons (cut into 2 Mi-photon batches over the library's lanes)
+  // instead of cnt launch sequences of onetime = 100 photons each: same photons, same newN, tao in
+  // a different summation order.  PROGRESSIVE updates (or fuse_rounds = false) keep one pass per round.
+  bool fuse_rounds = true;
 
   explicit RayTracer(sppm_ctx* shared = nullptr) : ctx(shared), own(shared == nullptr) { sppm_default_params(&params); }
   ~RayTracer() {
@@ -69,8 +77,11 @@ class RayTracer {
     cout << "hitpoint::" << n << endl;
   }
   void PhotonMap(int cnt_) {  // Raytracer.h:210-295
-    for (int i = 0; i < cnt_; i++) {
-      sppm_host::check(sppm_photon_pass(ctx, 0, (uint64_t)onetime, pass_base * (uint64_t)cnt_ + i), ctx, "sppm_photon_pass");
+    const bool fuse = fuse_rounds && params.update_mode == SPPM_UPDATE_REFERENCE;
+    const uint64_t step = sppm_host::rounds_per_call((uint64_t)onetime, fuse);
+    for (uint64_t i = 0; i < (uint64_t)cnt_; i += step) {
+      const uint64_t nr = std::min<uint64_t>(step, (uint64_t)cnt_ - i);
+      sppm_host::check(sppm_photon_pass(ctx, i * (uint64_t)onetime, nr * (uint64_t)onetime, pass_base), ctx, "sppm_photon_pass");
       sppm_host::check(sppm_allreduce(ctx), ctx, "sppm_allreduce");
       sppm_host::check(sppm_update(ctx), ctx, "sppm_update");
     }
@@ -137,6 +148,7 @@ class SPPMRayTracer {  // Raytracer.h:421-477
   // jitters -- SPPM proper (sppm_shared_*); runs on devices[0].
   bool shared_statistics = false;
   SppmParams params;                 // arithmetic modes / seed of every RayTracer of the loop
+  bool fuse_rounds = true;           // see RayTracer::fuse_rounds
   std::string format = "ppm";        // "ppm" or "jpg" (nvJPEG, the reference's cv::imwrite target, Raytracer.h:474)
   int jpeg_quality = 95;
   // Film checkpoint: every `checkpoint_every` iterations the accumulated film (or
@@ -178,6 +190,7 @@ class SPPMRayTracer {  // Raytracer.h:421-477
         for (int j = d; j < replicas; j += ndev) {
           RayTracer rt(ctxs[d]);
           rt.params = params;
+          rt.fuse_rounds = fuse_rounds;
           rt.camera = &c[j];
           rt.scene = &scene;
           rt.cnt = cnt;
@@ -235,8 +248,10 @@ class SPPMRayTracer {  // Raytracer.h:421-477
         sppm_host::check(sppm_eye_pass(ctx, &cd, pass_base, &n), ctx, "sppm_eye_pass");
         sppm_host::check(sppm_build_index(ctx), ctx, "sppm_build_index");
         sppm_host::check(sppm_shared_load(ctx), ctx, "sppm_shared_load");
-        for (int k = 0; k < cnt; k++) {
-          sppm_host::check(sppm_photon_pass(ctx, 0, (uint64_t)onetime, pass_base * (uint64_t)cnt + k), ctx, "sppm_photon_pass");
+        const uint64_t step = sppm_host::rounds_per_call((uint64_t)onetime, fuse_rounds);  // the update is the reference's no-op here
+        for (uint64_t k = 0; k < (uint64_t)cnt; k += step) {
+          const uint64_t nr = std::min<uint64_t>(step, (uint64_t)cnt - k);
+          sppm_host::check(sppm_photon_pass(ctx, k * (uint64_t)onetime, nr * (uint64_t)onetime, pass_base), ctx, "sppm_photon_pass");
           sppm_host::check(sppm_update(ctx), ctx, "sppm_update");
         }
         sppm_host::check(sppm_shared_fold(ctx, (uint64_t)cnt * onetime * scene.plvec.size()), ctx, "sppm_shared_fold");

@@ -2,6 +2,7 @@
 // (include/sppm_b200.h): error handling, the per-process device context used by the
 // single-ray compatibility calls, and the flattened scene holder.
 #pragma once
+#include <cstdint>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -24,6 +25,15 @@ inline sppm_ctx* create_ctx(int device) {
 inline sppm_ctx* compat_ctx() {
   static sppm_ctx* c = create_ctx(std::getenv("SPPM_DEVICE") ? std::atoi(std::getenv("SPPM_DEVICE")) : 0);
   return c;
+}
+// Rounds of `onetime` photons handed to one sppm_photon_pass call (RayTracer::PhotonMap): whole
+// rounds, at most FUSE_PHOTONS photons per light and call (the per-call accumulators are int32 per
+// hit point), one round when the rounds are not independent.  Python twin: api.rounds_per_call.
+constexpr uint64_t FUSE_PHOTONS = 1ull << 28;
+inline uint64_t rounds_per_call(uint64_t onetime, bool fuse) {
+  if (!fuse || onetime == 0) return 1;
+  const uint64_t r = FUSE_PHOTONS / onetime;
+  return r < 1 ? 1 : r;
 }
 struct FlatScene {
   std::vector<SppmObject> objs;

@@ -93,6 +93,42 @@ def test_photon_range_partitions_exactly():
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
 
 
+def test_photon_calls_cover_the_eye_pass_exactly(tmp_path):
+    """RayTracer::PhotonMap's round fusion: whatever the fusion and the number of ranks, the photon
+    passes issued for PhotonMap(cnt) cover the ids [0, cnt*onetime) exactly once; the reference's
+    defaults (10000 rounds x 100 photons) become one pass; the C++ twin agrees."""
+    from raytrace3_b200 import photon_calls, rounds_per_call
+    from raytrace3_b200.api import FUSE_PHOTONS
+    assert photon_calls(10000, 100, True) == [(0, 1_000_000)]
+    assert photon_calls(3, 100, False) == [(0, 100), (100, 100), (200, 100)]
+    assert len(photon_calls(1000, 64_000_000, True)) == 250      # whole rounds, <= 2^28 photons per call
+    for cnt, onetime in ((1, 1), (7, 13), (10000, 100), (10, 2_000_000), (5, 300_000_001), (33, 64_000_000)):
+        for fuse in (False, True):
+            for world in (1, 2, 3, 8):
+                spans = sorted(sp for r in range(world) for sp in photon_calls(cnt, onetime, fuse, r, world) if sp[1] > 0)
+                pos = 0
+                for b, c in spans:
+                    assert b == pos
+                    pos += c
+                assert pos == cnt * onetime
+                per_rank = photon_calls(cnt, onetime, fuse, 0, world)
+                assert len(per_rank) == -(-cnt // rounds_per_call(onetime, fuse))
+                assert all(c <= max(FUSE_PHOTONS, onetime) for _, c in per_rank)
+                if not fuse:
+                    assert len(per_rank) == cnt
+    vals = [1, 7, 100, 2_000_000, 64_000_000, 300_000_001, 1 << 28, (1 << 28) + 1]
+    prog = ('#include <cstdio>\n#include "SppmBridge.h"\nint main(){' +
+            "".join(f'std::printf("%llu %llu\\n", (unsigned long long)sppm_host::rounds_per_call({v}ull, true), '
+                    f'(unsigned long long)sppm_host::rounds_per_call({v}ull, false));' for v in vals) + "return 0;}")
+    src = tmp_path / "rpc.cpp"
+    src.write_text(prog)
+    exe = tmp_path / "rpc"
+    inc = os.path.join(os.path.dirname(os.path.dirname(HEADER)), "raytrace3_b200", "include", "raytracer")
+    subprocess.run(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = [tuple(int(x) for x in ln.split()) for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines()]
+    assert out == [(rounds_per_call(v, True), rounds_per_call(v, False)) for v in vals]
+
+
 def test_scene_flatten_roundtrip():
     from raytrace3_b200.scene import make_scene
     sc = make_scene("reference", textures="synthetic")

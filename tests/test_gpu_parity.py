@@ -417,6 +417,40 @@ def test_image_rrmse(ctx, oracle):
     assert np.abs(img.astype(int) - img_ref.astype(int)).max() <= 2
 
 
+@pytest.mark.parametrize("world", [1, 2])
+def test_fused_rounds_equal_round_by_round(ctx, world):
+    """RayTracer::PhotonMap traces the rounds of one eye pass as one photon pass while the update is
+    the reference's no-op (Q1): same photons (ids i*onetime + k under the eye pass's id), so newN is
+    bit-identical to the round-by-round loop and tao / the film agree to summation order; the ranks
+    of a sharded run cover the same ids."""
+    from raytrace3_b200 import RayTracer
+    sc = make_scene("reference", textures=None)
+    prm = _params()
+    ctx.set_params(prm)
+    cam = reference_camera(64, 48)
+    cnt, onetime = 7, 1501
+    res = []
+    for fuse in (False, True):
+        ctx.reset_counters()
+        rt = RayTracer(ctx)
+        rt.camera, rt.scene, rt.cnt, rt.onetime, rt.fuse_rounds, rt.pass_base = cam.copy(), sc, cnt, onetime, fuse, 3
+        n = rt.GetHitPoint()
+        ctx.build_index()
+        l0 = ctx.counters()["launches"]             # cumulative over the context's life
+        for r in range(world):                      # the ranks of a sharded run, one after the other on this GPU
+            rt.rank, rt.world = r, world
+            rt.PhotonMap(cnt)                       # the last resolve sees every rank's photons
+        c = ctx.counters()
+        res.append((ctx.export_stats(n), rt.camera.pic.copy(), c, c["launches"] - l0))
+    (a, fa, ca, la), (b, fb, cb, lb) = res
+    assert ca["photons"] == cb["photons"] == cnt * onetime * len(sc.plvec)
+    assert a["newN"].sum() > 0
+    np.testing.assert_array_equal(a["newN"], b["newN"])
+    np.testing.assert_allclose(a["tao"], b["tao"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(fa, fb, rtol=1e-12, atol=0)
+    assert lb < la                                  # one launch sequence per rank instead of cnt
+
+
 def test_photon_range_invariance(ctx):
     """§8(e): splitting a round's photons over R ranks gives the same accumulators (newN
     bit-exact, tao to rounding) because the RNG is keyed by the global photon id."""
