@@ -201,7 +201,11 @@ int sppm_build_index(sppm_ctx* ctx);
 /* One round of RayTracer::PhotonMap (Raytracer.h:226-233) restricted to photons
  * [photon_begin, photon_begin+photon_count) of every light: Light::emit, PhotonTrace
  * and the radiusSearch gather (Raytracer.h:117-209).  Adds into the per-round
- * accumulators (dN, dtao); call sppm_update to fold them into the hit points. */
+ * accumulators (dN, dtao); call sppm_update to fold them into the hit points.
+ * Draws are addressed by (pass_id, photon id), never streamed: any split of an id range over
+ * calls, batches or GPUs traces the same photons.  While HitPoint::update is the reference's
+ * no-op (N = 0, Raytracer.h:70) several rounds may be one call: round i = ids
+ * [i*onetime, (i+1)*onetime) -- what the host mirrors' PhotonMap does. */
 int sppm_photon_pass(sppm_ctx* ctx, uint64_t photon_begin, uint64_t photon_count, uint64_t pass_id);
 /* Sum the per-round accumulators over the ranks of the communicator (no-op without one). */
 int sppm_allreduce(sppm_ctx* ctx);
