@@ -40,7 +40,8 @@ def _f64(a, shape=None):
 
 class Oracle:
     def __init__(self):
-        self.lib = C.CDLL(build_oracle())
+        # SPPM_ORACLE_LIB: an instrumented build of the same source (`make -C oracle asan`)
+        self.lib = C.CDLL(os.environ.get("SPPM_ORACLE_LIB") or build_oracle())
         L = self.lib
         L.orc_draw2.argtypes = [U64, U64, U64, U32, U32, U32, U32, VP]
         L.orc_newton.argtypes = [VP, VP, VP, VP, C.c_int, C.c_int, VP]

@@ -247,3 +247,26 @@ def test_golden_vectors(oracle, params, name):
         np.testing.assert_array_equal(r["newN"], g["newN"])
         np.testing.assert_allclose(r["tao"], g["tao"], rtol=1e-12)
         np.testing.assert_allclose(r["dep"]["x"], g["dep_x"], rtol=0, atol=1e-9)
+
+
+def test_oracle_is_clean_under_asan_ubsan():
+    """the same oracle source built with -fsanitize=address,undefined (`make -C oracle asan`)
+    passes the golden-vector tests without a sanitizer report (out-of-bounds reads would silently
+    bend a checker that everything else is held to)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    asan = subprocess.run([cxx, "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan.so not installed")
+    r = subprocess.run(["make", "-C", os.path.join(root, "oracle"), "asan"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1", UBSAN_OPTIONS="print_stacktrace=1",
+               SPPM_ORACLE_LIB=os.path.join(root, "oracle", "_build", "liboracle_asan.so"))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_ref_golden_cpu.py"), "-q", "-s", "-x",
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, cwd=root, timeout=600)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "runtime error" not in out and "AddressSanitizer" not in out, out[-3000:]
