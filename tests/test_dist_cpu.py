@@ -82,6 +82,73 @@ def test_sharded_photon_pass_equals_single_rank():
     np.testing.assert_allclose(tao, ref_tao, rtol=1e-12, atol=0)
 
 
+def _fused_worker(rank, world, port, cnt, onetime, q):
+    """RayTracer.PhotonMap's sharded, fused form: every rank traces its share of the fused id range
+    under the eye pass's id, ONE all_reduce per call."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "1"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import Oracle
+    from raytrace3_b200 import abi, photon_calls
+    from raytrace3_b200.scene import make_scene, reference_camera
+    orc = Oracle()
+    prm = abi.default_params()
+    sc = make_scene("cornell", textures=None)
+    hp = orc.eye_pass(sc, prm, reference_camera(32, 24), 0)
+    n = hp["pos"].shape[0]
+    newN, tao = np.zeros(n, np.int32), np.zeros((n, 3))
+    calls = photon_calls(cnt, onetime, True, rank, world)
+    for b, c in calls:
+        r = orc.photon_pass(sc, prm, b, c, 5, hp=hp)
+        dN, dtao = torch.from_numpy(r["newN"].copy()), torch.from_numpy(r["tao"].copy())
+        dist.all_reduce(dN)
+        dist.all_reduce(dtao)
+        newN += dN.numpy()
+        tao += dtao.numpy()
+    if rank == 0:
+        q.put((newN, tao, len(calls)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_sharded_photon_map_equals_round_by_round():
+    """The rounds of an eye pass fused into one call and split over 2 ranks trace the same photons as
+    one rank going round by round (photon k of round i = id i*onetime + k under the eye pass's id)."""
+    cnt, onetime, world = 5, 301, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fused_worker, args=(r, world, port, cnt, onetime, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    newN, tao, n_calls = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert n_calls == 1
+    sys.path.insert(0, ROOT)
+    from oracle import Oracle
+    from raytrace3_b200 import abi, photon_calls
+    from raytrace3_b200.scene import make_scene, reference_camera
+    orc = Oracle()
+    prm = abi.default_params()
+    sc = make_scene("cornell", textures=None)
+    hp = orc.eye_pass(sc, prm, reference_camera(32, 24), 0)
+    n = hp["pos"].shape[0]
+    ref_N, ref_tao = np.zeros(n, np.int32), np.zeros((n, 3))
+    rounds = photon_calls(cnt, onetime, False)
+    assert rounds == [(i * onetime, onetime) for i in range(cnt)]
+    for b, c in rounds:
+        r = orc.photon_pass(sc, prm, b, c, 5, hp=hp)
+        ref_N += r["newN"]
+        ref_tao += r["tao"]
+    assert ref_N.sum() > 0
+    np.testing.assert_array_equal(newN, ref_N)
+    np.testing.assert_allclose(tao, ref_tao, rtol=1e-12, atol=0)
+
+
 def _eye_worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
