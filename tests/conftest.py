@@ -82,3 +82,17 @@ def custom_scene():
     s.objvec[0].setTexture(Texture(synthetic_texture(50, 30, 8)))
     s.plvec.append(SpotLight((10, 40, 140), (0., 2000., 2000.)))  # Scene.h:158 (commented-out second light)
     return s
+
+
+def quirks_scene():
+    """Branches of the reference the shipped scene never reaches: a TEXTURED teapot (Bezier3Obj looks
+    its colour up as GetColor(u, t) -- the ray parameter as second coordinate, Bezier.h:278, Q6) and
+    materials with a zero diffuse channel (IsZero(Vec3) is true if ANY channel is < 1e-4, so such an
+    object is not IsDiff() and gets no hit points / deposits, yet Obj::Roulette, which uses channel
+    means, still sends photons down the DIFF branch, Vec3.h:72-79, Obj.h:12-15,30-45, Q8)."""
+    from raytrace3_b200.scene import Material, Texture, make_scene, synthetic_texture
+    s = make_scene("reference", textures=None)
+    s.objvec[8].setTexture(Texture(synthetic_texture(37, 53, 11)))
+    s.objvec[5].material = Material((.5, 0., .5), (.3, .3, .3), (0., 0., 0.), 1.5)
+    s.objvec[2].material = Material((0., .7, .7), (0., 0., 0.), (0., 0., 0.), 1.5)
+    return s

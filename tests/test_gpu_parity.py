@@ -746,15 +746,19 @@ def test_newton_fast_sweep_against_exact(ctx):
 
 # ---- against golden vectors produced by the reference's OWN code (tests/golden/ref_*.npz, frozen by
 # tools/make_ref_golden.py from the reference's headers compiled against the OpenCV/FLANN shim) --------
-def _ref_golden(name):
+def _ref_golden(name, scene=None):
     import os
+    if scene == "quirks":   # the quirks scene's vectors use the same keys, in files of their own
+        name = name.replace("ref_", "ref_quirks_")
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
 
 
 def _ref_scene(name):
-    from conftest import custom_scene
+    from conftest import custom_scene, quirks_scene
     if name == "custom":
         return custom_scene()
+    if name == "quirks":
+        return quirks_scene()
     return make_scene(name, textures="synthetic" if name == "reference" else None)
 
 
@@ -779,7 +783,7 @@ def test_ref_golden_newton_exact(ctx):
 @pytest.mark.parametrize("name", ["cornell", "custom", "reference", "stress"])
 def test_ref_golden_near_collide(ctx, name):
     """Scene::NearCollide as computed by the reference's own PlaneObj / SphereObj / Bezier3Obj classes."""
-    g = _ref_golden("ref_near_collide")
+    g = _ref_golden("ref_near_collide", name)
     ctx.set_params(_params())
     ctx.upload_scene(_ref_scene(name))
     rays = g[name + "_rays"]
@@ -796,7 +800,7 @@ def test_ref_golden_near_collide(ctx, name):
 def test_ref_golden_view_trace(ctx, name):
     """GetHitPoint / ViewTrace: the hit points the reference's own recursion produces for a grid of pixels
     (mirror and glass chains, branching materials, the teapot) are the eye pass's hit points of those pixels."""
-    g = _ref_golden("ref_view_trace")
+    g = _ref_golden("ref_view_trace", name)
     w, h = (int(v) for v in g["film"])
     ctx.set_params(_params())
     ctx.upload_scene(_ref_scene(name))
@@ -825,7 +829,7 @@ def test_ref_golden_photon_pass(ctx, name):
     photons per light: the GPU photon pass over the same hit points gives the same newN (bit-exact
     except where ulp differences of acos / sin / cos between libm and CUDA move a deposit across a
     radius boundary or flip a path decision: near-total agreement required) and tao within 1e-5."""
-    g = _ref_golden("ref_photon")
+    g = _ref_golden("ref_photon", name)
     hp = {k: g[f"{name}_hp_{k}"] for k in ("pos", "n", "wgt", "r2", "pix")}
     ctx.set_params(_params())
     ctx.upload_scene(_ref_scene(name))

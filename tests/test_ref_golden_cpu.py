@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import custom_scene
+from conftest import custom_scene, quirks_scene
 from raytrace3_b200 import abi
 from raytrace3_b200.scene import make_scene, reference_camera, teapot_patches
 
@@ -18,11 +18,12 @@ SCENES = {
     "reference": lambda: make_scene("reference", textures="synthetic"),
     "stress": lambda: make_scene("stress", textures=None),
     "custom": custom_scene,
+    "quirks": quirks_scene,   # Q6 textured teapot, Q8 zero diffuse channels; its vectors live in ref_quirks_*.npz
 }
 
 
-def _load(name):
-    return np.load(os.path.join(GOLD, name + ".npz"))
+def _load(name, scene=None):
+    return np.load(os.path.join(GOLD, (name.replace("ref_", "ref_quirks_") if scene == "quirks" else name) + ".npz"))
 
 
 def test_pieces(oracle):
@@ -80,20 +81,23 @@ def test_newton(oracle):
 @pytest.mark.parametrize("name", sorted(SCENES))
 def test_near_collide(oracle, params, name):
     """Scene::NearCollide through the reference's own PlaneObj / SphereObj / Bezier3Obj."""
-    g = _load("ref_near_collide")
+    g = _load("ref_near_collide", name)
     sc = SCENES[name]()
     rays = g[name + "_rays"]
     got = oracle.intersect_batch(sc, params, rays, np.arange(rays.shape[0], dtype=np.uint64), pass_id=1, node=2)
     for f in ("obj", "inside", "t", "pos", "n", "color"):
         assert np.array_equal(got[f], g[f"{name}_{f}"]), f
-    if name in ("reference", "stress"):
+    if name in ("reference", "stress", "quirks"):
         assert (got["patch"] >= 0).sum() > 15
+    if name == "quirks":   # Q6: the teapot's colour comes from its texture, looked up at (u, t)
+        tp = got["obj"] == 8
+        assert len(np.unique(got["color"][tp].round(6), axis=0)) > 10
 
 
-@pytest.mark.parametrize("name", ["cornell", "custom", "reference"])
+@pytest.mark.parametrize("name", ["cornell", "custom", "quirks", "reference"])
 def test_photon_trace(oracle, params, name):
     """Light::emit + PhotonTrace + radiusSearch / accumulate: per-photon totals and the sum over 300 photons."""
-    g = _load("ref_photon")
+    g = _load("ref_photon", name)
     sc = SCENES[name]()
     hp = {k: g[f"{name}_hp_{k}"] for k in ("pos", "n", "wgt", "r2", "pix")}
     eye = oracle.eye_pass(sc, params, reference_camera(64, 48), 0)   # the stored hit points are the oracle's eye pass
@@ -111,10 +115,10 @@ def test_photon_trace(oracle, params, name):
     assert acc_n.sum() > 50
 
 
-@pytest.mark.parametrize("name", ["custom", "reference"])
+@pytest.mark.parametrize("name", ["custom", "quirks", "reference"])
 def test_view_trace(oracle, params, name):
     """ViewTrace: mirror / glass chains, branching materials, the teapot."""
-    g = _load("ref_view_trace")
+    g = _load("ref_view_trace", name)
     w, h = (int(v) for v in g["film"])
     sc = SCENES[name]()
     cam = reference_camera(w, h)
@@ -128,3 +132,5 @@ def test_view_trace(oracle, params, name):
     assert off == g[name + "_pos"].shape[0]
     if name == "custom":
         assert off > len(g[name + "_counts"])  # branching produced extra hit points
+    if name == "quirks":
+        assert off < len(g[name + "_counts"])  # Q8: no hit point on an object with a zero diffuse channel

@@ -21,7 +21,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from conftest import custom_scene, rays_at_patches, rays_at_teapot, rays_in_room  # noqa: E402
+from conftest import custom_scene, quirks_scene, rays_at_patches, rays_at_teapot, rays_in_room  # noqa: E402
 from oracle import Oracle  # noqa: E402
 from oracle import ref as ref_mod  # noqa: E402
 from raytrace3_b200 import abi  # noqa: E402
@@ -34,6 +34,7 @@ SCENES = {
     "reference": lambda: make_scene("reference", textures="synthetic"),
     "stress": lambda: make_scene("stress", textures=None),
     "custom": custom_scene,
+    "quirks": quirks_scene,   # textured teapot (Q6), materials with a zero diffuse channel (Q8): stored in ref_quirks_*.npz
 }
 
 
@@ -130,10 +131,10 @@ def newton(ref):
     return dict(rays=rays, patch=patch, seeds=seeds, tuv=tuv, flat_P=g.reshape(16, 3), flat_rays=fr, flat_tuv=ft)
 
 
-def near_collide(orc, ref, prm):
+def near_collide(orc, ref, prm, names=("cornell", "reference", "stress", "custom")):
     out = {}
-    for name, mk in SCENES.items():
-        sc = mk()
+    for name in names:
+        sc = SCENES[name]()
         h = ref.scene(sc)
         n_room, n_tp = (160, 0) if name in ("cornell", "custom") else (80, 100)
         rays = rays_in_room(n_room, 43)
@@ -153,12 +154,12 @@ def near_collide(orc, ref, prm):
     return out
 
 
-def photon(orc, ref, prm):
+def photon(orc, ref, prm, names=("cornell", "reference", "custom")):
     """Light::emit + PhotonTrace + radiusSearch/accumulate, one photon per light per call, on the
     hit points of a 64x48 eye pass (stored: they are the input).  Per photon the totals, and the
     accumulation over all photons in photon order (numpy float64 adds, so a checker can repeat it)."""
     out = {}
-    for name in ("cornell", "reference", "custom"):
+    for name in names:
         sc = SCENES[name]()
         h = ref.scene(sc)
         hp = orc.eye_pass(sc, prm, reference_camera(64, 48), 0)
@@ -181,10 +182,10 @@ def photon(orc, ref, prm):
     return out
 
 
-def view_trace(orc, ref, prm):
+def view_trace(orc, ref, prm, names=("reference", "custom")):
     out = {}
     w, hh = 40, 30
-    for name in ("reference", "custom"):
+    for name in names:
         sc = SCENES[name]()
         h = ref.scene(sc)
         cam = reference_camera(w, hh)
@@ -213,8 +214,17 @@ if __name__ == "__main__":
         sys.exit("oracle/_ref/libref.so is missing: run oracle/ref_shim/build_ref.py where /root/reference exists")
     os.makedirs(GOLD, exist_ok=True)
     orc, ref, prm = Oracle(), ref_mod.Reference(), abi.default_params()
-    for name, data in (("ref_pieces", pieces(ref)), ("ref_newton", newton(ref)), ("ref_near_collide", near_collide(orc, ref, prm)),
-                       ("ref_photon", photon(orc, ref, prm)), ("ref_view_trace", view_trace(orc, ref, prm))):
+    only = sys.argv[1:]          # e.g. `make_ref_golden.py ref_quirks_photon` regenerates one file
+    q = ("quirks",)   # same keys as the three files above, so in files of their own
+    for name, make in (("ref_pieces", lambda: pieces(ref)), ("ref_newton", lambda: newton(ref)),
+                       ("ref_near_collide", lambda: near_collide(orc, ref, prm)), ("ref_photon", lambda: photon(orc, ref, prm)),
+                       ("ref_view_trace", lambda: view_trace(orc, ref, prm)),
+                       ("ref_quirks_near_collide", lambda: near_collide(orc, ref, prm, q)),
+                       ("ref_quirks_photon", lambda: photon(orc, ref, prm, q)),
+                       ("ref_quirks_view_trace", lambda: view_trace(orc, ref, prm, q))):
+        if only and name not in only:
+            continue
+        data = make()
         path = os.path.join(GOLD, name + ".npz")
         np.savez_compressed(path, **data)
         print(name, os.path.getsize(path), "bytes,", len(data), "arrays")
