@@ -364,7 +364,11 @@ __device__ __forceinline__ PatchEval eval_mono(const double* __restrict__ A, dou
 // rounding", checked against EXACT to 1e-6 by the sweep tests).
 __device__ __forceinline__ double rcp_newton(double x) {
   double r;
+#ifdef SPPM_HOST_EMULATION  // tests/device_host only (g++ cannot assemble PTX); never defined in the library build
+  r = dh_rcp_approx(x);
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
   double e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);

@@ -1,0 +1,201 @@
+"""tests/device_host — TEST INFRASTRUCTURE: the product's device headers compiled for the CPU.
+
+`DeviceHost()` builds (g++, a few seconds) and loads tests/device_host/_build/libdevice_host.so:
+raytrace3_b200/csrc/{device_math.cuh, scene.cuh, scene_prep.h} through cuda_host_shim.h, with a
+warp emulated by 32 fibers.  It lets the `-m "not gpu"` suite hold the very source lines the
+sm_100a kernels are compiled from to the oracle.  Nothing in raytrace3_b200/ imports this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from raytrace3_b200 import abi
+from raytrace3_b200.api import hit_dtype
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_CSRC = os.path.join(_ROOT, "raytrace3_b200", "csrc")
+LIB_PATH = os.path.join(_HERE, "_build", "libdevice_host.so")
+SOURCES = [os.path.join(_HERE, f) for f in ("device_host.cpp", "cuda_host_shim.h")] + [
+    os.path.join(_CSRC, f) for f in ("scene.cuh", "device_math.cuh", "scene_prep.h")] + [
+    os.path.join(_ROOT, "include", "sppm_b200.h")]
+# -ffp-contract=off: no FMA contraction, the library's -fmad=false (explicit fma() calls stay fused)
+CXXFLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread"]
+
+VP, I32, I64, U64, U32, DBL = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.c_double
+
+
+def cuda_include_dir() -> str:
+    for d in (os.environ.get("CUDA_HOME"), "/usr/local/cuda"):
+        if d and os.path.exists(os.path.join(d, "include", "cuda_runtime.h")):
+            return os.path.join(d, "include")
+    raise RuntimeError("cuda_runtime.h not found (CUDA_HOME)")
+
+
+def build(force: bool = False) -> str:
+    stale = force or not os.path.exists(LIB_PATH) or any(
+        os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in SOURCES)
+    if stale:
+        os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+        tmp = LIB_PATH + ".%d.tmp" % os.getpid()
+        cmd = ["g++"] + CXXFLAGS + ["-I", cuda_include_dir(), "-I", os.path.join(_ROOT, "include"), "-o", tmp, SOURCES[0]]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("device_host build failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a.reshape(shape) if shape is not None else a
+
+
+class HostScene:
+    """A scene flattened by the product's prep_scene (scene_prep.h), viewed as the kernels view it."""
+
+    def __init__(self, dh: "DeviceHost", scene):
+        self.dh = dh
+        self.desc = scene.flatten() if hasattr(scene, "flatten") else scene
+        err = C.create_string_buffer(256)
+        self.h = dh.lib.dh_scene_create(C.byref(self.desc), err, 256)
+        if not self.h:
+            raise ValueError(err.value.decode())
+        self.n_patches = dh.lib.dh_scene_n_patches(self.h)
+        self.n_objects = self.desc.n_objects
+
+    def close(self):
+        if self.h:
+            self.dh.lib.dh_scene_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def tables(self):
+        n, m = self.n_patches, self.n_objects
+        box, dop, sub, A, obox = np.empty((n, 6)), np.empty((n, 26)), np.empty((n, 16, 6)), np.empty((n, 48)), np.empty((m, 6))
+        self.dh.lib.dh_scene_tables(self.h, _p(box), _p(dop), _p(sub), _p(A), _p(obox))
+        return dict(box=box, dop=dop, sub=sub, A=A, objbox=obox)
+
+    def material(self, i):
+        fl, w = np.zeros(3, dtype=np.int32), np.zeros(4)
+        self.dh.lib.dh_scene_material(self.h, i, _p(fl), _p(w))
+        return fl.astype(bool), w
+
+    @property
+    def culled(self):
+        return self.dh.lib.dh_scene_culled(self.h)
+
+    def analytic_nearest(self, rays6):
+        rays6 = _f64(rays6, (-1, 6))
+        n = rays6.shape[0]
+        obj, t, inside = np.empty(n, dtype=np.int32), np.empty(n), np.empty(n, dtype=np.int32)
+        self.dh.lib.dh_analytic_nearest(self.h, n, _p(rays6), _p(obj), _p(t), _p(inside))
+        return obj, t, inside
+
+    def newton_cull(self, rays6, patch):
+        rays6 = _f64(rays6, (-1, 6))
+        patch = np.ascontiguousarray(patch, dtype=np.int32)
+        n = rays6.shape[0]
+        dop, sub = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+        self.dh.lib.dh_newton_cull(self.h, n, _p(rays6), _p(patch), _p(dop), _p(sub))
+        return dop.astype(bool), sub.astype(bool)
+
+    def near_collide(self, prm, rays6, ids=None, pass_id=0, node=0, cull=1):
+        rays6 = _f64(rays6, (-1, 6))
+        n = rays6.shape[0]
+        out = np.zeros(n, dtype=hit_dtype)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        solves = C.c_uint64()
+        self.dh.lib.dh_near_collide(self.h, prm.newton_mode, prm.newton_restarts, prm.newton_iters, cull, prm.seed, n,
+                                    _p(rays6), _p(ids), pass_id, node, _p(out), C.addressof(solves))
+        return out, solves.value
+
+
+class DeviceHost:
+    def __init__(self):
+        self.lib = L = C.CDLL(build())
+        L.dh_draw2.argtypes = [U64, U64, U64, U32, U32, U32, U32, VP]
+        L.dh_unit_rand_vec.argtypes = [U64, U64, I64, VP, U32, VP]
+        L.dh_aabb_intersect.argtypes = [VP, I64, VP, VP]
+        L.dh_bezier_eval.argtypes = [C.c_int, VP, I64, VP, VP]
+        L.dh_newton.argtypes = [C.c_int, VP, I64, VP, VP, C.c_int, C.c_int, VP]
+        L.dh_color_uv.argtypes = [C.c_int, C.c_int, VP, I64, VP, VP]
+        L.dh_unit_rand_refl.argtypes = [I64, VP, VP, C.c_int, VP]
+        L.dh_refracted.argtypes = [I64, VP, VP, VP, VP]
+        L.dh_scene_create.argtypes = [C.POINTER(abi.SppmSceneDesc), C.c_char_p, C.c_int]
+        L.dh_scene_create.restype = VP
+        L.dh_scene_free.argtypes = [VP]
+        L.dh_scene_n_patches.argtypes = [VP]
+        L.dh_scene_n_patches.restype = I64
+        L.dh_scene_culled.argtypes = [VP]
+        L.dh_scene_culled.restype = U64
+        L.dh_scene_tables.argtypes = [VP] * 6
+        L.dh_scene_material.argtypes = [VP, C.c_int, VP, VP]
+        L.dh_analytic_nearest.argtypes = [VP, I64, VP, VP, VP, VP]
+        L.dh_newton_cull.argtypes = [VP, I64, VP, VP, VP, VP]
+        L.dh_near_collide.argtypes = [VP, C.c_int, C.c_int, C.c_int, C.c_int, U64, I64, VP, VP, U64, C.c_int, VP, VP]
+
+    def draw2(self, seed, pass_id, ident, node, purpose, sub, patch):
+        o = (C.c_double * 2)()
+        self.lib.dh_draw2(seed, pass_id, ident, node, purpose, sub, patch, o)
+        return o[0], o[1]
+
+    def aabb_intersect(self, box6, rays6):
+        box6, rays6 = _f64(box6, (6,)), _f64(rays6, (-1, 6))
+        out = np.empty(rays6.shape[0], dtype=np.int32)
+        self.lib.dh_aabb_intersect(_p(box6), rays6.shape[0], _p(rays6), _p(out))
+        return out.astype(bool)
+
+    def bezier_eval(self, mode, P48, uv):
+        """mode 0: eval_exact(P), 1: eval_mono(A), 2: eval_fast(P) -> (S, Su, Sv) [n, 3] each."""
+        P48, uv = _f64(P48, (48,)), _f64(uv, (-1, 2))
+        out = np.empty((uv.shape[0], 9))
+        self.lib.dh_bezier_eval(mode, _p(P48), uv.shape[0], _p(uv), _p(out))
+        return out[:, 0:3], out[:, 3:6], out[:, 6:9]
+
+    def newton(self, mode, P48, rays6, seeds, iters=10):
+        """Bezier3::newton of the kernels on ONE patch (P for modes 0/2, the monomial A for mode 1)."""
+        P48, rays6 = _f64(P48, (48,)), _f64(rays6, (-1, 6))
+        n = rays6.shape[0]
+        seeds = _f64(seeds, (n, -1, 2))
+        out = np.empty((n, 3))
+        self.lib.dh_newton(mode, _p(P48), n, _p(rays6), _p(seeds), seeds.shape[1], iters, _p(out))
+        return out
+
+    def color_uv(self, tex_map, uv):
+        tex_map = np.ascontiguousarray(tex_map, dtype=np.uint8)
+        uv = _f64(uv, (-1, 2))
+        out = np.empty((uv.shape[0], 3))
+        self.lib.dh_color_uv(tex_map.shape[0], tex_map.shape[1], _p(tex_map), uv.shape[0], _p(uv), _p(out))
+        return out
+
+    def unit_rand_refl(self, norm3, u12, fast=False):
+        norm3, u12 = _f64(norm3, (-1, 3)), _f64(u12, (-1, 2))
+        out = np.empty_like(norm3)
+        self.lib.dh_unit_rand_refl(norm3.shape[0], _p(norm3), _p(u12), int(fast), _p(out))
+        return out
+
+    def refracted(self, I3, N3, nn):
+        I3, N3, nn = _f64(I3, (-1, 3)), _f64(N3, (-1, 3)), _f64(nn, (-1,))
+        out = np.empty_like(I3)
+        self.lib.dh_refracted(I3.shape[0], _p(I3), _p(N3), _p(nn), _p(out))
+        return out
+
+    def unit_rand_vec(self, seed, pass_id, ids, purpose):
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        out = np.empty((ids.shape[0], 3))
+        self.lib.dh_unit_rand_vec(seed, pass_id, ids.shape[0], _p(ids), purpose, _p(out))
+        return out
+
+    def scene(self, scene) -> HostScene:
+        return HostScene(self, scene)

@@ -1,0 +1,128 @@
+// cuda_host_shim.h — TEST INFRASTRUCTURE, not product.  Lets g++ compile the device headers of
+// raytrace3_b200/csrc (device_math.cuh, scene.cuh, scene_prep.h) for the host, so the CPU test
+// suite can hold the PRODUCT's own arithmetic (not a restatement of it) to the oracle without a
+// GPU: tests/test_device_host_cpu.py.  Nothing under raytrace3_b200/ includes this file and the
+// library never runs these functions on the host.
+//
+// A warp is emulated by 32 fibers (ucontext) on ONE host thread, switched round-robin at every warp
+// collective (__ballot_sync, __shfl_sync, __shfl_xor_sync, __any_sync, __syncwarp, __syncthreads):
+// lane l runs until its next collective and then hands over to lane (l+1) % 32, so when lane 31
+// arrives every lane has, and lane 0 resumes behind the barrier.  That is exact for code whose
+// collectives are called convergently with the full mask, which is how scene.cuh calls all of its
+// collectives (and what the hardware requires of __syncwarp(FULL) anyway); a divergent collective
+// would deadlock or mis-pair here instead of passing silently.  Values are exchanged through a
+// 32-slot table between two such barriers.  One emulated block = one warp; several warps run on
+// several host threads.
+#pragma once
+#define SPPM_HOST_EMULATION 1
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <ucontext.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+using std::max;
+using std::min;
+
+// nvcc's __noinline__ keyword; empty (not an attribute) so that libstdc++'s own
+// __attribute__((__noinline__)) still parses after this point
+#ifndef __noinline__
+#define __noinline__
+#endif
+
+// ---- thread coordinates and the fiber warp ------------------------------------------------
+struct DhDim {
+  unsigned x = 0, y = 0, z = 0;
+};
+struct DhWarp {
+  ucontext_t main_ctx;
+  ucontext_t lane_ctx[32];
+  bool done[32];
+  int cur = 0;  // the lane that is running
+  uint64_t slot[32];
+  unsigned long long barriers = 0;
+};
+extern thread_local DhWarp* dh_warp;  // null: a lone lane (collectives degenerate to one participant)
+struct DhThreadIdx {
+  struct X {
+    operator unsigned() const { return dh_warp ? (unsigned)dh_warp->cur : 0u; }
+  } x;
+};
+static const DhThreadIdx dh_thread_idx{};
+static const DhDim dh_block_dim_32{32, 1, 1};
+#define threadIdx dh_thread_idx
+#define blockDim dh_block_dim_32
+
+inline void dh_barrier() {
+  DhWarp* w = dh_warp;
+  if (!w) return;
+  const int me = w->cur, next = (me + 1) & 31;
+  w->barriers += (me == 0);
+  w->cur = next;
+  swapcontext(&w->lane_ctx[me], &w->lane_ctx[next]);
+}
+template <class T>
+inline T dh_exchange(T v, int src) {  // every lane publishes v, then reads lane src's value
+  static_assert(sizeof(T) <= 8, "exchange slot is 64 bits");
+  if (!dh_warp) return v;
+  uint64_t bits = 0;
+  memcpy(&bits, &v, sizeof(T));
+  dh_warp->slot[dh_warp->cur] = bits;
+  dh_barrier();
+  const uint64_t got = dh_warp->slot[src & 31];
+  dh_barrier();  // the table may be rewritten after everyone has read
+  T out;
+  memcpy(&out, &got, sizeof(T));
+  return out;
+}
+inline void __syncwarp() { dh_barrier(); }
+inline void __syncthreads() { dh_barrier(); }
+inline unsigned __ballot_sync(unsigned, bool p) {
+  if (!dh_warp) return p ? 1u : 0u;
+  dh_warp->slot[dh_warp->cur] = p ? 1 : 0;
+  dh_barrier();
+  unsigned m = 0;
+  for (int l = 0; l < 32; l++) m |= (unsigned)dh_warp->slot[l] << l;
+  dh_barrier();
+  return m;
+}
+inline bool __any_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) != 0; }
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src) { return dh_exchange(v, src); }
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int off) { return dh_exchange(v, (dh_warp ? dh_warp->cur : 0) ^ off); }
+
+// ---- scalar intrinsics --------------------------------------------------------------------
+template <class T>
+inline T __ldg(const T* p) { return *p; }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+inline double __longlong_as_double(long long v) {
+  double d;
+  memcpy(&d, &v, 8);
+  return d;
+}
+inline long long __double_as_longlong(double d) {
+  long long v;
+  memcpy(&v, &d, 8);
+  return v;
+}
+inline float __double2float_rn(double d) { return (float)d; }
+// __fdividef has <= 2 ulp error on the device; the exact quotient lies inside that band
+inline float __fdividef(float a, float b) { return a / b; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
+// stand-in for rcp.approx.ftz.f64 (scene.cuh rcp_newton): a reciprocal good to ~20 bits whose
+// low mantissa word is zero, as PTX specifies; the two Newton-Raphson steps that follow it are
+// the product's own
+inline double dh_rcp_approx(double x) {
+  long long b = __double_as_longlong(1.0 / x);
+  b &= (long long)0xFFFFFFFF00000000ull;
+  return __longlong_as_double(b);
+}

@@ -1,0 +1,295 @@
+// device_host.cpp — TEST INFRASTRUCTURE, not product: the device functions of
+// raytrace3_b200/csrc/{device_math.cuh, scene.cuh} and the host table builder scene_prep.h,
+// compiled for the CPU by g++ through cuda_host_shim.h and exported as batch functions for
+// tests/test_device_host_cpu.py.  The point is that the `-m "not gpu"` suite checks the SAME source
+// lines the sm_100a kernels are built from (plane / sphere / AABB tests with their division-free
+// rejects, patch evaluation in the three arithmetic modes, the Newton step and restart, the Newton
+// culls, texture look-up, sampling and optics, the whole warp-cooperative near_collide + shade_hit)
+// against the oracle, at fuzz sizes that would cost GPU minutes.  Built by tests/device_host/build.py:
+//   g++ -O2 -ffp-contract=off (no FMA contraction, like the library's -fmad=false) -pthread
+#include "cuda_host_shim.h"
+
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../raytrace3_b200/csrc/scene_prep.h"
+
+thread_local DhWarp* dh_warp = nullptr;
+
+using namespace sppm;
+
+namespace {
+
+struct DhScene {
+  PreppedScene ps;
+  std::vector<std::vector<uint32_t>> bgrx;
+  std::vector<DevTexture> tex;
+  double lut255[256];
+  unsigned long long culled = 0;
+  SceneView sv;
+};
+
+// the expansion tex_expand_kernel (abi.cu) does on the device
+std::vector<uint32_t> expand_texels(const uint8_t* bgr, size_t n) {
+  std::vector<uint32_t> out(n);
+  for (size_t i = 0; i < n; i++) out[i] = (uint32_t)bgr[3 * i] | ((uint32_t)bgr[3 * i + 1] << 8) | ((uint32_t)bgr[3 * i + 2] << 16);
+  return out;
+}
+
+NewtonCfg make_cfg(int mode, int restarts, int iters, int cull, uint64_t seed) {
+  NewtonCfg c;
+  c.restarts = restarts;
+  c.iters = iters;
+  c.mode = mode;
+  c.cull = cull;
+  c.seed = seed;
+  return c;
+}
+
+// run f(lane) for the 32 lanes of one emulated warp (fibers on the calling thread, see the shim)
+thread_local std::function<void(int)>* dh_fn = nullptr;
+void fiber_entry() {
+  DhWarp* w = dh_warp;
+  const int me = w->cur;
+  (*dh_fn)(me);
+  w->done[me] = true;
+  // every lane passes the same barriers, so lane 0 ends first and the others wait behind the last one
+  const int next = (me + 1) & 31;
+  if (!w->done[next]) {
+    w->cur = next;
+    setcontext(&w->lane_ctx[next]);
+  }
+  setcontext(&w->main_ctx);
+}
+unsigned long long run_warp(std::function<void(int)> f) {
+  constexpr size_t STACK = 256 << 10;
+  std::vector<char> stacks(32 * STACK);
+  DhWarp warp;
+  for (int l = 0; l < 32; l++) {
+    warp.done[l] = false;
+    getcontext(&warp.lane_ctx[l]);
+    warp.lane_ctx[l].uc_stack.ss_sp = stacks.data() + (size_t)l * STACK;
+    warp.lane_ctx[l].uc_stack.ss_size = STACK;
+    warp.lane_ctx[l].uc_link = nullptr;
+    makecontext(&warp.lane_ctx[l], fiber_entry, 0);
+  }
+  dh_warp = &warp;
+  dh_fn = &f;
+  warp.cur = 0;
+  swapcontext(&warp.main_ctx, &warp.lane_ctx[0]);
+  dh_warp = nullptr;
+  dh_fn = nullptr;
+  for (int l = 0; l < 32; l++)
+    if (!warp.done[l]) abort();  // a divergent collective
+  return warp.barriers;
+}
+
+}  // namespace
+
+extern "C" {
+
+void dh_draw2(uint64_t seed, uint64_t pass, uint64_t id, uint32_t node, uint32_t purpose, uint32_t sub, uint32_t patch,
+              double out[2]) {
+  draw2(seed, pass, id, node, purpose, sub, patch, out[0], out[1]);
+}
+void dh_unit_rand_vec(uint64_t seed, uint64_t pass, int64_t n, const uint64_t* ids, uint32_t purpose, double* out3) {
+  for (int64_t i = 0; i < n; i++) {
+    const d3 v = unit_rand_vec(seed, pass, ids[i], purpose);
+    out3[3 * i] = v.x; out3[3 * i + 1] = v.y; out3[3 * i + 2] = v.z;
+  }
+}
+void dh_aabb_intersect(const double box[6], int64_t n, const double* rays6, int32_t* out) {
+  for (int64_t i = 0; i < n; i++) out[i] = aabb_intersect(box, ld3(rays6 + 6 * i), ld3(rays6 + 6 * i + 3)) ? 1 : 0;
+}
+// mode 0: eval_exact(P), 1: eval_mono(A), 2: eval_fast(P); out[n][9] = S, Su, Sv
+void dh_bezier_eval(int mode, const double* P48, int64_t n, const double* uv, double* out9) {
+  for (int64_t i = 0; i < n; i++) {
+    const double u = uv[2 * i], v = uv[2 * i + 1];
+    const PatchEval e = mode == 0 ? eval_exact(P48, u, v) : (mode == 1 ? eval_mono(P48, u, v) : eval_fast(P48, u, v));
+    double* o = out9 + 9 * i;
+    o[0] = e.S.x; o[1] = e.S.y; o[2] = e.S.z;
+    o[3] = e.Su.x; o[4] = e.Su.y; o[5] = e.Su.z;
+    o[6] = e.Sv.x; o[7] = e.Sv.y; o[8] = e.Sv.z;
+  }
+}
+// Bezier3::newton as the kernels run it: `restarts` x newton_restart<MODE>, the min over restarts
+// kept with (t, restart index) order -- flush_items' segmented arg-min.  seeds[n][restarts][2].
+void dh_newton(int mode, const double* P48, int64_t n, const double* rays6, const double* seeds, int restarts, int iters,
+               double* tuv) {
+  for (int64_t i = 0; i < n; i++) {
+    const d3 org = ld3(rays6 + 6 * i), dir = ld3(rays6 + 6 * i + 3);
+    double bt = SPPM_MAX_NUM, bu = SPPM_MAX_NUM, bv = SPPM_MAX_NUM;
+    for (int r = 0; r < restarts; r++) {
+      const double u0 = seeds[((size_t)i * restarts + r) * 2], v0 = seeds[((size_t)i * restarts + r) * 2 + 1];
+      double t, u, v;
+      const bool found = mode == 0   ? newton_restart<0>(P48, org, dir, u0, v0, iters, t, u, v)
+                         : mode == 1 ? newton_restart<1>(P48, org, dir, u0, v0, iters, t, u, v)
+                                     : newton_restart<2>(P48, org, dir, u0, v0, iters, t, u, v);
+      if (found && t < bt) {
+        bt = t; bu = u; bv = v;
+      }
+    }
+    tuv[3 * i] = bt; tuv[3 * i + 1] = bu; tuv[3 * i + 2] = bv;
+  }
+}
+void dh_color_uv(int rows, int cols, const uint8_t* bgr8, int64_t n, const double* uv, double* out3) {
+  const std::vector<uint32_t> words = expand_texels(bgr8, (size_t)rows * cols);
+  DevTexture t;
+  t.rows = rows; t.cols = cols; t.bgr = bgr8; t.bgrx = words.data();
+  double lut[256];
+  for (int i = 0; i < 256; i++) lut[i] = i / 255.0;
+  for (int64_t i = 0; i < n; i++) {
+    const d3 c = color_uv(t, lut, uv[2 * i], uv[2 * i + 1]);
+    out3[3 * i] = c.x; out3[3 * i + 1] = c.y; out3[3 * i + 2] = c.z;
+  }
+}
+void dh_unit_rand_refl(int64_t n, const double* norm3, const double* u12, int fast, double* out3) {
+  for (int64_t i = 0; i < n; i++) {
+    const d3 v = unit_rand_refl(ld3(norm3 + 3 * i), u12[2 * i], u12[2 * i + 1], fast != 0);
+    out3[3 * i] = v.x; out3[3 * i + 1] = v.y; out3[3 * i + 2] = v.z;
+  }
+}
+// normalize3(refracted(...)) as every call site has it (trace.cu, wavefront.cu), like orc_refracted
+void dh_refracted(int64_t n, const double* I3, const double* N3, const double* nn, double* out3) {
+  for (int64_t i = 0; i < n; i++) {
+    const d3 v = normalize3(refracted(ld3(I3 + 3 * i), ld3(N3 + 3 * i), nn[i]));
+    out3[3 * i] = v.x; out3[3 * i + 1] = v.y; out3[3 * i + 2] = v.z;
+  }
+}
+
+// ---- a scene flattened by the product's own prep_scene ----------------------------------------
+void* dh_scene_create(const SppmSceneDesc* s, char* err, int errlen) {
+  DhScene* h = new DhScene();
+  if (const char* bad = prep_scene(s, h->ps)) {
+    if (err && errlen > 0) {
+      strncpy(err, bad, (size_t)errlen - 1);
+      err[errlen - 1] = 0;
+    }
+    delete h;
+    return nullptr;
+  }
+  h->tex.resize((size_t)s->n_textures);
+  for (int t = 0; t < s->n_textures; t++) {
+    const SppmTexture& ht = s->textures[t];
+    h->bgrx.push_back(expand_texels(ht.bgr8, (size_t)ht.rows * ht.cols));
+    h->tex[t].rows = ht.rows;
+    h->tex[t].cols = ht.cols;
+    h->tex[t].bgr = ht.bgr8;  // borrowed; the tracers read bgrx only
+  }
+  for (int t = 0; t < s->n_textures; t++) h->tex[t].bgrx = h->bgrx[t].data();
+  for (int i = 0; i < 256; i++) h->lut255[i] = i / 255.0;  // stage_scene
+  SceneView& v = h->sv;
+  v.obj = h->ps.objs.data();
+  v.patchP = h->ps.patchP.data();
+  v.patchA = h->ps.patchA.data();
+  v.patchBox = h->ps.patchBox.data();
+  v.patchDop = h->ps.patchDop.data();
+  v.patchSub = h->ps.patchSub.data();
+  v.culled = &h->culled;
+  v.tex = h->tex.data();
+  v.lut255 = h->lut255;
+  v.n_obj = (int)h->ps.objs.size();
+  return h;
+}
+void dh_scene_free(void* p) { delete (DhScene*)p; }
+int64_t dh_scene_n_patches(void* p) { return (int64_t)(((DhScene*)p)->ps.patchBox.size() / 6); }
+uint64_t dh_scene_culled(void* p) { return ((DhScene*)p)->culled; }
+void dh_scene_tables(void* p, double* box6, double* dop26, double* sub96, double* A48, double* objbox6) {
+  const DhScene* h = (const DhScene*)p;
+  memcpy(box6, h->ps.patchBox.data(), h->ps.patchBox.size() * 8);
+  memcpy(dop26, h->ps.patchDop.data(), h->ps.patchDop.size() * 8);
+  memcpy(sub96, h->ps.patchSub.data(), h->ps.patchSub.size() * 8);
+  memcpy(A48, h->ps.patchA.data(), h->ps.patchA.size() * 8);
+  for (size_t i = 0; i < h->ps.objs.size(); i++) memcpy(objbox6 + 6 * i, h->ps.objs[i].box, 48);
+}
+// the material flags and Roulette weights of object i (Element.h:16-18, Obj.h:12-15)
+void dh_scene_material(void* p, int i, int32_t flags[3], double weights[4]) {
+  const DevObject& o = ((const DhScene*)p)->ps.objs[(size_t)i];
+  flags[0] = o.isDiff; flags[1] = o.isRefl; flags[2] = o.isRefr;
+  weights[0] = o.diffr; weights[1] = o.reflr; weights[2] = o.refrr; weights[3] = o.allr;
+}
+// planes and spheres only, per ray, in object order: the analytic loop of photon_step_kernel
+void dh_analytic_nearest(void* p, int64_t n, const double* rays6, int32_t* obj, double* t, int32_t* inside) {
+  const SceneView& sv = ((const DhScene*)p)->sv;
+  for (int64_t i = 0; i < n; i++) {
+    const d3 org = ld3(rays6 + 6 * i), dir = ld3(rays6 + 6 * i + 3);
+    Hit best;
+    best.dist = SPPM_MAX_NUM;
+    best.obj = -1;
+    best.inside = false;
+    for (int o = 0; o < sv.n_obj; o++) {
+      const DevObject& ob = sv.obj[o];
+      if (ob.kind == SPPM_OBJ_PLANE) test_plane(ob, o, org, dir, best);
+      else if (ob.kind == SPPM_OBJ_SPHERE) test_sphere(ob, o, org, dir, best);
+    }
+    obj[i] = best.obj;
+    t[i] = best.dist;
+    inside[i] = best.inside ? 1 : 0;
+  }
+}
+// the two Newton culls of flush_items on (ray, global patch) pairs: 1 = "this solve records nothing"
+void dh_newton_cull(void* p, int64_t n, const double* rays6, const int32_t* patch, int32_t* dop_miss, int32_t* sub_miss) {
+  const SceneView& sv = ((const DhScene*)p)->sv;
+  for (int64_t i = 0; i < n; i++) {
+    const d3 org = ld3(rays6 + 6 * i), dir = ld3(rays6 + 6 * i + 3);
+    dop_miss[i] = dop_line_miss(sv.patchDop + (size_t)patch[i] * 26, org, dir) ? 1 : 0;
+    sub_miss[i] = sub_boxes_miss(sv.patchSub + (size_t)patch[i] * 96, org, dir) ? 1 : 0;
+  }
+}
+// Scene::NearCollide through the warp-cooperative near_collide + shade_hit, as intersect_kernel
+// (trace.cu) runs it: ray i on lane i % 32 of an emulated warp, draws addressed by (pass, id, node).
+void dh_near_collide(void* p, int newton_mode, int restarts, int iters, int cull, uint64_t seed, int64_t n,
+                     const double* rays6, const uint64_t* ids, uint64_t pass, int node, SppmHit* out,
+                     uint64_t* patch_solves) {
+  const SceneView& sv = ((const DhScene*)p)->sv;
+  const NewtonCfg cfg = make_cfg(newton_mode, restarts, iters, cull, seed);
+  const int64_t n_batch = (n + 31) / 32;
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_batch, std::min(16u, std::max(1u, std::thread::hardware_concurrency()))));
+  std::vector<unsigned long long> solves_of(T, 0);
+  std::vector<std::thread> th;
+  for (int w = 0; w < T; w++)
+    th.emplace_back([&, w] {
+      WarpScratch* ws = new WarpScratch();
+      run_warp([&](int lane) {
+        unsigned long long solves = 0;
+        for (int64_t b = w; b < n_batch; b += T) {  // one batch of 32 rays = one warp of intersect_kernel
+          const int64_t i = b * 32 + lane;
+          const bool active = i < n;
+          d3 org = mk(0, 0, 0), dir = mk(0, 0, 1);
+          uint64_t id = (uint64_t)i;
+          if (active) {
+            org = ld3(rays6 + 6 * i);
+            dir = ld3(rays6 + 6 * i + 3);
+            if (ids) id = ids[i];
+          }
+          const Hit h = near_collide(sv, ws, cfg, active, org, dir, pass, id, (uint32_t)node, SPPM_DOMAIN_TEST, solves);
+          if (active) {
+            SppmHit o;
+            o.t = h.obj >= 0 ? h.dist : SPPM_MAX_NUM;
+            o.u = h.u; o.v = h.v;
+            o.obj = h.obj; o.patch = h.patch; o.inside = h.inside ? 1 : 0; o.pad = 0;
+            for (int k = 0; k < 3; k++) o.pos[k] = o.n[k] = o.color[k] = 0;
+            if (h.obj >= 0) {
+              const Surface s = shade_hit(sv, h, org, dir);
+              o.pos[0] = s.pos.x; o.pos[1] = s.pos.y; o.pos[2] = s.pos.z;
+              o.n[0] = s.n.x; o.n[1] = s.n.y; o.n[2] = s.n.z;
+              o.color[0] = s.color.x; o.color[1] = s.color.y; o.color[2] = s.color.z;
+            }
+            out[i] = o;
+          }
+          __syncwarp();  // near_collide's scratch is reused by the next batch of rays
+        }
+        if (lane == 0) solves_of[w] = solves;
+      });
+      delete ws;
+    });
+  for (auto& t : th) t.join();
+  if (patch_solves) {
+    *patch_solves = 0;
+    for (unsigned long long v : solves_of) *patch_solves += v;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,330 @@
+"""The PRODUCT's device source on the CPU: raytrace3_b200/csrc/{device_math.cuh, scene.cuh} and the
+host table builder scene_prep.h compiled by g++ through tests/device_host/cuda_host_shim.h (a warp
+= 32 fibers switched at every warp collective), held to the oracle and to the golden vectors the
+reference's own code produced.  These are the same source lines the sm_100a kernels are built
+from, so the arithmetic, the division-free rejects, the Newton culls, the item queue and the
+segmented arg-min of near_collide are fuzzed here at sizes that would cost GPU minutes; what this
+cannot see is nvcc's code generation (the `-m gpu` tests hold that)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import custom_scene, quirks_scene, rays_at_patches, rays_at_teapot, rays_in_room
+from raytrace3_b200 import abi
+from raytrace3_b200.scene import make_scene, synthetic_texture
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def dh():
+    from device_host import DeviceHost
+    return DeviceHost()
+
+
+def _params(**kw):
+    p = abi.default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _patches(sc):
+    return np.concatenate([o.P for o in sc.objvec if o.kind == 2], axis=0).reshape(-1, 48)
+
+
+def _scene(name):
+    if name == "custom":
+        return custom_scene()
+    if name == "quirks":
+        return quirks_scene()
+    return make_scene(name, textures="synthetic" if name == "reference" else None)
+
+
+# ---- the counter RNG and the samplers ---------------------------------------------------------
+def test_draw2_is_the_oracles_philox(dh, oracle):
+    rng = np.random.RandomState(1)
+    for _ in range(300):
+        a = [int(rng.randint(0, 2 ** 62)) for _ in range(3)] + [int(rng.randint(0, 2 ** 31)) for _ in range(4)]
+        assert dh.draw2(*a) == oracle.draw2(*a)
+
+
+def test_unit_rand_refl_and_refracted(dh, oracle):
+    """Vec3::UnitRandRefl / Refracted (Vec3.h:57-65, 90-115, 124-134), incl. total internal reflection."""
+    rng = np.random.RandomState(2)
+    n = 2000
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[:6] = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0], [0, -1, 0], [0, 0, -1]], dtype=float)  # axis branches
+    u12 = rng.uniform(size=(n, 2))
+    got = dh.unit_rand_refl(nrm, u12, fast=False)
+    ref = np.stack([oracle.unit_rand_refl(nrm[i], u12[i, 0], u12[i, 1]) for i in range(n)])
+    np.testing.assert_array_equal(got, ref)
+    fast = dh.unit_rand_refl(nrm, u12, fast=True)       # SPPM_MATH_FAST: sincospi-style evaluation
+    np.testing.assert_allclose(fast, ref, rtol=0, atol=1e-12)
+    I = rng.normal(size=(n, 3))
+    I /= np.linalg.norm(I, axis=1, keepdims=True)
+    nn = np.where(rng.uniform(size=n) < 0.5, 1.5, 1 / 1.5)
+    got = dh.refracted(I, nrm, nn)
+    ref = np.stack([oracle.refracted(I[i], nrm[i], nn[i]) for i in range(n)])
+    np.testing.assert_array_equal(got, ref)
+
+
+def test_color_uv_bilinear(dh, oracle):
+    """Texture::colorUV (Element.h:61-72) through the one-word-per-texel device layout."""
+    tex = synthetic_texture(37, 53, 11)
+    rng = np.random.RandomState(3)
+    uv = rng.uniform(-0.2, 1.2, size=(3000, 2))
+    uv[:8] = [[0, 0], [1, 1], [0, 1], [1, 0], [0.5, 0.5], [1 - 1e-16, 1 - 1e-16], [1e-300, 0], [0.999999, 0.000001]]
+    got = dh.color_uv(tex, uv)
+    ref = np.stack([oracle.color_uv(tex, u, v) for u, v in uv])
+    np.testing.assert_array_equal(got, ref)
+
+
+# ---- boxes, patch evaluation, Newton ----------------------------------------------------------
+def test_aabb_intersect_fuzz(dh, oracle):
+    """AABBbox::intersect (Bezier.h:20-51), incl. axis-parallel rays and origins inside the box."""
+    rng = np.random.RandomState(4)
+    box = np.array([-3.0, 1.0, 2.0, 4.0, 5.0, 2.5])
+    n = 20000
+    org = rng.uniform(-12, 12, size=(n, 3))
+    d = rng.normal(size=(n, 3))
+    tgt = box[:3] + (box[3:] - box[:3]) * rng.uniform(-0.3, 1.3, size=(n // 2, 3))
+    d[:n // 2] = tgt - org[:n // 2]                      # half aimed at (or just past) the box
+    d[rng.uniform(size=(n, 3)) < 0.15] = 0.0           # zero components
+    d[np.abs(d).sum(1) == 0] = [0, 0, 1]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([org, d], axis=1)
+    got = dh.aabb_intersect(box, rays)
+    ref = np.array([oracle.aabb_intersect(box, r[:3], r[3:]) for r in rays])
+    np.testing.assert_array_equal(got, ref)
+    assert 2000 < ref.sum() < n - 2000
+
+
+def test_bezier_eval_three_modes(dh, oracle):
+    """evalPatchPoint / DerivU / DerivV (Bezier.h:85-111): EXACT bit for bit; the monomial (FAST)
+    and the factored Bernstein (FAST_BERNSTEIN) forms to 1e-12 of the patch's scale."""
+    sc = make_scene("reference", textures=None)
+    P = _patches(sc)
+    hs = dh.scene(sc)
+    A = hs.tables()["A"]
+    rng = np.random.RandomState(5)
+    uv = rng.uniform(-0.5, 1.5, size=(400, 2))   # Newton iterates leave [0,1]^2
+    uv[:4] = [[0, 0], [1, 1], [0, 1], [1, 0]]
+    for p in range(P.shape[0]):
+        ref = np.stack([np.concatenate(oracle.bezier_eval(P[p], u, v)) for u, v in uv])
+        S, Su, Sv = dh.bezier_eval(0, P[p], uv)
+        np.testing.assert_array_equal(np.concatenate([S, Su, Sv], axis=1), ref)
+        scale = np.abs(P[p]).max()
+        for mode, coef in ((1, A[p]), (2, P[p])):
+            S, Su, Sv = dh.bezier_eval(mode, coef, uv)
+            np.testing.assert_allclose(np.concatenate([S, Su, Sv], axis=1), ref, rtol=0, atol=2e-12 * scale)
+
+
+def test_newton_exact_is_the_reference_bit_for_bit(dh, oracle):
+    """Bezier3::newton (Bezier.h:112-159): the kernels' newton_restart<EXACT> + min over restarts
+    == the golden vectors of the reference's own code, and == the oracle on a larger fuzz."""
+    g = np.load(os.path.join(GOLDEN, "ref_newton.npz"))
+    sc = make_scene("reference", textures=None)
+    P = _patches(sc)
+    for p in np.unique(g["patch"]):
+        sel = g["patch"] == p
+        got = dh.newton(0, P[p], g["rays"][sel], g["seeds"][sel])
+        np.testing.assert_array_equal(got, g["tuv"][sel])
+    prm = _params()
+    rng = np.random.RandomState(6)
+    n = 6000
+    patch = np.sort(rng.randint(0, P.shape[0], size=n)).astype(np.int32)
+    rays = rays_at_patches(patch, 7, sc)
+    rays[::7] = rays_at_teapot(len(rays[::7]), 8, sc)
+    seeds = rng.uniform(size=(n, 20, 2))
+    prm.newton_restarts = 20
+    ref = oracle.bezier_patch_batch(sc, prm, rays, patch, seeds)
+    for p in range(P.shape[0]):
+        sel = patch == p
+        np.testing.assert_array_equal(dh.newton(0, P[p], rays[sel], seeds[sel]), ref[sel])
+    assert (ref[:, 0] < 1e19).sum() > 3000 and (ref[:, 0] >= 1e19).sum() > 300
+
+
+@pytest.mark.parametrize("mode", [abi.SPPM_NEWTON_FAST, abi.SPPM_NEWTON_FAST_BERNSTEIN])
+def test_newton_fast_modes_within_1e6(dh, oracle, mode):
+    """FAST modes (FMA, reciprocal by rcp + 2 Newton-Raphson steps — here a 20-bit stand-in for
+    rcp.approx.ftz.f64 — and Cramer's rule) against the reference arithmetic: same hit/miss,
+    (t, u, v) within the north-star 1e-6."""
+    sc = make_scene("reference", textures=None)
+    P = _patches(sc)
+    A = dh.scene(sc).tables()["A"]
+    prm = _params(newton_restarts=50)
+    rng = np.random.RandomState(9)
+    n = 3200
+    patch = (np.arange(n) % P.shape[0]).astype(np.int32)
+    rays = rays_at_patches(patch, 10, sc)
+    seeds = rng.uniform(size=(n, 50, 2))
+    ref = oracle.bezier_patch_batch(sc, prm, rays, patch, seeds)
+    got = np.empty_like(ref)
+    for p in range(P.shape[0]):
+        sel = patch == p
+        got[sel] = dh.newton(mode, A[p] if mode == abi.SPPM_NEWTON_FAST else P[p], rays[sel], seeds[sel])
+    hit = ref[:, 0] < 1e19
+    assert hit.sum() > 2000
+    np.testing.assert_array_equal(got[:, 0] < 1e19, hit)
+    rel = np.abs(got[hit] - ref[hit]) / np.maximum(np.abs(ref[hit]), 1e-12)
+    assert rel.max() <= 1e-6  # north-star tolerance on (t, u, v)
+
+
+# ---- the tables sppm_scene_upload builds (scene_prep.h) ----------------------------------------
+@pytest.mark.parametrize("name", ["reference", "stress"])
+def test_scene_tables(dh, oracle, name):
+    sc = _scene(name)
+    P = _patches(sc).reshape(-1, 16, 3)
+    hs = dh.scene(sc)
+    T = hs.tables()
+    assert hs.n_patches == P.shape[0]
+    # per-patch and per-object AABBs: the control points' min / max (Bezier.h:165-175, 219-222)
+    np.testing.assert_array_equal(T["box"][:, :3], P.min(1))
+    np.testing.assert_array_equal(T["box"][:, 3:], P.max(1))
+    first = 0
+    for i, o in enumerate(sc.objvec):
+        if o.kind == 2:
+            k = o.P.reshape(-1, 16, 3).shape[0]
+            np.testing.assert_array_equal(T["objbox"][i, :3], P[first:first + k].min((0, 1)))
+            np.testing.assert_array_equal(T["objbox"][i, 3:], P[first:first + k].max((0, 1)))
+            first += k
+    # the cull volumes contain every surface point grown by the acceptance radius sqrt(M_EPS) = 0.01
+    A13 = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [1, -1, 0], [1, 0, 1], [1, 0, -1],
+                    [0, 1, 1], [0, 1, -1], [1, 1, 1], [1, 1, -1], [1, -1, 1], [-1, 1, 1]], dtype=float)
+    rng = np.random.RandomState(11)
+    for p in range(P.shape[0]):
+        uv = rng.uniform(size=(600, 2))
+        S, _, _ = dh.bezier_eval(0, P[p].reshape(48), uv)
+        e = S @ A13.T
+        r = 0.01 * np.linalg.norm(A13, axis=1)
+        assert (e - r >= T["dop"][p, :13]).all() and (e + r <= T["dop"][p, 13:]).all()
+        b = np.minimum((uv[:, 0] * 4).astype(int), 3) * 4 + np.minimum((uv[:, 1] * 4).astype(int), 3)  # su * 4 + sv
+        lo, hi = T["sub"][p][b, :3], T["sub"][p][b, 3:]
+        assert (S - 0.01 >= lo).all() and (S + 0.01 <= hi).all()
+    # material flags and Roulette weights (Element.h:16-18, Vec3.h:72-79, Obj.h:12-15)
+    for i, o in enumerate(sc.objvec):
+        fl, w = hs.material(i)
+        m = o.material
+        for k, ch in enumerate((m.diff, m.refl, m.refr)):
+            assert fl[k] == (not any(abs(c) < 1e-4 for c in ch))
+            assert w[k] == (ch[0] + ch[1] + ch[2]) / 3
+        assert w[3] == w[0] + w[1] + w[2]
+
+
+def test_quirk_q8_any_zero_channel_is_not_diffuse(dh):
+    """IsZero(Vec3) is true when ANY channel is < 1e-4 (Vec3.h:72-79): (.5, 0, .5) is not IsDiff()
+    though its Roulette weight is 1/3 (Obj.h:12-15) — prep_scene keeps both facts."""
+    hs = dh.scene(quirks_scene())
+    fl, w = hs.material(5)
+    assert not fl[0] and fl[1] and not fl[2]
+    assert w[0] == (0.5 + 0.0 + 0.5) / 3
+
+
+def test_prep_scene_rejects_bad_scenes(dh):
+    sc = make_scene("reference", textures=None)
+    d = sc.flatten()
+    d.objects[8].first_patch = 5        # 5 + 32 > 32 patches
+    with pytest.raises(ValueError, match="patch range"):
+        dh.scene(d)
+    d = sc.flatten()
+    d.objects[0].tex_id = 3
+    with pytest.raises(ValueError, match="tex_id"):
+        dh.scene(d)
+    d = sc.flatten()
+    d.objects[1].kind = 7
+    with pytest.raises(ValueError, match="kind"):
+        dh.scene(d)
+
+
+def test_newton_culls_never_drop_a_solve_that_records(dh, oracle):
+    """Soundness of the two Newton culls (13-DOP line test, sub-patch boxes): whenever the
+    reference's solve records a root on a patch, neither cull may fire for that (ray, patch)."""
+    sc = make_scene("reference", textures=None)
+    hs = dh.scene(sc)
+    prm = _params(newton_restarts=50)
+    n_p = hs.n_patches
+    n = 40000
+    patch = (np.arange(n) % n_p).astype(np.int32)
+    rays = rays_at_patches(patch, 12, sc)
+    k = n // 2
+    rays[:k] = rays_at_teapot(k, 13, sc)       # rays that graze or miss their patch
+    ref = oracle.bezier_patch_batch(sc, prm, rays, patch, None)
+    dop, sub = hs.newton_cull(rays, patch)
+    hit = ref[:, 0] < 1e19
+    assert hit.sum() > 15000
+    assert not (dop & hit).any()
+    assert not (sub & hit).any()
+    miss = ~hit
+    assert (dop | sub)[miss].mean() > 0.5      # and they do prove most of the empty solves empty
+
+
+def test_analytic_rejects_do_not_change_the_winner(dh, oracle):
+    """test_plane / test_sphere (Obj.h:65-85, 111-139) with the sign and FP32-estimate shortcuts:
+    the same nearest object and t as the reference's divide-everything loop."""
+    sc = make_scene("cornell", textures=None)
+    hs = dh.scene(sc)
+    rays = np.concatenate([rays_in_room(60000, 14), rays_in_room(200, 15)])
+    rays[-200:, 3:] = np.eye(3)[np.arange(200) % 3] * np.where(np.arange(200) % 2, 1.0, -1.0)[:, None]  # axis-parallel
+    ref = oracle.intersect_batch(sc, _params(), rays)
+    obj, t, inside = hs.analytic_nearest(rays)
+    np.testing.assert_array_equal(obj, ref["obj"])
+    np.testing.assert_array_equal(t, ref["t"])
+    np.testing.assert_array_equal(inside, ref["inside"])
+
+
+# ---- Scene::NearCollide through the warp-cooperative path --------------------------------------
+@pytest.mark.parametrize("name", ["cornell", "custom", "reference", "stress", "quirks"])
+def test_near_collide_golden_of_the_reference(dh, name):
+    """near_collide + shade_hit (scene.cuh) == Scene::NearCollide as computed by the reference's own
+    PlaneObj / SphereObj / Bezier3Obj classes (tests/golden/ref_*near_collide.npz)."""
+    fn = "ref_quirks_near_collide.npz" if name == "quirks" else "ref_near_collide.npz"
+    g = np.load(os.path.join(GOLDEN, fn))
+    hs = dh.scene(_scene(name))
+    rays = g[name + "_rays"]
+    got, _ = hs.near_collide(_params(), rays, np.arange(rays.shape[0], dtype=np.uint64), pass_id=1, node=2)
+    np.testing.assert_array_equal(got["obj"], g[name + "_obj"])
+    np.testing.assert_array_equal(got["inside"], g[name + "_inside"])
+    np.testing.assert_array_equal(got["t"], g[name + "_t"])
+    np.testing.assert_array_equal(got["pos"], g[name + "_pos"])
+    np.testing.assert_allclose(got["n"], g[name + "_n"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(got["color"], g[name + "_color"], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("name,n_room,n_tea", [("reference", 20000, 12000), ("stress", 4000, 2500), ("quirks", 4000, 4000)])
+def test_near_collide_fuzz_against_oracle(dh, oracle, name, n_room, n_tea):
+    """A fuzz some 6x the GPU test's size: queue flushes, ragged last warp, culls on and off."""
+    sc = _scene(name)
+    hs = dh.scene(sc)
+    prm = _params()
+    rays = np.concatenate([rays_in_room(n_room, 16), rays_at_teapot(n_tea, 17, sc)])[:-5]  # ragged warp
+    ids = np.arange(rays.shape[0], dtype=np.uint64) * 7 + 3
+    ref = oracle.intersect_batch(sc, prm, rays, ids, pass_id=2, node=5)
+    got, solves = hs.near_collide(prm, rays, ids, pass_id=2, node=5)
+    for k in ("obj", "patch", "inside", "t", "pos", "u", "v"):
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    np.testing.assert_allclose(got["n"], ref["n"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(got["color"], ref["color"], rtol=1e-12, atol=1e-15)
+    assert (ref["patch"] >= 0).sum() > 500 and solves > 5000 and hs.culled > 0
+    sub = slice(0, None, 9)
+    nocull, solves0 = hs.near_collide(prm, rays[sub], ids[sub], pass_id=2, node=5, cull=0)
+    for k in ("obj", "patch", "t", "u", "v"):
+        np.testing.assert_array_equal(nocull[k], ref[k][sub], err_msg=k)
+
+
+def test_near_collide_fast_newton_within_1e6(dh, oracle):
+    """The bench configuration (SPPM_NEWTON_FAST) picks the same object and patch wherever the
+    runner-up is not within 1e-6, and lands within 1e-6 on t and the hit position."""
+    sc = make_scene("reference", textures="synthetic")
+    hs = dh.scene(sc)
+    rays = np.concatenate([rays_in_room(6000, 18), rays_at_teapot(6000, 19, sc)])
+    ids = np.arange(rays.shape[0], dtype=np.uint64)
+    ref = oracle.intersect_batch(sc, _params(), rays, ids, pass_id=3, node=1)
+    got, _ = hs.near_collide(_params(newton_mode=abi.SPPM_NEWTON_FAST), rays, ids, pass_id=3, node=1)
+    same = (got["obj"] == ref["obj"]) & (got["patch"] == ref["patch"])
+    assert same.mean() > 0.9995
+    hit = same & (ref["obj"] >= 0)
+    assert (np.abs(got["t"][hit] - ref["t"][hit]) <= 1e-6 * np.abs(ref["t"][hit])).all()
+    assert np.abs(got["pos"][hit] - ref["pos"][hit]).max() <= 1e-6 * 250
