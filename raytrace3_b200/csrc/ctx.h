@@ -46,7 +46,7 @@ __host__ __device__ inline bool grid_keeps(const Grid& g, double x, double y, do
          z <= g.keep_hi[2];
 }
 __host__ __device__ inline int64_t grid_cell(const Grid& g, double x, double y, double z) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) || defined(SPPM_HOST_EMULATION)  // the latter: tests/device_host only
   int ix = __double2int_rd((x - g.org[0]) * g.inv_cell);
   int iy = __double2int_rd((y - g.org[1]) * g.inv_cell);
   int iz = __double2int_rd((z - g.org[2]) * g.inv_cell);

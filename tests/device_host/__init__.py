@@ -1,8 +1,8 @@
 """tests/device_host — TEST INFRASTRUCTURE: the product's device headers compiled for the CPU.
 
 `DeviceHost()` builds (g++, a few seconds) and loads tests/device_host/_build/libdevice_host.so:
-raytrace3_b200/csrc/{device_math.cuh, scene.cuh, scene_prep.h} through cuda_host_shim.h, with a
-warp emulated by 32 fibers.  It lets the `-m "not gpu"` suite hold the very source lines the
+raytrace3_b200/csrc/{device_math.cuh, scene.cuh, scene_prep.h, trace_kernels.cuh} through
+cuda_host_shim.h, with a warp emulated by 32 fibers and kernels launched as one-warp blocks.  It lets the `-m "not gpu"` suite hold the very source lines the
 sm_100a kernels are compiled from to the oracle.  Nothing in raytrace3_b200/ imports this."""
 from __future__ import annotations
 
@@ -20,12 +20,20 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _CSRC = os.path.join(_ROOT, "raytrace3_b200", "csrc")
 LIB_PATH = os.path.join(_HERE, "_build", "libdevice_host.so")
 SOURCES = [os.path.join(_HERE, f) for f in ("device_host.cpp", "cuda_host_shim.h")] + [
-    os.path.join(_CSRC, f) for f in ("scene.cuh", "device_math.cuh", "scene_prep.h")] + [
+    os.path.join(_CSRC, f) for f in ("scene.cuh", "device_math.cuh", "scene_prep.h", "trace_kernels.cuh", "ctx.h")] + [
     os.path.join(_ROOT, "include", "sppm_b200.h")]
 # -ffp-contract=off: no FMA contraction, the library's -fmad=false (explicit fma() calls stay fused)
-CXXFLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread"]
+# -fno-extern-tls-init: the kernels' block-scope `extern __shared__` (= thread_local here) array has no dynamic initialiser
+CXXFLAGS = ["-O2", "-std=c++17", "-ffp-contract=off", "-fno-extern-tls-init", "-fPIC", "-shared", "-pthread"]
 
 VP, I32, I64, U64, U32, DBL = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_uint32, C.c_double
+
+# ctx.h HpRaw / Deposit
+hpraw_dtype = np.dtype([("pos", "f8", 3), ("n", "f8", 3), ("wgt", "f8", 3), ("r2", "f8"), ("row", "i4"), ("col", "i4"),
+                        ("okey", "u8")])
+deposit_dtype = np.dtype([("x", "f8", 3), ("n", "f8", 3), ("flux", "f8", 3), ("meta", "u8")])
+COUNTERS = ("photons", "isect_queries", "patch_solves", "deposits", "deposits_kept", "cand_pairs", "acc_pairs", "overflow",
+            "patch_culled")
 
 
 def cuda_include_dir() -> str:
@@ -110,15 +118,56 @@ class HostScene:
         return dop.astype(bool), sub.astype(bool)
 
     def near_collide(self, prm, rays6, ids=None, pass_id=0, node=0, cull=1):
+        """Scene::NearCollide through intersect_kernel -> SppmHit records."""
+        return self.intersect_kernel(prm, rays6, ids, pass_id, node, cull)[0]
+
+    # ---- the kernels of trace_kernels.cuh, launched as one-warp blocks
+    def eye_pass_kernel(self, prm, cam, pass_id=0, row_begin=0, row_end=None):
+        """eye_pass_kernel -> hit points in the canonical (pixel, node) order + counters."""
+        cd = cam.desc() if hasattr(cam, "desc") else cam
+        row_end = cd.h if row_end is None else row_end
+        cap = cd.w * cd.h * 4 + 1024
+        out = np.zeros(cap, dtype=hpraw_dtype)
+        cnt = np.zeros(len(COUNTERS), dtype=np.uint64)
+        n = self.dh.lib.dh_eye_pass_kernel(self.h, C.byref(prm), C.byref(cd), pass_id, row_begin, row_end, cap, _p(out), _p(cnt))
+        assert n <= cap
+        out = out[:n]
+        return out[np.argsort(out["okey"], kind="stable")], dict(zip(COUNTERS, cnt.tolist()))
+
+    def photon_trace_kernel(self, prm, begin, count, pass_id, blocks=24):
+        """photon_trace_kernel (persistent warps), every diffuse deposit kept -> deposits sorted by
+        (photon id, bounce) + counters."""
+        cap = int(count * max(1, self.desc.n_lights) * (prm.max_dep + 2))
+        out = np.zeros(cap, dtype=deposit_dtype)
+        cnt = np.zeros(len(COUNTERS), dtype=np.uint64)
+        n = self.dh.lib.dh_photon_trace_kernel(self.h, C.byref(prm), begin, count, pass_id, blocks, cap, _p(out), _p(cnt))
+        assert n <= cap
+        out = out[:n]
+        photon = out["meta"] & np.uint64((1 << 56) - 1)
+        bounce = (out["meta"] >> np.uint64(56)).astype(np.int32)
+        order = np.lexsort((bounce, photon))
+        return dict(x=out["x"][order], n=out["n"][order], flux=out["flux"][order], photon=photon[order],
+                    bounce=bounce[order]), dict(zip(COUNTERS, cnt.tolist()))
+
+    def intersect_kernel(self, prm, rays6, ids=None, pass_id=0, node=0, cull=1):
         rays6 = _f64(rays6, (-1, 6))
         n = rays6.shape[0]
         out = np.zeros(n, dtype=hit_dtype)
         if ids is not None:
             ids = np.ascontiguousarray(ids, dtype=np.uint64)
-        solves = C.c_uint64()
-        self.dh.lib.dh_near_collide(self.h, prm.newton_mode, prm.newton_restarts, prm.newton_iters, cull, prm.seed, n,
-                                    _p(rays6), _p(ids), pass_id, node, _p(out), C.addressof(solves))
-        return out, solves.value
+        cnt = np.zeros(len(COUNTERS), dtype=np.uint64)
+        self.dh.lib.dh_intersect_kernel(self.h, C.byref(prm), cull, n, _p(rays6), _p(ids), pass_id, node, _p(out), _p(cnt))
+        return out, dict(zip(COUNTERS, cnt.tolist()))
+
+    def patch_batch_kernel(self, prm, rays6, patch, seeds=None, cull=0, blocks=16):
+        rays6 = _f64(rays6, (-1, 6))
+        n = rays6.shape[0]
+        patch = np.ascontiguousarray(patch, dtype=np.int32)
+        if seeds is not None:
+            seeds = _f64(seeds, (n, prm.newton_restarts, 2))
+        out = np.empty((n, 3))
+        self.dh.lib.dh_patch_batch_kernel(self.h, C.byref(prm), cull, n, _p(rays6), _p(patch), _p(seeds), blocks, _p(out))
+        return out
 
 
 class DeviceHost:
@@ -143,7 +192,14 @@ class DeviceHost:
         L.dh_scene_material.argtypes = [VP, C.c_int, VP, VP]
         L.dh_analytic_nearest.argtypes = [VP, I64, VP, VP, VP, VP]
         L.dh_newton_cull.argtypes = [VP, I64, VP, VP, VP, VP]
-        L.dh_near_collide.argtypes = [VP, C.c_int, C.c_int, C.c_int, C.c_int, U64, I64, VP, VP, U64, C.c_int, VP, VP]
+        L.dh_eye_pass_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.POINTER(abi.SppmCameraDesc), U64, C.c_int, C.c_int,
+                                         I64, VP, VP]
+        L.dh_eye_pass_kernel.restype = I64
+        L.dh_photon_trace_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), U64, U64, U64, C.c_int, I64, VP, VP]
+        L.dh_photon_trace_kernel.restype = I64
+        L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
+        L.dh_patch_batch_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, VP, C.c_int, VP]
+        assert L.dh_sizeof_hpraw() == hpraw_dtype.itemsize and L.dh_sizeof_deposit() == deposit_dtype.itemsize
 
     def draw2(self, seed, pass_id, ident, node, purpose, sub, patch):
         o = (C.c_double * 2)()

@@ -43,6 +43,7 @@ struct DhWarp {
   ucontext_t lane_ctx[32];
   bool done[32];
   int cur = 0;  // the lane that is running
+  unsigned block = 0, grid = 1;  // blockIdx.x / gridDim.x of the emulated one-warp block
   uint64_t slot[32];
   unsigned long long barriers = 0;
 };
@@ -54,8 +55,29 @@ struct DhThreadIdx {
 };
 static const DhThreadIdx dh_thread_idx{};
 static const DhDim dh_block_dim_32{32, 1, 1};
+struct DhBlockIdx {
+  struct X {
+    operator unsigned() const { return dh_warp ? dh_warp->block : 0u; }
+  } x;
+};
+struct DhGridDim {
+  struct X {
+    operator unsigned() const { return dh_warp ? dh_warp->grid : 1u; }
+  } x;
+};
+static const DhBlockIdx dh_block_idx{};
+static const DhGridDim dh_grid_dim{};
 #define threadIdx dh_thread_idx
 #define blockDim dh_block_dim_32
+#define blockIdx dh_block_idx
+#define gridDim dh_grid_dim
+// `extern __shared__ unsigned char smem[];` of a kernel = the emulating host thread's own array
+// (one block at a time per host thread), defined in device_host.cpp
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+#undef __shared__
+#define __shared__ thread_local
 
 inline void dh_barrier() {
   DhWarp* w = dh_warp;
@@ -118,6 +140,8 @@ inline float __fdividef(float a, float b) { return a / b; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
   return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int __double2int_rd(double d) { return (int)floor(d); }
 // stand-in for rcp.approx.ftz.f64 (scene.cuh rcp_newton): a reciprocal good to ~20 bits whose
 // low mantissa word is zero, as PTX specifies; the two Newton-Raphson steps that follow it are
 // the product's own

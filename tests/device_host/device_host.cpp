@@ -1,6 +1,7 @@
 // device_host.cpp — TEST INFRASTRUCTURE, not product: the device functions of
-// raytrace3_b200/csrc/{device_math.cuh, scene.cuh} and the host table builder scene_prep.h,
-// compiled for the CPU by g++ through cuda_host_shim.h and exported as batch functions for
+// raytrace3_b200/csrc/{device_math.cuh, scene.cuh}, the host table builder scene_prep.h and the
+// KERNELS of trace_kernels.cuh (eye pass, persistent photon tracer, NearCollide batch, Newton
+// batch), compiled for the CPU by g++ through cuda_host_shim.h and exported as batch functions for
 // tests/test_device_host_cpu.py.  The point is that the `-m "not gpu"` suite checks the SAME source
 // lines the sm_100a kernels are built from (plane / sphere / AABB tests with their division-free
 // rejects, patch evaluation in the three arithmetic modes, the Newton step and restart, the Newton
@@ -9,12 +10,20 @@
 //   g++ -O2 -ffp-contract=off (no FMA contraction, like the library's -fmad=false) -pthread
 #include "cuda_host_shim.h"
 
+#include <atomic>
 #include <functional>
 #include <string>
 #include <thread>
 #include <vector>
 
+// dynamic shared memory of the block a host thread is emulating (see __shared__ in the shim)
+namespace sppm {
+namespace {
+alignas(16) thread_local unsigned char smem[160 << 10];
+}
+}  // namespace sppm
 #include "../../raytrace3_b200/csrc/scene_prep.h"
+#include "../../raytrace3_b200/csrc/trace_kernels.cuh"
 
 thread_local DhWarp* dh_warp = nullptr;
 
@@ -29,6 +38,8 @@ struct DhScene {
   double lut255[256];
   unsigned long long culled = 0;
   SceneView sv;
+  std::vector<SppmLight> lights;
+  DevScene dev;  // what sppm_scene_upload hands the kernels (pointers into this object)
 };
 
 // the expansion tex_expand_kernel (abi.cu) does on the device
@@ -63,7 +74,7 @@ void fiber_entry() {
   }
   setcontext(&w->main_ctx);
 }
-unsigned long long run_warp(std::function<void(int)> f) {
+unsigned long long run_warp(std::function<void(int)> f, unsigned block = 0, unsigned grid = 1) {
   constexpr size_t STACK = 256 << 10;
   std::vector<char> stacks(32 * STACK);
   DhWarp warp;
@@ -78,12 +89,46 @@ unsigned long long run_warp(std::function<void(int)> f) {
   dh_warp = &warp;
   dh_fn = &f;
   warp.cur = 0;
+  warp.block = block;
+  warp.grid = grid;
   swapcontext(&warp.main_ctx, &warp.lane_ctx[0]);
   dh_warp = nullptr;
   dh_fn = nullptr;
   for (int l = 0; l < 32; l++)
     if (!warp.done[l]) abort();  // a divergent collective
   return warp.barriers;
+}
+
+// kernel<<<blocks, 32, trace_smem>>>(args): one-warp blocks, handed out to host threads in order
+template <class K, class A>
+void launch(K kernel, const A& args, long long blocks) {
+  const int T = (int)std::max<long long>(1, std::min<long long>(blocks, std::min(16u, std::max(1u, std::thread::hardware_concurrency()))));
+  std::atomic<long long> next{0};
+  std::vector<std::thread> th;
+  for (int w = 0; w < T; w++)
+    th.emplace_back([&] {
+      for (;;) {
+        const long long b = next.fetch_add(1);
+        if (b >= blocks) break;
+        run_warp([&](int) { kernel(args); }, (unsigned)b, (unsigned)blocks);
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
+// make_common (trace.cu) for an emulated launch; patches staged in shared memory like the library
+// does whenever they fit (trace_configure)
+TraceCommon common_of(DhScene* h, const SppmParams* prm, int cull, uint64_t pass, DevCounters* counters) {
+  TraceCommon t;
+  t.scene = h->dev;
+  t.ncfg = make_cfg(prm->newton_mode, prm->newton_restarts, prm->newton_iters, cull, prm->seed);
+  const size_t with = scene_smem_bytes(t.scene.n_obj, t.scene.n_patch, true) + sizeof(WarpScratch);
+  t.patches_in_smem = with <= 100 * 1024 ? 1 : 0;
+  t.max_dep = prm->max_dep;
+  t.fast_math = prm->math_mode == SPPM_MATH_FAST ? 1 : 0;
+  t.pass = pass;
+  t.counters = counters;
+  return t;
 }
 
 }  // namespace
@@ -191,6 +236,21 @@ void* dh_scene_create(const SppmSceneDesc* s, char* err, int errlen) {
   v.tex = h->tex.data();
   v.lut255 = h->lut255;
   v.n_obj = (int)h->ps.objs.size();
+  h->lights.assign(s->lights, s->lights + s->n_lights);
+  DevScene& d = h->dev;
+  d.n_obj = v.n_obj;
+  d.n_patch = s->n_patches;
+  d.n_light = s->n_lights;
+  d.n_tex = s->n_textures;
+  d.obj = v.obj;
+  d.patchP = v.patchP;
+  d.patchA = v.patchA;
+  d.patchBox = v.patchBox;
+  d.patchDop = v.patchDop;
+  d.patchSub = v.patchSub;
+  d.culled = &h->culled;
+  d.lights = h->lights.data();
+  d.tex = v.tex;
   return h;
 }
 void dh_scene_free(void* p) { delete (DhScene*)p; }
@@ -238,58 +298,87 @@ void dh_newton_cull(void* p, int64_t n, const double* rays6, const int32_t* patc
     sub_miss[i] = sub_boxes_miss(sv.patchSub + (size_t)patch[i] * 96, org, dir) ? 1 : 0;
   }
 }
-// Scene::NearCollide through the warp-cooperative near_collide + shade_hit, as intersect_kernel
-// (trace.cu) runs it: ray i on lane i % 32 of an emulated warp, draws addressed by (pass, id, node).
-void dh_near_collide(void* p, int newton_mode, int restarts, int iters, int cull, uint64_t seed, int64_t n,
-                     const double* rays6, const uint64_t* ids, uint64_t pass, int node, SppmHit* out,
-                     uint64_t* patch_solves) {
-  const SceneView& sv = ((const DhScene*)p)->sv;
-  const NewtonCfg cfg = make_cfg(newton_mode, restarts, iters, cull, seed);
-  const int64_t n_batch = (n + 31) / 32;
-  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_batch, std::min(16u, std::max(1u, std::thread::hardware_concurrency()))));
-  std::vector<unsigned long long> solves_of(T, 0);
-  std::vector<std::thread> th;
-  for (int w = 0; w < T; w++)
-    th.emplace_back([&, w] {
-      WarpScratch* ws = new WarpScratch();
-      run_warp([&](int lane) {
-        unsigned long long solves = 0;
-        for (int64_t b = w; b < n_batch; b += T) {  // one batch of 32 rays = one warp of intersect_kernel
-          const int64_t i = b * 32 + lane;
-          const bool active = i < n;
-          d3 org = mk(0, 0, 0), dir = mk(0, 0, 1);
-          uint64_t id = (uint64_t)i;
-          if (active) {
-            org = ld3(rays6 + 6 * i);
-            dir = ld3(rays6 + 6 * i + 3);
-            if (ids) id = ids[i];
-          }
-          const Hit h = near_collide(sv, ws, cfg, active, org, dir, pass, id, (uint32_t)node, SPPM_DOMAIN_TEST, solves);
-          if (active) {
-            SppmHit o;
-            o.t = h.obj >= 0 ? h.dist : SPPM_MAX_NUM;
-            o.u = h.u; o.v = h.v;
-            o.obj = h.obj; o.patch = h.patch; o.inside = h.inside ? 1 : 0; o.pad = 0;
-            for (int k = 0; k < 3; k++) o.pos[k] = o.n[k] = o.color[k] = 0;
-            if (h.obj >= 0) {
-              const Surface s = shade_hit(sv, h, org, dir);
-              o.pos[0] = s.pos.x; o.pos[1] = s.pos.y; o.pos[2] = s.pos.z;
-              o.n[0] = s.n.x; o.n[1] = s.n.y; o.n[2] = s.n.z;
-              o.color[0] = s.color.x; o.color[1] = s.color.y; o.color[2] = s.color.z;
-            }
-            out[i] = o;
-          }
-          __syncwarp();  // near_collide's scratch is reused by the next batch of rays
-        }
-        if (lane == 0) solves_of[w] = solves;
-      });
-      delete ws;
-    });
-  for (auto& t : th) t.join();
-  if (patch_solves) {
-    *patch_solves = 0;
-    for (unsigned long long v : solves_of) *patch_solves += v;
-  }
+// ---- the kernels of trace_kernels.cuh, launched with one-warp blocks -----------------------------
+// counters9 = DevCounters {photons, isect_queries, patch_solves, deposits, deposits_kept, cand_pairs,
+// acc_pairs, overflow, patch_culled}
+int64_t dh_eye_pass_kernel(void* p, const SppmParams* prm, const SppmCameraDesc* cam, uint64_t pass, int row_begin,
+                           int row_end, int64_t cap, HpRaw* out, uint64_t* counters9) {
+  DhScene* h = (DhScene*)p;
+  DevCounters cnt;
+  memset(&cnt, 0, sizeof(cnt));
+  unsigned long long n_hp = 0;
+  EyeArgs a;
+  a.c = common_of(h, prm, 1, pass, &cnt);
+  a.cam = *cam;
+  a.out = out;
+  a.cap = (unsigned long long)cap;
+  a.hp_count = &n_hp;
+  a.init_r2 = prm->init_r2;
+  a.pix_begin = (long long)row_begin * cam->w;
+  a.pix_end = (long long)row_end * cam->w;
+  const long long npix = a.pix_end - a.pix_begin;
+  if (npix > 0) launch(eye_pass_kernel, a, (npix + 31) / 32);
+  if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
+  return (int64_t)n_hp;
 }
+// photon_trace_kernel without a hit-point map (keep_all: every diffuse deposit is recorded)
+int64_t dh_photon_trace_kernel(void* p, const SppmParams* prm, uint64_t begin, uint64_t count, uint64_t pass, int blocks,
+                               int64_t cap, Deposit* out, uint64_t* counters9) {
+  DhScene* h = (DhScene*)p;
+  DevCounters cnt;
+  memset(&cnt, 0, sizeof(cnt));
+  std::vector<uint32_t> key((size_t)cap), rank((size_t)cap);
+  unsigned int slot_count[2] = {0, 0};
+  unsigned long long n_dep = 0, cursor = 0;
+  PhotonArgs a;
+  a.c = common_of(h, prm, 1, pass, &cnt);
+  memset(&a.grid, 0, sizeof(a.grid));
+  a.cell_slot = nullptr;
+  a.n_slots = 0;
+  a.keep_all = 1;
+  a.dep = out;
+  a.dep_key = key.data();
+  a.dep_rank = rank.data();
+  a.slot_count = slot_count;
+  a.dep_cap = (unsigned long long)cap;
+  a.dep_count = &n_dep;
+  a.cursor = &cursor;
+  a.begin = begin;
+  a.count = count;
+  launch(photon_trace_kernel, a, blocks);
+  if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
+  return (int64_t)n_dep;
+}
+void dh_intersect_kernel(void* p, const SppmParams* prm, int cull, int64_t n, const double* rays6, const uint64_t* ids,
+                         uint64_t pass, int node, SppmHit* out, uint64_t* counters9) {
+  DhScene* h = (DhScene*)p;
+  DevCounters cnt;
+  memset(&cnt, 0, sizeof(cnt));
+  IsectArgs a;
+  a.c = common_of(h, prm, cull, pass, &cnt);
+  a.rays6 = rays6;
+  a.ids = ids;
+  a.n = n;
+  a.node = node;
+  a.out = out;
+  if (n > 0) launch(intersect_kernel, a, (n + 31) / 32);
+  if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
+}
+void dh_patch_batch_kernel(void* p, const SppmParams* prm, int cull, int64_t n, const double* rays6, const int32_t* patch,
+                           const double* seeds, int blocks, double* tuv) {
+  DhScene* h = (DhScene*)p;
+  DevCounters cnt;
+  memset(&cnt, 0, sizeof(cnt));
+  PatchArgs a;
+  a.c = common_of(h, prm, cull, 0, &cnt);
+  a.rays6 = rays6;
+  a.patch = patch;
+  a.n = n;
+  a.seeds = seeds;
+  a.tuv = tuv;
+  if (n > 0) launch(patch_batch_kernel, a, blocks);
+}
+int dh_sizeof_hpraw() { return (int)sizeof(HpRaw); }
+int dh_sizeof_deposit() { return (int)sizeof(Deposit); }
 
 }  // extern "C"

@@ -275,16 +275,16 @@ def test_analytic_rejects_do_not_change_the_winner(dh, oracle):
     np.testing.assert_array_equal(inside, ref["inside"])
 
 
-# ---- Scene::NearCollide through the warp-cooperative path --------------------------------------
+# ---- Scene::NearCollide: intersect_kernel (near_collide + shade_hit), one-warp blocks on fibers ----
 @pytest.mark.parametrize("name", ["cornell", "custom", "reference", "stress", "quirks"])
-def test_near_collide_golden_of_the_reference(dh, name):
+def test_intersect_kernel_golden_of_the_reference(dh, name):
     """near_collide + shade_hit (scene.cuh) == Scene::NearCollide as computed by the reference's own
     PlaneObj / SphereObj / Bezier3Obj classes (tests/golden/ref_*near_collide.npz)."""
     fn = "ref_quirks_near_collide.npz" if name == "quirks" else "ref_near_collide.npz"
     g = np.load(os.path.join(GOLDEN, fn))
     hs = dh.scene(_scene(name))
     rays = g[name + "_rays"]
-    got, _ = hs.near_collide(_params(), rays, np.arange(rays.shape[0], dtype=np.uint64), pass_id=1, node=2)
+    got = hs.near_collide(_params(), rays, np.arange(rays.shape[0], dtype=np.uint64), pass_id=1, node=2)
     np.testing.assert_array_equal(got["obj"], g[name + "_obj"])
     np.testing.assert_array_equal(got["inside"], g[name + "_inside"])
     np.testing.assert_array_equal(got["t"], g[name + "_t"])
@@ -294,7 +294,7 @@ def test_near_collide_golden_of_the_reference(dh, name):
 
 
 @pytest.mark.parametrize("name,n_room,n_tea", [("reference", 20000, 12000), ("stress", 4000, 2500), ("quirks", 4000, 4000)])
-def test_near_collide_fuzz_against_oracle(dh, oracle, name, n_room, n_tea):
+def test_intersect_kernel_fuzz_against_oracle(dh, oracle, name, n_room, n_tea):
     """A fuzz some 6x the GPU test's size: queue flushes, ragged last warp, culls on and off."""
     sc = _scene(name)
     hs = dh.scene(sc)
@@ -302,19 +302,19 @@ def test_near_collide_fuzz_against_oracle(dh, oracle, name, n_room, n_tea):
     rays = np.concatenate([rays_in_room(n_room, 16), rays_at_teapot(n_tea, 17, sc)])[:-5]  # ragged warp
     ids = np.arange(rays.shape[0], dtype=np.uint64) * 7 + 3
     ref = oracle.intersect_batch(sc, prm, rays, ids, pass_id=2, node=5)
-    got, solves = hs.near_collide(prm, rays, ids, pass_id=2, node=5)
+    got = hs.near_collide(prm, rays, ids, pass_id=2, node=5)
     for k in ("obj", "patch", "inside", "t", "pos", "u", "v"):
         np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
     np.testing.assert_allclose(got["n"], ref["n"], rtol=0, atol=1e-15)
     np.testing.assert_allclose(got["color"], ref["color"], rtol=1e-12, atol=1e-15)
-    assert (ref["patch"] >= 0).sum() > 500 and solves > 5000 and hs.culled > 0
+    assert (ref["patch"] >= 0).sum() > 500 and hs.culled > 1000
     sub = slice(0, None, 9)
-    nocull, solves0 = hs.near_collide(prm, rays[sub], ids[sub], pass_id=2, node=5, cull=0)
+    nocull = hs.near_collide(prm, rays[sub], ids[sub], pass_id=2, node=5, cull=0)
     for k in ("obj", "patch", "t", "u", "v"):
         np.testing.assert_array_equal(nocull[k], ref[k][sub], err_msg=k)
 
 
-def test_near_collide_fast_newton_within_1e6(dh, oracle):
+def test_intersect_kernel_fast_newton_within_1e6(dh, oracle):
     """The bench configuration (SPPM_NEWTON_FAST) picks the same object and patch wherever the
     runner-up is not within 1e-6, and lands within 1e-6 on t and the hit position."""
     sc = make_scene("reference", textures="synthetic")
@@ -322,9 +322,141 @@ def test_near_collide_fast_newton_within_1e6(dh, oracle):
     rays = np.concatenate([rays_in_room(6000, 18), rays_at_teapot(6000, 19, sc)])
     ids = np.arange(rays.shape[0], dtype=np.uint64)
     ref = oracle.intersect_batch(sc, _params(), rays, ids, pass_id=3, node=1)
-    got, _ = hs.near_collide(_params(newton_mode=abi.SPPM_NEWTON_FAST), rays, ids, pass_id=3, node=1)
+    got = hs.near_collide(_params(newton_mode=abi.SPPM_NEWTON_FAST), rays, ids, pass_id=3, node=1)
     same = (got["obj"] == ref["obj"]) & (got["patch"] == ref["patch"])
     assert same.mean() > 0.9995
     hit = same & (ref["obj"] >= 0)
     assert (np.abs(got["t"][hit] - ref["t"][hit]) <= 1e-6 * np.abs(ref["t"][hit])).all()
     assert np.abs(got["pos"][hit] - ref["pos"][hit]).max() <= 1e-6 * 250
+
+
+# ---- the KERNELS of trace_kernels.cuh, launched as one-warp blocks -------------------------------
+# Same libm on both sides here, so what the GPU tests can only hold to 99.8 % (acos / sin / cos
+# differ by ulps between CUDA and libm) is held bit for bit: every hit point, every deposit.
+def test_patch_batch_kernel(dh, oracle):
+    """patch_batch_kernel (the M2 microbenchmark's kernel): the reference's golden (t, u, v), and the
+    oracle with injected and with counter-RNG seeds; grid-stride loop with fewer warps than work."""
+    sc = make_scene("reference", textures=None)
+    hs = dh.scene(sc)
+    g = np.load(os.path.join(GOLDEN, "ref_newton.npz"))
+    prm = _params()
+    np.testing.assert_array_equal(hs.patch_batch_kernel(prm, g["rays"], g["patch"], g["seeds"], blocks=3), g["tuv"])
+    n = 1500
+    rng = np.random.RandomState(21)
+    patch = rng.randint(0, 32, size=n).astype(np.int32)
+    rays = rays_at_patches(patch, 22, sc)
+    rays[:300] = rays_at_teapot(300, 23, sc)
+    ref = oracle.bezier_patch_batch(sc, prm, rays, patch, None)
+    np.testing.assert_array_equal(hs.patch_batch_kernel(prm, rays, patch, None, blocks=7), ref)
+    np.testing.assert_array_equal(hs.patch_batch_kernel(prm, rays, patch, None, cull=1, blocks=16), ref)
+    assert hs.culled > 100 and (ref[:, 0] < 1e19).sum() > 700
+
+
+@pytest.mark.parametrize("name,w,h", [("reference", 320, 240), ("custom", 160, 120), ("quirks", 160, 120), ("stress", 128, 96)])
+def test_eye_pass_kernel_against_oracle(dh, oracle, name, w, h):
+    """eye_pass_kernel == GetHitPoint / ViewTrace (Raytracer.h:102-116, 296-357) of the oracle for every
+    pixel — the reference scene at BASELINE config 1's full 320x240 — incl. branching materials
+    (deferred refraction subtrees) and the row-sharded launch of the multi-GPU eye pass."""
+    from raytrace3_b200.scene import reference_camera
+    sc = _scene(name)
+    hs = dh.scene(sc)
+    prm = _params()
+    cam = reference_camera(w, h)
+    ref = oracle.eye_pass(sc, prm, cam, pass_id=3)
+    got, cnt = hs.eye_pass_kernel(prm, cam, pass_id=3)
+    order = np.lexsort((ref["node"], ref["pix"][:, 0] * w + ref["pix"][:, 1]))
+    assert got.shape[0] == order.shape[0]
+    np.testing.assert_array_equal(got["row"], ref["pix"][order, 0])
+    np.testing.assert_array_equal(got["col"], ref["pix"][order, 1])
+    np.testing.assert_array_equal(got["okey"] & np.uint64((1 << 20) - 1), ref["node"][order])
+    for k in ("pos", "n", "wgt", "r2"):
+        np.testing.assert_array_equal(got[k], ref[k][order], err_msg=k)
+    assert cnt["isect_queries"] >= w * h
+    if name == "custom":
+        assert got.shape[0] > w * h * 1.02      # branching
+    cut = h // 3
+    a, _ = hs.eye_pass_kernel(prm, cam, pass_id=3, row_begin=0, row_end=cut)
+    b, _ = hs.eye_pass_kernel(prm, cam, pass_id=3, row_begin=cut, row_end=h)
+    assert np.array_equal(np.concatenate([a, b]), got)
+
+
+@pytest.mark.parametrize("name", ["custom", "quirks", "reference"])
+def test_eye_pass_kernel_golden_of_the_reference(dh, name):
+    """The hit points the reference's OWN recursion produced (tests/golden/ref_*view_trace.npz)."""
+    from raytrace3_b200.scene import reference_camera
+    fn = "ref_quirks_view_trace.npz" if name == "quirks" else "ref_view_trace.npz"
+    g = np.load(os.path.join(GOLDEN, fn))
+    w, h = (int(v) for v in g["film"])
+    got, _ = dh.scene(_scene(name)).eye_pass_kernel(_params(), reference_camera(w, h), pass_id=0)
+    gp = got["row"].astype(np.int64) * w + got["col"]
+    off = 0
+    for (i, j), cnt in zip(g[name + "_pixels"], g[name + "_counts"]):
+        sel = np.nonzero(gp == int(i) * w + int(j))[0]
+        assert sel.size == cnt, (i, j)
+        want = {f: g[f"{name}_{f}"][off:off + cnt] for f in ("pos", "n", "wgt", "r2")}
+        off += cnt
+        a = sel[np.lexsort(got["pos"][sel].T[::-1])]      # recursion order vs (pixel, node) order
+        b = np.lexsort(want["pos"].T[::-1])
+        for f in want:
+            np.testing.assert_array_equal(got[f][a], want[f][b], err_msg=f)
+    assert off == g[name + "_pos"].shape[0]
+
+
+@pytest.mark.parametrize("name,count", [("reference", 100000), ("custom", 20000), ("quirks", 20000), ("stress", 20000)])
+def test_photon_trace_kernel_against_oracle(dh, oracle, name, count):
+    """photon_trace_kernel == Light::emit + PhotonTrace (Light.h:8-13, Raytracer.h:117-209) of the
+    oracle: the same deposit list (x, N, incoming flux per (photon, bounce)) and the same counters,
+    bit for bit — the reference scene with BASELINE config 1's 100 k photons."""
+    sc = _scene(name)
+    hs = dh.scene(sc)
+    prm = _params()
+    ref = oracle.photon_pass(sc, prm, 100, count, 9, keep_deposits=True)
+    dep, cnt = hs.photon_trace_kernel(prm, 100, count, 9)
+    rd, rc = ref["dep"], ref["counters"]
+    assert cnt["photons"] == rc["photons"] == count * len(sc.plvec)
+    assert cnt["isect_queries"] == rc["queries"] and cnt["deposits"] == rc["deposits"] == cnt["deposits_kept"]
+    assert cnt["patch_solves"] == rc["solves"]
+    order = np.lexsort((rd["bounce"], rd["photon"]))
+    assert dep["x"].shape[0] == order.shape[0] > 2 * count
+    for k in ("photon", "bounce", "x", "n", "flux"):
+        np.testing.assert_array_equal(dep[k], rd[k][order], err_msg=k)
+
+
+def test_photon_trace_kernel_is_launch_invariant(dh):
+    """Persistent warps pick photons from a global cursor: the deposits do not depend on the grid."""
+    hs = dh.scene(_scene("reference"))
+    prm = _params()
+    one, _ = hs.photon_trace_kernel(prm, 7, 3001, 4, blocks=1)
+    many, _ = hs.photon_trace_kernel(prm, 7, 3001, 4, blocks=40)
+    for k in one:
+        np.testing.assert_array_equal(one[k], many[k], err_msg=k)
+    # photon-range invariance: [7, 3008) = [7, 1000) + [1000, 3008), ids are global
+    a, _ = hs.photon_trace_kernel(prm, 7, 993, 4)
+    b, _ = hs.photon_trace_kernel(prm, 1000, 2008, 4)
+    for k in one:
+        np.testing.assert_array_equal(np.concatenate([a[k], b[k]]), one[k], err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["cornell", "custom", "quirks", "reference"])
+def test_photon_trace_kernel_golden_of_the_reference(dh, oracle, name):
+    """Level 2 against the reference itself: the kernel's deposits of 300 photons, gathered over the
+    golden hit points by the exhaustive search, give the newN / tao the reference's own PhotonTrace +
+    radiusSearch accumulated (tests/golden/ref_*photon.npz) — bit for bit, per photon and in total."""
+    fn = "ref_quirks_photon.npz" if name == "quirks" else "ref_photon.npz"
+    g = np.load(os.path.join(GOLDEN, fn))
+    hp = {k: g[f"{name}_hp_{k}"] for k in ("pos", "n", "wgt", "r2", "pix")}
+    prm = _params()
+    count = g[f"{name}_tot_newN"].shape[0]
+    dep, _ = dh.scene(_scene(name)).photon_trace_kernel(prm, 0, count, 5)
+    n = hp["pos"].shape[0]
+    acc_n, acc_t = np.zeros(n, np.int64), np.zeros((n, 3))
+    search_r2 = float(hp["r2"].max())
+    for j in range(count):
+        sel = (dep["photon"] & np.uint64((1 << 40) - 1)) == j
+        d = {k: dep[k][sel] for k in ("x", "n", "flux")}
+        newN, tao, _, _ = oracle.gather_brute(hp, d, search_r2)
+        assert int(newN.sum()) == g[f"{name}_tot_newN"][j], j
+        assert np.array_equal(tao.sum(axis=0), g[f"{name}_tot_tao"][j]), j
+        acc_n += newN
+        acc_t += tao
+    assert np.array_equal(acc_n, g[f"{name}_acc_newN"]) and np.array_equal(acc_t, g[f"{name}_acc_tao"])
