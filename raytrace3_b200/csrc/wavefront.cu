@@ -17,414 +17,10 @@
 // on a finished photon, the register-heavy Newton solver does not limit the occupancy of the
 // light per-photon code, and the Newton tasks of the whole GPU are packed densely.
 // Results are identical: the RNG is addressed by (pass, photon id, bounce, ...).
-#include <cooperative_groups.h>
-
-#include <algorithm>
-#include <cstdlib>
-
 #include "ctx.h"
-
-#ifndef SPPM_STEP_MINBLOCKS
-#define SPPM_STEP_MINBLOCKS 6    // CTAs/SM the step kernel's register budget is sized for (80 regs; measured best)
-#endif
-#ifndef SPPM_NEWTON_MINBLOCKS
-#define SPPM_NEWTON_MINBLOCKS 2  // same for the Newton item kernel
-#endif
+#include "wavefront_kernels.cuh"
 
 namespace sppm {
-
-namespace {
-
-constexpr int STEP_THREADS = 128;
-constexpr unsigned long long ID_MASK = 0x00ffffffffffffffull;
-
-struct Queue {  // SoA photon state, one entry per live photon
-  double *ox, *oy, *oz, *dx, *dy, *dz, *fx, *fy, *fz, *hdist;
-  unsigned long long* idd;  // photon id | dep << 56
-  int* hobj;                // analytic best of the pending query: obj | inside << 16, -1 = none
-  unsigned *item_begin, *item_cnt;
-};
-struct Items {
-  unsigned* slot;   // photon slot in the queue the items were generated for
-  unsigned* patch;  // global patch | object << 16
-  double *t, *u, *v;
-};
-
-struct StepArgs {
-  DevScene scene;
-  int patches_in_smem, max_dep, bounce, do_intersect, fast_math;
-  uint64_t seed, pass;
-  DevCounters* counters;
-  Queue qin, qout;
-  Items it_in, it_out;
-  const unsigned* n_in_ptr;  // [4]: photons queued in the four regions (see photon_step_kernel)
-  unsigned n_in_host;
-  unsigned* n_out;           // [4]
-  unsigned q_cap;
-  unsigned* n_items_out;
-  unsigned item_cap;
-  unsigned* overflow;
-  uint64_t begin, count;  // photon range per light of this batch
-  Grid grid;
-  const int32_t* cell_slot;
-  int32_t n_slots;
-  int keep_all;
-  Deposit* dep;
-  uint32_t* dep_key;
-  uint32_t* dep_rank;
-  unsigned int* slot_count;
-  unsigned long long dep_cap;
-  unsigned long long* dep_count;
-};
-
-__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
-  return v;
-}
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
-
-__global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step_kernel(const StepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem, false);
-  const int lane = threadIdx.x & 31;
-  // The queue arrays hold 2 x q_cap entries and are filled from four ends, by what the pending hit
-  // will make the next step do, so that warps shade uniform work:
-  //   region 0 [0 ->)             a plane with a diffuse part (most photons: one coherent path)
-  //   region 1 [<- q_cap)         a purely specular object (mirror / glass: short reflect / refract paths)
-  //   region 2 [q_cap ->)         a sphere with a diffuse part
-  //   region 3 [<- 2 q_cap)       Bezier solves pending (the item merge + patch evaluation path)
-  // Photons that hit nothing are dropped when they are found.  The virtual index space of a step is
-  // [region 0 | region 1 | region 2 | region 3], the first three padded to whole warps.
-  unsigned nreg[4];
-  nreg[0] = a.bounce == 0 ? a.n_in_host : a.n_in_ptr[0];
-#pragma unroll
-  for (int r = 1; r < 4; r++) nreg[r] = a.bounce == 0 ? 0u : a.n_in_ptr[r];
-  const unsigned c0 = ((nreg[0] + 31) >> 5) * 32, c1 = c0 + ((nreg[1] + 31) >> 5) * 32, c2 = c1 + ((nreg[2] + 31) >> 5) * 32;
-  const unsigned n_in = c2 + nreg[3];
-  const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-  unsigned queries = 0, solves = 0, photons = 0, deposits = 0, kept = 0;  // per thread, < 2^32
-
-  for (unsigned base = warp_global * 32; base < n_in; base += n_warps * 32) {
-    const unsigned vi = base + lane;
-    const int reg = base < c0 ? 0 : (base < c1 ? 1 : (base < c2 ? 2 : 3));  // warp-uniform
-    const unsigned k = vi - (reg == 0 ? 0u : (reg == 1 ? c0 : (reg == 2 ? c1 : c2)));  // index within the region
-    const bool active = k < nreg[reg];
-    const unsigned i = reg == 0 ? k : (reg == 1 ? a.q_cap - 1 - k : (reg == 2 ? a.q_cap + k : 2 * a.q_cap - 1 - k));
-    bool alive = false;
-    unsigned rank_val = 0;
-    unsigned long long rank_at = ~0ull;  // deposit whose rank-in-slot is still in flight
-    d3 org = mk(0, 0, 0), dir = mk(0, 0, 1), flux = mk(0, 0, 0);
-    uint64_t id = 0;
-    int dep = 0;
-    if (active) {
-      if (a.bounce == 0) {  // Light::emit (Light.h:8-13)
-        const unsigned pl = (unsigned)(i / a.count);
-        id = ((uint64_t)pl << 40) | (a.begin + i % a.count);
-        const SppmLight& L = a.scene.lights[pl];
-        flux = ld3(L.color) * SPPM_PI * 4;
-        dir = unit_rand_vec(a.seed, a.pass, id, P_EMIT);
-        org = ld3(L.pos);
-        alive = true;
-        photons++;
-      } else {
-        // ---- finish the pending query: nearest of the analytic best and the Bezier solves
-        const unsigned long long idd = a.qin.idd[i];
-        id = idd & ID_MASK;
-        dep = (int)(idd >> 56);
-        org = mk(a.qin.ox[i], a.qin.oy[i], a.qin.oz[i]);
-        dir = mk(a.qin.dx[i], a.qin.dy[i], a.qin.dz[i]);
-        Hit h;
-        h.dist = a.qin.hdist[i];
-        const int ho = a.qin.hobj[i];
-        h.obj = ho < 0 ? -1 : (ho & 0xffff);
-        h.inside = ho >= 0 && ((ho >> 16) & 1);
-        h.patch = -1;
-        h.u = h.v = 0;
-        const unsigned ic = a.qin.item_cnt[i];
-        if (ic) {  // Bezier3Obj::GetIntersect filter, per object in patch order (Bezier.h:246-261)
-          const unsigned ib = a.qin.item_begin[i];
-          int cur = -1, index = -1;
-          double pt = SPPM_MAX_NUM, pu = SPPM_MAX_NUM, pv = SPPM_MAX_NUM;
-          for (unsigned k = 0; k <= ic; k++) {
-            const unsigned pk = k < ic ? a.it_in.patch[ib + k] : 0xffffffffu;
-            const int ob = k < ic ? (int)(pk >> 16) : -2;
-            if (ob != cur) {
-              if (cur >= 0 && index != -1 && (pt < h.dist || (pt == h.dist && cur < h.obj))) {
-                h.dist = pt; h.obj = cur; h.patch = index; h.u = pu; h.v = pv; h.inside = false;
-              }
-              cur = ob;
-              index = -1;
-              pt = pu = pv = SPPM_MAX_NUM;
-            }
-            if (k < ic) {
-              const double qt = a.it_in.t[ib + k], qu = a.it_in.u[ib + k], qv = a.it_in.v[ib + k];
-              if (!(qt < SPPM_M_EPS || qt > pt || qu < -SPPM_M_EPS || qu > 1 + SPPM_M_EPS || qv < -SPPM_M_EPS ||
-                    qv > 1 + SPPM_M_EPS)) {
-                if (qt < pt) {
-                  pt = qt; pu = qu; pv = qv;
-                  index = (int)(pk & 0xffffu);
-                }
-              }
-            }
-          }
-        }
-        if (!(h.obj < 0 || dep > a.max_dep)) {  // Raytracer.h:127-133
-          flux = mk(a.qin.fx[i], a.qin.fy[i], a.qin.fz[i]);
-          const int node = dep;
-          dep++;
-          const DevObject& ob = sv.obj[h.obj];
-          const Surface s = shade_hit(sv, h, org, dir);
-          // Raytracer.h:136-160: the gather input (x, N, incoming flux).  The slot lookup is issued
-          // before the Roulette / direction arithmetic and consumed after it, and the rank atomic's
-          // result is stored at the end of the iteration, so neither latency is waited for here.
-          int32_t slot = -1;
-          if (ob.isDiff && a.cell_slot && grid_keeps(a.grid, s.pos.x, s.pos.y, s.pos.z))
-            slot = __ldg(a.cell_slot + grid_cell(a.grid, s.pos.x, s.pos.y, s.pos.z));
-          // Obj::Roulette (Obj.h:30-45) and the single continuation (Raytracer.h:162-190)
-          double ur, U1;
-          draw2(a.seed, a.pass, id, (uint32_t)node, P_BOUNCE, 0, 0, ur, U1);
-          const double r = randu(ur, 0., ob.allr);
-          d3 ndir;
-          if (ob.diffr > r) {
-            double U2, unused;
-            draw2(a.seed, a.pass, id, (uint32_t)node, P_BOUNCE, 1, 0, U2, unused);
-            ndir = unit_rand_refl(s.n, U1, U2, a.fast_math != 0);
-          } else if (ob.diffr + ob.reflr > r) {
-            ndir = get_unit(get_refl(dir, s.n));
-          } else {
-            const double refrn = h.inside ? ob.refrn : 1 / ob.refrn;
-            ndir = normalize3(refracted(dir, h.inside ? -s.n : s.n, refrn));
-          }
-          if (ob.isDiff) {  // Raytracer.h:136-160: the gather input (x, N, incoming flux)
-            deposits++;
-            if (slot >= 0 || a.keep_all) {
-              // append with one atomic per group of lanes that are here together
-              const cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
-              unsigned long long dbase = 0;
-              if (g.thread_rank() == 0) dbase = atomicAdd(a.dep_count, (unsigned long long)g.size());
-              const unsigned long long ds = g.shfl(dbase, 0) + g.thread_rank();
-              if (ds < a.dep_cap) {
-                Deposit rec;
-                rec.x[0] = s.pos.x; rec.x[1] = s.pos.y; rec.x[2] = s.pos.z;
-                rec.n[0] = s.n.x; rec.n[1] = s.n.y; rec.n[2] = s.n.z;
-                rec.flux[0] = flux.x; rec.flux[1] = flux.y; rec.flux[2] = flux.z;
-                rec.meta = id | ((uint64_t)node << 56);
-                a.dep[ds] = rec;
-                const uint32_t key = slot >= 0 ? (uint32_t)slot : (uint32_t)a.n_slots;
-                a.dep_key[ds] = key;
-                rank_val = atomicAdd(a.slot_count + key, 1u);  // counting sort: rank within the slot
-                rank_at = ds;
-                kept++;
-              }
-            }
-          }
-          flux = mul3(s.color, flux);
-          org = s.pos;
-          dir = ndir;
-          alive = true;
-        }
-      }
-    }
-    // ---- next query: analytic objects per lane, Bezier object boxes noted in a bit mask
-    Hit best;
-    best.dist = SPPM_MAX_NUM;
-    best.obj = -1;
-    best.inside = false;
-    unsigned long long boxobj = 0;
-    if (alive) {
-      queries++;
-      if (a.do_intersect) {
-        for (int o = 0; o < sv.n_obj; o++) {
-          const DevObject& ob = sv.obj[o];
-          if (ob.kind == SPPM_OBJ_PLANE) test_plane(ob, o, org, dir, best);
-          else if (ob.kind == SPPM_OBJ_SPHERE) test_sphere(ob, o, org, dir, best);
-          else if (aabb_intersect(ob.box, org, dir)) boxobj |= 1ull << o;  // Bezier.h:244
-        }
-      } else {
-        alive = false;  // the last query's result is never used (depth limit, Raytracer.h:129-132)
-      }
-    }
-    if (rank_at != ~0ull) a.dep_rank[rank_at] = rank_val;  // the atomic issued before the Roulette has landed by now
-    // ---- compaction of the survivors into the output queue (front: plane hits, back: the rest)
-    if (alive && best.obj < 0 && boxobj == 0) alive = false;  // hit nothing (Raytracer.h:127): the photon is gone
-    int oreg = 3;  // Bezier solves pending
-    if (alive && boxobj == 0) {
-      const DevObject& bo = sv.obj[best.obj];
-      oreg = !bo.isDiff ? 1 : (bo.kind == SPPM_OBJ_PLANE ? 0 : 2);
-    }
-    const unsigned am = __ballot_sync(FULL, alive);
-    if (!am) continue;
-    unsigned rm[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) rm[r] = __ballot_sync(FULL, alive && oreg == r);
-    unsigned rbase = 0;
-    if (lane < 4 && rm[lane]) rbase = atomicAdd(a.n_out + lane, (unsigned)__popc(rm[lane]));  // one atomic per non-empty region
-    rbase = __shfl_sync(FULL, rbase, oreg);
-    const unsigned lt = (1u << lane) - 1;
-    const unsigned kk = rbase + __popc(rm[oreg] & lt);
-    const unsigned my_slot = oreg == 0 ? kk : (oreg == 1 ? a.q_cap - 1 - kk : (oreg == 2 ? a.q_cap + kk : 2 * a.q_cap - 1 - kk));
-    // ---- cooperative Bezier culling: per in-box ray, 32 lanes test 32 patch boxes (Bezier.h:178)
-    unsigned my_begin = 0, my_cnt = 0;
-    unsigned bm = __ballot_sync(FULL, alive && boxobj != 0);
-    while (bm) {
-      const int src = __ffs(bm) - 1;
-      bm &= bm - 1;
-      const d3 so = mk(shfl_d(org.x, src), shfl_d(org.y, src), shfl_d(org.z, src));
-      const d3 sd = mk(shfl_d(dir.x, src), shfl_d(dir.y, src), shfl_d(dir.z, src));
-      const unsigned long long omask = __shfl_sync(FULL, boxobj, src);
-      const unsigned sslot = __shfl_sync(FULL, my_slot, src);
-      unsigned total = 0, ibase = 0;
-      for (int pass2 = 0; pass2 < 2; pass2++) {  // count, reserve one contiguous range, then write
-        unsigned off = 0;
-        unsigned long long om = omask;
-        while (om) {
-          const int o = __ffsll((long long)om) - 1;
-          om &= om - 1;
-          const DevObject& ob = sv.obj[o];
-          for (int ch = 0; ch < ob.n_patch; ch += 32) {
-            const int p = ch + lane;
-            const bool hitp = p < ob.n_patch && aabb_intersect(sv.patchBox + (size_t)(ob.first_patch + p) * 6, so, sd);
-            const unsigned b = __ballot_sync(FULL, hitp);
-            if (pass2 && hitp) {
-              const unsigned k = ibase + off + __popc(b & ((1u << lane) - 1));
-              if (k < a.item_cap) {
-                a.it_out.slot[k] = sslot;
-                a.it_out.patch[k] = (unsigned)(ob.first_patch + p) | ((unsigned)o << 16);
-              }
-            }
-            off += __popc(b);
-          }
-        }
-        if (!pass2) {
-          total = off;
-          if (total == 0) break;
-          if (lane == 0) ibase = atomicAdd(a.n_items_out, total);
-          ibase = __shfl_sync(FULL, ibase, 0);
-          if (ibase + total > a.item_cap) {  // item list full: drop (flagged, the host reports it)
-            if (lane == 0) atomicExch(a.overflow, 1u);
-            total = ibase < a.item_cap ? a.item_cap - ibase : 0;
-          }
-        }
-      }
-      if (lane == src) {
-        my_begin = ibase;
-        my_cnt = total;
-      }
-      if (lane == 0) solves += total;
-    }
-    if (alive) {
-      const unsigned s = my_slot;
-      a.qout.ox[s] = org.x; a.qout.oy[s] = org.y; a.qout.oz[s] = org.z;
-      a.qout.dx[s] = dir.x; a.qout.dy[s] = dir.y; a.qout.dz[s] = dir.z;
-      a.qout.fx[s] = flux.x; a.qout.fy[s] = flux.y; a.qout.fz[s] = flux.z;
-      a.qout.idd[s] = id | ((unsigned long long)dep << 56);
-      a.qout.hdist[s] = best.dist;
-      a.qout.hobj[s] = best.obj < 0 ? -1 : (best.obj | (best.inside ? 1 << 16 : 0));
-      a.qout.item_begin[s] = my_begin;
-      a.qout.item_cnt[s] = my_cnt;
-    }
-  }
-  const unsigned long long q64 = warp_sum64(queries), s64 = warp_sum64(solves), p64 = warp_sum64(photons),
-                           d64 = warp_sum64(deposits), k64 = warp_sum64(kept);
-  if (lane == 0) {
-    if (q64) atomicAdd(&a.counters->isect_queries, q64);
-    if (s64) atomicAdd(&a.counters->patch_solves, s64);
-    if (p64) atomicAdd(&a.counters->photons, p64);
-    if (d64) atomicAdd(&a.counters->deposits, d64);
-    if (k64) atomicAdd(&a.counters->deposits_kept, k64);
-  }
-}
-
-struct NewtonArgs {
-  DevScene scene;
-  NewtonCfg ncfg;
-  int patches_in_smem;
-  uint64_t pass;
-  Queue q;
-  Items it;
-  const unsigned* n_items_ptr;
-  unsigned item_cap;
-};
-
-// Bezier3::newton for the queued (photon slot, patch) items.  Each warp takes chunks of C items
-// (C chosen so that all warps of the grid get work) and runs the C*restarts tasks over its 32
-// lanes with flush_items (scene.cuh): lanes = restarts, arg-min on (t, restart) per item.
-__global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_items_kernel(const NewtonArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  const unsigned n = min(*a.n_items_ptr, a.item_cap);
-  if (n == 0) return;
-  const size_t scene_bytes = scene_smem_bytes(a.scene.n_obj, a.scene.n_patch, a.patches_in_smem);
-  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem);
-  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + scene_bytes) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-  unsigned C = (n + n_warps - 1) / n_warps;
-  C = C < 1 ? 1 : (C > 32 ? 32 : C);  // few items: one per warp keeps the serial Newton chain short
-  for (unsigned c0 = warp_global * C; c0 < n; c0 += n_warps * C) {
-    const int cnt = (int)min(C, n - c0);
-    if (lane < cnt) {
-      const unsigned s = a.it.slot[c0 + lane];
-      const unsigned pk = a.it.patch[c0 + lane];
-      ws->ray[0][lane] = a.q.ox[s]; ws->ray[1][lane] = a.q.oy[s]; ws->ray[2][lane] = a.q.oz[s];
-      ws->ray[3][lane] = a.q.dx[s]; ws->ray[4][lane] = a.q.dy[s]; ws->ray[5][lane] = a.q.dz[s];
-      const unsigned long long idd = a.q.idd[s];
-      ws->id[lane] = idd & ID_MASK;
-      ws->node[lane] = (unsigned)(idd >> 56);
-      ws->item[lane] = (unsigned)lane | ((pk & 0xffffu) << 8);
-    }
-    __syncwarp();
-    flush_items(sv, ws, cnt, a.ncfg, a.pass, SPPM_DOMAIN_PHOTON, nullptr, 0, lane);
-    if (lane < cnt) {
-      a.it.t[c0 + lane] = ws->it_t[lane];
-      a.it.u[c0 + lane] = ws->it_u[lane];
-      a.it.v[c0 + lane] = ws->it_v[lane];
-    }
-    __syncwarp();
-  }
-}
-
-struct WfLayout {
-  Queue q[2];
-  Items it[2];
-  unsigned* counters;  // [4*b + r] queue count of region r at bounce b, [64+b] item counts, [96] overflow
-  unsigned item_cap;
-};
-
-size_t wf_bytes(int64_t cap, int64_t item_cap) {
-  return 2 * (size_t)(2 * cap) * (10 * 8 + 8 + 4 + 4 + 4) + 2 * (size_t)item_cap * (4 + 4 + 24) + 128 * 4 + 65536;
-}
-WfLayout wf_layout(void* store, int64_t cap, int64_t item_cap) {
-  WfLayout L;
-  unsigned char* p = (unsigned char*)store;
-  auto take = [&](size_t bytes) {
-    void* r = p;
-    p += (bytes + 255) & ~(size_t)255;
-    return r;
-  };
-  for (int k = 0; k < 2; k++) {
-    Queue& q = L.q[k];
-    double** d[] = {&q.ox, &q.oy, &q.oz, &q.dx, &q.dy, &q.dz, &q.fx, &q.fy, &q.fz, &q.hdist};
-    for (double** x : d) *x = (double*)take((size_t)cap * 16);  // 2 x cap entries: four regions, see photon_step_kernel
-    q.idd = (unsigned long long*)take((size_t)cap * 16);
-    q.hobj = (int*)take((size_t)cap * 8);
-    q.item_begin = (unsigned*)take((size_t)cap * 8);
-    q.item_cnt = (unsigned*)take((size_t)cap * 8);
-    Items& it = L.it[k];
-    it.slot = (unsigned*)take((size_t)item_cap * 4);
-    it.patch = (unsigned*)take((size_t)item_cap * 4);
-    it.t = (double*)take((size_t)item_cap * 8);
-    it.u = (double*)take((size_t)item_cap * 8);
-    it.v = (double*)take((size_t)item_cap * 8);
-  }
-  L.counters = (unsigned*)take(128 * 4);
-  L.item_cap = (unsigned)item_cap;
-  return L;
-}
-
-}  // namespace
 
 cudaError_t wavefront_configure(sppm_ctx* c, int* step_blocks, int* newton_blocks, size_t* step_smem, size_t* newton_smem) {
   const size_t scene = scene_smem_bytes(c->scene.n_obj, c->scene.n_patch, c->patches_in_smem, true);
@@ -459,41 +55,34 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
   if ((e = wavefront_configure(c, &step_blocks, &newton_blocks, &step_smem, &newton_smem))) return e;
   cudaStream_t st = Ln.stream;
   if ((e = cudaMemsetAsync(L.counters, 0, 128 * 4, st))) return e;
-  const int n_steps = c->prm.max_dep + 2;  // queries at dep = 0 .. max_dep+1 (Q9)
+  WfBatch w;
+  w.scene = c->scene;
+  w.patches_in_smem = c->patches_in_smem ? 1 : 0;
+  w.newton_cull = c->newton_cull ? 1 : 0;
+  w.max_dep = c->prm.max_dep;
+  w.newton_restarts = c->prm.newton_restarts;
+  w.newton_iters = c->prm.newton_iters;
+  w.newton_mode = c->prm.newton_mode;
+  w.fast_math = c->prm.math_mode == SPPM_MATH_FAST ? 1 : 0;
+  w.seed = c->prm.seed;
+  w.pass = pass_id;
+  w.counters = (DevCounters*)c->counters.p;
+  w.begin = begin;
+  w.count = count;
+  w.q_cap = (unsigned)Ln.wf_cap;
+  w.grid = c->grid;
+  w.cell_slot = c->index_ok ? (const int32_t*)c->cell_slot.p : nullptr;
+  w.n_slots = c->n_slots;
+  w.keep_all = c->keep_all_deposits ? 1 : 0;
+  w.dep = (Deposit*)Ln.dep_raw.p;
+  w.dep_key = (uint32_t*)Ln.dep_key.p;
+  w.dep_rank = (uint32_t*)Ln.dep_rank.p;
+  w.slot_count = (unsigned int*)Ln.slot_count.p;
+  w.dep_cap = (unsigned long long)Ln.dep_cap;
+  w.dep_count = (unsigned long long*)Ln.scalars.p + 1;
+  const int n_steps = wf_n_steps(c->prm.max_dep);
   for (int b = 0; b < n_steps; b++) {
-    StepArgs a;
-    a.scene = c->scene;
-    a.patches_in_smem = c->patches_in_smem ? 1 : 0;
-    a.max_dep = c->prm.max_dep;
-    a.bounce = b;
-    a.do_intersect = b < n_steps - 1;
-    a.fast_math = c->prm.math_mode == SPPM_MATH_FAST ? 1 : 0;
-    a.seed = c->prm.seed;
-    a.pass = pass_id;
-    a.counters = (DevCounters*)c->counters.p;
-    a.qin = L.q[b & 1];
-    a.qout = L.q[(b + 1) & 1];
-    a.it_in = L.it[b & 1];
-    a.it_out = L.it[(b + 1) & 1];
-    a.n_in_ptr = L.counters + 4 * b;
-    a.n_in_host = (unsigned)total;
-    a.n_out = L.counters + 4 * (b + 1);
-    a.q_cap = (unsigned)Ln.wf_cap;
-    a.n_items_out = L.counters + 64 + b + 1;
-    a.item_cap = L.item_cap;
-    a.overflow = L.counters + 96;
-    a.begin = begin;
-    a.count = count;
-    a.grid = c->grid;
-    a.cell_slot = c->index_ok ? (const int32_t*)c->cell_slot.p : nullptr;
-    a.n_slots = c->n_slots;
-    a.keep_all = c->keep_all_deposits ? 1 : 0;
-    a.dep = (Deposit*)Ln.dep_raw.p;
-    a.dep_key = (uint32_t*)Ln.dep_key.p;
-    a.dep_rank = (uint32_t*)Ln.dep_rank.p;
-    a.slot_count = (unsigned int*)Ln.slot_count.p;
-    a.dep_cap = (unsigned long long)Ln.dep_cap;
-    a.dep_count = (unsigned long long*)Ln.scalars.p + 1;
+    const StepArgs a = wf_step_args(w, L, b);
     int blocks = step_blocks;
     if (b == 0) {
       const int64_t want = (total + STEP_THREADS - 1) / STEP_THREADS;
@@ -502,19 +91,7 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
     photon_step_kernel<<<blocks, STEP_THREADS, step_smem, st>>>(a);
     c->host_counters.launches++;
     if (a.do_intersect && c->scene.n_patch > 0) {
-      NewtonArgs n;
-      n.scene = c->scene;
-      n.ncfg.restarts = c->prm.newton_restarts;
-      n.ncfg.iters = c->prm.newton_iters;
-      n.ncfg.mode = c->prm.newton_mode;
-      n.ncfg.seed = c->prm.seed;
-      n.ncfg.cull = c->newton_cull ? 1 : 0;
-      n.patches_in_smem = a.patches_in_smem;
-      n.pass = pass_id;
-      n.q = a.qout;
-      n.it = a.it_out;
-      n.n_items_ptr = a.n_items_out;
-      n.item_cap = L.item_cap;
+      const NewtonArgs n = wf_newton_args(w, L, a);
       newton_items_kernel<<<newton_blocks, TRACE_THREADS, newton_smem, st>>>(n);
       c->host_counters.launches++;
     }

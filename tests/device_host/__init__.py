@@ -20,7 +20,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _CSRC = os.path.join(_ROOT, "raytrace3_b200", "csrc")
 LIB_PATH = os.path.join(_HERE, "_build", "libdevice_host.so")
 SOURCES = [os.path.join(_HERE, f) for f in ("device_host.cpp", "cuda_host_shim.h")] + [
-    os.path.join(_CSRC, f) for f in ("scene.cuh", "device_math.cuh", "scene_prep.h", "trace_kernels.cuh", "ctx.h")] + [
+    os.path.join(_CSRC, f) for f in ("scene.cuh", "device_math.cuh", "scene_prep.h", "trace_kernels.cuh", "wavefront_kernels.cuh", "ctx.h")] + [
     os.path.join(_ROOT, "include", "sppm_b200.h")]
 # -ffp-contract=off: no FMA contraction, the library's -fmad=false (explicit fma() calls stay fused)
 # -fno-extern-tls-init: the kernels' block-scope `extern __shared__` (= thread_local here) array has no dynamic initialiser
@@ -149,6 +149,24 @@ class HostScene:
         return dict(x=out["x"][order], n=out["n"][order], flux=out["flux"][order], photon=photon[order],
                     bounce=bounce[order]), dict(zip(COUNTERS, cnt.tolist()))
 
+    def photon_trace_wavefront(self, prm, begin, count, pass_id, step_blocks=24, newton_blocks=24):
+        """The bounce-synchronous pass (photon_step_kernel + newton_items_kernel per bounce, the
+        product's wf_layout / wf_step_args / wf_newton_args) -> deposits sorted by (photon id, bounce),
+        counters, and the queue counts [bounce][region]."""
+        cap = int(count * max(1, self.desc.n_lights) * (prm.max_dep + 2))
+        out = np.zeros(cap, dtype=deposit_dtype)
+        cnt = np.zeros(len(COUNTERS), dtype=np.uint64)
+        qc = np.zeros((prm.max_dep + 3, 4), dtype=np.uint32)
+        n = self.dh.lib.dh_photon_trace_wavefront(self.h, C.byref(prm), begin, count, pass_id, step_blocks, newton_blocks,
+                                                  cap, _p(out), _p(cnt), _p(qc))
+        assert 0 <= n <= cap
+        out = out[:n]
+        photon = out["meta"] & np.uint64((1 << 56) - 1)
+        bounce = (out["meta"] >> np.uint64(56)).astype(np.int32)
+        order = np.lexsort((bounce, photon))
+        return dict(x=out["x"][order], n=out["n"][order], flux=out["flux"][order], photon=photon[order],
+                    bounce=bounce[order]), dict(zip(COUNTERS, cnt.tolist())), qc
+
     def intersect_kernel(self, prm, rays6, ids=None, pass_id=0, node=0, cull=1):
         rays6 = _f64(rays6, (-1, 6))
         n = rays6.shape[0]
@@ -197,6 +215,8 @@ class DeviceHost:
         L.dh_eye_pass_kernel.restype = I64
         L.dh_photon_trace_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), U64, U64, U64, C.c_int, I64, VP, VP]
         L.dh_photon_trace_kernel.restype = I64
+        L.dh_photon_trace_wavefront.argtypes = [VP, C.POINTER(abi.SppmParams), U64, U64, U64, C.c_int, C.c_int, I64, VP, VP, VP]
+        L.dh_photon_trace_wavefront.restype = I64
         L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
         L.dh_patch_batch_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, VP, C.c_int, VP]
         assert L.dh_sizeof_hpraw() == hpraw_dtype.itemsize and L.dh_sizeof_deposit() == deposit_dtype.itemsize

@@ -141,7 +141,21 @@ inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
   return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline int __double2int_rd(double d) { return (int)floor(d); }
+
+// cooperative_groups::coalesced_threads() returns whichever lanes of the warp happen to be
+// converged at the call; the lanes here run one at a time between collectives, so the group is the
+// calling lane alone -- one of the groupings the hardware may form
+namespace cooperative_groups {
+struct coalesced_group {
+  unsigned thread_rank() const { return 0; }
+  unsigned size() const { return 1; }
+  template <class T>
+  T shfl(T v, int) const { return v; }
+};
+inline coalesced_group coalesced_threads() { return coalesced_group(); }
+}  // namespace cooperative_groups
 // stand-in for rcp.approx.ftz.f64 (scene.cuh rcp_newton): a reciprocal good to ~20 bits whose
 // low mantissa word is zero, as PTX specifies; the two Newton-Raphson steps that follow it are
 // the product's own

@@ -24,6 +24,7 @@ alignas(16) thread_local unsigned char smem[160 << 10];
 }  // namespace sppm
 #include "../../raytrace3_b200/csrc/scene_prep.h"
 #include "../../raytrace3_b200/csrc/trace_kernels.cuh"
+#include "../../raytrace3_b200/csrc/wavefront_kernels.cuh"
 
 thread_local DhWarp* dh_warp = nullptr;
 
@@ -377,6 +378,66 @@ void dh_patch_batch_kernel(void* p, const SppmParams* prm, int cull, int64_t n, 
   a.seeds = seeds;
   a.tuv = tuv;
   if (n > 0) launch(patch_batch_kernel, a, blocks);
+}
+// launch_photon_trace_wavefront (wavefront.cu) with the product's own queue layout and per-bounce
+// arguments (wf_layout / wf_step_args / wf_newton_args): photon_step_kernel and newton_items_kernel
+// per bounce, every diffuse deposit kept.  Returns the deposit count; -1 if the item list overflowed.
+int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin, uint64_t count, uint64_t pass,
+                                  int step_blocks, int newton_blocks, int64_t cap, Deposit* out, uint64_t* counters9,
+                                  uint32_t* queue_counts /* [4 * (max_dep + 3)] or null */) {
+  DhScene* h = (DhScene*)p;
+  const int64_t total = (int64_t)h->dev.n_light * (int64_t)count;
+  if (total <= 0) return 0;
+  DevCounters cnt;
+  memset(&cnt, 0, sizeof(cnt));
+  const int64_t item_cap = std::max<int64_t>(total * 2, 1 << 16);
+  std::vector<unsigned char> store(wf_bytes(total, item_cap) + 256);
+  void* base = (void*)(((uintptr_t)store.data() + 255) & ~(uintptr_t)255);
+  const WfLayout L = wf_layout(base, total, item_cap);
+  memset(L.counters, 0, 128 * 4);
+  std::vector<uint32_t> key((size_t)cap), rank((size_t)cap);
+  unsigned int slot_count[2] = {0, 0};
+  unsigned long long n_dep = 0;
+  const TraceCommon tc = common_of(h, prm, 1, pass, &cnt);
+  WfBatch w;
+  w.scene = h->dev;
+  w.patches_in_smem = tc.patches_in_smem;
+  w.newton_cull = 1;
+  w.max_dep = prm->max_dep;
+  w.newton_restarts = prm->newton_restarts;
+  w.newton_iters = prm->newton_iters;
+  w.newton_mode = prm->newton_mode;
+  w.fast_math = tc.fast_math;
+  w.seed = prm->seed;
+  w.pass = pass;
+  w.counters = &cnt;
+  w.begin = begin;
+  w.count = count;
+  w.q_cap = (unsigned)total;
+  memset(&w.grid, 0, sizeof(w.grid));
+  w.cell_slot = nullptr;
+  w.n_slots = 0;
+  w.keep_all = 1;
+  w.dep = out;
+  w.dep_key = key.data();
+  w.dep_rank = rank.data();
+  w.slot_count = slot_count;
+  w.dep_cap = (unsigned long long)cap;
+  w.dep_count = &n_dep;
+  const int n_steps = wf_n_steps(prm->max_dep);
+  for (int b = 0; b < n_steps; b++) {
+    const StepArgs a = wf_step_args(w, L, b);
+    long long blocks = step_blocks;
+    if (b == 0) blocks = std::min<long long>(blocks, (total + 31) / 32);
+    launch(photon_step_kernel, a, blocks);
+    if (a.do_intersect && h->dev.n_patch > 0) {
+      const NewtonArgs n = wf_newton_args(w, L, a);
+      launch(newton_items_kernel, n, newton_blocks);
+    }
+  }
+  if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
+  if (queue_counts) memcpy(queue_counts, L.counters, sizeof(uint32_t) * 4 * (size_t)(n_steps + 1));
+  return L.counters[96] ? -1 : (int64_t)n_dep;
 }
 int dh_sizeof_hpraw() { return (int)sizeof(HpRaw); }
 int dh_sizeof_deposit() { return (int)sizeof(Deposit); }

@@ -460,3 +460,47 @@ def test_photon_trace_kernel_golden_of_the_reference(dh, oracle, name):
         acc_n += newN
         acc_t += tao
     assert np.array_equal(acc_n, g[f"{name}_acc_newN"]) and np.array_equal(acc_t, g[f"{name}_acc_tao"])
+
+
+# ---- the bounce-synchronous pass (wavefront_kernels.cuh): the bench's default tracer -------------
+@pytest.mark.parametrize("name,count", [("reference", 100000), ("custom", 20000), ("quirks", 20000), ("stress", 20000),
+                                        ("cornell", 20000)])
+def test_wavefront_kernels_against_oracle(dh, oracle, name, count):
+    """photon_step_kernel + newton_items_kernel per bounce, driven by the product's own wf_layout /
+    wf_step_args / wf_newton_args, == Light::emit + PhotonTrace of the oracle: every deposit and every
+    counter, bit for bit (reference scene: BASELINE config 1's 100 k photons).  Also checks the
+    four-region queue: each bounce's survivors = the next bounce's input, all photons accounted for."""
+    sc = _scene(name)
+    hs = dh.scene(sc)
+    prm = _params()
+    ref = oracle.photon_pass(sc, prm, 100, count, 9, keep_deposits=True)
+    dep, cnt, qc = hs.photon_trace_wavefront(prm, 100, count, 9)
+    rd, rc = ref["dep"], ref["counters"]
+    total = count * len(sc.plvec)
+    assert cnt["photons"] == rc["photons"] == total
+    assert cnt["deposits"] == rc["deposits"] == cnt["deposits_kept"]
+    assert cnt["patch_solves"] == rc["solves"]
+    # the oracle counts a query per NearCollide call; the wavefront drops a photon that hits nothing when
+    # it finds that out (same query), and never issues the query past the depth limit (Raytracer.h:129-132)
+    assert rc["queries"] - qc[prm.max_dep + 2].sum() <= cnt["isect_queries"] <= rc["queries"]
+    order = np.lexsort((rd["bounce"], rd["photon"]))
+    assert dep["x"].shape[0] == order.shape[0] > 2 * total
+    for k in ("photon", "bounce", "x", "n", "flux"):
+        np.testing.assert_array_equal(dep[k], rd[k][order], err_msg=k)
+    alive = qc.sum(axis=1).astype(np.int64)
+    assert alive[0] == 0 and alive[1] <= total and (np.diff(alive[1:]) <= 0).all()
+    if any(o.kind == 2 for o in sc.objvec):
+        assert qc[1:, 3].sum() > 0          # photons with Bezier solves pending
+    else:
+        assert qc[:, 3].sum() == 0
+
+
+def test_wavefront_equals_persistent_on_the_cpu(dh):
+    """Both tracer organisations, FAST Newton + FAST math (the bench configuration): same deposits."""
+    hs = dh.scene(_scene("reference"))
+    prm = _params(newton_mode=abi.SPPM_NEWTON_FAST, math_mode=abi.SPPM_MATH_FAST)
+    a, ca = hs.photon_trace_kernel(prm, 0, 30000, 2)
+    b, cb, _ = hs.photon_trace_wavefront(prm, 0, 30000, 2, step_blocks=5, newton_blocks=3)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert ca["deposits"] == cb["deposits"] and ca["patch_solves"] == cb["patch_solves"]
