@@ -20,7 +20,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _CSRC = os.path.join(_ROOT, "raytrace3_b200", "csrc")
 LIB_PATH = os.path.join(_HERE, "_build", "libdevice_host.so")
 SOURCES = [os.path.join(_HERE, f) for f in ("device_host.cpp", "cuda_host_shim.h")] + [
-    os.path.join(_CSRC, f) for f in ("scene.cuh", "device_math.cuh", "scene_prep.h", "trace_kernels.cuh", "wavefront_kernels.cuh", "ctx.h")] + [
+    os.path.join(_CSRC, f) for f in ("scene.cuh", "device_math.cuh", "scene_prep.h", "trace_kernels.cuh", "wavefront_kernels.cuh", "gather_kernels.cuh", "ctx.h")] + [
     os.path.join(_ROOT, "include", "sppm_b200.h")]
 # -ffp-contract=off: no FMA contraction, the library's -fmad=false (explicit fma() calls stay fused)
 # -fno-extern-tls-init: the kernels' block-scope `extern __shared__` (= thread_local here) array has no dynamic initialiser
@@ -34,6 +34,25 @@ hpraw_dtype = np.dtype([("pos", "f8", 3), ("n", "f8", 3), ("wgt", "f8", 3), ("r2
 deposit_dtype = np.dtype([("x", "f8", 3), ("n", "f8", 3), ("flux", "f8", 3), ("meta", "u8")])
 COUNTERS = ("photons", "isect_queries", "patch_solves", "deposits", "deposits_kept", "cand_pairs", "acc_pairs", "overflow",
             "patch_culled")
+
+
+class Grid(C.Structure):  # ctx.h Grid
+    _fields_ = [("org", DBL * 3), ("inv_cell", DBL), ("dim", C.c_int * 3), ("n_cells", I64), ("keep_lo", DBL * 3),
+                ("keep_hi", DBL * 3)]
+
+
+def make_grid(pos, search_r2) -> Grid:
+    """The hash grid build_index (gather.cu) lays over the hit points: cell edge sqrt(searchR2) (1 + 1e-9),
+    origin at their minimum, deposits kept within one cell edge of their bounding box (no 2^26-cell cap here)."""
+    cell = float(np.sqrt(search_r2)) * (1.0 + 1e-9)
+    lo, hi = pos.min(0), pos.max(0)
+    dim = [int(np.floor((hi[k] - lo[k]) / cell) + 1) for k in range(3)]
+    g = Grid()
+    for k in range(3):
+        g.org[k], g.dim[k], g.keep_lo[k], g.keep_hi[k] = lo[k], dim[k], lo[k] - cell, hi[k] + cell
+    g.inv_cell = 1.0 / cell
+    g.n_cells = dim[0] * dim[1] * dim[2]
+    return g
 
 
 def cuda_include_dir() -> str:
@@ -217,6 +236,7 @@ class DeviceHost:
         L.dh_photon_trace_kernel.restype = I64
         L.dh_photon_trace_wavefront.argtypes = [VP, C.POINTER(abi.SppmParams), U64, U64, U64, C.c_int, C.c_int, I64, VP, VP, VP]
         L.dh_photon_trace_wavefront.restype = I64
+        L.dh_gather_filtered.argtypes = [I64, VP, C.POINTER(Grid), I64, VP, DBL, C.c_int, C.c_int, VP, VP, VP, VP, VP]
         L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
         L.dh_patch_batch_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, VP, C.c_int, VP]
         assert L.dh_sizeof_hpraw() == hpraw_dtype.itemsize and L.dh_sizeof_deposit() == deposit_dtype.itemsize
@@ -272,6 +292,32 @@ class DeviceHost:
         out = np.empty((ids.shape[0], 3))
         self.lib.dh_unit_rand_vec(seed, pass_id, ids.shape[0], _p(ids), purpose, _p(out))
         return out
+
+    def gather_filtered(self, hp, dep, search_r2, count_pairs=True, blocks=16):
+        """build_index + deposit binning + gather_filtered_kernel (the product's kernels; CUB's sorts and
+        scans restated with std:: algorithms) -> newN [n], tao [n, 3] in the order of `hp`, info, pairs."""
+        n, m = hp["pos"].shape[0], dep["x"].shape[0]
+        raw = np.zeros(n, dtype=hpraw_dtype)
+        for k in ("pos", "n", "wgt", "r2"):
+            raw[k] = hp[k]
+        raw["okey"] = np.arange(n, dtype=np.uint64)
+        d = np.zeros(max(m, 1), dtype=deposit_dtype)
+        for k in ("x", "n", "flux"):
+            d[k][:m] = dep[k]
+        g = make_grid(_f64(hp["pos"]), search_r2)
+        order = np.zeros(n, dtype=np.uint32)
+        dN = np.zeros(n, dtype=np.int32)
+        dtao = np.zeros((3, n))
+        info = np.zeros(5, dtype=np.int64)
+        pairs = np.zeros(2, dtype=np.uint64)
+        rc = self.lib.dh_gather_filtered(n, _p(raw), C.byref(g), m, _p(d), search_r2, int(count_pairs), blocks, _p(order),
+                                         _p(dN), _p(dtao), _p(info), _p(pairs))
+        assert rc == 0
+        newN = np.zeros(n, dtype=np.int32)
+        tao = np.zeros((n, 3))
+        newN[order] = dN
+        tao[order] = dtao.T
+        return newN, tao, dict(zip(("n_occ", "n_slots", "n_units", "n_items", "kept"), info.tolist())), pairs.tolist()
 
     def scene(self, scene) -> HostScene:
         return HostScene(self, scene)

@@ -20,6 +20,7 @@
 #include <math.h>
 #include <ucontext.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -113,8 +114,14 @@ inline unsigned __ballot_sync(unsigned, bool p) {
   return m;
 }
 inline bool __any_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) != 0; }
+inline bool __all_sync(unsigned mask, bool p) { return __ballot_sync(mask, p) == (dh_warp ? 0xffffffffu : 1u); }
 template <class T>
 inline T __shfl_sync(unsigned, T v, int src) { return dh_exchange(v, src); }
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, int delta) {  // lanes below delta keep their own value
+  const int me = dh_warp ? dh_warp->cur : 0;
+  return dh_exchange(v, me >= delta ? me - delta : me);
+}
 template <class T>
 inline T __shfl_xor_sync(unsigned, T v, int off) { return dh_exchange(v, (dh_warp ? dh_warp->cur : 0) ^ off); }
 
@@ -135,12 +142,45 @@ inline long long __double_as_longlong(double d) {
   return v;
 }
 inline float __double2float_rn(double d) { return (float)d; }
+inline float __double2float_ru(double d) {  // round towards +inf
+  float f = (float)d;
+  return (double)f < d ? nextafterf(f, INFINITY) : f;
+}
+inline unsigned __float_as_uint(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return u;
+}
+inline void __trap() { abort(); }
 // __fdividef has <= 2 ulp error on the device; the exact quotient lies inside that band
 inline float __fdividef(float a, float b) { return a / b; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
   return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline double atomicAdd(double* p, double v) {
+  uint64_t* q = reinterpret_cast<uint64_t*>(p);
+  uint64_t old = __atomic_load_n(q, __ATOMIC_RELAXED);
+  for (;;) {
+    double o, nw;
+    memcpy(&o, &old, 8);
+    nw = o + v;
+    uint64_t nb;
+    memcpy(&nb, &nw, 8);
+    if (__atomic_compare_exchange_n(q, &old, nb, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return o;
+  }
+}
+inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
+inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
 inline unsigned atomicExch(unsigned* p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
 inline int __double2int_rd(double d) { return (int)floor(d); }
 

@@ -12,19 +12,24 @@
 
 #include <atomic>
 #include <functional>
+#include <numeric>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 // dynamic shared memory of the block a host thread is emulating (see __shared__ in the shim)
 namespace sppm {
 namespace {
-alignas(16) thread_local unsigned char smem[160 << 10];
+alignas(16) thread_local unsigned char smem[160 << 10];   // trace / wavefront kernels
+alignas(128) thread_local unsigned char gsm[64 << 10];    // gather_kernel
+alignas(128) thread_local unsigned char wsm[64 << 10];    // gather_filtered_kernel
 }
 }  // namespace sppm
 #include "../../raytrace3_b200/csrc/scene_prep.h"
 #include "../../raytrace3_b200/csrc/trace_kernels.cuh"
 #include "../../raytrace3_b200/csrc/wavefront_kernels.cuh"
+#include "../../raytrace3_b200/csrc/gather_kernels.cuh"
 
 thread_local DhWarp* dh_warp = nullptr;
 
@@ -77,12 +82,17 @@ void fiber_entry() {
 }
 unsigned long long run_warp(std::function<void(int)> f, unsigned block = 0, unsigned grid = 1) {
   constexpr size_t STACK = 256 << 10;
-  std::vector<char> stacks(32 * STACK);
+  struct Stacks {  // one set of lane stacks per host thread, reused by every block it emulates
+    char* p = (char*)malloc(32 * STACK);
+    ~Stacks() { free(p); }
+  };
+  static thread_local Stacks lane_stacks;
+  char* stacks = lane_stacks.p;
   DhWarp warp;
   for (int l = 0; l < 32; l++) {
     warp.done[l] = false;
     getcontext(&warp.lane_ctx[l]);
-    warp.lane_ctx[l].uc_stack.ss_sp = stacks.data() + (size_t)l * STACK;
+    warp.lane_ctx[l].uc_stack.ss_sp = stacks + (size_t)l * STACK;
     warp.lane_ctx[l].uc_stack.ss_size = STACK;
     warp.lane_ctx[l].uc_link = nullptr;
     makecontext(&warp.lane_ctx[l], fiber_entry, 0);
@@ -102,7 +112,12 @@ unsigned long long run_warp(std::function<void(int)> f, unsigned block = 0, unsi
 
 // kernel<<<blocks, 32, trace_smem>>>(args): one-warp blocks, handed out to host threads in order
 template <class K, class A>
+void call_kernel(K kernel, const A& args) { kernel(args); }
+template <class K, class... As>
+void call_kernel(K kernel, const std::tuple<As...>& args) { std::apply(kernel, args); }
+template <class K, class A>
 void launch(K kernel, const A& args, long long blocks) {
+  if (blocks <= 0) return;
   const int T = (int)std::max<long long>(1, std::min<long long>(blocks, std::min(16u, std::max(1u, std::thread::hardware_concurrency()))));
   std::atomic<long long> next{0};
   std::vector<std::thread> th;
@@ -111,7 +126,7 @@ void launch(K kernel, const A& args, long long blocks) {
       for (;;) {
         const long long b = next.fetch_add(1);
         if (b >= blocks) break;
-        run_warp([&](int) { kernel(args); }, (unsigned)b, (unsigned)blocks);
+        run_warp([&](int) { call_kernel(kernel, args); }, (unsigned)b, (unsigned)blocks);
       }
     });
   for (auto& t : th) t.join();
@@ -438,6 +453,120 @@ int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin
   if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
   if (queue_counts) memcpy(queue_counts, L.counters, sizeof(uint32_t) * 4 * (size_t)(n_steps + 1));
   return L.counters[96] ? -1 : (int64_t)n_dep;
+}
+// ---- build_index + bin_deposits + launch_gather (gather.cu) with the product's kernels ----------
+// The host orchestration is restated here with std:: algorithms in place of CUB (stable sort by cell
+// key, run-length encode, exclusive scans, flagged select); every kernel between them is the
+// product's: hp_key / hp_permute / mark_nbr / finalize_slot / run_flag / unit_count / unit_fill /
+// dep_key / unit_parts and gather_filtered_kernel<COUNT>.  (dep_scatter_kernel needs its 320-thread
+// blocks, so sorted[off[key] + rank] = raw is done here.)  raw = hit points in canonical order.
+// Outputs in the CELL-SORTED order of the hit-point map: order[i] = raw index of sorted hit point i,
+// dN[n], dtao[3][n]; info = {n_occ, n_slots, n_units, n_items, kept deposits}; pairs = {cand, acc}.
+int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m, const Deposit* dep_raw, double search_r2,
+                       int count_pairs, int blocks, uint32_t* order, int32_t* dN, double* dtao, int64_t* info,
+                       uint64_t* pairs) {
+  const Grid g = *grid;
+  if (n <= 0) return -1;
+  const int T = 32;
+  auto nb = [&](long long k) { return (k + T - 1) / T; };
+  // hit points: cell keys, stable sort, SoA permute
+  std::vector<uint32_t> iota((size_t)n), key((size_t)n), idx((size_t)n), skey((size_t)n);
+  std::iota(iota.begin(), iota.end(), 0u);
+  launch(hp_key_kernel, std::make_tuple(raw, (const uint32_t*)iota.data(), (long long)n, g, key.data()), nb(n));
+  idx = iota;
+  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+  for (int64_t i = 0; i < n; i++) skey[(size_t)i] = key[idx[(size_t)i]];
+  const size_t nd = (size_t)n;
+  std::vector<double> dstore(nd * 16);
+  std::vector<uint64_t> okey(nd);
+  std::vector<int32_t> istore(nd * 5);
+  HpSoA s;
+  double* d = dstore.data();
+  s.px = d; s.py = d + nd; s.pz = d + 2 * nd; s.nx = d + 3 * nd; s.ny = d + 4 * nd; s.nz = d + 5 * nd; s.r2 = d + 6 * nd;
+  s.wx = d + 7 * nd; s.wy = d + 8 * nd; s.wz = d + 9 * nd; s.tao = d + 10 * nd; s.dtao = d + 13 * nd;
+  s.okey = okey.data();
+  int32_t* ip = istore.data();
+  s.N = ip; s.newN = ip + nd; s.dN = ip + 2 * nd; s.row = ip + 3 * nd; s.col = ip + 4 * nd;
+  launch(hp_permute_kernel, std::make_tuple(raw, (const uint32_t*)idx.data(), (long long)n, s), nb(n));
+  // occupied cells and their hit-point ranges
+  std::vector<uint32_t> occ_cell;
+  std::vector<int32_t> occ_start;
+  for (int64_t i = 0; i < n; i++)
+    if (i == 0 || skey[(size_t)i] != skey[(size_t)i - 1]) {
+      occ_cell.push_back(skey[(size_t)i]);
+      occ_start.push_back((int32_t)i);
+    }
+  const int n_occ = (int)occ_cell.size();
+  occ_start.push_back((int32_t)n);
+  // compact slots of the cells whose 27-neighbourhood holds a hit point
+  std::vector<int32_t> cell_slot((size_t)g.n_cells, 0), scan((size_t)g.n_cells);
+  launch(mark_nbr_kernel, std::make_tuple((const uint32_t*)occ_cell.data(), n_occ, g, cell_slot.data()), nb((long long)n_occ * 27));
+  std::exclusive_scan(cell_slot.begin(), cell_slot.end(), scan.begin(), 0);
+  int32_t n_slots = 0;
+  launch(finalize_slot_kernel, std::make_tuple(cell_slot.data(), (const int32_t*)scan.data(), (long long)g.n_cells, &n_slots),
+         nb(g.n_cells));
+  // work units
+  std::vector<int32_t> flag((size_t)n_occ), run_first, ucnt((size_t)n_occ + 1, 0), uoff((size_t)n_occ + 1);
+  launch(run_flag_kernel, std::make_tuple((const uint32_t*)occ_cell.data(), n_occ, g.dim[0], flag.data()), nb(n_occ));
+  for (int o = 0; o < n_occ; o++)
+    if (flag[(size_t)o]) run_first.push_back(o);
+  int32_t n_runs = (int32_t)run_first.size();
+  run_first.resize((size_t)n_occ + 1, 0);
+  launch(unit_count_kernel, std::make_tuple((const int32_t*)run_first.data(), (const int32_t*)&n_runs, n_occ,
+                                            (const int32_t*)occ_start.data(), ucnt.data()), nb(n_occ));
+  std::exclusive_scan(ucnt.begin(), ucnt.end(), uoff.begin(), 0);
+  const int n_units = uoff[(size_t)n_occ];
+  std::vector<GUnit> units((size_t)std::max(n_units, 1));
+  launch(unit_fill_kernel, std::make_tuple((const int32_t*)run_first.data(), (const int32_t*)&n_runs, n_occ,
+                                           (const int32_t*)occ_start.data(), (const uint32_t*)occ_cell.data(),
+                                           (const int32_t*)uoff.data(), g, (const int32_t*)cell_slot.data(), units.data()), nb(n_occ));
+  // deposits: slot key + arrival rank, CSR offsets, scatter (key n_slots = not kept)
+  std::vector<uint32_t> dkey((size_t)std::max<int64_t>(m, 1)), drank((size_t)std::max<int64_t>(m, 1));
+  std::vector<unsigned int> slot_count((size_t)n_slots + 2, 0);
+  std::vector<int32_t> dep_off((size_t)n_slots + 2);
+  if (m > 0)
+    launch(dep_key_kernel, std::make_tuple(dep_raw, (long long)m, g, (const int32_t*)cell_slot.data(), n_slots, dkey.data(),
+                                           drank.data(), slot_count.data()), nb(m));
+  std::exclusive_scan(slot_count.begin(), slot_count.end(), dep_off.begin(), 0);
+  std::vector<Deposit> sorted((size_t)std::max<int64_t>(m, 1));
+  {
+    // arrival ranks depend on the order the emulated blocks ran in; any order is a valid counting sort
+    for (int64_t i = 0; i < m; i++) sorted[(size_t)(dep_off[dkey[(size_t)i]] + (int32_t)drank[(size_t)i])] = dep_raw[i];
+  }
+  // work items of the batch and the gather
+  std::vector<int32_t> parts((size_t)n_units + 1), item_off((size_t)n_units + 1);
+  launch(unit_parts_kernel, std::make_tuple((const GUnit*)units.data(), n_units, (const int32_t*)dep_off.data(), parts.data()),
+         nb(n_units + 1));
+  std::exclusive_scan(parts.begin(), parts.end(), item_off.begin(), 0);
+  DevCounters cnt;
+  memset(&cnt, 0, sizeof(cnt));
+  GatherArgs a;
+  memset(&a, 0, sizeof(a));
+  a.s = s;
+  a.n_hp = n;
+  a.occ_start = occ_start.data();
+  a.occ_run = nullptr;  // exact kernel only
+  a.n_occ = n_occ;
+  a.dep_off = dep_off.data();
+  a.dep = sorted.data();
+  a.search_r2 = search_r2;
+  a.counters = &cnt;
+  a.grid = g;
+  a.occ_cell = occ_cell.data();
+  a.units = units.data();
+  a.n_units = n_units;
+  a.item_off = item_off.data();
+  unsigned int work_counter = 0;
+  if (n_units > 0) {
+    if (count_pairs) launch(gather_filtered_kernel<true>, std::make_tuple(a, &work_counter), blocks);
+    else launch(gather_filtered_kernel<false>, std::make_tuple(a, &work_counter), blocks);
+  }
+  memcpy(order, idx.data(), nd * 4);
+  memcpy(dN, s.dN, nd * 4);
+  memcpy(dtao, s.dtao, nd * 24);
+  info[0] = n_occ; info[1] = n_slots; info[2] = n_units; info[3] = item_off[(size_t)n_units]; info[4] = dep_off[(size_t)n_slots];
+  pairs[0] = cnt.cand_pairs; pairs[1] = cnt.acc_pairs;
+  return 0;
 }
 int dh_sizeof_hpraw() { return (int)sizeof(HpRaw); }
 int dh_sizeof_deposit() { return (int)sizeof(Deposit); }

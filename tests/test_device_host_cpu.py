@@ -504,3 +504,130 @@ def test_wavefront_equals_persistent_on_the_cpu(dh):
     for k in a:
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
     assert ca["deposits"] == cb["deposits"] and ca["patch_solves"] == cb["patch_solves"]
+
+
+# ---- the hash grid and the FP32-filtered gather (gather_kernels.cuh) -----------------------------
+# build_index's kernels (cell keys, SoA permute, neighbourhood slots, work units), the deposit keys
+# and gather_filtered_kernel run as one-warp blocks; CUB's sorts / scans are std:: algorithms in the
+# harness.  The inputs are those of the GPU tests of the same names (tests/test_gpu_parity.py).
+def _check_gather(dh, oracle, hp, x, dn, flux, search_r2=2.0, min_acc=100):
+    dep = dict(x=x, n=dn, flux=flux)
+    newN, tao, cand, acc = oracle.gather_brute(hp, dep, search_r2)
+    gn, gt, info, pairs = dh.gather_filtered(hp, dep, search_r2)
+    assert newN.sum() > min_acc
+    np.testing.assert_array_equal(gn, newN)                 # level 2: newN bit-exact
+    assert pairs == [cand, acc]
+    np.testing.assert_allclose(gt, tao, rtol=1e-11, atol=0)  # far inside the 1e-5 bar: only the order of summation differs
+    return info
+
+
+def test_gather_filtered_kernel_bit_exact_newN(dh, oracle):
+    """Raytracer.h:139-159 incl. deposits exactly at distance^2 == searchR2 (strict '<', Q3) and == R2 ('<=')."""
+    rng = np.random.RandomState(7)
+    n, m = 6000, 20000
+    hp = dict(pos=np.stack([rng.uniform(0, 30, n), rng.uniform(0, 2, n), rng.uniform(0, 30, n)], axis=1),
+              wgt=rng.uniform(0.1, 1, size=(n, 3)), r2=rng.uniform(0.2, 2.0, size=n))
+    nrm = rng.normal(size=(n, 3))
+    hp["n"] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    x = np.stack([rng.uniform(-2, 32, m), rng.uniform(-1, 3, m), rng.uniform(-2, 32, m)], axis=1)
+    dn = rng.normal(size=(m, 3))
+    dn /= np.linalg.norm(dn, axis=1, keepdims=True)
+    flux = rng.uniform(0, 100, size=(m, 3))
+    hp["pos"][0], hp["r2"][0], hp["n"][0] = (10.0, 1.0, 10.0), 2.0, (0, 1, 0)
+    x[0] = (11.0, 2.0, 10.0)   # vv == 2.0 exactly -> excluded by the strict radius search
+    x[1] = (11.0, 1.0, 10.0)   # vv == 1.0 -> included
+    hp["pos"][1], hp["r2"][1], hp["n"][1] = (20.0, 1.0, 20.0), 1.0, (0, 1, 0)
+    x[2] = (21.0, 1.0, 20.0)   # vv == R2 exactly -> accepted ('<=')
+    dn[0] = dn[1] = dn[2] = (0, 1, 0)
+    info = _check_gather(dh, oracle, hp, x, dn, flux, min_acc=1000)
+    assert info["n_units"] >= info["n_occ"] // 40 and info["kept"] > m // 2
+
+
+def test_gather_filtered_kernel_threshold_band_adversarial(dh, oracle):
+    """Deposits at dist^2 = T(1+d) for T in {searchR2, R2}, |d| from 1e-16 to 1e-4 (both signs, and 0),
+    normals with n.N = 1e-3(1+d), coordinates near 150 where an FP32 ulp is 1.5e-5: the FP32
+    classification must fall back to FP64 inside its error bound, never misclassify."""
+    rng = np.random.RandomState(11)
+    n_hp, m = 3000, 60000
+    pos = np.stack([rng.uniform(120, 150, n_hp), rng.uniform(100, 103, n_hp), rng.uniform(130, 150, n_hp)], axis=1)
+    nrm = rng.normal(size=(n_hp, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    r2 = np.where(rng.uniform(size=n_hp) < 0.5, 2.0, rng.uniform(0.3, 2.0, size=n_hp))
+    hp = dict(pos=pos, n=nrm, wgt=rng.uniform(0.1, 1, size=(n_hp, 3)), r2=r2)
+    who = rng.randint(0, n_hp, m)
+    e = rng.normal(size=(m, 3))
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    delta = np.sign(rng.uniform(-1, 1, m)) * 10.0 ** rng.uniform(-16, -4, m)
+    delta[rng.uniform(size=m) < 0.05] = 0.0
+    T = np.where(rng.uniform(size=m) < 0.5, 2.0, r2[who])
+    x = pos[who] + e * np.sqrt(T * (1 + delta))[:, None]
+    t = np.cross(nrm[who], rng.normal(size=(m, 3)))
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    d2 = np.sign(rng.uniform(-1, 1, m)) * 10.0 ** rng.uniform(-16, -3, m)
+    cosv = np.where(rng.uniform(size=m) < 0.5, 1e-3 * (1 + d2), rng.uniform(0.2, 1.0, m))
+    dn = nrm[who] * cosv[:, None] + t * np.sqrt(1 - cosv ** 2)[:, None]
+    near = rng.uniform(size=m) < 0.3
+    x[near] = pos[who[near]] + e[near] * rng.uniform(0.1, 1.0, near.sum())[:, None]
+    _check_gather(dh, oracle, hp, x, dn, rng.uniform(0, 100, size=(m, 3)), min_acc=10000)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_gather_filtered_kernel_shapes_fuzz(dh, oracle, seed):
+    """Planar sheets, a sparse run along x, one cell with hundreds of hit points (units split every 64),
+    isolated points, thousands of deposits on a few cells (units cut into several work items, which
+    accumulate with atomics), deposits far outside the hit points' bounds, per-hit-point radii."""
+    rng = np.random.RandomState(100 + seed)
+    n_sheet = rng.randint(200, 4000)
+    parts = [np.stack([rng.uniform(0, 40, n_sheet), np.full(n_sheet, 3.0) + rng.normal(0, 1e-3, n_sheet), rng.uniform(0, 25, n_sheet)], 1)]
+    n_run = rng.randint(5, 80)
+    parts.append(np.stack([50 + 1.42 * np.arange(n_run) + rng.uniform(0, 0.3, n_run), np.full(n_run, 10.0), np.full(n_run, 5.0)], 1))
+    n_blob = rng.randint(70, 600)
+    parts.append(np.array([20.0, 20.0, 20.0]) + rng.uniform(-0.6, 0.6, size=(n_blob, 3)))
+    parts.append(rng.uniform(-30, 120, size=(rng.randint(1, 30), 3)))
+    pos = np.concatenate(parts)
+    n = pos.shape[0]
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[:n_sheet] = (0, 1, 0)
+    hp = dict(pos=pos, n=nrm, wgt=rng.uniform(0.1, 1, size=(n, 3)),
+              r2=np.where(rng.uniform(size=n) < 0.6, 2.0, rng.uniform(0.05, 2.0, size=n)))
+    m = rng.randint(2000, 60000)
+    x = pos[rng.randint(0, n, m)] + rng.normal(0, rng.choice([0.3, 1.0, 3.0]), size=(m, 3))
+    heavy = rng.randint(0, m, m // 3)
+    x[heavy] = np.array([20.0, 20.0, 20.0]) + rng.normal(0, 1.0, size=(heavy.size, 3))
+    x[: m // 50] = rng.uniform(-5000, 5000, size=(m // 50, 3))
+    dn = rng.normal(size=(m, 3))
+    dn /= np.linalg.norm(dn, axis=1, keepdims=True)
+    dn[rng.uniform(size=m) < 0.5] = (0, 1, 0)
+    info = _check_gather(dh, oracle, hp, x, dn, rng.uniform(0, 50, size=(m, 3)))
+    assert info["kept"] < m                      # the far deposits are not binned
+    if m > 12000:
+        assert info["n_items"] > info["n_units"] - info["n_occ"]  # some unit was cut into several work items
+
+
+def test_gather_filtered_kernel_out_of_range_normals_take_the_exact_path(dh, oracle):
+    """A deposit normal with a component above 1.0001 (not a unit vector: the ABI takes any deposit list)
+    voids the FP32 error bound; such a slice is evaluated in FP64 wholesale."""
+    rng = np.random.RandomState(5)
+    n, m = 800, 5000
+    hp = dict(pos=rng.uniform(0, 12, size=(n, 3)), wgt=rng.uniform(0.1, 1, size=(n, 3)), r2=np.full(n, 2.0))
+    nrm = rng.normal(size=(n, 3))
+    hp["n"] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    x = rng.uniform(-1, 13, size=(m, 3))
+    dn = rng.normal(size=(m, 3)) * 3.0           # |components| up to ~10
+    _check_gather(dh, oracle, hp, x, dn, rng.uniform(0, 10, size=(m, 3)))
+
+
+@pytest.mark.parametrize("name", ["cornell", "reference"])
+def test_photon_kernels_and_gather_kernel_reproduce_the_reference(dh, name):
+    """The whole device path on the CPU against the reference's own code: wavefront kernels -> deposits
+    -> grid + filtered gather kernel over the golden hit points == the newN the reference's PhotonTrace
+    + FLANN radius search accumulated over 300 photons (bit-exact), tao to rounding."""
+    g = np.load(os.path.join(GOLDEN, "ref_photon.npz"))
+    hp = {k: g[f"{name}_hp_{k}"] for k in ("pos", "n", "wgt", "r2")}
+    count = g[f"{name}_tot_newN"].shape[0]
+    dep, _, _ = dh.scene(_scene(name)).photon_trace_wavefront(_params(), 0, count, 5)
+    newN, tao, _, _ = dh.gather_filtered(hp, dep, float(hp["r2"].max()))
+    np.testing.assert_array_equal(newN, g[f"{name}_acc_newN"])
+    np.testing.assert_allclose(tao, g[f"{name}_acc_tao"], rtol=1e-12, atol=0)
+    assert newN.sum() > 50
