@@ -169,17 +169,19 @@ class Oracle:
         self.lib.orc_bezier_patch_batch(C.byref(d), C.byref(prm), _p(rays6), _p(patch_idx), n, _p(seeds_uv), _p(out))
         return out
 
-    def eye_pass(self, scene, prm, cam, pass_id=0):
+    def eye_pass(self, scene, prm, cam, pass_id=0, cap=None):
         d = self._desc(scene)
         cd = cam.desc() if isinstance(cam, Camera) else cam
-        cap = cd.w * cd.h * 4 + 1024
+        if cap is None:
+            cap = cd.w * cd.h * 4 + 1024
         pos3, n3, wgt3 = (np.zeros((cap, 3)) for _ in range(3))
         r2 = np.zeros(cap)
         pix = np.zeros((cap, 2), dtype=np.int32)
         node = np.zeros(cap, dtype=np.uint32)
         n = self.lib.orc_eye_pass(C.byref(d), C.byref(prm), C.byref(cd), pass_id, cap, _p(pos3), _p(n3), _p(wgt3), _p(r2),
                                   _p(pix), _p(node))
-        assert n <= cap
+        if n > cap:   # branching materials (Raytracer.h:312-335): the count is returned, trace again with room for it
+            return self.eye_pass(scene, prm, cam, pass_id, cap=n)
         return dict(pos=pos3[:n].copy(), n=n3[:n].copy(), wgt=wgt3[:n].copy(), r2=r2[:n].copy(), pix=pix[:n].copy(),
                     node=node[:n].copy())
 

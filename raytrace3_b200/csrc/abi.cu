@@ -392,22 +392,34 @@ int sppm_eye_pass_rows(sppm_ctx* c, const SppmCameraDesc* cam, uint64_t pass_id,
   const int64_t npix = (int64_t)cam->w * cam->h;
   if (append && (c->film_w != cam->w || c->film_h != cam->h || !c->hp_raw.p))
     return fail(c, SPPM_ERR_INVALID, "append: the film size differs from the hit points already traced");
-  c->hp_cap = npix * 4 + 1024;
+  // 4 hit points per pixel to start with (the shipped scene makes exactly one); a scene whose
+  // materials branch more (diffuse + mirror + glass on many objects: up to 2^14 per pixel,
+  // Raytracer.h:312-335) reports its true count through the counter, and a whole-film pass is then
+  // traced again into a buffer of that size (the pass is a function of the inputs alone).
+  const int64_t want_cap = npix * 4 + 1024;
+  if (!append || c->hp_cap < want_cap) c->hp_cap = want_cap;
   CU(c, dev_reserve(c->hp_raw, (size_t)c->hp_cap * sizeof(HpRaw)));
   c->film_w = cam->w;
   c->film_h = cam->h;
   c->index_ok = false;
-  if (!append) CU(c, cudaMemsetAsync(scalars(c), 0, 8, c->stream));
-  CU(c, cudaEventRecord(c->ev[4], c->stream));
-  CU(c, launch_eye_pass(c, *cam, pass_id, row_begin, row_end));
-  CU(c, cudaEventRecord(c->ev[5], c->stream));
   unsigned long long n = 0;
-  CU(c, cudaMemcpyAsync(&n, scalars(c), 8, cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  for (int attempt = 0;; attempt++) {
+    if (!append) CU(c, cudaMemsetAsync(scalars(c), 0, 8, c->stream));
+    CU(c, cudaEventRecord(c->ev[4], c->stream));
+    CU(c, launch_eye_pass(c, *cam, pass_id, row_begin, row_end));
+    CU(c, cudaEventRecord(c->ev[5], c->stream));
+    CU(c, cudaMemcpyAsync(&n, scalars(c), 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if ((int64_t)n <= c->hp_cap) break;
+    // appended row ranges share the buffer with the rows traced before: those cannot be re-made here
+    if (append || attempt > 0)
+      return fail(c, SPPM_ERR_CAPACITY, "hit-point buffer overflow (more than 4 hit points per pixel in a row-sharded eye pass)");
+    c->hp_cap = (int64_t)n + 1024;
+    CU(c, dev_reserve(c->hp_raw, (size_t)c->hp_cap * sizeof(HpRaw)));
+  }
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
   c->host_counters.ms_eye = ms;
-  if ((int64_t)n > c->hp_cap) return fail(c, SPPM_ERR_CAPACITY, "hit-point buffer overflow (more than 4 hit points per pixel)");
   c->n_hp = (int64_t)n;
   if (n_hitpoints) *n_hitpoints = c->n_hp;
   return SPPM_OK;

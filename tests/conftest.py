@@ -96,3 +96,14 @@ def quirks_scene():
     s.objvec[5].material = Material((.5, 0., .5), (.3, .3, .3), (0., 0., 0.), 1.5)
     s.objvec[2].material = Material((0., .7, .7), (0., 0., 0.), (0., 0., 0.), 1.5)
     return s
+
+
+def branching_scene():
+    """Eye paths that branch at most hits: diffuse + mirror + glass on the left and back walls and on two
+    spheres (Raytracer.h:312-335 takes all three branches) -> about 8 hit points per pixel, more than
+    the 4 per pixel the eye pass reserves up front (sppm_eye_pass_rows grows the buffer and traces again)."""
+    from raytrace3_b200.scene import Material, make_scene
+    s = make_scene("cornell", textures=None)
+    for i in (0, 2, 5, 6):
+        s.objvec[i].material = Material((.3, .3, .3), (.4, .4, .4), (.3, .3, .3), 1.5)
+    return s

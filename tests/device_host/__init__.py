@@ -141,15 +141,17 @@ class HostScene:
         return self.intersect_kernel(prm, rays6, ids, pass_id, node, cull)[0]
 
     # ---- the kernels of trace_kernels.cuh, launched as one-warp blocks
-    def eye_pass_kernel(self, prm, cam, pass_id=0, row_begin=0, row_end=None):
+    def eye_pass_kernel(self, prm, cam, pass_id=0, row_begin=0, row_end=None, cap=None):
         """eye_pass_kernel -> hit points in the canonical (pixel, node) order + counters."""
         cd = cam.desc() if hasattr(cam, "desc") else cam
         row_end = cd.h if row_end is None else row_end
-        cap = cd.w * cd.h * 4 + 1024
+        if cap is None:
+            cap = cd.w * cd.h * 4 + 1024
         out = np.zeros(cap, dtype=hpraw_dtype)
         cnt = np.zeros(len(COUNTERS), dtype=np.uint64)
         n = self.dh.lib.dh_eye_pass_kernel(self.h, C.byref(prm), C.byref(cd), pass_id, row_begin, row_end, cap, _p(out), _p(cnt))
-        assert n <= cap
+        if n > cap:   # as sppm_eye_pass_rows does: the counter holds the true count, trace again with room for it
+            return self.eye_pass_kernel(prm, cam, pass_id, row_begin, row_end, cap=n)
         out = out[:n]
         return out[np.argsort(out["okey"], kind="stable")], dict(zip(COUNTERS, cnt.tolist()))
 

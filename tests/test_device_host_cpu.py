@@ -380,6 +380,26 @@ def test_eye_pass_kernel_against_oracle(dh, oracle, name, w, h):
     assert np.array_equal(np.concatenate([a, b]), got)
 
 
+def test_eye_pass_kernel_branching_overflow(dh, oracle):
+    """About 8 hit points per pixel (conftest.branching_scene): the kernel reports the true count when its
+    buffer is too small (nothing is written past the capacity), and the second pass holds them all."""
+    from conftest import branching_scene
+    from raytrace3_b200.scene import reference_camera
+    sc = branching_scene()
+    hs = dh.scene(sc)
+    prm = _params()
+    w, h = 48, 36
+    cam = reference_camera(w, h)
+    ref = oracle.eye_pass(sc, prm, cam, pass_id=1)
+    assert ref["pos"].shape[0] > 4 * w * h + 1024
+    got, _ = hs.eye_pass_kernel(prm, cam, pass_id=1)
+    order = np.lexsort((ref["node"], ref["pix"][:, 0] * w + ref["pix"][:, 1]))
+    assert got.shape[0] == order.shape[0]
+    assert len(np.unique(got["okey"])) == got.shape[0]       # (pixel, node) identifies a hit point
+    for k in ("pos", "n", "wgt", "r2"):
+        np.testing.assert_array_equal(got[k], ref[k][order], err_msg=k)
+
+
 @pytest.mark.parametrize("name", ["custom", "quirks", "reference"])
 def test_eye_pass_kernel_golden_of_the_reference(dh, name):
     """The hit points the reference's OWN recursion produced (tests/golden/ref_*view_trace.npz)."""
@@ -631,3 +651,87 @@ def test_photon_kernels_and_gather_kernel_reproduce_the_reference(dh, name):
     np.testing.assert_array_equal(newN, g[f"{name}_acc_newN"])
     np.testing.assert_allclose(tao, g[f"{name}_acc_tao"], rtol=1e-12, atol=0)
     assert newN.sum() > 50
+
+
+# ---- random scenes ------------------------------------------------------------------------------
+def _random_scene(seed):
+    """Scenes the fixed ones never combine: oblique planes, spheres of any size (the light may sit inside
+    one), materials with any mix of diffuse / mirror / glass incl. zero channels and odd indices of
+    refraction, textures on any object, mirror / glass / textured teapots under random transforms."""
+    from raytrace3_b200.scene import (Bezier3Obj, Material, PlaneObj, Scene, SphereObj, SpotLight, Texture, teapot_patches)
+    rng = np.random.RandomState(1000 + seed)
+
+    branching = [rng.uniform() < 0.6]   # at most one object whose eye paths branch (mirror AND glass: 2^depth hit points)
+
+    def material(may_branch=False):
+        ch = lambda: tuple(float(v) for v in rng.choice([0.0, 0.0, 0.3, 0.6, 0.999], 3)) if rng.uniform() < 0.3 else \
+            (float(rng.uniform(0.1, 0.999)),) * 3
+        kind = rng.randint(0, 5)
+        if may_branch and branching[0]:
+            kind, branching[0] = 5, False
+        Z = (0.0, 0.0, 0.0)
+        d, s, r = [(ch(), Z, Z), (Z, ch(), Z), (Z, Z, ch()), (ch(), ch(), Z), (ch(), Z, ch()), (ch(), ch(), ch())][kind]
+        return Material(d, s, r, float(rng.choice([1.5, 1.33, 2.4, 0.8])))
+
+    def colour():
+        return tuple(float(v) for v in rng.uniform(0.2, 0.999, 3))
+
+    def texture():
+        return Texture(synthetic_texture(int(rng.randint(3, 90)), int(rng.randint(3, 90)), int(rng.randint(1 << 20))))
+
+    s = Scene()
+    s.objvec = []
+    walls = [((0, 40, 80), (1, 0, 0)), ((100, 40, 80), (1, 0, 0)), ((50, 40, 0), (0, 0, 1)), ((50, 0, 80), (0, -1, 0)),
+             ((50, 82, 80), (0, 1, 0)), ((50, 40, 230), (0, 0, -1))]
+    for p, nrm in walls:
+        if rng.uniform() < 0.85:
+            nrm = np.array(nrm, dtype=float)
+            if rng.uniform() < 0.4:
+                nrm = nrm + rng.normal(0, 0.25, 3)        # oblique: Obj.h:89-96 picks the texture axes by the last non-zero component
+            s.objvec.append(PlaneObj(p, tuple(nrm), colour(), material()))
+    for _ in range(rng.randint(1, 6)):
+        s.objvec.append(SphereObj(float(rng.uniform(2, 25)), tuple(rng.uniform((10, 5, 20), (90, 60, 200))), colour(), material(True)))
+    if rng.uniform() < 0.3:                               # a sphere around the light
+        s.objvec.append(SphereObj(float(rng.uniform(5, 40)), (50, 60, 85), colour(), material()))
+    tp = teapot_patches()
+    for _ in range(rng.randint(0, 3)):
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        s.objvec.append(Bezier3Obj(tuple(rng.uniform((15, 0, 40), (85, 40, 180))), float(rng.uniform(1.5, 5)), tp, colour(),
+                                   material(), q))
+    for o in s.objvec:
+        if rng.uniform() < 0.4:
+            o.setTexture(texture())
+    rng.shuffle(s.objvec)                                 # Scene::NearCollide: first object wins ties
+    s.plvec = [SpotLight((50, 60, 85), (5000., 4000., 3000.))]
+    if rng.uniform() < 0.4:
+        s.plvec.append(SpotLight(tuple(rng.uniform((10, 10, 20), (90, 70, 200))), (100., 2000., 900.)))
+    return s
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_scenes_eye_and_photon_kernels(dh, oracle, seed):
+    from raytrace3_b200.scene import reference_camera
+    sc = _random_scene(seed)
+    hs = dh.scene(sc)
+    prm = _params()
+    cam = reference_camera(80, 60)
+    ref = oracle.eye_pass(sc, prm, cam, pass_id=seed)
+    got, _ = hs.eye_pass_kernel(prm, cam, pass_id=seed)
+    order = np.lexsort((ref["node"], ref["pix"][:, 0] * 80 + ref["pix"][:, 1]))
+    assert got.shape[0] == order.shape[0]
+    np.testing.assert_array_equal(got["okey"] & np.uint64((1 << 20) - 1), ref["node"][order])
+    for k in ("pos", "n", "wgt", "r2"):
+        np.testing.assert_array_equal(got[k], ref[k][order], err_msg=k)
+    count = 3000
+    rp = oracle.photon_pass(sc, prm, 11, count, seed, keep_deposits=True)
+    rd = rp["dep"]
+    order = np.lexsort((rd["bounce"], rd["photon"]))
+    for name, (dep, cnt) in (("wavefront", hs.photon_trace_wavefront(prm, 11, count, seed)[:2]),
+                             ("persistent", hs.photon_trace_kernel(prm, 11, count, seed))):
+        assert cnt["deposits"] == rp["counters"]["deposits"], name
+        if name == "persistent":
+            assert cnt["patch_solves"] == rp["counters"]["solves"] and cnt["isect_queries"] == rp["counters"]["queries"]
+        else:   # the wavefront never issues the query past the depth limit, whose result nobody reads (Raytracer.h:129-132)
+            assert cnt["patch_solves"] <= rp["counters"]["solves"]
+        for k in ("photon", "bounce", "x", "n", "flux"):
+            np.testing.assert_array_equal(dep[k], rd[k][order], err_msg=f"{name} {k}")

@@ -1,0 +1,36 @@
+"""GPU eye pass on a scene whose eye paths branch at most hits (conftest.branching_scene): more hit
+points than the 4 per pixel sppm_eye_pass_rows reserves up front, so the pass is traced a second time
+into a buffer of the size the first one counted.  Written after the round's GPU budget was spent (first
+run by the round-end driver); the kernel itself is held to the oracle on this scene by the CPU
+emulation (tests/test_device_host_cpu.py::test_eye_pass_kernel_branching_overflow)."""
+import numpy as np
+import pytest
+
+from conftest import branching_scene
+from raytrace3_b200 import abi
+from raytrace3_b200.scene import reference_camera
+
+pytestmark = pytest.mark.gpu
+
+
+def test_eye_pass_grows_its_buffer(ctx, oracle):
+    sc = branching_scene()
+    prm = abi.default_params()
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    w, h = 48, 36
+    cam = reference_camera(w, h)
+    ref = oracle.eye_pass(sc, prm, cam, pass_id=1)
+    assert ref["pos"].shape[0] > 4 * w * h + 1024
+    n = ctx.eye_pass(cam, pass_id=1)
+    assert n == ref["pos"].shape[0]
+    ctx.build_index()
+    got = ctx.export_hitpoints()
+    order = np.lexsort((ref["node"], ref["pix"][:, 0] * w + ref["pix"][:, 1]))
+    np.testing.assert_array_equal(got["pix"], ref["pix"][order])
+    np.testing.assert_array_equal(got["node"], ref["node"][order])
+    np.testing.assert_array_equal(got["pos"], ref["pos"][order])
+    np.testing.assert_allclose(got["wgt"], ref["wgt"][order], rtol=1e-12, atol=0)
+    # and a smaller film afterwards still works (the buffer only ever grows)
+    n2 = ctx.eye_pass(reference_camera(16, 12), pass_id=1)
+    assert n2 == oracle.eye_pass(sc, prm, reference_camera(16, 12), pass_id=1)["pos"].shape[0]
