@@ -62,6 +62,14 @@ def cuda_include_dir() -> str:
     raise RuntimeError("cuda_runtime.h not found (CUDA_HOME)")
 
 
+# SPPM_DEVICE_HOST_SANITIZE=1: the same sources with -fsanitize=address,undefined (a memcheck of the kernel
+# bodies on the CPU; run python with LD_PRELOAD=libasan.so, see test_device_kernels_are_clean_under_asan_ubsan)
+SANITIZE = bool(os.environ.get("SPPM_DEVICE_HOST_SANITIZE"))
+if SANITIZE:
+    LIB_PATH = os.path.join(_HERE, "_build", "libdevice_host_asan.so")
+    CXXFLAGS = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] + CXXFLAGS[1:]
+
+
 def build(force: bool = False) -> str:
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in SOURCES)

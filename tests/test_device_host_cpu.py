@@ -735,3 +735,31 @@ def test_random_scenes_eye_and_photon_kernels(dh, oracle, seed):
             assert cnt["patch_solves"] <= rp["counters"]["solves"]
         for k in ("photon", "bounce", "x", "n", "flux"):
             np.testing.assert_array_equal(dep[k], rd[k][order], err_msg=f"{name} {k}")
+
+
+def test_device_kernels_are_clean_under_asan_ubsan():
+    """A memcheck of the kernel bodies without a GPU: the same emulation library built with
+    -fsanitize=address,undefined (SPPM_DEVICE_HOST_SANITIZE=1) runs a cross-section of this file — every
+    kernel of trace / wavefront / gather_kernels.cuh on several scenes — without a single report (global
+    and shared-memory bounds, alignment, shifts, signed overflow).  The whole file was run this way for
+    profiles/r1_K_device_host_asan.txt."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if os.environ.get("SPPM_DEVICE_HOST_SANITIZE"):
+        pytest.skip("already inside the sanitizer run")
+    asan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan.so not installed")
+    env = dict(os.environ, LD_PRELOAD=asan, SPPM_DEVICE_HOST_SANITIZE="1", UBSAN_OPTIONS="print_stacktrace=1",
+               ASAN_OPTIONS="detect_leaks=0:halt_on_error=1:detect_stack_use_after_return=0")
+    pick = ("intersect_kernel_golden or patch_batch or eye_pass_kernel_branching or eye_pass_kernel_golden or "
+            "(wavefront_kernels_against_oracle and (quirks or stress)) or photon_trace_kernel_golden or launch_invariant or "
+            "threshold_band or (shapes_fuzz and 0) or out_of_range_normals or reproduce_the_reference or "
+            "(random_scenes and (0 or 7)) or scene_tables or newton_culls")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-s", "-x", "-p", "no:cacheprovider",
+                        "-k", pick], capture_output=True, text=True, env=env, cwd=root, timeout=1500)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "runtime error" not in out and "ERROR: AddressSanitizer" not in out, out[-3000:]
+    assert " passed" in out
