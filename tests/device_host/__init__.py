@@ -2,7 +2,7 @@
 
 `DeviceHost()` builds (g++, a few seconds) and loads tests/device_host/_build/libdevice_host.so:
 raytrace3_b200/csrc/{device_math.cuh, scene.cuh, scene_prep.h, trace_kernels.cuh} through
-cuda_host_shim.h, with a warp emulated by 32 fibers and kernels launched as one-warp blocks.  It lets the `-m "not gpu"` suite hold the very source lines the
+cuda_host_shim.h, with a warp emulated by 32 fibers and kernels launched with the product's block sizes (or one-warp blocks).  It lets the `-m "not gpu"` suite hold the very source lines the
 sm_100a kernels are compiled from to the oracle.  Nothing in raytrace3_b200/ imports this."""
 from __future__ import annotations
 
@@ -246,7 +246,8 @@ class DeviceHost:
         L.dh_photon_trace_kernel.restype = I64
         L.dh_photon_trace_wavefront.argtypes = [VP, C.POINTER(abi.SppmParams), U64, U64, U64, C.c_int, C.c_int, I64, VP, VP, VP]
         L.dh_photon_trace_wavefront.restype = I64
-        L.dh_gather_filtered.argtypes = [I64, VP, C.POINTER(Grid), I64, VP, DBL, C.c_int, C.c_int, VP, VP, VP, VP, VP]
+        L.dh_gather_filtered.argtypes = [I64, VP, C.POINTER(Grid), I64, VP, DBL, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP]
+        L.dh_set_one_warp_blocks.argtypes = [C.c_int]
         L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
         L.dh_patch_batch_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, VP, C.c_int, VP]
         assert L.dh_sizeof_hpraw() == hpraw_dtype.itemsize and L.dh_sizeof_deposit() == deposit_dtype.itemsize
@@ -303,7 +304,7 @@ class DeviceHost:
         self.lib.dh_unit_rand_vec(seed, pass_id, ids.shape[0], _p(ids), purpose, _p(out))
         return out
 
-    def gather_filtered(self, hp, dep, search_r2, count_pairs=True, blocks=16):
+    def gather_filtered(self, hp, dep, search_r2, count_pairs=True, blocks=16, exact=False):
         """build_index + deposit binning + gather_filtered_kernel (the product's kernels; CUB's sorts and
         scans restated with std:: algorithms) -> newN [n], tao [n, 3] in the order of `hp`, info, pairs."""
         n, m = hp["pos"].shape[0], dep["x"].shape[0]
@@ -320,7 +321,7 @@ class DeviceHost:
         dtao = np.zeros((3, n))
         info = np.zeros(5, dtype=np.int64)
         pairs = np.zeros(2, dtype=np.uint64)
-        rc = self.lib.dh_gather_filtered(n, _p(raw), C.byref(g), m, _p(d), search_r2, int(count_pairs), blocks, _p(order),
+        rc = self.lib.dh_gather_filtered(n, _p(raw), C.byref(g), m, _p(d), search_r2, int(count_pairs), int(exact), blocks, _p(order),
                                          _p(dN), _p(dtao), _p(info), _p(pairs))
         assert rc == 0
         newN = np.zeros(n, dtype=np.int32)
@@ -328,6 +329,10 @@ class DeviceHost:
         newN[order] = dN
         tao[order] = dtao.T
         return newN, tao, dict(zip(("n_occ", "n_slots", "n_units", "n_items", "kept"), info.tolist())), pairs.tolist()
+
+    def one_warp_blocks(self, on: bool):
+        """Launch with one-warp blocks instead of the product's block sizes (a second schedule)."""
+        self.lib.dh_set_one_warp_blocks(int(on))
 
     def scene(self, scene) -> HostScene:
         return HostScene(self, scene)

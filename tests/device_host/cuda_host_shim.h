@@ -11,8 +11,10 @@
 // collectives are called convergently with the full mask, which is how scene.cuh calls all of its
 // collectives (and what the hardware requires of __syncwarp(FULL) anyway); a divergent collective
 // would deadlock or mis-pair here instead of passing silently.  Values are exchanged through a
-// 32-slot table between two such barriers.  One emulated block = one warp; several warps run on
-// several host threads.
+// 32-slot table between two such barriers.  A block of several warps is the same thing one level up:
+// __syncthreads hands over to the next thread of the block, and a warp is only ever left at a block
+// barrier or when it has finished.  One block at a time per host thread; blocks run on several host
+// threads.
 #pragma once
 #define SPPM_HOST_EMULATION 1
 
@@ -39,13 +41,15 @@ using std::min;
 struct DhDim {
   unsigned x = 0, y = 0, z = 0;
 };
-struct DhWarp {
+constexpr int DH_MAX_THREADS = 320;  // the largest block of the product (dep_scatter_kernel)
+struct DhWarp {  // one emulated thread block: n_threads fibers, warps of 32 consecutive threads
   ucontext_t main_ctx;
-  ucontext_t lane_ctx[32];
-  bool done[32];
-  int cur = 0;  // the lane that is running
-  unsigned block = 0, grid = 1;  // blockIdx.x / gridDim.x of the emulated one-warp block
-  uint64_t slot[32];
+  ucontext_t lane_ctx[DH_MAX_THREADS];
+  bool done[DH_MAX_THREADS];
+  int cur = 0;         // the thread that is running (threadIdx.x)
+  int n_threads = 32;  // blockDim.x, a multiple of 32
+  unsigned block = 0, grid = 1;  // blockIdx.x / gridDim.x
+  uint64_t slot[DH_MAX_THREADS];  // exchange table, 32 entries per warp
   unsigned long long barriers = 0;
 };
 extern thread_local DhWarp* dh_warp;  // null: a lone lane (collectives degenerate to one participant)
@@ -54,8 +58,13 @@ struct DhThreadIdx {
     operator unsigned() const { return dh_warp ? (unsigned)dh_warp->cur : 0u; }
   } x;
 };
+struct DhBlockDim {
+  struct X {
+    operator unsigned() const { return dh_warp ? (unsigned)dh_warp->n_threads : 1u; }
+  } x;
+};
 static const DhThreadIdx dh_thread_idx{};
-static const DhDim dh_block_dim_32{32, 1, 1};
+static const DhBlockDim dh_block_dim{};
 struct DhBlockIdx {
   struct X {
     operator unsigned() const { return dh_warp ? dh_warp->block : 0u; }
@@ -69,7 +78,7 @@ struct DhGridDim {
 static const DhBlockIdx dh_block_idx{};
 static const DhGridDim dh_grid_dim{};
 #define threadIdx dh_thread_idx
-#define blockDim dh_block_dim_32
+#define blockDim dh_block_dim
 #define blockIdx dh_block_idx
 #define gridDim dh_grid_dim
 // `extern __shared__ unsigned char smem[];` of a kernel = the emulating host thread's own array
@@ -80,11 +89,26 @@ static const DhGridDim dh_grid_dim{};
 #undef __shared__
 #define __shared__ thread_local
 
+// warp collective: hand over to the next lane of the same warp; when lane 31 arrives every lane of the
+// warp has, and lane 0 resumes behind the barrier
 inline void dh_barrier() {
   DhWarp* w = dh_warp;
   if (!w) return;
-  const int me = w->cur, next = (me + 1) & 31;
+  const int me = w->cur, next = (me & ~31) | ((me + 1) & 31);
   w->barriers += (me == 0);
+  w->cur = next;
+  swapcontext(&w->lane_ctx[me], &w->lane_ctx[next]);
+}
+// __syncthreads: hand over to the next thread of the block (a warp is only ever left at a block
+// barrier or when it has finished, so the other warps are parked at the previous block barrier or
+// have not started); when the last thread arrives thread 0 resumes
+inline void dh_block_barrier() {
+  DhWarp* w = dh_warp;
+  if (!w) return;
+  const int me = w->cur;
+  int next = me;
+  do next = (next + 1) % w->n_threads; while (w->done[next] && next != me);  // threads that exited count as arrived
+  if (next == me) return;
   w->cur = next;
   swapcontext(&w->lane_ctx[me], &w->lane_ctx[next]);
 }
@@ -94,22 +118,24 @@ inline T dh_exchange(T v, int src) {  // every lane publishes v, then reads lane
   if (!dh_warp) return v;
   uint64_t bits = 0;
   memcpy(&bits, &v, sizeof(T));
-  dh_warp->slot[dh_warp->cur] = bits;
+  const int me = dh_warp->cur;
+  dh_warp->slot[me] = bits;
   dh_barrier();
-  const uint64_t got = dh_warp->slot[src & 31];
+  const uint64_t got = dh_warp->slot[(me & ~31) | (src & 31)];
   dh_barrier();  // the table may be rewritten after everyone has read
   T out;
   memcpy(&out, &got, sizeof(T));
   return out;
 }
 inline void __syncwarp() { dh_barrier(); }
-inline void __syncthreads() { dh_barrier(); }
+inline void __syncthreads() { dh_block_barrier(); }
 inline unsigned __ballot_sync(unsigned, bool p) {
   if (!dh_warp) return p ? 1u : 0u;
-  dh_warp->slot[dh_warp->cur] = p ? 1 : 0;
+  const int me = dh_warp->cur;
+  dh_warp->slot[me] = p ? 1 : 0;
   dh_barrier();
   unsigned m = 0;
-  for (int l = 0; l < 32; l++) m |= (unsigned)dh_warp->slot[l] << l;
+  for (int l = 0; l < 32; l++) m |= (unsigned)dh_warp->slot[(me & ~31) | l] << l;
   dh_barrier();
   return m;
 }
@@ -119,11 +145,11 @@ template <class T>
 inline T __shfl_sync(unsigned, T v, int src) { return dh_exchange(v, src); }
 template <class T>
 inline T __shfl_up_sync(unsigned, T v, int delta) {  // lanes below delta keep their own value
-  const int me = dh_warp ? dh_warp->cur : 0;
+  const int me = dh_warp ? dh_warp->cur & 31 : 0;
   return dh_exchange(v, me >= delta ? me - delta : me);
 }
 template <class T>
-inline T __shfl_xor_sync(unsigned, T v, int off) { return dh_exchange(v, (dh_warp ? dh_warp->cur : 0) ^ off); }
+inline T __shfl_xor_sync(unsigned, T v, int off) { return dh_exchange(v, (dh_warp ? dh_warp->cur & 31 : 0) ^ off); }
 
 // ---- scalar intrinsics --------------------------------------------------------------------
 template <class T>

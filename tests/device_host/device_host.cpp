@@ -72,24 +72,38 @@ void fiber_entry() {
   const int me = w->cur;
   (*dh_fn)(me);
   w->done[me] = true;
-  // every lane passes the same barriers, so lane 0 ends first and the others wait behind the last one
-  const int next = (me + 1) & 31;
-  if (!w->done[next]) {
-    w->cur = next;
-    setcontext(&w->lane_ctx[next]);
+  // the lanes of a warp pass the same barriers, so lane 0 ends first and the others wait behind the
+  // warp's last barrier: finish the warp, then go on with the next warp that has not finished (parked
+  // at a block barrier, or not started)
+  for (int k = 1; k < 32; k++) {
+    const int next = (me & ~31) | ((me + k) & 31);
+    if (!w->done[next]) {
+      w->cur = next;
+      setcontext(&w->lane_ctx[next]);
+    }
+  }
+  for (int k = 1; k < w->n_threads; k++) {
+    const int next = (me + k) % w->n_threads;
+    if (!w->done[next]) {
+      w->cur = next;
+      setcontext(&w->lane_ctx[next]);
+    }
   }
   setcontext(&w->main_ctx);
 }
-unsigned long long run_warp(std::function<void(int)> f, unsigned block = 0, unsigned grid = 1) {
-  constexpr size_t STACK = 256 << 10;
-  struct Stacks {  // one set of lane stacks per host thread, reused by every block it emulates
-    char* p = (char*)malloc(32 * STACK);
+unsigned long long run_block(std::function<void(int)> f, int n_threads, unsigned block = 0, unsigned grid = 1) {
+  constexpr size_t STACK = 160 << 10;
+  struct Stacks {  // one set of thread stacks per host thread, reused by every block it emulates
+    char* p = (char*)malloc((size_t)DH_MAX_THREADS * STACK);
     ~Stacks() { free(p); }
   };
   static thread_local Stacks lane_stacks;
+  static thread_local DhWarp warp;  // ~300 KB of contexts: not on the stack
   char* stacks = lane_stacks.p;
-  DhWarp warp;
-  for (int l = 0; l < 32; l++) {
+  if (n_threads % 32 || n_threads > DH_MAX_THREADS) abort();
+  warp.n_threads = n_threads;
+  warp.barriers = 0;
+  for (int l = 0; l < n_threads; l++) {
     warp.done[l] = false;
     getcontext(&warp.lane_ctx[l]);
     warp.lane_ctx[l].uc_stack.ss_sp = stacks + (size_t)l * STACK;
@@ -105,18 +119,18 @@ unsigned long long run_warp(std::function<void(int)> f, unsigned block = 0, unsi
   swapcontext(&warp.main_ctx, &warp.lane_ctx[0]);
   dh_warp = nullptr;
   dh_fn = nullptr;
-  for (int l = 0; l < 32; l++)
+  for (int l = 0; l < n_threads; l++)
     if (!warp.done[l]) abort();  // a divergent collective
   return warp.barriers;
 }
 
-// kernel<<<blocks, 32, trace_smem>>>(args): one-warp blocks, handed out to host threads in order
+// kernel<<<blocks, threads, smem>>>(args): blocks handed out to host threads in order
 template <class K, class A>
 void call_kernel(K kernel, const A& args) { kernel(args); }
 template <class K, class... As>
 void call_kernel(K kernel, const std::tuple<As...>& args) { std::apply(kernel, args); }
 template <class K, class A>
-void launch(K kernel, const A& args, long long blocks) {
+void launch(K kernel, const A& args, long long blocks, int threads = 32) {
   if (blocks <= 0) return;
   const int T = (int)std::max<long long>(1, std::min<long long>(blocks, std::min(16u, std::max(1u, std::thread::hardware_concurrency()))));
   std::atomic<long long> next{0};
@@ -126,11 +140,16 @@ void launch(K kernel, const A& args, long long blocks) {
       for (;;) {
         const long long b = next.fetch_add(1);
         if (b >= blocks) break;
-        run_warp([&](int) { call_kernel(kernel, args); }, (unsigned)b, (unsigned)blocks);
+        run_block([&](int) { call_kernel(kernel, args); }, threads, (unsigned)b, (unsigned)blocks);
       }
     });
   for (auto& t : th) t.join();
 }
+
+// Block sizes: the product's own (TRACE_THREADS, STEP_THREADS, W_THREADS, TPB, 320) by default, or
+// one-warp blocks (dh_set_one_warp_blocks(1)), a second schedule every kernel but dep_scatter allows.
+int g_one_warp = 0;
+inline int bt(int product_threads) { return g_one_warp ? 32 : product_threads; }
 
 // make_common (trace.cu) for an emulated launch; patches staged in shared memory like the library
 // does whenever they fit (trace_configure)
@@ -138,7 +157,7 @@ TraceCommon common_of(DhScene* h, const SppmParams* prm, int cull, uint64_t pass
   TraceCommon t;
   t.scene = h->dev;
   t.ncfg = make_cfg(prm->newton_mode, prm->newton_restarts, prm->newton_iters, cull, prm->seed);
-  const size_t with = scene_smem_bytes(t.scene.n_obj, t.scene.n_patch, true) + sizeof(WarpScratch);
+  const size_t with = scene_smem_bytes(t.scene.n_obj, t.scene.n_patch, true) + TRACE_WARPS * sizeof(WarpScratch);
   t.patches_in_smem = with <= 100 * 1024 ? 1 : 0;
   t.max_dep = prm->max_dep;
   t.fast_math = prm->math_mode == SPPM_MATH_FAST ? 1 : 0;
@@ -333,7 +352,7 @@ int64_t dh_eye_pass_kernel(void* p, const SppmParams* prm, const SppmCameraDesc*
   a.pix_begin = (long long)row_begin * cam->w;
   a.pix_end = (long long)row_end * cam->w;
   const long long npix = a.pix_end - a.pix_begin;
-  if (npix > 0) launch(eye_pass_kernel, a, (npix + 31) / 32);
+  if (npix > 0) launch(eye_pass_kernel, a, (npix + bt(TRACE_THREADS) - 1) / bt(TRACE_THREADS), bt(TRACE_THREADS));
   if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
   return (int64_t)n_hp;
 }
@@ -361,7 +380,7 @@ int64_t dh_photon_trace_kernel(void* p, const SppmParams* prm, uint64_t begin, u
   a.cursor = &cursor;
   a.begin = begin;
   a.count = count;
-  launch(photon_trace_kernel, a, blocks);
+  launch(photon_trace_kernel, a, blocks, bt(TRACE_THREADS));
   if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
   return (int64_t)n_dep;
 }
@@ -377,7 +396,7 @@ void dh_intersect_kernel(void* p, const SppmParams* prm, int cull, int64_t n, co
   a.n = n;
   a.node = node;
   a.out = out;
-  if (n > 0) launch(intersect_kernel, a, (n + 31) / 32);
+  if (n > 0) launch(intersect_kernel, a, (n + bt(TRACE_THREADS) - 1) / bt(TRACE_THREADS), bt(TRACE_THREADS));
   if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
 }
 void dh_patch_batch_kernel(void* p, const SppmParams* prm, int cull, int64_t n, const double* rays6, const int32_t* patch,
@@ -392,7 +411,7 @@ void dh_patch_batch_kernel(void* p, const SppmParams* prm, int cull, int64_t n, 
   a.n = n;
   a.seeds = seeds;
   a.tuv = tuv;
-  if (n > 0) launch(patch_batch_kernel, a, blocks);
+  if (n > 0) launch(patch_batch_kernel, a, blocks, bt(TRACE_THREADS));
 }
 // launch_photon_trace_wavefront (wavefront.cu) with the product's own queue layout and per-bounce
 // arguments (wf_layout / wf_step_args / wf_newton_args): photon_step_kernel and newton_items_kernel
@@ -443,11 +462,11 @@ int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin
   for (int b = 0; b < n_steps; b++) {
     const StepArgs a = wf_step_args(w, L, b);
     long long blocks = step_blocks;
-    if (b == 0) blocks = std::min<long long>(blocks, (total + 31) / 32);
-    launch(photon_step_kernel, a, blocks);
+    if (b == 0) blocks = std::min<long long>(blocks, (total + bt(STEP_THREADS) - 1) / bt(STEP_THREADS));
+    launch(photon_step_kernel, a, blocks, bt(STEP_THREADS));
     if (a.do_intersect && h->dev.n_patch > 0) {
       const NewtonArgs n = wf_newton_args(w, L, a);
-      launch(newton_items_kernel, n, newton_blocks);
+      launch(newton_items_kernel, n, newton_blocks, bt(TRACE_THREADS));
     }
   }
   if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
@@ -458,21 +477,21 @@ int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin
 // The host orchestration is restated here with std:: algorithms in place of CUB (stable sort by cell
 // key, run-length encode, exclusive scans, flagged select); every kernel between them is the
 // product's: hp_key / hp_permute / mark_nbr / finalize_slot / run_flag / unit_count / unit_fill /
-// dep_key / unit_parts and gather_filtered_kernel<COUNT>.  (dep_scatter_kernel needs its 320-thread
-// blocks, so sorted[off[key] + rank] = raw is done here.)  raw = hit points in canonical order.
+// occ_run / dep_key / dep_scatter / unit_parts and gather_filtered_kernel<COUNT> or, with `exact`, the
+// all-FP64 gather_kernel (CTA per occupied cell).  raw = hit points in canonical order.
 // Outputs in the CELL-SORTED order of the hit-point map: order[i] = raw index of sorted hit point i,
 // dN[n], dtao[3][n]; info = {n_occ, n_slots, n_units, n_items, kept deposits}; pairs = {cand, acc}.
 int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m, const Deposit* dep_raw, double search_r2,
-                       int count_pairs, int blocks, uint32_t* order, int32_t* dN, double* dtao, int64_t* info,
+                       int count_pairs, int exact, int blocks, uint32_t* order, int32_t* dN, double* dtao, int64_t* info,
                        uint64_t* pairs) {
   const Grid g = *grid;
   if (n <= 0) return -1;
-  const int T = 32;
+  const int T = bt(TPB);
   auto nb = [&](long long k) { return (k + T - 1) / T; };
   // hit points: cell keys, stable sort, SoA permute
   std::vector<uint32_t> iota((size_t)n), key((size_t)n), idx((size_t)n), skey((size_t)n);
   std::iota(iota.begin(), iota.end(), 0u);
-  launch(hp_key_kernel, std::make_tuple(raw, (const uint32_t*)iota.data(), (long long)n, g, key.data()), nb(n));
+  launch(hp_key_kernel, std::make_tuple(raw, (const uint32_t*)iota.data(), (long long)n, g, key.data()), nb(n), T);
   idx = iota;
   std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
   for (int64_t i = 0; i < n; i++) skey[(size_t)i] = key[idx[(size_t)i]];
@@ -487,7 +506,7 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   s.okey = okey.data();
   int32_t* ip = istore.data();
   s.N = ip; s.newN = ip + nd; s.dN = ip + 2 * nd; s.row = ip + 3 * nd; s.col = ip + 4 * nd;
-  launch(hp_permute_kernel, std::make_tuple(raw, (const uint32_t*)idx.data(), (long long)n, s), nb(n));
+  launch(hp_permute_kernel, std::make_tuple(raw, (const uint32_t*)idx.data(), (long long)n, s), nb(n), T);
   // occupied cells and their hit-point ranges
   std::vector<uint32_t> occ_cell;
   std::vector<int32_t> occ_start;
@@ -500,43 +519,49 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   occ_start.push_back((int32_t)n);
   // compact slots of the cells whose 27-neighbourhood holds a hit point
   std::vector<int32_t> cell_slot((size_t)g.n_cells, 0), scan((size_t)g.n_cells);
-  launch(mark_nbr_kernel, std::make_tuple((const uint32_t*)occ_cell.data(), n_occ, g, cell_slot.data()), nb((long long)n_occ * 27));
+  launch(mark_nbr_kernel, std::make_tuple((const uint32_t*)occ_cell.data(), n_occ, g, cell_slot.data()), nb((long long)n_occ * 27), T);
   std::exclusive_scan(cell_slot.begin(), cell_slot.end(), scan.begin(), 0);
   int32_t n_slots = 0;
   launch(finalize_slot_kernel, std::make_tuple(cell_slot.data(), (const int32_t*)scan.data(), (long long)g.n_cells, &n_slots),
-         nb(g.n_cells));
+         nb(g.n_cells), T);
+  std::vector<int2> occ_run((size_t)n_occ * 9);
+  launch(occ_run_kernel, std::make_tuple((const uint32_t*)occ_cell.data(), n_occ, g, (const int32_t*)cell_slot.data(), occ_run.data()),
+         nb((long long)n_occ * 9), T);
   // work units
   std::vector<int32_t> flag((size_t)n_occ), run_first, ucnt((size_t)n_occ + 1, 0), uoff((size_t)n_occ + 1);
-  launch(run_flag_kernel, std::make_tuple((const uint32_t*)occ_cell.data(), n_occ, g.dim[0], flag.data()), nb(n_occ));
+  launch(run_flag_kernel, std::make_tuple((const uint32_t*)occ_cell.data(), n_occ, g.dim[0], flag.data()), nb(n_occ), T);
   for (int o = 0; o < n_occ; o++)
     if (flag[(size_t)o]) run_first.push_back(o);
   int32_t n_runs = (int32_t)run_first.size();
   run_first.resize((size_t)n_occ + 1, 0);
   launch(unit_count_kernel, std::make_tuple((const int32_t*)run_first.data(), (const int32_t*)&n_runs, n_occ,
-                                            (const int32_t*)occ_start.data(), ucnt.data()), nb(n_occ));
+                                            (const int32_t*)occ_start.data(), ucnt.data()), nb(n_occ), T);
   std::exclusive_scan(ucnt.begin(), ucnt.end(), uoff.begin(), 0);
   const int n_units = uoff[(size_t)n_occ];
   std::vector<GUnit> units((size_t)std::max(n_units, 1));
   launch(unit_fill_kernel, std::make_tuple((const int32_t*)run_first.data(), (const int32_t*)&n_runs, n_occ,
                                            (const int32_t*)occ_start.data(), (const uint32_t*)occ_cell.data(),
-                                           (const int32_t*)uoff.data(), g, (const int32_t*)cell_slot.data(), units.data()), nb(n_occ));
+                                           (const int32_t*)uoff.data(), g, (const int32_t*)cell_slot.data(), units.data()), nb(n_occ), T);
   // deposits: slot key + arrival rank, CSR offsets, scatter (key n_slots = not kept)
   std::vector<uint32_t> dkey((size_t)std::max<int64_t>(m, 1)), drank((size_t)std::max<int64_t>(m, 1));
   std::vector<unsigned int> slot_count((size_t)n_slots + 2, 0);
   std::vector<int32_t> dep_off((size_t)n_slots + 2);
   if (m > 0)
     launch(dep_key_kernel, std::make_tuple(dep_raw, (long long)m, g, (const int32_t*)cell_slot.data(), n_slots, dkey.data(),
-                                           drank.data(), slot_count.data()), nb(m));
+                                           drank.data(), slot_count.data()), nb(m), T);
   std::exclusive_scan(slot_count.begin(), slot_count.end(), dep_off.begin(), 0);
   std::vector<Deposit> sorted((size_t)std::max<int64_t>(m, 1));
   {
     // arrival ranks depend on the order the emulated blocks ran in; any order is a valid counting sort
-    for (int64_t i = 0; i < m; i++) sorted[(size_t)(dep_off[dkey[(size_t)i]] + (int32_t)drank[(size_t)i])] = dep_raw[i];
+    const unsigned long long m_dev = (unsigned long long)m;
+    if (m > 0)
+      launch(dep_scatter_kernel, std::make_tuple(dep_raw, (const uint32_t*)dkey.data(), (const uint32_t*)drank.data(), &m_dev,
+                                                 (unsigned long long)m, (const int32_t*)dep_off.data(), sorted.data()), 12, 320);
   }
   // work items of the batch and the gather
   std::vector<int32_t> parts((size_t)n_units + 1), item_off((size_t)n_units + 1);
   launch(unit_parts_kernel, std::make_tuple((const GUnit*)units.data(), n_units, (const int32_t*)dep_off.data(), parts.data()),
-         nb(n_units + 1));
+         nb(n_units + 1), T);
   std::exclusive_scan(parts.begin(), parts.end(), item_off.begin(), 0);
   DevCounters cnt;
   memset(&cnt, 0, sizeof(cnt));
@@ -545,7 +570,7 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   a.s = s;
   a.n_hp = n;
   a.occ_start = occ_start.data();
-  a.occ_run = nullptr;  // exact kernel only
+  a.occ_run = occ_run.data();  // exact kernel only
   a.n_occ = n_occ;
   a.dep_off = dep_off.data();
   a.dep = sorted.data();
@@ -558,8 +583,9 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   a.item_off = item_off.data();
   unsigned int work_counter = 0;
   if (n_units > 0) {
-    if (count_pairs) launch(gather_filtered_kernel<true>, std::make_tuple(a, &work_counter), blocks);
-    else launch(gather_filtered_kernel<false>, std::make_tuple(a, &work_counter), blocks);
+    if (exact) launch(gather_kernel, std::make_tuple(a, &work_counter), std::min(blocks, n_occ), G_THREADS);
+    else if (count_pairs) launch(gather_filtered_kernel<true>, std::make_tuple(a, &work_counter), blocks, bt(W_THREADS));
+    else launch(gather_filtered_kernel<false>, std::make_tuple(a, &work_counter), blocks, bt(W_THREADS));
   }
   memcpy(order, idx.data(), nd * 4);
   memcpy(dN, s.dN, nd * 4);
@@ -568,6 +594,7 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   pairs[0] = cnt.cand_pairs; pairs[1] = cnt.acc_pairs;
   return 0;
 }
+void dh_set_one_warp_blocks(int on) { g_one_warp = on ? 1 : 0; }
 int dh_sizeof_hpraw() { return (int)sizeof(HpRaw); }
 int dh_sizeof_deposit() { return (int)sizeof(Deposit); }
 

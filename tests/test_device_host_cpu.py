@@ -531,13 +531,15 @@ def test_wavefront_equals_persistent_on_the_cpu(dh):
 # and gather_filtered_kernel run as one-warp blocks; CUB's sorts / scans are std:: algorithms in the
 # harness.  The inputs are those of the GPU tests of the same names (tests/test_gpu_parity.py).
 def _check_gather(dh, oracle, hp, x, dn, flux, search_r2=2.0, min_acc=100):
+    """FILTERED (default) and EXACT gather kernels against the exhaustive search."""
     dep = dict(x=x, n=dn, flux=flux)
     newN, tao, cand, acc = oracle.gather_brute(hp, dep, search_r2)
-    gn, gt, info, pairs = dh.gather_filtered(hp, dep, search_r2)
     assert newN.sum() > min_acc
-    np.testing.assert_array_equal(gn, newN)                 # level 2: newN bit-exact
-    assert pairs == [cand, acc]
-    np.testing.assert_allclose(gt, tao, rtol=1e-11, atol=0)  # far inside the 1e-5 bar: only the order of summation differs
+    for exact in (False, True):
+        gn, gt, info, pairs = dh.gather_filtered(hp, dep, search_r2, exact=exact)
+        np.testing.assert_array_equal(gn, newN)                 # level 2: newN bit-exact
+        assert pairs == [cand, acc], exact
+        np.testing.assert_allclose(gt, tao, rtol=1e-11, atol=0)  # far inside the 1e-5 bar: only the order of summation differs
     return info
 
 
@@ -735,6 +737,36 @@ def test_random_scenes_eye_and_photon_kernels(dh, oracle, seed):
             assert cnt["patch_solves"] <= rp["counters"]["solves"]
         for k in ("photon", "bounce", "x", "n", "flux"):
             np.testing.assert_array_equal(dep[k], rd[k][order], err_msg=f"{name} {k}")
+
+
+def test_one_warp_blocks_give_the_same_results(dh, oracle):
+    """The tests above launch the kernels with the product's block sizes (128-thread trace / step blocks,
+    256-thread gather blocks, 320-thread scatter); one-warp blocks are a second schedule of the same
+    work (other warp-to-work assignment, other arrival order of the deposits)."""
+    sc = _scene("quirks")
+    hs = dh.scene(sc)
+    prm = _params()
+    from raytrace3_b200.scene import reference_camera
+    cam = reference_camera(96, 72)
+    eye, _ = hs.eye_pass_kernel(prm, cam, pass_id=2)
+    dep, cnt, _ = hs.photon_trace_wavefront(prm, 5, 8000, 2)
+    hp = dict(pos=eye["pos"], n=eye["n"], wgt=eye["wgt"], r2=eye["r2"])
+    newN, tao, _, pairs = dh.gather_filtered(hp, dep, 2.0)
+    dh.one_warp_blocks(True)
+    try:
+        eye1, _ = hs.eye_pass_kernel(prm, cam, pass_id=2)
+        dep1, cnt1, _ = hs.photon_trace_wavefront(prm, 5, 8000, 2)
+        per1, _ = hs.photon_trace_kernel(prm, 5, 8000, 2)
+        newN1, tao1, _, pairs1 = dh.gather_filtered(hp, dep, 2.0)
+    finally:
+        dh.one_warp_blocks(False)
+    assert np.array_equal(eye, eye1) and cnt == cnt1 and pairs == pairs1
+    for k in dep:
+        np.testing.assert_array_equal(dep[k], dep1[k], err_msg=k)
+        np.testing.assert_array_equal(dep[k], per1[k], err_msg=k)
+    np.testing.assert_array_equal(newN, newN1)
+    np.testing.assert_allclose(tao, tao1, rtol=1e-12, atol=0)
+    assert newN.sum() > 1000
 
 
 def test_device_kernels_are_clean_under_asan_ubsan():
