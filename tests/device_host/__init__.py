@@ -248,6 +248,7 @@ class DeviceHost:
         L.dh_photon_trace_wavefront.restype = I64
         L.dh_gather_filtered.argtypes = [I64, VP, C.POINTER(Grid), I64, VP, DBL, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP]
         L.dh_set_one_warp_blocks.argtypes = [C.c_int]
+        L.dh_update_resolve.argtypes = [I64, C.c_int, DBL, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, VP]
         L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
         L.dh_patch_batch_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, VP, C.c_int, VP]
         assert L.dh_sizeof_hpraw() == hpraw_dtype.itemsize and L.dh_sizeof_deposit() == deposit_dtype.itemsize
@@ -329,6 +330,17 @@ class DeviceHost:
         newN[order] = dN
         tao[order] = dtao.T
         return newN, tao, dict(zip(("n_occ", "n_slots", "n_units", "n_items", "kept"), info.tolist())), pairs.tolist()
+
+    def update_resolve(self, mode, alpha, N, newN, dN, r2, tao, dtao, pix, cnt, onetime, w, h, rounds=1):
+        """update_kernel x rounds, then resolve_kernel; tao / dtao [n, 3].  In place on N, newN, r2; returns
+        (tao [n, 3], film [h, w, 3])."""
+        n = N.shape[0]
+        t, dt = np.ascontiguousarray(tao.T), np.ascontiguousarray(dtao.T)
+        row, col = np.ascontiguousarray(pix[:, 0], dtype=np.int32), np.ascontiguousarray(pix[:, 1], dtype=np.int32)
+        film = np.zeros((h, w, 3))
+        self.lib.dh_update_resolve(n, mode, alpha, rounds, _p(N), _p(newN), _p(dN), _p(r2), _p(t), _p(dt), _p(row), _p(col),
+                                   cnt, onetime, w, _p(film))
+        return np.ascontiguousarray(t.T), film
 
     def one_warp_blocks(self, on: bool):
         """Launch with one-warp blocks instead of the product's block sizes (a second schedule)."""

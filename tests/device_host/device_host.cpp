@@ -594,6 +594,20 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   pairs[0] = cnt.cand_pairs; pairs[1] = cnt.acc_pairs;
   return 0;
 }
+// update_kernel (HitPoint::update, Raytracer.h:69-79, on the round's accumulators) and resolve_kernel
+// (Raytracer.h:281-293) over caller-owned structure-of-arrays; tao / dtao are [3][n], film is [h][w][3]
+// (zeroed by the caller).  rounds = how many update launches (each folds dN / dtao, given once).
+void dh_update_resolve(int64_t n, int mode, double alpha, int rounds, int32_t* N, int32_t* newN, int32_t* dN, double* r2,
+                       double* tao, double* dtao, const int32_t* row, const int32_t* col, int cnt, int onetime, int w,
+                       double* film) {
+  HpSoA s;
+  memset(&s, 0, sizeof(s));
+  s.N = N; s.newN = newN; s.dN = dN; s.r2 = r2; s.tao = tao; s.dtao = dtao;
+  s.row = const_cast<int32_t*>(row); s.col = const_cast<int32_t*>(col);
+  const int T = bt(TPB);
+  for (int k = 0; k < rounds; k++) launch(update_kernel, std::make_tuple(s, (long long)n, mode, alpha), (n + T - 1) / T, T);
+  if (film) launch(resolve_kernel, std::make_tuple(s, (long long)n, cnt, onetime, w, film), (n + T - 1) / T, T);
+}
 void dh_set_one_warp_blocks(int on) { g_one_warp = on ? 1 : 0; }
 int dh_sizeof_hpraw() { return (int)sizeof(HpRaw); }
 int dh_sizeof_deposit() { return (int)sizeof(Deposit); }

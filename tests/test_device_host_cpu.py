@@ -739,6 +739,35 @@ def test_random_scenes_eye_and_photon_kernels(dh, oracle, seed):
             np.testing.assert_array_equal(dep[k], rd[k][order], err_msg=f"{name} {k}")
 
 
+@pytest.mark.parametrize("mode", [abi.SPPM_UPDATE_REFERENCE, abi.SPPM_UPDATE_PROGRESSIVE])
+def test_update_and_resolve_kernels(dh, oracle, mode):
+    """update_kernel == HitPoint::update (Raytracer.h:69-79: the shipped no-op while N == 0 (Q1), the
+    progressive radius / flux shrink with the int truncation of N) and resolve_kernel == the film
+    expression of Raytracer.h:281-293, three rounds of fresh accumulators."""
+    rng = np.random.RandomState(31)
+    n, w, h = 5000, 40, 30
+    N, newN = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    N[: n // 2] = rng.randint(0, 50, n // 2)             # REFERENCE mode only acts where N > 0
+    r2, tao = rng.uniform(0.2, 2.0, n), np.zeros((n, 3))
+    pix = np.stack([rng.randint(0, h, n), rng.randint(0, w, n)], axis=1).astype(np.int32)
+    oN, onewN, or2, otao = N.copy(), newN.copy(), r2.copy(), tao.copy()
+    for _ in range(3):
+        dN = rng.randint(0, 4, n).astype(np.int32)
+        dtao = rng.uniform(0, 10, size=(n, 3)) * (dN > 0)[:, None]
+        onewN += dN                                      # the round's accumulators, then HitPoint::update
+        otao += dtao
+        oracle.update(mode, 0.7, onewN, oN, or2, otao)
+        tao, film = dh.update_resolve(mode, 0.7, N, newN, dN, r2, tao, dtao, pix, 3, 1000, w, h)   # zeroes dN / dtao
+        assert not dN.any()
+    np.testing.assert_array_equal(N, oN)
+    np.testing.assert_array_equal(newN, onewN)
+    np.testing.assert_array_equal(r2, or2)
+    np.testing.assert_array_equal(tao, otao)
+    want = oracle.resolve(pix, or2, otao, 3, 1000, w, h)
+    np.testing.assert_allclose(film, want, rtol=1e-13, atol=0)   # several hit points per pixel: order of the adds
+    assert (N != 0).any() and film.sum() > 0
+
+
 def test_one_warp_blocks_give_the_same_results(dh, oracle):
     """The tests above launch the kernels with the product's block sizes (128-thread trace / step blocks,
     256-thread gather blocks, 320-thread scatter); one-warp blocks are a second schedule of the same
