@@ -82,7 +82,7 @@ int check_overflow(sppm_ctx* c) {
       bool ovf = false;
       cudaError_t e = wavefront_overflowed(c, L, &ovf);
       if (e) return cuda_fail(c, e, "wavefront_overflowed");
-      if (ovf) return fail(c, SPPM_ERR_CAPACITY, "Bezier work-item list overflow (more than 2 (ray, patch) items per photon in one bounce)");
+      if (ovf) return fail(c, SPPM_ERR_CAPACITY, "Bezier work-item list overflow (more than 2 (ray, patch) items per photon in one bounce); SppmParams.trace_mode = SPPM_TRACE_PERSISTENT has no such list");
     }
   }
   return SPPM_OK;
