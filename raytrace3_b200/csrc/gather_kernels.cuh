@@ -697,6 +697,18 @@ __device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const 
 #ifndef SPPM_GATHER_MINBLOCKS
 #define SPPM_GATHER_MINBLOCKS 2
 #endif
+// Algorithmic work counters of the filtered gather (tools/gather_work_model.py): they exist in the CPU
+// emulation of tests/device_host only and expand to nothing in the library.
+#ifdef SPPM_HOST_EMULATION
+enum { WK_ITEMS, WK_SLICES, WK_VISITS, WK_KEPT, WK_PAIRS, WK_PAIR_SLOTS, WK_REDO_LANES, WK_N };
+extern unsigned long long dh_work[WK_N];
+#define SPPM_WORK(k, v)                                                                          \
+  do {                                                                                           \
+    if (lane == 0) __atomic_fetch_add(&dh_work[k], (unsigned long long)(v), __ATOMIC_RELAXED);   \
+  } while (0)
+#else
+#define SPPM_WORK(k, v) ((void)0)
+#endif
 template <bool COUNT>
 __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filtered_kernel(const GatherArgs a, unsigned int* work_counter) {
   extern __shared__ __align__(128) unsigned char wsm[];
@@ -770,6 +782,7 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
       __syncwarp();
     }
     if (D == 0) continue;
+    SPPM_WORK(WK_ITEMS, 1);
     constexpr int ITEM_SLICES = ITEM_DEP / W_SLICE;
     const int sl0 = part * ITEM_SLICES;  // this item: slices [sl0, sl0 + n_sl) of the concatenation
     const int n_sl = min(ITEM_SLICES, (D + W_SLICE - 1) / W_SLICE - sl0);
@@ -901,6 +914,11 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
         n_k += __popc(kmask);
       }
       const bool any_badn = __any_sync(FULL, badn);
+      SPPM_WORK(WK_SLICES, 1);
+      SPPM_WORK(WK_VISITS, fill);
+      SPPM_WORK(WK_KEPT, n_k);
+      SPPM_WORK(WK_PAIRS, (long long)n_k * H);
+      SPPM_WORK(WK_PAIR_SLOTS, (long long)((n_k + 1) & ~1) * (two ? 64 : hl));
       if (lane == 0 && (n_k & 1)) {  // pad the last pair
         float4* pr = conv + (n_k >> 1) * F_PAIR_F4;
         float* f = reinterpret_cast<float*>(pr) + 1;
@@ -933,6 +951,12 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
           redo[b] = valid[b] && (any_badn || far_hp[b] || !(uv[b] > hp[b].band) || !(un2[b] > SPPM_F_NBAND));
           any_redo = any_redo || redo[b];
         }
+#ifdef SPPM_HOST_EMULATION
+        {
+          const unsigned redo_mask = __ballot_sync(FULL, any_redo);
+          SPPM_WORK(WK_REDO_LANES, __popc(redo_mask));
+        }
+#endif
         if (any_redo) {
           // the fast counters of this lane cover both hit points: recount them exactly
           unsigned cd_x = 0;

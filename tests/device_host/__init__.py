@@ -70,6 +70,15 @@ if SANITIZE:
     CXXFLAGS = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"] + CXXFLAGS[1:]
 
 
+# SPPM_DEVICE_HOST_EXTRA="-DSPPM_UNIT_HP=32 ...": the library's compile-time knobs (SPPM_NVCC_EXTRA of raytrace3_b200/build.py)
+# for the emulation, in a library of its own (tools/gather_work_model.py compares them)
+EXTRA = os.environ.get("SPPM_DEVICE_HOST_EXTRA", "").split()
+if EXTRA:
+    import hashlib
+    LIB_PATH = LIB_PATH.replace(".so", "_" + hashlib.md5(" ".join(EXTRA).encode()).hexdigest()[:8] + ".so")
+    CXXFLAGS = CXXFLAGS + EXTRA
+
+
 def build(force: bool = False) -> str:
     stale = force or not os.path.exists(LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in SOURCES)
@@ -248,6 +257,7 @@ class DeviceHost:
         L.dh_photon_trace_wavefront.restype = I64
         L.dh_gather_filtered.argtypes = [I64, VP, C.POINTER(Grid), I64, VP, DBL, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP]
         L.dh_set_one_warp_blocks.argtypes = [C.c_int]
+        L.dh_work_read.argtypes = [VP, C.c_int]
         L.dh_update_resolve.argtypes = [I64, C.c_int, DBL, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, VP]
         L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
         L.dh_patch_batch_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, VP, C.c_int, VP]
@@ -341,6 +351,14 @@ class DeviceHost:
         self.lib.dh_update_resolve(n, mode, alpha, rounds, _p(N), _p(newN), _p(dN), _p(r2), _p(t), _p(dt), _p(row), _p(col),
                                    cnt, onetime, w, _p(film))
         return np.ascontiguousarray(t.T), film
+
+    WORK = ("items", "slices", "visits", "kept", "pairs", "pair_slots", "redo_lanes")
+
+    def gather_work(self, reset=True):
+        """Algorithmic work counters of gather_filtered_kernel since the last reset (emulation only)."""
+        out = np.zeros(len(self.WORK), dtype=np.uint64)
+        self.lib.dh_work_read(_p(out), int(reset))
+        return dict(zip(self.WORK, out.tolist()))
 
     def one_warp_blocks(self, on: bool):
         """Launch with one-warp blocks instead of the product's block sizes (a second schedule)."""

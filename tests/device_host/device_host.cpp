@@ -30,6 +30,11 @@ alignas(128) thread_local unsigned char wsm[64 << 10];    // gather_filtered_ker
 #include "../../raytrace3_b200/csrc/trace_kernels.cuh"
 #include "../../raytrace3_b200/csrc/wavefront_kernels.cuh"
 #include "../../raytrace3_b200/csrc/gather_kernels.cuh"
+namespace sppm {
+namespace {
+unsigned long long dh_work[WK_N] = {};  // SPPM_WORK counters of gather_filtered_kernel
+}
+}  // namespace sppm
 
 thread_local DhWarp* dh_warp = nullptr;
 
@@ -607,6 +612,14 @@ void dh_update_resolve(int64_t n, int mode, double alpha, int rounds, int32_t* N
   const int T = bt(TPB);
   for (int k = 0; k < rounds; k++) launch(update_kernel, std::make_tuple(s, (long long)n, mode, alpha), (n + T - 1) / T, T);
   if (film) launch(resolve_kernel, std::make_tuple(s, (long long)n, cnt, onetime, w, film), (n + T - 1) / T, T);
+}
+// items, slices, deposit visits, deposits kept by the cull, (hit point, deposit) pairs classified, pair slots
+// issued (padding and idle lanes included), lanes that repeated a slice on the careful path
+void dh_work_read(uint64_t* out7, int reset) {
+  for (int k = 0; k < WK_N; k++) {
+    out7[k] = dh_work[k];
+    if (reset) dh_work[k] = 0;
+  }
 }
 void dh_set_one_warp_blocks(int on) { g_one_warp = on ? 1 : 0; }
 int dh_sizeof_hpraw() { return (int)sizeof(HpRaw); }
