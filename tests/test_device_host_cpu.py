@@ -814,10 +814,10 @@ def test_device_kernels_are_clean_under_asan_ubsan():
         pytest.skip("libasan.so not installed")
     env = dict(os.environ, LD_PRELOAD=asan, SPPM_DEVICE_HOST_SANITIZE="1", UBSAN_OPTIONS="print_stacktrace=1",
                ASAN_OPTIONS="detect_leaks=0:halt_on_error=1:detect_stack_use_after_return=0")
-    pick = ("intersect_kernel_golden or patch_batch or eye_pass_kernel_branching or eye_pass_kernel_golden or "
-            "(wavefront_kernels_against_oracle and (quirks or stress)) or photon_trace_kernel_golden or launch_invariant or "
-            "threshold_band or (shapes_fuzz and 0) or out_of_range_normals or reproduce_the_reference or "
-            "(random_scenes and (0 or 7)) or scene_tables or newton_culls")
+    pick = ("intersect_kernel_golden or patch_batch or eye_pass_kernel_branching or "
+            "(wavefront_kernels_against_oracle and stress) or (photon_trace_kernel_golden and quirks) or launch_invariant or "
+            "(shapes_fuzz and 0) or out_of_range_normals or (reproduce_the_reference and cornell) or "
+            "(random_scenes and 7) or update_and_resolve")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-s", "-x", "-p", "no:cacheprovider",
                         "-k", pick], capture_output=True, text=True, env=env, cwd=root, timeout=1500)
     out = r.stdout + r.stderr
