@@ -258,6 +258,7 @@ class DeviceHost:
         L.dh_gather_filtered.argtypes = [I64, VP, C.POINTER(Grid), I64, VP, DBL, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP]
         L.dh_set_one_warp_blocks.argtypes = [C.c_int]
         L.dh_work_read.argtypes = [VP, C.c_int]
+        L.dh_shared_pass.argtypes = [I64, C.c_int, DBL, DBL, DBL, VP, VP, VP, I64, VP, VP, VP, VP, VP, VP]
         L.dh_update_resolve.argtypes = [I64, C.c_int, DBL, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, VP]
         L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
         L.dh_patch_batch_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, VP, C.c_int, VP]
@@ -351,6 +352,20 @@ class DeviceHost:
         self.lib.dh_update_resolve(n, mode, alpha, rounds, _p(N), _p(newN), _p(dN), _p(r2), _p(t), _p(dt), _p(row), _p(col),
                                    cnt, onetime, w, _p(film))
         return np.ascontiguousarray(t.T), film
+
+    def shared_pass(self, r2, n, tau, pix, newN, tao, alpha, photons, init_r2=0.0):
+        """One eye pass of the shared per-pixel statistics through shared_{init,load,accum,update,resolve}_kernel.
+        r2, n [h, w] and tau [h, w, 3] in place; returns (radius each hit point measured with, film [h, w, 3])."""
+        h, w = r2.shape
+        t3 = np.ascontiguousarray(tau.reshape(h * w, 3).T)
+        hp_r2 = np.zeros(newN.shape[0])
+        film = np.zeros((h, w, 3))
+        row, col = np.ascontiguousarray(pix[:, 0], dtype=np.int32), np.ascontiguousarray(pix[:, 1], dtype=np.int32)
+        nn, tt = np.ascontiguousarray(newN, dtype=np.int32), np.ascontiguousarray(tao.T)
+        self.lib.dh_shared_pass(h * w, w, init_r2, alpha, photons, _p(r2), _p(n), _p(t3), newN.shape[0], _p(row), _p(col),
+                                _p(nn), _p(tt), _p(hp_r2), _p(film))
+        tau[...] = t3.T.reshape(h, w, 3)
+        return hp_r2, film
 
     WORK = ("items", "slices", "visits", "kept", "pairs", "pair_slots", "redo_lanes")
 

@@ -613,6 +613,31 @@ void dh_update_resolve(int64_t n, int mode, double alpha, int rounds, int32_t* N
   for (int k = 0; k < rounds; k++) launch(update_kernel, std::make_tuple(s, (long long)n, mode, alpha), (n + T - 1) / T, T);
   if (film) launch(resolve_kernel, std::make_tuple(s, (long long)n, cnt, onetime, w, film), (n + T - 1) / T, T);
 }
+// Shared per-pixel statistics: shared_init (if init_r2 > 0) -> shared_load (the hit points take
+// their pixel's radius; hp_r2 out) -> [the caller's newN / tao stand for the pass's gather] -> shared_accum
+// -> shared_update -> shared_resolve.  Pixel arrays: r2[np], n[np], tau[3][np]; tao is [3][n_hp].
+void dh_shared_pass(int64_t np, int w, double init_r2, double alpha, double photons, double* px_r2, double* px_n,
+                    double* px_tau, int64_t n_hp, const int32_t* row, const int32_t* col, const int32_t* newN,
+                    const double* tao, double* hp_r2_out, double* film) {
+  std::vector<double> phi((size_t)np * 3, 0.0);
+  std::vector<int32_t> m((size_t)np, 0);
+  PxStats p;
+  p.r2 = px_r2; p.n = px_n; p.tau = px_tau; p.phi = phi.data(); p.m = m.data(); p.np = np;
+  const int T = bt(TPB);
+  if (init_r2 > 0) launch(shared_init_kernel, std::make_tuple(p, init_r2), (np + T - 1) / T, T);
+  std::vector<int32_t> iN((size_t)n_hp), inew((size_t)n_hp);
+  std::vector<double> t((size_t)n_hp * 3);
+  HpSoA s;
+  memset(&s, 0, sizeof(s));
+  s.row = const_cast<int32_t*>(row); s.col = const_cast<int32_t*>(col);
+  s.r2 = hp_r2_out; s.N = iN.data(); s.newN = inew.data(); s.tao = t.data();
+  launch(shared_load_kernel, std::make_tuple(s, (long long)n_hp, p, w), (n_hp + T - 1) / T, T);
+  memcpy(inew.data(), newN, (size_t)n_hp * 4);   // the pass's photon rounds
+  memcpy(t.data(), tao, (size_t)n_hp * 24);
+  launch(shared_accum_kernel, std::make_tuple(s, (long long)n_hp, p, w), (n_hp + T - 1) / T, T);
+  launch(shared_update_kernel, std::make_tuple(p, alpha), (np + T - 1) / T, T);
+  if (film) launch(shared_resolve_kernel, std::make_tuple(p, photons, film), (np + T - 1) / T, T);
+}
 // items, slices, deposit visits, deposits kept by the cull, (hit point, deposit) pairs classified, pair slots
 // issued (padding and idle lanes included), lanes that repeated a slice on the careful path
 void dh_work_read(uint64_t* out7, int reset) {

@@ -768,6 +768,34 @@ def test_update_and_resolve_kernels(dh, oracle, mode):
     assert (N != 0).any() and film.sum() > 0
 
 
+def test_shared_statistics_kernels(dh, oracle):
+    """shared_{init,load,accum,update,resolve}_kernel: three eye passes of the per-pixel statistics
+    (N' = N + alpha M, R2' = R2 (N + alpha M)/(N + M), tau' = (tau + Phi) R2'/R2; Hachisuka & Jensen 2009)
+    against the restated fold (oracle.shared_fold); radii only shrink, hit points measure with their
+    pixel's current radius."""
+    from raytrace3_b200.scene import PI
+    rng = np.random.RandomState(41)
+    w, h = 24, 18
+    r2, n, tau = np.zeros((h, w)), np.zeros((h, w)), np.zeros((h, w, 3))
+    o_r2, o_n, o_tau = np.full((h, w), 2.0), np.zeros((h, w)), np.zeros((h, w, 3))
+    photons = 0
+    for k in range(3):
+        n_hp = 700 + 50 * k                                # hit points move with the jittered camera
+        pix = np.stack([rng.randint(0, h, n_hp), rng.randint(0, w, n_hp)], axis=1).astype(np.int32)
+        newN = rng.randint(0, 5, n_hp).astype(np.int32)
+        tao = rng.uniform(0, 10, size=(n_hp, 3)) * (newN > 0)[:, None]
+        photons += 1000
+        want_r2 = o_r2[pix[:, 0], pix[:, 1]].copy()        # before the fold
+        hp_r2, film = dh.shared_pass(r2, n, tau, pix, newN, tao, 0.7, float(photons), init_r2=2.0 if k == 0 else 0.0)
+        oracle.shared_fold(o_r2, o_n, o_tau, pix, newN, tao, 0.7)
+        np.testing.assert_array_equal(hp_r2, want_r2)
+        np.testing.assert_allclose(r2, o_r2, rtol=1e-14, atol=0)
+        np.testing.assert_allclose(n, o_n, rtol=1e-14, atol=0)
+        np.testing.assert_allclose(tau, o_tau, rtol=1e-13, atol=0)
+        np.testing.assert_allclose(film, o_tau / (PI * o_r2 * photons)[..., None], rtol=1e-12, atol=0)   # the reference's PI (Vec3.h:8)
+    assert (r2 <= 2.0).all() and (r2 < 2.0).any()
+
+
 def test_one_warp_blocks_give_the_same_results(dh, oracle):
     """The tests above launch the kernels with the product's block sizes (128-thread trace / step blocks,
     256-thread gather blocks, 320-thread scatter); one-warp blocks are a second schedule of the same
