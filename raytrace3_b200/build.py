@@ -17,7 +17,7 @@ CSRC = os.path.join(ROOT, "csrc")
 LIBDIR = os.path.join(ROOT, "lib")
 LIB = os.path.join(LIBDIR, "libsppm_b200.so")
 SOURCES = ["abi.cu", "trace.cu", "wavefront.cu", "gather.cu", "imageio.cu"]
-HEADERS = ["ctx.h", "scene.cuh", "scene_prep.h", "trace_kernels.cuh", "wavefront_kernels.cuh", "gather_kernels.cuh", "device_math.cuh", os.path.join("..", "..", "include", "sppm_b200.h")]
+HEADERS = ["ctx.h", "scene.cuh", "scene_prep.h", "trace_kernels.cuh", "wavefront_kernels.cuh", "gather_kernels.cuh", "image_kernels.cuh", "device_math.cuh", os.path.join("..", "..", "include", "sppm_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

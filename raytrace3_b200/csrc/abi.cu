@@ -12,6 +12,7 @@
 
 #include "ctx.h"
 #include "scene_prep.h"
+#include "image_kernels.cuh"
 
 using namespace sppm;
 
@@ -88,17 +89,6 @@ int check_overflow(sppm_ctx* c) {
   return SPPM_OK;
 }
 
-__global__ void tonemap_kernel(const double* film, int w, int h, double div, uint8_t* bgr) {
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)w * h * 3) return;
-  const int k = (int)(t % 3);
-  const long long p = t / 3;
-  const int j = (int)(p % w), i1 = (int)(p / w);
-  const double x = film[t] / div;
-  const int v = (int)(pow(1 - exp(-x), 1 / 2.2) * 255 + .5);  // toInt (Raytracer.h:24-26)
-  bgr[((size_t)(h - 1 - i1) * w + j) * 3 + k] = (uint8_t)v;    // row flip (Raytracer.h:467)
-}
-
 // FP64 FMA throughput probe (the roofline denominator of the Newton / gather kernels; not in
 // MEASURED_PEAKS.json): 8 independent DFMA chains per thread.
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
@@ -167,10 +157,6 @@ void free_scene(sppm_ctx* c) {
   for (auto& b : c->scene_bufs) dev_free(b);
   c->scene_bufs.clear();
   c->scene_ok = false;
-}
-__global__ void tex_expand_kernel(const uint8_t* bgr, size_t n, uint32_t* out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (uint32_t)bgr[3 * i] | ((uint32_t)bgr[3 * i + 1] << 8) | ((uint32_t)bgr[3 * i + 2] << 16);
 }
 // Scene arrays live in grow-only device buffers (slot i of scene_bufs) that are reused by the
 // next upload: re-uploading a scene of the same shape costs only the copies.

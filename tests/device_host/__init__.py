@@ -20,7 +20,7 @@ _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _CSRC = os.path.join(_ROOT, "raytrace3_b200", "csrc")
 LIB_PATH = os.path.join(_HERE, "_build", "libdevice_host.so")
 SOURCES = [os.path.join(_HERE, f) for f in ("device_host.cpp", "cuda_host_shim.h")] + [
-    os.path.join(_CSRC, f) for f in ("scene.cuh", "device_math.cuh", "scene_prep.h", "trace_kernels.cuh", "wavefront_kernels.cuh", "gather_kernels.cuh", "ctx.h")] + [
+    os.path.join(_CSRC, f) for f in ("scene.cuh", "device_math.cuh", "scene_prep.h", "trace_kernels.cuh", "wavefront_kernels.cuh", "gather_kernels.cuh", "image_kernels.cuh", "ctx.h")] + [
     os.path.join(_ROOT, "include", "sppm_b200.h")]
 # -ffp-contract=off: no FMA contraction, the library's -fmad=false (explicit fma() calls stay fused)
 # -fno-extern-tls-init: the kernels' block-scope `extern __shared__` (= thread_local here) array has no dynamic initialiser
@@ -258,6 +258,8 @@ class DeviceHost:
         L.dh_gather_filtered.argtypes = [I64, VP, C.POINTER(Grid), I64, VP, DBL, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP]
         L.dh_set_one_warp_blocks.argtypes = [C.c_int]
         L.dh_work_read.argtypes = [VP, C.c_int]
+        L.dh_tonemap.argtypes = [VP, C.c_int, C.c_int, DBL, VP]
+        L.dh_tex_expand.argtypes = [VP, I64, VP]
         L.dh_shared_pass.argtypes = [I64, C.c_int, DBL, DBL, DBL, VP, VP, VP, I64, VP, VP, VP, VP, VP, VP]
         L.dh_update_resolve.argtypes = [I64, C.c_int, DBL, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, VP]
         L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
@@ -366,6 +368,19 @@ class DeviceHost:
                                 _p(nn), _p(tt), _p(hp_r2), _p(film))
         tau[...] = t3.T.reshape(h, w, 3)
         return hp_r2, film
+
+    def tonemap(self, film, div):
+        film = _f64(film)
+        h, w = film.shape[:2]
+        out = np.zeros((h, w, 3), dtype=np.uint8)
+        self.lib.dh_tonemap(_p(film), w, h, div, _p(out))
+        return out
+
+    def tex_expand(self, bgr8):
+        bgr8 = np.ascontiguousarray(bgr8, dtype=np.uint8)
+        out = np.zeros(bgr8.shape[:2], dtype=np.uint32)
+        self.lib.dh_tex_expand(_p(bgr8), out.size, _p(out))
+        return out
 
     WORK = ("items", "slices", "visits", "kept", "pairs", "pair_slots", "redo_lanes")
 

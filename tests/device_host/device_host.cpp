@@ -30,6 +30,7 @@ alignas(128) thread_local unsigned char wsm[64 << 10];    // gather_filtered_ker
 #include "../../raytrace3_b200/csrc/trace_kernels.cuh"
 #include "../../raytrace3_b200/csrc/wavefront_kernels.cuh"
 #include "../../raytrace3_b200/csrc/gather_kernels.cuh"
+#include "../../raytrace3_b200/csrc/image_kernels.cuh"
 namespace sppm {
 namespace {
 unsigned long long dh_work[WK_N] = {};  // SPPM_WORK counters of gather_filtered_kernel
@@ -637,6 +638,14 @@ void dh_shared_pass(int64_t np, int w, double init_r2, double alpha, double phot
   launch(shared_accum_kernel, std::make_tuple(s, (long long)n_hp, p, w), (n_hp + T - 1) / T, T);
   launch(shared_update_kernel, std::make_tuple(p, alpha), (np + T - 1) / T, T);
   if (film) launch(shared_resolve_kernel, std::make_tuple(p, photons, film), (np + T - 1) / T, T);
+}
+// tonemap_kernel (toInt + row flip, Raytracer.h:24-26, 460-470) and tex_expand_kernel (scene upload)
+void dh_tonemap(const double* film, int w, int h, double div, uint8_t* bgr) {
+  const long long n = (long long)w * h * 3;
+  launch(tonemap_kernel, std::make_tuple(film, w, h, div, bgr), (n + 255) / 256, 256);
+}
+void dh_tex_expand(const uint8_t* bgr, int64_t n, uint32_t* out) {
+  launch(tex_expand_kernel, std::make_tuple(bgr, (size_t)n, out), (n + 255) / 256, 256);
 }
 // items, slices, deposit visits, deposits kept by the cull, (hit point, deposit) pairs classified, pair slots
 // issued (padding and idle lanes included), lanes that repeated a slice on the careful path

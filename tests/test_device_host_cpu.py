@@ -796,6 +796,20 @@ def test_shared_statistics_kernels(dh, oracle):
     assert (r2 <= 2.0).all() and (r2 < 2.0).any()
 
 
+def test_tonemap_and_texel_expansion_kernels(dh, oracle):
+    """tonemap_kernel == toInt + the row flip of Raytracer.h:24-26, 460-470 (same libm: bit for bit, incl. the
+    values that land on a .5 boundary region and the clamp-free overflow of huge radiances);
+    tex_expand_kernel == B | G << 8 | R << 16 per texel."""
+    rng = np.random.RandomState(51)
+    film = rng.uniform(0, 30, size=(37, 53, 3)) * (rng.uniform(size=(37, 53, 1)) < 0.9)
+    film[0, :5] = [[0, 0, 0], [1e-12, 1e-6, 1e-3], [4.0, 40.0, 400.0], [1e5, 1e9, 1e12], [0.5, 2.0, 8.0]]
+    for div in (4.0, 8.0, 400.0):
+        np.testing.assert_array_equal(dh.tonemap(film, div), oracle.tonemap(film, div))
+    tex = synthetic_texture(19, 45, 3)
+    want = tex[..., 0].astype(np.uint32) | (tex[..., 1].astype(np.uint32) << 8) | (tex[..., 2].astype(np.uint32) << 16)
+    np.testing.assert_array_equal(dh.tex_expand(tex), want)
+
+
 def test_one_warp_blocks_give_the_same_results(dh, oracle):
     """The tests above launch the kernels with the product's block sizes (128-thread trace / step blocks,
     256-thread gather blocks, 320-thread scatter); one-warp blocks are a second schedule of the same

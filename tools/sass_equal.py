@@ -6,7 +6,8 @@
 Builds libsppm_b200.so of <rev> in a temporary git worktree (nvcc cross-compiles sm_100a without a
 GPU), dumps the SASS of every object of both builds with cuobjdump and compares it after removing
 what legitimately differs between two checkouts: the -lineinfo file markers, the source path
-identifier and the hash nvcc puts into the names of anonymous-namespace kernels.  Exit status 0 =
+identifier, the hash nvcc puts into the names of anonymous-namespace kernels and the order in which
+the kernels are defined.  Exit status 0 =
 identical instruction streams, i.e. a refactor (moving code between files, host-only changes) is
 proven device-neutral and the GPU evidence of <rev> still describes the tree; 1 = they differ.
 """
@@ -25,7 +26,10 @@ OBJECTS = ["abi", "trace", "wavefront", "gather", "imageio"]
 def sass(obj_path: str) -> str:
     out = subprocess.run(["cuobjdump", "-sass", obj_path], capture_output=True, text=True, check=True).stdout
     keep = [l for l in out.splitlines() if "//##" not in l and "identifier =" not in l]
-    return re.sub(r"_GLOBAL__N__[0-9a-f]+_", "_G_", "\n".join(keep))
+    text = re.sub(r"_GLOBAL__N__[0-9a-f]+_", "_G_", "\n".join(keep))
+    # one block per kernel, sorted by name: the order of definition in the source is not device code
+    parts = re.split(r"(?m)^(?=\s*Function : )", text)
+    return parts[0] + "".join(sorted(parts[1:]))
 
 
 def build(tree: str) -> str:
