@@ -258,6 +258,7 @@ class DeviceHost:
         L.dh_gather_filtered.argtypes = [I64, VP, C.POINTER(Grid), I64, VP, DBL, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP]
         L.dh_set_one_warp_blocks.argtypes = [C.c_int]
         L.dh_work_read.argtypes = [VP, C.c_int]
+        L.dh_bounds.argtypes = [I64, VP, C.c_int, VP]
         L.dh_tonemap.argtypes = [VP, C.c_int, C.c_int, DBL, VP]
         L.dh_tex_expand.argtypes = [VP, I64, VP]
         L.dh_shared_pass.argtypes = [I64, C.c_int, DBL, DBL, DBL, VP, VP, VP, I64, VP, VP, VP, VP, VP, VP]
@@ -318,7 +319,7 @@ class DeviceHost:
         self.lib.dh_unit_rand_vec(seed, pass_id, ids.shape[0], _p(ids), purpose, _p(out))
         return out
 
-    def gather_filtered(self, hp, dep, search_r2, count_pairs=True, blocks=16, exact=False):
+    def gather_filtered(self, hp, dep, search_r2, count_pairs=True, blocks=16, exact=False, shuffle_seed=None):
         """build_index + deposit binning + gather_filtered_kernel (the product's kernels; CUB's sorts and
         scans restated with std:: algorithms) -> newN [n], tao [n, 3] in the order of `hp`, info, pairs."""
         n, m = hp["pos"].shape[0], dep["x"].shape[0]
@@ -326,6 +327,9 @@ class DeviceHost:
         for k in ("pos", "n", "wgt", "r2"):
             raw[k] = hp[k]
         raw["okey"] = np.arange(n, dtype=np.uint64)
+        if shuffle_seed is not None:     # arrival order of the eye pass: the canonical order is restored from okey
+            perm = np.random.RandomState(shuffle_seed).permutation(n)
+            raw = np.ascontiguousarray(raw[perm])
         d = np.zeros(max(m, 1), dtype=deposit_dtype)
         for k in ("x", "n", "flux"):
             d[k][:m] = dep[k]
@@ -340,6 +344,8 @@ class DeviceHost:
         assert rc == 0
         newN = np.zeros(n, dtype=np.int32)
         tao = np.zeros((n, 3))
+        if shuffle_seed is not None:
+            order = perm[order]
         newN[order] = dN
         tao[order] = dtao.T
         return newN, tao, dict(zip(("n_occ", "n_slots", "n_units", "n_items", "kept"), info.tolist())), pairs.tolist()
@@ -381,6 +387,13 @@ class DeviceHost:
         out = np.zeros(bgr8.shape[:2], dtype=np.uint32)
         self.lib.dh_tex_expand(_p(bgr8), out.size, _p(out))
         return out
+
+    def bounds(self, pos, blocks=7):
+        raw = np.zeros(pos.shape[0], dtype=hpraw_dtype)
+        raw["pos"] = pos
+        out = np.zeros(9)
+        self.lib.dh_bounds(pos.shape[0], _p(raw), blocks, _p(out))
+        return out[:3], out[3:6], out[6:]
 
     WORK = ("items", "slices", "visits", "kept", "pairs", "pair_slots", "redo_lanes")
 

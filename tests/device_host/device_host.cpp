@@ -496,11 +496,18 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   auto nb = [&](long long k) { return (k + T - 1) / T; };
   // hit points: cell keys, stable sort, SoA permute
   std::vector<uint32_t> iota((size_t)n), key((size_t)n), idx((size_t)n), skey((size_t)n);
-  std::iota(iota.begin(), iota.end(), 0u);
+  // canonical order first (sort by okey = pixel, eye-path node), then a stable sort by cell key
+  std::vector<uint64_t> okey0((size_t)n);
+  launch(hp_okey_kernel, std::make_tuple(raw, (long long)n, okey0.data(), iota.data()), nb(n), T);
+  std::stable_sort(iota.begin(), iota.end(), [&](uint32_t a, uint32_t b) { return okey0[a] < okey0[b]; });
   launch(hp_key_kernel, std::make_tuple(raw, (const uint32_t*)iota.data(), (long long)n, g, key.data()), nb(n), T);
-  idx = iota;
-  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
-  for (int64_t i = 0; i < n; i++) skey[(size_t)i] = key[idx[(size_t)i]];
+  std::vector<uint32_t> pos((size_t)n);  // key[] is indexed by canonical position
+  std::iota(pos.begin(), pos.end(), 0u);
+  std::stable_sort(pos.begin(), pos.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+  for (int64_t i = 0; i < n; i++) {
+    idx[(size_t)i] = iota[pos[(size_t)i]];
+    skey[(size_t)i] = key[pos[(size_t)i]];
+  }
   const size_t nd = (size_t)n;
   std::vector<double> dstore(nd * 16);
   std::vector<uint64_t> okey(nd);
@@ -646,6 +653,21 @@ void dh_tonemap(const double* film, int w, int h, double div, uint8_t* bgr) {
 }
 void dh_tex_expand(const uint8_t* bgr, int64_t n, uint32_t* out) {
   launch(tex_expand_kernel, std::make_tuple(bgr, (size_t)n, out), (n + 255) / 256, 256);
+}
+// bounds_kernel (build_index step 1): out9 = min[3], max[3], sum[3] of the hit-point positions
+void dh_bounds(int64_t n, const HpRaw* raw, int blocks, double* out9) {
+  unsigned long long mm[6];
+  double sum[3] = {0, 0, 0};
+  for (int k = 0; k < 3; k++) {
+    mm[k] = ~0ull;
+    mm[3 + k] = 0ull;
+  }
+  launch(bounds_kernel, std::make_tuple(raw, (long long)n, mm, sum), blocks, bt(TPB));
+  for (int k = 0; k < 3; k++) {
+    out9[k] = key_dbl(mm[k]);
+    out9[3 + k] = key_dbl(mm[3 + k]);
+    out9[6 + k] = sum[k];
+  }
 }
 // items, slices, deposit visits, deposits kept by the cull, (hit point, deposit) pairs classified, pair slots
 // issued (padding and idle lanes included), lanes that repeated a slice on the careful path

@@ -627,6 +627,27 @@ def test_gather_filtered_kernel_shapes_fuzz(dh, oracle, seed):
         assert info["n_items"] > info["n_units"] - info["n_occ"]  # some unit was cut into several work items
 
 
+def test_bounds_and_canonical_order_kernels(dh, oracle):
+    """bounds_kernel (min / max / sum through the order-preserving integer keys, negative coordinates
+    included) and hp_okey_kernel: hit points handed over in arrival order give the same map."""
+    rng = np.random.RandomState(61)
+    n, m = 3000, 9000
+    pos = rng.uniform(-40, 60, size=(n, 3))
+    lo, hi, sm = dh.bounds(pos)
+    np.testing.assert_array_equal(lo, pos.min(0))
+    np.testing.assert_array_equal(hi, pos.max(0))
+    np.testing.assert_allclose(sm, pos.sum(0), rtol=1e-12)
+    hp = dict(pos=rng.uniform(0, 14, size=(n, 3)), wgt=rng.uniform(0.1, 1, size=(n, 3)), r2=rng.uniform(0.5, 2.0, n))
+    nrm = rng.normal(size=(n, 3))
+    hp["n"] = nrm / np.linalg.norm(nrm, axis=1, keepdims=True)
+    dep = dict(x=rng.uniform(-1, 15, size=(m, 3)), n=hp["n"][rng.randint(0, n, m)], flux=rng.uniform(0, 9, size=(m, 3)))
+    a = dh.gather_filtered(hp, dep, 2.0)
+    b = dh.gather_filtered(hp, dep, 2.0, shuffle_seed=3)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-12, atol=0)   # the deposits' arrival ranks within a cell vary from run to run
+    assert a[3] == b[3] and a[0].sum() > 1000
+
+
 def test_gather_filtered_kernel_out_of_range_normals_take_the_exact_path(dh, oracle):
     """A deposit normal with a component above 1.0001 (not a unit vector: the ABI takes any deposit list)
     voids the FP32 error bound; such a slice is evaluated in FP64 wholesale."""
