@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SPPM_ABI_VERSION 2
+#define SPPM_ABI_VERSION 3
 
 typedef enum SppmError {
   SPPM_OK = 0,
@@ -171,6 +171,11 @@ typedef struct SppmCounters {
   uint64_t launches;         /* kernels launched by this library */
   double ms_eye, ms_build, ms_trace, ms_sort, ms_gather, ms_update, ms_resolve; /* last call of each */
   uint64_t patch_culled;     /* ... of patch_solves, proven empty by the 13-DOP line test and not run */
+  /* ABI version 3 */
+  uint64_t spilled_photons;  /* photons the wavefront tracer handed to the persistent tracer (item list full) */
+  /* per-kernel times of the photon passes run under sppm_set_profiling(ctx, 1) (serialised batches) */
+  double ms_step, ms_newton, ms_spill, ms_bin_scan, ms_bin_scatter, ms_gather_prep, ms_gather_kernel;
+  double ms_allreduce;       /* sppm_allreduce calls (event span on the communication stream) */
 } SppmCounters;
 
 typedef struct sppm_ctx sppm_ctx;
@@ -293,6 +298,10 @@ int sppm_keep_deposits(sppm_ctx* ctx, int32_t keep_all);
 int sppm_export_deposits(sppm_ctx* ctx, int64_t cap, double* x3, double* n3, double* flux3,
                          uint64_t* photon_id, int32_t* bounce, int64_t* m);
 int sppm_get_counters(sppm_ctx* ctx, SppmCounters* out);
+/* Measurement aid: on = 1 makes every batch of sppm_photon_pass run alone (device sync after it) with a
+ * CUDA event between its launches, so that SppmCounters.ms_step / ms_newton / ... hold the time of each
+ * kernel class as an ncu launch list sees it; on = 0 (default) is the pipelined production path. */
+int sppm_set_profiling(sppm_ctx* ctx, int32_t on);
 int sppm_reset_counters(sppm_ctx* ctx);
 
 #ifdef __cplusplus

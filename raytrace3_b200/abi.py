@@ -76,7 +76,10 @@ class SppmCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "photons", "isect_queries", "patch_solves", "deposits", "deposits_kept", "cand_pairs", "acc_pairs",
         "hit_points", "grid_cells", "launches")] + [(n, C.c_double) for n in (
-            "ms_eye", "ms_build", "ms_trace", "ms_sort", "ms_gather", "ms_update", "ms_resolve")] + [("patch_culled", C.c_uint64)]
+            "ms_eye", "ms_build", "ms_trace", "ms_sort", "ms_gather", "ms_update", "ms_resolve")] + [
+                ("patch_culled", C.c_uint64), ("spilled_photons", C.c_uint64)] + [(n, C.c_double) for n in (
+                    "ms_step", "ms_newton", "ms_spill", "ms_bin_scan", "ms_bin_scatter", "ms_gather_prep", "ms_gather_kernel",
+                    "ms_allreduce")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -137,6 +140,7 @@ PROTOTYPES = {
     "sppm_export_deposits": (C.c_int, [VP, I64, VP, VP, VP, VP, VP, C.POINTER(I64)]),
     "sppm_get_counters": (C.c_int, [VP, C.POINTER(SppmCounters)]),
     "sppm_reset_counters": (C.c_int, [VP]),
+    "sppm_set_profiling": (C.c_int, [VP, I32]),
 }
 
 _lib = None

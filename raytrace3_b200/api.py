@@ -317,6 +317,10 @@ class Context:
         self._ck(self.lib.sppm_get_counters(self.h, C.byref(c)), "sppm_get_counters")
         return c.as_dict()
 
+    def set_profiling(self, on: bool):
+        """Serialised batches with an event between launches: per-kernel ms in counters() (measurement only)."""
+        self._ck(self.lib.sppm_set_profiling(self.h, 1 if on else 0), "sppm_set_profiling")
+
     def reset_counters(self):
         self._ck(self.lib.sppm_reset_counters(self.h), "sppm_reset_counters")
 

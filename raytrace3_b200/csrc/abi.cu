@@ -67,7 +67,9 @@ void fold_timings(sppm_ctx* c) {
   c->t_pending = 0;
 }
 
-// Device-side overflow flags (deposit list, Bezier work-item list) are checked at sync points.
+// The deposit list's device-side count is checked at sync points (it is sized for max_dep + 1 deposits per
+// photon, the most Raytracer.h:127-133 allows, so this cannot fire; the wavefront tracer's (ray, patch) item
+// list cannot overflow either: photons that find it full are finished by the persistent tracer).
 int check_overflow(sppm_ctx* c) {
   for (int j = 0; j < sppm_ctx::MAX_LANES; j++) {
     Lane& L = c->lanes[j];
@@ -79,12 +81,6 @@ int check_overflow(sppm_ctx* c) {
       return cuda_fail(c, cudaGetLastError(), "check_overflow");
     if (j == c->last_lane) c->n_dep = (int64_t)std::min<unsigned long long>(m, (unsigned long long)L.dep_cap);
     if ((int64_t)m > L.dep_cap) return fail(c, SPPM_ERR_CAPACITY, "deposit buffer overflow");
-    if (c->prm.trace_mode != SPPM_TRACE_PERSISTENT) {
-      bool ovf = false;
-      cudaError_t e = wavefront_overflowed(c, L, &ovf);
-      if (e) return cuda_fail(c, e, "wavefront_overflowed");
-      if (ovf) return fail(c, SPPM_ERR_CAPACITY, "Bezier work-item list overflow (more than 2 (ray, patch) items per photon in one bounce); SppmParams.trace_mode = SPPM_TRACE_PERSISTENT has no such list");
-    }
   }
   return SPPM_OK;
 }
@@ -281,11 +277,13 @@ void sppm_ctx_destroy(sppm_ctx* c) {
     Lane& L = c->lanes[j];
     DevBuf* lb[] = {&L.dep_raw, &L.dep_sorted, &L.dep_key, &L.dep_rank, &L.slot_count, &L.dep_start, &L.wf_store, &L.scalars, &L.cub_tmp};
     for (DevBuf* d : lb) dev_free(*d);
+    L.prof.destroy();
     if (L.ev_trace_done) cudaEventDestroy(L.ev_trace_done);
     if (L.ev_gather_done) cudaEventDestroy(L.ev_gather_done);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   if (c->ev_setup) cudaEventDestroy(c->ev_setup);
+  c->prof.destroy();
   free_scene(c);
   DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->units, &c->item_parts, &c->item_off, &c->px_store, &c->hp_raw_alt, &c->dep_key, &c->dep_key2,
                     &c->dep_idx, &c->dep_idx2, &c->scan_scratch, &c->cub_tmp, &c->dev_scalars, &c->counters, &c->film, &c->scratch};
@@ -397,11 +395,24 @@ int sppm_eye_pass_rows(sppm_ctx* c, const SppmCameraDesc* cam, uint64_t pass_id,
     CU(c, cudaMemcpyAsync(&n, scalars(c), 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     if ((int64_t)n <= c->hp_cap) break;
-    // appended row ranges share the buffer with the rows traced before: those cannot be re-made here
-    if (append || attempt > 0)
-      return fail(c, SPPM_ERR_CAPACITY, "hit-point buffer overflow (more than 4 hit points per pixel in a row-sharded eye pass)");
-    c->hp_cap = (int64_t)n + 1024;
-    CU(c, dev_reserve(c->hp_raw, (size_t)c->hp_cap * sizeof(HpRaw)));
+    if (attempt > 0) return fail(c, SPPM_ERR_CAPACITY, "hit-point buffer overflow (the eye pass grew between two identical traces)");
+    // n is the true count (the kernel counts past the capacity): trace the same rows again into a buffer of
+    // that size.  Appended row ranges share the buffer with the rows traced before, which cannot be re-made
+    // here: they are carried over and the device-side count is put back to where this call found it.
+    const int64_t new_cap = (int64_t)n + 1024;
+    if (append) {
+      const unsigned long long before = (unsigned long long)c->n_hp;
+      DevBuf grown;
+      CU(c, dev_reserve(grown, (size_t)new_cap * sizeof(HpRaw)));
+      if (before) CU(c, cudaMemcpyAsync(grown.p, c->hp_raw.p, (size_t)before * sizeof(HpRaw), cudaMemcpyDeviceToDevice, c->stream));
+      CU(c, cudaMemcpyAsync(scalars(c), &before, 8, cudaMemcpyHostToDevice, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));  // `before` is a stack variable; the old buffer is freed next
+      dev_free(c->hp_raw);
+      c->hp_raw = grown;
+    } else {
+      CU(c, dev_reserve(c->hp_raw, (size_t)new_cap * sizeof(HpRaw)));
+    }
+    c->hp_cap = new_cap;
   }
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
@@ -442,9 +453,12 @@ int sppm_allgather_hitpoints(sppm_ctx* c, int64_t* n_hitpoints) {
   CU(c, cudaStreamSynchronize(c->stream));
   unsigned long long total = 0;
   for (auto v : counts) total += v;
-  if ((int64_t)total > c->hp_cap) return fail(c, SPPM_ERR_CAPACITY, "hit-point buffer overflow in the all-gather");
+  // The receive buffer is sized from `total`, which every rank computes from the same gathered counts: no
+  // rank can leave before the collective below while the others enter it (the ranks' own hp_cap differ when
+  // one of them re-traced a branching eye pass into a larger buffer).
+  const int64_t cap_all = std::max<int64_t>(c->hp_cap, (int64_t)total + 1024);
   DevBuf& all = c->hp_raw_alt;  // second raw buffer, kept across calls (no allocation in steady state)
-  CU(c, dev_reserve(all, (size_t)c->hp_cap * sizeof(HpRaw)));
+  CU(c, dev_reserve(all, (size_t)cap_all * sizeof(HpRaw)));
   r = n.GroupStart();
   unsigned long long off = 0;
   for (int k = 0; k < R && r == ncclSuccess; k++) {
@@ -459,6 +473,7 @@ int sppm_allgather_hitpoints(sppm_ctx* c, int64_t* n_hitpoints) {
   if (r != ncclSuccess)
     return fail(c, SPPM_ERR_NCCL, std::string("hit-point exchange: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
   std::swap(c->hp_raw, c->hp_raw_alt);  // stream-ordered: later work on c->stream sees the gathered map
+  c->hp_cap = cap_all;
   c->n_hp = (int64_t)total;
   const unsigned long long t = total;
   CU(c, cudaMemcpyAsync(scalars(c), &t, 8, cudaMemcpyHostToDevice, c->stream));
@@ -519,6 +534,7 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
     if (c->prm.trace_mode == SPPM_TRACE_PERSISTENT) CU(c, launch_photon_trace(c, L, photon_begin + off, cnt, pass_id));
     else CU(c, launch_photon_trace_wavefront(c, L, photon_begin + off, cnt, pass_id));
     if (gather) CU(c, bin_deposits(c, L, L.stream));
+    CU(c, L.prof.mark(PK_END, L.stream));
     CU(c, cudaEventRecord(te[1], L.stream));
     CU(c, cudaEventRecord(L.ev_trace_done, L.stream));
     CU(c, cudaStreamWaitEvent(c->stream, L.ev_trace_done, 0));
@@ -526,6 +542,17 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
     CU(c, cudaEventRecord(L.ev_gather_done, c->stream));
     c->t_has_gather[c->t_pending] = gather;
     c->t_pending++;
+    if (c->profiling) {  // measurement mode: the batch runs alone, its launches are timed one by one
+      CU(c, cudaStreamSynchronize(L.stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+      double b[PK_N] = {};
+      L.prof.fold(b);
+      c->prof.fold(b);
+      SppmCounters& h = c->host_counters;
+      h.ms_step += b[PK_STEP]; h.ms_newton += b[PK_NEWTON]; h.ms_spill += b[PK_SPILL];
+      h.ms_bin_scan += b[PK_BIN_SCAN]; h.ms_bin_scatter += b[PK_BIN_SCATTER];
+      h.ms_gather_prep += b[PK_GATHER_PREP]; h.ms_gather_kernel += b[PK_GATHER_KERNEL];
+    }
   }
   return SPPM_OK;  // stream-ordered: nothing above waited for the device
 }
@@ -989,6 +1016,7 @@ int sppm_get_counters(sppm_ctx* c, SppmCounters* out) {
   h.isect_queries = d.isect_queries;
   h.patch_solves = d.patch_solves;
   h.patch_culled = d.patch_culled;
+  h.spilled_photons = d.overflow;
   h.deposits = d.deposits;
   h.deposits_kept = d.deposits_kept;
   h.cand_pairs = d.cand_pairs;
@@ -996,6 +1024,18 @@ int sppm_get_counters(sppm_ctx* c, SppmCounters* out) {
   h.hit_points = (uint64_t)c->n_hp;
   h.grid_cells = (uint64_t)c->grid.n_cells;
   *out = h;
+  return SPPM_OK;
+}
+
+int sppm_set_profiling(sppm_ctx* c, int32_t on) {
+  if (!c) return SPPM_ERR_INVALID;
+  c->profiling = on != 0;
+  c->prof.on = c->profiling;
+  c->prof.n = 0;
+  for (int j = 0; j < sppm_ctx::MAX_LANES; j++) {
+    c->lanes[j].prof.on = c->profiling;
+    c->lanes[j].prof.n = 0;
+  }
   return SPPM_OK;
 }
 

@@ -85,6 +85,40 @@ struct DevCounters {
   unsigned long long photons, isect_queries, patch_solves, deposits, deposits_kept, cand_pairs, acc_pairs, overflow, patch_culled;
 };
 
+// sppm_set_profiling: one event before every launch of a batch; the span up to the next event goes to a bucket
+enum ProfKind { PK_STEP, PK_NEWTON, PK_SPILL, PK_BIN_SCAN, PK_BIN_SCATTER, PK_GATHER_PREP, PK_GATHER_KERNEL, PK_END, PK_N };
+struct ProfMarks {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;
+  int n = 0;
+  bool on = false;
+  cudaError_t mark(int k, cudaStream_t st) {
+    if (!on) return cudaSuccess;
+    if (n == (int)ev.size()) {
+      cudaEvent_t e;
+      cudaError_t r = cudaEventCreate(&e);
+      if (r) return r;
+      ev.push_back(e);
+      kind.push_back(0);
+    }
+    kind[n] = k;
+    return cudaEventRecord(ev[n++], st);
+  }
+  void fold(double* bucket /*[PK_N]*/) {  // after the stream was synchronised
+    for (int i = 0; i + 1 < n; i++) {
+      float ms = 0;
+      if (kind[i] != PK_END && cudaEventElapsedTime(&ms, ev[i], ev[i + 1]) == cudaSuccess) bucket[kind[i]] += ms;
+    }
+    n = 0;
+  }
+  void destroy() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+    kind.clear();
+    n = 0;
+  }
+};
+
 struct DevBuf {  // growable device allocation
   void* p = nullptr;
   size_t bytes = 0;
@@ -102,6 +136,7 @@ struct Lane {
   DevBuf scalars;                                 // u64[8]: [1] deposit count, [2] photon cursor
   DevBuf cub_tmp;
   int64_t dep_cap = 0, wf_cap = 0;
+  ProfMarks prof;
 };
 
 }  // namespace sppm
@@ -155,6 +190,8 @@ struct sppm_ctx {
   bool newton_cull = true;    // 13-DOP line test before Newton solves (off only inside sppm_bezier_patch_bench)
   bool keep_all_deposits = false;
   SppmCounters host_counters{};
+  bool profiling = false;     // sppm_set_profiling
+  sppm::ProfMarks prof;       // marks on the main stream (gather)
   cudaEvent_t ev[8] = {};  // 4/5 generic, 6/7 user stopwatch
   static constexpr int TIMING_RING = 32;
   cudaEvent_t tev[TIMING_RING][4] = {};  // per batch: trace start, bin start, gather start, gather end
@@ -168,7 +205,9 @@ struct sppm_ctx {
 namespace sppm {
 // trace.cu
 cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pass_id, int row_begin, int row_end);
-cudaError_t launch_photon_trace(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t count, uint64_t pass_id);
+cudaError_t launch_photon_trace(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t count, uint64_t pass_id,
+                                const unsigned* r_count = nullptr, double* const* r_st = nullptr,
+                                const unsigned long long* r_idd = nullptr);
 cudaError_t launch_intersect(sppm_ctx* c, const double* d_rays6, int64_t n, const uint64_t* d_ids, uint64_t pass_id,
                              int node, SppmHit* d_out);
 cudaError_t launch_patch_batch(sppm_ctx* c, const double* d_rays6, const int32_t* d_patch, int64_t n,
@@ -176,7 +215,6 @@ cudaError_t launch_patch_batch(sppm_ctx* c, const double* d_rays6, const int32_t
 cudaError_t trace_configure(sppm_ctx* c);
 // wavefront.cu
 cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t count, uint64_t pass_id);
-cudaError_t wavefront_overflowed(sppm_ctx* c, Lane& L, bool* overflow);
 // gather.cu
 cudaError_t build_index(sppm_ctx* c);
 cudaError_t key_host_deposits(sppm_ctx* c, Lane& L, int64_t m, cudaStream_t st);

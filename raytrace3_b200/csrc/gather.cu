@@ -277,7 +277,9 @@ cudaError_t bin_deposits(sppm_ctx* c, Lane& L, cudaStream_t st) {
   const int n_scan = c->n_slots + 2;
   CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int32_t*)L.slot_count.p, (int32_t*)L.dep_start.p, n_scan, st));
   CK(dev_reserve(L.cub_tmp, tmp));
+  CK(L.prof.mark(PK_BIN_SCAN, st));
   CK(cub::DeviceScan::ExclusiveSum(L.cub_tmp.p, tmp, (const int32_t*)L.slot_count.p, (int32_t*)L.dep_start.p, n_scan, st));
+  CK(L.prof.mark(PK_BIN_SCATTER, st));
   dep_scatter_kernel<<<(unsigned)c->sm_count * 6, 320, 0, st>>>((const Deposit*)L.dep_raw.p, (const uint32_t*)L.dep_key.p,
                                                                 (const uint32_t*)L.dep_rank.p,
                                                                 (const unsigned long long*)L.scalars.p + 1,
@@ -324,6 +326,7 @@ cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cud
       const int nu = c->n_units;
       CK(dev_reserve(c->item_parts, ((size_t)nu + 1) * 4));
       CK(dev_reserve(c->item_off, ((size_t)nu + 1) * 4));
+      CK(c->prof.mark(PK_GATHER_PREP, st));
       unit_parts_kernel<<<nblk(nu + 1), TPB, 0, st>>>(a.units, nu, a.dep_off, (int32_t*)c->item_parts.p);
       size_t tmp = 0;
       CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (int32_t*)c->item_parts.p, (int32_t*)c->item_off.p, nu + 1, st));
@@ -332,8 +335,10 @@ cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cud
       a.item_off = (const int32_t*)c->item_off.p;
       c->host_counters.launches += 2;
     }
+    CK(c->prof.mark(PK_GATHER_KERNEL, st));
     kern<<<blocks, threads, tile_bytes, st>>>(a, work_counter);
     c->host_counters.launches++;
+    CK(c->prof.mark(PK_END, st));
   }
   if (ev_gather_end) CK(cudaEventRecord(ev_gather_end, st));
   return cudaGetLastError();

@@ -62,9 +62,13 @@ cudaError_t launch_eye_pass(sppm_ctx* c, const SppmCameraDesc& cam, uint64_t pas
   return cudaGetLastError();
 }
 
-cudaError_t launch_photon_trace(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t count, uint64_t pass_id) {
+cudaError_t launch_photon_trace(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t count, uint64_t pass_id,
+                                const unsigned* r_count, double* const* r_st, const unsigned long long* r_idd) {
   PhotonArgs a;
   a.c = make_common(c, pass_id);
+  a.r_count = r_count;  // resume mode: finish the photons the wavefront tracer spilled (count stays on the device)
+  for (int k = 0; k < 9; k++) a.r_st[k] = r_count ? r_st[k] : nullptr;
+  a.r_idd = r_idd;
   a.grid = c->grid;
   a.cell_slot = c->index_ok ? (const int32_t*)c->cell_slot.p : nullptr;
   a.n_slots = c->n_slots;

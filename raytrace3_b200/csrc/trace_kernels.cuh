@@ -166,6 +166,12 @@ struct PhotonArgs {
   unsigned long long* dep_count;
   unsigned long long* cursor;
   uint64_t begin, count;  // photon range per light
+  // Resume mode (r_count != null): instead of emitting, take *r_count photons in flight from a list of
+  // states (org, dir, flux, id | dep << 56) — the photons the wavefront tracer spilled when the (ray, patch)
+  // item list of a bounce was full (wavefront_kernels.cuh).  Same RNG addresses, so the same paths.
+  const unsigned* r_count;
+  const double* r_st[9];
+  const unsigned long long* r_idd;
 };
 
 // Persistent warps: a lane whose photon ended picks the next photon index from a global
@@ -173,11 +179,12 @@ struct PhotonArgs {
 // addressed by photon id, so the result does not depend on which lane traces what.
 __global__ void __launch_bounds__(TRACE_THREADS, SPPM_TRACE_MINBLOCKS) photon_trace_kernel(const PhotonArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
+  if (a.r_count && *a.r_count == 0) return;  // nothing was spilled (the usual case): no scene staging either
   const size_t scene_bytes = scene_smem_bytes(a.c.scene.n_obj, a.c.scene.n_patch, a.c.patches_in_smem);
   const SceneView sv = stage_scene(a.c.scene, smem, a.c.patches_in_smem);
   WarpScratch* ws = warp_scratch(smem, scene_bytes);
   const int lane = threadIdx.x & 31;
-  const unsigned long long total = (unsigned long long)a.c.scene.n_light * a.count;
+  const unsigned long long total = a.r_count ? (unsigned long long)*a.r_count : (unsigned long long)a.c.scene.n_light * a.count;
 
   bool alive = false, exhausted = false;
   d3 org = mk(0, 0, 0), dir = mk(0, 0, 1), flux = mk(0, 0, 0);
@@ -194,7 +201,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_TRACE_MINBLOCKS) photon_tr
       if (base + __popc(dead) >= total) exhausted = true;
       if (!alive) {
         const unsigned long long q = base + __popc(dead & ((1u << lane) - 1));
-        if (q < total) {  // Light::emit (Light.h:8-13)
+        if (q < total && a.r_count) {  // a photon in flight
+          org = mk(a.r_st[0][q], a.r_st[1][q], a.r_st[2][q]);
+          dir = mk(a.r_st[3][q], a.r_st[4][q], a.r_st[5][q]);
+          flux = mk(a.r_st[6][q], a.r_st[7][q], a.r_st[8][q]);
+          const unsigned long long idd = a.r_idd[q];
+          id = idd & 0x00ffffffffffffffull;
+          dep = (int)(idd >> 56);
+          alive = true;
+        } else if (q < total) {  // Light::emit (Light.h:8-13)
           const unsigned pl = (unsigned)(q / a.count);
           id = ((uint64_t)pl << 40) | (a.begin + q % a.count);
           const SppmLight& L = a.c.scene.lights[pl];

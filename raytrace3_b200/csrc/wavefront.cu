@@ -43,13 +43,14 @@ cudaError_t wavefront_configure(sppm_ctx* c, int* step_blocks, int* newton_block
 cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin, uint64_t count, uint64_t pass_id) {
   const int64_t total = (int64_t)c->scene.n_light * (int64_t)count;
   if (total <= 0) return cudaSuccess;
-  const int64_t item_cap = std::max<int64_t>(total * 2, 1 << 16);
   cudaError_t e;
   if (total > Ln.wf_cap) {
-    if ((e = dev_reserve(Ln.wf_store, wf_bytes(total, item_cap)))) return e;
+    if ((e = dev_reserve(Ln.wf_store, wf_bytes(total, wf_item_cap(total))))) return e;
     Ln.wf_cap = total;
   }
-  const WfLayout L = wf_layout(Ln.wf_store.p, Ln.wf_cap, std::max<int64_t>(Ln.wf_cap * 2, 1 << 16));
+  WfLayout L = wf_layout(Ln.wf_store.p, Ln.wf_cap, wf_item_cap(Ln.wf_cap));
+  // test knob: a short item list, so that the spill path (photons finished by the persistent tracer) runs
+  if (const char* e = getenv("SPPM_WF_ITEM_CAP")) L.item_cap = (unsigned)std::max<long long>(1, std::min<long long>(L.item_cap, atoll(e)));
   int step_blocks, newton_blocks;
   size_t step_smem, newton_smem;
   if ((e = wavefront_configure(c, &step_blocks, &newton_blocks, &step_smem, &newton_smem))) return e;
@@ -88,27 +89,23 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
       const int64_t want = (total + STEP_THREADS - 1) / STEP_THREADS;
       if (want < blocks) blocks = (int)want;
     }
+    if ((e = Ln.prof.mark(PK_STEP, st))) return e;
     photon_step_kernel<<<blocks, STEP_THREADS, step_smem, st>>>(a);
     c->host_counters.launches++;
     if (a.do_intersect && c->scene.n_patch > 0) {
       const NewtonArgs n = wf_newton_args(w, L, a);
+      if ((e = Ln.prof.mark(PK_NEWTON, st))) return e;
       newton_items_kernel<<<newton_blocks, TRACE_THREADS, newton_smem, st>>>(n);
       c->host_counters.launches++;
     }
   }
+  if ((e = Ln.prof.mark(PK_SPILL, st))) return e;
+  // Photons whose bounce found the item list full were taken out of the wavefront (spill list): the
+  // persistent tracer finishes them (it returns at once when the list is empty, the usual case).
+  if (c->scene.n_patch > 0) {
+    if ((e = launch_photon_trace(c, Ln, begin, count, pass_id, L.spill.count, L.spill.st, L.spill.idd))) return e;
+  }
   return cudaGetLastError();
-}
-
-cudaError_t wavefront_overflowed(sppm_ctx* c, Lane& Ln, bool* overflow) {
-  *overflow = false;
-  if (!Ln.wf_store.p || Ln.wf_cap <= 0) return cudaSuccess;
-  const WfLayout L = wf_layout(Ln.wf_store.p, Ln.wf_cap, std::max<int64_t>(Ln.wf_cap * 2, 1 << 16));
-  unsigned v = 0;
-  cudaError_t e = cudaMemcpyAsync(&v, L.counters + 96, 4, cudaMemcpyDeviceToHost, c->stream);
-  if (e) return e;
-  if ((e = cudaStreamSynchronize(c->stream))) return e;
-  *overflow = v != 0;
-  return cudaSuccess;
 }
 
 }  // namespace sppm

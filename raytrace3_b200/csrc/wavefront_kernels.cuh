@@ -39,6 +39,15 @@ struct Items {
   double *t, *u, *v;
 };
 
+// Photons that leave the wavefront because the (ray, patch) item list of their bounce is full: the state
+// before the pending query.  photon_trace_kernel (trace_kernels.cuh, persistent warps with the Newton
+// solver inline) finishes them from here on — same RNG addresses, so the same path.
+struct Spill {
+  double* st[9];             // org, dir, flux
+  unsigned long long* idd;   // photon id | dep << 56
+  unsigned* count;
+};
+
 struct StepArgs {
   DevScene scene;
   int patches_in_smem, max_dep, bounce, do_intersect, fast_math;
@@ -52,7 +61,7 @@ struct StepArgs {
   unsigned q_cap;
   unsigned* n_items_out;
   unsigned item_cap;
-  unsigned* overflow;
+  Spill spill;
   uint64_t begin, count;  // photon range per light of this batch
   Grid grid;
   const int32_t* cell_slot;
@@ -93,7 +102,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
   const unsigned n_in = c2 + nreg[3];
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-  unsigned queries = 0, solves = 0, photons = 0, deposits = 0, kept = 0;  // per thread, < 2^32
+  unsigned queries = 0, solves = 0, photons = 0, deposits = 0, kept = 0, spilled = 0;  // per thread, < 2^32
 
   for (unsigned base = warp_global * 32; base < n_in; base += n_warps * 32) {
     const unsigned vi = base + lane;
@@ -256,6 +265,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
     const unsigned my_slot = oreg == 0 ? kk : (oreg == 1 ? a.q_cap - 1 - kk : (oreg == 2 ? a.q_cap + kk : 2 * a.q_cap - 1 - kk));
     // ---- cooperative Bezier culling: per in-box ray, 32 lanes test 32 patch boxes (Bezier.h:178)
     unsigned my_begin = 0, my_cnt = 0;
+    bool spill_me = false;
     unsigned bm = __ballot_sync(FULL, alive && boxobj != 0);
     while (bm) {
       const int src = __ffs(bm) - 1;
@@ -291,9 +301,19 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
           if (total == 0) break;
           if (lane == 0) ibase = atomicAdd(a.n_items_out, total);
           ibase = __shfl_sync(FULL, ibase, 0);
-          if (ibase + total > a.item_cap) {  // item list full: drop (flagged, the host reports it)
-            if (lane == 0) atomicExch(a.overflow, 1u);
-            total = ibase < a.item_cap ? a.item_cap - ibase : 0;
+          if (ibase + total > a.item_cap) {
+            // Item list full: this photon leaves the wavefront (spill list) and the persistent tracer
+            // finishes it.  The first failed reservation may own the list's tail: give it well-formed
+            // items (this ray, its first boxed object's first patch) — the Newton kernel runs every
+            // entry below min(count, capacity); nobody reads their results.
+            const unsigned fp = (unsigned)sv.obj[__ffsll((long long)omask) - 1].first_patch | ((unsigned)(__ffsll((long long)omask) - 1) << 16);
+            for (unsigned k = ibase + lane; k < a.item_cap; k += 32) {
+              a.it_out.slot[k] = sslot;
+              a.it_out.patch[k] = fp;
+            }
+            total = 0;
+            if (lane == src) spill_me = true;
+            break;
           }
         }
       }
@@ -302,6 +322,18 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
         my_cnt = total;
       }
       if (lane == 0) solves += total;
+    }
+    if (spill_me) {  // rare: one atomic per photon
+      const unsigned k = atomicAdd(a.spill.count, 1u);  // < q_cap: every photon spills at most once
+      a.spill.st[0][k] = org.x; a.spill.st[1][k] = org.y; a.spill.st[2][k] = org.z;
+      a.spill.st[3][k] = dir.x; a.spill.st[4][k] = dir.y; a.spill.st[5][k] = dir.z;
+      a.spill.st[6][k] = flux.x; a.spill.st[7][k] = flux.y; a.spill.st[8][k] = flux.z;
+      a.spill.idd[k] = id | ((unsigned long long)dep << 56);
+      best.obj = -1;  // its queue entry reads "hit nothing" (no items): the next step drops it without a trace
+      best.dist = SPPM_MAX_NUM;
+      my_cnt = 0;
+      queries--;      // the query is counted where it is answered
+      spilled++;
     }
     if (alive) {
       const unsigned s = my_slot;
@@ -316,8 +348,9 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
     }
   }
   const unsigned long long q64 = warp_sum64(queries), s64 = warp_sum64(solves), p64 = warp_sum64(photons),
-                           d64 = warp_sum64(deposits), k64 = warp_sum64(kept);
+                           d64 = warp_sum64(deposits), k64 = warp_sum64(kept), o64 = warp_sum64(spilled);
   if (lane == 0) {
+    if (o64) atomicAdd(&a.counters->overflow, o64);
     if (q64) atomicAdd(&a.counters->isect_queries, q64);
     if (s64) atomicAdd(&a.counters->patch_solves, s64);
     if (p64) atomicAdd(&a.counters->photons, p64);
@@ -378,12 +411,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_i
 struct WfLayout {
   Queue q[2];
   Items it[2];
-  unsigned* counters;  // [4*b + r] queue count of region r at bounce b, [64+b] item counts, [96] overflow
+  unsigned* counters;  // [4*b + r] queue count of region r at bounce b, [64+b] item counts, [97] spilled photons
   unsigned item_cap;
+  Spill spill;         // [cap]
 };
 
+// (ray, patch) items a bounce of `cap` photons may queue before photons spill to the persistent tracer
+inline int64_t wf_item_cap(int64_t cap) { return std::max<int64_t>(cap * 2, 1 << 16); }
 size_t wf_bytes(int64_t cap, int64_t item_cap) {
-  return 2 * (size_t)(2 * cap) * (10 * 8 + 8 + 4 + 4 + 4) + 2 * (size_t)item_cap * (4 + 4 + 24) + 128 * 4 + 65536;
+  return 2 * (size_t)(2 * cap) * (10 * 8 + 8 + 4 + 4 + 4) + 2 * (size_t)item_cap * (4 + 4 + 24) + (size_t)cap * 80 + 128 * 4 + 65536;
 }
 WfLayout wf_layout(void* store, int64_t cap, int64_t item_cap) {
   WfLayout L;
@@ -408,7 +444,10 @@ WfLayout wf_layout(void* store, int64_t cap, int64_t item_cap) {
     it.u = (double*)take((size_t)item_cap * 8);
     it.v = (double*)take((size_t)item_cap * 8);
   }
+  for (int k = 0; k < 9; k++) L.spill.st[k] = (double*)take((size_t)cap * 8);
+  L.spill.idd = (unsigned long long*)take((size_t)cap * 8);
   L.counters = (unsigned*)take(128 * 4);
+  L.spill.count = L.counters + 97;
   L.item_cap = (unsigned)item_cap;
   return L;
 }
@@ -458,7 +497,7 @@ inline StepArgs wf_step_args(const WfBatch& w, const WfLayout& L, int b) {
   a.q_cap = w.q_cap;
   a.n_items_out = L.counters + 64 + b + 1;
   a.item_cap = L.item_cap;
-  a.overflow = L.counters + 96;
+  a.spill = L.spill;
   a.begin = w.begin;
   a.count = w.count;
   a.grid = w.grid;

@@ -386,6 +386,9 @@ int64_t dh_photon_trace_kernel(void* p, const SppmParams* prm, uint64_t begin, u
   a.cursor = &cursor;
   a.begin = begin;
   a.count = count;
+  a.r_count = nullptr;
+  for (int k = 0; k < 9; k++) a.r_st[k] = nullptr;
+  a.r_idd = nullptr;
   launch(photon_trace_kernel, a, blocks, bt(TRACE_THREADS));
   if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
   return (int64_t)n_dep;
@@ -424,16 +427,18 @@ void dh_patch_batch_kernel(void* p, const SppmParams* prm, int cull, int64_t n, 
 // per bounce, every diffuse deposit kept.  Returns the deposit count; -1 if the item list overflowed.
 int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin, uint64_t count, uint64_t pass,
                                   int step_blocks, int newton_blocks, int64_t cap, Deposit* out, uint64_t* counters9,
-                                  uint32_t* queue_counts /* [4 * (max_dep + 3)] or null */) {
+                                  uint32_t* queue_counts /* [4 * (max_dep + 3)] or null */,
+                                  int64_t item_cap_override /* > 0: a short item list, so that photons spill */) {
   DhScene* h = (DhScene*)p;
   const int64_t total = (int64_t)h->dev.n_light * (int64_t)count;
   if (total <= 0) return 0;
   DevCounters cnt;
   memset(&cnt, 0, sizeof(cnt));
-  const int64_t item_cap = std::max<int64_t>(total * 2, 1 << 16);
+  const int64_t item_cap = wf_item_cap(total);
   std::vector<unsigned char> store(wf_bytes(total, item_cap) + 256);
   void* base = (void*)(((uintptr_t)store.data() + 255) & ~(uintptr_t)255);
-  const WfLayout L = wf_layout(base, total, item_cap);
+  WfLayout L = wf_layout(base, total, item_cap);
+  if (item_cap_override > 0) L.item_cap = (unsigned)std::min<int64_t>(item_cap, item_cap_override);  // SPPM_WF_ITEM_CAP of wavefront.cu
   memset(L.counters, 0, 128 * 4);
   std::vector<uint32_t> key((size_t)cap), rank((size_t)cap);
   unsigned int slot_count[2] = {0, 0};
@@ -475,9 +480,31 @@ int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin
       launch(newton_items_kernel, n, newton_blocks, bt(TRACE_THREADS));
     }
   }
+  if (h->dev.n_patch > 0) {  // the spilled photons, finished by the persistent tracer (launch_photon_trace's resume mode)
+    unsigned long long cursor = 0;
+    PhotonArgs a;
+    a.c = tc;
+    a.grid = w.grid;
+    a.cell_slot = nullptr;
+    a.n_slots = 0;
+    a.keep_all = 1;
+    a.dep = out;
+    a.dep_key = key.data();
+    a.dep_rank = rank.data();
+    a.slot_count = slot_count;
+    a.dep_cap = (unsigned long long)cap;
+    a.dep_count = &n_dep;
+    a.cursor = &cursor;
+    a.begin = begin;
+    a.count = count;
+    a.r_count = L.spill.count;
+    for (int k = 0; k < 9; k++) a.r_st[k] = L.spill.st[k];
+    a.r_idd = L.spill.idd;
+    launch(photon_trace_kernel, a, newton_blocks, bt(TRACE_THREADS));
+  }
   if (counters9) memcpy(counters9, &cnt, sizeof(cnt));
   if (queue_counts) memcpy(queue_counts, L.counters, sizeof(uint32_t) * 4 * (size_t)(n_steps + 1));
-  return L.counters[96] ? -1 : (int64_t)n_dep;
+  return (int64_t)n_dep;
 }
 // ---- build_index + bin_deposits + launch_gather (gather.cu) with the product's kernels ----------
 // The host orchestration is restated here with std:: algorithms in place of CUB (stable sort by cell

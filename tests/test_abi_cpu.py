@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in sppm_b200.h but not exported"
         assert n in abi.PROTOTYPES, f"{n} has no ctypes prototype"
     assert set(abi.PROTOTYPES) == set(names)
-    assert lib.sppm_abi_version() == 2
+    assert lib.sppm_abi_version() == 3
 
 
 def test_struct_layout_matches_header(tmp_path):

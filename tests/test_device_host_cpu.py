@@ -526,6 +526,43 @@ def test_wavefront_equals_persistent_on_the_cpu(dh):
     assert ca["deposits"] == cb["deposits"] and ca["patch_solves"] == cb["patch_solves"]
 
 
+def _light_over_teapot_scene():
+    """The case the (ray, patch) item list can be too short for (2 items per photon and bounce): the light hangs
+    just above the teapot's bounding box (AABBbox::intersect only sees rays that ENTER a box, Q5, so a light inside
+    it queues nothing), and every downward ray passes the object box and several patch boxes: 1.5 solves per
+    emitted photon instead of the shipped scene's 0.037."""
+    from raytrace3_b200.scene import make_scene
+    sc = make_scene("reference", textures=None)
+    bz = [o for o in sc.objvec if o.kind == 2][0]
+    lo, hi = bz.P.reshape(-1, 3).min(0), bz.P.reshape(-1, 3).max(0)
+    sc.plvec[0].pos = tuple(0.5 * (lo + hi) + np.array([0.0, 0.6 * (hi[1] - lo[1]), 0.0]))
+    return sc
+
+
+@pytest.mark.parametrize("name,item_cap", [("reference", 16), ("reference", 1), ("stress", 64), ("light_over_teapot", 4096),
+                                           ("light_over_teapot", 0)])
+def test_wavefront_item_list_spills_to_the_persistent_tracer(dh, oracle, name, item_cap):
+    """A bounce whose item list is full hands its photons to photon_trace_kernel's resume mode instead of dropping
+    their Bezier solves (Bezier.h:240-282 must run for every boxed ray): deposits and counters equal the oracle's,
+    bit for bit, however short the list; item_cap = 0 is the product's sizing."""
+    sc = _light_over_teapot_scene() if name == "light_over_teapot" else _scene(name)
+    hs = dh.scene(sc)
+    prm = _params()
+    count = 6000
+    ref = oracle.photon_pass(sc, prm, 0, count, 4, keep_deposits=True)
+    dep, cnt, qc = hs.photon_trace_wavefront(prm, 0, count, 4, step_blocks=7, newton_blocks=5, item_cap=item_cap)
+    rd, rc = ref["dep"], ref["counters"]
+    order = np.lexsort((rd["bounce"], rd["photon"]))
+    for k in ("photon", "bounce", "x", "n", "flux"):
+        np.testing.assert_array_equal(dep[k], rd[k][order], err_msg=k)
+    assert cnt["photons"] == rc["photons"] and cnt["deposits"] == rc["deposits"]
+    assert cnt["patch_solves"] == rc["solves"]
+    if item_cap:
+        assert cnt["overflow"] > 0          # photons did spill
+    if name == "light_over_teapot":
+        assert rc["solves"] > count
+
+
 # ---- the hash grid and the FP32-filtered gather (gather_kernels.cuh) -----------------------------
 # build_index's kernels (cell keys, SoA permute, neighbourhood slots, work units), the deposit keys
 # and gather_filtered_kernel run as one-warp blocks; CUB's sorts / scans are std:: algorithms in the
