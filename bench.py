@@ -2,18 +2,23 @@
 """bench.py — photons traced+gathered per second (BASELINE.json metric M1) on N B200s.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl b200|reference]
+                  [--scaling weak|strong] [--update reference|progressive]
 
-A step = one round of RayTracer::PhotonMap (Raytracer.h:226-246): every rank traces
-`onetime` photons through the scene (Light::emit + PhotonTrace), gathers them into the
-replicated hit-point map, the per-round accumulators are summed over ranks (NCCL, N > 1) and
-HitPoint::update runs.  Weak scaling: `onetime` photons PER GPU per step.  The hit-point map
-(eye pass + hash grid) is built once before the timed region, as in the reference where one
-eye pass serves cnt rounds; `e2e` times the whole RayTracer::render() (scene upload from host
-memory, eye pass, grid build, one round, film resolve + read-back) through the public API.
+A step = one round of RayTracer::PhotonMap (Raytracer.h:226-246): the ranks trace the round's photons
+(Light::emit + PhotonTrace), gather them into the replicated hit-point map, the per-round accumulators are
+summed over ranks (NCCL, N > 1) and HitPoint::update runs.  Weak scaling (default workload): `onetime` photons
+PER GPU per step; strong scaling (caustics-1080p, stress-4k: BASELINE configs 4 / 5): the step's `onetime`
+photons are sharded over the GPUs.  The hit-point map (eye pass + hash grid) is built once before the timed
+region, as in the reference where one eye pass serves cnt rounds; `e2e` times RayTracer.render() of the host
+mirror (scene upload from pinned host memory, eye pass, grid build, cnt rounds, film resolve + read-back).
 
---impl reference times the CPU restatement of the reference (oracle/, OpenMP over all host
-cores, each thread an independent photon tracer as in Raytracer.h:442-447) on a bounded
-sample of the same workload; the GPU is not touched.
+Besides `value` the line carries: `roofline` (the kernel class with the largest total time per step, from
+serialised rounds timed with CUDA events between launches), `kernels` (every class the same way), `exact_mode`
+(the same steps with the reference's arithmetic order), `multi_gpu_parity` (N > 1), `cpu_baseline`.
+
+--impl reference times the CPU restatement of the reference (oracle/, OpenMP over all host cores, each thread
+an independent photon tracer as in Raytracer.h:442-447) on a bounded sample of the same workload; the GPU is
+not touched.
 """
 from __future__ import annotations
 
@@ -220,6 +225,40 @@ def run_reference(args):
     _emit(line)
 
 
+# BASELINE.json: config 4 shards 16 M photons/pass over the GPUs (strong), config 5 runs radius-shrinking passes
+WORKLOAD_DEFAULTS = {
+    "caustics-1080p": dict(scaling="strong", update="reference"),
+    "stress-4k": dict(scaling="strong", update="progressive"),
+}
+
+
+def csrc_digest() -> str:
+    """Digest of the kernel sources: ncu-derived numbers in profiles/ncu_traffic.json are only quoted when they
+    were captured from this very source."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "raytrace3_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith(".cuh"):  # the kernel bodies (the .cu files hold launchers and plumbing)
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel: str, workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from a capture of THIS kernel source), or
+    None: a number captured from another version of the kernels is not quoted."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("csrc_digest") != csrc_digest():
+            return None, None
+        e = t.get("kernels", {}).get(f"{kernel}@{workload}")
+        return (float(e["dram_bytes"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -231,8 +270,15 @@ def main():
     ap.add_argument("--trace", default="wavefront", choices=["wavefront", "persistent"])
     ap.add_argument("--gather", default="filtered", choices=["filtered", "exact"],
                     help="gather predicate: packed-FP32 interval filter + FP64 fallback (same newN), or FP64 on every pair")
+    ap.add_argument("--update", default=None, choices=["reference", "progressive"],
+                    help="HitPoint::update as shipped (a no-op on fresh hit points, Q1) or the radius-shrinking rule "
+                         "(default: progressive for stress-4k, as BASELINE config 5 states; reference otherwise)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak: `onetime` photons per GPU and step; strong: the step's `onetime` photons are sharded over the "
+                         "GPUs (default for caustics-1080p and stress-4k, as BASELINE configs 4 / 5 state)")
     ap.add_argument("--count-pairs", action="store_true", help="keep the diagnostic cand_pairs counter on in the timed loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exact-mode", action="store_true", help="skip the EXACT-arithmetic leg (exact_mode in the line)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-rounds", type=int, default=10, help="PhotonMap rounds per RayTracer::render() in the e2e leg "
                     "(the reference runs 10000 rounds per eye pass, Raytracer.h:384)")
@@ -246,7 +292,7 @@ def main():
     assert world == args.gpus or world == 1 and args.gpus == 1, f"launch with torchrun --nproc-per-node {args.gpus}"
 
     import torch
-    from raytrace3_b200 import Context, abi, row_range
+    from raytrace3_b200 import Context, RayTracer, abi, photon_range
     from raytrace3_b200.scene import make_scene, reference_camera
 
     dist = None
@@ -256,14 +302,30 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     wl = WORKLOADS[args.workload]
-    prm = make_params(abi, fast=args.newton == "fast")
-    prm.trace_mode = abi.SPPM_TRACE_PERSISTENT if args.trace == "persistent" else abi.SPPM_TRACE_WAVEFRONT
-    prm.gather_mode = abi.SPPM_GATHER_EXACT if args.gather == "exact" else abi.SPPM_GATHER_FILTERED
-    prm.count_pairs = 1 if args.count_pairs else 0   # diagnostic pair counter: off in the timed loop, see below
+    wd = WORKLOAD_DEFAULTS.get(args.workload, {})
+    scaling = args.scaling or wd.get("scaling", "weak")
+    update = args.update or wd.get("update", "reference")
+
+    def params_for(fast):
+        p = make_params(abi, fast=fast)
+        p.trace_mode = abi.SPPM_TRACE_PERSISTENT if args.trace == "persistent" else abi.SPPM_TRACE_WAVEFRONT
+        p.gather_mode = abi.SPPM_GATHER_EXACT if args.gather == "exact" else abi.SPPM_GATHER_FILTERED
+        p.update_mode = abi.SPPM_UPDATE_PROGRESSIVE if update == "progressive" else abi.SPPM_UPDATE_REFERENCE
+        p.count_pairs = 1 if args.count_pairs else 0   # diagnostic pair counter: off in the timed loop, see below
+        return p
+
+    prm = params_for(args.newton == "fast")
     ctx = Context(local_rank, prm)
     scene = make_scene(wl["scene"])
     cam = reference_camera(wl["w"], wl["h"])
     onetime = wl["onetime"]
+    n_light = len(scene.plvec)
+    # photons this rank traces per step, and the whole job's
+    if scaling == "weak":
+        my_begin, my_count, step_photons = rank * onetime, onetime, onetime * n_light * world
+    else:
+        my_begin, my_count = photon_range(onetime, rank, world)
+        step_photons = onetime * n_light
 
     def barrier():
         ctx.synchronize()
@@ -281,60 +343,89 @@ def main():
         ctx.comm_init_rank(rank, world, uid[0])
 
     def step(i):
-        # weak scaling: rank r traces the global photon indices [r*onetime, (r+1)*onetime) of round i
-        ctx.photon_pass(rank * onetime, onetime, 1 + i)
+        # round i: rank r traces its photon range of the round (ids are global: any sharding traces the same set)
+        ctx.photon_pass(my_begin, my_count, 1 + i)
         if world > 1:
             ctx.allreduce()
         ctx.update()
 
+    def timed(first, k):
+        barrier()
+        ctx.timer_record(0)
+        for i in range(k):
+            step(first + i)
+        ctx.timer_record(1)
+        t = ctx.timer_elapsed_ms()
+        barrier()
+        if dist is not None:
+            tt = torch.tensor([t], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt.item())
+        return t
+
+    next_round = 0
     for i in range(args.warmup):
         step(i)
+    next_round += args.warmup
     barrier()
     ctx.reset_counters()
     launches0 = ctx.counters()["launches"]
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ctx.timer_record(0)
-    for i in range(args.steps):
-        step(args.warmup + i)
-    ctx.timer_record(1)
-    ms = ctx.timer_elapsed_ms()
-    barrier()
+    ms = timed(next_round, args.steps)
+    next_round += args.steps
     clocks = sampler.stop() if sampler else None
     cnt = ctx.counters()
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    total_photons = onetime * len(scene.plvec) * world * args.steps
-    # work statistics (cand_pairs feeds the SURVEY 8d flop count): two untimed rounds with the
-    # diagnostic counter on -- the timed loop above runs with it off unless --count-pairs
+    steps = args.steps
+    value = step_photons * steps / (ms * 1e-3)
+
+    # ---- the same steps in EXACT arithmetic (Newton as written in Bezier.h:112-159 without FMA, sampling through
+    # acos / sin / cos as Vec3.h:90-115): what bit-exactness with the reference costs
+    exact_mode = None
+    if args.newton == "fast" and not args.no_exact_mode:
+        ctx.set_params(params_for(False))
+        k = max(2, min(steps, 10))
+        for i in range(3):
+            step(next_round + i)
+        ms_x = timed(next_round + 3, k)
+        next_round += 3 + k
+        exact_mode = {"value": step_photons * k / (ms_x * 1e-3), "unit": "photons/s", "ms_per_step": ms_x / k, "steps": k,
+                      "newton": "50x10 exact (Bezier.h:112-159 operation order, no FMA; bit-identical to the reference's own code)",
+                      "math": "exact (Vec3.h:90-115 through acos/sin/cos)"}
+        ctx.set_params(prm)
+
+    # ---- work statistics (cand_pairs feeds the SURVEY 8d flop count): two untimed rounds with the diagnostic
+    # counter on -- the timed loop above runs with it off unless --count-pairs
     prm.count_pairs = 1
     ctx.set_params(prm)
     ctx.reset_counters()
     for i in range(2):
-        step(args.warmup + args.steps + i)
+        step(next_round + i)
+    next_round += 2
     barrier()
     stat = ctx.counters()
-    cnt["cand_pairs"] = stat["cand_pairs"] * args.steps // 2
-    value = total_photons / (ms * 1e-3)
-    # serialised rounds (a device sync after every step, so no lane overlaps another): per-kernel
-    # times as ncu's launch list sees them, to check the kernels' shares of a round against it
+    cnt["cand_pairs"] = stat["cand_pairs"] * steps // 2
     prm.count_pairs = 1 if args.count_pairs else 0
     ctx.set_params(prm)
-    ctx.reset_counters()
-    n_serial = 4
-    for i in range(n_serial):
-        step(args.warmup + args.steps + 2 + i)
-        barrier()
-    ser = ctx.counters()
-    serial = {k: ser[f"ms_{k}"] / n_serial for k in ("trace", "sort", "gather")}
-    serial["round"] = serial["trace"] + serial["sort"] + serial["gather"]  # + update, 0.05 ms
 
-    # ---- e2e: RayTracer::render() through the public API with host buffers
-    from raytrace3_b200 import RayTracer
+    # ---- serialised rounds: every batch alone on the GPU with a CUDA event between its launches
+    # (sppm_set_profiling), so each kernel class gets the time an ncu launch list gives it
+    n_serial = 4 if onetime <= 4_000_000 else 2
+    ctx.reset_counters()
+    ctx.set_profiling(True)
+    for i in range(n_serial):
+        step(next_round + i)
+        barrier()
+    next_round += n_serial
+    ser = ctx.counters()
+    ctx.set_profiling(False)
+    ser_ms = {k: ser[f"ms_{k}"] / n_serial for k in ("step", "newton", "spill", "bin_scan", "bin_scatter", "gather_prep",
+                                                     "gather_kernel", "update", "allreduce")}
+    ser_round = sum(ser_ms.values())
+    ser_work = {k: ser[k] / n_serial for k in ("isect_queries", "patch_solves", "patch_culled", "deposits_kept", "acc_pairs",
+                                                "spilled_photons", "photons")}
+
+    # ---- e2e: RayTracer::render() of the host mirror (the call a user makes) with pinned host buffers
     e2e_ms, e2e_phases = [], None
-    # host buffers of the e2e leg live in pinned memory (the contract's H2D / D2H from pinned host memory):
-    # the texture pixels the scene hands to sppm_scene_upload and the film sppm_resolve writes
     pins = []
     for tex in {id(o.texture): o.texture for o in scene.objvec if o.texture is not None}.values():
         buf = torch.empty(tex.map.shape, dtype=torch.uint8, pin_memory=True)
@@ -343,44 +434,35 @@ def main():
         tex.map = arr
         pins.append(buf)
     film_pin = torch.zeros((wl["h"], wl["w"], 3), dtype=torch.float64, pin_memory=True)
-    film = film_pin.numpy()
+    cam.pic = film_pin.numpy()
     h2d = scene.texture_bytes() + sum(o.P.nbytes for o in scene.objvec if o.kind == 2) + 328 * len(scene.objvec) + 256
-    d2h = film.nbytes + 8 * 3
+    d2h = cam.pic.nbytes + 8 * 3
+    e2e_onetime = onetime * world if scaling == "weak" else onetime     # photons per round over all ranks
+    rt = RayTracer(ctx, rank=rank, world=world)
+    rt.camera, rt.scene, rt.cnt, rt.onetime = cam, scene, args.e2e_rounds, e2e_onetime
     for i in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         barrier()
         t0 = time.perf_counter()
-        ctx.upload_scene(scene)                      # H2D: objects, patches, textures (pinned host memory)
-        t1 = time.perf_counter()
-        if world > 1:  # eye-pass sharding: every rank traces its film rows, the shares are exchanged over NCCL
-            r0, r1 = row_range(cam.h, rank, world)
-            ctx.eye_pass_rows(cam, 100 + i, r0, r1)
-            ctx.allgather_hitpoints()
-        else:
-            ctx.eye_pass(cam, 100 + i)
-        t2 = time.perf_counter()
-        ctx.build_index()
-        t3 = time.perf_counter()
-        for rnd in range(args.e2e_rounds):
-            ctx.photon_pass(rank * onetime, onetime, 200 + i * args.e2e_rounds + rnd)
-            if world > 1:
-                ctx.allreduce()
-            ctx.update()
-        ctx.synchronize()
-        t4 = time.perf_counter()
-        ctx.resolve(args.e2e_rounds, onetime * world, wl["w"], wl["h"], out=film)   # D2H: the film
+        rt._scene_uploaded = None      # H2D every step: objects, patches, textures from pinned host memory
+        rt.pass_base = 100 + i
+        rt.render()                    # eye pass, grid build, cnt rounds, resolve, D2H of the film into cam.pic
         barrier()
-        t5 = time.perf_counter()
+        t1 = time.perf_counter()
         if i > 0:
-            e2e_ms.append((t5 - t0) * 1e3)
-            e2e_phases = {"upload": (t1 - t0) * 1e3, "eye": (t2 - t1) * 1e3, "build": (t3 - t2) * 1e3,
-                          "photon_rounds": (t4 - t3) * 1e3, "resolve_readback": (t5 - t4) * 1e3}
+            e2e_ms.append((t1 - t0) * 1e3)
     e2e = statistics.median(e2e_ms) if e2e_ms else float('nan')
     if dist is not None:
         t = torch.tensor([e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = float(t.item())
-    e2e_value = onetime * len(scene.plvec) * world * args.e2e_rounds / (e2e * 1e-3)
+    e2e_value = e2e_onetime * n_light * args.e2e_rounds / (e2e * 1e-3)
     e2e_counters = ctx.counters()
+
+    # ---- multi-GPU parity (world > 1): one small round sharded over the ranks + allreduce must leave every rank
+    # with the same accumulators, equal to the same round traced by rank 0 alone
+    mgp = None
+    if world > 1:
+        mgp = multi_gpu_parity(ctx, Context, abi, torch, dist, scene, cam, prm, rank, world, local_rank, photon_range)
 
     if rank != 0:
         if dist is not None:
@@ -388,106 +470,173 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (per launch = per step at this batch size)
+    # ---- rooflines.  Algorithmic work per launch: bytes and flops per unit x units per step,
+    # divided by the launches per step; times from the serialised rounds above (CUDA events on the launching
+    # stream, measured live in this run).
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     fp64_peak = ctx.fp64_peak()
-    steps = args.steps
-    ms_trace, ms_sort, ms_gather = cnt["ms_trace"] / steps, cnt["ms_sort"] / steps, cnt["ms_gather"] / steps
-    dep_kept, cand, acc = cnt["deposits_kept"] / steps, cnt["cand_pairs"] / steps, cnt["acc_pairs"] / steps
-    solves, queries = cnt["patch_solves"] / steps, cnt["isect_queries"] / steps
-    gather_bytes = 136.0 * n_hp + 72.0 * dep_kept
-    gather_flops = 13.0 * cand + 9.0 * acc
-    trace_bytes = 84.0 * dep_kept                                      # deposits written (80 B + 4 B key)
-    trace_flops = 175000.0 * solves + 140.0 * queries                  # Newton (350 x 500) + analytic tests
-    trace_name = "photon_trace_kernel" if prm.trace_mode == abi.SPPM_TRACE_PERSISTENT else "photon_step_kernel+newton_items_kernel"
+    per = lambda k: cnt[k] / steps
+    dep_kept, cand, acc = per("deposits_kept"), per("cand_pairs"), per("acc_pairs")
+    solves, culled, queries = per("patch_solves"), per("patch_culled"), per("isect_queries")
+    n_batches = max(1, -(-my_count * n_light // (1 << 21)))
+    n_bounce = prm.max_dep + 2
+    has_bezier = any(o.kind == 2 for o in scene.objvec)
+    wave = prm.trace_mode != abi.SPPM_TRACE_PERSISTENT
     gather_name = "gather_kernel" if args.gather == "exact" else "gather_filtered_kernel"
-    kern = {
-        trace_name: dict(ms=ms_trace, bytes=trace_bytes, flops=trace_flops),
-        gather_name: dict(ms=ms_gather, bytes=gather_bytes, flops=gather_flops),
-    }
-    # the dominant KERNEL is the largest single launch: gather_kernel (one launch per step); the
-    # tracer's time is spread over ~29 launches (15 step + 14 Newton kernels, <= 0.5 ms each)
-    dom = gather_name if ms_gather * 4 >= ms_trace or prm.trace_mode != abi.SPPM_TRACE_PERSISTENT else trace_name
-    if prm.trace_mode == abi.SPPM_TRACE_PERSISTENT and ms_trace > ms_gather:
-        dom = trace_name
-    d = kern[dom]
-    achieved = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
-    # dram__bytes_read.sum + dram__bytes_write.sum of one gather launch on this workload, from the
-    # ncu --set full captures profiles/r1_A_gather_filtered_ncu.md (297.9 MB read + 30.8 MB written)
-    # and profiles/r1_h_gather_ncu.md (exact kernel: 621.3 + 26.4 MB)
-    traffic = None
-    if dom == gather_name and args.workload == DEFAULT_WORKLOAD and world == 1:
-        traffic = 647.7e6 if args.gather == "exact" else 328.7e6
-    if args.gather == "exact":
-        note = ("the binding resource is the FP64 pipe (ncu: 46 % FP64-pipe active, DRAM 2 % busy): per step the kernel "
-                "distance-tests ~5x more (hit point, deposit) pairs than cand_pairs (27-cell neighbourhood vs ball), "
-                "8 FP64 ops each, against 0.5 GB of compulsory traffic; fp64_tflops counts only the SURVEY 8d flops")
+    K = {}
+
+    def add(name, ms_k, launches, bytes_, flops, bound):
+        if ms_k <= 0:
+            return
+        gbs = bytes_ / (ms_k * 1e-3) / 1e9
+        tf = flops / (ms_k * 1e-3) / 1e12
+        K[name] = {"ms_per_step": ms_k, "launches_per_step": launches, "ms_per_launch": ms_k / launches,
+                   "share_of_round": ms_k / ser_round if ser_round > 0 else None, "bound": bound,
+                   "algorithmic_bytes_per_step": bytes_, "algorithmic_flops_per_step": flops,
+                   "GBps": gbs, "hbm_frac": gbs / hbm_peak, "fp64_tflops": tf,
+                   "fp64_frac": tf / fp64_peak if fp64_peak > 0 else None}
+
+    executed = max(solves - culled, 0.0)
+    if wave:
+        # step kernel: 100 B of queue state read + 100 B written per live photon and bounce, 88 B per kept deposit
+        # (80 B record + key + rank), 40 B per (ray, patch) item (slot, patch written; t, u, v read back)
+        add("photon_step_kernel", ser_ms["step"], n_bounce * n_batches, 200.0 * queries + 88.0 * dep_kept + 40.0 * solves,
+            140.0 * queries, "latency (issue slots / long scoreboard), HBM second")
+        if has_bezier:
+            add("newton_items_kernel", ser_ms["newton"], (n_bounce - 1) * n_batches, 40.0 * solves, 175000.0 * executed, "fp64")
     else:
-        note = ("instruction-issue bound, not HBM bound (ncu r1_A: issue slots 70 % busy, ALU pipe 39 %, FMA pipe 24 % "
-                "[packed FADD2/FFMA2], FP64 pipe 20 %, DRAM 5 % busy): ~0.5 G (hit point, deposit) pairs survive the "
-                "bounding-box cull and are classified in FP32 at ~17 warp instructions per 64 pairs, against 0.3 GB of "
-                "compulsory traffic; the timed span is measured while a photon-tracing lane shares the SMs "
-                "(0.84 ms when the kernel runs alone); fp64_tflops counts only the SURVEY 8d flops")
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": d["bytes"],
+        add("photon_trace_kernel", ser_ms["spill"] + ser_ms["step"], n_batches, 88.0 * dep_kept, 175000.0 * executed + 140.0 * queries, "fp64 / latency")
+    add("deposit_binning (cub scan + dep_scatter_kernel)", ser_ms["bin_scan"] + ser_ms["bin_scatter"], 2 * n_batches,
+        168.0 * dep_kept + 8.0 * n_hp / 4, 0.0, "hbm")
+    add(gather_name, ser_ms["gather_kernel"], n_batches, 136.0 * n_hp + 72.0 * dep_kept, 13.0 * cand + 9.0 * acc,
+        "instruction issue (packed FP32 classification), HBM is the stated roofline")
+    add("update_kernel", ser_ms["update"], 1, 136.0 * n_hp, 6.0 * n_hp, "hbm")
+    dom = max(K, key=lambda k: K[k]["ms_per_step"])
+    d = K[dom]
+    traffic, traffic_src = ncu_traffic(dom, args.workload) if world == 1 else (None, None)
+    in_loop = {"trace+binning": cnt["ms_trace"] / steps, "gather(prep+kernel)": cnt["ms_gather"] / steps}
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": d["GBps"],
+                "peak": hbm_peak, "unit": "GB/s", "frac": d["hbm_frac"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes": d["algorithmic_bytes_per_step"] / d["launches_per_step"],
+                "ms_per_launch": d["ms_per_launch"], "launches_per_step": d["launches_per_step"],
+                "share_of_round": d["share_of_round"],
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, sustained copy)",
-                "ms_per_launch": d["ms"], "share_of_step": d["ms"] / (ms / steps),
-                "serialized": {"what": "rounds separated by device syncs (no overlap between lanes): the view ncu's launch list has",
-                               "ms_per_launch": serial["gather"], "trace_and_binning_ms": serial["trace"],
-                               "share_of_round": serial["gather"] / serial["round"] if serial["round"] > 0 else None,
-                               "GBps": d["bytes"] / (serial["gather"] * 1e-3) / 1e9 if dom == gather_name and serial["gather"] > 0 else None},
-                "fp64_tflops": d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0, "fp64_peak_tflops": fp64_peak,
-                "fp64_frac": (d["flops"] / (d["ms"] * 1e-3) / 1e12 / fp64_peak) if d["ms"] > 0 and fp64_peak > 0 else None,
-                "note": note}
-    kernels = {k: {"ms_per_step": v["ms"], "GBps": v["bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0,
-                   "hbm_frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak if v["ms"] > 0 else 0.0,
-                   "fp64_tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0} for k, v in kern.items()}
-    kernels["deposit_binning"] = {"ms_per_step": ms_sort}
-    kernels["note"] = ("rounds rotate over four lanes: the traces of rounds i+1 .. i+3 (lane streams) overlap the gather of round i "
-                       "(main stream); per-kernel ms are event spans on their own stream and sum to more than ms_per_step")
+                "timing": "CUDA events on the launching stream around every launch of the class, in serialised rounds of this run "
+                          "(sppm_set_profiling: a batch alone on the GPU, as ncu's launch list sees it); "
+                          "in the pipelined timed loop the lanes' spans overlap (in_pipeline_span_ms) and do not add up to ms_per_step",
+                "in_pipeline_span_ms": in_loop, "serialized_round_ms": ser_round,
+                "fp64_tflops": d["fp64_tflops"], "fp64_peak_tflops": fp64_peak, "fp64_frac": d["fp64_frac"],
+                "binding_resource": d["bound"],
+                "dominant_by": "largest total time per step among the kernel classes (serialised)"}
 
     # ---- Bezier ray-patch intersections per second (metric M2), device-resident microbench
     m2 = None
-    if any(o.kind == 2 for o in scene.objvec):
+    if has_bezier:
         npairs = 1 << 18
         ms_rep = ctx.bezier_patch_bench(npairs, 3)
+        nt = K.get("newton_items_kernel")
         m2 = {"value": npairs / (ms_rep * 1e-3), "unit": "ray-patch isects/s", "pairs": npairs, "ms": ms_rep,
               "fp64_tflops": 175000.0 * npairs / (ms_rep * 1e-3) / 1e12, "fp64_peak_tflops": fp64_peak,
-              "in_render": solves * steps / (cnt["ms_trace"] * 1e-3) if cnt["ms_trace"] > 0 else None}
+              "in_render": {"executed_solves_per_step": executed, "culled_per_step": culled,
+                            "isects_per_s": executed / (nt["ms_per_step"] * 1e-3) if nt else None,
+                            "fp64_frac": nt["fp64_frac"] if nt else None,
+                            "what": "solves that ran (patch_solves - patch_culled) / serialised newton_items_kernel time"}}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         hp = ctx.export_hitpoints()
         cpu, _, _ = cpu_photon_baseline(args.workload, scene, make_params(abi, fast=False), hp, cam=cam)
 
+    ph = onetime * n_light if scaling == "strong" else my_count * n_light
     line = {
         "metric": "photons traced+gathered/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "scene": wl["scene"], "film": [wl["w"], wl["h"]], "hit_points": n_hp,
-                   "photons_per_gpu_per_step": onetime * len(scene.plvec), "newton": f"50x10 {args.newton}", "tracer": args.trace, "gather": args.gather,
-                   "update_mode": "reference", "l2": "inputs larger than L2 (deposit list + hit-point map > 126 MB); new photons every step",
-                   "textures": "synthetic, reference sizes", "parallelism": f"photons x{world}, hit points replicated"},
+                   "photons_per_step": step_photons, "photons_per_gpu_per_step": my_count * n_light,
+                   "newton": f"50x10 {args.newton}", "math": "fast" if args.newton == "fast" else "exact", "tracer": args.trace,
+                   "gather": args.gather, "update_mode": update,
+                   "l2": "inputs larger than L2 (deposit list + hit-point map > 126 MB); new photons every step",
+                   "textures": "synthetic, reference sizes",
+                   "parallelism": f"photons x{world} ({scaling}), hit points replicated, allreduce of dN/dtao per step"},
         "e2e": {"value": e2e_value, "unit": "photons/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e, "rounds_per_step": args.e2e_rounds, "phases_ms": e2e_phases,
-                "what": f"RayTracer::render() with cnt={args.e2e_rounds}: host scene+texture upload, eye pass, grid build, "
-                        f"{args.e2e_rounds} PhotonMap rounds, resolve, film read-back (the reference runs cnt=10000 rounds per eye pass)"},
+                "ms_per_step": e2e, "rounds_per_step": args.e2e_rounds,
+                "phases_ms": {"eye": e2e_counters["ms_eye"], "build": e2e_counters["ms_build"], "resolve": e2e_counters["ms_resolve"]},
+                "what": f"RayTracer.render() of the host mirror (raytrace3_b200.api, twin of include/raytracer/Raytracer.h) with "
+                        f"cnt={args.e2e_rounds}, onetime={e2e_onetime}: scene + textures from pinned host memory, eye pass, grid build, "
+                        f"PhotonMap (rounds fused into one photon pass while the update is the reference's), resolve, film "
+                        f"read-back into pinned camera.pic (the reference runs cnt=10000 rounds per eye pass)"},
         "gpu_launches": int(cnt["launches"] - launches0),
         "clocks": clocks,
         "roofline": roofline,
-        "kernels": kernels,
+        "kernels": K,
+        "exact_mode": exact_mode,
+        "multi_gpu_parity": mgp,
+        "allreduce_ms_per_step": cnt["ms_allreduce"] / steps if world > 1 else None,
         "cpu_baseline": cpu,
         "bezier_isects": m2,
-        "per_photon": {"isect_queries": queries / (onetime * len(scene.plvec)), "deposits": cnt["deposits"] / steps / (onetime * len(scene.plvec)),
-                       "deposits_kept": dep_kept / (onetime * len(scene.plvec)), "cand_pairs": cand / (onetime * len(scene.plvec)),
-                       "patch_solves": solves / (onetime * len(scene.plvec))},
+        "per_photon": {"isect_queries": queries / ph, "deposits": per("deposits") / ph,
+                       "deposits_kept": dep_kept / ph, "cand_pairs": cand / ph,
+                       "patch_solves": solves / ph, "patch_solves_executed": executed / ph,
+                       "spilled": per("spilled_photons") / ph},
         "setup_ms": {"eye": setup["ms_eye"], "build": setup["ms_build"], "eye_e2e": e2e_counters["ms_eye"], "build_e2e": e2e_counters["ms_build"]},
     }
     _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def multi_gpu_parity(ctx, Context, abi, torch, dist, scene, cam, prm, rank, world, local_rank, photon_range):
+    """One small round, sharded over the ranks (photon_range) + NCCL allreduce + update, against the same round
+    traced by rank 0 alone in a second context: newN identical on every rank and equal to the one-GPU run's,
+    tao within 1e-11 (summation order).  Returns "ok" or a description of the first difference."""
+    import hashlib
+    small = 200_000
+    p = abi.SppmParams.from_buffer_copy(prm)
+    p.count_pairs = 0
+    ctx.set_params(p)
+    ctx.build_index()                      # fresh accumulators on the benchmark's hit-point map
+    b, c = photon_range(small, rank, world)
+    ctx.photon_pass(b, c, 7777)
+    ctx.allreduce()
+    ctx.update()
+    n = ctx.counters()["hit_points"]
+    st = ctx.export_stats(n)
+    digest = hashlib.sha256(st["newN"].tobytes()).digest()[:8]
+    mine = torch.tensor(list(digest), dtype=torch.uint8, device=f"cuda:{local_rank}")
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    same_ranks = all(bool((v == allv[0]).all().item()) for v in allv)
+    tsum = torch.tensor(st["tao"].sum(0), dtype=torch.float64, device=f"cuda:{local_rank}")
+    tall = [torch.empty_like(tsum) for _ in range(world)]
+    dist.all_gather(tall, tsum)
+    out = "ok"
+    if not same_ranks:
+        out = "newN differs between ranks"
+    if rank == 0:
+        with Context(local_rank, p) as solo:
+            solo.upload_scene(scene)
+            m = solo.eye_pass(cam, 0)
+            solo.build_index()
+            solo.photon_pass(0, small, 7777)
+            solo.update()
+            ref = solo.export_stats(m)
+        if m != n or not np.array_equal(ref["newN"], st["newN"]):
+            out = f"newN of the {world}-GPU round differs from the 1-GPU round ({int((ref['newN'] != st['newN']).sum()) if m == n else 'hit-point counts differ'})"
+        elif not np.allclose(ref["tao"], st["tao"], rtol=1e-11, atol=1e-300):
+            out = "tao differs from the 1-GPU round beyond 1e-11"
+        elif int(st["newN"].sum()) == 0:
+            out = "empty round"
+        else:
+            rel = max(abs(float(t[k]) - float(tall[0][k])) / max(1e-300, abs(float(tall[0][k]))) for t in tall for k in range(3))
+            if rel > 1e-12:
+                out = f"tao sums differ between ranks by {rel:.2e}"
+            else:
+                out = {"status": "ok", "photons": small, "ranks": world, "newN_sum": int(st["newN"].sum()),
+                       "what": "newN bit-identical on all ranks and equal to a 1-GPU run of the same round; tao <= 1e-11"}
+    return out
 
 
 _REAL_STDOUT = None

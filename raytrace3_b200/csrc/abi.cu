@@ -54,6 +54,14 @@ unsigned long long* scalars(sppm_ctx* c) { return (unsigned long long*)c->dev_sc
 // into the host counters when the ring is full or at the next natural sync point, so the
 // photon pass itself never waits for the device.
 void fold_timings(sppm_ctx* c) {
+  if (c->a_pending) {
+    cudaEventSynchronize(c->aev[c->a_pending - 1][1]);
+    for (int i = 0; i < c->a_pending; i++) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, c->aev[i][0], c->aev[i][1]) == cudaSuccess) c->host_counters.ms_allreduce += ms;
+    }
+    c->a_pending = 0;
+  }
   if (c->t_pending == 0) return;
   cudaEventSynchronize(c->tev[c->t_pending - 1][c->t_has_gather[c->t_pending - 1] ? 3 : 1]);
   for (int i = 0; i < c->t_pending; i++) {
@@ -242,6 +250,8 @@ int sppm_ctx_create(int device, sppm_ctx** out) {
   for (int i = 0; i < 8 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   for (int i = 0; i < sppm_ctx::TIMING_RING && ok; i++)
     for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&c->tev[i][k]) == cudaSuccess;
+  for (int i = 0; i < sppm_ctx::TIMING_RING && ok; i++)
+    for (int k = 0; k < 2 && ok; k++) ok = cudaEventCreate(&c->aev[i][k]) == cudaSuccess;
   ok = ok && dev_reserve(c->dev_scalars, 64) == cudaSuccess && dev_reserve(c->counters, sizeof(DevCounters)) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->ev_setup, cudaEventDisableTiming) == cudaSuccess;
   if (const char* e = getenv("SPPM_LANES")) c->n_lanes = std::max(1, std::min((int)sppm_ctx::MAX_LANES, atoi(e)));
@@ -293,6 +303,9 @@ void sppm_ctx_destroy(sppm_ctx* c) {
   for (int i = 0; i < sppm_ctx::TIMING_RING; i++)
     for (int k = 0; k < 4; k++)
       if (c->tev[i][k]) cudaEventDestroy(c->tev[i][k]);
+  for (int i = 0; i < sppm_ctx::TIMING_RING; i++)
+    for (int k = 0; k < 2; k++)
+      if (c->aev[i][k]) cudaEventDestroy(c->aev[i][k]);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -562,6 +575,9 @@ int sppm_allreduce(sppm_ctx* c) {
   if (!c->nccl_comm || c->nranks <= 1 || c->n_hp == 0) return SPPM_OK;
   Bind b(c);
   NcclApi& n = nccl();
+  if (c->a_pending == sppm_ctx::TIMING_RING) fold_timings(c);
+  cudaEvent_t* ae = c->aev[c->a_pending];
+  CU(c, cudaEventRecord(ae[0], c->stream));
   ncclResult_t r = n.GroupStart();
   if (r == ncclSuccess) r = n.AllReduce(c->soa.dN, c->soa.dN, (size_t)c->n_hp, ncclInt32, ncclSum, (ncclComm_t)c->nccl_comm, c->stream);
   if (r == ncclSuccess)
@@ -569,6 +585,8 @@ int sppm_allreduce(sppm_ctx* c) {
   ncclResult_t r2 = n.GroupEnd();
   if (r == ncclSuccess) r = r2;
   if (r != ncclSuccess) return fail(c, SPPM_ERR_NCCL, std::string("ncclAllReduce: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
+  CU(c, cudaEventRecord(ae[1], c->stream));
+  c->a_pending++;
   return SPPM_OK;
 }
 
@@ -576,7 +594,15 @@ int sppm_update(sppm_ctx* c) {
   if (!c) return SPPM_ERR_INVALID;
   if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
   Bind b(c);
+  CU(c, c->prof.mark(PK_UPDATE, c->stream));
   CU(c, launch_update(c));
+  if (c->profiling) {
+    CU(c, c->prof.mark(PK_END, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    double bk[PK_N] = {};
+    c->prof.fold(bk);
+    c->host_counters.ms_update += bk[PK_UPDATE];
+  }
   return SPPM_OK;
 }
 

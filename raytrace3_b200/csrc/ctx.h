@@ -86,7 +86,7 @@ struct DevCounters {
 };
 
 // sppm_set_profiling: one event before every launch of a batch; the span up to the next event goes to a bucket
-enum ProfKind { PK_STEP, PK_NEWTON, PK_SPILL, PK_BIN_SCAN, PK_BIN_SCATTER, PK_GATHER_PREP, PK_GATHER_KERNEL, PK_END, PK_N };
+enum ProfKind { PK_STEP, PK_NEWTON, PK_SPILL, PK_BIN_SCAN, PK_BIN_SCATTER, PK_GATHER_PREP, PK_GATHER_KERNEL, PK_UPDATE, PK_END, PK_N };
 struct ProfMarks {
   std::vector<cudaEvent_t> ev;
   std::vector<int> kind;
@@ -196,6 +196,8 @@ struct sppm_ctx {
   static constexpr int TIMING_RING = 32;
   cudaEvent_t tev[TIMING_RING][4] = {};  // per batch: trace start, bin start, gather start, gather end
   int t_pending = 0;          // batches whose timings are not folded into host_counters yet
+  cudaEvent_t aev[TIMING_RING][2] = {};  // sppm_allreduce: start / end on the main stream
+  int a_pending = 0;
   bool t_has_gather[TIMING_RING] = {};
   // NCCL (dlopen)
   void* nccl_comm = nullptr;

@@ -645,7 +645,9 @@ __device__ __noinline__ void careful_pairs(const HpSoA s, const int i, const dou
 // {ny0,ny1,nz0,nz1} in FP32 and the two fluxes {fx0,fy0} {fz0,fx1} {fy1,fz1} in FP64; the
 // accumulation is predicated, not branched.
 constexpr int HBMAX = UNIT_HP > 32 ? 2 : 1;  // hit points per lane
-template <bool UNI, bool COUNT, int HB>
+// NN = false: every hit point of the unit has the same normal, the normal test of Raytracer.h:154 was made
+// once per deposit (in FP64, exactly) when the slice was culled, and the loop tests distances only.
+template <bool UNI, bool COUNT, int HB, bool NN = true>
 __device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const int j0, const int jstep, const int npair,
                                            const HpF (&h)[HBMAX], const float sr2f, int (&c)[HBMAX], unsigned& cand,
                                            double (&acc)[HBMAX][3], float (&uv)[HBMAX], float (&un)[HBMAX]) {
@@ -655,7 +657,9 @@ __device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const 
   const int stride = jstep * F_PAIR_F4;
 #pragma unroll 2
   for (int j = j0; j < npair; j += jstep, q += stride) {
-    const float4 A = q[0], B = q[1], C = q[2];
+    const float4 A = q[0], B = q[1];
+    float4 C = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NN) C = q[2];
     const double2 F0 = *reinterpret_cast<const double2*>(q + 3), F1 = *reinterpret_cast<const double2*>(q + 4),
                   F2 = *reinterpret_cast<const double2*>(q + 5);
 #pragma unroll
@@ -666,13 +670,16 @@ __device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const 
       float2 vv = f2mul(vx, vx);
       vv = f2fma(vy, vy, vv);
       vv = f2fma(vz, vz, vv);
-      float2 nn = f2mul(bc2(h[b].nx), make_float2(B.z, B.w));
-      nn = f2fma(bc2(h[b].ny), make_float2(C.x, C.y), nn);
-      nn = f2fma(bc2(h[b].nz), make_float2(C.z, C.w), nn);
+      float2 nn = make_float2(1.f, 1.f);
+      if (NN) {
+        nn = f2mul(bc2(h[b].nx), make_float2(B.z, B.w));
+        nn = f2fma(bc2(h[b].ny), make_float2(C.x, C.y), nn);
+        nn = f2fma(bc2(h[b].nz), make_float2(C.z, C.w), nn);
+        const float2 dn = f2sub(nn, bc2(thrf));
+        un[b] = fminf(un[b], fminf(fabsf(dn.x), fabsf(dn.y)));
+      }
       const float2 dv = f2sub(vv, bc2(sr2f));
-      const float2 dn = f2sub(nn, bc2(thrf));
       uv[b] = fminf(uv[b], fminf(fabsf(dv.x), fabsf(dv.y)));
-      un[b] = fminf(un[b], fminf(fabsf(dn.x), fabsf(dn.y)));
       bool in0 = vv.x < sr2f, in1 = vv.y < sr2f;
       if (COUNT) cd += (__float_as_uint(dv.x) >> 31) + (__float_as_uint(dv.y) >> 31);  // dv < 0 (never -0)
       if (!UNI) {
@@ -681,11 +688,11 @@ __device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const 
         in0 = in0 && vv.x < h[b].r2f;
         in1 = in1 && vv.y < h[b].r2f;
       }
-      if (in0 && nn.x > thrf) {
+      if (in0 && (!NN || nn.x > thrf)) {
         c[b]++;
         acc[b][0] += F0.x; acc[b][1] += F0.y; acc[b][2] += F1.x;
       }
-      if (in1 && nn.y > thrf) {
+      if (in1 && (!NN || nn.y > thrf)) {
         c[b]++;
         acc[b][0] += F1.y; acc[b][1] += F2.x; acc[b][2] += F2.y;
       }
@@ -834,10 +841,11 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
     const double half_x = 0.5 * ncx * cell * (1.0 + 1e-7), M_x = (0.5 * ncx + 1.0) * cell * (1.0 + 1e-6);
     const double Mn = sqrt(M_x * M_x + 2.0 * M_yz * M_yz);
     const double band_v = SPPM_F_U * (8.0 * a.search_r2 + 6.0 * sqrt(a.search_r2) * Mn) + 1e-13 * Mn * Mn;
-    const float cull_thr = __double2float_ru(a.search_r2 + 2.0 * band_v);
     HpF hp[HBMAX];
     bool far_hp[HBMAX] = {};
-    bool uni_me = true;
+    bool uni_me = true, nuni_me = true;
+    const double rnx = a.s.nx[h0], rny = a.s.ny[h0], rnz = a.s.nz[h0];  // the unit's first normal (uniform loads)
+    double rmax = 0;  // largest R2 among the unit's hit points on the FP32 path
     float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
 #pragma unroll
     for (int b = 0; b < HBMAX; b++) {
@@ -857,10 +865,24 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
           blo[0] = fminf(blo[0], hp[b].x); blo[1] = fminf(blo[1], hp[b].y); blo[2] = fminf(blo[2], hp[b].z);
           bhi[0] = fmaxf(bhi[0], hp[b].x); bhi[1] = fmaxf(bhi[1], hp[b].y); bhi[2] = fmaxf(bhi[2], hp[b].z);
           uni_me = uni_me && (r2 == a.search_r2);
+          nuni_me = nuni_me && (nx == rnx && ny == rny && nz == rnz);
+          rmax = fmax(rmax, r2);
         }
       }
     }
     const bool uni = __all_sync(FULL, uni_me);
+    // All hit points of the unit (on the FP32 path) carry the same normal, bit for bit — the units of a plane, i.e.
+    // most of them: hp->n.dot(N) (Raytracer.h:154) then has ONE value per deposit, which the cull below computes in
+    // FP64 with the reference's expression, and the pair loop leaves the normal out (fast_pairs<.., NN = false>).
+    // Not in the diagnostic COUNT build: cand_pairs counts pairs by distance alone.
+    const bool nuni = !COUNT && __all_sync(FULL, nuni_me);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) rmax = fmax(rmax, __shfl_xor_sync(FULL, rmax, off));
+    // Cull radius: a pair is accepted only if vv < searchR2 AND vv <= R2 of its hit point (Raytracer.h:146,154), so a
+    // deposit farther than min(searchR2, max R2 of the unit) from the unit's bounding box cannot be accepted by any
+    // of its hit points.  Once HitPoint::update has shrunk the radii (PROGRESSIVE passes) this removes most of the
+    // pairs between sqrt(R2) and sqrt(searchR2).  The diagnostic candidate count (vv < searchR2) needs them all.
+    const float cull_thr = __double2float_ru((COUNT ? a.search_r2 : fmin(a.search_r2, rmax)) + 2.0 * band_v);
 #pragma unroll
     for (int k = 0; k < 3; k++)
 #pragma unroll
@@ -894,12 +916,14 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
           q3 = q[3]; q4 = q[4];
           const double ax = q0.x - ox, ay = q0.y - oy, az = q1.x - oz;
           const bool out = !(fabs(ax) <= M_x && fabs(ay) <= M_yz && fabs(az) <= M_yz);
-          badn = badn || !(fabs(q1.y) <= SPPM_F_NMAX && fabs(q2.x) <= SPPM_F_NMAX && fabs(q2.y) <= SPPM_F_NMAX);
+          bool n_ok = true;
+          if (nuni) n_ok = (rnx * q1.y + rny * q2.x) + rnz * q2.y > SPPM_NORMAL_AGREE;  // exact: Raytracer.h:154 for the whole unit
+          else badn = badn || !(fabs(q1.y) <= SPPM_F_NMAX && fabs(q2.x) <= SPPM_F_NMAX && fabs(q2.y) <= SPPM_F_NMAX);
           fx = __double2float_rn(ax); fy = __double2float_rn(ay); fz = __double2float_rn(az);
           gx = __double2float_rn(q1.y); gy = __double2float_rn(q2.x); gz = __double2float_rn(q2.y);
           const float ex = fmaxf(fmaxf(blo[0] - fx, fx - bhi[0]), 0.f), ey = fmaxf(fmaxf(blo[1] - fy, fy - bhi[1]), 0.f),
                       ez = fmaxf(fmaxf(blo[2] - fz, fz - bhi[2]), 0.f);
-          keep = !out && !(fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > cull_thr);
+          keep = !out && n_ok && !(fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > cull_thr);
         }
         const unsigned kmask = __ballot_sync(FULL, keep);
         if (keep) {
@@ -936,7 +960,15 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
         unsigned cd_t = 0;
         const int npair = (n_k + 1) >> 1;
         if (!any_badn) {
-          if (HBMAX > 1 && two) {
+          if (!COUNT && nuni) {
+            if (HBMAX > 1 && two) {
+              if (uni) fast_pairs<true, COUNT, HBMAX, false>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+              else fast_pairs<false, COUNT, HBMAX, false>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+            } else {
+              if (uni) fast_pairs<true, COUNT, 1, false>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+              else fast_pairs<false, COUNT, 1, false>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
+            }
+          } else if (HBMAX > 1 && two) {
             if (uni) fast_pairs<true, COUNT, HBMAX>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
             else fast_pairs<false, COUNT, HBMAX>(conv, sub_id, sub, npair, hp, sr2f, c_t, cd_t, t, uv, un2);
           } else {

@@ -572,12 +572,53 @@ def _check_gather(dh, oracle, hp, x, dn, flux, search_r2=2.0, min_acc=100):
     dep = dict(x=x, n=dn, flux=flux)
     newN, tao, cand, acc = oracle.gather_brute(hp, dep, search_r2)
     assert newN.sum() > min_acc
-    for exact in (False, True):
-        gn, gt, info, pairs = dh.gather_filtered(hp, dep, search_r2, exact=exact)
+    # count_pairs = False is the build the bench times (gather_filtered_kernel<COUNT = false>): the cull radius follows
+    # the unit's largest R2 and units whose hit points share one normal test it once per deposit (cand_pairs stays 0)
+    for exact, count in ((False, True), (False, False), (True, True)):
+        gn, gt, info, pairs = dh.gather_filtered(hp, dep, search_r2, exact=exact, count_pairs=count)
         np.testing.assert_array_equal(gn, newN)                 # level 2: newN bit-exact
-        assert pairs == [cand, acc], exact
+        assert pairs[1] == acc and (pairs[0] == cand or not count), (exact, count)  # cand_pairs is only kept by the COUNT build
         np.testing.assert_allclose(gt, tao, rtol=1e-11, atol=0)  # far inside the 1e-5 bar: only the order of summation differs
     return info
+
+
+def test_gather_filtered_plane_units_and_shrunk_radii(dh, oracle):
+    """Hit points on planes (one normal per plane, bit for bit: the units of a wall) with radii that PROGRESSIVE updates
+    have shrunk (R2 from 0.05 to 2): the normal test of Raytracer.h:154 is made once per deposit and unit, the cull
+    radius is the unit's largest R2.  Deposits sit at n.N = 1e-3 (1 +- delta) and at distance^2 = R2 (1 +- delta) of a
+    hit point, delta down to 1e-16: newN must still equal the exhaustive FP64 search."""
+    rng = np.random.RandomState(21)
+    sheets = [((0., 1., 0.), (0, 2)), ((1., 0., 0.), (1, 2)), ((0.6, 0., 0.8), (0, 1))]
+    pos, nrm = [], []
+    for nvec, (a, b) in sheets:
+        k = 2500
+        p = np.zeros((k, 3))
+        p[:, a], p[:, b] = rng.uniform(0, 12, k), rng.uniform(0, 12, k)
+        free = 3 - a - b
+        p[:, free] = 3.0 + 1e-3 * rng.uniform(-1, 1, k)
+        pos.append(p)
+        nrm.append(np.tile(np.array(nvec), (k, 1)))
+    pos, nrm = np.concatenate(pos), np.concatenate(nrm)
+    n = pos.shape[0]
+    r2 = rng.choice([0.05, 0.3, 0.9, 1.4, 2.0], size=n)
+    r2[:2500][pos[:2500, 0] < 4] = 0.3           # whole units with one small radius
+    hp = dict(pos=pos, n=nrm, wgt=rng.uniform(0.1, 1, size=(n, 3)), r2=r2)
+    m = 40000
+    who = rng.randint(0, n, m)
+    delta = rng.choice([0.0, 1e-16, 1e-15, 1e-13, 1e-10, 1e-7, 1e-4, 1e-2], size=m) * rng.choice([-1, 1], size=m)
+    d = rng.normal(size=(m, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rad = np.sqrt(r2[who] * (1 + delta))
+    half = m // 2
+    rad[half:] = np.sqrt(r2[who[half:]]) * rng.uniform(0, 1.3, m - half)
+    x = pos[who] + d * rad[:, None]
+    # normals at the agreement threshold of the hit point's plane
+    cosv = np.where(rng.uniform(size=m) < 0.5, 1e-3 * (1 + delta), rng.uniform(-1, 1, m))
+    t = np.cross(nrm[who], rng.normal(size=(m, 3)))
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    dn = nrm[who] * cosv[:, None] + t * np.sqrt(np.maximum(0, 1 - cosv ** 2))[:, None]
+    info = _check_gather(dh, oracle, hp, x, dn, rng.uniform(0, 100, size=(m, 3)), min_acc=10000)
+    assert info["n_units"] > 100
 
 
 def test_gather_filtered_kernel_bit_exact_newN(dh, oracle):

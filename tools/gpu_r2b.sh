@@ -53,5 +53,6 @@ if want ncu; then
   timeout 200 $NCU --import-source on -k regex:photon_step -s 1 -c 1 -o $OUT/${TAG}_step1 $T --region round > $OUT/${TAG}_ncu_step1.log 2>&1
   export_rep ${TAG}_step1 src
 fi
+python -c "import bench; print(bench.csrc_digest())" > $OUT/${TAG}_csrc_digest.txt
 rm -f $OUT/*.ncu-rep.tmp
 du -sh $OUT; ls -la $OUT | grep ${TAG} | awk '{print $5, $9}'
