@@ -178,9 +178,12 @@ cudaError_t build_index(sppm_ctx* c) {
   {
     uint64_t *o1 = (uint64_t*)c->dep_key.p, *o2 = (uint64_t*)c->dep_key2.p;
     hp_okey_kernel<<<nblk(n), TPB, 0, st>>>(raw, n, o1, i2);
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, o1, o2, i2, i1, (int)n, 0, 64, st));
+    // okey = pixel << 20 | eye-path node: only the bits a film of this size can set are sorted (5 radix passes
+    // instead of 8 at 1024 x 768)
+    const int okey_bits = std::min(64, 20 + bits_for((uint64_t)std::max<int64_t>((int64_t)c->film_w * c->film_h, 2) - 1));
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, o1, o2, i2, i1, (int)n, 0, okey_bits, st));
     CK(dev_reserve(c->cub_tmp, tmp));
-    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, o1, o2, i2, i1, (int)n, 0, 64, st));
+    CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, o1, o2, i2, i1, (int)n, 0, okey_bits, st));
     c->host_counters.launches += 2;
   }
   hp_key_kernel<<<nblk(n), TPB, 0, st>>>(raw, i1, n, g, k1);
@@ -247,9 +250,10 @@ cudaError_t build_index(sppm_ctx* c) {
     CK(cudaStreamSynchronize(st));
     c->n_units = n_units;
     CK(dev_reserve(c->units, (size_t)(n_units > 0 ? n_units : 1) * sizeof(GUnit)));
-    unit_fill_kernel<<<nblk(n_occ), TPB, 0, st>>>(run_first, d_nr, n_occ, (const int32_t*)c->occ_start.p,
-                                                  (const uint32_t*)c->occ_cell.p, uoff, g, (const int32_t*)c->cell_slot.p,
-                                                  (GUnit*)c->units.p);
+    if (n_units > 0)
+      unit_fill_kernel<<<nblk(n_units), TPB, 0, st>>>(run_first, d_nr, n_occ, (const int32_t*)c->occ_start.p,
+                                                      (const uint32_t*)c->occ_cell.p, uoff, n_units, g,
+                                                      (const int32_t*)c->cell_slot.p, (GUnit*)c->units.p);
     c->host_counters.launches += 5;
   }
   CK(cudaGetLastError());

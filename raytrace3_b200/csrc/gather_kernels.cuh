@@ -137,45 +137,59 @@ __global__ void unit_count_kernel(const int32_t* run_first, const int32_t* n_run
   const int o0 = run_first[r], o1 = r + 1 < n_runs ? run_first[r + 1] : n_occ;
   cnt[r] = (occ_start[o1] - occ_start[o0] + UNIT_HP - 1) / UNIT_HP;
 }
+// One thread per unit: unit u belongs to run r = the last run with unit_off[r] <= u and holds hit points
+// [b, e) of it, b = (first hit point of the run) + (u - unit_off[r]) * UNIT_HP; its first / last cells are found
+// by bisection in occ_start.  (One thread per RUN walking its units serially took 120 us at 786 k hit points:
+// the long runs of the dense walls were the whole launch.)
 __global__ void unit_fill_kernel(const int32_t* run_first, const int32_t* n_runs_p, int n_occ, const int32_t* occ_start,
-                                 const uint32_t* occ_cell, const int32_t* unit_off, Grid g, const int32_t* cell_slot,
-                                 GUnit* units) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+                                 const uint32_t* occ_cell, const int32_t* unit_off, int n_units, Grid g,
+                                 const int32_t* cell_slot, GUnit* units) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
   const int n_runs = *n_runs_p;
-  if (r >= n_runs) return;
-  const int o0 = run_first[r], o1 = r + 1 < n_runs ? run_first[r + 1] : n_occ;
-  const int p0 = occ_start[o0], p1 = occ_start[o1];
-  const double cell = 1.0 / g.inv_cell;
-  int o = o0;  // first cell of the current unit
-  for (int u = unit_off[r], b = p0; b < p1; u++, b += UNIT_HP) {
-    const int e = min(b + UNIT_HP, p1);
-    while (occ_start[o + 1] <= b) o++;
-    int ol = o;
-    while (occ_start[ol + 1] < e) ol++;  // cell of hit point e-1
-    const uint32_t c = occ_cell[o];
-    const int ix = c % g.dim[0], iy = (c / g.dim[0]) % g.dim[1], iz = c / (g.dim[0] * g.dim[1]);
-    const int nx = ol - o + 1;
-    GUnit un;
-    un.hp_begin = b;
-    un.hp_count = e - b;
-    un.n_cells_x = nx;
-    un.pad = 0;
-    un.org[0] = g.org[0] + (ix + 0.5 * nx) * cell;
-    un.org[1] = g.org[1] + (iy + 0.5) * cell;
-    un.org[2] = g.org[2] + (iz + 0.5) * cell;
-    for (int k = 0; k < 9; k++) {
-      const int jy = iy + k % 3 - 1, jz = iz + k / 3 - 1;
-      int2 rr = make_int2(0, 0);
-      if (!(jy < 0 || jz < 0 || jy >= g.dim[1] || jz >= g.dim[2])) {
-        const int x0 = max(ix - 1, 0), x1 = min(ix + nx, g.dim[0] - 1);
-        const long long row = ((long long)jz * g.dim[1] + jy) * g.dim[0];
-        rr.x = cell_slot[row + x0];
-        rr.y = cell_slot[row + x1] + 1;
-      }
-      un.run[k] = rr;
-    }
-    units[u] = un;
+  int lo = 0, hi = n_runs;  // last r in [0, n_runs) with unit_off[r] <= u (runs without units cannot own u: strict progress)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (unit_off[mid] <= u) lo = mid; else hi = mid;
   }
+  const int r = lo;
+  const int o0 = run_first[r], o1 = r + 1 < n_runs ? run_first[r + 1] : n_occ;
+  const int p1 = occ_start[o1];
+  const int b = occ_start[o0] + (u - unit_off[r]) * UNIT_HP;
+  const int e = min(b + UNIT_HP, p1);
+  auto cell_of = [&](int p) {  // the cell o in [o0, o1) with occ_start[o] <= p < occ_start[o + 1]
+    int a = o0, z = o1;
+    while (z - a > 1) {
+      const int mid = (a + z) >> 1;
+      if (occ_start[mid] <= p) a = mid; else z = mid;
+    }
+    return a;
+  };
+  const int o = cell_of(b), ol = cell_of(e - 1);
+  const double cell = 1.0 / g.inv_cell;
+  const uint32_t c = occ_cell[o];
+  const int ix = c % g.dim[0], iy = (c / g.dim[0]) % g.dim[1], iz = c / (g.dim[0] * g.dim[1]);
+  const int nx = ol - o + 1;
+  GUnit un;
+  un.hp_begin = b;
+  un.hp_count = e - b;
+  un.n_cells_x = nx;
+  un.pad = 0;
+  un.org[0] = g.org[0] + (ix + 0.5 * nx) * cell;
+  un.org[1] = g.org[1] + (iy + 0.5) * cell;
+  un.org[2] = g.org[2] + (iz + 0.5) * cell;
+  for (int k = 0; k < 9; k++) {
+    const int jy = iy + k % 3 - 1, jz = iz + k / 3 - 1;
+    int2 rr = make_int2(0, 0);
+    if (!(jy < 0 || jz < 0 || jy >= g.dim[1] || jz >= g.dim[2])) {
+      const int x0 = max(ix - 1, 0), x1 = min(ix + nx, g.dim[0] - 1);
+      const long long row = ((long long)jz * g.dim[1] + jy) * g.dim[0];
+      rr.x = cell_slot[row + x0];
+      rr.y = cell_slot[row + x1] + 1;
+    }
+    un.run[k] = rr;
+  }
+  units[u] = un;
 }
 
 // ---- deposits --------------------------------------------------------------------------

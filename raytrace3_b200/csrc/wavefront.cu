@@ -70,6 +70,10 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
   w.counters = (DevCounters*)c->counters.p;
   w.begin = begin;
   w.count = count;
+  // from this bounce on (about 1 photon in 6 still alive) the Bezier solves go to the persistent tracer in one
+  // launch instead of one latency-bound Newton launch per bounce; SPPM_WF_TAIL = -1 switches it off
+  w.tail_bounce = 6;
+  if (const char* e = getenv("SPPM_WF_TAIL")) w.tail_bounce = atoi(e);
   w.q_cap = (unsigned)Ln.wf_cap;
   w.grid = c->grid;
   w.cell_slot = c->index_ok ? (const int32_t*)c->cell_slot.p : nullptr;
@@ -92,7 +96,7 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
     if ((e = Ln.prof.mark(PK_STEP, st))) return e;
     photon_step_kernel<<<blocks, STEP_THREADS, step_smem, st>>>(a);
     c->host_counters.launches++;
-    if (a.do_intersect && c->scene.n_patch > 0) {
+    if (a.do_intersect && c->scene.n_patch > 0 && !a.spill_all) {
       const NewtonArgs n = wf_newton_args(w, L, a);
       if ((e = Ln.prof.mark(PK_NEWTON, st))) return e;
       newton_items_kernel<<<newton_blocks, TRACE_THREADS, newton_smem, st>>>(n);

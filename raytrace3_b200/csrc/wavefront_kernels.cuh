@@ -62,6 +62,7 @@ struct StepArgs {
   unsigned* n_items_out;
   unsigned item_cap;
   Spill spill;
+  int spill_all;          // tail bounces: every photon with Bezier solves pending goes to the spill list
   uint64_t begin, count;  // photon range per light of this batch
   Grid grid;
   const int32_t* cell_slot;
@@ -267,6 +268,13 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
     unsigned my_begin = 0, my_cnt = 0;
     bool spill_me = false;
     unsigned bm = __ballot_sync(FULL, alive && boxobj != 0);
+    if (a.spill_all) {
+      // Tail bounces (few photons alive, a handful of them inside a Bezier box): a Newton launch would cost its
+      // serial chain (2 rounds x 10 iterations, ~35 us) for almost no work.  These photons leave the wavefront
+      // here and the persistent tracer finishes them after the last bounce, all tails in one launch.
+      spill_me = alive && boxobj != 0;
+      bm = 0;
+    }
     while (bm) {
       const int src = __ffs(bm) - 1;
       bm &= bm - 1;
@@ -368,11 +376,14 @@ struct NewtonArgs {
   Items it;
   const unsigned* n_items_ptr;
   unsigned item_cap;
+  unsigned* work;  // chunk cursor of this launch (zeroed with the batch's counters)
 };
 
-// Bezier3::newton for the queued (photon slot, patch) items.  Each warp takes chunks of C items
-// (C chosen so that all warps of the grid get work) and runs the C*restarts tasks over its 32
-// lanes with flush_items (scene.cuh): lanes = restarts, arg-min on (t, restart) per item.
+// Bezier3::newton for the queued (photon slot, patch) items.  Warps take chunks of C items from a global
+// cursor and run the C*restarts tasks over their 32 lanes with flush_items (scene.cuh): lanes = restarts,
+// arg-min on (t, restart) per item.  Chunks are handed out dynamically because the work of an item is
+// either a full solve or nothing (46 % are proven empty by the 13-DOP line test): with a static partition
+// the slowest warp of the first bounces ran about twice the average number of rounds.
 __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_items_kernel(const NewtonArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned n = min(*a.n_items_ptr, a.item_cap);
@@ -383,9 +394,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_i
   const int lane = threadIdx.x & 31;
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-  unsigned C = (n + n_warps - 1) / n_warps;
-  C = C < 1 ? 1 : (C > 32 ? 32 : C);  // few items: one per warp keeps the serial Newton chain short
-  for (unsigned c0 = warp_global * C; c0 < n; c0 += n_warps * C) {
+  (void)warp_global;
+  // about four chunks per warp; few items: one per warp keeps the serial Newton chain short
+  unsigned C = (n + 4 * n_warps - 1) / (4 * n_warps);
+  C = C < 1 ? 1 : (C > 32 ? 32 : C);
+  for (;;) {
+    unsigned c0 = 0;
+    if (lane == 0) c0 = atomicAdd(a.work, C);
+    c0 = __shfl_sync(FULL, c0, 0);
+    if (c0 >= n) break;
     const int cnt = (int)min(C, n - c0);
     if (lane < cnt) {
       const unsigned s = a.it.slot[c0 + lane];
@@ -411,7 +428,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_i
 struct WfLayout {
   Queue q[2];
   Items it[2];
-  unsigned* counters;  // [4*b + r] queue count of region r at bounce b, [64+b] item counts, [97] spilled photons
+  unsigned* counters;  // [4*b + r] queue count of region r at bounce b, [64+b] item counts, [97] spilled photons, [100+b] Newton chunk cursors
   unsigned item_cap;
   Spill spill;         // [cap]
 };
@@ -462,6 +479,7 @@ struct WfBatch {
   uint64_t seed, pass;
   DevCounters* counters;
   uint64_t begin, count;  // photon range per light
+  int tail_bounce;        // >= 0: from this bounce on Bezier-pending photons spill to the persistent tracer
   unsigned q_cap;         // entries per queue half (>= n_light * count)
   Grid grid;
   const int32_t* cell_slot;
@@ -498,6 +516,7 @@ inline StepArgs wf_step_args(const WfBatch& w, const WfLayout& L, int b) {
   a.n_items_out = L.counters + 64 + b + 1;
   a.item_cap = L.item_cap;
   a.spill = L.spill;
+  a.spill_all = w.tail_bounce >= 0 && b >= w.tail_bounce;
   a.begin = w.begin;
   a.count = w.count;
   a.grid = w.grid;
@@ -527,6 +546,7 @@ inline NewtonArgs wf_newton_args(const WfBatch& w, const WfLayout& L, const Step
   n.it = a.it_out;
   n.n_items_ptr = a.n_items_out;
   n.item_cap = L.item_cap;
+  n.work = L.counters + 100 + a.bounce;
   return n;
 }
 

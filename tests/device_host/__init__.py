@@ -187,7 +187,7 @@ class HostScene:
         return dict(x=out["x"][order], n=out["n"][order], flux=out["flux"][order], photon=photon[order],
                     bounce=bounce[order]), dict(zip(COUNTERS, cnt.tolist()))
 
-    def photon_trace_wavefront(self, prm, begin, count, pass_id, step_blocks=24, newton_blocks=24, item_cap=0):
+    def photon_trace_wavefront(self, prm, begin, count, pass_id, step_blocks=24, newton_blocks=24, item_cap=0, tail_bounce=6):
         """The bounce-synchronous pass (photon_step_kernel + newton_items_kernel per bounce, the
         product's wf_layout / wf_step_args / wf_newton_args) -> deposits sorted by (photon id, bounce),
         counters, and the queue counts [bounce][region]."""
@@ -196,7 +196,7 @@ class HostScene:
         cnt = np.zeros(len(COUNTERS), dtype=np.uint64)
         qc = np.zeros((prm.max_dep + 3, 4), dtype=np.uint32)
         n = self.dh.lib.dh_photon_trace_wavefront(self.h, C.byref(prm), begin, count, pass_id, step_blocks, newton_blocks,
-                                                  cap, _p(out), _p(cnt), _p(qc), item_cap)
+                                                  cap, _p(out), _p(cnt), _p(qc), item_cap, tail_bounce)
         assert 0 <= n <= cap
         out = out[:n]
         photon = out["meta"] & np.uint64((1 << 56) - 1)
@@ -253,7 +253,7 @@ class DeviceHost:
         L.dh_eye_pass_kernel.restype = I64
         L.dh_photon_trace_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), U64, U64, U64, C.c_int, I64, VP, VP]
         L.dh_photon_trace_kernel.restype = I64
-        L.dh_photon_trace_wavefront.argtypes = [VP, C.POINTER(abi.SppmParams), U64, U64, U64, C.c_int, C.c_int, I64, VP, VP, VP, I64]
+        L.dh_photon_trace_wavefront.argtypes = [VP, C.POINTER(abi.SppmParams), U64, U64, U64, C.c_int, C.c_int, I64, VP, VP, VP, I64, C.c_int]
         L.dh_photon_trace_wavefront.restype = I64
         L.dh_gather_filtered.argtypes = [I64, VP, C.POINTER(Grid), I64, VP, DBL, C.c_int, C.c_int, C.c_int, VP, VP, VP, VP, VP]
         L.dh_set_one_warp_blocks.argtypes = [C.c_int]

@@ -428,7 +428,8 @@ void dh_patch_batch_kernel(void* p, const SppmParams* prm, int cull, int64_t n, 
 int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin, uint64_t count, uint64_t pass,
                                   int step_blocks, int newton_blocks, int64_t cap, Deposit* out, uint64_t* counters9,
                                   uint32_t* queue_counts /* [4 * (max_dep + 3)] or null */,
-                                  int64_t item_cap_override /* > 0: a short item list, so that photons spill */) {
+                                  int64_t item_cap_override /* > 0: a short item list, so that photons spill */,
+                                  int tail_bounce /* WfBatch::tail_bounce, -1 = off */) {
   DhScene* h = (DhScene*)p;
   const int64_t total = (int64_t)h->dev.n_light * (int64_t)count;
   if (total <= 0) return 0;
@@ -459,6 +460,7 @@ int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin
   w.begin = begin;
   w.count = count;
   w.q_cap = (unsigned)total;
+  w.tail_bounce = tail_bounce;
   memset(&w.grid, 0, sizeof(w.grid));
   w.cell_slot = nullptr;
   w.n_slots = 0;
@@ -475,7 +477,7 @@ int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin
     long long blocks = step_blocks;
     if (b == 0) blocks = std::min<long long>(blocks, (total + bt(STEP_THREADS) - 1) / bt(STEP_THREADS));
     launch(photon_step_kernel, a, blocks, bt(STEP_THREADS));
-    if (a.do_intersect && h->dev.n_patch > 0) {
+    if (a.do_intersect && h->dev.n_patch > 0 && !a.spill_all) {
       const NewtonArgs n = wf_newton_args(w, L, a);
       launch(newton_items_kernel, n, newton_blocks, bt(TRACE_THREADS));
     }
@@ -581,7 +583,8 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   std::vector<GUnit> units((size_t)std::max(n_units, 1));
   launch(unit_fill_kernel, std::make_tuple((const int32_t*)run_first.data(), (const int32_t*)&n_runs, n_occ,
                                            (const int32_t*)occ_start.data(), (const uint32_t*)occ_cell.data(),
-                                           (const int32_t*)uoff.data(), g, (const int32_t*)cell_slot.data(), units.data()), nb(n_occ), T);
+                                           (const int32_t*)uoff.data(), n_units, g, (const int32_t*)cell_slot.data(), units.data()),
+         nb(std::max(n_units, 1)), T);
   // deposits: slot key + arrival rank, CSR offsets, scatter (key n_slots = not kept)
   std::vector<uint32_t> dkey((size_t)std::max<int64_t>(m, 1)), drank((size_t)std::max<int64_t>(m, 1));
   std::vector<unsigned int> slot_count((size_t)n_slots + 2, 0);

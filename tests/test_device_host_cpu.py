@@ -515,15 +515,19 @@ def test_wavefront_kernels_against_oracle(dh, oracle, name, count):
         assert qc[:, 3].sum() == 0
 
 
-def test_wavefront_equals_persistent_on_the_cpu(dh):
-    """Both tracer organisations, FAST Newton + FAST math (the bench configuration): same deposits."""
-    hs = dh.scene(_scene("reference"))
+@pytest.mark.parametrize("tail", [-1, 6, 2, 0])
+def test_wavefront_equals_persistent_on_the_cpu(dh, tail):
+    """Both tracer organisations, FAST Newton + FAST math (the bench configuration): same deposits — with the
+    tail hand-over off (-1), at the product's bounce (6), early (2) and with every Bezier solve handed over (0)."""
+    hs = dh.scene(_scene("stress"))
     prm = _params(newton_mode=abi.SPPM_NEWTON_FAST, math_mode=abi.SPPM_MATH_FAST)
     a, ca = hs.photon_trace_kernel(prm, 0, 30000, 2)
-    b, cb, _ = hs.photon_trace_wavefront(prm, 0, 30000, 2, step_blocks=5, newton_blocks=3)
+    b, cb, _ = hs.photon_trace_wavefront(prm, 0, 30000, 2, step_blocks=5, newton_blocks=3, tail_bounce=tail)
     for k in a:
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
     assert ca["deposits"] == cb["deposits"] and ca["patch_solves"] == cb["patch_solves"]
+    assert ca["isect_queries"] >= cb["isect_queries"] > 0.9 * ca["isect_queries"]
+    assert (cb["overflow"] > 0) == (tail >= 0)
 
 
 def _light_over_teapot_scene():
