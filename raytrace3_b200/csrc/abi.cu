@@ -189,6 +189,18 @@ int ensure_deposit_capacity(sppm_ctx* c, Lane& L, int64_t cap) {
 // every later trace must see the scene / hit-point map that the main stream just produced
 cudaError_t mark_setup(sppm_ctx* c) { return cudaEventRecord(c->ev_setup, c->stream); }
 
+// Order the main stream after whatever the communication stream still holds (allreduce + update of the last
+// round): every entry point that reads or rebuilds hit-point state on the main stream starts with this.
+cudaError_t join_comm(sppm_ctx* c) {
+  if (!c->comm_busy) return cudaSuccess;
+  cudaError_t e = cudaStreamWaitEvent(c->stream, c->ev_comm, 0);
+  if (e == cudaSuccess) c->comm_busy = false;
+  return e;
+}
+bool use_async_comm(const sppm_ctx* c) {
+  return c->async_comm && c->nccl_comm && c->nranks > 1 && c->comm_stream && c->prm.update_mode == SPPM_UPDATE_REFERENCE;
+}
+
 // canonical export order = ascending okey
 std::vector<int64_t> canonical_order(const std::vector<uint64_t>& okey) {
   std::vector<int64_t> ord(okey.size());
@@ -254,6 +266,16 @@ int sppm_ctx_create(int device, sppm_ctx** out) {
     for (int k = 0; k < 2 && ok; k++) ok = cudaEventCreate(&c->aev[i][k]) == cudaSuccess;
   ok = ok && dev_reserve(c->dev_scalars, 64) == cudaSuccess && dev_reserve(c->counters, sizeof(DevCounters)) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->ev_setup, cudaEventDisableTiming) == cudaSuccess;
+  {
+    int lo_p = 0, hi_p = 0;  // the exchange gets the highest priority: its few CTAs should not queue behind a trace
+    cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+    ok = ok && cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi_p) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_gathers_done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_acc_free[0], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_acc_free[1], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming) == cudaSuccess;
+    if (const char* e = getenv("SPPM_ASYNC_COMM")) c->async_comm = atoi(e) != 0;
+  }
   if (const char* e = getenv("SPPM_LANES")) c->n_lanes = std::max(1, std::min((int)sppm_ctx::MAX_LANES, atoi(e)));
   for (int j = 0; j < sppm_ctx::MAX_LANES && ok; j++) {
     Lane& L = c->lanes[j];
@@ -281,8 +303,12 @@ void sppm_ctx_destroy(sppm_ctx* c) {
   Bind b(c);
   for (int j = 0; j < sppm_ctx::MAX_LANES; j++)
     if (c->lanes[j].stream) cudaStreamSynchronize(c->lanes[j].stream);
+  if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->nccl_comm && nccl().ok) nccl().CommDestroy((ncclComm_t)c->nccl_comm);
+  for (cudaEvent_t e : {c->ev_gathers_done, c->ev_acc_free[0], c->ev_acc_free[1], c->ev_comm})
+    if (e) cudaEventDestroy(e);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
   for (int j = 0; j < sppm_ctx::MAX_LANES; j++) {
     Lane& L = c->lanes[j];
     DevBuf* lb[] = {&L.dep_raw, &L.dep_sorted, &L.dep_key, &L.dep_rank, &L.slot_count, &L.dep_start, &L.wf_store, &L.scalars, &L.cub_tmp};
@@ -452,6 +478,7 @@ int sppm_allgather_hitpoints(sppm_ctx* c, int64_t* n_hitpoints) {
     return SPPM_OK;
   }
   Bind b(c);
+  CU(c, join_comm(c));
   NcclApi& n = nccl();
   if (!n.AllGather || !n.Broadcast) return fail(c, SPPM_ERR_NCCL, "ncclAllGather / ncclBroadcast not found");
   const int R = c->nranks;
@@ -499,6 +526,7 @@ int sppm_allgather_hitpoints(sppm_ctx* c, int64_t* n_hitpoints) {
 int sppm_build_index(sppm_ctx* c) {
   if (!c) return SPPM_ERR_INVALID;
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, cudaEventRecord(c->ev[4], c->stream));
   CU(c, build_index(c));
   CU(c, cudaEventRecord(c->ev[5], c->stream));
@@ -577,16 +605,31 @@ int sppm_allreduce(sppm_ctx* c) {
   NcclApi& n = nccl();
   if (c->a_pending == sppm_ctx::TIMING_RING) fold_timings(c);
   cudaEvent_t* ae = c->aev[c->a_pending];
-  CU(c, cudaEventRecord(ae[0], c->stream));
+  // REFERENCE update: the exchange and the update that follows run on the communication stream, behind the
+  // round's gathers, while the main stream goes on with the next round (see ctx.h); otherwise in line
+  const bool async = use_async_comm(c) && !c->profiling;
+  cudaStream_t st = async ? c->comm_stream : c->stream;
+  if (async) {
+    CU(c, cudaEventRecord(c->ev_gathers_done, c->stream));
+    CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_gathers_done, 0));
+  } else {
+    CU(c, join_comm(c));
+  }
+  CU(c, cudaEventRecord(ae[0], st));
   ncclResult_t r = n.GroupStart();
-  if (r == ncclSuccess) r = n.AllReduce(c->soa.dN, c->soa.dN, (size_t)c->n_hp, ncclInt32, ncclSum, (ncclComm_t)c->nccl_comm, c->stream);
+  if (r == ncclSuccess) r = n.AllReduce(c->soa.dN, c->soa.dN, (size_t)c->n_hp, ncclInt32, ncclSum, (ncclComm_t)c->nccl_comm, st);
   if (r == ncclSuccess)
-    r = n.AllReduce(c->soa.dtao, c->soa.dtao, (size_t)c->n_hp * 3, ncclFloat64, ncclSum, (ncclComm_t)c->nccl_comm, c->stream);
+    r = n.AllReduce(c->soa.dtao, c->soa.dtao, (size_t)c->n_hp * 3, ncclFloat64, ncclSum, (ncclComm_t)c->nccl_comm, st);
   ncclResult_t r2 = n.GroupEnd();
   if (r == ncclSuccess) r = r2;
   if (r != ncclSuccess) return fail(c, SPPM_ERR_NCCL, std::string("ncclAllReduce: ") + (n.GetErrorString ? n.GetErrorString(r) : "error"));
-  CU(c, cudaEventRecord(ae[1], c->stream));
+  CU(c, cudaEventRecord(ae[1], st));
   c->a_pending++;
+  if (async) {
+    CU(c, cudaEventRecord(c->ev_comm, c->comm_stream));
+    c->comm_pending = true;
+    c->comm_busy = true;
+  }
   return SPPM_OK;
 }
 
@@ -594,8 +637,23 @@ int sppm_update(sppm_ctx* c) {
   if (!c) return SPPM_ERR_INVALID;
   if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
   Bind b(c);
+  if (c->comm_pending) {
+    // the update of the round whose exchange is in flight: same stream, then the accumulator sets swap
+    CU(c, launch_update(c, c->comm_stream));
+    CU(c, cudaEventRecord(c->ev_acc_free[c->acc_cur], c->comm_stream));
+    CU(c, cudaEventRecord(c->ev_comm, c->comm_stream));
+    c->comm_pending = false;
+    c->comm_busy = true;
+    c->acc_cur ^= 1;
+    c->soa.dN = c->dN_set[c->acc_cur];
+    c->soa.dtao = c->dtao_set[c->acc_cur];
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_acc_free[c->acc_cur], 0));  // the update that last emptied this set
+    if (c->prm.update_mode != SPPM_UPDATE_REFERENCE) CU(c, join_comm(c));  // the mode changed in between: radii may move
+    return SPPM_OK;
+  }
+  CU(c, join_comm(c));
   CU(c, c->prof.mark(PK_UPDATE, c->stream));
-  CU(c, launch_update(c));
+  CU(c, launch_update(c, c->stream));
   if (c->profiling) {
     CU(c, c->prof.mark(PK_END, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -610,6 +668,7 @@ int sppm_resolve(sppm_ctx* c, int32_t cnt, int32_t onetime, double* film_hw3) {
   if (!c || !film_hw3) return SPPM_ERR_INVALID;
   if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, cudaEventRecord(c->ev[4], c->stream));
   CU(c, launch_resolve(c, cnt, onetime));
   CU(c, cudaEventRecord(c->ev[5], c->stream));
@@ -635,6 +694,7 @@ int sppm_shared_load(sppm_ctx* c) {
   if (!c->px_store.p || c->px_w != c->film_w || c->px_h != c->film_h)
     return fail(c, SPPM_ERR_INVALID, "sppm_shared_begin must be called with the film size of the eye pass");
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, shared_load(c));
   CU(c, mark_setup(c));  // the lanes read the hit-point radii
   return SPPM_OK;
@@ -644,6 +704,7 @@ int sppm_shared_fold(sppm_ctx* c, uint64_t photons_emitted) {
   if (!c) return SPPM_ERR_INVALID;
   if (!c->index_ok || !c->px_store.p) return fail(c, SPPM_ERR_INVALID, "sppm_shared_load must be called first");
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, shared_fold(c));
   c->px_photons += photons_emitted;
   return SPPM_OK;
@@ -653,6 +714,7 @@ int sppm_shared_resolve(sppm_ctx* c, double* film_hw3) {
   if (!c || !film_hw3) return SPPM_ERR_INVALID;
   if (!c->px_store.p) return fail(c, SPPM_ERR_INVALID, "sppm_shared_begin must be called first");
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, shared_resolve(c));
   CU(c, cudaMemcpyAsync(film_hw3, c->film.p, (size_t)c->px_w * c->px_h * 24, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -664,6 +726,7 @@ int sppm_shared_export(sppm_ctx* c, double* r2_hw, double* n_hw, double* tau3, u
   if (!c) return SPPM_ERR_INVALID;
   if (!c->px_store.p) return fail(c, SPPM_ERR_INVALID, "sppm_shared_begin must be called first");
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, shared_export(c, r2_hw, n_hw, tau3));
   if (photons_emitted) *photons_emitted = c->px_photons;
   return SPPM_OK;
@@ -673,6 +736,7 @@ int sppm_shared_import(sppm_ctx* c, const double* r2_hw, const double* n_hw, con
   if (!c || !r2_hw || !n_hw || !tau3) return SPPM_ERR_INVALID;
   if (!c->px_store.p) return fail(c, SPPM_ERR_INVALID, "sppm_shared_begin must be called first");
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, shared_import(c, r2_hw, n_hw, tau3));
   c->px_photons = photons_emitted;
   return SPPM_OK;
@@ -732,6 +796,7 @@ int sppm_accum_device_ptrs(sppm_ctx* c, void** dN, void** dtao, int64_t* n) {
 int sppm_device_synchronize(sppm_ctx* c) {
   if (!c) return SPPM_ERR_INVALID;
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, cudaStreamSynchronize(c->stream));
   fold_timings(c);
   return check_overflow(c);
@@ -743,6 +808,7 @@ void* sppm_stream_handle(sppm_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int sppm_timer_record(sppm_ctx* c, int slot) {
   if (!c || slot < 0 || slot > 1) return SPPM_ERR_INVALID;
   Bind b(c);
+  CU(c, join_comm(c));  // the stopwatch covers the exchange in flight
   CU(c, cudaEventRecord(c->ev[6 + slot], c->stream));
   return SPPM_OK;
 }
@@ -872,6 +938,7 @@ int sppm_import_hitpoints(sppm_ctx* c, int64_t n, const double* pos3, const doub
   if (!c || n < 0 || w <= 0 || h <= 0) return SPPM_ERR_INVALID;
   if (n > 0 && (!pos3 || !n3 || !wgt3 || !r2 || !pix)) return SPPM_ERR_INVALID;
   Bind b(c);
+  CU(c, join_comm(c));
   std::vector<HpRaw> raw((size_t)n);
   for (int64_t i = 0; i < n; i++) {
     HpRaw& r = raw[i];
@@ -901,6 +968,7 @@ int sppm_export_hitpoints(sppm_ctx* c, int64_t cap, double* pos3, double* n3, do
                           uint32_t* node, int64_t* n_out) {
   if (!c) return SPPM_ERR_INVALID;
   Bind b(c);
+  CU(c, join_comm(c));
   const int64_t n = c->n_hp;
   if (n_out) *n_out = n;
   if (n == 0) return SPPM_OK;
@@ -933,6 +1001,7 @@ int sppm_gather_deposits(sppm_ctx* c, int64_t m, const double* x3, const double*
   if (m == 0) return SPPM_OK;
   if (!x3 || !n3 || !flux3) return SPPM_ERR_INVALID;
   Bind b(c);
+  CU(c, join_comm(c));
   Lane& L = c->lanes[0];
   c->last_lane = 0;
   CU(c, cudaStreamSynchronize(L.stream));
@@ -972,6 +1041,7 @@ int sppm_export_stats(sppm_ctx* c, int64_t cap, int32_t* newN, int32_t* N, doubl
   if (!c) return SPPM_ERR_INVALID;
   if (!c->index_ok) return fail(c, SPPM_ERR_INVALID, "sppm_build_index must be called first");
   Bind b(c);
+  CU(c, join_comm(c));
   const int64_t n = c->n_hp;
   if (n == 0) return SPPM_OK;
   std::vector<uint64_t> okey((size_t)n);
@@ -1033,6 +1103,7 @@ int sppm_export_deposits(sppm_ctx* c, int64_t cap, double* x3, double* n3, doubl
 int sppm_get_counters(sppm_ctx* c, SppmCounters* out) {
   if (!c || !out) return SPPM_ERR_INVALID;
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, cudaStreamSynchronize(c->stream));
   fold_timings(c);
   DevCounters d;
@@ -1068,6 +1139,7 @@ int sppm_set_profiling(sppm_ctx* c, int32_t on) {
 int sppm_reset_counters(sppm_ctx* c) {
   if (!c) return SPPM_ERR_INVALID;
   Bind b(c);
+  CU(c, join_comm(c));
   CU(c, cudaStreamSynchronize(c->stream));
   fold_timings(c);
   CU(c, cudaMemset(c->counters.p, 0, sizeof(DevCounters)));

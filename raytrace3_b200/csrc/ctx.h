@@ -202,6 +202,18 @@ struct sppm_ctx {
   // NCCL (dlopen)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  // Exchange overlapped with the next round (REFERENCE update only: HitPoint::update then never changes a radius,
+  // Raytracer.h:70, so the next round's gather does not depend on it).  The per-round accumulators dN / dtao
+  // exist twice: while the allreduce + update of round i run on comm_stream over one set, the gather of round
+  // i+1 fills the other on the main stream.
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_gathers_done = nullptr, ev_acc_free[2] = {nullptr, nullptr}, ev_comm = nullptr;
+  int32_t* dN_set[2] = {nullptr, nullptr};
+  double* dtao_set[2] = {nullptr, nullptr};
+  int acc_cur = 0;
+  bool async_comm = true;     // SPPM_ASYNC_COMM=0 keeps the exchange on the main stream
+  bool comm_pending = false;  // an allreduce was issued on comm_stream and its update has not been yet
+  bool comm_busy = false;     // comm_stream holds work the main stream has not been ordered after
 };
 
 namespace sppm {
@@ -222,7 +234,7 @@ cudaError_t build_index(sppm_ctx* c);
 cudaError_t key_host_deposits(sppm_ctx* c, Lane& L, int64_t m, cudaStream_t st);
 cudaError_t bin_deposits(sppm_ctx* c, Lane& L, cudaStream_t st);
 cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cudaEvent_t ev_gather_end);
-cudaError_t launch_update(sppm_ctx* c);
+cudaError_t launch_update(sppm_ctx* c, cudaStream_t st);
 cudaError_t launch_resolve(sppm_ctx* c, int cnt, int onetime);
 cudaError_t shared_begin(sppm_ctx* c, int w, int h);
 cudaError_t shared_load(sppm_ctx* c);

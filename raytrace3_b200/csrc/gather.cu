@@ -62,7 +62,7 @@ inline int bits_for(uint64_t max_value) {
 
 cudaError_t layout_soa(sppm_ctx* c, int64_t n) {
   const size_t nd = (size_t)(n > 0 ? n : 1);
-  const size_t bytes = nd * (10 * 8 + 6 * 8 + 3 * 4 + 2 * 4 + 8) + 4096;
+  const size_t bytes = nd * (10 * 8 + 6 * 8 + 3 * 4 + 2 * 4 + 8) + nd * (3 * 8 + 4) + 4096;  // + the second accumulator set
   CK(dev_reserve(c->soa_store, bytes));
   unsigned char* p = (unsigned char*)c->soa_store.p;
   auto takeD = [&](size_t k) { double* r = (double*)p; p += k * 8; return r; };
@@ -76,6 +76,12 @@ cudaError_t layout_soa(sppm_ctx* c, int64_t n) {
   s.okey = (uint64_t*)p; p += nd * 8;
   auto takeI = [&](size_t k) { int32_t* r = (int32_t*)p; p += k * 4; return r; };
   s.N = takeI(nd); s.newN = takeI(nd); s.dN = takeI(nd); s.row = takeI(nd); s.col = takeI(nd);
+  c->dtao_set[0] = s.dtao;
+  c->dN_set[0] = s.dN;
+  c->dN_set[1] = takeI(nd);
+  p = (unsigned char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+  c->dtao_set[1] = (double*)p;
+  c->acc_cur = 0;
   return cudaSuccess;
 }
 
@@ -193,6 +199,8 @@ cudaError_t build_index(sppm_ctx* c) {
   CK(dev_reserve(c->cub_tmp, tmp));
   CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k1, k2, i1, i2, (int)n, 0, end_bit, st));
   hp_permute_kernel<<<nblk(n), TPB, 0, st>>>(raw, i2, n, c->soa);
+  CK(cudaMemsetAsync(c->dN_set[1], 0, (size_t)n * 4, st));
+  CK(cudaMemsetAsync(c->dtao_set[1], 0, (size_t)n * 24, st));
   c->host_counters.launches += 3;
   // 4. occupied cells (run-length encode of the sorted keys) and their hit-point ranges
   CK(dev_reserve(c->occ_cell, (size_t)n * 4));
@@ -348,9 +356,9 @@ cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cud
   return cudaGetLastError();
 }
 
-cudaError_t launch_update(sppm_ctx* c) {
+cudaError_t launch_update(sppm_ctx* c, cudaStream_t st) {
   if (c->n_hp == 0) return cudaSuccess;
-  update_kernel<<<nblk(c->n_hp), TPB, 0, c->stream>>>(c->soa, c->n_hp, c->prm.update_mode, c->prm.alpha);
+  update_kernel<<<nblk(c->n_hp), TPB, 0, st>>>(c->soa, c->n_hp, c->prm.update_mode, c->prm.alpha);
   c->host_counters.launches++;
   return cudaGetLastError();
 }

@@ -70,10 +70,14 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
   w.counters = (DevCounters*)c->counters.p;
   w.begin = begin;
   w.count = count;
-  // from this bounce on (about 1 photon in 6 still alive) the Bezier solves go to the persistent tracer in one
-  // launch instead of one latency-bound Newton launch per bounce; SPPM_WF_TAIL = -1 switches it off
-  w.tail_bounce = 6;
+  // Tuning knobs, both measured and left off (profiles/r2_D_ab.txt).  SPPM_WF_TAIL = b: from bounce b on the
+  // Bezier-pending photons go to the persistent tracer in one launch instead of one latency-bound Newton launch
+  // per bounce — the Newton launches shrink by 0.2 ms per round but the hand-over kernel costs 0.44 ms (a warp of
+  // 32 such photons runs ~100 serial Newton rounds).  SPPM_NEWTON_DYNAMIC = 1: see newton_items_kernel.
+  w.tail_bounce = -1;
   if (const char* e = getenv("SPPM_WF_TAIL")) w.tail_bounce = atoi(e);
+  w.newton_dynamic = 0;
+  if (const char* e = getenv("SPPM_NEWTON_DYNAMIC")) w.newton_dynamic = atoi(e);
   w.q_cap = (unsigned)Ln.wf_cap;
   w.grid = c->grid;
   w.cell_slot = c->index_ok ? (const int32_t*)c->cell_slot.p : nullptr;

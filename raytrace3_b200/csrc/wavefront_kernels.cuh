@@ -379,11 +379,12 @@ struct NewtonArgs {
   unsigned* work;  // chunk cursor of this launch (zeroed with the batch's counters)
 };
 
-// Bezier3::newton for the queued (photon slot, patch) items.  Warps take chunks of C items from a global
-// cursor and run the C*restarts tasks over their 32 lanes with flush_items (scene.cuh): lanes = restarts,
-// arg-min on (t, restart) per item.  Chunks are handed out dynamically because the work of an item is
-// either a full solve or nothing (46 % are proven empty by the 13-DOP line test): with a static partition
-// the slowest warp of the first bounces ran about twice the average number of rounds.
+// Bezier3::newton for the queued (photon slot, patch) items.  Each warp takes chunks of C items and runs the
+// C*restarts tasks over its 32 lanes with flush_items (scene.cuh): lanes = restarts, arg-min on (t, restart)
+// per item.  Chunks come from a static partition, or (WfBatch::newton_dynamic) from a global cursor: the work of
+// an item is either a full solve or nothing (46 % are proven empty by the 13-DOP line test), but measured on
+// the B200 the kernel is bound by the latency of the FP64 chain at 2 warps per scheduler, not by imbalance
+// (0.83 ms per round either way), and warps that finish early make room for the other lanes' kernels.
 __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_items_kernel(const NewtonArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned n = min(*a.n_items_ptr, a.item_cap);
@@ -394,14 +395,17 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_i
   const int lane = threadIdx.x & 31;
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-  (void)warp_global;
-  // about four chunks per warp; few items: one per warp keeps the serial Newton chain short
-  unsigned C = (n + 4 * n_warps - 1) / (4 * n_warps);
+  // static: C items per warp so that all warps of the grid get work (few items: one per warp keeps the serial
+  // Newton chain short); dynamic (a.work != null): about four chunks per warp from a global cursor
+  const unsigned per = a.work ? 4u * n_warps : n_warps;
+  unsigned C = (n + per - 1) / per;
   C = C < 1 ? 1 : (C > 32 ? 32 : C);
-  for (;;) {
-    unsigned c0 = 0;
-    if (lane == 0) c0 = atomicAdd(a.work, C);
-    c0 = __shfl_sync(FULL, c0, 0);
+  for (unsigned c_static = warp_global * C;; c_static += n_warps * C) {
+    unsigned c0 = c_static;
+    if (a.work) {
+      if (lane == 0) c0 = atomicAdd(a.work, C);
+      c0 = __shfl_sync(FULL, c0, 0);
+    }
     if (c0 >= n) break;
     const int cnt = (int)min(C, n - c0);
     if (lane < cnt) {
@@ -480,6 +484,7 @@ struct WfBatch {
   DevCounters* counters;
   uint64_t begin, count;  // photon range per light
   int tail_bounce;        // >= 0: from this bounce on Bezier-pending photons spill to the persistent tracer
+  int newton_dynamic;     // Newton chunks from a global cursor instead of a static partition
   unsigned q_cap;         // entries per queue half (>= n_light * count)
   Grid grid;
   const int32_t* cell_slot;
@@ -546,7 +551,7 @@ inline NewtonArgs wf_newton_args(const WfBatch& w, const WfLayout& L, const Step
   n.it = a.it_out;
   n.n_items_ptr = a.n_items_out;
   n.item_cap = L.item_cap;
-  n.work = L.counters + 100 + a.bounce;
+  n.work = w.newton_dynamic ? L.counters + 100 + a.bounce : nullptr;
   return n;
 }
 

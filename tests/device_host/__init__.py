@@ -187,7 +187,7 @@ class HostScene:
         return dict(x=out["x"][order], n=out["n"][order], flux=out["flux"][order], photon=photon[order],
                     bounce=bounce[order]), dict(zip(COUNTERS, cnt.tolist()))
 
-    def photon_trace_wavefront(self, prm, begin, count, pass_id, step_blocks=24, newton_blocks=24, item_cap=0, tail_bounce=6):
+    def photon_trace_wavefront(self, prm, begin, count, pass_id, step_blocks=24, newton_blocks=24, item_cap=0, tail_bounce=-1):
         """The bounce-synchronous pass (photon_step_kernel + newton_items_kernel per bounce, the
         product's wf_layout / wf_step_args / wf_newton_args) -> deposits sorted by (photon id, bounce),
         counters, and the queue counts [bounce][region]."""

@@ -515,10 +515,11 @@ def test_wavefront_kernels_against_oracle(dh, oracle, name, count):
         assert qc[:, 3].sum() == 0
 
 
-@pytest.mark.parametrize("tail", [-1, 6, 2, 0])
+@pytest.mark.parametrize("tail", [-1, 6, 3, 0])
 def test_wavefront_equals_persistent_on_the_cpu(dh, tail):
     """Both tracer organisations, FAST Newton + FAST math (the bench configuration): same deposits — with the
-    tail hand-over off (-1), at the product's bounce (6), early (2) and with every Bezier solve handed over (0)."""
+    tail hand-over off (-1, the product's setting), late (6), early (3) and with every Bezier solve handed over (0);
+    odd values also switch the Newton kernel to dynamic chunks."""
     hs = dh.scene(_scene("stress"))
     prm = _params(newton_mode=abi.SPPM_NEWTON_FAST, math_mode=abi.SPPM_MATH_FAST)
     a, ca = hs.photon_trace_kernel(prm, 0, 30000, 2)
