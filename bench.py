@@ -597,7 +597,8 @@ def multi_gpu_parity(ctx, Context, abi, torch, dist, scene, cam, prm, rank, worl
     p = abi.SppmParams.from_buffer_copy(prm)
     p.count_pairs = 0
     ctx.set_params(p)
-    ctx.build_index()                      # fresh accumulators on the benchmark's hit-point map
+    ctx.eye_pass(cam, 0)                   # the same eye pass as the one-GPU run below (the e2e leg left pass 100 + i's map)
+    ctx.build_index()                      # fresh accumulators
     b, c = photon_range(small, rank, world)
     ctx.photon_pass(b, c, 7777)
     ctx.allreduce()

@@ -192,12 +192,16 @@ cudaError_t build_index(sppm_ctx* c) {
     CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, o1, o2, i2, i1, (int)n, 0, okey_bits, st));
     c->host_counters.launches += 2;
   }
-  hp_key_kernel<<<nblk(n), TPB, 0, st>>>(raw, i1, n, g, k1);
+  uint64_t *m1 = (uint64_t*)c->dep_key.p, *m2 = (uint64_t*)c->dep_key2.p;  // (cell, Morton code in the cell) keys
+  hp_key_kernel<<<nblk(n), TPB, 0, st>>>(raw, i1, n, g, m1);
   c->host_counters.launches++;
-  const int end_bit = bits_for((uint64_t)g.n_cells - 1);
-  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k1, k2, i1, i2, (int)n, 0, end_bit, st));
+  const int end_bit = bits_for((uint64_t)g.n_cells - 1) + HP_MORTON_BITS;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, m1, m2, i1, i2, (int)n, 0, end_bit, st));
   CK(dev_reserve(c->cub_tmp, tmp));
-  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, k1, k2, i1, i2, (int)n, 0, end_bit, st));
+  CK(cub::DeviceRadixSort::SortPairs(c->cub_tmp.p, tmp, m1, m2, i1, i2, (int)n, 0, end_bit, st));
+  hp_cell_of_key_kernel<<<nblk(n), TPB, 0, st>>>(m2, n, k1);  // k1 aliases m1, which the sort has consumed
+  c->host_counters.launches++;
+  k2 = k1;
   hp_permute_kernel<<<nblk(n), TPB, 0, st>>>(raw, i2, n, c->soa);
   CK(cudaMemsetAsync(c->dN_set[1], 0, (size_t)n * 4, st));
   CK(cudaMemsetAsync(c->dtao_set[1], 0, (size_t)n * 24, st));

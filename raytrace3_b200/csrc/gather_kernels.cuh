@@ -52,12 +52,38 @@ __global__ void hp_okey_kernel(const HpRaw* hp, long long n, uint64_t* okey, uin
   okey[i] = hp[i].okey;
   idx[i] = (uint32_t)i;
 }
-// cell key of the hit points taken in canonical (okey) order
-__global__ void hp_key_kernel(const HpRaw* hp, const uint32_t* idx, long long n, Grid g, uint32_t* key) {
+// Sort key of the hit points taken in canonical (okey) order: grid cell in the high bits, below it a 15-bit
+// Morton code of the position inside the cell (5 bits per axis).  Hit points that are consecutive in the sorted
+// map are then neighbours in space, so a work unit of the gather (<= 64 consecutive hit points) is a compact
+// cluster with a small bounding box instead of a strip of film rows — fewer deposits survive its cull.  Ties
+// keep the canonical order (stable sort), so every rank of a multi-GPU run still holds the same map.
+constexpr int HP_MORTON_BITS = 15;
+__device__ __forceinline__ uint32_t spread5(uint32_t v) {  // abcde -> a00b00c00d00e
+  v &= 31u;
+  v = (v | (v << 8)) & 0x100fu;
+  v = (v | (v << 4)) & 0x10c3u;
+  v = (v | (v << 2)) & 0x1249u;
+  return v;
+}
+__global__ void hp_key_kernel(const HpRaw* hp, const uint32_t* idx, long long n, Grid g, uint64_t* key) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const HpRaw& r = hp[idx[i]];
-  key[i] = (uint32_t)grid_cell(g, r.pos[0], r.pos[1], r.pos[2]);
+  const int64_t c = grid_cell(g, r.pos[0], r.pos[1], r.pos[2]);
+  const int ix = (int)(c % g.dim[0]), iy = (int)((c / g.dim[0]) % g.dim[1]), iz = (int)(c / ((int64_t)g.dim[0] * g.dim[1]));
+  uint32_t q[3];
+  const int ic[3] = {ix, iy, iz};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {  // a hit point clamped into a boundary cell lies outside it: clamp the code too
+    const double f = ((r.pos[k] - g.org[k]) * g.inv_cell - ic[k]) * 32.0;
+    q[k] = f > 0 ? (f < 31 ? (uint32_t)f : 31u) : 0u;
+  }
+  key[i] = ((uint64_t)c << HP_MORTON_BITS) | spread5(q[0]) | (spread5(q[1]) << 1) | (spread5(q[2]) << 2);
+}
+// the grid cell of every sorted key (run-length encoded into the occupied-cell list)
+__global__ void hp_cell_of_key_kernel(const uint64_t* key, long long n, uint32_t* cell) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cell[i] = (uint32_t)(key[i] >> HP_MORTON_BITS);
 }
 
 __global__ void hp_permute_kernel(const HpRaw* hp, const uint32_t* idx, long long n, HpSoA s) {
@@ -559,7 +585,8 @@ constexpr int W_SLICE = SPPM_W_SLICE;                          // deposits per w
 constexpr int W_RAW_BYTES = W_SLICE * (int)sizeof(Deposit);   // 2560
 constexpr int F_PAIR_F4 = 6;                                  // 16-byte words per converted pair (96 B)
 constexpr int W_CONV_BYTES = (W_SLICE / 2) * F_PAIR_F4 * 16;  // 1536
-constexpr int W_PER_WARP = 2 * W_RAW_BYTES + W_CONV_BYTES + 128;  // + kept-index list
+constexpr int W_FULL_BYTES = 3 * 32 * 8;                       // per lane: flux sums of the deposits the whole unit accepts
+constexpr int W_PER_WARP = 2 * W_RAW_BYTES + W_CONV_BYTES + 128 + W_FULL_BYTES;  // + kept-index list + full-accept sums
 constexpr size_t F_SMEM = (size_t)W_WARPS * W_PER_WARP;
 constexpr int W_CHUNK = 64;                                   // hit points per chunk (2 per lane)
 #define SPPM_F_U 5.9604644775390625e-8 /* 2^-24 */
@@ -721,7 +748,7 @@ __device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const 
 // Algorithmic work counters of the filtered gather (tools/gather_work_model.py): they exist in the CPU
 // emulation of tests/device_host only and expand to nothing in the library.
 #ifdef SPPM_HOST_EMULATION
-enum { WK_ITEMS, WK_SLICES, WK_VISITS, WK_KEPT, WK_PAIRS, WK_PAIR_SLOTS, WK_REDO_LANES, WK_N };
+enum { WK_ITEMS, WK_SLICES, WK_VISITS, WK_KEPT, WK_PAIRS, WK_PAIR_SLOTS, WK_REDO_LANES, WK_FULL, WK_N };
 extern unsigned long long dh_work[WK_N];
 #define SPPM_WORK(k, v)                                                                          \
   do {                                                                                           \
@@ -740,6 +767,7 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
   unsigned char* my = wsm + w * W_PER_WARP;
   float4* conv = reinterpret_cast<float4*>(my + 2 * W_RAW_BYTES);
   unsigned char* kidx = my + 2 * W_RAW_BYTES + W_CONV_BYTES;
+  double* fsum = reinterpret_cast<double*>(my + 2 * W_RAW_BYTES + W_CONV_BYTES + 128);  // [3][32]
   if (lane == 0) {
     mbar_init(&bar[w][0], 1);
     mbar_init(&bar[w][1], 1);
@@ -859,7 +887,7 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
     bool far_hp[HBMAX] = {};
     bool uni_me = true, nuni_me = true;
     const double rnx = a.s.nx[h0], rny = a.s.ny[h0], rnz = a.s.nz[h0];  // the unit's first normal (uniform loads)
-    double rmax = 0;  // largest R2 among the unit's hit points on the FP32 path
+    double rmax = 0, rmin = 1e300;  // largest / smallest R2 among the unit's hit points on the FP32 path
     float blo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bhi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
 #pragma unroll
     for (int b = 0; b < HBMAX; b++) {
@@ -881,6 +909,7 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
           uni_me = uni_me && (r2 == a.search_r2);
           nuni_me = nuni_me && (nx == rnx && ny == rny && nz == rnz);
           rmax = fmax(rmax, r2);
+          rmin = fmin(rmin, r2);
         }
       }
     }
@@ -891,7 +920,10 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
     // Not in the diagnostic COUNT build: cand_pairs counts pairs by distance alone.
     const bool nuni = !COUNT && __all_sync(FULL, nuni_me);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) rmax = fmax(rmax, __shfl_xor_sync(FULL, rmax, off));
+    for (int off = 16; off > 0; off >>= 1) {
+      rmax = fmax(rmax, __shfl_xor_sync(FULL, rmax, off));
+      rmin = fmin(rmin, __shfl_xor_sync(FULL, rmin, off));
+    }
     // Cull radius: a pair is accepted only if vv < searchR2 AND vv <= R2 of its hit point (Raytracer.h:146,154), so a
     // deposit farther than min(searchR2, max R2 of the unit) from the unit's bounding box cannot be accepted by any
     // of its hit points.  Once HitPoint::update has shrunk the radii (PROGRESSIVE passes) this removes most of the
@@ -904,6 +936,20 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
         blo[k] = fminf(blo[k], __shfl_xor_sync(FULL, blo[k], off));
         bhi[k] = fmaxf(bhi[k], __shfl_xor_sync(FULL, bhi[k], off));
       }
+    // Whole-unit accept.  A deposit whose distance to the FARTHEST corner of the unit's bounding box is below
+    // min(searchR2, smallest R2 of the unit) by more than the classification bound is inside the ball of every hit
+    // point of the unit; if it also passes the unit's (single, exact) normal test, all H hit points accept it
+    // (Raytracer.h:154).  Such deposits never reach the pair loop: their flux goes to one sum per lane and the
+    // unit's hit points receive count and sum once, at the end.  The bound: the far-corner offset per coordinate
+    // is max(x^ - lo^, hi^ - x^) over FP32 values that bracket every hit point's FP32 coordinate, so the FP32 sum
+    // of squares over-estimates each pair's S^ up to rounding, and S^ is within band_v of the reference's vv
+    // (derivation above): S^far < T - 2 band_v  =>  vv < T for every hit point.  Dense maps (4K film) accept a
+    // third to a half of the surviving deposits this way; at 1024 x 768 a unit is as wide as the radius and few do.
+    const bool full_ok = !COUNT && nuni && !__any_sync(FULL, far_hp[0] || far_hp[HBMAX - 1]);
+    const double full_T = fmin(a.search_r2, rmin) - 2.0 * band_v;
+    const float full_thr = full_ok && full_T > 0 ? __double2float_rd(full_T) : -1.f;
+    int fcnt = 0;
+    if (full_ok) fsum[lane] = fsum[32 + lane] = fsum[64 + lane] = 0;
     int cnt[HBMAX] = {};
     double sum[HBMAX][3] = {};
     unsigned cand32 = 0;
@@ -938,6 +984,14 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
           const float ex = fmaxf(fmaxf(blo[0] - fx, fx - bhi[0]), 0.f), ey = fmaxf(fmaxf(blo[1] - fy, fy - bhi[1]), 0.f),
                       ez = fmaxf(fmaxf(blo[2] - fz, fz - bhi[2]), 0.f);
           keep = !out && n_ok && !(fmaf(ez, ez, fmaf(ey, ey, ex * ex)) > cull_thr);
+          if (keep && full_thr > 0.f) {
+            const float mx = fmaxf(fx - blo[0], bhi[0] - fx), my2 = fmaxf(fy - blo[1], bhi[1] - fy), mz = fmaxf(fz - blo[2], bhi[2] - fz);
+            if (fmaf(mz, mz, fmaf(my2, my2, mx * mx)) < full_thr) {  // every hit point of the unit accepts this deposit
+              keep = false;
+              fcnt++;
+              fsum[lane] += q3.x; fsum[32 + lane] += q3.y; fsum[64 + lane] += q4.x;
+            }
+          }
         }
         const unsigned kmask = __ballot_sync(FULL, keep);
         if (keep) {
@@ -1032,6 +1086,22 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
     }
     acc_total += (unsigned)(cnt[0] + (HBMAX > 1 ? cnt[HBMAX - 1] : 0));
     cand += cand32;
+    // whole-unit accepts of this item: one count and one flux sum for all H hit points
+    int fc_all = 0;
+    double fall[3] = {0, 0, 0};
+    if (full_ok && __any_sync(FULL, fcnt > 0)) {
+      fc_all = fcnt;
+      fall[0] = fsum[lane]; fall[1] = fsum[32 + lane]; fall[2] = fsum[64 + lane];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        fc_all += __shfl_xor_sync(FULL, fc_all, off);
+        fall[0] += __shfl_xor_sync(FULL, fall[0], off);
+        fall[1] += __shfl_xor_sync(FULL, fall[1], off);
+        fall[2] += __shfl_xor_sync(FULL, fall[2], off);
+      }
+      if (lane == 0) acc_total += (unsigned long long)fc_all * (unsigned)H;
+      SPPM_WORK(WK_FULL, fc_all);
+    }
     // combine the sub-slices of a hit point (lanes my_h, my_h + hl, ...)
     for (int o = hl; o < 32; o <<= 1) {
 #pragma unroll
@@ -1045,10 +1115,11 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
     if (sub_id == 0) {
 #pragma unroll
       for (int b = 0; b < HBMAX; b++) {
+        cnt[b] += fc_all;
         if (valid[b] && cnt[b] > 0) {  // hp->newN++, hp->tao += wgt.mul(flux)*PI_INV (Raytracer.h:155-156)
           const int i = idx[b];
-          const double d0 = (a.s.wx[i] * sum[b][0]) * SPPM_PI_INV, d1 = (a.s.wy[i] * sum[b][1]) * SPPM_PI_INV,
-                       d2 = (a.s.wz[i] * sum[b][2]) * SPPM_PI_INV;
+          const double d0 = (a.s.wx[i] * (sum[b][0] + fall[0])) * SPPM_PI_INV, d1 = (a.s.wy[i] * (sum[b][1] + fall[1])) * SPPM_PI_INV,
+                       d2 = (a.s.wz[i] * (sum[b][2] + fall[2])) * SPPM_PI_INV;
           if (shared_unit) {
             atomicAdd(&a.s.dN[i], cnt[b]);
             atomicAdd(&a.s.dtao[i], d0);

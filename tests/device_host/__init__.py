@@ -395,7 +395,7 @@ class DeviceHost:
         self.lib.dh_bounds(pos.shape[0], _p(raw), blocks, _p(out))
         return out[:3], out[3:6], out[6:]
 
-    WORK = ("items", "slices", "visits", "kept", "pairs", "pair_slots", "redo_lanes")
+    WORK = ("items", "slices", "visits", "kept", "pairs", "pair_slots", "redo_lanes", "full_accepts")
 
     def gather_work(self, reset=True):
         """Algorithmic work counters of gather_filtered_kernel since the last reset (emulation only)."""

@@ -172,6 +172,10 @@ inline float __double2float_ru(double d) {  // round towards +inf
   float f = (float)d;
   return (double)f < d ? nextafterf(f, INFINITY) : f;
 }
+inline float __double2float_rd(double d) {  // round towards -inf
+  float f = (float)d;
+  return (double)f > d ? nextafterf(f, -INFINITY) : f;
+}
 inline unsigned __float_as_uint(float f) {
   unsigned u;
   memcpy(&u, &f, 4);

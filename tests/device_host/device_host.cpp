@@ -525,7 +525,8 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   const int T = bt(TPB);
   auto nb = [&](long long k) { return (k + T - 1) / T; };
   // hit points: cell keys, stable sort, SoA permute
-  std::vector<uint32_t> iota((size_t)n), key((size_t)n), idx((size_t)n), skey((size_t)n);
+  std::vector<uint32_t> iota((size_t)n), idx((size_t)n), skey((size_t)n);
+  std::vector<uint64_t> key((size_t)n), skey64((size_t)n);  // (cell, Morton code in the cell)
   // canonical order first (sort by okey = pixel, eye-path node), then a stable sort by cell key
   std::vector<uint64_t> okey0((size_t)n);
   launch(hp_okey_kernel, std::make_tuple(raw, (long long)n, okey0.data(), iota.data()), nb(n), T);
@@ -536,8 +537,9 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   std::stable_sort(pos.begin(), pos.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
   for (int64_t i = 0; i < n; i++) {
     idx[(size_t)i] = iota[pos[(size_t)i]];
-    skey[(size_t)i] = key[pos[(size_t)i]];
+    skey64[(size_t)i] = key[pos[(size_t)i]];
   }
+  launch(hp_cell_of_key_kernel, std::make_tuple((const uint64_t*)skey64.data(), (long long)n, skey.data()), nb(n), T);
   const size_t nd = (size_t)n;
   std::vector<double> dstore(nd * 16);
   std::vector<uint64_t> okey(nd);

@@ -626,6 +626,44 @@ def test_gather_filtered_plane_units_and_shrunk_radii(dh, oracle):
     assert info["n_units"] > 100
 
 
+def test_gather_filtered_whole_unit_accept_on_dense_planes(dh, oracle):
+    """A dense hit-point map (the 4K film's regime: a work unit of 64 hit points is much smaller than the radius):
+    deposits inside the ball of EVERY hit point of a unit are accepted for the whole unit without a pair test.  Deposits
+    at distance^2 = T (1 +- delta) of single hit points, T in {searchR2, R2}, delta down to 1e-16, and at the normal
+    threshold must still give the exhaustive search's newN bit for bit; the full-accept path must have been taken."""
+    rng = np.random.RandomState(33)
+    k = 9000
+    pos = np.zeros((k, 3))
+    pos[:, 0], pos[:, 2] = rng.uniform(0, 5, k), rng.uniform(0, 5, k)
+    pos[:, 1] = 1.0
+    nrm = np.tile(np.array([0., 1., 0.]), (k, 1))
+    side = np.zeros((3000, 3))                       # a second plane meeting the first at a right angle
+    side[:, 1], side[:, 2] = rng.uniform(1, 4, 3000), rng.uniform(0, 5, 3000)
+    pos = np.concatenate([pos, side])
+    nrm = np.concatenate([nrm, np.tile(np.array([1., 0., 0.]), (3000, 1))])
+    n = pos.shape[0]
+    r2 = np.where(rng.uniform(size=n) < 0.5, 2.0, rng.choice([0.6, 1.1, 1.7], size=n))
+    r2[(pos[:, 0] > 2.5) & (pos[:, 1] == 1.0)] = 2.0   # half of the floor: units with R2 == searchR2 throughout
+    hp = dict(pos=pos, n=nrm, wgt=rng.uniform(0.1, 1, size=(n, 3)), r2=r2)
+    m = 30000
+    who = rng.randint(0, n, m)
+    delta = rng.choice([0.0, 1e-16, 1e-15, 1e-13, 1e-10, 1e-7, 1e-4], size=m) * rng.choice([-1, 1], size=m)
+    d = rng.normal(size=(m, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    T = np.where(rng.uniform(size=m) < 0.5, 2.0, r2[who])
+    rad = np.sqrt(T * (1 + delta))
+    rad[m // 2:] = rng.uniform(0, 1.6, m - m // 2)
+    x = pos[who] + d * rad[:, None]
+    x[m // 2:, 1] = np.where(rng.uniform(size=m - m // 2) < 0.7, 1.0 + 1e-3 * rng.normal(size=m - m // 2), x[m // 2:, 1])  # most lie on the floor
+    cosv = np.where(rng.uniform(size=m) < 0.2, 1e-3 * (1 + delta), rng.uniform(0.01, 1, m))
+    t = np.cross(nrm[who], rng.normal(size=(m, 3)))
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    dn = nrm[who] * cosv[:, None] + t * np.sqrt(np.maximum(0, 1 - cosv ** 2))[:, None]
+    dh.gather_work(reset=True)
+    _check_gather(dh, oracle, hp, x, dn, rng.uniform(0, 100, size=(m, 3)), min_acc=100000)
+    assert dh.gather_work()["full_accepts"] > 10000
+
+
 def test_gather_filtered_kernel_bit_exact_newN(dh, oracle):
     """Raytracer.h:139-159 incl. deposits exactly at distance^2 == searchR2 (strict '<', Q3) and == R2 ('<=')."""
     rng = np.random.RandomState(7)
