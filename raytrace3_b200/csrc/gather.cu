@@ -193,7 +193,9 @@ cudaError_t build_index(sppm_ctx* c) {
     c->host_counters.launches += 2;
   }
   uint64_t *m1 = (uint64_t*)c->dep_key.p, *m2 = (uint64_t*)c->dep_key2.p;  // (cell, Morton code in the cell) keys
-  hp_key_kernel<<<nblk(n), TPB, 0, st>>>(raw, i1, n, g, m1);
+  int morton = 1;  // SPPM_HP_MORTON=0: film order inside a cell, as round 1 (A/B knob)
+  if (const char* e = getenv("SPPM_HP_MORTON")) morton = atoi(e);
+  hp_key_kernel<<<nblk(n), TPB, 0, st>>>(raw, i1, n, g, m1, morton);
   c->host_counters.launches++;
   const int end_bit = bits_for((uint64_t)g.n_cells - 1) + HP_MORTON_BITS;
   CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, m1, m2, i1, i2, (int)n, 0, end_bit, st));
@@ -326,6 +328,8 @@ cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cud
     a.occ_cell = (const uint32_t*)c->occ_cell.p;
     a.units = (const GUnit*)c->units.p;
     a.n_units = c->n_units;
+    a.full_accept = 1;
+    if (const char* e = getenv("SPPM_GATHER_FULL")) a.full_accept = atoi(e);
     const bool filtered = c->prm.gather_mode == SPPM_GATHER_FILTERED;
     auto kern = !filtered ? gather_kernel : (c->prm.count_pairs ? gather_filtered_kernel<true> : gather_filtered_kernel<false>);
     const size_t tile_bytes = filtered ? F_SMEM : 2 * (size_t)G_TILE * sizeof(Deposit);

@@ -65,7 +65,7 @@ __device__ __forceinline__ uint32_t spread5(uint32_t v) {  // abcde -> a00b00c00
   v = (v | (v << 2)) & 0x1249u;
   return v;
 }
-__global__ void hp_key_kernel(const HpRaw* hp, const uint32_t* idx, long long n, Grid g, uint64_t* key) {
+__global__ void hp_key_kernel(const HpRaw* hp, const uint32_t* idx, long long n, Grid g, uint64_t* key, int morton) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const HpRaw& r = hp[idx[i]];
@@ -78,7 +78,7 @@ __global__ void hp_key_kernel(const HpRaw* hp, const uint32_t* idx, long long n,
     const double f = ((r.pos[k] - g.org[k]) * g.inv_cell - ic[k]) * 32.0;
     q[k] = f > 0 ? (f < 31 ? (uint32_t)f : 31u) : 0u;
   }
-  key[i] = ((uint64_t)c << HP_MORTON_BITS) | spread5(q[0]) | (spread5(q[1]) << 1) | (spread5(q[2]) << 2);
+  key[i] = ((uint64_t)c << HP_MORTON_BITS) | (morton ? spread5(q[0]) | (spread5(q[1]) << 1) | (spread5(q[2]) << 2) : 0u);
 }
 // the grid cell of every sorted key (run-length encoded into the occupied-cell list)
 __global__ void hp_cell_of_key_kernel(const uint64_t* key, long long n, uint32_t* cell) {
@@ -279,6 +279,7 @@ struct GatherArgs {
   const GUnit* units;        // filtered kernel: work units
   int n_units;
   const int32_t* item_off;   // [n_units + 1] exclusive scan of the units' work-item counts (this batch)
+  int full_accept;           // filtered kernel: whole-unit accept on (see gather_filtered_kernel)
 };
 
 // ---- TMA (cp.async.bulk) + mbarrier helpers -----------------------------------------------
@@ -945,8 +946,12 @@ __global__ void __launch_bounds__(W_THREADS, SPPM_GATHER_MINBLOCKS) gather_filte
     // of squares over-estimates each pair's S^ up to rounding, and S^ is within band_v of the reference's vv
     // (derivation above): S^far < T - 2 band_v  =>  vv < T for every hit point.  Dense maps (4K film) accept a
     // third to a half of the surviving deposits this way; at 1024 x 768 a unit is as wide as the radius and few do.
-    const bool full_ok = !COUNT && nuni && !__any_sync(FULL, far_hp[0] || far_hp[HBMAX - 1]);
+    // Only units that are small against the radius try: the deposits that qualify lie within sqrt(T) - half
+    // the box diagonal of the box centre, and where that region is small the test costs more than it saves.
     const double full_T = fmin(a.search_r2, rmin) - 2.0 * band_v;
+    const double hdx = 0.5 * ((double)bhi[0] - (double)blo[0]), hdy = 0.5 * ((double)bhi[1] - (double)blo[1]), hdz = 0.5 * ((double)bhi[2] - (double)blo[2]);
+    const bool full_ok = !COUNT && a.full_accept && nuni && !__any_sync(FULL, far_hp[0] || far_hp[HBMAX - 1]) &&
+                         (hdx * hdx + hdy * hdy + hdz * hdz) * 9.0 < full_T;  // half diagonal < a third of the radius
     const float full_thr = full_ok && full_T > 0 ? __double2float_rd(full_T) : -1.f;
     int fcnt = 0;
     if (full_ok) fsum[lane] = fsum[32 + lane] = fsum[64 + lane] = 0;

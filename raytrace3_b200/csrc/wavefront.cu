@@ -76,7 +76,7 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
   // 32 such photons runs ~100 serial Newton rounds).  SPPM_NEWTON_DYNAMIC = 1: see newton_items_kernel.
   w.tail_bounce = -1;
   if (const char* e = getenv("SPPM_WF_TAIL")) w.tail_bounce = atoi(e);
-  w.newton_dynamic = 0;
+  w.newton_dynamic = 1;
   if (const char* e = getenv("SPPM_NEWTON_DYNAMIC")) w.newton_dynamic = atoi(e);
   w.q_cap = (unsigned)Ln.wf_cap;
   w.grid = c->grid;

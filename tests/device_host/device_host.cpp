@@ -531,7 +531,7 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   std::vector<uint64_t> okey0((size_t)n);
   launch(hp_okey_kernel, std::make_tuple(raw, (long long)n, okey0.data(), iota.data()), nb(n), T);
   std::stable_sort(iota.begin(), iota.end(), [&](uint32_t a, uint32_t b) { return okey0[a] < okey0[b]; });
-  launch(hp_key_kernel, std::make_tuple(raw, (const uint32_t*)iota.data(), (long long)n, g, key.data()), nb(n), T);
+  launch(hp_key_kernel, std::make_tuple(raw, (const uint32_t*)iota.data(), (long long)n, g, key.data(), 1), nb(n), T);
   std::vector<uint32_t> pos((size_t)n);  // key[] is indexed by canonical position
   std::iota(pos.begin(), pos.end(), 0u);
   std::stable_sort(pos.begin(), pos.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
@@ -626,6 +626,7 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
   a.occ_cell = occ_cell.data();
   a.units = units.data();
   a.n_units = n_units;
+  a.full_accept = 1;
   a.item_off = item_off.data();
   unsigned int work_counter = 0;
   if (n_units > 0) {
