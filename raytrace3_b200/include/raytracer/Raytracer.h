@@ -209,9 +209,10 @@ class SPPMRayTracer {  // Raytracer.h:421-477
           for (int k = 0; k < 3; k++) film[((size_t)i1 * camera.w + jj) * 3 + k] = camera.pic[i1][jj].val[k];
       image.resize(film.size());
       sppm_host::check(sppm_tonemap(ctxs[0], film.data(), camera.w, camera.h, (i + 1) * (double)replicas, image.data()), ctxs[0], "sppm_tonemap");
-      saveImage(ctxs[0], i, camera.w, camera.h);
+      // checkpoint first, image second: a crash between the two repeats the image, not the iteration
       if (checkpoint_every > 0 && !checkpoint_path.empty() && (i + 1) % checkpoint_every == 0)
         saveCheckpoint(camera.w, camera.h, false, i + 1, film, 0);
+      saveImage(ctxs[0], i, camera.w, camera.h);
     }
     for (sppm_ctx* x : ctxs) sppm_ctx_destroy(x);
   }
@@ -258,13 +259,13 @@ class SPPMRayTracer {  // Raytracer.h:421-477
       }
       sppm_host::check(sppm_shared_resolve(ctx, film.data()), ctx, "sppm_shared_resolve");
       sppm_host::check(sppm_tonemap(ctx, film.data(), camera.w, camera.h, 1.0, image.data()), ctx, "sppm_tonemap");
-      saveImage(ctx, i, camera.w, camera.h);
       if (checkpoint_every > 0 && !checkpoint_path.empty() && (i + 1) % checkpoint_every == 0) {
         std::vector<double> st(5 * np);
         uint64_t photons = 0;
         sppm_host::check(sppm_shared_export(ctx, st.data(), st.data() + np, st.data() + 2 * np, &photons), ctx, "sppm_shared_export");
         saveCheckpoint(camera.w, camera.h, true, i + 1, st, photons);
       }
+      saveImage(ctx, i, camera.w, camera.h);
     }
     sppm_ctx_destroy(ctx);
   }
@@ -291,6 +292,13 @@ class SPPMRayTracer {  // Raytracer.h:421-477
     if (ok && (hdr[0] != w || hdr[1] != h || hdr[2] != (shared ? 1 : 0))) {
       std::fclose(f);
       throw std::runtime_error("checkpoint: film size / estimator differ from this job: " + checkpoint_path);
+    }
+    // the payload length and the iteration count are the file's word: hold them to what this job can use
+    // (film: w*h*3 doubles; shared statistics: R2, N, tau[3] per pixel) before anything is sized from them
+    const int64_t want = (int64_t)(shared ? 5 : 3) * w * h;
+    if (ok && (hdr[4] != want || hdr[3] < 0 || hdr[3] > sppmtime)) {
+      std::fclose(f);
+      throw std::runtime_error("checkpoint: payload length or iteration count does not fit this job: " + checkpoint_path);
     }
     if (ok) {
       data.resize((size_t)hdr[4]);
