@@ -605,7 +605,8 @@ def multi_gpu_parity(ctx, Context, abi, torch, dist, scene, cam, prm, rank, worl
     ctx.update()
     n = ctx.counters()["hit_points"]
     st = ctx.export_stats(n)
-    digest = hashlib.sha256(st["newN"].tobytes()).digest()[:8]
+    count = st["newN"] + st["N"]      # PROGRESSIVE update folds newN into N (alpha = 0.7, truncated) and clears it
+    digest = hashlib.sha256(count.tobytes()).digest()[:8]
     mine = torch.tensor(list(digest), dtype=torch.uint8, device=f"cuda:{local_rank}")
     allv = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allv, mine)
@@ -624,18 +625,18 @@ def multi_gpu_parity(ctx, Context, abi, torch, dist, scene, cam, prm, rank, worl
             solo.photon_pass(0, small, 7777)
             solo.update()
             ref = solo.export_stats(m)
-        if m != n or not np.array_equal(ref["newN"], st["newN"]):
-            out = f"newN of the {world}-GPU round differs from the 1-GPU round ({int((ref['newN'] != st['newN']).sum()) if m == n else 'hit-point counts differ'})"
+        if m != n or not (np.array_equal(ref["newN"], st["newN"]) and np.array_equal(ref["N"], st["N"])):
+            out = f"newN of the {world}-GPU round differs from the 1-GPU round ({int((ref['newN'] + ref['N'] != count).sum()) if m == n else 'hit-point counts differ'})"
         elif not np.allclose(ref["tao"], st["tao"], rtol=1e-11, atol=1e-300):
             out = "tao differs from the 1-GPU round beyond 1e-11"
-        elif int(st["newN"].sum()) == 0:
+        elif int(count.sum()) == 0:
             out = "empty round"
         else:
             rel = max(abs(float(t[k]) - float(tall[0][k])) / max(1e-300, abs(float(tall[0][k]))) for t in tall for k in range(3))
             if rel > 1e-12:
                 out = f"tao sums differ between ranks by {rel:.2e}"
             else:
-                out = {"status": "ok", "photons": small, "ranks": world, "newN_sum": int(st["newN"].sum()),
+                out = {"status": "ok", "photons": small, "ranks": world, "newN_sum": int(count.sum()),
                        "what": "newN bit-identical on all ranks and equal to a 1-GPU run of the same round; tao <= 1e-11"}
     return out
 

@@ -141,7 +141,8 @@ typedef struct SppmParams {
   int32_t gather_mode;     /* SPPM_GATHER_* (ABI version 2) */
   int32_t count_pairs;     /* 1: the gather counts cand_pairs (diagnostic; a few % of its time), 0: cand_pairs stays 0 */
   int32_t math_mode;       /* SPPM_MATH_* */
-  int32_t reserved;
+  int32_t tex_lod;         /* mip level the tracers sample textures at: 0 = the uploaded image (Element.h:61-72, exact),
+                            * l > 0 = the l-th 2x2 box-filtered level (an approximation; ABI version 3, was `reserved`) */
 } SppmParams;
 
 /* Result of one Scene::NearCollide (Scene.h:165-182 / Element.h:20-39 Collision). */

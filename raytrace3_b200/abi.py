@@ -60,7 +60,7 @@ class SppmParams(C.Structure):
     _fields_ = [
         ("init_r2", C.c_double), ("alpha", C.c_double), ("max_dep", C.c_int32), ("newton_iters", C.c_int32),
         ("newton_restarts", C.c_int32), ("update_mode", C.c_int32), ("newton_mode", C.c_int32),
-        ("trace_mode", C.c_int32), ("seed", C.c_uint64), ("gather_mode", C.c_int32), ("count_pairs", C.c_int32), ("math_mode", C.c_int32), ("reserved", C.c_int32),
+        ("trace_mode", C.c_int32), ("seed", C.c_uint64), ("gather_mode", C.c_int32), ("count_pairs", C.c_int32), ("math_mode", C.c_int32), ("tex_lod", C.c_int32),
     ]
 
 
@@ -89,7 +89,7 @@ def default_params() -> SppmParams:
     """The reference's literals; identical to sppm_default_params()."""
     return SppmParams(init_r2=2.0, alpha=0.7, max_dep=13, newton_iters=10, newton_restarts=50,
                       update_mode=SPPM_UPDATE_REFERENCE, newton_mode=SPPM_NEWTON_EXACT, trace_mode=0,
-                      seed=0x5EED5EED, gather_mode=SPPM_GATHER_FILTERED, count_pairs=1, math_mode=SPPM_MATH_EXACT, reserved=0)
+                      seed=0x5EED5EED, gather_mode=SPPM_GATHER_FILTERED, count_pairs=1, math_mode=SPPM_MATH_EXACT, tex_lod=0)
 
 
 VP, I32, I64, U64, DBL = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double

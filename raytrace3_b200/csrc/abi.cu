@@ -231,7 +231,7 @@ int sppm_default_params(SppmParams* p) {
   p->gather_mode = SPPM_GATHER_FILTERED;
   p->count_pairs = 1;
   p->math_mode = SPPM_MATH_EXACT;
-  p->reserved = 0;
+  p->tex_lod = 0;
   return SPPM_OK;
 }
 
@@ -346,7 +346,9 @@ int sppm_set_params(sppm_ctx* c, const SppmParams* p) {
   if (p->newton_restarts < 1 || p->newton_restarts > 4095) return fail(c, SPPM_ERR_INVALID, "newton_restarts out of range");
   if (p->newton_iters < 1) return fail(c, SPPM_ERR_INVALID, "newton_iters must be >= 1");
   if (!(p->init_r2 > 0)) return fail(c, SPPM_ERR_INVALID, "init_r2 must be > 0");
+  if (p->tex_lod < 0 || p->tex_lod >= TEX_MAX_LEVELS) return fail(c, SPPM_ERR_INVALID, "tex_lod out of range");
   c->prm = *p;
+  c->scene.tex_lod = p->tex_lod;
   return SPPM_OK;
 }
 
@@ -375,19 +377,29 @@ int sppm_scene_upload(sppm_ctx* c, const SppmSceneDesc* s) {
     tex[t].rows = ht.rows;
     tex[t].cols = ht.cols;
     tex[t].bgr = dev;
-    // one 32-bit word per texel for the tracers (scene.cuh tex_fetch), expanded on the device
+    // one 32-bit word per texel in 8 x 4 tiles for the tracers (scene.cuh tex_fetch) + the mip chain below it,
+    // expanded and filtered on the device
     const size_t slot = 8 + (size_t)s->n_textures + (size_t)t, ntexel = (size_t)ht.rows * ht.cols;
     if (c->scene_bufs.size() <= slot) c->scene_bufs.resize(slot + 1);
-    CU(c, dev_reserve(c->scene_bufs[slot], ntexel * 4));
-    tex_expand_kernel<<<(unsigned)((ntexel + 255) / 256), 256, 0, c->stream>>>(dev, ntexel, (uint32_t*)c->scene_bufs[slot].p);
+    const size_t words = tex_layout_levels(ht.rows, ht.cols, nullptr, tex[t]);
+    CU(c, dev_reserve(c->scene_bufs[slot], words * 4));
+    tex_layout_levels(ht.rows, ht.cols, (const uint32_t*)c->scene_bufs[slot].p, tex[t]);
+    tex[t].bgr = dev;
+    tex_expand_kernel<<<(unsigned)((ntexel + 255) / 256), 256, 0, c->stream>>>(dev, ht.rows, ht.cols, tex[t].level[0].tiles_x,
+                                                                              (uint32_t*)c->scene_bufs[slot].p);
     c->host_counters.launches++;
-    tex[t].bgrx = (const uint32_t*)c->scene_bufs[slot].p;
+    for (int l = 1; l < tex[t].n_levels; l++) {
+      const size_t nl = (size_t)tex[t].level[l].rows * tex[t].level[l].cols;
+      tex_mip_kernel<<<(unsigned)((nl + 255) / 256), 256, 0, c->stream>>>(tex[t].level[l - 1], tex[t].level[l]);
+      c->host_counters.launches++;
+    }
   }
   DevScene ds;
   ds.n_obj = s->n_objects;
   ds.n_patch = s->n_patches;
   ds.n_light = s->n_lights;
   ds.n_tex = s->n_textures;
+  ds.tex_lod = c->prm.tex_lod;
   CU(c, upload(c, 0, objs.data(), objs.size(), &ds.obj));
   CU(c, upload(c, 1, patchP.data(), patchP.size(), &ds.patchP));
   CU(c, upload(c, 2, patchBox.data(), patchBox.size(), &ds.patchBox));

@@ -31,11 +31,25 @@ struct DevObject {
   double texUmod, texVmod;           // Obj.h:97-98 Module()
   double box[6];                     // Bezier3Obj::aabb
 };
+// Texels are stored one 32-bit word each (B | G << 8 | R << 16) in 8 x 4 tiles (one 128-byte line per tile:
+// block-linear), so the 2 x 2 footprint of a bilinear lookup (Element.h:61-72) falls into one line two times
+// out of three instead of always two lines 4*cols bytes apart; below level 0 a chain of 2 x 2 box-filtered
+// levels (SppmParams.tex_lod > 0: an opt-in approximation; level 0 is the reference's image, bit for bit).
+constexpr int TEX_MAX_LEVELS = 8;
+struct TexLevel {
+  const uint32_t* texel;
+  int rows, cols, tiles_x, pad;
+};
 struct DevTexture {
   int rows, cols;
-  const uint8_t* bgr;
-  const uint32_t* bgrx;  // the same texels, one 32-bit word each (B | G << 8 | R << 16): one load per texel
+  const uint8_t* bgr;   // the uploaded BGR8 image (row-major; JPEG encode / export paths)
+  int n_levels, pad;
+  TexLevel level[TEX_MAX_LEVELS];
 };
+__host__ __device__ inline size_t tex_tiled_index(int r, int c, int tiles_x) {
+  return ((size_t)(r >> 2) * tiles_x + (c >> 3)) * 32 + (size_t)((r & 3) * 8 + (c & 7));
+}
+__host__ __device__ inline size_t tex_tiled_words(int rows, int cols) { return (size_t)((rows + 3) >> 2) * ((cols + 7) >> 3) * 32; }
 struct DevScene {
   int n_obj, n_patch, n_light, n_tex;
   const DevObject* obj;     // [n_obj]
@@ -47,6 +61,7 @@ struct DevScene {
   unsigned long long* culled;  // counter: Newton solves proven empty by the 13-DOP line test
   const SppmLight* lights;  // [n_light]
   const DevTexture* tex;    // [n_tex]
+  int tex_lod;              // SppmParams.tex_lod: mip level the tracers sample (0 = the reference's image)
 };
 struct NewtonCfg {
   int restarts, iters, mode;
@@ -75,6 +90,7 @@ struct SceneView {
   const DevTexture* tex;
   const double* lut255;  // lut255[b] = b / 255.0 (Element.h:54-57), exact quotients
   int n_obj;
+  int tex_lod;
 };
 
 // with_A: also stage the monomial coefficients (only kernels that run the FAST Newton need them)
@@ -121,6 +137,7 @@ __device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, 
   v.patchSub = s.patchSub;
   v.culled = s.culled;
   v.tex = s.tex;
+  v.tex_lod = s.tex_lod;
   v.n_obj = s.n_obj;
   __syncthreads();
   return v;
@@ -135,8 +152,9 @@ struct TexFetch {
   uint32_t p11, p12, p21, p22;
   double detR, detC;
 };
-__device__ __forceinline__ TexFetch tex_fetch(const DevTexture& t, double u, double v) {
-  const int rows = t.rows, cols = t.cols;
+__device__ __forceinline__ TexFetch tex_fetch(const DevTexture& t, double u, double v, int lod = 0) {
+  const TexLevel& L = t.level[lod < t.n_levels ? (lod > 0 ? lod : 0) : t.n_levels - 1];
+  const int rows = L.rows, cols = L.cols;
   double row = (u - floor(u)) * rows, col = (v - floor(v)) * cols;
   int r1 = (int)floor(row + 1e-10), r2 = r1 + 1;
   int c1 = (int)floor(col + 1e-10), c2 = c1 + 1;
@@ -147,10 +165,10 @@ __device__ __forceinline__ TexFetch tex_fetch(const DevTexture& t, double u, dou
   c1 = (c1 >= 0) ? (c1 >= cols ? 0 : c1) : (cols - 1);
   r2 = (r2 < rows) ? r2 : 0;
   c2 = (c2 < cols) ? c2 : 0;
-  f.p11 = __ldg(t.bgrx + (size_t)r1 * cols + c1);
-  f.p12 = __ldg(t.bgrx + (size_t)r1 * cols + c2);
-  f.p21 = __ldg(t.bgrx + (size_t)r2 * cols + c1);
-  f.p22 = __ldg(t.bgrx + (size_t)r2 * cols + c2);
+  f.p11 = __ldg(L.texel + tex_tiled_index(r1, c1, L.tiles_x));
+  f.p12 = __ldg(L.texel + tex_tiled_index(r1, c2, L.tiles_x));
+  f.p21 = __ldg(L.texel + tex_tiled_index(r2, c1, L.tiles_x));
+  f.p22 = __ldg(L.texel + tex_tiled_index(r2, c2, L.tiles_x));
   return f;
 }
 __device__ __forceinline__ d3 tex_finish(const TexFetch& f, const double* __restrict__ lut255) {
@@ -164,8 +182,8 @@ __device__ __forceinline__ d3 tex_finish(const TexFetch& f, const double* __rest
   }
   return d3{o[0], o[1], o[2]};
 }
-__device__ inline d3 color_uv(const DevTexture& t, const double* __restrict__ lut255, double u, double v) {
-  return tex_finish(tex_fetch(t, u, v), lut255);
+__device__ inline d3 color_uv(const DevTexture& t, const double* __restrict__ lut255, double u, double v, int lod = 0) {
+  return tex_finish(tex_fetch(t, u, v, lod), lut255);
 }
 
 // ---- Bezier.h:20-51 AABBbox::intersect (entry faces only, Q5) ---------------------------
@@ -693,7 +711,7 @@ __device__ inline Surface shade_hit(const SceneView& sv, const Hit& h, d3 org, d
       const double P[3] = {s.pos.x, s.pos.y, s.pos.z};
       const double v = 0.5 + (P[ob.vdex] - ob.p0[ob.vdex]) / ob.texUmod;
       const double u = 0.5 + (P[ob.udex] - ob.p0[ob.udex]) / ob.texVmod;
-      s.color = color_uv(sv.tex[ob.tex_id], sv.lut255, u, v);
+      s.color = color_uv(sv.tex[ob.tex_id], sv.lut255, u, v, sv.tex_lod);
     }
   } else if (ob.kind == SPPM_OBJ_SPHERE) {
     const d3 N = get_unit(s.pos - ld3(ob.p0));
@@ -709,14 +727,14 @@ __device__ inline Surface shade_hit(const SceneView& sv, const Hit& h, d3 org, d
       const double u = theta / SPPM_PI;
       double v = phi / (2 * SPPM_PI);
       v = (dot3(N, ld3(ob.texW)) < 0) ? (1 - v) : v;
-      s.color = color_uv(sv.tex[ob.tex_id], sv.lut255, u, v);
+      s.color = color_uv(sv.tex[ob.tex_id], sv.lut255, u, v, sv.tex_lod);
     }
   } else {
     const PatchEval e = eval_exact(sv.patchP + (size_t)h.patch * 48, h.u, h.v);
     d3 N = cross3(e.Su, e.Sv);
     if (dot3(N, dir) > 0) N = -N;
     s.n = normalize3(N);
-    s.color = (ob.tex_id < 0) ? ld3(ob.color) : color_uv(sv.tex[ob.tex_id], sv.lut255, h.u, h.dist);  // Q6
+    s.color = (ob.tex_id < 0) ? ld3(ob.color) : color_uv(sv.tex[ob.tex_id], sv.lut255, h.u, h.dist, sv.tex_lod);  // Q6
   }
   return s;
 }

@@ -234,7 +234,7 @@ class DeviceHost:
         L.dh_aabb_intersect.argtypes = [VP, I64, VP, VP]
         L.dh_bezier_eval.argtypes = [C.c_int, VP, I64, VP, VP]
         L.dh_newton.argtypes = [C.c_int, VP, I64, VP, VP, C.c_int, C.c_int, VP]
-        L.dh_color_uv.argtypes = [C.c_int, C.c_int, VP, I64, VP, VP]
+        L.dh_color_uv.argtypes = [C.c_int, C.c_int, VP, I64, VP, VP, C.c_int]
         L.dh_unit_rand_refl.argtypes = [I64, VP, VP, C.c_int, VP]
         L.dh_refracted.argtypes = [I64, VP, VP, VP, VP]
         L.dh_scene_create.argtypes = [C.POINTER(abi.SppmSceneDesc), C.c_char_p, C.c_int]
@@ -260,7 +260,7 @@ class DeviceHost:
         L.dh_work_read.argtypes = [VP, C.c_int]
         L.dh_bounds.argtypes = [I64, VP, C.c_int, VP]
         L.dh_tonemap.argtypes = [VP, C.c_int, C.c_int, DBL, VP]
-        L.dh_tex_expand.argtypes = [VP, I64, VP]
+        L.dh_tex_expand.argtypes = [VP, C.c_int, C.c_int, VP, VP]
         L.dh_shared_pass.argtypes = [I64, C.c_int, DBL, DBL, DBL, VP, VP, VP, I64, VP, VP, VP, VP, VP, VP]
         L.dh_update_resolve.argtypes = [I64, C.c_int, DBL, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, VP]
         L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
@@ -294,11 +294,11 @@ class DeviceHost:
         self.lib.dh_newton(mode, _p(P48), n, _p(rays6), _p(seeds), seeds.shape[1], iters, _p(out))
         return out
 
-    def color_uv(self, tex_map, uv):
+    def color_uv(self, tex_map, uv, lod=0):
         tex_map = np.ascontiguousarray(tex_map, dtype=np.uint8)
         uv = _f64(uv, (-1, 2))
         out = np.empty((uv.shape[0], 3))
-        self.lib.dh_color_uv(tex_map.shape[0], tex_map.shape[1], _p(tex_map), uv.shape[0], _p(uv), _p(out))
+        self.lib.dh_color_uv(tex_map.shape[0], tex_map.shape[1], _p(tex_map), uv.shape[0], _p(uv), _p(out), lod)
         return out
 
     def unit_rand_refl(self, norm3, u12, fast=False):
@@ -383,10 +383,19 @@ class DeviceHost:
         return out
 
     def tex_expand(self, bgr8):
+        """tex_expand_kernel + tex_mip_kernel as sppm_scene_upload runs them -> the levels of the chain, untiled:
+        a list of uint32 arrays [rows_l, cols_l] (B | G << 8 | R << 16 per texel)."""
         bgr8 = np.ascontiguousarray(bgr8, dtype=np.uint8)
-        out = np.zeros(bgr8.shape[:2], dtype=np.uint32)
-        self.lib.dh_tex_expand(_p(bgr8), out.size, _p(out))
-        return out
+        rows, cols = bgr8.shape[:2]
+        out = np.zeros(2 * rows * cols + 64, dtype=np.uint32)
+        dims = np.zeros((8, 2), dtype=np.int32)
+        n = self.lib.dh_tex_expand(_p(bgr8), rows, cols, _p(out), _p(dims))
+        levels, o = [], 0
+        for l in range(n):
+            r, c = int(dims[l, 0]), int(dims[l, 1])
+            levels.append(out[o:o + r * c].reshape(r, c).copy())
+            o += r * c
+        return levels
 
     def bounds(self, pos, blocks=7):
         raw = np.zeros(pos.shape[0], dtype=hpraw_dtype)

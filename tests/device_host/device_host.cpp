@@ -54,13 +54,6 @@ struct DhScene {
   DevScene dev;  // what sppm_scene_upload hands the kernels (pointers into this object)
 };
 
-// the expansion tex_expand_kernel (abi.cu) does on the device
-std::vector<uint32_t> expand_texels(const uint8_t* bgr, size_t n) {
-  std::vector<uint32_t> out(n);
-  for (size_t i = 0; i < n; i++) out[i] = (uint32_t)bgr[3 * i] | ((uint32_t)bgr[3 * i + 1] << 8) | ((uint32_t)bgr[3 * i + 2] << 16);
-  return out;
-}
-
 NewtonCfg make_cfg(int mode, int restarts, int iters, int cull, uint64_t seed) {
   NewtonCfg c;
   c.restarts = restarts;
@@ -220,14 +213,26 @@ void dh_newton(int mode, const double* P48, int64_t n, const double* rays6, cons
     tuv[3 * i] = bt; tuv[3 * i + 1] = bu; tuv[3 * i + 2] = bv;
   }
 }
-void dh_color_uv(int rows, int cols, const uint8_t* bgr8, int64_t n, const double* uv, double* out3) {
-  const std::vector<uint32_t> words = expand_texels(bgr8, (size_t)rows * cols);
+// the tiled expansion + mip chain sppm_scene_upload builds on the device (abi.cu), by the product's kernels
+static std::vector<uint32_t> expand_texels(const uint8_t* bgr, int rows, int cols, DevTexture& t) {
+  std::vector<uint32_t> words(tex_layout_levels(rows, cols, nullptr, t));
+  tex_layout_levels(rows, cols, words.data(), t);
+  t.bgr = bgr;
+  const long long n0 = (long long)rows * cols;
+  launch(tex_expand_kernel, std::make_tuple(bgr, rows, cols, t.level[0].tiles_x, words.data()), (n0 + 255) / 256, 256);
+  for (int l = 1; l < t.n_levels; l++) {
+    const long long nl = (long long)t.level[l].rows * t.level[l].cols;
+    launch(tex_mip_kernel, std::make_tuple(t.level[l - 1], t.level[l]), (nl + 255) / 256, 256);
+  }
+  return words;
+}
+void dh_color_uv(int rows, int cols, const uint8_t* bgr8, int64_t n, const double* uv, double* out3, int lod) {
   DevTexture t;
-  t.rows = rows; t.cols = cols; t.bgr = bgr8; t.bgrx = words.data();
+  const std::vector<uint32_t> words = expand_texels(bgr8, rows, cols, t);
   double lut[256];
   for (int i = 0; i < 256; i++) lut[i] = i / 255.0;
   for (int64_t i = 0; i < n; i++) {
-    const d3 c = color_uv(t, lut, uv[2 * i], uv[2 * i + 1]);
+    const d3 c = color_uv(t, lut, uv[2 * i], uv[2 * i + 1], lod);
     out3[3 * i] = c.x; out3[3 * i + 1] = c.y; out3[3 * i + 2] = c.z;
   }
 }
@@ -259,12 +264,8 @@ void* dh_scene_create(const SppmSceneDesc* s, char* err, int errlen) {
   h->tex.resize((size_t)s->n_textures);
   for (int t = 0; t < s->n_textures; t++) {
     const SppmTexture& ht = s->textures[t];
-    h->bgrx.push_back(expand_texels(ht.bgr8, (size_t)ht.rows * ht.cols));
-    h->tex[t].rows = ht.rows;
-    h->tex[t].cols = ht.cols;
-    h->tex[t].bgr = ht.bgr8;  // borrowed; the tracers read bgrx only
+    h->bgrx.push_back(expand_texels(ht.bgr8, ht.rows, ht.cols, h->tex[t]));  // level pointers go into the vector's heap block: stable
   }
-  for (int t = 0; t < s->n_textures; t++) h->tex[t].bgrx = h->bgrx[t].data();
   for (int i = 0; i < 256; i++) h->lut255[i] = i / 255.0;  // stage_scene
   SceneView& v = h->sv;
   v.obj = h->ps.objs.data();
@@ -685,8 +686,18 @@ void dh_tonemap(const double* film, int w, int h, double div, uint8_t* bgr) {
   const long long n = (long long)w * h * 3;
   launch(tonemap_kernel, std::make_tuple(film, w, h, div, bgr), (n + 255) / 256, 256);
 }
-void dh_tex_expand(const uint8_t* bgr, int64_t n, uint32_t* out) {
-  launch(tex_expand_kernel, std::make_tuple(bgr, (size_t)n, out), (n + 255) / 256, 256);
+// all levels of the chain, untiled: out = level 0 [rows*cols] | level 1 | ...; returns the number of levels
+int dh_tex_expand(const uint8_t* bgr, int rows, int cols, uint32_t* out, int32_t* dims /* [8][2] */) {
+  DevTexture t;
+  const std::vector<uint32_t> words = expand_texels(bgr, rows, cols, t);
+  size_t o = 0;
+  for (int l = 0; l < t.n_levels; l++) {
+    const TexLevel& L = t.level[l];
+    dims[2 * l] = L.rows; dims[2 * l + 1] = L.cols;
+    for (int r = 0; r < L.rows; r++)
+      for (int c = 0; c < L.cols; c++) out[o++] = L.texel[tex_tiled_index(r, c, L.tiles_x)];
+  }
+  return t.n_levels;
 }
 // bounds_kernel (build_index step 1): out9 = min[3], max[3], sum[3] of the hit-point positions
 void dh_bounds(int64_t n, const HpRaw* raw, int blocks, double* out9) {

@@ -949,7 +949,34 @@ def test_tonemap_and_texel_expansion_kernels(dh, oracle):
         np.testing.assert_array_equal(dh.tonemap(film, div), oracle.tonemap(film, div))
     tex = synthetic_texture(19, 45, 3)
     want = tex[..., 0].astype(np.uint32) | (tex[..., 1].astype(np.uint32) << 8) | (tex[..., 2].astype(np.uint32) << 16)
-    np.testing.assert_array_equal(dh.tex_expand(tex), want)
+    levels = dh.tex_expand(tex)
+    np.testing.assert_array_equal(levels[0], want)      # level 0 (8 x 4 tiles on the device) == the uploaded image
+
+
+def test_texture_mip_chain_and_level_sampling(dh, oracle):
+    """SURVEY 8f-4 (texture tiling / mip): level l+1 = the rounded 2 x 2 box mean of level l (an odd edge repeats),
+    down to 1 x 1; color_uv at lod 0 is Texture::colorUV of the reference bit for bit (tiled storage is
+    invisible), at lod l it is the same wrap-around bilinear rule on level l."""
+    rng = np.random.RandomState(52)
+    tex = rng.randint(0, 256, size=(37, 70, 3)).astype(np.uint8)
+    levels = dh.tex_expand(tex)
+    cur = tex.astype(np.int64)
+    assert len(levels) == 7 and levels[-1].shape == (1, 1)
+    for l, got in enumerate(levels):
+        packed = cur[..., 0] | (cur[..., 1] << 8) | (cur[..., 2] << 16)
+        np.testing.assert_array_equal(got, packed.astype(np.uint32), err_msg=f"level {l}")
+        r, c = cur.shape[:2]
+        nr, nc = max(1, r >> 1), max(1, c >> 1)
+        ri = np.minimum(np.arange(nr)[:, None] * 2 + np.array([0, 1]), r - 1)      # [nr, 2]
+        ci = np.minimum(np.arange(nc)[:, None] * 2 + np.array([0, 1]), c - 1)
+        blk = cur[ri[:, None, :, None], ci[None, :, None, :]]                        # [nr, nc, 2, 2, 3]
+        cur = (blk.sum(axis=(2, 3)) + 2) >> 2
+    uv = rng.uniform(-2, 3, size=(4000, 2))
+    want0 = np.array([oracle.color_uv(tex, u, v) for u, v in uv])
+    np.testing.assert_array_equal(dh.color_uv(tex, uv, lod=0), want0)
+    lvl2 = np.stack([(levels[2] >> (8 * k)) & 255 for k in range(3)], axis=-1).astype(np.uint8)
+    want2 = np.array([oracle.color_uv(lvl2, u, v) for u, v in uv[:1500]])
+    np.testing.assert_array_equal(dh.color_uv(tex, uv[:1500], lod=2), want2)
 
 
 def test_one_warp_blocks_give_the_same_results(dh, oracle):

@@ -241,3 +241,30 @@ def test_wavefront_item_list_spill(ctx, monkeypatch, scene_name, item_cap):
     if item_cap:
         assert c0["spilled_photons"] > 0
     assert c1["spilled_photons"] == 0
+
+
+def test_texture_levels_on_device(ctx, oracle):
+    """textures are stored in 8 x 4 tiles with a 2 x 2 box-filtered mip chain below them.  tex_lod = 0
+    (default) is Texture::colorUV on the uploaded image, bit for bit (the textured NearCollide / eye-pass parity tests
+    run on it); tex_lod = 2 samples the second level: the same hit points, colours close to the full-resolution ones
+    and equal to the oracle's sampler on the box-filtered image."""
+    sc = make_scene("reference", textures="synthetic")
+    cam = reference_camera(160, 120)
+    out = []
+    for lod in (0, 2):
+        prm = bench_params()
+        prm.tex_lod = lod
+        ctx.set_params(prm)
+        ctx.upload_scene(sc)
+        n = ctx.eye_pass(cam, 0)
+        out.append(ctx.export_hitpoints())
+    ctx.set_params(bench_params())
+    a, b = out
+    np.testing.assert_array_equal(a["pos"], b["pos"])          # geometry does not depend on the level
+    np.testing.assert_array_equal(a["pix"], b["pix"])
+    textured = np.abs(a["wgt"] - b["wgt"]).max(1) > 0
+    assert 0.2 < textured.mean() < 1.0                          # the textured walls / spheres changed, the rest did not
+    assert np.abs(a["wgt"] - b["wgt"]).max() < 0.5 and np.abs(a["wgt"] - b["wgt"]).mean() < 0.05
+    ref = oracle.eye_pass(sc, exact_params(), cam, pass_id=0)
+    order = np.lexsort((ref["node"], ref["pix"][:, 0] * cam.w + ref["pix"][:, 1]))
+    np.testing.assert_allclose(a["wgt"], ref["wgt"][order], rtol=1e-9, atol=0)   # level 0 == the reference's sampler
