@@ -213,11 +213,20 @@ int sppm_build_index(sppm_ctx* ctx);
  * no-op (N = 0, Raytracer.h:70) several rounds may be one call: round i = ids
  * [i*onetime, (i+1)*onetime) -- what the host mirrors' PhotonMap does. */
 int sppm_photon_pass(sppm_ctx* ctx, uint64_t photon_begin, uint64_t photon_count, uint64_t pass_id);
-/* Sum the per-round accumulators over the ranks of the communicator (no-op without one). */
+/* Sum the per-round accumulators over the ranks of the communicator (no-op without one).
+ * With update_mode = SPPM_UPDATE_REFERENCE this call and the sppm_update that follows it are
+ * issued on a communication stream and overlap the next sppm_photon_pass (the reference's update
+ * never moves a radius on a fresh eye pass, Raytracer.h:70); every call that reads hit-point state
+ * is ordered behind them.  SPPM_ASYNC_COMM=0 in the environment keeps them in line. */
 int sppm_allreduce(sppm_ctx* ctx);
 /* newN += dN, tao += dtao, then HitPoint::update (Raytracer.h:69-79, 238-245). */
 int sppm_update(sppm_ctx* ctx);
-/* Film resolve (Raytracer.h:281-293): film[h][w][3] = sum tao/(PI*R2*cnt*onetime). */
+/* Film resolve (Raytracer.h:281-293): film[h][w][3] = sum tao/(PI*R2*cnt*onetime).
+ * A pixel with several hit points (branching eye paths, Raytracer.h:312-335) sums them with FP64
+ * atomics, i.e. in arrival order, not in Hvec order: such pixels are reproducible to rounding
+ * (<= 1e-15 relative), not bit for bit, from run to run.  Pixels with one hit point - every pixel
+ * of the shipped scene - are exact.  The same holds for tao itself: a round's deposits are summed
+ * in the order the binning placed them (newN is an integer and exact). */
 int sppm_resolve(sppm_ctx* ctx, int32_t cnt, int32_t onetime, double* film_hw3);
 /* film_acc += film (Raytracer.h:449-458) and tone map (Raytracer.h:24-26, 460-470):
  * bgr[h-1-i][j][k] = toInt(film[i][j][k] / div).  All host buffers. */
