@@ -214,10 +214,11 @@ int sppm_build_index(sppm_ctx* ctx);
  * [i*onetime, (i+1)*onetime) -- what the host mirrors' PhotonMap does. */
 int sppm_photon_pass(sppm_ctx* ctx, uint64_t photon_begin, uint64_t photon_count, uint64_t pass_id);
 /* Sum the per-round accumulators over the ranks of the communicator (no-op without one).
- * With update_mode = SPPM_UPDATE_REFERENCE this call and the sppm_update that follows it are
- * issued on a communication stream and overlap the next sppm_photon_pass (the reference's update
- * never moves a radius on a fresh eye pass, Raytracer.h:70); every call that reads hit-point state
- * is ordered behind them.  SPPM_ASYNC_COMM=0 in the environment keeps them in line. */
+ * Issued on the context's main stream, behind the round's gathers; the photon tracing of the next
+ * rounds (lane streams) runs beside it.  SPPM_ASYNC_COMM=1 in the environment (REFERENCE update only)
+ * moves this call and the sppm_update that follows it to a communication stream over a second set
+ * of accumulators, so that the next round's GATHER overlaps them too; every call that reads
+ * hit-point state is then ordered behind them. */
 int sppm_allreduce(sppm_ctx* ctx);
 /* newN += dN, tao += dtao, then HitPoint::update (Raytracer.h:69-79, 238-245). */
 int sppm_update(sppm_ctx* ctx);

@@ -202,7 +202,7 @@ struct sppm_ctx {
   // NCCL (dlopen)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
-  // Exchange overlapped with the next round (REFERENCE update only: HitPoint::update then never changes a radius,
+  // Optional (SPPM_ASYNC_COMM=1): exchange overlapped with the next round's gather (REFERENCE update only: HitPoint::update then never changes a radius,
   // Raytracer.h:70, so the next round's gather does not depend on it).  The per-round accumulators dN / dtao
   // exist twice: while the allreduce + update of round i run on comm_stream over one set, the gather of round
   // i+1 fills the other on the main stream.
@@ -211,7 +211,7 @@ struct sppm_ctx {
   int32_t* dN_set[2] = {nullptr, nullptr};
   double* dtao_set[2] = {nullptr, nullptr};
   int acc_cur = 0;
-  bool async_comm = true;     // SPPM_ASYNC_COMM=0 keeps the exchange on the main stream
+  bool async_comm = false;    // SPPM_ASYNC_COMM=1 moves the exchange to comm_stream (measured: no gain)
   bool comm_pending = false;  // an allreduce was issued on comm_stream and its update has not been yet
   bool comm_busy = false;     // comm_stream holds work the main stream has not been ordered after
 };

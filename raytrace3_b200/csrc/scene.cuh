@@ -470,9 +470,11 @@ __device__ __forceinline__ bool newton_restart(const double* __restrict__ P, d3 
 // Process the warp's queued (ray, patch) items: n_items * restarts Newton tasks spread over
 // the 32 lanes, per-item min-t written to ws->it_{t,u,v}.  seeds_uv (nullable) = injected
 // seeds double[pair][restarts][2], pair = seed_pair_base + item.
+// r_begin / r_count: only restarts [r_begin, r_begin + r_count) of every item (r_count < 0: all of them) — two
+// warps may share an item's restarts when there are few items (newton_items_kernel); the caller merges.
 __device__ inline void flush_items(const SceneView& sv, WarpScratch* ws, int n_items, const NewtonCfg& cfg,
                                    uint64_t pass, uint32_t domain, const double* seeds_uv, long long seed_pair_base,
-                                   int lane) {
+                                   int lane, int r_begin = 0, int r_count = -1) {
   for (int i = lane; i < n_items; i += 32) {
     ws->it_t[i] = SPPM_MAX_NUM;
     ws->it_u[i] = SPPM_MAX_NUM;
@@ -496,9 +498,9 @@ __device__ inline void flush_items(const SceneView& sv, WarpScratch* ws, int n_i
     if (live) ws->live[n_live + __popc(m & ((1u << lane) - 1))] = (unsigned char)i;
     n_live += __popc(m);
   }
-  if (lane == 0 && n_live < n_items) atomicAdd(sv.culled, (unsigned long long)(n_items - n_live));
+  if (lane == 0 && n_live < n_items && r_begin == 0) atomicAdd(sv.culled, (unsigned long long)(n_items - n_live));
   __syncwarp();
-  const int R = cfg.restarts;
+  const int R = r_count < 0 ? cfg.restarts : r_count;  // restarts of an item this call runs
   const int total = n_live * R;
   for (int base = 0; base < total; base += 32) {
     const int k = base + lane;
@@ -508,14 +510,14 @@ __device__ inline void flush_items(const SceneView& sv, WarpScratch* ws, int n_i
     double t = 0, u = 0, v = 0;
     bool found = false;
     if (valid) {
-      const int r = k - live_idx * R;
+      const int r = r_begin + (k - live_idx * R);
       const unsigned it = ws->item[item];
       const int owner = it & 31, gp = it >> 8;
       const d3 org = d3{ws->ray[0][owner], ws->ray[1][owner], ws->ray[2][owner]};
       const d3 dir = d3{ws->ray[3][owner], ws->ray[4][owner], ws->ray[5][owner]};
       double u0, v0;
       if (seeds_uv) {
-        const double* s = seeds_uv + ((size_t)(seed_pair_base + item) * R + r) * 2;
+        const double* s = seeds_uv + ((size_t)(seed_pair_base + item) * cfg.restarts + r) * 2;
         u0 = s[0];
         v0 = s[1];
       } else {
