@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(ROOT, "csrc")
-LIBDIR = os.path.join(ROOT, "lib")
+LIBDIR = os.environ.get("SPPM_BUILD_DIR") or os.path.join(ROOT, "lib")  # SPPM_BUILD_DIR + SPPM_NVCC_EXTRA: an A/B variant beside the product build
 LIB = os.path.join(LIBDIR, "libsppm_b200.so")
 SOURCES = ["abi.cu", "trace.cu", "wavefront.cu", "gather.cu", "imageio.cu"]
 HEADERS = ["ctx.h", "scene.cuh", "scene_prep.h", "trace_kernels.cuh", "wavefront_kernels.cuh", "gather_kernels.cuh", "image_kernels.cuh", "device_math.cuh", os.path.join("..", "..", "include", "sppm_b200.h")]

@@ -100,14 +100,29 @@ __host__ __device__ inline size_t scene_smem_bytes(int n_obj, int n_patch, bool 
   return (b + 15) & ~(size_t)15;
 }
 
+// Global -> shared copy of n doubles by the whole block, eight loads in flight per thread (the plain loop
+// `dst[i] = src[i]` compiles to LDG -> STS -> branch: one exposed L2 latency per element and thread, 31 of them
+// for the scene with the monomial coefficients).  Measured on the B200 against the plain loop: within noise
+// (782 vs 779-783 M photons/s, Newton launches 0.78 vs 0.78-0.79 ms) — the staging is not what a tail-bounce
+// launch waits for; kept because it is never slower.
+__device__ __forceinline__ void stage_copy(double* __restrict__ dst, const double* __restrict__ src, int n) {
+  const int bd = (int)blockDim.x;
+  for (int i = (int)threadIdx.x; i < n; i += 8 * bd) {
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (i + k * bd < n) ? src[i + k * bd] : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (i + k * bd < n) dst[i + k * bd] = v[k];
+  }
+}
+
 // Copy objects (and patches if they fit) into dynamic shared memory; all threads call.
 __device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, bool patches_in_smem, bool with_A = true) {
   SceneView v;
   {
     const int n = s.n_obj * (int)(sizeof(DevObject) / 8);
-    double* dst = reinterpret_cast<double*>(smem);
-    const double* src = reinterpret_cast<const double*>(s.obj);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    stage_copy(reinterpret_cast<double*>(smem), reinterpret_cast<const double*>(s.obj), n);
     v.obj = reinterpret_cast<const DevObject*>(smem);
   }
   {
@@ -118,14 +133,14 @@ __device__ inline SceneView stage_scene(const DevScene& s, unsigned char* smem, 
   if (patches_in_smem) {
     double* dp = reinterpret_cast<double*>(smem + (size_t)s.n_obj * sizeof(DevObject)) + 256;
     double* db = dp + (size_t)s.n_patch * 48;
-    for (int i = threadIdx.x; i < s.n_patch * 48; i += blockDim.x) dp[i] = s.patchP[i];
-    for (int i = threadIdx.x; i < s.n_patch * 6; i += blockDim.x) db[i] = s.patchBox[i];
+    stage_copy(dp, s.patchP, s.n_patch * 48);
+    stage_copy(db, s.patchBox, s.n_patch * 6);
     v.patchP = dp;
     v.patchBox = db;
     v.patchA = s.patchA;
     if (with_A) {
       double* da = db + (size_t)s.n_patch * 6;
-      for (int i = threadIdx.x; i < s.n_patch * 48; i += blockDim.x) da[i] = s.patchA[i];
+      stage_copy(da, s.patchA, s.n_patch * 48);
       v.patchA = da;
     }
   } else {
@@ -470,11 +485,9 @@ __device__ __forceinline__ bool newton_restart(const double* __restrict__ P, d3 
 // Process the warp's queued (ray, patch) items: n_items * restarts Newton tasks spread over
 // the 32 lanes, per-item min-t written to ws->it_{t,u,v}.  seeds_uv (nullable) = injected
 // seeds double[pair][restarts][2], pair = seed_pair_base + item.
-// r_begin / r_count: only restarts [r_begin, r_begin + r_count) of every item (r_count < 0: all of them) — two
-// warps may share an item's restarts when there are few items (newton_items_kernel); the caller merges.
 __device__ inline void flush_items(const SceneView& sv, WarpScratch* ws, int n_items, const NewtonCfg& cfg,
                                    uint64_t pass, uint32_t domain, const double* seeds_uv, long long seed_pair_base,
-                                   int lane, int r_begin = 0, int r_count = -1) {
+                                   int lane) {
   for (int i = lane; i < n_items; i += 32) {
     ws->it_t[i] = SPPM_MAX_NUM;
     ws->it_u[i] = SPPM_MAX_NUM;
@@ -498,9 +511,9 @@ __device__ inline void flush_items(const SceneView& sv, WarpScratch* ws, int n_i
     if (live) ws->live[n_live + __popc(m & ((1u << lane) - 1))] = (unsigned char)i;
     n_live += __popc(m);
   }
-  if (lane == 0 && n_live < n_items && r_begin == 0) atomicAdd(sv.culled, (unsigned long long)(n_items - n_live));
+  if (lane == 0 && n_live < n_items) atomicAdd(sv.culled, (unsigned long long)(n_items - n_live));
   __syncwarp();
-  const int R = r_count < 0 ? cfg.restarts : r_count;  // restarts of an item this call runs
+  const int R = cfg.restarts;
   const int total = n_live * R;
   for (int base = 0; base < total; base += 32) {
     const int k = base + lane;
@@ -510,14 +523,14 @@ __device__ inline void flush_items(const SceneView& sv, WarpScratch* ws, int n_i
     double t = 0, u = 0, v = 0;
     bool found = false;
     if (valid) {
-      const int r = r_begin + (k - live_idx * R);
+      const int r = k - live_idx * R;
       const unsigned it = ws->item[item];
       const int owner = it & 31, gp = it >> 8;
       const d3 org = d3{ws->ray[0][owner], ws->ray[1][owner], ws->ray[2][owner]};
       const d3 dir = d3{ws->ray[3][owner], ws->ray[4][owner], ws->ray[5][owner]};
       double u0, v0;
       if (seeds_uv) {
-        const double* s = seeds_uv + ((size_t)(seed_pair_base + item) * cfg.restarts + r) * 2;
+        const double* s = seeds_uv + ((size_t)(seed_pair_base + item) * R + r) * 2;
         u0 = s[0];
         v0 = s[1];
       } else {

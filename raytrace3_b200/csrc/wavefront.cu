@@ -77,8 +77,6 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
   w.tail_bounce = -1;
   if (const char* e = getenv("SPPM_WF_TAIL")) w.tail_bounce = atoi(e);
   w.newton_dynamic = 1;
-  w.newton_warps = (unsigned)newton_blocks * (TRACE_THREADS / 32);  // SPPM_NEWTON_SPLIT=0: never split
-  if (const char* e = getenv("SPPM_NEWTON_SPLIT")) if (atoi(e) == 0) w.newton_warps = 0;
   if (const char* e = getenv("SPPM_NEWTON_DYNAMIC")) w.newton_dynamic = atoi(e);
   w.q_cap = (unsigned)Ln.wf_cap;
   w.grid = c->grid;

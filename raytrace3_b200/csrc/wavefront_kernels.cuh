@@ -37,7 +37,6 @@ struct Items {
   unsigned* slot;   // photon slot in the queue the items were generated for
   unsigned* patch;  // global patch | object << 16
   double *t, *u, *v;
-  double *t2, *u2, *v2;  // second half of the restarts when a bounce's items were split over two warps each
 };
 
 // Photons that leave the wavefront because the (ray, patch) item list of their bounce is full: the state
@@ -57,8 +56,6 @@ struct StepArgs {
   Queue qin, qout;
   Items it_in, it_out;
   const unsigned* n_in_ptr;  // [4]: photons queued in the four regions (see photon_step_kernel)
-  const unsigned* n_items_in_ptr;  // items the previous step queued (null at bounce 0)
-  unsigned split_max_items;  // a bounce with at most this many items had each item's restarts split over two warps
   unsigned n_in_host;
   unsigned* n_out;           // [4]
   unsigned q_cap;
@@ -147,7 +144,6 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
         const unsigned ic = a.qin.item_cnt[i];
         if (ic) {  // Bezier3Obj::GetIntersect filter, per object in patch order (Bezier.h:246-261)
           const unsigned ib = a.qin.item_begin[i];
-          const bool split = min(*a.n_items_in_ptr, a.item_cap) <= a.split_max_items;
           int cur = -1, index = -1;
           double pt = SPPM_MAX_NUM, pu = SPPM_MAX_NUM, pv = SPPM_MAX_NUM;
           for (unsigned k = 0; k <= ic; k++) {
@@ -162,13 +158,7 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
               pt = pu = pv = SPPM_MAX_NUM;
             }
             if (k < ic) {
-              double qt = a.it_in.t[ib + k], qu = a.it_in.u[ib + k], qv = a.it_in.v[ib + k];
-              if (split) {  // restarts 25.. ran on another warp: they win only with a strictly smaller t (Bezier.h:149-157)
-                const double t2 = a.it_in.t2[ib + k];
-                if (t2 < qt) {
-                  qt = t2; qu = a.it_in.u2[ib + k]; qv = a.it_in.v2[ib + k];
-                }
-              }
+              const double qt = a.it_in.t[ib + k], qu = a.it_in.u[ib + k], qv = a.it_in.v[ib + k];
               if (!(qt < SPPM_M_EPS || qt > pt || qu < -SPPM_M_EPS || qu > 1 + SPPM_M_EPS || qv < -SPPM_M_EPS ||
                     qv > 1 + SPPM_M_EPS)) {
                 if (qt < pt) {
@@ -387,7 +377,6 @@ struct NewtonArgs {
   const unsigned* n_items_ptr;
   unsigned item_cap;
   unsigned* work;  // chunk cursor of this launch (zeroed with the batch's counters)
-  unsigned split_max_items;  // see StepArgs
 };
 
 // Bezier3::newton for the queued (photon slot, patch) items.  Each warp takes chunks of C items and runs the
@@ -408,36 +397,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_i
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
   // static: C items per warp so that all warps of the grid get work (few items: one per warp keeps the serial
   // Newton chain short); dynamic (a.work != null): about four chunks per warp from a global cursor
-  if (n <= a.split_max_items) {
-    // Few items (the tail bounces): a launch would cost the latency of one item's serial chain, 2 rounds of 32
-    // lanes x 10 iterations for its 50 restarts.  Two warps take 25 restarts each (one round); the step kernel
-    // that reads the results keeps the second half's only if its t is strictly smaller, as one pass over all
-    // restarts in order would.
-    const int R = a.ncfg.restarts, R0 = (R + 1) / 2;
-    for (unsigned T = warp_global; T < 2 * n; T += n_warps) {
-      const unsigned k = T >> 1;
-      const int half = (int)(T & 1);
-      if (lane == 0) {
-        const unsigned s = a.it.slot[k];
-        const unsigned pk = a.it.patch[k];
-        ws->ray[0][0] = a.q.ox[s]; ws->ray[1][0] = a.q.oy[s]; ws->ray[2][0] = a.q.oz[s];
-        ws->ray[3][0] = a.q.dx[s]; ws->ray[4][0] = a.q.dy[s]; ws->ray[5][0] = a.q.dz[s];
-        const unsigned long long idd = a.q.idd[s];
-        ws->id[0] = idd & ID_MASK;
-        ws->node[0] = (unsigned)(idd >> 56);
-        ws->item[0] = ((pk & 0xffffu) << 8);
-      }
-      __syncwarp();
-      flush_items(sv, ws, 1, a.ncfg, a.pass, SPPM_DOMAIN_PHOTON, nullptr, 0, lane, half ? R0 : 0, half ? R - R0 : R0);
-      if (lane == 0) {
-        (half ? a.it.t2 : a.it.t)[k] = ws->it_t[0];
-        (half ? a.it.u2 : a.it.u)[k] = ws->it_u[0];
-        (half ? a.it.v2 : a.it.v)[k] = ws->it_v[0];
-      }
-      __syncwarp();
-    }
-    return;
-  }
   // dynamic only where the static chunk would hit its cap of 32 items (4 teapots at 4K: 37 vs 46.5 ms per
   // 64 M photons); with fewer items the static partition is as fast and warps that run out of work early make
   // room for the other lanes' kernels (teapot room: 773-780 vs 755 M photons/s pipelined)
@@ -482,11 +441,10 @@ struct WfLayout {
   Spill spill;         // [cap]
 };
 
-constexpr int WF_SPLIT_CAP = 65536;  // upper bound of split_max_items (the second-half result arrays' size)
 // (ray, patch) items a bounce of `cap` photons may queue before photons spill to the persistent tracer
 inline int64_t wf_item_cap(int64_t cap) { return std::max<int64_t>(cap * 2, 1 << 16); }
 size_t wf_bytes(int64_t cap, int64_t item_cap) {
-  return 2 * (size_t)(2 * cap) * (10 * 8 + 8 + 4 + 4 + 4) + 2 * (size_t)item_cap * (4 + 4 + 24) + 2 * (size_t)65536 * 24 + (size_t)cap * 80 + 128 * 4 + 65536;
+  return 2 * (size_t)(2 * cap) * (10 * 8 + 8 + 4 + 4 + 4) + 2 * (size_t)item_cap * (4 + 4 + 24) + (size_t)cap * 80 + 128 * 4 + 65536;
 }
 WfLayout wf_layout(void* store, int64_t cap, int64_t item_cap) {
   WfLayout L;
@@ -510,9 +468,6 @@ WfLayout wf_layout(void* store, int64_t cap, int64_t item_cap) {
     it.t = (double*)take((size_t)item_cap * 8);
     it.u = (double*)take((size_t)item_cap * 8);
     it.v = (double*)take((size_t)item_cap * 8);
-    it.t2 = (double*)take((size_t)WF_SPLIT_CAP * 8);  // only bounces with few items are split
-    it.u2 = (double*)take((size_t)WF_SPLIT_CAP * 8);
-    it.v2 = (double*)take((size_t)WF_SPLIT_CAP * 8);
   }
   for (int k = 0; k < 9; k++) L.spill.st[k] = (double*)take((size_t)cap * 8);
   L.spill.idd = (unsigned long long*)take((size_t)cap * 8);
@@ -534,7 +489,6 @@ struct WfBatch {
   uint64_t begin, count;  // photon range per light
   int tail_bounce;        // >= 0: from this bounce on Bezier-pending photons spill to the persistent tracer
   int newton_dynamic;     // Newton chunks from a global cursor instead of a static partition
-  unsigned newton_warps;  // warps of a newton_items_kernel launch (0: never split an item's restarts)
   unsigned q_cap;         // entries per queue half (>= n_light * count)
   Grid grid;
   const int32_t* cell_slot;
@@ -565,8 +519,6 @@ inline StepArgs wf_step_args(const WfBatch& w, const WfLayout& L, int b) {
   a.it_in = L.it[b & 1];
   a.it_out = L.it[(b + 1) & 1];
   a.n_in_ptr = L.counters + 4 * b;
-  a.n_items_in_ptr = L.counters + 64 + b;  // what step b - 1 queued (zero at b = 0: nothing pending)
-  a.split_max_items = std::min<unsigned>(w.newton_warps / 2, (unsigned)WF_SPLIT_CAP);
   a.n_in_host = (unsigned)((uint64_t)w.scene.n_light * w.count);
   a.n_out = L.counters + 4 * (b + 1);
   a.q_cap = w.q_cap;
@@ -604,7 +556,6 @@ inline NewtonArgs wf_newton_args(const WfBatch& w, const WfLayout& L, const Step
   n.n_items_ptr = a.n_items_out;
   n.item_cap = L.item_cap;
   n.work = w.newton_dynamic ? L.counters + 100 + a.bounce : nullptr;
-  n.split_max_items = a.split_max_items;
   return n;
 }
 

@@ -463,7 +463,6 @@ int64_t dh_photon_trace_wavefront(void* p, const SppmParams* prm, uint64_t begin
   w.q_cap = (unsigned)total;
   w.tail_bounce = tail_bounce;
   w.newton_dynamic = (tail_bounce & 1) ? 1 : 0;  // both chunking schemes get exercised
-  w.newton_warps = (unsigned)((long long)newton_blocks * bt(TRACE_THREADS) / 32);
   memset(&w.grid, 0, sizeof(w.grid));
   w.cell_slot = nullptr;
   w.n_slots = 0;
