@@ -70,10 +70,11 @@ cudaError_t launch_photon_trace_wavefront(sppm_ctx* c, Lane& Ln, uint64_t begin,
   w.counters = (DevCounters*)c->counters.p;
   w.begin = begin;
   w.count = count;
-  // Tuning knobs, both measured and left off (profiles/r2_D_ab.txt).  SPPM_WF_TAIL = b: from bounce b on the
+  // Measured alternatives (profiles/r2_D_ab.txt, r2_F_ab_configs.txt).  SPPM_WF_TAIL = b: from bounce b on the
   // Bezier-pending photons go to the persistent tracer in one launch instead of one latency-bound Newton launch
   // per bounce — the Newton launches shrink by 0.2 ms per round but the hand-over kernel costs 0.44 ms (a warp of
-  // 32 such photons runs ~100 serial Newton rounds).  SPPM_NEWTON_DYNAMIC = 1: see newton_items_kernel.
+  // 32 such photons runs ~100 serial Newton rounds): off.  SPPM_NEWTON_DYNAMIC: chunks from a global cursor, which
+  // newton_items_kernel uses only for bounces whose static chunk would hit its cap (four teapots): on.
   w.tail_bounce = -1;
   if (const char* e = getenv("SPPM_WF_TAIL")) w.tail_bounce = atoi(e);
   w.newton_dynamic = 1;
