@@ -1014,7 +1014,7 @@ def test_device_kernels_are_clean_under_asan_ubsan():
     -fsanitize=address,undefined (SPPM_DEVICE_HOST_SANITIZE=1) runs a cross-section of this file — every
     kernel of trace / wavefront / gather_kernels.cuh on several scenes — without a single report (global
     and shared-memory bounds, alignment, shifts, signed overflow).  The whole file was run this way for
-    profiles/r1_K_device_host_asan.txt."""
+    profiles/r1_K_device_host_asan.txt and, at the end of round 2, profiles/r2_S_device_host_asan.txt."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -1028,7 +1028,8 @@ def test_device_kernels_are_clean_under_asan_ubsan():
     pick = ("intersect_kernel_golden or patch_batch or eye_pass_kernel_branching or "
             "(wavefront_kernels_against_oracle and stress) or (photon_trace_kernel_golden and quirks) or launch_invariant or "
             "(shapes_fuzz and 0) or out_of_range_normals or (reproduce_the_reference and cornell) or "
-            "(random_scenes and 7) or update_and_resolve")
+            "(random_scenes and 7) or update_and_resolve or (item_list_spills and light_over_teapot) or whole_unit_accept or "
+            "plane_units or texture_mip_chain")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-s", "-x", "-p", "no:cacheprovider",
                         "-k", pick], capture_output=True, text=True, env=env, cwd=root, timeout=1500)
     out = r.stdout + r.stderr
