@@ -45,6 +45,14 @@ def compile_ref(src):
                 assert a in text, (f, a)
                 text = text.replace(a, b)
         open(os.path.join(src, name), "w", encoding="latin-1").write(text)
+    # the reference includes its third-party headers with backslashes (`#include <opencv2\\highgui.hpp>`, MSVC): g++ looks
+    # the name up literally, so three forwarding headers with a backslash IN their file names satisfy them.  They are
+    # written here, into the scratch directory, and not tracked (such names cannot be checked out on Windows).
+    fwd = {"opencv2\\highgui.hpp": '#pragma once\n#include "cv_shim.hpp"\n',
+           "flann\\flann.hpp": '#pragma once\n#include "flann_shim.hpp"\n',
+           "Eigen\\Dense": "// Eigen is included by Bezier.h:3 but never used\n"}
+    for name, text in fwd.items():
+        open(os.path.join(src, name), "w").write(text)
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cmd = [cxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-fopenmp", "-w",
            "-I", os.path.join(HERE, "include"), "-I", src, "-I", os.path.join(HERE, "..", "..", "include"),
