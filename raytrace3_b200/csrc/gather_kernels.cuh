@@ -577,7 +577,10 @@ __device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
 // belongs to exactly one unit.
 // A unit whose ranges hold more than ITEM_DEP deposits is processed by several warps (work items,
 // see unit_parts_kernel); only those units accumulate with atomics.
-constexpr int W_WARPS = 8;
+#ifndef SPPM_W_WARPS
+#define SPPM_W_WARPS 8
+#endif
+constexpr int W_WARPS = SPPM_W_WARPS;
 constexpr int W_THREADS = W_WARPS * 32;
 #ifndef SPPM_W_SLICE
 #define SPPM_W_SLICE 32
@@ -687,6 +690,10 @@ __device__ __noinline__ void careful_pairs(const HpSoA s, const int i, const dou
 // {ny0,ny1,nz0,nz1} in FP32 and the two fluxes {fx0,fy0} {fz0,fx1} {fy1,fz1} in FP64; the
 // accumulation is predicated, not branched.
 constexpr int HBMAX = UNIT_HP > 32 ? 2 : 1;  // hit points per lane
+#ifndef SPPM_PAIR_UNROLL
+#define SPPM_PAIR_UNROLL 2
+#endif
+constexpr int PAIR_UNROLL = SPPM_PAIR_UNROLL;
 // NN = false: every hit point of the unit has the same normal, the normal test of Raytracer.h:154 was made
 // once per deposit (in FP64, exactly) when the slice was culled, and the loop tests distances only.
 template <bool UNI, bool COUNT, int HB, bool NN = true>
@@ -697,7 +704,7 @@ __device__ __forceinline__ void fast_pairs(const float4* __restrict__ cv, const 
   unsigned cd = 0;
   const float4* q = cv + j0 * F_PAIR_F4;
   const int stride = jstep * F_PAIR_F4;
-#pragma unroll 2
+#pragma unroll PAIR_UNROLL
   for (int j = j0; j < npair; j += jstep, q += stride) {
     const float4 A = q[0], B = q[1];
     float4 C = make_float4(0.f, 0.f, 0.f, 0.f);
