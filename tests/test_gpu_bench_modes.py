@@ -268,3 +268,49 @@ def test_texture_levels_on_device(ctx, oracle):
     ref = oracle.eye_pass(sc, exact_params(), cam, pass_id=0)
     order = np.lexsort((ref["node"], ref["pix"][:, 0] * cam.w + ref["pix"][:, 1]))
     np.testing.assert_allclose(a["wgt"], ref["wgt"][order], rtol=1e-9, atol=0)   # level 0 == the reference's sampler
+
+
+@pytest.mark.parametrize("workload,rounds", [("caustics-1080p", 1), ("stress-4k", 3)])
+def test_full_size_dense_maps_filtered_equals_exact(ctx, workload, rounds):
+    """BASELINE configs 4 / 5 at their full film sizes (1920x1080: 2.07 M hit points; 3840x2160 with four teapots:
+    8.29 M) — the dense maps on which a work unit is small against the radius, so the filtered gather's whole-unit
+    accept, Morton-ordered units and (config 5, PROGRESSIVE) per-unit cull radius all act.  Size-independent properties
+    over `rounds` rounds of 2 M photons in the bench's modes:
+    (a) the FP32-filtered gather (count_pairs = 0: the timed build) == the FP64-on-every-pair kernel on the same
+        photons: N, newN and R2 bit for bit, tao to rounding;
+    (b) sum of accepted pairs == the accept counter;
+    (c) PROGRESSIVE: the radii only shrink, and do so wherever photons were counted."""
+    wl = bench.WORKLOADS[workload]
+    sc = make_scene(wl["scene"])
+    cam = reference_camera(wl["w"], wl["h"])
+    progressive = workload == "stress-4k"
+    onetime = 2_000_000
+    out = []
+    for gmode in (abi.SPPM_GATHER_FILTERED, abi.SPPM_GATHER_EXACT):
+        prm = bench_params()
+        prm.gather_mode = gmode
+        prm.update_mode = abi.SPPM_UPDATE_PROGRESSIVE if progressive else abi.SPPM_UPDATE_REFERENCE
+        ctx.set_params(prm)
+        ctx.upload_scene(sc)
+        n = ctx.eye_pass(cam, 0)
+        ctx.build_index()
+        ctx.reset_counters()
+        for r in range(rounds):
+            ctx.photon_pass(0, onetime, 1 + r)
+            ctx.update()
+        out.append((ctx.export_stats(n), ctx.counters()))
+    ctx.set_params(bench_params())
+    (f, cf), (e, ce) = out
+    assert n > 0.99 * wl["w"] * wl["h"]
+    np.testing.assert_array_equal(f["newN"], e["newN"])
+    np.testing.assert_array_equal(f["N"], e["N"])
+    np.testing.assert_array_equal(f["r2"], e["r2"])
+    np.testing.assert_allclose(f["tao"], e["tao"], rtol=1e-10, atol=1e-300)
+    assert cf["acc_pairs"] == ce["acc_pairs"] > n
+    assert cf["deposits_kept"] == ce["deposits_kept"]
+    if progressive:
+        got_photons = f["N"] > 0          # (a single photon leaves N = int(0.7) = 0 but shrinks the radius all the same)
+        assert got_photons.mean() > 0.5
+        assert (f["r2"] <= 2.0).all() and (f["r2"][got_photons] < 2.0).all() and (f["r2"] == 2.0).any()
+    else:
+        assert int(f["newN"].astype(np.int64).sum()) == cf["acc_pairs"]
