@@ -100,6 +100,16 @@ class ClockSampler:
         return out
 
 
+def workload_config(name, n_hp, update):
+    """`config` of the JSON line: what defines the workload, identical in both arms (b200 / reference).  What an
+    arm does to run it (arithmetic modes, tracer, sample size, sharding) goes into `impl_config`."""
+    wl = WORKLOADS[name]
+    return {"workload": name, "scene": wl["scene"], "film": [wl["w"], wl["h"]], "hit_points": int(n_hp),
+            "photons_per_round": wl["onetime"], "newton": "50 restarts x 10 iterations, AABB culling", "update_mode": update,
+            "textures": "synthetic, reference sizes",
+            "l2": "inputs larger than L2 (deposit list + hit-point map > 126 MB); new photons every step"}
+
+
 def make_params(abi, fast=True):
     p = abi.default_params()
     p.newton_mode = abi.SPPM_NEWTON_FAST if fast else abi.SPPM_NEWTON_EXACT
@@ -216,8 +226,9 @@ def run_reference(args):
         "impl": "reference", "metric": "photons traced+gathered/sec", "value": value, "unit": "photons/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "scene": wl["scene"], "film": [wl["w"], wl["h"]],
-                   "photons_per_step": threads * per_thread, "newton": "50x10 exact order"},
+        "config": workload_config(args.workload, hp["pos"].shape[0], WORKLOAD_DEFAULTS.get(args.workload, {}).get("update", "reference")),
+        "impl_config": {"photons_per_step": threads * per_thread, "arithmetic": "exact order (oracle = the reference operation by operation)",
+                        "update": "none inside the sample (the reference's update is a no-op on fresh hit points, Raytracer.h:70)"},
         "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "bezier_isects_per_s": solves / total,
@@ -558,13 +569,11 @@ def main():
         "metric": "photons traced+gathered/sec", "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "scene": wl["scene"], "film": [wl["w"], wl["h"]], "hit_points": n_hp,
-                   "photons_per_step": step_photons, "photons_per_gpu_per_step": my_count * n_light,
-                   "newton": f"50x10 {args.newton}", "math": "fast" if args.newton == "fast" else "exact", "tracer": args.trace,
-                   "gather": args.gather, "update_mode": update,
-                   "l2": "inputs larger than L2 (deposit list + hit-point map > 126 MB); new photons every step",
-                   "textures": "synthetic, reference sizes",
-                   "parallelism": f"photons x{world} ({scaling}), hit points replicated, allreduce of dN/dtao per step"},
+        "config": workload_config(args.workload, n_hp, update),
+        "impl_config": {"photons_per_step": step_photons, "photons_per_gpu_per_step": my_count * n_light,
+                        "arithmetic": f"newton {args.newton}, math {'fast' if args.newton == 'fast' else 'exact'} (exact_mode: the same steps in the reference's order)",
+                        "tracer": args.trace, "gather": args.gather,
+                        "parallelism": f"photons x{world} ({scaling}), hit points replicated, allreduce of dN/dtao per step"},
         "e2e": {"value": e2e_value, "unit": "photons/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e, "rounds_per_step": args.e2e_rounds,
                 "phases_ms": {"eye": e2e_counters["ms_eye"], "build": e2e_counters["ms_build"], "resolve": e2e_counters["ms_resolve"]},
