@@ -9,10 +9,12 @@ eye pass, photon pass (deposit list per (photon, bounce), gathered newN / tao) a
 BASELINE configs 1 (as specified: 320x240, 100 k photons), 2 / 4 (Cornell object set) and 5 (four
 teapots) at photon counts the single-threaded oracle finishes in seconds.
 
-Bars: positions <= 1e-6 relative (north-star level 1); the same deposit for >= 99.5 % of the (photon,
-bounce) pairs (CUDA's sin / cos / acos differ from libm's by ulps, which flips a discrete decision on a
-rare path and re-routes that photon); newN equal on >= 99.5 % of the hit points with totals within
-0.2 %; film rRMSE <= 1 % (level 3)."""
+Bars: positions <= 1e-6 relative (north-star level 1); the same deposit for >= 99.95 % of the (photon,
+bounce) pairs (CUDA's sqrt-free transcendentals differ from libm's by ulps, which can flip a discrete
+decision on a rare path and re-route that photon); newN equal on >= 99.95 % of the hit points with totals
+within 0.02 %; film rRMSE <= 1 % (level 3).  Measured on the B200 (tools/test_margins.py,
+profiles/r2_margins.txt): every deposit matched (positions <= 1.5e-9), newN equal on every hit point, the
+counters identical, tao sums to 1e-15 — the bars leave room for another libm, not for a different algorithm."""
 import numpy as np
 import pytest
 
@@ -95,16 +97,16 @@ def _photon_check(ctx, oracle, scene_name, w, h, count, pass_id, begin=0):
     finally:
         ctx.keep_deposits(False)
     assert c["photons"] == rc["photons"] == count * len(sc.plvec)
-    assert abs(c["isect_queries"] - rc["queries"]) <= 0.001 * rc["queries"]
-    assert abs(c["deposits"] - rc["deposits"]) <= 0.001 * rc["deposits"]
-    assert abs(c["patch_solves"] - rc["solves"]) <= 0.002 * rc["solves"] + 2
+    assert abs(c["isect_queries"] - rc["queries"]) <= 0.0002 * rc["queries"]
+    assert abs(c["deposits"] - rc["deposits"]) <= 0.0002 * rc["deposits"]
+    assert abs(c["patch_solves"] - rc["solves"]) <= 0.001 * rc["solves"] + 2
     rd = ref["dep"]
     kg = dep["photon"].astype(np.int64) * 64 + dep["bounce"]
     kr = rd["photon"].astype(np.int64) * 64 + rd["bounce"]
     ig, ir = _match(kg, kr)
     rel = (np.abs(dep["x"][ig] - rd["x"][ir]) / np.maximum(1.0, np.abs(rd["x"][ir]))).max(1)
     same = rel <= 1e-6
-    assert same.sum() >= 0.995 * len(kr), (int(same.sum()), len(kr), len(kg))
+    assert same.sum() >= 0.9995 * len(kr), (int(same.sum()), len(kr), len(kg))
     # flux = product of the surface colours met so far: a bilinear texture lookup turns a 1e-7 difference in the
     # hit position into a ~1e-4 difference in colour, so the bar is 1e-6 for nearly all and 2e-3 for every deposit
     fg, fr = dep["flux"][ig][same], rd["flux"][ir][same]
@@ -119,9 +121,9 @@ def _photon_check(ctx, oracle, scene_name, w, h, count, pass_id, begin=0):
     ctx.update()
     got = ctx.export_stats(hp["pos"].shape[0])
     assert ref["newN"].sum() > 0
-    assert (got["newN"] == ref["newN"]).mean() >= 0.995
-    assert abs(int(got["newN"].sum()) - int(ref["newN"].sum())) <= 0.002 * ref["newN"].sum()
-    np.testing.assert_allclose(got["tao"].sum(0), ref["tao"].sum(0), rtol=2e-3)
+    assert (got["newN"] == ref["newN"]).mean() >= 0.9995
+    assert abs(int(got["newN"].sum()) - int(ref["newN"].sum())) <= 0.0002 * ref["newN"].sum()
+    np.testing.assert_allclose(got["tao"].sum(0), ref["tao"].sum(0), rtol=2e-4)
     # level 2 on the identical photon list: the GPU's own deposits through the oracle's exact kd-tree search
     # (held equal to the exhaustive scan by tests/test_oracle_cpu.py::test_kdtree_equals_brute)
     newN, tao = oracle.gather_kdtree(hp, dep, prm.init_r2)
