@@ -40,3 +40,27 @@ def test_reference_arm_other_ranks_are_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip() == ""
+
+
+def test_workload_config_is_shared_by_both_arms_and_traffic_is_digest_bound(tmp_path, monkeypatch):
+    """`config` of the JSON line defines the workload and is the same dict in both arms (arm-specific settings live in
+    `impl_config`); the ncu-derived `roofline.traffic` is only quoted while profiles/ncu_traffic.json was captured from
+    the kernel sources as they are now."""
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.workload_config("teapot-room-1024x768", 786429, "reference")
+    b = bench.workload_config("teapot-room-1024x768", 786429, "reference")
+    assert a == b and a["workload"] == "teapot-room-1024x768" and a["film"] == [1024, 768] and a["photons_per_round"] == 2_000_000
+    assert "l2" in a and "model" not in a
+    assert bench.WORKLOAD_DEFAULTS["stress-4k"] == dict(scaling="strong", update="progressive")   # BASELINE config 5
+    assert bench.WORKLOAD_DEFAULTS["caustics-1080p"]["scaling"] == "strong"                          # BASELINE config 4
+    d = bench.csrc_digest()
+    assert len(d) == 16 and d == bench.csrc_digest()
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+        t = json.load(f)
+    tr, src = bench.ncu_traffic("photon_step_kernel", "teapot-room-1024x768")
+    if t["csrc_digest"] == d:
+        assert tr == t["kernels"]["photon_step_kernel@teapot-room-1024x768"]["dram_bytes"] and src
+    else:
+        assert tr is None and src is None      # captured from other kernel sources: not quoted
+    assert bench.ncu_traffic("no_such_kernel", "teapot-room-1024x768") == (None, None)
