@@ -495,7 +495,7 @@ def main():
     per = lambda k: cnt[k] / steps
     dep_kept, cand, acc = per("deposits_kept"), per("cand_pairs"), per("acc_pairs")
     solves, culled, queries = per("patch_solves"), per("patch_culled"), per("isect_queries")
-    n_batches = max(1, -(-my_count * n_light // (1 << 21)))
+    n_batches = max(1, -(-my_count * n_light // int(os.environ.get("SPPM_PHOTON_BATCH", 1 << 23))))  # abi.cu PHOTON_BATCH
     n_bounce = prm.max_dep + 2
     has_bezier = any(o.kind == 2 for o in scene.objvec)
     wave = prm.trace_mode != abi.SPPM_TRACE_PERSISTENT

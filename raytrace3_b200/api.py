@@ -341,7 +341,7 @@ class RayTracer:
     Photon k of round i is photon i*onetime + k of pass `pass_base` in the counter RNG.  While
     HitPoint::update is the reference's (a no-op for the hit points of a fresh eye pass, N = 0,
     Raytracer.h:70, Q1) the rounds are independent and `fuse_rounds` traces them as one photon
-    pass of cnt*onetime photons (2 Mi-photon batches over the library's lanes) instead of cnt
+    pass of cnt*onetime photons (batches of at most 8 Mi photons over the library's lanes) instead of cnt
     launch sequences of onetime = 100 photons: same photons, same newN, tao in another summation
     order.  PROGRESSIVE updates keep one pass per round."""
 

@@ -46,7 +46,13 @@ struct Bind {  // make the context's device current for the duration of a call
   }
 };
 
-constexpr uint64_t PHOTON_BATCH = 1ull << 21;  // photons traced per kernel launch (all lights)
+// Photons traced per batch (all lights).  A photon pass larger than this is cut into equal batches that rotate over
+// the lanes.  8 Mi: on dense hit-point maps the gather's per-unit set-up and its partially filled 32-deposit
+// slices are amortised over four times the deposits of the 2 Mi batches of round 1, the step / Newton launches
+// over four times the photons (stress-4k 316 -> 348 M photons/s, caustics-1080p 800 -> 851;
+// profiles/r2_b_ab_photon_batch.txt); a lane's buffers are sized for its largest batch (19 GB of deposit
+// records + 4.4 GB of queues at 8 Mi photons, sized for max_dep + 1 deposits per photon).
+constexpr uint64_t PHOTON_BATCH = 1ull << 23;
 
 unsigned long long* scalars(sppm_ctx* c) { return (unsigned long long*)c->dev_scalars.p; }
 
@@ -563,7 +569,9 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
   // (A round is not split further: halving a batch doubles the per-cell and per-launch overheads.)
   const bool gather = c->index_ok && c->n_hp > 0;
   const uint64_t n_light = (uint64_t)c->scene.n_light;
-  uint64_t per_light_batch = std::max<uint64_t>(1, PHOTON_BATCH / n_light);
+  uint64_t batch = PHOTON_BATCH;
+  if (const char* e = getenv("SPPM_PHOTON_BATCH")) batch = std::max<uint64_t>(1u << 16, std::min<uint64_t>(1ull << 24, strtoull(e, nullptr, 10)));  // A/B knob
+  uint64_t per_light_batch = std::max<uint64_t>(1, batch / n_light);
   const bool split = !c->keep_all_deposits;
   if (photon_count > per_light_batch) {  // equal batches
     const uint64_t nb = (photon_count + per_light_batch - 1) / per_light_batch;
