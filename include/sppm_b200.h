@@ -223,11 +223,11 @@ int sppm_allreduce(sppm_ctx* ctx);
 /* newN += dN, tao += dtao, then HitPoint::update (Raytracer.h:69-79, 238-245). */
 int sppm_update(sppm_ctx* ctx);
 /* Film resolve (Raytracer.h:281-293): film[h][w][3] = sum tao/(PI*R2*cnt*onetime).
- * A pixel with several hit points (branching eye paths, Raytracer.h:312-335) sums them with FP64
- * atomics, i.e. in arrival order, not in Hvec order: such pixels are reproducible to rounding
- * (<= 1e-15 relative), not bit for bit, from run to run.  Pixels with one hit point - every pixel
- * of the shipped scene - are exact.  The same holds for tao itself: a round's deposits are summed
- * in the order the binning placed them (newN is an integer and exact). */
+ * A pixel with several hit points (branching eye paths, Raytracer.h:312-335) sums them in canonical
+ * order (eye-path node order, the order GetHitPoint appends them to Hvec) by one thread: the film is
+ * the same bit for bit from run to run.  tao itself is not: a round's deposits are summed in the order
+ * the binning placed them, which depends on the arrival order of the trace (<= 1e-15 relative; newN is
+ * an integer and exact). */
 int sppm_resolve(sppm_ctx* ctx, int32_t cnt, int32_t onetime, double* film_hw3);
 /* film_acc += film (Raytracer.h:449-458) and tone map (Raytracer.h:24-26, 460-470):
  * bgr[h-1-i][j][k] = toInt(film[i][j][k] / div).  All host buffers. */

@@ -328,7 +328,7 @@ void sppm_ctx_destroy(sppm_ctx* c) {
   c->prof.destroy();
   free_scene(c);
   DevBuf* bufs[] = {&c->hp_raw, &c->soa_store, &c->cell_slot, &c->occ_cell, &c->occ_start, &c->occ_nbr, &c->units, &c->item_parts, &c->item_off, &c->px_store, &c->hp_raw_alt, &c->dep_key, &c->dep_key2,
-                    &c->dep_idx, &c->dep_idx2, &c->scan_scratch, &c->cub_tmp, &c->dev_scalars, &c->counters, &c->film, &c->scratch};
+                    &c->dep_idx, &c->dep_idx2, &c->scan_scratch, &c->cub_tmp, &c->dev_scalars, &c->counters, &c->film, &c->scratch, &c->hp_canon};
   for (DevBuf* d : bufs) dev_free(*d);
   for (int i = 0; i < 8; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);

@@ -160,6 +160,7 @@ struct sppm_ctx {
   int film_w = 0, film_h = 0;
   sppm::DevBuf soa_store;  // backing store of HpSoA
   sppm::HpSoA soa{};
+  sppm::DevBuf hp_canon;   // u32[n_hp]: position in the sorted map by canonical rank (pixel, eye-path node)
   bool index_ok = false;
   // grid
   sppm::Grid grid{};

@@ -205,6 +205,14 @@ cudaError_t build_index(sppm_ctx* c) {
   c->host_counters.launches++;
   k2 = k1;
   hp_permute_kernel<<<nblk(n), TPB, 0, st>>>(raw, i2, n, c->soa);
+  {  // canonical rank -> position in the sorted map (resolve_kernel sums a pixel's hit points in that order);
+     // i1 = raw index by rank is still intact (the sort reads it), the upper half of the key buffer is free
+    CK(dev_reserve(c->hp_canon, (size_t)n * 4));
+    uint32_t* rank_of_raw = (uint32_t*)c->dep_key.p + n;
+    hp_rank_kernel<<<nblk(n), TPB, 0, st>>>(i1, n, rank_of_raw);
+    hp_canon_kernel<<<nblk(n), TPB, 0, st>>>(i2, rank_of_raw, n, (uint32_t*)c->hp_canon.p);
+    c->host_counters.launches += 2;
+  }
   CK(cudaMemsetAsync(c->dN_set[1], 0, (size_t)n * 4, st));
   CK(cudaMemsetAsync(c->dtao_set[1], 0, (size_t)n * 24, st));
   c->host_counters.launches += 3;
@@ -376,7 +384,7 @@ cudaError_t launch_resolve(sppm_ctx* c, int cnt, int onetime) {
   CK(dev_reserve(c->film, bytes));
   CK(cudaMemsetAsync(c->film.p, 0, bytes, c->stream));
   if (c->n_hp == 0) return cudaSuccess;
-  resolve_kernel<<<nblk(c->n_hp), TPB, 0, c->stream>>>(c->soa, c->n_hp, cnt, onetime, c->film_w, (double*)c->film.p);
+  resolve_kernel<<<nblk(c->n_hp), TPB, 0, c->stream>>>(c->soa, (const uint32_t*)c->hp_canon.p, c->n_hp, cnt, onetime, c->film_w, (double*)c->film.p);
   c->host_counters.launches++;
   return cudaGetLastError();
 }

@@ -1180,14 +1180,43 @@ __global__ void update_kernel(HpSoA s, long long n, int mode, double alpha) {
 }
 
 // camera->pic[x][y] += tao * (1.0 / PI / (R2*cnt*onetime))  (Raytracer.h:288-293)
-__global__ void resolve_kernel(HpSoA s, long long n, int cnt, int onetime, int w, double* film) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double sc = 1.0 / SPPM_PI / (s.r2[i] * cnt * onetime);
-  double* px = film + ((size_t)s.row[i] * w + s.col[i]) * 3;
-  atomicAdd(px + 0, s.tao[i] * sc);
-  atomicAdd(px + 1, s.tao[n + i] * sc);
-  atomicAdd(px + 2, s.tao[2 * n + i] * sc);
+// Position of every hit point in the sorted map, by canonical rank (ascending okey = pixel, eye-path node):
+// rank_of_raw scatters the first sort's order, canon gathers it through the second one.
+__global__ void hp_rank_kernel(const uint32_t* raw_of_rank, long long n, uint32_t* rank_of_raw) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) rank_of_raw[raw_of_rank[r]] = (uint32_t)r;
+}
+__global__ void hp_canon_kernel(const uint32_t* raw_of_pos, const uint32_t* rank_of_raw, long long n, uint32_t* canon) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) canon[rank_of_raw[raw_of_pos[j]]] = (uint32_t)j;
+}
+// One thread per canonical rank; the first hit point of a pixel sums the pixel's hit points in canonical
+// order (the order the reference's GetHitPoint appends a pixel's eye-path nodes to Hvec) and adds the sum
+// to the zeroed film once: the film is the same bit for bit from run to run.  (A map imported in an order
+// that separates a pixel's hit points gives several runs for the pixel, each added once.)
+__global__ void resolve_kernel(HpSoA s, const uint32_t* canon, long long n, int cnt, int onetime, int w, double* film) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  uint32_t i = canon[r];
+  const long long px = (long long)s.row[i] * w + s.col[i];
+  if (r > 0) {
+    const uint32_t q = canon[r - 1];
+    if ((long long)s.row[q] * w + s.col[q] == px) return;
+  }
+  double a[3] = {0, 0, 0};
+  for (long long k = r;;) {
+    const double sc = 1.0 / SPPM_PI / (s.r2[i] * cnt * onetime);
+    a[0] += s.tao[i] * sc;
+    a[1] += s.tao[n + i] * sc;
+    a[2] += s.tao[2 * n + i] * sc;
+    if (++k >= n) break;
+    i = canon[k];
+    if ((long long)s.row[i] * w + s.col[i] != px) break;
+  }
+  double* o = film + (size_t)px * 3;
+  atomicAdd(o + 0, a[0]);
+  atomicAdd(o + 1, a[1]);
+  atomicAdd(o + 2, a[2]);
 }
 
 // ---- shared statistics across eye passes -------------------------------------

@@ -262,7 +262,7 @@ class DeviceHost:
         L.dh_tonemap.argtypes = [VP, C.c_int, C.c_int, DBL, VP]
         L.dh_tex_expand.argtypes = [VP, C.c_int, C.c_int, VP, VP]
         L.dh_shared_pass.argtypes = [I64, C.c_int, DBL, DBL, DBL, VP, VP, VP, I64, VP, VP, VP, VP, VP, VP]
-        L.dh_update_resolve.argtypes = [I64, C.c_int, DBL, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, VP]
+        L.dh_update_resolve.argtypes = [I64, C.c_int, DBL, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP, C.c_int, C.c_int, C.c_int, VP, VP, VP]
         L.dh_intersect_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, U64, C.c_int, VP, VP]
         L.dh_patch_batch_kernel.argtypes = [VP, C.POINTER(abi.SppmParams), C.c_int, I64, VP, VP, VP, C.c_int, VP]
         assert L.dh_sizeof_hpraw() == hpraw_dtype.itemsize and L.dh_sizeof_deposit() == deposit_dtype.itemsize
@@ -351,14 +351,17 @@ class DeviceHost:
         return newN, tao, dict(zip(("n_occ", "n_slots", "n_units", "n_items", "kept"), info.tolist())), pairs.tolist()
 
     def update_resolve(self, mode, alpha, N, newN, dN, r2, tao, dtao, pix, cnt, onetime, w, h, rounds=1):
-        """update_kernel x rounds, then resolve_kernel; tao / dtao [n, 3].  In place on N, newN, r2; returns
+        """update_kernel x rounds, then hp_rank_kernel + hp_canon_kernel + resolve_kernel; tao / dtao [n, 3].  The
+        canonical order is (pixel, index), the map's own order is the index.  In place on N, newN, r2; returns
         (tao [n, 3], film [h, w, 3])."""
         n = N.shape[0]
         t, dt = np.ascontiguousarray(tao.T), np.ascontiguousarray(dtao.T)
         row, col = np.ascontiguousarray(pix[:, 0], dtype=np.int32), np.ascontiguousarray(pix[:, 1], dtype=np.int32)
         film = np.zeros((h, w, 3))
+        raw_of_rank = np.argsort(row.astype(np.int64) * w + col, kind="stable").astype(np.uint32)
+        raw_of_pos = np.arange(n, dtype=np.uint32)
         self.lib.dh_update_resolve(n, mode, alpha, rounds, _p(N), _p(newN), _p(dN), _p(r2), _p(t), _p(dt), _p(row), _p(col),
-                                   cnt, onetime, w, _p(film))
+                                   cnt, onetime, w, _p(film), _p(raw_of_rank), _p(raw_of_pos))
         return np.ascontiguousarray(t.T), film
 
     def shared_pass(self, r2, n, tau, pix, newN, tao, alpha, photons, init_r2=0.0):

@@ -647,14 +647,19 @@ int dh_gather_filtered(int64_t n, const HpRaw* raw, const Grid* grid, int64_t m,
 // (zeroed by the caller).  rounds = how many update launches (each folds dN / dtao, given once).
 void dh_update_resolve(int64_t n, int mode, double alpha, int rounds, int32_t* N, int32_t* newN, int32_t* dN, double* r2,
                        double* tao, double* dtao, const int32_t* row, const int32_t* col, int cnt, int onetime, int w,
-                       double* film) {
+                       double* film, const uint32_t* raw_of_rank, const uint32_t* raw_of_pos) {
   HpSoA s;
   memset(&s, 0, sizeof(s));
   s.N = N; s.newN = newN; s.dN = dN; s.r2 = r2; s.tao = tao; s.dtao = dtao;
   s.row = const_cast<int32_t*>(row); s.col = const_cast<int32_t*>(col);
   const int T = bt(TPB);
   for (int k = 0; k < rounds; k++) launch(update_kernel, std::make_tuple(s, (long long)n, mode, alpha), (n + T - 1) / T, T);
-  if (film) launch(resolve_kernel, std::make_tuple(s, (long long)n, cnt, onetime, w, film), (n + T - 1) / T, T);
+  if (!film) return;
+  // canonical rank -> position as build_index derives it from its two sorts
+  std::vector<uint32_t> rank_of_raw((size_t)n), canon((size_t)n);
+  launch(hp_rank_kernel, std::make_tuple(raw_of_rank, (long long)n, rank_of_raw.data()), (n + T - 1) / T, T);
+  launch(hp_canon_kernel, std::make_tuple(raw_of_pos, (const uint32_t*)rank_of_raw.data(), (long long)n, canon.data()), (n + T - 1) / T, T);
+  launch(resolve_kernel, std::make_tuple(s, (const uint32_t*)canon.data(), (long long)n, cnt, onetime, w, film), (n + T - 1) / T, T);
 }
 // Shared per-pixel statistics: shared_init (if init_r2 > 0) -> shared_load (the hit points take
 // their pixel's radius; hp_r2 out) -> [the caller's newN / tao stand for the pass's gather] -> shared_accum

@@ -885,7 +885,8 @@ def test_random_scenes_eye_and_photon_kernels(dh, oracle, seed):
 def test_update_and_resolve_kernels(dh, oracle, mode):
     """update_kernel == HitPoint::update (Raytracer.h:69-79: the shipped no-op while N == 0 (Q1), the
     progressive radius / flux shrink with the int truncation of N) and resolve_kernel == the film
-    expression of Raytracer.h:281-293, three rounds of fresh accumulators."""
+    expression of Raytracer.h:281-293 bit for bit (a pixel's hit points are summed in Hvec order), three
+    rounds of fresh accumulators."""
     rng = np.random.RandomState(31)
     n, w, h = 5000, 40, 30
     N, newN = np.zeros(n, np.int32), np.zeros(n, np.int32)
@@ -906,7 +907,7 @@ def test_update_and_resolve_kernels(dh, oracle, mode):
     np.testing.assert_array_equal(r2, or2)
     np.testing.assert_array_equal(tao, otao)
     want = oracle.resolve(pix, or2, otao, 3, 1000, w, h)
-    np.testing.assert_allclose(film, want, rtol=1e-13, atol=0)   # several hit points per pixel: order of the adds
+    np.testing.assert_array_equal(film, want)   # several hit points per pixel: summed in canonical order, as the oracle
     assert (N != 0).any() and film.sum() > 0
 
 

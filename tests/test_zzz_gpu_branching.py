@@ -34,3 +34,25 @@ def test_eye_pass_grows_its_buffer(ctx, oracle):
     # and a smaller film afterwards still works (the buffer only ever grows)
     n2 = ctx.eye_pass(reference_camera(16, 12), pass_id=1)
     assert n2 == oracle.eye_pass(sc, prm, reference_camera(16, 12), pass_id=1)["pos"].shape[0]
+
+
+def test_film_sums_a_pixels_hit_points_in_canonical_order(ctx, oracle):
+    """Raytracer.h:281-293 on a map with many hit points per pixel: sppm_resolve == the oracle's film of the
+    exported state (canonical order = pixel, eye-path node, the order GetHitPoint appends to Hvec) bit for
+    bit, and a second resolve gives the same bits (no arrival-order atomics between a pixel's hit points)."""
+    sc = branching_scene()
+    prm = abi.default_params()
+    ctx.set_params(prm)
+    ctx.upload_scene(sc)
+    w, h, onetime = 48, 36, 200_000
+    n = ctx.eye_pass(reference_camera(w, h), pass_id=1)
+    ctx.build_index()
+    ctx.photon_pass(0, onetime, 1)
+    ctx.update()
+    hp = ctx.export_hitpoints()
+    st = ctx.export_stats(n)
+    assert n > 4 * w * h and st["tao"].sum() > 0
+    want = oracle.resolve(hp["pix"], st["r2"], st["tao"], 1, onetime, w, h)
+    film = ctx.resolve(1, onetime, w, h)
+    np.testing.assert_array_equal(film, want)
+    np.testing.assert_array_equal(ctx.resolve(1, onetime, w, h), film)
