@@ -264,7 +264,13 @@ int sppm_ctx_create(int device, sppm_ctx** out) {
     delete c;
     return cuda_fail(nullptr, e, "cudaSetDevice");
   }
-  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  bool ok;
+  {  // SPPM_MAIN_PRIORITY=1 (A/B knob): the main stream (gathers, update) above the lanes' traces
+    int lo_p = 0, hi_p = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+    const char* e = getenv("SPPM_MAIN_PRIORITY");
+    ok = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, e && atoi(e) ? hi_p : 0) == cudaSuccess;
+  }
   for (int i = 0; i < 8 && ok; i++) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   for (int i = 0; i < sppm_ctx::TIMING_RING && ok; i++)
     for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&c->tev[i][k]) == cudaSuccess;
