@@ -85,7 +85,6 @@ __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync
 
 __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem, false);
   const int lane = threadIdx.x & 31;
   // The queue arrays hold 2 x q_cap entries and are filled from four ends, by what the pending hit
   // will make the next step do, so that warps shade uniform work:
@@ -101,6 +100,12 @@ __global__ void __launch_bounds__(STEP_THREADS, SPPM_STEP_MINBLOCKS) photon_step
   for (int r = 1; r < 4; r++) nreg[r] = a.bounce == 0 ? 0u : a.n_in_ptr[r];
   const unsigned c0 = ((nreg[0] + 31) >> 5) * 32, c1 = c0 + ((nreg[1] + 31) >> 5) * 32, c2 = c1 + ((nreg[2] + 31) >> 5) * 32;
   const unsigned n_in = c2 + nreg[3];
+#ifndef SPPM_NO_EARLY_EXIT
+  // A CTA whose first warp starts beyond the queue has no photon at all (the grid is sized for a full batch; in
+  // the tail bounces a few CTAs hold every live photon): it leaves before staging the scene.
+  if (blockIdx.x * blockDim.x >= n_in) return;
+#endif
+  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem, false);
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
   unsigned queries = 0, solves = 0, photons = 0, deposits = 0, kept = 0, spilled = 0;  // per thread, < 2^32
@@ -390,8 +395,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_i
   const unsigned n = min(*a.n_items_ptr, a.item_cap);
   if (n == 0) return;
   const size_t scene_bytes = scene_smem_bytes(a.scene.n_obj, a.scene.n_patch, a.patches_in_smem);
-  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem);
-  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + scene_bytes) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -404,6 +407,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, SPPM_NEWTON_MINBLOCKS) newton_i
   const unsigned per = dynamic ? 4u * n_warps : n_warps;
   unsigned C = (n + per - 1) / per;
   C = C < 1 ? 1 : (C > 32 ? 32 : C);
+#ifndef SPPM_NO_EARLY_EXIT
+  // static partition: a CTA whose first warp's chunk starts beyond the list has no item (tail bounces: a handful of
+  // items for a grid sized for thousands) and leaves before staging the scene
+  if (!dynamic && (blockIdx.x * blockDim.x >> 5) * C >= n) return;
+#endif
+  const SceneView sv = stage_scene(a.scene, smem, a.patches_in_smem);
+  WarpScratch* ws = reinterpret_cast<WarpScratch*>(smem + scene_bytes) + (threadIdx.x >> 5);
   for (unsigned c_static = warp_global * C;; c_static += n_warps * C) {
     unsigned c0 = c_static;
     if (dynamic) {
