@@ -8,8 +8,6 @@ OUT=gpurun_out; mkdir -p $OUT
 T="python tools/ncu_target.py"
 NCU="ncu --set full --clock-control none --import-source on --profile-from-start off -f"
 timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 > $OUT/${TAG}_gpu_tests.txt; cat $OUT/${TAG}_gpu_tests.txt
-timeout 400 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; cut -c1-200 $OUT/${TAG}_bench_n1.json
-timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference_arm.json 2>/dev/null; cut -c1-200 $OUT/${TAG}_bench_reference_arm.json
 for w in cornell-1024x768 caustics-1080p stress-4k ref-main-320x240; do
   timeout 400 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $OUT/${TAG}_bench_$w.json 2> $OUT/${TAG}_err_$w.txt
   cut -c1-160 $OUT/${TAG}_bench_$w.json
@@ -29,4 +27,8 @@ cap gather gather_filtered 0 1
 cap step photon_step 0 15
 cap newton newton_items 0 14
 python -c "import bench; print(bench.csrc_digest())" > $OUT/${TAG}_csrc_digest.txt
+# the traffic table of THIS kernel state, then the bench line that quotes it
+python tools/ncu_traffic.py $(cat $OUT/${TAG}_csrc_digest.txt) teapot-room-1024x768 $OUT/${TAG}_gather_raw.csv $OUT/${TAG}_step_raw.csv $OUT/${TAG}_newton_raw.csv > /dev/null && cp profiles/ncu_traffic.json $OUT/${TAG}_ncu_traffic.json
+timeout 400 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; cut -c1-200 $OUT/${TAG}_bench_n1.json
+timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_reference_arm.json 2>/dev/null; cut -c1-200 $OUT/${TAG}_bench_reference_arm.json
 du -sh $OUT
