@@ -377,9 +377,9 @@ def main():
     # set-up, untimed: one round per pipeline lane so that every lane has allocated its buffers (a lane's first
     # batch pays cudaMalloc); then the W warm-up steps the caller asked for
     next_round = 0
-    for i in range(4):
+    for i in range(8):
         step(next_round + i)
-    next_round += 4
+    next_round += 8
     for i in range(args.warmup):
         step(next_round + i)
     next_round += args.warmup

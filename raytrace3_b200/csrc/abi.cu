@@ -288,7 +288,8 @@ int sppm_ctx_create(int device, sppm_ctx** out) {
          cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming) == cudaSuccess;
     if (const char* e = getenv("SPPM_ASYNC_COMM")) c->async_comm = atoi(e) != 0;
   }
-  if (const char* e = getenv("SPPM_LANES")) c->n_lanes = std::max(1, std::min((int)sppm_ctx::MAX_LANES, atoi(e)));
+  if (const char* e = getenv("SPPM_LANES")) c->n_lanes = c->n_lanes_small = std::max(1, std::min((int)sppm_ctx::MAX_LANES, atoi(e)));
+  if (const char* e = getenv("SPPM_LANES_SMALL")) c->n_lanes_small = std::max(1, std::min((int)sppm_ctx::MAX_LANES, atoi(e)));
   for (int j = 0; j < sppm_ctx::MAX_LANES && ok; j++) {
     Lane& L = c->lanes[j];
     ok = cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -585,7 +586,9 @@ int sppm_photon_pass(sppm_ctx* c, uint64_t photon_begin, uint64_t photon_count, 
   }
   for (uint64_t off = 0; off < photon_count; off += per_light_batch) {
     const uint64_t cnt = std::min(per_light_batch, photon_count - off);
-    const int j = split ? (c->lane_rr++ % c->n_lanes) : 0;
+    // small batches (the reference's own round sizes) are chains of latency-bound launches: more of them in flight
+    const int lanes_now = cnt * n_light <= sppm_ctx::SMALL_BATCH ? c->n_lanes_small : c->n_lanes;
+    const int j = split ? (c->lane_rr++ % lanes_now) : 0;
     Lane& L = c->lanes[j];
     c->last_lane = j;
     const int64_t cap = (int64_t)(cnt * n_light) * (c->prm.max_dep + 1);

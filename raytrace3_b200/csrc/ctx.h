@@ -173,9 +173,11 @@ struct sppm_ctx {
   int32_t n_units = 0;
   sppm::DevBuf item_parts, item_off;  // per-batch work-item counts of the units and their exclusive scan
   // deposits
-  static constexpr int MAX_LANES = 4;
+  static constexpr int MAX_LANES = 8;
   sppm::Lane lanes[MAX_LANES];
-  int n_lanes = 4;            // lanes used round-robin (SPPM_LANES, 1..MAX_LANES); 4 measured best (2: 2.80, 3: 2.72, 4: 2.68 ms)
+  int n_lanes = 4;            // lanes used round-robin (SPPM_LANES, 1..MAX_LANES); 4 measured best (2: 2.80, 3: 2.72, 4: 2.68 ms; 5-8: no gain)
+  int n_lanes_small = 6;      // for batches of at most SMALL_BATCH photons (SPPM_LANES_SMALL): their launches are latency floors (100 k-photon rounds: 4: 354, 6: 381, 8: 375 M photons/s)
+  static constexpr uint64_t SMALL_BATCH = 1u << 19;
   int lane_rr = 0, last_lane = 0;
   cudaEvent_t ev_setup = nullptr;  // recorded on the main stream after scene / hit-point map changes
   sppm::DevBuf dep_key, dep_key2, dep_idx, dep_idx2, scan_scratch, cub_tmp;  // build_index scratch
