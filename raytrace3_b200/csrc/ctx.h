@@ -153,6 +153,10 @@ struct sppm_ctx {
   bool scene_ok = false;
   bool patches_in_smem = true;
   size_t trace_smem = 0;
+  // launch configurations, queried once per scene (trace_configure resets them) instead of once per batch
+  struct WfCfg { bool valid = false; int step_blocks = 0, newton_blocks = 0; size_t step_smem = 0, newton_smem = 0; } wf_cfg;
+  int trace_per_sm = 0;        // photon_trace_kernel CTAs per SM (0 = not queried yet)
+  int gather_per_sm[3] = {};   // gather_kernel, gather_filtered_kernel<false>, <true>
   // hit points
   sppm::DevBuf hp_raw;     // HpRaw[cap]
   sppm::DevBuf hp_raw_alt; // receive buffer of sppm_allgather_hitpoints (swapped with hp_raw)

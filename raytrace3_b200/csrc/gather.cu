@@ -341,10 +341,15 @@ cudaError_t launch_gather(sppm_ctx* c, Lane& L, cudaEvent_t ev_gather_start, cud
     const bool filtered = c->prm.gather_mode == SPPM_GATHER_FILTERED;
     auto kern = !filtered ? gather_kernel : (c->prm.count_pairs ? gather_filtered_kernel<true> : gather_filtered_kernel<false>);
     const size_t tile_bytes = filtered ? F_SMEM : 2 * (size_t)G_TILE * sizeof(Deposit);
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));  // per device
-    int per_sm = 1;
     const int threads = filtered ? W_THREADS : G_THREADS;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, tile_bytes));
+    int& cached = c->gather_per_sm[!filtered ? 0 : (c->prm.count_pairs ? 2 : 1)];
+    if (cached <= 0) {  // once per context and kernel variant
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));  // per device
+      int q = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, tile_bytes));
+      cached = q < 1 ? 1 : q;
+    }
+    int per_sm = cached;
     if (const char* e = getenv("SPPM_GATHER_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));  // tuning knob
     unsigned blocks = (unsigned)c->sm_count * (unsigned)(per_sm < 1 ? 1 : per_sm);  // persistent CTAs, cells handed out dynamically
     const unsigned max_blocks = filtered ? (unsigned)((c->n_units + W_WARPS - 1) / W_WARPS) : (unsigned)c->n_occ;

@@ -35,6 +35,8 @@ cudaError_t trace_configure(sppm_ctx* c) {
   size_t with = scene_smem_bytes(c->scene.n_obj, c->scene.n_patch, true) + scratch;
   c->patches_in_smem = with <= 100 * 1024;
   c->trace_smem = scene_smem_bytes(c->scene.n_obj, c->scene.n_patch, c->patches_in_smem) + scratch;
+  c->wf_cfg.valid = false;
+  c->trace_per_sm = 0;
   cudaError_t e;
   const int bytes = (int)c->trace_smem;
   if ((e = cudaFuncSetAttribute(eye_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))) return e;
@@ -82,10 +84,13 @@ cudaError_t launch_photon_trace(sppm_ctx* c, Lane& L, uint64_t begin, uint64_t c
   a.cursor = (unsigned long long*)L.scalars.p + 2;
   a.begin = begin;
   a.count = count;
-  int per_sm = 1;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, photon_trace_kernel, TRACE_THREADS, c->trace_smem);
-  if (e) return e;
-  if (per_sm < 1) per_sm = 1;
+  if (c->trace_per_sm <= 0) {
+    int q = 1;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, photon_trace_kernel, TRACE_THREADS, c->trace_smem);
+    if (e) return e;
+    c->trace_per_sm = q < 1 ? 1 : q;
+  }
+  const int per_sm = c->trace_per_sm;
   const unsigned long long total = (unsigned long long)c->scene.n_light * count;
   unsigned long long want = (total + TRACE_THREADS - 1) / TRACE_THREADS;
   unsigned long long blocks = (unsigned long long)c->sm_count * per_sm;  // persistent: a whole number of waves

@@ -23,6 +23,11 @@
 namespace sppm {
 
 cudaError_t wavefront_configure(sppm_ctx* c, int* step_blocks, int* newton_blocks, size_t* step_smem, size_t* newton_smem) {
+  if (c->wf_cfg.valid) {  // once per scene: four driver queries less per batch
+    *step_blocks = c->wf_cfg.step_blocks; *newton_blocks = c->wf_cfg.newton_blocks;
+    *step_smem = c->wf_cfg.step_smem; *newton_smem = c->wf_cfg.newton_smem;
+    return cudaSuccess;
+  }
   const size_t scene = scene_smem_bytes(c->scene.n_obj, c->scene.n_patch, c->patches_in_smem, true);
   *step_smem = scene_smem_bytes(c->scene.n_obj, c->scene.n_patch, c->patches_in_smem, false);
   *newton_smem = scene + TRACE_WARPS * sizeof(WarpScratch);
@@ -36,6 +41,9 @@ cudaError_t wavefront_configure(sppm_ctx* c, int* step_blocks, int* newton_block
   if (const char* e = getenv("SPPM_NEWTON_CTAS")) b = std::max(1, std::min(b, atoi(e)));
   *step_blocks = c->sm_count * (a < 1 ? 1 : a);
   *newton_blocks = c->sm_count * (b < 1 ? 1 : b);
+  c->wf_cfg.step_blocks = *step_blocks; c->wf_cfg.newton_blocks = *newton_blocks;
+  c->wf_cfg.step_smem = *step_smem; c->wf_cfg.newton_smem = *newton_smem;
+  c->wf_cfg.valid = true;
   return cudaSuccess;
 }
 
