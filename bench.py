@@ -377,9 +377,10 @@ def main():
     # set-up, untimed: one round per pipeline lane so that every lane has allocated its buffers (a lane's first
     # batch pays cudaMalloc); then the W warm-up steps the caller asked for
     next_round = 0
-    for i in range(8):
+    n_prime = 8 if my_count * n_light <= (1 << 19) else 4   # the library rotates small batches over more lanes (ctx.h)
+    for i in range(n_prime):
         step(next_round + i)
-    next_round += 8
+    next_round += n_prime
     for i in range(args.warmup):
         step(next_round + i)
     next_round += args.warmup
