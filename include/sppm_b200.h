@@ -313,6 +313,13 @@ int sppm_get_counters(sppm_ctx* ctx, SppmCounters* out);
  * CUDA event between its launches, so that SppmCounters.ms_step / ms_newton / ... hold the time of each
  * kernel class as an ncu launch list sees it; on = 0 (default) is the pipelined production path. */
 int sppm_set_profiling(sppm_ctx* ctx, int32_t on);
+
+/* Page-lock a host buffer the caller owns (and keeps alive until sppm_host_unpin), so that the film read-back of
+ * sppm_resolve and the texture / film uploads copy by DMA at the full PCIe rate instead of through the driver's
+ * staging buffer.  Optional: every entry point takes pageable memory as well.  What the reference's
+ * camera->pic (Camera.h:13, filled at Raytracer.h:281-293) becomes in the drop-in Camera.  Needs no context. */
+int sppm_host_pin(void* ptr, uint64_t bytes);
+int sppm_host_unpin(void* ptr);
 int sppm_reset_counters(sppm_ctx* ctx);
 
 #ifdef __cplusplus

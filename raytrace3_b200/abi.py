@@ -141,6 +141,8 @@ PROTOTYPES = {
     "sppm_get_counters": (C.c_int, [VP, C.POINTER(SppmCounters)]),
     "sppm_reset_counters": (C.c_int, [VP]),
     "sppm_set_profiling": (C.c_int, [VP, I32]),
+    "sppm_host_pin": (C.c_int, [VP, U64]),
+    "sppm_host_unpin": (C.c_int, [VP]),
 }
 
 _lib = None

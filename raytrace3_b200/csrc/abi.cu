@@ -791,6 +791,26 @@ int sppm_tonemap(sppm_ctx* c, const double* film_hw3, int32_t w, int32_t h, doub
   return SPPM_OK;
 }
 
+int sppm_host_pin(void* ptr, uint64_t bytes) {
+  if (!ptr || bytes == 0) return SPPM_ERR_INVALID;
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // not sticky; the caller goes on with pageable memory
+    g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e);
+    return SPPM_ERR_CUDA;
+  }
+  return SPPM_OK;
+}
+int sppm_host_unpin(void* ptr) {
+  if (!ptr) return SPPM_ERR_INVALID;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return SPPM_ERR_CUDA;
+  }
+  return SPPM_OK;
+}
+
 int sppm_comm_unique_id(void* id128) {
   if (!id128) return SPPM_ERR_INVALID;
   NcclApi& n = nccl();

@@ -12,7 +12,7 @@ class Camera {
   int w = 0, h = 0;
   Vec3 dir;
   Vec3 du, dv;
-  Color** pic = nullptr;
+  Color** pic = nullptr;  // pic[i][j] as upstream (Camera.h:13); the rows are slices of ONE page-locked block, see film()
   Camera() {}
   static const int DEFAULT_LENS = 100;
   static const int DEFAULT_HEIGHT = 1024;
@@ -45,6 +45,11 @@ class Camera {
     return *this;
   }
   void clear() { for (int i = 0; i < h; i++) for (int j = 0; j < w; j++) pic[i][j] = Color(); }
+  // The film as the C ABI sees it: double[h][w][3], row-major.  A Color is three doubles, so the block behind
+  // pic IS that array: sppm_resolve writes the read-back straight into camera.pic (no staging copy), and the
+  // block is page-locked (sppm_host_pin) so that the copy is one DMA transfer.
+  double* film() { return pic ? pic[0][0].val : nullptr; }
+  const double* film() const { return pic ? pic[0][0].val : nullptr; }
   ~Camera() { release(); }
   SppmCameraDesc desc() const {
     SppmCameraDesc d;
@@ -61,17 +66,25 @@ class Camera {
   void copyPose(const Camera& c) {
     look = c.look; pos = c.pos; len_w = c.len_w; len_h = c.len_h; w = c.w; h = c.h; dir = c.dir; du = c.du; dv = c.dv;
   }
+  Color* block = nullptr;
+  bool pinned = false;
   void alloc() {
+    static_assert(sizeof(Color) == 3 * sizeof(double), "a Color is three doubles: pic is double[h][w][3]");
     if (!pic && h > 0 && w > 0) {
+      block = new Color[(size_t)h * w];
       pic = new Color*[h];
-      for (int i = 0; i < h; i++) pic[i] = new Color[w];
+      for (int i = 0; i < h; i++) pic[i] = block + (size_t)i * w;
       ah = h;
+      pinned = sppm_host_pin(block, (uint64_t)h * w * sizeof(Color)) == SPPM_OK;  // best effort: pageable works too
     }
   }
   void release() {
     if (!pic) return;
-    for (int i = 0; i < ah; i++) delete[] pic[i];
+    if (pinned) sppm_host_unpin(block);
+    pinned = false;
+    delete[] block;
     delete[] pic;
+    block = nullptr;
     pic = nullptr;
   }
 };

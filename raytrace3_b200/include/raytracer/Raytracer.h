@@ -4,6 +4,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -65,11 +66,15 @@ class RayTracer {
 
   void GetHitPoint() {  // Raytracer.h:102-116
     ensure();
-    sppm_host::FlatScene fs;
-    scene->flatten(fs);
-    SppmSceneDesc d = fs.desc();
-    sppm_host::check(sppm_set_params(ctx, &params), ctx, "sppm_set_params");
-    sppm_host::check(sppm_scene_upload(ctx, &d), ctx, "sppm_scene_upload");
+    {
+      sppm_host::Phase ph("scene flatten+upload");
+      sppm_host::FlatScene fs;
+      scene->flatten(fs);
+      SppmSceneDesc d = fs.desc();
+      sppm_host::check(sppm_set_params(ctx, &params), ctx, "sppm_set_params");
+      sppm_host::check(sppm_scene_upload(ctx, &d), ctx, "sppm_scene_upload");
+    }
+    sppm_host::Phase ph("eye pass");
     SppmCameraDesc cd = camera->desc();
     int64_t n = 0;
     sppm_host::check(sppm_eye_pass(ctx, &cd, pass_base, &n), ctx, "sppm_eye_pass");
@@ -79,21 +84,25 @@ class RayTracer {
   void PhotonMap(int cnt_) {  // Raytracer.h:210-295
     const bool fuse = fuse_rounds && params.update_mode == SPPM_UPDATE_REFERENCE;
     const uint64_t step = sppm_host::rounds_per_call((uint64_t)onetime, fuse);
-    for (uint64_t i = 0; i < (uint64_t)cnt_; i += step) {
-      const uint64_t nr = std::min<uint64_t>(step, (uint64_t)cnt_ - i);
-      sppm_host::check(sppm_photon_pass(ctx, i * (uint64_t)onetime, nr * (uint64_t)onetime, pass_base), ctx, "sppm_photon_pass");
-      sppm_host::check(sppm_allreduce(ctx), ctx, "sppm_allreduce");
-      sppm_host::check(sppm_update(ctx), ctx, "sppm_update");
+    {
+      sppm_host::Phase ph("photon passes (enqueue)");
+      for (uint64_t i = 0; i < (uint64_t)cnt_; i += step) {
+        const uint64_t nr = std::min<uint64_t>(step, (uint64_t)cnt_ - i);
+        sppm_host::check(sppm_photon_pass(ctx, i * (uint64_t)onetime, nr * (uint64_t)onetime, pass_base), ctx, "sppm_photon_pass");
+        sppm_host::check(sppm_allreduce(ctx), ctx, "sppm_allreduce");
+        sppm_host::check(sppm_update(ctx), ctx, "sppm_update");
+      }
     }
-    vector<double> film((size_t)camera->w * camera->h * 3);
-    sppm_host::check(sppm_resolve(ctx, cnt_, onetime, film.data()), ctx, "sppm_resolve");
-    for (int i1 = 0; i1 < camera->h; i1++)
-      for (int j = 0; j < camera->w; j++)
-        for (int k = 0; k < 3; k++) camera->pic[i1][j].val[k] = film[((size_t)i1 * camera->w + j) * 3 + k];
+    // camera->pic is one page-locked double[h][w][3] block (Camera::film): the read-back lands in it directly
+    sppm_host::Phase ph("resolve + read-back");
+    sppm_host::check(sppm_resolve(ctx, cnt_, onetime, camera->film()), ctx, "sppm_resolve");
   }
   void render() {  // Raytracer.h:366-387
     GetHitPoint();
-    sppm_host::check(sppm_build_index(ctx), ctx, "sppm_build_index");
+    {
+      sppm_host::Phase ph("build index");
+      sppm_host::check(sppm_build_index(ctx), ctx, "sppm_build_index");
+    }
     PhotonMap(cnt);
   }
   // Copy the device hit-point map (positions, normals, weights, statistics) into Hvec.
@@ -179,15 +188,20 @@ class SPPMRayTracer {  // Raytracer.h:421-477
           for (int k = 0; k < 3; k++) camera.pic[i1][jj].val[k] = saved[((size_t)i1 * camera.w + jj) * 3 + k];
     }
     for (int i = first; i < sppmtime; i++) {
-      for (int j = 0; j < replicas; j++) {
-        c[j] = camera;
-        c[j].MoveTo(camera.pos + jitter * Vec3::GetUnitRandVec());
-        c[j].lookAt(camera.look, 1.);
+      sppm_host::Phase whole("pass (everything)");
+      {
+        sppm_host::Phase ph("replica cameras");
+        for (int j = 0; j < replicas; j++) {
+          c[j] = camera;
+          c[j].MoveTo(camera.pos + jitter * Vec3::GetUnitRandVec());
+          c[j].lookAt(camera.look, 1.);
+        }
       }
       // the reference runs its 4 RayTracers on 4 OpenMP threads; here one host thread per GPU
 #pragma omp parallel for num_threads(ndev) schedule(static, 1)
       for (int d = 0; d < ndev; d++) {
         for (int j = d; j < replicas; j += ndev) {
+          sppm_host::Phase whole_r("replica (everything)");
           RayTracer rt(ctxs[d]);
           rt.params = params;
           rt.fuse_rounds = fuse_rounds;
@@ -199,22 +213,31 @@ class SPPMRayTracer {  // Raytracer.h:421-477
           rt.render();
         }
       }
-      for (int j = 0; j < replicas; j++)  // Raytracer.h:449-458
-        for (int i1 = 0; i1 < camera.h; i1++)
-          for (int jj = 0; jj < camera.w; jj++) camera.pic[i1][jj] += c[j].pic[i1][jj];
+      {
+        sppm_host::Phase ph("film accumulate");
+        film.resize((size_t)camera.w * camera.h * 3);
+        const int hh = camera.h, ww = camera.w, nrep = replicas;
+#pragma omp parallel for schedule(static)
+        for (int i1 = 0; i1 < hh; i1++) {  // Raytracer.h:449-458, replicas summed in order j = 0, 1, ... per pixel
+          for (int j = 0; j < nrep; j++)
+            for (int jj = 0; jj < ww; jj++) camera.pic[i1][jj] += c[j].pic[i1][jj];
+          std::memcpy(&film[(size_t)i1 * ww * 3], camera.pic[i1], (size_t)ww * 3 * sizeof(double));
+        }
+      }
       // tone map (Raytracer.h:460-470) on the device, then save (PPM instead of cv::imwrite)
-      film.resize((size_t)camera.w * camera.h * 3);
-      for (int i1 = 0; i1 < camera.h; i1++)
-        for (int jj = 0; jj < camera.w; jj++)
-          for (int k = 0; k < 3; k++) film[((size_t)i1 * camera.w + jj) * 3 + k] = camera.pic[i1][jj].val[k];
       image.resize(film.size());
-      sppm_host::check(sppm_tonemap(ctxs[0], film.data(), camera.w, camera.h, (i + 1) * (double)replicas, image.data()), ctxs[0], "sppm_tonemap");
+      {
+        sppm_host::Phase ph("tone map");
+        sppm_host::check(sppm_tonemap(ctxs[0], film.data(), camera.w, camera.h, (i + 1) * (double)replicas, image.data()), ctxs[0], "sppm_tonemap");
+      }
       // checkpoint first, image second: a crash between the two repeats the image, not the iteration
       if (checkpoint_every > 0 && !checkpoint_path.empty() && (i + 1) % checkpoint_every == 0)
         saveCheckpoint(camera.w, camera.h, false, i + 1, film, 0);
+      sppm_host::Phase ph("save image");
       saveImage(ctxs[0], i, camera.w, camera.h);
     }
     for (sppm_ctx* x : ctxs) sppm_ctx_destroy(x);
+    sppm_host::print_host_times();
   }
 
  private:
@@ -333,10 +356,13 @@ class SPPMRayTracer {  // Raytracer.h:421-477
     FILE* f = std::fopen(path.c_str(), "wb");
     if (!f) return;
     std::fprintf(f, "P6\n%d %d\n255\n", w, h);
-    for (size_t p = 0; p < (size_t)w * h; p++) {
-      const uchar rgb[3] = {image[3 * p + 2], image[3 * p + 1], image[3 * p]};  // film channels are BGR (Q11)
-      std::fwrite(rgb, 1, 3, f);
+    std::vector<uchar> rgb((size_t)w * h * 3);
+    for (size_t p = 0; p < (size_t)w * h; p++) {  // film channels are BGR (Q11)
+      rgb[3 * p] = image[3 * p + 2];
+      rgb[3 * p + 1] = image[3 * p + 1];
+      rgb[3 * p + 2] = image[3 * p];
     }
+    std::fwrite(rgb.data(), 1, rgb.size(), f);
     std::fclose(f);
   }
 };

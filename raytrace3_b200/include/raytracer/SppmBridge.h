@@ -2,8 +2,11 @@
 // (include/sppm_b200.h): error handling, the per-process device context used by the
 // single-ray compatibility calls, and the flattened scene holder.
 #pragma once
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -25,6 +28,37 @@ inline sppm_ctx* create_ctx(int device) {
 inline sppm_ctx* compat_ctx() {
   static sppm_ctx* c = create_ctx(std::getenv("SPPM_DEVICE") ? std::atoi(std::getenv("SPPM_DEVICE")) : 0);
   return c;
+}
+// Host-side phase times of the render loop (SPPM_HOST_TIMING=1): wall-clock seconds per named phase, summed over
+// all threads and printed by SPPMRayTracer::render when it returns.  Off: one getenv per process.
+inline bool host_timing_on() {
+  static const bool on = std::getenv("SPPM_HOST_TIMING") && std::atoi(std::getenv("SPPM_HOST_TIMING")) != 0;
+  return on;
+}
+inline std::map<std::string, std::pair<double, long>>& host_times() {
+  static std::map<std::string, std::pair<double, long>> t;
+  return t;
+}
+struct Phase {  // scope timer
+  const char* name;
+  std::chrono::steady_clock::time_point t0;
+  explicit Phase(const char* n) : name(n) { if (host_timing_on()) t0 = std::chrono::steady_clock::now(); }
+  ~Phase() {
+    if (!host_timing_on()) return;
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+#pragma omp critical(sppm_host_times)
+    {
+      auto& e = host_times()[name];
+      e.first += dt;
+      e.second++;
+    }
+  }
+};
+inline void print_host_times() {
+  if (!host_timing_on()) return;
+  for (const auto& kv : host_times())
+    std::printf("host phase %-22s %9.3f ms total  %6ld calls  %8.3f ms each\n", kv.first.c_str(), kv.second.first * 1e3, kv.second.second,
+                kv.second.first * 1e3 / (double)kv.second.second);
 }
 // Rounds of `onetime` photons handed to one sppm_photon_pass call (RayTracer::PhotonMap): whole
 // rounds, at most FUSE_PHOTONS photons per light and call (the per-call accumulators are int32 per
