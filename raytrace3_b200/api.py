@@ -66,6 +66,17 @@ def row_range(h: int, rank: int, world: int):
     return int(h) * rank // world, int(h) * (rank + 1) // world
 
 
+def host_pin(a: np.ndarray) -> bool:
+    """Page-lock a C-contiguous array the caller keeps alive (sppm_host_pin): the film read-back of `resolve(out=a)` and
+    texture uploads then copy by DMA.  Best effort: False if the driver refuses; pair with host_unpin."""
+    assert a.flags.c_contiguous
+    return abi.load_library().sppm_host_pin(a.ctypes.data, a.nbytes) == 0
+
+
+def host_unpin(a: np.ndarray) -> bool:
+    return abi.load_library().sppm_host_unpin(a.ctypes.data) == 0
+
+
 class Context:
     """One sppm_ctx = one CUDA device.  Methods map 1:1 onto include/sppm_b200.h."""
 

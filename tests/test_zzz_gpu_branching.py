@@ -56,3 +56,27 @@ def test_film_sums_a_pixels_hit_points_in_canonical_order(ctx, oracle):
     film = ctx.resolve(1, onetime, w, h)
     np.testing.assert_array_equal(film, want)
     np.testing.assert_array_equal(ctx.resolve(1, onetime, w, h), film)
+
+
+def test_resolve_into_a_page_locked_film(ctx):
+    """sppm_host_pin / sppm_host_unpin (what the drop-in Camera does with camera.pic): the film read back into a
+    page-locked caller buffer is the film read back into pageable memory; a null pointer is refused."""
+    from raytrace3_b200 import api
+    sc = branching_scene()
+    ctx.set_params(abi.default_params())
+    ctx.upload_scene(sc)
+    w, h, onetime = 48, 36, 50_000
+    ctx.eye_pass(reference_camera(w, h), pass_id=1)
+    ctx.build_index()
+    ctx.photon_pass(0, onetime, 1)
+    ctx.update()
+    plain = ctx.resolve(1, onetime, w, h)
+    film = np.full((h, w, 3), -1.0)
+    assert api.host_pin(film)
+    try:
+        ctx.resolve(1, onetime, w, h, out=film)
+        np.testing.assert_array_equal(film, plain)
+    finally:
+        assert api.host_unpin(film)
+    assert ctx.lib.sppm_host_pin(None, 16) == -1 and ctx.lib.sppm_host_unpin(None) == -1   # SPPM_ERR_INVALID
+    assert not api.host_unpin(film)      # not registered any more: an error code, no crash
