@@ -98,3 +98,51 @@ def test_cli_scene_file_checkpoint_resume_and_jpeg(tmp_path, ctx):
     job.w, job.h, job.replicas, job.rounds, job.photons, job.passes, job.jitter = 48, 36, 2, 1, 20000, 1, 0.0
     film, _ = render_job(ctx, sc, job)
     np.testing.assert_allclose(cpp, film.sum(), rtol=1e-9)
+
+
+def test_camera_film_is_one_block_with_the_reference_copy_semantics(tmp_path):
+    """Camera.h:13 `Color** pic` of the drop-in: pic[i][j] addresses one double[h][w][3] block (Camera::film(), what
+    sppm_resolve fills directly); a copy takes the pose and a fresh zeroed film (Camera.h:55-74); assigning a camera of
+    another size re-allocates.  Runs without a GPU: page-locking is best effort."""
+    from raytrace3_b200 import abi
+    abi.load_library()
+    src = tmp_path / "cam.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "Camera.h"
+int main() {
+  Camera a;
+  a.init(7, 5);
+  a.MoveTo(Vec3(50, 35, 230));
+  a.lookAt(Vec3(50, 35.04, 229), 1.);
+  if (!a.pic || a.film() != a.pic[0][0].val) return 1;
+  for (int i = 0; i < a.h; i++)
+    for (int j = 0; j < a.w; j++)
+      for (int k = 0; k < 3; k++) {
+        if (&a.pic[i][j].val[k] != a.film() + ((size_t)i * a.w + j) * 3 + k) return 2;
+        if (a.pic[i][j].val[k] != 0) return 3;
+        a.pic[i][j].val[k] = i * 100 + j * 10 + k;
+      }
+  Camera b = a;                       // pose copied, film fresh
+  if (b.w != 7 || b.h != 5 || b.pic == a.pic || b.film() == a.film() || b.pic[4][6].val[2] != 0) return 4;
+  if (b.pos.val[2] != 230 || b.du.val[0] != a.du.val[0]) return 5;
+  Camera c;
+  c.init(3, 2);
+  c.lookAt(Vec3(0, 1, 0), 1.);
+  c = a;                              // other size: re-allocated
+  if (c.w != 7 || c.h != 5 || c.film() == nullptr) return 6;
+  c.pic[4][6].val[2] = 1;             // the last element of the block is addressable
+  a.clear();
+  if (a.pic[4][6].val[2] != 0) return 7;
+  std::puts("camera ok");
+  return 0;
+}
+''')
+    inc = os.path.join(ROOT, "raytrace3_b200", "include", "raytracer")
+    lib = os.path.dirname(abi.LIB_PATH)
+    exe = tmp_path / "cam"
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-fopenmp", "-I", inc, str(src), "-o", str(exe), "-L", lib, "-lsppm_b200",
+                        f"-Wl,-rpath,{lib}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "camera ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
