@@ -49,7 +49,7 @@ class RayTracer {
   // Photon k of round i is photon i*onetime + k of pass `pass_base` in the counter RNG.  While
   // HitPoint::update is the reference's -- a no-op for the hit points of a fresh eye pass (N = 0,
   // Raytracer.h:70, Q1) -- the rounds of PhotonMap are independent, so they are traced as one
-  // photon pass of cnt*onetime photons (cut into 2 Mi-photon batches over the library's lanes)
+  // photon pass of cnt*onetime photons (cut into batches of at most 8 Mi photons over the library's lanes)
   // instead of cnt launch sequences of onetime = 100 photons each: same photons, same newN, tao in
   // a different summation order.  PROGRESSIVE updates (or fuse_rounds = false) keep one pass per round.
   bool fuse_rounds = true;
