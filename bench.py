@@ -477,6 +477,28 @@ def main():
         e2e = float(t.item())
     e2e_value = e2e_onetime * n_light * args.e2e_rounds / (e2e * 1e-3)
     e2e_counters = ctx.counters()
+    # the same call in the reference's OWN loop shape (Raytracer.h:218, 384: cnt = 10000 rounds of onetime = 100
+    # photons per eye pass, i.e. an eye pass and a grid build per 1 M photons); one GPU only, reported beside e2e
+    ref_shape = None
+    if world == 1 and args.e2e_steps > 0 and update == "reference":
+        try:
+            rs_ms = []
+            rt.cnt, rt.onetime = 10000, 100
+            for i in range(E2E_WARM + 5):
+                ctx.synchronize()
+                t0 = time.perf_counter()
+                rt._scene_uploaded = None
+                rt.pass_base = 200 + i
+                rt.render()
+                t1 = time.perf_counter()
+                if i >= E2E_WARM:
+                    rs_ms.append((t1 - t0) * 1e3)
+            m = statistics.median(rs_ms)
+            ref_shape = {"value": 10000 * 100 * n_light / (m * 1e-3), "unit": "photons/s", "ms_per_render": m,
+                         "what": "RayTracer.render() with the reference's literals cnt=10000, onetime=100: scene upload, eye pass, "
+                                 "grid build, 1 M photons (the rounds fused into one pass), resolve, film read-back"}
+        except Exception as e:  # a side figure: never costs the line
+            ref_shape = {"error": str(e)[:200]}
 
     # ---- multi-GPU parity (world > 1): one small round sharded over the ranks + allreduce must leave every rank
     # with the same accumulators, equal to the same round traced by rank 0 alone
@@ -584,7 +606,9 @@ def main():
                 "what": f"RayTracer.render() of the host mirror (raytrace3_b200.api, twin of include/raytracer/Raytracer.h) with "
                         f"cnt={args.e2e_rounds}, onetime={e2e_onetime}: scene + textures from pinned host memory, eye pass, grid build, "
                         f"PhotonMap (rounds fused into one photon pass while the update is the reference's), resolve, film "
-                        f"read-back into pinned camera.pic (the reference runs cnt=10000 rounds per eye pass)"},
+                        f"read-back into pinned camera.pic (the reference runs cnt=10000 rounds of 100 photons per eye pass: "
+                        f"reference_loop_shape)",
+                "reference_loop_shape": ref_shape},
         "gpu_launches": int(cnt["launches"] - launches0),
         "clocks": clocks,
         "roofline": roofline,
