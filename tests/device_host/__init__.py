@@ -350,7 +350,7 @@ class DeviceHost:
         tao[order] = dtao.T
         return newN, tao, dict(zip(("n_occ", "n_slots", "n_units", "n_items", "kept"), info.tolist())), pairs.tolist()
 
-    def update_resolve(self, mode, alpha, N, newN, dN, r2, tao, dtao, pix, cnt, onetime, w, h, rounds=1):
+    def update_resolve(self, mode, alpha, N, newN, dN, r2, tao, dtao, pix, cnt, onetime, w, h, rounds=1, canonical="pixel"):
         """update_kernel x rounds, then hp_rank_kernel + hp_canon_kernel + resolve_kernel; tao / dtao [n, 3].  The
         canonical order is (pixel, index), the map's own order is the index.  In place on N, newN, r2; returns
         (tao [n, 3], film [h, w, 3])."""
@@ -358,7 +358,8 @@ class DeviceHost:
         t, dt = np.ascontiguousarray(tao.T), np.ascontiguousarray(dtao.T)
         row, col = np.ascontiguousarray(pix[:, 0], dtype=np.int32), np.ascontiguousarray(pix[:, 1], dtype=np.int32)
         film = np.zeros((h, w, 3))
-        raw_of_rank = np.argsort(row.astype(np.int64) * w + col, kind="stable").astype(np.uint32)
+        # canonical = "index": an imported map whose order separates a pixel's hit points (several runs per pixel)
+        raw_of_rank = (np.argsort(row.astype(np.int64) * w + col, kind="stable") if canonical == "pixel" else np.arange(n)).astype(np.uint32)
         raw_of_pos = np.arange(n, dtype=np.uint32)
         self.lib.dh_update_resolve(n, mode, alpha, rounds, _p(N), _p(newN), _p(dN), _p(r2), _p(t), _p(dt), _p(row), _p(col),
                                    cnt, onetime, w, _p(film), _p(raw_of_rank), _p(raw_of_pos))

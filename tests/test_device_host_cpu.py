@@ -911,6 +911,22 @@ def test_update_and_resolve_kernels(dh, oracle, mode):
     assert (N != 0).any() and film.sum() > 0
 
 
+def test_resolve_kernel_with_a_pixels_hit_points_apart_in_canonical_order(dh, oracle):
+    """An imported map numbers its hit points in the caller's order (sppm_import_hitpoints: okey = index), so a
+    pixel's hit points need not be neighbours in canonical order: resolve_kernel then adds one partial sum per run
+    of neighbours — the same film as the oracle's up to the order of those adds."""
+    rng = np.random.RandomState(32)
+    n, w, h = 3000, 20, 15                      # 10 hit points per pixel on average, scattered over the index range
+    N, newN, dN = np.zeros(n, np.int32), rng.randint(1, 9, n).astype(np.int32), np.zeros(n, np.int32)
+    r2, tao = rng.uniform(0.2, 2.0, n), rng.uniform(0, 10, size=(n, 3))
+    pix = np.stack([rng.randint(0, h, n), rng.randint(0, w, n)], axis=1).astype(np.int32)
+    _, film = dh.update_resolve(abi.SPPM_UPDATE_REFERENCE, 0.7, N, newN, dN, r2, tao.copy(), np.zeros((n, 3)), pix, 2, 500, w, h,
+                                rounds=0, canonical="index")
+    want = oracle.resolve(pix, r2, tao, 2, 500, w, h)
+    np.testing.assert_allclose(film, want, rtol=1e-13, atol=0)
+    assert film.sum() > 0
+
+
 def test_shared_statistics_kernels(dh, oracle):
     """shared_{init,load,accum,update,resolve}_kernel: three eye passes of the per-pixel statistics
     (N' = N + alpha M, R2' = R2 (N + alpha M)/(N + M), tau' = (tau + Phi) R2'/R2; Hachisuka & Jensen 2009)
